@@ -1,0 +1,234 @@
+/*
+ * maua_b200.h -- C ABI of libmaua_b200.so: the B200-native (sm_100a) VGG-19 neural-style inner loop
+ * of JCBrouwer/maua-style.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; these entry points are what a
+ * ctypes binding inside the reference's loss.py / models.py / optim.py would call (INTEGRATION.md shows
+ * the stub).  Each entry cites the reference code (relative to the reference repo root) it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative maua_status code and never throws;
+ *     maua_last_error() returns a thread-local human readable message for the last failure;
+ *   - all pointers are DEVICE pointers owned by the caller unless stated otherwise, fp32, 16-byte aligned;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *     the device unless stated otherwise;
+ *   - images at the API boundary are NCHW [B,3,H,W] like the reference (BGR, 0-255, mean-subtracted,
+ *     load.py:21-32); feature maps inside the library are NHWC with values rounded to TF32;
+ *   - there is no CPU fallback: on a non-sm_100 device every compute entry fails with MAUA_ERR_ARCH.
+ */
+#ifndef MAUA_B200_H
+#define MAUA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MAUA_API __attribute__((visibility("default")))
+#else
+#define MAUA_API
+#endif
+
+typedef void* maua_stream_t; /* cudaStream_t */
+
+typedef enum maua_status {
+    MAUA_STATUS_OK = 0,
+    MAUA_STATUS_BAD_ARG = -1,
+    MAUA_STATUS_CUDA = -2,
+    MAUA_STATUS_ARCH = -3,
+    MAUA_STATUS_OOM = -4,
+    MAUA_STATUS_STATE = -5
+} maua_status;
+
+/* implementation selector of the GEMM-shaped kernels: 0 = tcgen05/TMEM/TMA (product path),
+ * 1 = naive SIMT cross-check (tests / debugging only; never selected by the library itself). */
+#define MAUA_IMPL_TC 0
+#define MAUA_IMPL_REF 1
+
+MAUA_API int maua_abi_version(void);
+MAUA_API const char* maua_last_error(void);
+/* 0 if `device` is an sm_100 GPU usable by this library, MAUA_STATUS_ARCH otherwise. */
+MAUA_API int maua_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / weight preparation (once per model load; replaces nothing in the reference, which keeps
+ * NCHW tensors and OIHW weights for cuDNN -- models.py:351-363)
+ * ---------------------------------------------------------------------------------------------- */
+/* w_oihw [Cout][Cin][3][3] -> GEMM layout, TF32-rounded.
+ *   dgrad = 0: out[co][tap*Cin + ci]  = w[co][ci][ky][kx]      (forward, tap = ky*3+kx)
+ *   dgrad = 1: out[ci][tap*Cout + co] = w[co][ci][2-ky][2-kx]  (input-gradient: rotated + transposed) */
+MAUA_API int maua_prep_conv_weights(const float* w_oihw, float* out, int cout, int cin, int dgrad,
+                                    maua_stream_t stream);
+MAUA_API int maua_nchw_to_nhwc(const float* src, float* dst, int b, int c, int h, int w, int round_tf32,
+                               maua_stream_t stream);
+MAUA_API int maua_nhwc_to_nchw(const float* src, float* dst, int b, int c, int h, int w, maua_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VGG feature stack kernels -- models.py:116-132 build_sequential (Conv2d 3x3 pad 1 -> ReLU(inplace)
+ * -> MaxPool2d/AvgPool2d(2,2)) and their autograd backward (optim.py:213), weights frozen
+ * (models.py:443-445) so input-gradients only.
+ * ---------------------------------------------------------------------------------------------- */
+/* y = [relu](conv3x3(x) + bias); x NHWC [B,H,W,Cin] (Cin % 32 == 0), y NHWC [B,H,W,Cout] (Cout % 64 == 0),
+ * wg from maua_prep_conv_weights(dgrad=0).  Output rounded to TF32. */
+MAUA_API int maua_conv3x3_fwd(const float* x, const float* wg, const float* bias, float* y, int b, int h, int w,
+                              int cin, int cout, int relu, int impl, maua_stream_t stream);
+/* gx = (conv3x3_dgrad(gy) [+ aux_f @ aux_d^T + aux_bias] [+ cont_coef*(cont_f - cont_t)]) * (mask_src > 0)
+ *   gy NHWC [B,H,W,Cout]; wd from maua_prep_conv_weights(dgrad=1); gx NHWC [B,H,W,Cin].
+ *   mask_src (optional) is the post-ReLU activation that fed this conv (ReLU backward of the layer below).
+ *   aux_* (optional): StyleLoss backward folded in as extra GEMM k-steps -- aux_f NHWC [B,H,W,Cin] is the
+ *   tapped feature map, aux_d [Cin][Cin] the scaled symmetric (G - A) matrix, aux_bias [Cin] the covariance
+ *   mean correction (loss.py:87-89).  cont_* (optional): ContentLoss gradient (loss.py:53-59), cont_coef is
+ *   a device scalar.  gy may be NULL (wd too) when only the loss terms contribute (last tap layer). */
+MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int b, int h, int w, int cout, int cin,
+                                const float* mask_src, const float* aux_f, const float* aux_d,
+                                const float* aux_bias, const float* cont_f, const float* cont_t,
+                                const float* cont_coef, int round_tf32, int impl, maua_stream_t stream);
+/* First layer (Cin = 3): image NCHW [B,3,H,W] -> NHWC [B,H,W,Cout], bias + ReLU; w is plain OIHW fp32. */
+MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const float* bias, float* y, int b, int h,
+                                 int w, int cout, maua_stream_t stream);
+/* First layer dgrad + image-side tail: gimg NCHW [B,3,H,W] = dgrad(gy) + tv_coef * dTV/dimg
+ *   + temp_coef * w * (img*w - temp_target).  tv_coef / temp_coef are device scalars (NULL = term absent). */
+MAUA_API int maua_conv_first_dgrad(const float* gy, const float* w_oihw, float* gimg, int b, int h, int w, int cout,
+                                   const float* img, const float* tv_coef, const float* temp_target,
+                                   const float* temp_weights, const float* temp_coef, maua_stream_t stream);
+/* 2x2/2 pooling on NHWC, floor semantics; avg = 0 max (first maximum wins ties), 1 average. */
+MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream);
+/* gx = unpool(gy) * (x > 0) [+ addend * (x > 0)]; x is the post-ReLU pre-pool activation. */
+MAUA_API int maua_pool2x2_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w,
+                              int c, int avg, int round_tf32, maua_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss kernels -- loss.py
+ * ---------------------------------------------------------------------------------------------- */
+/* GramMatrix.forward (loss.py:67-91) / nelement: gram[c][d] = sum_p X[p][c] X[p][d] / (C*P) for one image,
+ * f NHWC [P][C] (P = H*W), optionally mean-centred (use_covariance).  Symmetric tensor-core SYRK,
+ * split-K over pixels.  mean_out [C] (may be NULL unless use_covariance).  workspace: maua_gram_workspace_bytes. */
+MAUA_API size_t maua_gram_workspace_bytes(int c);
+MAUA_API int maua_gram(const float* f, long p, int c, int use_covariance, float* gram, float* mean_out,
+                       void* workspace, int impl, maua_stream_t stream);
+/* StyleLoss in "loss" mode (loss.py:141-181): mse = mean((gram - target)^2); *loss_out = value_scale * mse;
+ * diff[c][d] = gram - target (kept for the backward). */
+MAUA_API int maua_style_loss_fwd(const float* gram, const float* target, int c, float value_scale, float* loss_out,
+                                 float* diff, void* workspace, maua_stream_t stream);
+/* Backward coefficient matrix: aux_d = (*coef) * 4/(C^3 P) * diff (TF32-rounded), aux_bias = -aux_d @ mean
+ * (covariance only, else NULL).  coef is a device scalar.  Feed to maua_conv3x3_dgrad(aux_*). */
+MAUA_API int maua_style_loss_bwd_prep(const float* diff, const float* mean, int c, long p, const float* coef,
+                                      float* aux_d, float* aux_bias, maua_stream_t stream);
+/* ContentLoss value (loss.py:53-59): *loss_out = value_scale * mean((x*weights? - target)^2).
+ * weights (optional) has `plane` elements broadcast over n/plane leading slices (NCHW temporal loss). */
+MAUA_API int maua_content_loss_fwd(const float* x, const float* weights, const float* target, long n, long plane,
+                                   float value_scale, float* loss_out, void* workspace, maua_stream_t stream);
+/* TVLoss value (loss.py:224-233) on an NCHW image. */
+MAUA_API int maua_tv_loss_fwd(const float* img, int planes, int h, int w, float strength, float* loss_out,
+                              void* workspace, maua_stream_t stream);
+MAUA_API size_t maua_reduce_workspace_bytes(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer kernels -- optim.py:180-196 (torch.optim.Adam / torch.optim.LBFGS on the pastiche pixels)
+ * ---------------------------------------------------------------------------------------------- */
+MAUA_API int maua_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
+                            float beta1, float beta2, float eps, int step, maua_stream_t stream);
+
+typedef struct maua_lbfgs maua_lbfgs_t;
+/* L-BFGS state for one n-element parameter vector (torch.optim.LBFGS semantics without line search:
+ * history ring of `history` (s, y) pairs, lr, first-step t = min(1, 1/|g|_1) * lr, ys > 1e-10 update gate,
+ * H_diag = ys / y.y, gtd > -tolerance_change halts).  Owns 2*history + 4 vectors of n floats. */
+MAUA_API int maua_lbfgs_create(long n, int history, float lr, float tolerance_change, maua_lbfgs_t** out);
+MAUA_API void maua_lbfgs_destroy(maua_lbfgs_t* s);
+/* One L-BFGS iteration given the gradient at the current parameters: updates history, computes the two-loop
+ * direction and applies param += t * d.  Fully asynchronous (all scalars stay on the device). */
+MAUA_API int maua_lbfgs_step(maua_lbfgs_t* s, float* param, const float* grad, maua_stream_t stream);
+/* Debug / test read-back (synchronises): n_iter, history length, halted flag. */
+MAUA_API int maua_lbfgs_query(maua_lbfgs_t* s, int* n_iter, int* hist_len, int* halted, maua_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Plan: the whole feval of optim.py:201-238 (net(pastiche) -> sum of module losses -> backward to the
+ * image) for one network description, as a fixed launch sequence with library-owned workspaces.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct maua_plan maua_plan_t;
+
+#define MAUA_MAX_LAYERS 32
+#define MAUA_MAX_TAPS 16
+
+typedef enum maua_tap_kind { MAUA_TAP_STYLE = 0, MAUA_TAP_CONTENT = 1 } maua_tap_kind;
+typedef enum maua_tap_mode { MAUA_MODE_NONE = 0, MAUA_MODE_CAPTURE = 1, MAUA_MODE_LOSS = 2 } maua_tap_mode;
+
+/* Network description: models.py:135-139 channel_list entry truncated after the last tapped ReLU
+ * (models.py:382).  channels[i] > 0: conv3x3(channels[i]) + ReLU;  channels[i] == 0: 2x2 pool. */
+typedef struct maua_net_desc {
+    int n_entries;
+    int channels[MAUA_MAX_LAYERS];
+    int avg_pool;                       /* models.py:119-122 */
+    const float* weights[MAUA_MAX_LAYERS]; /* per conv entry: OIHW fp32 device pointer (copied + transformed) */
+    const float* biases[MAUA_MAX_LAYERS];
+    int n_taps;
+    int tap_relu_index[MAUA_MAX_TAPS];  /* 0-based index of the ReLU (= conv count - 1) the loss module follows */
+    int tap_kind[MAUA_MAX_TAPS];        /* maua_tap_kind; taps must be ordered by relu index (style before content
+                                           at the same index, as models.py:403-431 inserts them) */
+} maua_net_desc;
+
+/* Per-call, per-tap state: targets are caller-owned tensors so the Python loss modules can expose them
+ * as `.target` (loss.py:40,124-126). */
+typedef struct maua_tap_io {
+    int mode;                 /* maua_tap_mode */
+    int use_covariance;       /* style only */
+    float value_scale;        /* style: strength*(1+vsf) ; content: strength   (B = 1) */
+    float capture_weight;     /* style capture: target (+)= capture_weight * gram   (blend_weight, loss.py:148-151) */
+    int capture_accumulate;   /* 0: overwrite target, 1: add */
+    float* target;            /* style: [C][C]; content: NHWC [H][W][C] at the tap resolution */
+    long target_elems;        /* content: elements of `target` (0 = not captured yet); shape mismatch => skipped */
+} maua_tap_io;
+
+typedef struct maua_image_io {
+    /* TVLoss (module index 0 when tv_weight > 0, models.py:369-373) */
+    int tv_mode;              /* maua_tap_mode: NONE or LOSS (value is assigned on every forward, loss.py:232) */
+    float tv_strength;
+    /* temporal ContentLoss on the image (models.py:375-379, loss.py:46-54) */
+    int temporal_mode;        /* NONE / CAPTURE / LOSS */
+    float temporal_strength;
+    float* temporal_target;   /* NCHW [3][H][W] */
+    long temporal_target_elems;
+    const float* temporal_weights; /* [H][W] or NULL */
+} maua_image_io;
+
+MAUA_API int maua_plan_create(int device, const maua_net_desc* desc, maua_plan_t** out);
+MAUA_API void maua_plan_destroy(maua_plan_t* plan);
+/* Bytes of device memory the plan currently owns (weights + workspaces), for capacity planning. */
+MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* plan);
+
+/* net(image): forward to the last tap.  image NCHW [1,3,H,W].  For taps in CAPTURE mode updates `target`;
+ * for taps in LOSS mode writes the module loss value into losses_out[tap] (device, n_taps + 2 floats:
+ * [0..n_taps) taps in order, [n_taps] TV, [n_taps+1] temporal).  Entries of modules not in LOSS mode are 0.
+ * keep_for_backward != 0 retains activations so maua_plan_backward can follow. */
+MAUA_API int maua_plan_forward(maua_plan_t* plan, const float* image, int h, int w, const maua_tap_io* taps,
+                               const maua_image_io* image_io, float* losses_out, int keep_for_backward,
+                               maua_stream_t stream);
+/* Backward of the last forward: grad_coefs (device, n_taps + 2 floats) are the per-module gradient weights
+ * (upstream dL/dloss_i already combined with strength / ScaleGradients semantics by
+ * maua_loss_grad_coefs); writes d(sum)/d(image) NCHW into grad_image. */
+MAUA_API int maua_plan_backward(maua_plan_t* plan, const float* grad_coefs, float* grad_image,
+                                maua_stream_t stream);
+/* ScaleGradients (loss.py:10-20) + strength bookkeeping on the device: for module i with upstream gradient
+ * up[i], coef[i] = sum over its loss terms of  normalize ? sg(up*term_scale)*strength^2 : up*term_scale,
+ * sg(x) = x/(|x|+1e-8).  term scales: style {strength, vsf*strength (if vsf>0)}, content {strength},
+ * TV {strength, never normalised}. */
+MAUA_API int maua_loss_grad_coefs(const float* upstream, float* coefs, int n, const float* strength,
+                                  const float* vsf, const int* normalize, const int* kind,
+                                  maua_stream_t stream);
+
+/* Gram matrix of tap `tap` from the last forward (normalised, [C][C]); valid until the next forward. */
+MAUA_API int maua_plan_tap_gram(maua_plan_t* plan, int tap, const float** gram, int* c);
+/* Feature map of tap `tap` from the last forward (NHWC [H_l][W_l][C]). */
+MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, const float** feat, int* h, int* w, int* c);
+/* Switch the GEMM-shaped kernels of this plan between MAUA_IMPL_TC and MAUA_IMPL_REF (tests only). */
+MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
+/* Number of kernel launches issued by the last forward / backward (for bench.py's gpu_launches). */
+MAUA_API int maua_plan_last_launches(const maua_plan_t* plan, int* forward, int* backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAUA_B200_H */

@@ -1,0 +1,210 @@
+// extern "C" surface of libmaua_b200.so for the per-kernel entry points (include/maua_b200.h).
+// The plan-level entry points live in plan.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "conv_tc.cuh"
+#include "gram.cuh"
+#include "maua_b200.h"
+#include "pointwise.cuh"
+
+namespace maua {
+
+static thread_local char g_last_error[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_device_arch(int device) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        set_last_error("cudaGetDeviceProperties(%d) failed: %s (no CUDA device? this library has no CPU fallback)",
+                       device, cudaGetErrorString(e));
+        return MAUA_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        set_last_error("device %d is sm_%d%d; libmaua_b200 is built for sm_100a (B200) only", device, prop.major,
+                       prop.minor);
+        return MAUA_ERR_ARCH;
+    }
+    return MAUA_OK;
+}
+
+static int current_device_ok() {
+    static thread_local int checked_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_last_error("cudaGetDevice failed: %s (no CUDA device? this library has no CPU fallback)",
+                       cudaGetErrorString(e));
+        return MAUA_ERR_CUDA;
+    }
+    if (dev == checked_dev) return MAUA_OK;
+    int rc = check_device_arch(dev);
+    if (rc == MAUA_OK) checked_dev = dev;
+    return rc;
+}
+
+ReduceScratch scratch_from_workspace(void* ws) {
+    ReduceScratch rs;
+    rs.counter = reinterpret_cast<unsigned int*>(ws);
+    rs.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+    rs.max_blocks = 148 * 8;
+    return rs;
+}
+
+}  // namespace maua
+
+using namespace maua;
+
+#define MAUA_ENTRY_GUARD()                      \
+    do {                                        \
+        int _rc = current_device_ok();          \
+        if (_rc != MAUA_OK) return _rc;         \
+    } while (0)
+
+extern "C" {
+
+MAUA_API int maua_abi_version(void) { return 1; }
+MAUA_API const char* maua_last_error(void) { return g_last_error; }
+MAUA_API int maua_device_check(int device) { return check_device_arch(device); }
+
+MAUA_API int maua_prep_conv_weights(const float* w, float* out, int cout, int cin, int dgrad, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(w && out && cout > 0 && cin > 0, "maua_prep_conv_weights: bad arguments");
+    return prep_weights_launch(w, out, cout, cin, dgrad, 1, (cudaStream_t)stream);
+}
+MAUA_API int maua_nchw_to_nhwc(const float* src, float* dst, int b, int c, int h, int w, int round_tf32,
+                               maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(src && dst && b > 0 && c > 0 && h > 0 && w > 0, "maua_nchw_to_nhwc: bad arguments");
+    return nchw_to_nhwc_launch(src, dst, b, c, h, w, round_tf32, (cudaStream_t)stream);
+}
+MAUA_API int maua_nhwc_to_nchw(const float* src, float* dst, int b, int c, int h, int w, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(src && dst && b > 0 && c > 0 && h > 0 && w > 0, "maua_nhwc_to_nchw: bad arguments");
+    return nhwc_to_nchw_launch(src, dst, b, c, h, w, (cudaStream_t)stream);
+}
+
+MAUA_API int maua_conv3x3_fwd(const float* x, const float* wg, const float* bias, float* y, int b, int h, int w,
+                              int cin, int cout, int relu, int impl, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && wg && y, "maua_conv3x3_fwd: null pointer");
+    ConvArgs a;
+    a.B = b; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ntaps = 9;
+    a.in = x; a.wg = wg;
+    a.ep.out = y; a.ep.bias = bias; a.ep.relu = relu; a.ep.round = 1;
+    return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
+}
+
+MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int b, int h, int w, int cout, int cin,
+                                const float* mask_src, const float* aux_f, const float* aux_d,
+                                const float* aux_bias, const float* cont_f, const float* cont_t,
+                                const float* cont_coef, int round_tf32, int impl, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(gx, "maua_conv3x3_dgrad: null output");
+    MAUA_REQUIRE((gy != nullptr) == (wd != nullptr), "maua_conv3x3_dgrad: gy and wd must both be given or both NULL");
+    MAUA_REQUIRE((aux_f != nullptr) == (aux_d != nullptr), "maua_conv3x3_dgrad: aux_f and aux_d go together");
+    MAUA_REQUIRE(!cont_f || (cont_t && cont_coef), "maua_conv3x3_dgrad: cont_f needs cont_t and cont_coef");
+    ConvArgs a;
+    a.B = b; a.H = h; a.W = w;
+    a.Cin = cout;  // GEMM K per tap = channels of the incoming gradient
+    a.Cout = cin;  // GEMM N = channels of the produced gradient
+    a.ntaps = gy ? 9 : 0;
+    a.in = gy; a.wg = wd;
+    if (aux_f) { a.K2 = cin; a.in2 = aux_f; a.w2 = aux_d; }
+    a.ep.out = gx; a.ep.bias = aux_bias; a.ep.mask_src = mask_src;
+    a.ep.cont_f = cont_f; a.ep.cont_t = cont_t; a.ep.cont_coef = cont_coef;
+    a.ep.relu = 0; a.ep.round = round_tf32;
+    if (!gy && !aux_f) {
+        MAUA_REQUIRE(false, "maua_conv3x3_dgrad: nothing to compute (no gy and no aux term)");
+    }
+    return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
+}
+
+MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const float* bias, float* y, int b, int h,
+                                 int w, int cout, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(img && w_oihw && y, "maua_conv_first_fwd: null pointer");
+    return conv_first_fwd_launch(img, w_oihw, bias, y, b, h, w, cout, 1, (cudaStream_t)stream);
+}
+MAUA_API int maua_conv_first_dgrad(const float* gy, const float* w_oihw, float* gimg, int b, int h, int w, int cout,
+                                   const float* img, const float* tv_coef, const float* temp_target,
+                                   const float* temp_weights, const float* temp_coef, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(gy && w_oihw && gimg, "maua_conv_first_dgrad: null pointer");
+    MAUA_REQUIRE(!(tv_coef || temp_coef) || img, "maua_conv_first_dgrad: TV / temporal terms need the image");
+    ImageTail t;
+    t.img = img; t.tv_coef = tv_coef; t.temp_target = temp_target; t.temp_weights = temp_weights;
+    t.temp_coef = temp_target ? temp_coef : nullptr;
+    return conv_first_dgrad_launch(gy, w_oihw, gimg, b, h, w, cout, t, (cudaStream_t)stream);
+}
+
+MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && y, "maua_pool2x2_fwd: null pointer");
+    return pool_fwd_launch(x, y, b, h, w, c, avg, (cudaStream_t)stream);
+}
+MAUA_API int maua_pool2x2_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w,
+                              int c, int avg, int round_tf32, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && gy && gx, "maua_pool2x2_bwd: null pointer");
+    return pool_bwd_launch(x, gy, addend, gx, b, h, w, c, avg, round_tf32, (cudaStream_t)stream);
+}
+
+MAUA_API size_t maua_reduce_workspace_bytes(void) { return 256 + sizeof(double) * 148 * 8 * 4; }
+
+MAUA_API size_t maua_gram_workspace_bytes(int c) { return gram_workspace_bytes(c); }
+
+MAUA_API int maua_gram(const float* f, long p, int c, int use_covariance, float* gram, float* mean_out,
+                       void* workspace, int impl, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(f && gram && workspace, "maua_gram: null pointer");
+    MAUA_REQUIRE(!use_covariance || mean_out, "maua_gram: covariance needs mean_out");
+    return gram_launch(f, p, c, use_covariance, gram, mean_out, workspace, impl, (cudaStream_t)stream);
+}
+MAUA_API int maua_style_loss_fwd(const float* gram, const float* target, int c, float value_scale, float* loss_out,
+                                 float* diff, void* workspace, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(gram && target && loss_out && diff && workspace, "maua_style_loss_fwd: null pointer");
+    return style_loss_fwd_launch(gram, target, c, value_scale, loss_out, diff, scratch_from_workspace(workspace),
+                                 (cudaStream_t)stream);
+}
+MAUA_API int maua_style_loss_bwd_prep(const float* diff, const float* mean, int c, long p, const float* coef,
+                                      float* aux_d, float* aux_bias, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(diff && coef && aux_d, "maua_style_loss_bwd_prep: null pointer");
+    MAUA_REQUIRE((mean != nullptr) == (aux_bias != nullptr), "maua_style_loss_bwd_prep: mean and aux_bias go together");
+    return style_loss_bwd_prep_launch(diff, mean, c, p, coef, aux_d, aux_bias, (cudaStream_t)stream);
+}
+MAUA_API int maua_content_loss_fwd(const float* x, const float* weights, const float* target, long n, long plane,
+                                   float value_scale, float* loss_out, void* workspace, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && target && loss_out && workspace && n > 0, "maua_content_loss_fwd: bad arguments");
+    const float scale = value_scale / (float)n;
+    ReduceScratch rs = scratch_from_workspace(workspace);
+    if (!weights && n % 4 == 0) return mse_value_launch(x, target, n, scale, loss_out, rs, (cudaStream_t)stream);
+    return wmse_value_launch(x, weights, target, n, plane > 0 ? plane : n, scale, loss_out, rs, (cudaStream_t)stream);
+}
+MAUA_API int maua_tv_loss_fwd(const float* img, int planes, int h, int w, float strength, float* loss_out,
+                              void* workspace, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(img && loss_out && workspace, "maua_tv_loss_fwd: null pointer");
+    return tv_value_launch(img, planes, h, w, strength, loss_out, scratch_from_workspace(workspace),
+                           (cudaStream_t)stream);
+}
+
+MAUA_API int maua_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
+                            float beta1, float beta2, float eps, int step, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "maua_adam_step: bad arguments");
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+}
+
+}  // extern "C"

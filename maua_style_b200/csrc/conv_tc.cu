@@ -1,0 +1,408 @@
+// conv3x3 (pad 1, stride 1) as a TMA-fed tcgen05 / TMEM implicit GEMM for sm_100a.
+//
+// Replaces cuDNN fprop / bwd-data behind reference models.py:129 (nn.Conv2d in build_sequential)
+// and the autograd dgrad of it (optim.py:213 total_loss.backward()).  Weights are frozen
+// (models.py:443-445) so only input-gradients are ever needed: the backward pass is this same
+// kernel run on 180-degree-rotated, channel-transposed weights.
+//
+// GEMM view (NHWC activations):   D[pixel][n] = sum_{tap, c} A_tap[pixel][c] * Wg[n][tap*Cin + c]
+//   M = pixels.  One CTA owns MT sub-tiles of 128 pixels (16 wide x 8 high), stacked along h.
+//   N = output channels, BN in {64,128,256} per CTA.
+//   K = 9 taps x Cin, walked in k-steps of 32 channels (= one 128-byte swizzle span of fp32).
+// A operand: one 4-D TMA box {32 c, 16 w, 8 h, 1 b} per (tap, channel chunk); the tap shift is
+//   applied to the box origin and out-of-bounds pixels are zero-filled by TMA, which is exactly
+//   the conv zero padding and also handles ragged right/bottom tiles for arbitrary H x W.
+// B operand: 2-D TMA box {32 k, BN n} of the K-major GEMM weights.
+// Both land in the canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms, SBO = 1024 B).
+// Accumulators: MT x [128 lanes x BN fp32 columns] in TMEM.
+// An optional second ("aux") GEMM term sum_{c2} A2[pixel][c2] * W2[n][c2] accumulates into the
+// same TMEM tile as extra k-steps: this is the StyleLoss backward 4(G-A)F/(C^3 N) (loss.py:141-157)
+// folded into the dgrad of the following layer.
+//
+// Warp roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused epilogue -> global).
+#include "conv_tc.cuh"
+
+#include <mutex>
+
+namespace maua {
+
+namespace {
+
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;   // one 128-pixel sub-tile = 16 x 8
+constexpr int KCHUNK = 32;  // fp32 channels per k-step (128 bytes)
+constexpr int A_BYTES = 128 * 128;
+
+struct ConvKParams {
+    int B, H, W, Cin, Cout, ntaps, K2;
+    int tiles_w, tiles_h;
+    ConvEpilogue ep;
+};
+
+template <int BN, int MT>
+struct ConvCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+    static constexpr int NSTAGES_RAW = (200 * 1024) / STAGE_BYTES;
+    static constexpr int NSTAGES = NSTAGES_RAW > 6 ? 6 : NSTAGES_RAW;
+    static constexpr int TMEM_COLS = MT * BN;  // 64..512, power of two
+    static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const ConvKParams p) {
+    using Cfg = ConvCfg<BN, MT>;
+    constexpr int NST = Cfg::NSTAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NST;
+    uint64_t* tmem_full_bar = empty_bar + NST;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int b = t / p.tiles_h;
+    const int w0 = tw * TILE_W;
+    const int h0 = th * (TILE_H * MT);
+    const int n0 = blockIdx.y * BN;
+
+    const int cpt = p.Cin / KCHUNK;      // channel chunks per tap
+    const int nk1 = p.ntaps * cpt;       // main k-steps
+    const int nk2 = p.K2 / KCHUNK;       // aux k-steps
+    const int nk = nk1 + nk2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (nk2 > 0) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        for (int ks = 0; ks < nk; ++ks) {
+            const int stage = ks % NST;
+            const uint32_t phase = (ks / NST) & 1;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sB = sA + MT * A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (ks < nk1) {
+                const int tap = ks / cpt;
+                const int c0 = (ks - tap * cpt) * KCHUNK;
+                int dy = 0, dx = 0;
+                if (p.ntaps == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap % 3 - 1;
+                }
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    tma_load_4d(sA + m * A_BYTES, &tmA, &full_bar[stage], c0, w0 + dx, h0 + m * TILE_H + dy, b);
+                tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.Cin + c0, n0);
+            } else {
+                const int c0 = (ks - nk1) * KCHUNK;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    tma_load_4d(sA + m * A_BYTES, &tmA2, &full_bar[stage], c0, w0, h0 + m * TILE_H, b);
+                tma_load_2d(sB, &tmB2, &full_bar[stage], c0, n0);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+        for (int ks = 0; ks < nk; ++ks) {
+            const int stage = ks % NST;
+            const uint32_t phase = (ks / NST) & 1;
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sB = sA + MT * A_BYTES;
+            const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const uint64_t adesc = make_smem_desc_sw128(sA + m * A_BYTES, 16, 1024);
+#pragma unroll
+                for (int kk = 0; kk < KCHUNK / 8; ++kk) {
+                    // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
+                    umma_tf32(tmem_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc,
+                              (ks > 0 || kk > 0) ? 1u : 0u);
+                }
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(tmem_full_bar);  // accumulator complete
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int hl = row / TILE_W;
+        const int wl = row % TILE_W;
+        const ConvEpilogue& ep = p.ep;
+        const float ccoef = ep.cont_f ? *ep.cont_coef : 0.f;
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+            const int h = h0 + m * TILE_H + hl;
+            const int w = w0 + wl;
+            const bool valid = (h < p.H) && (w < p.W);
+            const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.Cout + n0;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                float v[16];
+                tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * BN + c, v);
+                if (valid) {
+                    if (ep.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n0 + c + i);
+                            v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+                        }
+                    }
+                    if (ep.cont_f) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 f = *reinterpret_cast<const float4*>(ep.cont_f + off + c + i);
+                            const float4 tg = *reinterpret_cast<const float4*>(ep.cont_t + off + c + i);
+                            v[i] += ccoef * (f.x - tg.x); v[i + 1] += ccoef * (f.y - tg.y);
+                            v[i + 2] += ccoef * (f.z - tg.z); v[i + 3] += ccoef * (f.w - tg.w);
+                        }
+                    }
+                    if (ep.addend) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 a = *reinterpret_cast<const float4*>(ep.addend + off + c + i);
+                            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+                        }
+                    }
+                    if (ep.relu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (ep.mask_src) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 mk = *reinterpret_cast<const float4*>(ep.mask_src + off + c + i);
+                            v[i] = mk.x > 0.f ? v[i] : 0.f; v[i + 1] = mk.y > 0.f ? v[i + 1] : 0.f;
+                            v[i + 2] = mk.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = mk.w > 0.f ? v[i + 3] : 0.f;
+                        }
+                    }
+                    if (ep.round) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(ep.out + off + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+}  // namespace
+
+// NHWC activation tensor [B][H][W][C] -> 4-D map, box {32, box_w, box_h, 1}, 128B swizzle.
+int make_tmap_nhwc(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+        return MAUA_ERR_CUDA;
+    }
+    MAUA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "activation pointer must be 16-byte aligned");
+    MAUA_REQUIRE(C % 4 == 0, "NHWC channel count %d must be a multiple of 4", C);
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {KCHUNK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d) failed: CUresult %d", B, H, W, C, (int)r);
+        return MAUA_ERR_CUDA;
+    }
+    return MAUA_OK;
+}
+
+// Row-major matrix [rows][cols] (cols contiguous) -> 2-D map, box {32, box_rows}, 128B swizzle.
+int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+        return MAUA_ERR_CUDA;
+    }
+    MAUA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "matrix pointer must be 16-byte aligned");
+    MAUA_REQUIRE(cols % 4 == 0, "matrix row length %ld must be a multiple of 4", cols);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {KCHUNK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(2D %ldx%ld) failed: CUresult %d", rows, cols, (int)r);
+        return MAUA_ERR_CUDA;
+    }
+    return MAUA_OK;
+}
+
+namespace {
+
+template <int BN, int MT>
+int launch_cfg(const ConvArgs& a, cudaStream_t st) {
+    using Cfg = ConvCfg<BN, MT>;
+    static unsigned long long attr_done = 0;  // per (BN, MT) instantiation; benign race (idempotent call)
+    MAUA_CUDA_CHECK(ensure_dynamic_smem(conv_tc_kernel<BN, MT>, Cfg::SMEM_BYTES, &attr_done));
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    int rc;
+    const bool has_main = a.ntaps > 0;
+    const bool has_aux = a.K2 > 0;
+    if (has_main) {
+        if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, TILE_H))) return rc;
+        if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, BN))) return rc;
+    }
+    if (has_aux) {
+        if ((rc = make_tmap_nhwc(&tmA2, a.in2, a.B, a.H, a.W, a.K2, TILE_W, TILE_H))) return rc;
+        if ((rc = make_tmap_2d(&tmB2, a.w2, a.Cout, a.K2, BN))) return rc;
+    }
+    if (!has_main) { tmA = tmA2; tmB = tmB2; }
+    if (!has_aux) { tmA2 = tmA; tmB2 = tmB; }
+
+    ConvKParams p;
+    p.B = a.B; p.H = a.H; p.W = a.W;
+    p.Cin = has_main ? a.Cin : KCHUNK;
+    p.Cout = a.Cout;
+    p.ntaps = has_main ? a.ntaps : 0;
+    p.K2 = a.K2;
+    p.tiles_w = (a.W + TILE_W - 1) / TILE_W;
+    p.tiles_h = (a.H + TILE_H * MT - 1) / (TILE_H * MT);
+    p.ep = a.ep;
+    dim3 grid(p.tiles_w * p.tiles_h * a.B, a.Cout / BN);
+    conv_tc_kernel<BN, MT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+}  // namespace
+
+int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
+    MAUA_REQUIRE(a.ntaps == 9 || a.ntaps == 1 || a.ntaps == 0, "ntaps must be 9, 1 or 0 (got %d)", a.ntaps);
+    MAUA_REQUIRE(a.ntaps > 0 || a.K2 > 0, "conv has neither a main nor an aux term");
+    MAUA_REQUIRE(a.ntaps == 0 || (a.Cin % KCHUNK == 0 && a.Cin >= KCHUNK),
+                 "tcgen05 conv needs Cin %% 32 == 0 (got %d); the 3-channel image layer uses conv_first_*", a.Cin);
+    MAUA_REQUIRE(a.K2 % KCHUNK == 0, "aux K2 must be a multiple of 32 (got %d)", a.K2);
+    MAUA_REQUIRE(a.Cout % 64 == 0, "Cout must be a multiple of 64 (got %d)", a.Cout);
+    MAUA_REQUIRE(a.B >= 1 && a.H >= 1 && a.W >= 1, "bad extent B=%d H=%d W=%d", a.B, a.H, a.W);
+    MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
+
+    const int bn = (a.Cout % 256 == 0) ? 256 : (a.Cout % 128 == 0) ? 128 : 64;
+    // MT=2 (256 pixels per CTA) halves weight traffic per FLOP; use it when it still fills the GPU.
+    const long tiles2 = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + 2 * TILE_H - 1) / (2 * TILE_H)) * a.B *
+                        (a.Cout / bn);
+    const int mt = tiles2 >= 148 ? 2 : 1;
+    if (bn == 256) return mt == 2 ? launch_cfg<256, 2>(a, st) : launch_cfg<256, 1>(a, st);
+    if (bn == 128) return mt == 2 ? launch_cfg<128, 2>(a, st) : launch_cfg<128, 1>(a, st);
+    return mt == 2 ? launch_cfg<64, 2>(a, st) : launch_cfg<64, 1>(a, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Naive SIMT cross-check of exactly the same contract (debug / tests only, any channel counts).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void conv_ref_kernel(ConvArgs a) {
+    const long total = (long)a.B * a.H * a.W * a.Cout;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int n = idx % a.Cout;
+        long pix = idx / a.Cout;
+        const int w = pix % a.W;
+        const int h = (pix / a.W) % a.H;
+        const int b = pix / ((long)a.W * a.H);
+        float acc = 0.f;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+            const int dy = a.ntaps == 9 ? tap / 3 - 1 : 0, dx = a.ntaps == 9 ? tap % 3 - 1 : 0;
+            const int hh = h + dy, ww = w + dx;
+            if (hh < 0 || hh >= a.H || ww < 0 || ww >= a.W) continue;
+            const float* ip = a.in + (((long)b * a.H + hh) * a.W + ww) * a.Cin;
+            const float* wp = a.wg + (long)n * a.ntaps * a.Cin + (long)tap * a.Cin;
+            for (int c = 0; c < a.Cin; ++c) acc = fmaf(ip[c], wp[c], acc);
+        }
+        for (int c = 0; c < a.K2; ++c) acc = fmaf(a.in2[pix * a.K2 + c], a.w2[(long)n * a.K2 + c], acc);
+        const ConvEpilogue& ep = a.ep;
+        float v = acc;
+        if (ep.bias) v += ep.bias[n];
+        if (ep.cont_f) v += *ep.cont_coef * (ep.cont_f[idx] - ep.cont_t[idx]);
+        if (ep.addend) v += ep.addend[idx];
+        if (ep.relu) v = fmaxf(v, 0.f);
+        if (ep.mask_src) v = ep.mask_src[idx] > 0.f ? v : 0.f;
+        if (ep.round) v = round_tf32(v);
+        ep.out[idx] = v;
+    }
+}
+}  // namespace
+
+int conv_ref_launch(const ConvArgs& a, cudaStream_t st) {
+    MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
+    const long total = (long)a.B * a.H * a.W * a.Cout;
+    const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    conv_ref_kernel<<<blocks, 256, 0, st>>>(a);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+}  // namespace maua

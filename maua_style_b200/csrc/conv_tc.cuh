@@ -1,0 +1,61 @@
+// Host-visible interface of the tcgen05 implicit-GEMM convolution (conv_tc.cu) and of the
+// direct edge kernels (conv_edge.cu).  Internal to libmaua_b200.so; the C ABI is in
+// include/maua_b200.h.
+#pragma once
+#include "common.cuh"
+
+namespace maua {
+
+// Fused epilogue applied to every accumulator element v = acc[pixel][n], in this order:
+//   v += bias[n]                         (forward bias; covariance rank-1 correction in backward)
+//   v += *cont_coef * (cont_f - cont_t)  (ContentLoss gradient, loss.py:53-59)
+//   v += addend                          (gradient arriving from another branch, e.g. un-pooled)
+//   v  = max(v, 0)                       (ReLU, models.py:130)                       if relu
+//   v  = mask_src > 0 ? v : 0            (ReLU backward through the *previous* layer) if mask_src
+//   v  = round_tf32(v)                   (operand rounding for the consuming MMA)     if round
+struct ConvEpilogue {
+    float* out = nullptr;             // NHWC [B][H][W][Cout]
+    const float* bias = nullptr;      // [Cout]
+    const float* mask_src = nullptr;  // NHWC like out
+    const float* cont_f = nullptr;    // NHWC like out
+    const float* cont_t = nullptr;    // NHWC like out
+    const float* cont_coef = nullptr; // device scalar
+    const float* addend = nullptr;    // NHWC like out
+    int relu = 0;
+    int round = 1;
+};
+
+// out[b][h][w][n] = epilogue( sum_{tap,c} in[b][h+dy][w+dx][c] * wg[n][tap*Cin + c]
+//                           + sum_{c2}    in2[b][h][w][c2]     * w2[n][c2] )
+// ntaps is 9 (3x3, pad 1), 1 (pointwise) or 0 (main term absent, aux GEMM only).
+struct ConvArgs {
+    int B = 1, H = 0, W = 0;
+    int Cin = 0, Cout = 0, ntaps = 9;
+    const float* in = nullptr;   // NHWC [B][H][W][Cin], values tf32-representable
+    const float* wg = nullptr;   // [Cout][ntaps*Cin], tf32-rounded
+    int K2 = 0;
+    const float* in2 = nullptr;  // NHWC [B][H][W][K2]
+    const float* w2 = nullptr;   // [Cout][K2]
+    ConvEpilogue ep;
+};
+
+int conv_tc_launch(const ConvArgs& a, cudaStream_t st);   // tcgen05 / TMEM / TMA path
+int conv_ref_launch(const ConvArgs& a, cudaStream_t st);  // naive SIMT cross-check (debug only)
+
+// conv1_1 forward: NCHW 3-channel image -> NHWC Cout, bias + ReLU, fp32 FFMA (K = 27).
+int conv_first_fwd_launch(const float* img, const float* w /*[Cout][3][3][3]*/, const float* bias, float* out,
+                          int B, int H, int W, int Cout, int round, cudaStream_t st);
+
+// conv1_1 dgrad (+ fused image-side tail): NHWC Cout gradient -> NCHW 3-channel image gradient,
+// plus TV gradient and temporal ContentLoss gradient.
+struct ImageTail {
+    const float* img = nullptr;        // NCHW image (needed for TV / temporal)
+    const float* tv_coef = nullptr;    // device scalar: upstream * strength (TVLoss, loss.py:224-233)
+    const float* temp_target = nullptr;// NCHW warped previous frame
+    const float* temp_weights = nullptr;// [H][W] reliability map or null
+    const float* temp_coef = nullptr;  // device scalar: coef * 2 / numel
+};
+int conv_first_dgrad_launch(const float* gout, const float* w, float* gimg, int B, int H, int W, int Cout,
+                            const ImageTail& tail, cudaStream_t st);
+
+}  // namespace maua

@@ -1,0 +1,332 @@
+// Gram / covariance matrix as a symmetric tensor-core SYRK (tcgen05, TF32 operands, FP32 accumulate),
+// plus the small StyleLoss reductions around it.
+//
+// Replaces reference loss.py:67-91 (GramMatrix.forward: torch.mm(x_flat, x_flat.t()) on the
+// [C, H*W] view) and loss.py:141-181 (StyleLoss static + dynamic terms; for B = 1 the dynamic Gram is
+// identical to the static one, so ONE SYRK serves both -- SURVEY.md section 8a "net effect of R4-R6").
+//
+// Layout: features are NHWC, i.e. the flattened matrix is F[P][C] with channels contiguous, and
+//   G[c][d] = sum_p F[p][c] F[p][d]  is a GEMM whose M, N are channels and whose K is pixels.
+// Both operands are therefore "MN-major" for the tensor core (the M/N index is the contiguous one).
+// A TMA box {32 channels, 64 pixels} lands as 64 rows of 128 bytes with the 128B swizzle, which is exactly
+// the canonical MN-major SWIZZLE_128B UMMA layout: 8 K-rows x 128 B atoms (SBO = 1024 B between 8-pixel
+// groups), 32-channel groups LBO = 8192 B apart.  Only upper-triangular 128x128 tiles are computed; for
+// diagonal tiles the B operand aliases the A tile in shared memory (half the smem traffic).
+// K (pixels) is split across CTAs so that all 148 SMs stream F once: the C = 64 / 128 layers are
+// HBM-bound (intensity C/2 flop/B).  Partials are written to a workspace and summed in a fixed order by
+// the finalize kernel (deterministic, no float atomics), which also symmetrises, applies the covariance
+// rank-1 correction  sum (x-mu)(y-mu) = sum xy - P mu mu^T  and the 1/(C*P) normalisation.
+#include "gram.cuh"
+
+namespace maua {
+
+namespace {
+
+constexpr int GK = 64;                // pixels per pipeline stage
+constexpr int BOX_BYTES = GK * 128;   // one {32 ch, 64 px} box
+constexpr int kMaxSplit = 148;
+
+struct GramParams {
+    int C;
+    long P;
+    int T;        // 128-wide tiles per side
+    int nsplit;
+    float* partial;  // [nsplit][C][C]
+};
+
+template <int BN, bool OFFDIAG>
+struct GramCfg {
+    static constexpr int A_BYTES = 4 * BOX_BYTES;                       // 128 channels
+    static constexpr int B_BYTES = OFFDIAG ? (BN / 32) * BOX_BYTES : 0;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NSTAGES = (192 * 1024) / STAGE_BYTES;          // 6 or 3
+    static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, bool OFFDIAG>
+__global__ void __launch_bounds__(256, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
+    using Cfg = GramCfg<BN, OFFDIAG>;
+    constexpr int NST = Cfg::NSTAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NST;
+    uint64_t* tmem_full_bar = empty_bar + NST;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // upper-triangular tile id -> (ti, tj), ti <= tj
+    int ti = 0, tj = 0;
+    {
+        int id = blockIdx.x;
+        for (ti = 0; ti < p.T; ++ti) {
+            const int rowlen = p.T - ti;
+            if (id < rowlen) { tj = ti + id; break; }
+            id -= rowlen;
+        }
+    }
+    const bool diag = (ti == tj);
+    const int m0 = ti * 128, n0 = tj * 128;
+    const int boxesA = min(4, (p.C - m0) / 32);
+    const int boxesB = diag ? 0 : BN / 32;
+
+    const long total_st = (p.P + GK - 1) / GK;
+    const long st0 = total_st * blockIdx.y / p.nsplit;
+    const long st1 = total_st * (blockIdx.y + 1) / p.nsplit;
+    const int nk = (int)(st1 - st0);
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmF);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_ptr_smem, BN); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        for (int ks = 0; ks < nk; ++ks) {
+            const int stage = ks % NST;
+            const uint32_t phase = (ks / NST) & 1;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sB = sA + Cfg::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], (boxesA + boxesB) * BOX_BYTES);
+            const int prow = (int)((st0 + ks) * GK);
+            for (int bx = 0; bx < boxesA; ++bx) tma_load_2d(sA + bx * BOX_BYTES, &tmF, &full_bar[stage], m0 + bx * 32, prow);
+            for (int bx = 0; bx < boxesB; ++bx) tma_load_2d(sB + bx * BOX_BYTES, &tmF, &full_bar[stage], n0 + bx * 32, prow);
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);  // both operands MN-major
+        for (int ks = 0; ks < nk; ++ks) {
+            const int stage = ks % NST;
+            const uint32_t phase = (ks / NST) & 1;
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sB = (OFFDIAG && !diag) ? sA + Cfg::A_BYTES : sA;
+#pragma unroll
+            for (int kk = 0; kk < GK / 8; ++kk) {
+                const uint64_t adesc = make_smem_desc_sw128(sA + kk * 1024, BOX_BYTES, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(sB + kk * 1024, BOX_BYTES, 1024);
+                umma_tf32(tmem_base, adesc, bdesc, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(tmem_full_bar);
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int c = m0 + row;
+        float* dst = p.partial + ((size_t)blockIdx.y * p.C + c) * p.C + n0;
+        if (nk > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int col = 0; col < BN; col += 16) {
+                float v[16];
+                tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+                if (c < p.C) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(dst + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+        } else if (c < p.C) {
+            for (int col = 0; col < BN; col += 4) *reinterpret_cast<float4*>(dst + col) = make_float4(0, 0, 0, 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+// naive SIMT cross-check: partial slot 0 = full (upper + lower) raw Gram
+__global__ void gram_ref_kernel(const float* __restrict__ f, long P, int C, float* __restrict__ out) {
+    __shared__ float sa[16][17], sb[16][17];
+    const int c = blockIdx.y * 16 + threadIdx.y, d = blockIdx.x * 16 + threadIdx.x;
+    float acc = 0.f;
+    for (long p0 = 0; p0 < P; p0 += 16) {
+        const long pa = p0 + threadIdx.x;
+        sa[threadIdx.y][threadIdx.x] = (pa < P && c < C) ? f[pa * C + c] : 0.f;                          // [c][p]
+        const long pb = p0 + threadIdx.y;
+        sb[threadIdx.y][threadIdx.x] = (pb < P && d < C) ? f[pb * C + d] : 0.f;                          // [p][d]
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = fmaf(sa[threadIdx.y][k], sb[k][threadIdx.x], acc);
+        __syncthreads();
+    }
+    if (c < C && d < C) out[(size_t)c * C + d] = acc;
+}
+
+__global__ void gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long P, int full,
+                                     const float* __restrict__ mean, float* __restrict__ gram) {
+    const long total = (long)C * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = i / C, d = i % C;
+        const bool up = full || ((c >> 7) <= (d >> 7));
+        const size_t src = up ? (size_t)c * C + d : (size_t)d * C + c;
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * total + src];
+        if (mean) s -= (float)P * mean[c] * mean[d];
+        gram[i] = s / ((float)C * (float)P);
+    }
+}
+
+__global__ void style_loss_fwd_kernel(const float* __restrict__ gram, const float* __restrict__ target, long n,
+                                      float scale, float* __restrict__ loss_out, float* __restrict__ diff,
+                                      double* partials, unsigned int* counter) {
+    double acc = 0.0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float dd = gram[i] - target[i];
+        diff[i] = dd;
+        acc += (double)dd * dd;
+    }
+    __shared__ double sh[8];
+    __shared__ bool is_last;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        if (is_last) {
+            __threadfence();
+            double tot = 0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tot += partials[b];
+            *counter = 0;
+            *loss_out = scale * (float)(tot / (double)n);
+        }
+    }
+}
+
+// aux_d = coef * 4 / (C^3 P) * diff  (TF32-rounded: it is the B operand of the backward MMA)
+__global__ void style_bwd_prep_kernel(const float* __restrict__ diff, int C, long P, const float* __restrict__ coef,
+                                      float* __restrict__ aux_d) {
+    const long total = (long)C * C;
+    const float k = *coef * 4.f / ((float)C * (float)C * (float)C * (float)P);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        aux_d[i] = round_tf32(k * diff[i]);
+}
+// aux_bias[c] = - sum_d aux_d[c][d] * mean[d]
+__global__ void style_bwd_bias_kernel(const float* __restrict__ aux_d, const float* __restrict__ mean, int C,
+                                      float* __restrict__ aux_bias) {
+    const int c = blockIdx.x;
+    float acc = 0.f;
+    for (int d = threadIdx.x; d < C; d += blockDim.x) acc += aux_d[(size_t)c * C + d] * mean[d];
+    acc = warp_sum(acc);
+    __shared__ float sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+        aux_bias[c] = -s;
+    }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float a, int accumulate) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = (accumulate ? y[i] : 0.f) + a * x[i];
+}
+
+template <int BN, bool OFFDIAG>
+int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, int ntiles, cudaStream_t st) {
+    using Cfg = GramCfg<BN, OFFDIAG>;
+    static unsigned long long attr_done = 0;
+    MAUA_CUDA_CHECK(ensure_dynamic_smem(gram_tc_kernel<BN, OFFDIAG>, Cfg::SMEM_BYTES, &attr_done));
+    gram_tc_kernel<BN, OFFDIAG><<<dim3(ntiles, p.nsplit), 256, Cfg::SMEM_BYTES, st>>>(tm, p);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+}  // namespace
+
+size_t gram_workspace_bytes(int C) {
+    // [kMaxSplit-bounded partials][C][C] floats + channel-mean scratch (doubles)
+    const int T = (C + 127) / 128;
+    const int ntiles = T * (T + 1) / 2;
+    const int nsplit = kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1;
+    return (size_t)nsplit * C * C * sizeof(float) + (size_t)kMaxSplit * 4 * C * sizeof(double) + 1024;
+}
+
+int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* mean_out, void* workspace, int impl,
+                cudaStream_t st) {
+    MAUA_REQUIRE(C >= 64 && (C == 64 || C % 128 == 0) && C <= 1024,
+                 "gram: channel count %d unsupported (need 64 or a multiple of 128, <= 1024)", C);
+    MAUA_REQUIRE(P >= 1 && P < (1L << 31), "gram: bad pixel count %ld", P);
+    const int T = (C + 127) / 128;
+    const int ntiles = T * (T + 1) / 2;
+    int nsplit = kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1;
+    const long total_st = (P + GK - 1) / GK;
+    if (nsplit > total_st) nsplit = (int)total_st;
+    float* partial = reinterpret_cast<float*>(workspace);
+    double* mean_scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
+                                                     (((size_t)(kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1) * C * C *
+                                                       sizeof(float) + 255) & ~size_t(255)));
+    if (use_cov) {
+        int rc = channel_mean_launch(f, P, C, mean_out, mean_scratch, kMaxSplit * 4, st);
+        if (rc) return rc;
+    }
+    int full = 0;
+    if (impl == 1) {
+        nsplit = 1;
+        full = 1;
+        gram_ref_kernel<<<dim3((C + 15) / 16, (C + 15) / 16), dim3(16, 16), 0, st>>>(f, P, C, partial);
+        MAUA_CUDA_CHECK(cudaGetLastError());
+    } else {
+        CUtensorMap tm;
+        int rc = make_tmap_2d(&tm, f, P, C, GK);
+        if (rc) return rc;
+        GramParams p;
+        p.C = C; p.P = P; p.T = T; p.nsplit = nsplit; p.partial = partial;
+        if (C == 64) rc = launch_gram_tc<64, false>(tm, p, ntiles, st);
+        else if (C == 128) rc = launch_gram_tc<128, false>(tm, p, ntiles, st);
+        else rc = launch_gram_tc<128, true>(tm, p, ntiles, st);
+        if (rc) return rc;
+    }
+    const long total = (long)C * C;
+    gram_finalize_kernel<<<(int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256), 256, 0, st>>>(
+        partial, nsplit, C, P, full, use_cov ? mean_out : nullptr, gram);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+int style_loss_fwd_launch(const float* gram, const float* target, int C, float value_scale, float* loss_out,
+                          float* diff, ReduceScratch rs, cudaStream_t st) {
+    const long n = (long)C * C;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148) grid = 148;
+    MAUA_REQUIRE(grid <= rs.max_blocks, "reduce scratch too small");
+    style_loss_fwd_kernel<<<grid, 256, 0, st>>>(gram, target, n, value_scale, loss_out, diff, rs.partials, rs.counter);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+int style_loss_bwd_prep_launch(const float* diff, const float* mean, int C, long P, const float* coef, float* aux_d,
+                               float* aux_bias, cudaStream_t st) {
+    const long n = (long)C * C;
+    style_bwd_prep_kernel<<<(int)((n + 255) / 256 > 592 ? 592 : (n + 255) / 256), 256, 0, st>>>(diff, C, P, coef, aux_d);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    if (mean) {
+        style_bwd_bias_kernel<<<C, 128, 0, st>>>(aux_d, mean, C, aux_bias);
+        MAUA_CUDA_CHECK(cudaGetLastError());
+    }
+    return MAUA_OK;
+}
+
+int axpby_launch(const float* x, float* y, long n, float a, int accumulate, cudaStream_t st) {
+    axpby_kernel<<<(int)((n + 255) / 256 > 592 ? 592 : (n + 255) / 256), 256, 0, st>>>(x, y, n, a, accumulate);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+}  // namespace maua

@@ -1,0 +1,31 @@
+// Launchers of the memory-bound kernels (pointwise.cu) and the L-BFGS vector kernels (lbfgs.cu).
+#pragma once
+#include "common.cuh"
+
+namespace maua {
+
+// scratch for deterministic grid-wide sums: one double per block per value + a self-resetting counter
+struct ReduceScratch {
+    double* partials = nullptr;
+    unsigned int* counter = nullptr;  // must be zero-initialised once
+    int max_blocks = 0;
+};
+
+int nchw_to_nhwc_launch(const float* src, float* dst, int B, int C, int H, int W, int do_round, cudaStream_t st);
+int nhwc_to_nchw_launch(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
+int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad, int do_round, cudaStream_t st);
+int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, cudaStream_t st);
+int pool_bwd_launch(const float* x, const float* gy, const float* addend, float* gx, int B, int H, int W, int C,
+                    int avg, int do_round, cudaStream_t st);
+int tv_value_launch(const float* x, int planes, int H, int W, float strength, float* loss_out, ReduceScratch rs,
+                    cudaStream_t st);
+int mse_value_launch(const float* x, const float* t, long n, float scale, float* loss_out, ReduceScratch rs,
+                     cudaStream_t st);
+int wmse_value_launch(const float* x, const float* wts, const float* t, long n, long plane, float scale,
+                      float* loss_out, ReduceScratch rs, cudaStream_t st);
+int channel_mean_launch(const float* x, long P, int C, float* mean_out, double* scratch, int scratch_blocks,
+                        cudaStream_t st);
+int adam_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
+                int step, cudaStream_t st);
+
+}  // namespace maua

@@ -1,0 +1,268 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against plain fp32 torch on the CPU.
+
+Floating-point kernels: the conv / Gram kernels compute with TF32 operands and FP32 accumulation, so the
+tolerance is stated per test as a relative L2 error (||a-b|| / ||b||); element-wise kernels are compared at
+fp32 round-off.  The naive SIMT implementation (MAUA_IMPL_REF) is cross-checked too: it shares the
+contract, not the code, of the tcgen05 path.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from maua_style_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+TF32_REL = 1.5e-3  # single conv layer, TF32 operands (eps 2^-11 each), fp32 accumulate
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def tf32_round(x):
+    """RNA rounding of fp32 to tf32 (10-bit mantissa), matching cvt.rna.tf32.f32."""
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+IMPLS = pytest.mark.parametrize("impl", [pytest.param(_lib.MAUA_IMPL_REF, id="ref"), pytest.param(_lib.MAUA_IMPL_TC, id="tc")])
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _lib.require_gpu()
+    return _lib.load()
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def prep(lib, w, dgrad):
+    cout, cin = w.shape[:2]
+    out = torch.empty((cin if dgrad else cout, 9 * (cout if dgrad else cin)), device="cuda")
+    _lib.check(lib.maua_prep_conv_weights(_lib.ptr(w), _lib.ptr(out), cout, cin, int(dgrad), _lib.stream_ptr()))
+    return out
+
+
+@IMPLS
+@pytest.mark.parametrize(
+    "cin,cout,h,w",
+    [(64, 64, 32, 48), (64, 128, 16, 16), (128, 256, 24, 40), (256, 512, 11, 13), (512, 512, 8, 8), (64, 64, 90, 122),
+     (128, 128, 181, 77)],
+)
+def test_conv3x3_fwd(lib, impl, cin, cout, h, w):
+    g = torch.Generator().manual_seed(cin * 7 + cout + h)
+    x = tf32_round(torch.randn(1, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x, tf32_round(wt), b, padding=1))
+    xd, wd, bd = nhwc(x).cuda(), wt.cuda(), b.cuda()
+    wg = prep(lib, wd, False)
+    y = torch.empty(1, h, w, cout, device="cuda")
+    _lib.check(lib.maua_conv3x3_fwd(_lib.ptr(xd), _lib.ptr(wg), _lib.ptr(bd), _lib.ptr(y), 1, h, w, cin, cout, 1, impl,
+                                    _lib.stream_ptr()), "conv3x3_fwd")
+    torch.cuda.synchronize()
+    err = rel(nchw(y), ref)
+    assert err < TF32_REL, f"conv fwd rel err {err}"
+
+
+@IMPLS
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 64, 32, 48), (64, 128, 17, 23), (256, 512, 12, 20), (512, 512, 9, 7)])
+def test_conv3x3_dgrad_with_mask(lib, impl, cin, cout, h, w):
+    g = torch.Generator().manual_seed(cin + cout * 3 + h)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    gy = tf32_round(torch.randn(1, cout, h, w, generator=g))
+    act = torch.randn(1, cin, h, w, generator=g)  # sign pattern of the layer below
+    x = torch.zeros(1, cin, h, w, requires_grad=True)
+    F.conv2d(x, tf32_round(wt), None, padding=1).backward(gy)
+    ref = x.grad * (act > 0)
+    wdg = prep(lib, wt.cuda(), True)
+    gx = torch.empty(1, h, w, cin, device="cuda")
+    null = C.c_void_p(0)
+    _lib.check(lib.maua_conv3x3_dgrad(_lib.ptr(nhwc(gy).cuda()), _lib.ptr(wdg), _lib.ptr(gx), 1, h, w, cout, cin,
+                                      _lib.ptr(nhwc(act).cuda()), null, null, null, null, null, null, 0, impl,
+                                      _lib.stream_ptr()), "conv3x3_dgrad")
+    torch.cuda.synchronize()
+    err = rel(nchw(gx), ref)
+    assert err < TF32_REL, f"dgrad rel err {err}"
+
+
+@IMPLS
+@pytest.mark.parametrize("with_main", [True, False])
+def test_dgrad_with_style_and_content_terms(lib, impl, with_main):
+    """gx = (dgrad(gy) + F @ D + bias + coef (F - T)) * (F > 0)  -- the fused tap-gradient epilogue."""
+    cin, cout, h, w = 128, 256, 20, 28
+    g = torch.Generator().manual_seed(5)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.03
+    gy = tf32_round(torch.randn(1, cout, h, w, generator=g))
+    feat = tf32_round(torch.randn(1, cin, h, w, generator=g))
+    targ = torch.randn(1, cin, h, w, generator=g)
+    D = torch.randn(cin, cin, generator=g) * 0.05
+    D = tf32_round(D + D.t())
+    bias = torch.randn(cin, generator=g)
+    coef = torch.tensor([0.37])
+    ref = torch.einsum("bdhw,cd->bchw", feat, D) + bias.view(1, -1, 1, 1) + coef * (feat - targ)
+    if with_main:
+        x = torch.zeros(1, cin, h, w, requires_grad=True)
+        F.conv2d(x, tf32_round(wt), None, padding=1).backward(gy)
+        ref = ref + x.grad
+    ref = ref * (feat > 0)
+    gx = torch.empty(1, h, w, cin, device="cuda")
+    fd, td = nhwc(feat).cuda(), nhwc(targ).cuda()
+    null = C.c_void_p(0)
+    gyd = nhwc(gy).cuda() if with_main else None
+    wdg = prep(lib, wt.cuda(), True) if with_main else None
+    _lib.check(lib.maua_conv3x3_dgrad(_lib.ptr(gyd), _lib.ptr(wdg), _lib.ptr(gx), 1, h, w, cout, cin, _lib.ptr(fd),
+                                      _lib.ptr(fd), _lib.ptr(D.cuda()), _lib.ptr(bias.cuda()), _lib.ptr(fd), _lib.ptr(td),
+                                      _lib.ptr(coef.cuda()), 0, impl, _lib.stream_ptr()), "conv3x3_dgrad+aux")
+    torch.cuda.synchronize()
+    err = rel(nchw(gx), ref)
+    assert err < TF32_REL, f"fused dgrad rel err {err}"
+
+
+@pytest.mark.parametrize("h,w", [(32, 32), (37, 53), (5, 3)])
+def test_conv_first_fwd_and_dgrad(lib, h, w):
+    g = torch.Generator().manual_seed(h)
+    img = torch.rand(1, 3, h, w, generator=g) * 255 - 110
+    wt = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(64, generator=g)
+    ref = F.relu(F.conv2d(img, wt, b, padding=1))
+    y = torch.empty(1, h, w, 64, device="cuda")
+    _lib.check(lib.maua_conv_first_fwd(_lib.ptr(img.cuda()), _lib.ptr(wt.cuda()), _lib.ptr(b.cuda()), _lib.ptr(y), 1, h, w,
+                                       64, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel(nchw(y), tf32_round(ref)) < 2e-5  # rare 1-ulp tf32 rounding flips
+
+    # dgrad + TV + temporal tail
+    gy = torch.randn(1, 64, h, w, generator=g)
+    x = img.clone().requires_grad_(True)
+    warp = torch.rand(1, 3, h, w, generator=g) * 255 - 110
+    wts = torch.rand(1, 1, h, w, generator=g)
+    tvc, tpc = 0.013, 0.7
+    tv = (x[:, :, 1:, :] - x[:, :, :-1, :]).abs().sum() + (x[:, :, :, 1:] - x[:, :, :, :-1]).abs().sum()
+    temporal = ((x * wts - warp) ** 2).sum() * 0.5
+    total = (F.conv2d(x, wt, None, padding=1) * gy).sum() + tvc * tv + tpc * temporal
+    total.backward()
+    gimg = torch.empty(1, 3, h, w, device="cuda")
+    _lib.check(lib.maua_conv_first_dgrad(_lib.ptr(nhwc(gy).cuda()), _lib.ptr(wt.cuda()), _lib.ptr(gimg), 1, h, w, 64,
+                                         _lib.ptr(img.cuda()), _lib.ptr(torch.tensor([tvc]).cuda()), _lib.ptr(warp.cuda()),
+                                         _lib.ptr(wts.cuda()), _lib.ptr(torch.tensor([tpc]).cuda()), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel(gimg, x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("avg", [0, 1])
+@pytest.mark.parametrize("h,w", [(16, 16), (17, 23), (9, 2)])
+def test_pool_fwd_bwd(lib, avg, h, w):
+    c = 64
+    g = torch.Generator().manual_seed(h * w)
+    x = F.relu(torch.randn(1, c, h, w, generator=g))
+    x[0, :, : h // 2 * 2 : 2, : w // 2 * 2 : 2] = x[0, :, 1 : h // 2 * 2 : 2, 1 : w // 2 * 2 : 2]  # force ties
+    x = tf32_round(x).requires_grad_(True)
+    y = (F.avg_pool2d if avg else F.max_pool2d)(x, 2, 2)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    ref_g = x.grad * (x > 0)
+    yd = torch.empty(1, h // 2, w // 2, c, device="cuda")
+    xd = nhwc(x.detach()).cuda()
+    _lib.check(lib.maua_pool2x2_fwd(_lib.ptr(xd), _lib.ptr(yd), 1, h, w, c, avg, _lib.stream_ptr()))
+    gx = torch.full((1, h, w, c), 7.0, device="cuda")
+    _lib.check(lib.maua_pool2x2_bwd(_lib.ptr(xd), _lib.ptr(nhwc(gy).cuda()), C.c_void_p(0), _lib.ptr(gx), 1, h, w, c, avg, 0,
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    yref = y.detach()
+    assert rel(nchw(yd), tf32_round(yref) if avg else yref) < 2e-5
+    assert rel(nchw(gx), ref_g) < 1e-6
+
+
+@IMPLS
+@pytest.mark.parametrize("cov", [0, 1])
+@pytest.mark.parametrize("c,h,w", [(64, 40, 56), (128, 33, 21), (256, 16, 16), (512, 9, 13), (64, 3, 5)])
+def test_gram(lib, impl, cov, c, h, w):
+    g = torch.Generator().manual_seed(c + h)
+    f = tf32_round(F.relu(torch.randn(1, c, h, w, generator=g) + 0.3))
+    X = f.reshape(c, h * w).double()
+    if cov:
+        X = X - X.mean(1, keepdim=True)
+    ref = (X @ X.t() / (c * h * w)).float()
+    fd = nhwc(f).cuda()
+    ws = torch.empty(lib.maua_gram_workspace_bytes(c), dtype=torch.uint8, device="cuda")
+    G = torch.empty(c, c, device="cuda")
+    mean = torch.empty(c, device="cuda")
+    _lib.check(lib.maua_gram(_lib.ptr(fd), C.c_long(h * w), c, cov, _lib.ptr(G), _lib.ptr(mean), _lib.ptr(ws), impl,
+                             _lib.stream_ptr()), "gram")
+    torch.cuda.synchronize()
+    err = rel(G, ref)
+    assert err < (2e-5 if cov else 2e-6), f"gram rel err {err}"
+    assert rel(G, G.t()) < 1e-7
+
+
+def test_style_loss_and_prep(lib):
+    c, p = 128, 1000
+    g = torch.Generator().manual_seed(0)
+    G, A = torch.randn(c, c, generator=g), torch.randn(c, c, generator=g)
+    mean = torch.rand(c, generator=g)
+    ws = torch.zeros(lib.maua_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    diff = torch.empty(c, c, device="cuda")
+    _lib.check(lib.maua_style_loss_fwd(_lib.ptr(G.cuda()), _lib.ptr(A.cuda()), c, C.c_float(3.5), _lib.ptr(loss),
+                                       _lib.ptr(diff), _lib.ptr(ws), _lib.stream_ptr()))
+    coef = torch.tensor([2.25], device="cuda")
+    D = torch.empty(c, c, device="cuda")
+    bias = torch.empty(c, device="cuda")
+    _lib.check(lib.maua_style_loss_bwd_prep(_lib.ptr(diff), _lib.ptr(mean.cuda()), c, C.c_long(p), _lib.ptr(coef),
+                                            _lib.ptr(D), _lib.ptr(bias), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - 3.5 * ((G - A) ** 2).mean().item()) < 1e-4
+    Dref = tf32_round(2.25 * 4 / (c ** 3 * p) * (G - A))
+    assert rel(D, Dref) < 1e-6
+    assert rel(bias, -(Dref @ mean)) < 1e-5
+
+
+def test_content_tv_adam(lib):
+    g = torch.Generator().manual_seed(1)
+    ws = torch.zeros(lib.maua_reduce_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    x, t = torch.randn(4096 * 3, generator=g), torch.randn(4096 * 3, generator=g)
+    loss = torch.zeros(1, device="cuda")
+    _lib.check(lib.maua_content_loss_fwd(_lib.ptr(x.cuda()), C.c_void_p(0), _lib.ptr(t.cuda()), C.c_long(x.numel()),
+                                         C.c_long(0), C.c_float(5.0), _lib.ptr(loss), _lib.ptr(ws), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert abs(loss.item() / (5.0 * F.mse_loss(x, t).item()) - 1) < 1e-5
+    wts = torch.rand(4096, generator=g)
+    _lib.check(lib.maua_content_loss_fwd(_lib.ptr(x.cuda()), _lib.ptr(wts.cuda()), _lib.ptr(t.cuda()), C.c_long(x.numel()),
+                                         C.c_long(4096), C.c_float(50.0), _lib.ptr(loss), _lib.ptr(ws), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    refw = 50.0 * F.mse_loss(x.view(3, 4096) * wts, t.view(3, 4096)).item()
+    assert abs(loss.item() / refw - 1) < 1e-5
+
+    img = torch.rand(1, 3, 37, 41, generator=g) * 255
+    _lib.check(lib.maua_tv_loss_fwd(_lib.ptr(img.cuda()), 3, 37, 41, C.c_float(1e-3), _lib.ptr(loss), _lib.ptr(ws),
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    tv = 1e-3 * ((img[:, :, 1:] - img[:, :, :-1]).abs().sum() + (img[:, :, :, 1:] - img[:, :, :, :-1]).abs().sum())
+    assert abs(loss.item() / tv.item() - 1) < 1e-5
+
+    n = 3 * 37 * 41 + 3
+    p = torch.randn(n, generator=g).requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=1.0)
+    pd = p.detach().clone().cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g) * 10 ** (step - 3)
+        p.grad = grad.clone()
+        opt.step()
+        _lib.check(lib.maua_adam_step(_lib.ptr(pd), _lib.ptr(grad.cuda()), _lib.ptr(m), _lib.ptr(v), C.c_long(n),
+                                      C.c_float(1.0), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), step,
+                                      _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel(pd, p.detach()) < 1e-6
