@@ -81,6 +81,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
 
         _build.build()
     lib = C.CDLL(str(LIB_PATH))
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing and os.environ.get("MAUA_DEV_ALLOW_MISSING") == "1":  # bring-up only
+        for s in missing:
+            setattr(lib, s, lib.maua_abi_version)
+    elif missing:
+        raise RuntimeError(f"{LIB_PATH} does not export {missing}: stale build? run `python -m maua_style_b200.build --force`")
     lib.maua_last_error.restype = C.c_char_p
     lib.maua_gram_workspace_bytes.restype = C.c_size_t
     lib.maua_reduce_workspace_bytes.restype = C.c_size_t

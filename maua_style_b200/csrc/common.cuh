@@ -198,6 +198,16 @@ MAUA_DEVINL void tmem_ld_x16(uint32_t taddr, float* v) {
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset>>4 [46,48) version = 1
 //   [61,64) layout: 0 none, 2 = 128B swizzle
+//            1 = 128B swizzle with 32-byte atoms (the only layout allowed for MN-major TF32 operands)
+MAUA_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= static_cast<uint64_t>(layout_type & 7u) << 61;
+    return d;
+}
 MAUA_DEVINL uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);

@@ -280,7 +280,7 @@ int make_tmap_nhwc(CUtensorMap* m, const float* ptr, int B, int H, int W, int C,
 }
 
 // Row-major matrix [rows][cols] (cols contiguous) -> 2-D map, box {32, box_rows}, 128B swizzle.
-int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box_rows) {
+int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box_rows, int atom32) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
@@ -293,7 +293,9 @@ int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box
     cuuint32_t box[2] = {KCHUNK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(2D %ldx%ld) failed: CUresult %d", rows, cols, (int)r);
@@ -315,11 +317,11 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     const bool has_aux = a.K2 > 0;
     if (has_main) {
         if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, TILE_H))) return rc;
-        if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, BN))) return rc;
+        if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, BN, 0))) return rc;
     }
     if (has_aux) {
         if ((rc = make_tmap_nhwc(&tmA2, a.in2, a.B, a.H, a.W, a.K2, TILE_W, TILE_H))) return rc;
-        if ((rc = make_tmap_2d(&tmB2, a.w2, a.Cout, a.K2, BN))) return rc;
+        if ((rc = make_tmap_2d(&tmB2, a.w2, a.Cout, a.K2, BN, 0))) return rc;
     }
     if (!has_main) { tmA = tmA2; tmB = tmB2; }
     if (!has_aux) { tmA2 = tmA; tmB2 = tmB; }

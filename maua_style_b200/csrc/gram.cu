@@ -8,9 +8,10 @@
 // Layout: features are NHWC, i.e. the flattened matrix is F[P][C] with channels contiguous, and
 //   G[c][d] = sum_p F[p][c] F[p][d]  is a GEMM whose M, N are channels and whose K is pixels.
 // Both operands are therefore "MN-major" for the tensor core (the M/N index is the contiguous one).
-// A TMA box {32 channels, 64 pixels} lands as 64 rows of 128 bytes with the 128B swizzle, which is exactly
-// the canonical MN-major SWIZZLE_128B UMMA layout: 8 K-rows x 128 B atoms (SBO = 1024 B between 8-pixel
-// groups), 32-channel groups LBO = 8192 B apart.  Only upper-triangular 128x128 tiles are computed; for
+// For TF32 the only MN-major shared-memory layout the tensor core accepts is the 128B swizzle with 32-byte
+// atoms (UMMA layout type SWIZZLE_128B_BASE32B, TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a TMA box
+// {32 channels, 64 pixels} lands as 64 rows of 128 bytes whose 32-byte chunks are XOR-swizzled with (row % 4),
+// i.e. 4 K-rows x 128 B atoms (SBO = 512 B between 4-pixel groups), 32-channel groups LBO = 8192 B apart.  Only upper-triangular 128x128 tiles are computed; for
 // diagonal tiles the B operand aliases the A tile in shared memory (half the smem traffic).
 // K (pixels) is split across CTAs so that all 148 SMs stream F once: the C = 64 / 128 layers are
 // HBM-bound (intensity C/2 flop/B).  Partials are written to a workspace and summed in a fixed order by
@@ -112,8 +113,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
             const uint32_t sB = (OFFDIAG && !diag) ? sA + Cfg::A_BYTES : sA;
 #pragma unroll
             for (int kk = 0; kk < GK / 8; ++kk) {
-                const uint64_t adesc = make_smem_desc_sw128(sA + kk * 1024, BOX_BYTES, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(sB + kk * 1024, BOX_BYTES, 1024);
+                // MN-major TF32: layout type 1 (128B swizzle, 32-byte atoms): 4-row x 128 B atoms, SBO = 512 B
+                const uint64_t adesc = make_smem_desc(sA + kk * 1024, BOX_BYTES, 512, 1);
+                const uint64_t bdesc = make_smem_desc(sB + kk * 1024, BOX_BYTES, 512, 1);
                 umma_tf32(tmem_base, adesc, bdesc, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);
@@ -284,7 +286,7 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
         MAUA_CUDA_CHECK(cudaGetLastError());
     } else {
         CUtensorMap tm;
-        int rc = make_tmap_2d(&tm, f, P, C, GK);
+        int rc = make_tmap_2d(&tm, f, P, C, GK, 1);
         if (rc) return rc;
         GramParams p;
         p.C = C; p.P = P; p.T = T; p.nsplit = nsplit; p.partial = partial;

@@ -17,6 +17,7 @@ int style_loss_bwd_prep_launch(const float* diff, const float* mean, int C, long
 int axpby_launch(const float* x, float* y, long n, float a, int accumulate, cudaStream_t st);
 
 // shared with conv_tc.cu
-int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box_rows);
+// atom32 != 0 selects CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (needed for MN-major TF32 UMMA operands)
+int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box_rows, int atom32);
 
 }  // namespace maua

@@ -8,7 +8,7 @@ run() { # name, -k expression
   timeout -k 10 420 python -m pytest tests/test_kernels_gpu.py -q -k "$2" --timeout 180 -p no:cacheprovider > "gpurun_out/kt_$1.log" 2>&1
   echo "== $1: exit $? =="; tail -n 6 "gpurun_out/kt_$1.log"
 }
-run ref "ref or first or pool or style_loss or content_tv"
+run ref "ref or first or pool or style_loss or content_tv or lbfgs"
 run tc_fwd "test_conv3x3_fwd and tc"
 run tc_dgrad "test_conv3x3_dgrad and tc"
 run tc_aux "test_dgrad_with_style and tc"
