@@ -219,10 +219,12 @@ MAUA_API int maua_loss_grad_coefs(const float* upstream, float* coefs, int n, co
                                   const float* vsf, const int* normalize, const int* kind,
                                   maua_stream_t stream);
 
-/* Gram matrix of tap `tap` from the last forward (normalised, [C][C]); valid until the next forward. */
-MAUA_API int maua_plan_tap_gram(maua_plan_t* plan, int tap, const float** gram, int* c);
-/* Feature map of tap `tap` from the last forward (NHWC [H_l][W_l][C]). */
-MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, const float** feat, int* h, int* w, int* c);
+/* Copy the Gram matrix of style tap `tap` from the last forward (normalised, [C][C]) into dst (may be NULL to
+ * query *c only). */
+MAUA_API int maua_plan_tap_gram(maua_plan_t* plan, int tap, float* dst, int* c, maua_stream_t stream);
+/* Copy the feature map of tap `tap` from the last forward (NHWC [H_l][W_l][C]) into dst (NULL: query the shape). */
+MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, float* dst, int* h, int* w, int* c,
+                                   maua_stream_t stream);
 /* Switch the GEMM-shaped kernels of this plan between MAUA_IMPL_TC and MAUA_IMPL_REF (tests only). */
 MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
 /* Number of kernel launches issued by the last forward / backward (for bench.py's gpu_launches). */

@@ -1,0 +1,219 @@
+"""Loss modules with the reference's interface (reference loss.py), backed by the sm_100a kernels.
+
+Same class names, constructor arguments, attributes (`mode`, `loss`, `target`, `strength`, `blend_weight`,
+`weights`, `name`, `normalize`, `use_covariance`, `video_style_factor`, `reset_targets()`) and mode protocol
+("none" / "capture" / "loss") as reference loss.py:32-64 (ContentLoss), :67-91 (GramMatrix), :94-186 (StyleLoss),
+:224-233 (TVLoss), :10-20 (ScaleGradients).
+
+Inside a `models.B200Net` the modules are descriptors: the network reads their mode / strength / target and runs
+the fused plan (one SYRK per style layer, loss gradients folded into the dgrad kernels).  Called on their own
+(`module(feature_map)`) they run the same kernels one at a time through the per-kernel C ABI, so they remain
+usable as drop-in nn.Modules.  Only batch size 1 is supported (the reference's B > 1 video-style semantics are
+out of scope).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class ScaleGradients(torch.autograd.Function):
+    """loss.py:10-20 -- identity forward; backward grad / (||grad|| + 1e-8) * strength^2.  Kept for API parity;
+    the fused path applies the same rule to the scalar loss gradients on the device (maua_loss_grad_coefs)."""
+
+    @staticmethod
+    def forward(ctx, input_tensor, strength):
+        ctx.strength = strength
+        return input_tensor
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_input = grad_output / (torch.norm(grad_output, keepdim=True) + 1e-8)
+        return grad_input * ctx.strength * ctx.strength, None
+
+
+def _to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[1,C,H,W] CUDA tensor -> contiguous NHWC memory, TF32-rounded (kernel), returned as [H*W, C]."""
+    _lib.require_gpu()
+    lib = _lib.load()
+    x = x.detach().float().contiguous()
+    b, c, h, w = x.shape
+    out = torch.empty(b, h, w, c, device=x.device)
+    _lib.check(lib.maua_nchw_to_nhwc(_lib.ptr(x), _lib.ptr(out), b, c, h, w, 1, _lib.stream_ptr()), "maua_nchw_to_nhwc")
+    return out
+
+
+def _gram_normalised(x: torch.Tensor, use_covariance: bool):
+    """gram(x) / x.nelement() for a [1,C,H,W] CUDA tensor via the tcgen05 SYRK; returns (gram [C,C], nhwc, mean)."""
+    lib = _lib.load()
+    b, c, h, w = x.shape
+    if b != 1:
+        raise NotImplementedError("maua_style_b200 supports batch size 1 only (B > 1 video-style Grams are out of scope)")
+    f = _to_nhwc(x)
+    ws = torch.empty(lib.maua_gram_workspace_bytes(c), dtype=torch.uint8, device=x.device)
+    gram = torch.empty(c, c, device=x.device)
+    mean = torch.empty(c, device=x.device)
+    _lib.check(lib.maua_gram(_lib.ptr(f), C.c_long(h * w), c, int(use_covariance), _lib.ptr(gram), _lib.ptr(mean),
+                             _lib.ptr(ws), _lib.MAUA_IMPL_TC, _lib.stream_ptr()), "maua_gram")
+    return gram, f, mean
+
+
+class GramMatrix(nn.Module):
+    """loss.py:67-91: [B,C,H,W] -> un-normalised [B*C, B*C] Gram (or covariance) matrix, B = 1."""
+
+    def forward(self, x, shift_x=0, shift_y=0, shift_t=0, flip_h=False, flip_v=False, use_covariance=False):
+        if shift_x or shift_y or shift_t or flip_h or flip_v:
+            raise NotImplementedError("shifted / flipped Grams are dead code in the reference (loss.py:188-221)")
+        gram, _, _ = _gram_normalised(x.cuda(), use_covariance)
+        return gram * float(x[0].nelement())
+
+
+class _StyleLossFn(torch.autograd.Function):
+    """mean((gram/nel - target)^2) for a standalone StyleLoss call; backward 4 (G-A) X / (C^3 N) via the aux GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, target, use_covariance):
+        lib = _lib.load()
+        gram, f, mean = _gram_normalised(x, use_covariance)
+        c = gram.shape[0]
+        ws = torch.zeros(lib.maua_reduce_workspace_bytes(), dtype=torch.uint8, device=x.device)
+        loss = torch.zeros(1, device=x.device)
+        diff = torch.empty_like(gram)
+        tgt = target.detach().float().contiguous()
+        _lib.check(lib.maua_style_loss_fwd(_lib.ptr(gram), _lib.ptr(tgt), c, C.c_float(1.0), _lib.ptr(loss), _lib.ptr(diff),
+                                           _lib.ptr(ws), _lib.stream_ptr()), "maua_style_loss_fwd")
+        ctx.save_for_backward(f, diff, mean)
+        ctx.use_covariance = use_covariance
+        ctx.shape = x.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        f, diff, mean = ctx.saved_tensors
+        _, c, h, w = ctx.shape
+        coef = g.detach().float().reshape(1).contiguous()
+        aux_d = torch.empty_like(diff)
+        aux_bias = torch.empty(c, device=f.device) if ctx.use_covariance else None
+        _lib.check(lib.maua_style_loss_bwd_prep(_lib.ptr(diff), _lib.ptr(mean if ctx.use_covariance else None), c,
+                                                C.c_long(h * w), _lib.ptr(coef), _lib.ptr(aux_d), _lib.ptr(aux_bias),
+                                                _lib.stream_ptr()), "maua_style_loss_bwd_prep")
+        gx = torch.empty_like(f)
+        null = C.c_void_p(0)
+        _lib.check(lib.maua_conv3x3_dgrad(null, null, _lib.ptr(gx), 1, h, w, c, c, null, _lib.ptr(f), _lib.ptr(aux_d),
+                                          _lib.ptr(aux_bias), null, null, null, 0, _lib.MAUA_IMPL_TC, _lib.stream_ptr()),
+                   "maua_conv3x3_dgrad(aux)")
+        return gx.permute(0, 3, 1, 2), None, None
+
+
+class ContentLoss(nn.Module):
+    """loss.py:32-64."""
+
+    def __init__(self, strength, normalize=False):
+        super().__init__()
+        self.strength = strength
+        self.crit = nn.MSELoss()
+        self.mode = "none"
+        self.weights = None
+        self.normalize = normalize
+        self.loss = 0
+        self.target = torch.Tensor()
+        self.name = "cont"
+
+    def forward(self, input):
+        # standalone use (outside a B200Net): plain tensor ops on the device, same control flow as loss.py:42-64
+        if self.mode == "none" or (input.shape[1:] != self.target.shape[1:] and self.target.nelement() != 0):
+            return input
+        if "temporal" in self.name and self.target.shape[0] == 0 and self.mode == "loss":
+            return input
+        self.loss = 0
+        for idx in range(input.shape[0]):
+            if self.mode == "loss":
+                xi = input[[idx]]
+                loss = self.crit(xi * self.weights, self.target) if self.weights is not None else self.crit(xi, self.target)
+                if self.normalize:
+                    loss = ScaleGradients.apply(loss, self.strength)
+                self.loss = self.loss + loss * self.strength / input.shape[0]
+            if self.mode == "capture":
+                self.target = input.detach()
+        return input
+
+
+class StyleLoss(nn.Module):
+    """loss.py:94-186 (static + dynamic term; shift / flip losses are dead code there and absent here)."""
+
+    def __init__(self, strength, use_covariance=False, normalize=False, video_style_factor=0, shift_factor=0,
+                 flip_factor=0, rotation_factor=0):
+        super().__init__()
+        self.reset_targets()
+        self.strength = strength
+        self.blend_weight = None
+        self.video_style_factor = video_style_factor
+        self.shift_factor = shift_factor
+        self.flip_factor = flip_factor
+        self.rotation_factor = rotation_factor
+        self.gram = GramMatrix()
+        self.crit = nn.MSELoss()
+        self.loss = 0
+        self.mode = "none"
+        self.use_covariance = use_covariance
+        self.normalize = normalize
+        self.name = "style"
+
+    def reset_targets(self):
+        self.target = torch.Tensor()
+        self.video_target = torch.Tensor()
+        self.shift_targets_x = []
+        self.shift_targets_y = []
+
+    def forward(self, input):
+        # standalone use: one SYRK serves the static and the dynamic term (identical for B = 1)
+        if self.mode == "none":
+            return input
+        if input.shape[0] != 1:
+            raise NotImplementedError("maua_style_b200 supports batch size 1 only")
+        x = input.cuda()
+        if self.mode == "capture":
+            gram, _, _ = _gram_normalised(x, self.use_covariance)
+            self.loss = 0
+            if self.target.nelement() == 0:
+                self.target = self.blend_weight * gram
+            else:
+                self.target = self.target + self.blend_weight * gram
+            self.video_target = self.target
+        elif self.mode == "loss":
+            mse = _StyleLossFn.apply(x, self.target, self.use_covariance)
+            terms = [1.0] + ([float(self.video_style_factor)] if self.video_style_factor > 0 else [])
+            for scale in terms:
+                l = ScaleGradients.apply(mse, self.strength) if self.normalize else mse
+                self.loss = self.loss + scale * l * self.strength
+        return input
+
+
+class TVLoss(nn.Module):
+    """loss.py:224-233."""
+
+    def __init__(self, strength):
+        super().__init__()
+        self.strength = strength
+        self.loss = 0
+        self.mode = "none"
+        self.name = "tv"
+
+    def forward(self, input):
+        x_diff = input[:, :, 1:, :] - input[:, :, :-1, :]
+        y_diff = input[:, :, :, 1:] - input[:, :, :, :-1]
+        self.loss = self.strength * (torch.sum(torch.abs(x_diff)) + torch.sum(torch.abs(y_diff)))
+        return input
+
+
+def normalize_weights(content_losses, style_losses):
+    """loss.py:23-28."""
+    for i in content_losses:
+        i.strength = i.strength / max(i.target.size())
+    for i in style_losses:
+        i.strength = i.strength / max(i.target.size())

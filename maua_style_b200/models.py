@@ -1,0 +1,425 @@
+"""`load_model(args) -> (net, losses)` with the reference's interface (reference models.py:351-453), backed by a
+maua_plan (the fused sm_100a forward / backward launch sequence in csrc/plan.cu).
+
+What is kept from the reference:
+  * the channel lists and layer-name tables (models.py:135-139, :140-243) for the VGG-16 / VGG-19 stacks;
+  * checkpoint loading: `torch.load(model_file)` of a torchvision-style state dict with `features.N.weight/bias`
+    keys, `disable_check` => non-strict (models.py:343);
+  * module splicing order TVLoss, temporal ContentLoss, then ContentLoss / StyleLoss after the named layers, and
+    truncation after the last requested tap (models.py:369-436, :382);
+  * the returned `net` is callable on a [1,3,H,W] image, carries `.content_losses / .style_losses / .tv_losses /
+    .temporal_losses` (models.py:447-451) and leaves 0-dim autograd-connected tensors in each module's `.loss`.
+What is different: `net` is a single nn.Module (B200Net), not an nn.Sequential of torch layers; the weights live in
+GEMM layout inside the plan.  Only `relu*` taps are supported -- the reference's `conv*` taps alias a buffer that the
+in-place ReLU overwrites (SURVEY.md section 8a hazard 1), so they never meant what they say.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .loss import ContentLoss, ScaleGradients, StyleLoss, TVLoss  # noqa: F401  (models.py:13 `from loss import *`)
+
+# models.py:135-139
+channel_list = {
+    "VGG-16": [64, 64, "P", 128, 128, "P", 256, 256, 256, "P", 512, 512, 512, "P", 512, 512, 512, "P"],
+    "VGG-19": [64, 64, "P", 128, 128, "P", 256, 256, 256, 256, "P", 512, 512, 512, 512, "P", 512, 512, 512, 512, "P"],
+}
+
+
+def _layer_names(channels):
+    """models.py:140-243 (vgg16_dict / vgg19_dict): conv{b}_{i}, relu{b}_{i}, pool{b}."""
+    names = {"C": [], "R": [], "P": []}
+    block, idx = 1, 1
+    for c in channels:
+        if c == "P":
+            names["P"].append(f"pool{block}")
+            block, idx = block + 1, 1
+        else:
+            names["C"].append(f"conv{block}_{idx}")
+            names["R"].append(f"relu{block}_{idx}")
+            idx += 1
+    return names
+
+
+vgg16_dict = _layer_names(channel_list["VGG-16"])
+vgg19_dict = _layer_names(channel_list["VGG-19"])
+
+_MODES = {"none": _lib.MODE_NONE, "capture": _lib.MODE_CAPTURE, "loss": _lib.MODE_LOSS}
+
+
+def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bool):
+    """models.py:246-347 for the architectures this backend accelerates.  Returns (channels, layer names, state dict)."""
+    name = str(model_file).lower()
+    if "vgg19" in name or "vgg-19" in name:
+        channels, layer_list = channel_list["VGG-19"], vgg19_dict
+    elif "vgg16" in name or "vgg-16" in name:
+        channels, layer_list = channel_list["VGG-16"], vgg16_dict
+    else:
+        raise ValueError(
+            f"maua_style_b200 accelerates the VGG-19 / VGG-16 feature stacks only (model_file={model_file!r}); "
+            "use the reference's torch modules for other model families")
+    if pooling not in ("max", "avg"):
+        raise ValueError("Unrecognized pooling argseter")  # models.py:124
+    sd = torch.load(model_file, map_location="cpu")
+    return channels, layer_list, sd
+
+
+def _conv_params(sd, channels, disable_check):
+    """(weight, bias) per conv, from torchvision-style keys features.{k}.weight (k counts conv/relu/pool slots)."""
+    params, k, cin = [], 0, 3
+    for c in channels:
+        if c == "P":
+            k += 1
+            continue
+        wk, bk = f"features.{k}.weight", f"features.{k}.bias"
+        if wk not in sd or bk not in sd:
+            raise KeyError(f"checkpoint is missing {wk} / {bk}")
+        w, b = sd[wk].float(), sd[bk].float()
+        if tuple(w.shape) != (c, cin, 3, 3):
+            raise ValueError(f"{wk} has shape {tuple(w.shape)}, expected {(c, cin, 3, 3)}")
+        params.append((w, b))
+        cin = c
+        k += 2
+    return params
+
+
+class _PlanFunction(torch.autograd.Function):
+    """net(pastiche) as one autograd node: forward -> vector of module losses, backward -> pastiche.grad."""
+
+    @staticmethod
+    def forward(ctx, x, net):
+        ctx.net = net
+        ctx.token = net._forward_plan(x, keep=True)
+        return net._loss_vec.clone()
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        net = ctx.net
+        if ctx.token != net._fwd_token:
+            raise RuntimeError("maua_style_b200: backward() called after another forward pass of the same network")
+        return net._backward_plan(grad_losses), None
+
+
+class B200Net(nn.Module):
+    """The truncated feature stack with its loss modules, executed by libmaua_b200 (csrc/plan.cu)."""
+
+    def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device):
+        super().__init__()
+        _lib.require_gpu()
+        self._lib = _lib.load()
+        self.device = device
+        self.entries = entries
+        self.taps = taps  # [(relu_index, module)] ordered by relu index
+        self.tv_mod = tv_mod
+        self.temporal_mod = temporal_mod
+        # parameters are kept (frozen) so that net.parameters() / state inspection behave like the reference's net
+        self.weights = nn.ParameterList([nn.Parameter(w.to(device).contiguous(), requires_grad=False) for w, _ in params])
+        self.biases = nn.ParameterList([nn.Parameter(b.to(device).contiguous(), requires_grad=False) for _, b in params])
+        desc = _lib.NetDesc()
+        desc.n_entries = len(entries)
+        ci = 0
+        for i, c in enumerate(entries):
+            desc.channels[i] = c
+            if c > 0:
+                desc.weights[i] = self.weights[ci].data_ptr()
+                desc.biases[i] = self.biases[ci].data_ptr()
+                ci += 1
+        desc.avg_pool = int(avg_pool)
+        desc.n_taps = len(taps)
+        for t, (ridx, mod) in enumerate(taps):
+            desc.tap_relu_index[t] = ridx
+            desc.tap_kind[t] = _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT
+        self._plan = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self._lib.maua_plan_create(device.index or 0, C.byref(desc), C.byref(self._plan)), "maua_plan_create")
+        self._n_slots = len(taps) + 2
+        self._loss_vec = torch.zeros(self._n_slots, device=device)
+        self._coefs = torch.zeros(self._n_slots, device=device)
+        self._fwd_token = 0
+        self._tap_channels = []
+        ch = [c for c in entries if c > 0]
+        for ridx, _ in taps:
+            self._tap_channels.append(ch[ridx])
+        self.content_losses, self.style_losses, self.tv_losses, self.temporal_losses = [], [], [], []
+
+    def __del__(self):
+        plan, self._plan = getattr(self, "_plan", None), None
+        if plan:
+            try:
+                self._lib.maua_plan_destroy(plan)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------------------------------------
+    def set_impl(self, impl: int):
+        _lib.check(self._lib.maua_plan_set_impl(self._plan, impl), "maua_plan_set_impl")
+
+    def device_bytes(self) -> int:
+        return int(self._lib.maua_plan_device_bytes(self._plan))
+
+    def last_launches(self):
+        f, b = C.c_int(), C.c_int()
+        _lib.check(self._lib.maua_plan_last_launches(self._plan, C.byref(f), C.byref(b)))
+        return f.value, b.value
+
+    def slot_modules(self):
+        """Loss modules in plan slot order: taps..., TV, temporal (None where absent)."""
+        return [m for _, m in self.taps] + [self.tv_mod, self.temporal_mod]
+
+    def _tap_hw(self, H, W, ridx):
+        h, w, conv = H, W, -1
+        for c in self.entries:
+            if c == 0:
+                h, w = h // 2, w // 2
+            else:
+                conv += 1
+                if conv == ridx:
+                    return h, w
+        raise AssertionError
+
+    def _forward_plan(self, x: torch.Tensor, keep: bool) -> int:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected a [1,3,H,W] image, got {tuple(x.shape)}")
+        if x.shape[0] != 1:
+            raise NotImplementedError("maua_style_b200 supports batch size 1 only (img_vid windows are out of scope)")
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("internal: image must be a contiguous fp32 CUDA tensor")
+        H, W = int(x.shape[2]), int(x.shape[3])
+        tio = (_lib.TapIO * max(len(self.taps), 1))()
+        for t, (ridx, mod) in enumerate(self.taps):
+            io = tio[t]
+            io.mode = _MODES[mod.mode]
+            C_ = self._tap_channels[t]
+            if isinstance(mod, StyleLoss):
+                io.use_covariance = int(bool(mod.use_covariance))
+                vsf = float(mod.video_style_factor)
+                io.value_scale = float(mod.strength) * (1.0 + (vsf if vsf > 0 else 0.0))
+                if mod.mode == "capture":
+                    fresh = mod.target.nelement() == 0
+                    if fresh:
+                        mod.target = torch.zeros(C_, C_, device=self.device)
+                    mod.video_target = mod.target  # identical for B = 1 (loss.py:164-175)
+                    mod.loss = 0
+                    io.capture_weight = float(mod.blend_weight)
+                    io.capture_accumulate = 0 if fresh else 1
+                if mod.mode != "none":
+                    if not (mod.target.is_cuda and mod.target.dtype == torch.float32 and mod.target.is_contiguous()):
+                        mod.target = mod.target.to(self.device, torch.float32).contiguous()
+                    io.target = mod.target.data_ptr()
+                    io.target_elems = mod.target.numel()
+            else:
+                io.value_scale = float(mod.strength)
+                h, w = self._tap_hw(H, W, ridx)
+                if mod.mode == "capture":
+                    # NCHW-shaped view over NHWC memory (channels_last): .size() matches the reference's target
+                    mod.target = torch.empty(1, h, w, C_, device=self.device).permute(0, 3, 1, 2)
+                if mod.mode != "none" and mod.target.nelement() != 0:
+                    tgt = mod.target
+                    if tuple(tgt.shape[1:]) == (C_, h, w):
+                        if not (tgt.is_cuda and tgt.permute(0, 2, 3, 1).is_contiguous()):
+                            tgt = tgt.to(self.device, torch.float32).contiguous(memory_format=torch.channels_last)
+                            mod.target = tgt
+                        io.target = tgt.data_ptr()
+                        io.target_elems = tgt.numel()
+                    # else: shape mismatch -> module is skipped, as loss.py:44 does
+        iio = _lib.ImageIO()
+        if self.tv_mod is not None:
+            iio.tv_mode = _lib.MODE_LOSS  # TVLoss.loss is assigned on every forward (loss.py:232)
+            iio.tv_strength = float(self.tv_mod.strength)
+        tm = self.temporal_mod
+        if tm is not None and tm.mode != "none":
+            iio.temporal_mode = _MODES[tm.mode]
+            iio.temporal_strength = float(tm.strength)
+            if tm.mode == "capture":
+                tm.target = torch.empty(1, 3, H, W, device=self.device)
+            if tm.target.nelement() != 0 and tuple(tm.target.shape[1:]) == (3, H, W):
+                if not (tm.target.is_cuda and tm.target.is_contiguous()):
+                    tm.target = tm.target.to(self.device, torch.float32).contiguous()
+                iio.temporal_target = tm.target.data_ptr()
+                iio.temporal_target_elems = tm.target.numel()
+                if tm.weights is not None:
+                    wts = tm.weights
+                    if wts.numel() != H * W:
+                        raise ValueError("temporal weights must have H*W elements ([1,1,H,W])")
+                    if not (wts.is_cuda and wts.dtype == torch.float32 and wts.is_contiguous()):
+                        wts = wts.to(self.device, torch.float32).contiguous()
+                        tm.weights = wts
+                    iio.temporal_weights = wts.data_ptr()
+        self._keepalive = (x, tio, iio)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.maua_plan_forward(self._plan, _lib.ptr(x), H, W, tio, C.byref(iio), _lib.ptr(self._loss_vec),
+                                                   int(keep), _lib.stream_ptr()), "maua_plan_forward")
+        self._fwd_token += 1
+        return self._fwd_token
+
+    def _backward_plan(self, grad_losses: torch.Tensor) -> torch.Tensor:
+        x = self._keepalive[0]
+        n = self._n_slots
+        strength = (C.c_float * n)()
+        vsf = (C.c_float * n)()
+        normalize = (C.c_int * n)()
+        kind = (C.c_int * n)()
+        for i, mod in enumerate(self.slot_modules()):
+            if mod is None:
+                continue
+            strength[i] = float(mod.strength)
+            if isinstance(mod, StyleLoss):
+                kind[i], vsf[i], normalize[i] = 0, float(mod.video_style_factor), int(bool(mod.normalize))
+            elif isinstance(mod, ContentLoss):
+                kind[i], normalize[i] = 1, int(bool(mod.normalize))
+            else:
+                kind[i] = 2
+        up = grad_losses.detach().to(self.device, torch.float32).contiguous()
+        grad = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.maua_loss_grad_coefs(_lib.ptr(up), _lib.ptr(self._coefs), n, strength, vsf, normalize, kind,
+                                                      _lib.stream_ptr()), "maua_loss_grad_coefs")
+            _lib.check(self._lib.maua_plan_backward(self._plan, _lib.ptr(self._coefs), _lib.ptr(grad), _lib.stream_ptr()),
+                       "maua_plan_backward")
+        return grad
+
+    def _live_slots(self):
+        """Slots whose module produced a loss in the last forward (mode 'loss' and not skipped)."""
+        live = []
+        for i, mod in enumerate(self.slot_modules()):
+            if mod is None:
+                continue
+            if isinstance(mod, TVLoss):
+                live.append(i)
+            elif mod.mode == "loss" and mod.target.nelement() != 0:
+                live.append(i)
+        return live
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        x = input
+        if not x.is_cuda or x.device != self.device:
+            x = x.to(self.device)
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        any_loss = any(m is not None and getattr(m, "mode", "none") == "loss" for m in self.slot_modules())
+        if any_loss and x.requires_grad and torch.is_grad_enabled():
+            vec = _PlanFunction.apply(x, self)
+        else:
+            with torch.no_grad():
+                self._forward_plan(x.detach(), keep=False)
+            vec = self._loss_vec.clone()
+        # hand the module losses out the way the reference modules do: `.loss` accumulates (loss.py:157,181)
+        for i in self._live_slots():
+            mod = self.slot_modules()[i]
+            if isinstance(mod, TVLoss):
+                mod.loss = vec[i]  # assigned, not accumulated (loss.py:232)
+            elif isinstance(mod, ContentLoss):
+                mod.loss = vec[i]  # loss.py:49 resets to 0 before accumulating over the batch
+            else:
+                mod.loss = mod.loss + vec[i]
+        return input
+
+    # -- debugging / tests ---------------------------------------------------------------------------------
+    def tap_feature(self, t: int) -> torch.Tensor:
+        """Feature map of tap t from the last forward as an NCHW tensor (copy)."""
+        h, w, c = C.c_int(), C.c_int(), C.c_int()
+        null = C.c_void_p(0)
+        _lib.check(self._lib.maua_plan_tap_feature(self._plan, t, null, C.byref(h), C.byref(w), C.byref(c), _lib.stream_ptr()))
+        out = torch.empty(1, h.value, w.value, c.value, device=self.device)
+        _lib.check(self._lib.maua_plan_tap_feature(self._plan, t, _lib.ptr(out), C.byref(h), C.byref(w), C.byref(c),
+                                                   _lib.stream_ptr()))
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    def tap_gram(self, t: int) -> torch.Tensor:
+        """Normalised Gram / covariance matrix of style tap t from the last forward (copy)."""
+        c = C.c_int()
+        _lib.check(self._lib.maua_plan_tap_gram(self._plan, t, C.c_void_p(0), C.byref(c), _lib.stream_ptr()))
+        out = torch.empty(c.value, c.value, device=self.device)
+        _lib.check(self._lib.maua_plan_tap_gram(self._plan, t, _lib.ptr(out), C.byref(c), _lib.stream_ptr()))
+        return out
+
+
+def _device_from_args(args) -> torch.device:
+    gpu = str(getattr(args, "gpu", "0")).lower()
+    if "c" in gpu.split(",")[0]:
+        raise RuntimeError("maua_style_b200 has no CPU path: --gpu c is not supported (use the reference's torch modules)")
+    return torch.device("cuda", int(gpu.split(",")[0]))
+
+
+def load_model(args):
+    """models.py:351-453."""
+    channels, layer_list, sd = select_model(str(args.model_file), args.pooling,
+                                            getattr(args, "verbose", False), getattr(args, "disable_check", False))
+    params_all = _conv_params(sd, channels, getattr(args, "disable_check", False))
+    device = _device_from_args(args)
+    content_layers = args.content_layers.split(",")
+    style_layers = args.style_layers.split(",")
+    for nm in content_layers + style_layers:
+        if nm.startswith("conv"):
+            raise ValueError(f"tap {nm!r}: only relu* taps are supported (conv* taps alias the in-place ReLU buffer in the "
+                             "reference, models.py:130)")
+
+    content_losses, style_losses, tv_losses, temporal_losses = [], [], [], []
+    n_modules = 0
+    tv_mod = temporal_mod = None
+    if args.tv_weight > 0:
+        tv_mod = TVLoss(args.tv_weight)
+        tv_mod.name = f"tv {n_modules}"
+        n_modules += 1
+        tv_losses.append(tv_mod)
+    if args.temporal_weight > 0:
+        temporal_mod = ContentLoss(args.temporal_weight, args.normalize_gradients)
+        temporal_mod.name = f"temporal {n_modules}"
+        n_modules += 1
+        temporal_losses.append(temporal_mod)
+
+    entries, taps, params = [], [], []
+    next_content_idx, next_style_idx, r, conv_i = 1, 1, 0, 0
+    for c in channels:
+        if not (next_content_idx <= len(content_layers) or next_style_idx <= len(style_layers)):
+            break  # models.py:382: nothing below the last requested tap is built
+        if c == "P":
+            entries.append(0)
+            n_modules += 1
+            continue
+        entries.append(c)
+        params.append(params_all[conv_i])
+        conv_i += 1
+        n_modules += 2  # conv + relu
+        name = layer_list["R"][r]
+        if name in content_layers:
+            if getattr(args, "verbose", False):
+                print("Setting up content layer " + str(n_modules) + ": " + name)
+            mod = ContentLoss(args.content_weight, args.normalize_gradients)
+            mod.name = f"cont {n_modules}"
+            n_modules += 1
+            content_losses.append(mod)
+            taps.append((r, mod))
+            next_content_idx += 1
+        if name in style_layers:
+            if getattr(args, "verbose", False):
+                print("Setting up style layer " + str(n_modules) + ": " + name)
+            mod = StyleLoss(args.style_weight, args.use_covariance, args.normalize_gradients,
+                            video_style_factor=args.video_style_factor, shift_factor=getattr(args, "shift_factor", 0))
+            mod.name = f"style {n_modules}"
+            n_modules += 1
+            style_losses.append(mod)
+            taps.append((r, mod))
+            next_style_idx += 1
+        r += 1
+    while entries and entries[-1] == 0:
+        entries.pop()  # a trailing pool feeds nothing
+
+    if getattr(args, "multidevice", False):
+        from .parallel import setup_multi_device  # layer-wise split over NVLink peers (models.py:537-566)
+
+        return setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses,
+                                  tv_losses, temporal_losses)
+
+    net = B200Net(entries, params, args.pooling == "avg", taps, tv_mod, temporal_mod, device)
+    net.content_losses = content_losses
+    net.style_losses = style_losses
+    net.tv_losses = tv_losses
+    net.temporal_losses = temporal_losses
+    return net, content_losses + style_losses + tv_losses + temporal_losses

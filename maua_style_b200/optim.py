@@ -1,0 +1,204 @@
+"""`optimize(content, styles, init, num_iters, args, net=None, losses=None)` with the reference's interface
+(reference optim.py:111-255) on top of the fused sm_100a plan.
+
+Kept from the reference: the target-capture protocol (optim.py:22-66), per-size scaling args (optim.py:93-108), the
+Adam loop that runs num_iters + 1 evaluate-and-step rounds (`while i[0] <= iters`, optim.py:240) and the single
+L-BFGS `step()` of num_iters iterations without line search (optim.py:180-191), `--normalize_weights`
+(optim.py:176-178), `--print_iter` / `--save_iter` hooks, and the CPU tensor it returns (optim.py:249).
+
+Different by design: the loop body never synchronises with the host.  feval is two C calls (maua_plan_forward /
+maua_plan_backward), the Adam / L-BFGS pixel update is our own kernel (maua_adam_step / maua_lbfgs_step) and the
+per-module `.cpu().item()` bookkeeping of optim.py:210 (written to a list nobody reads) only happens when
+`--print_iter` asks for a number.  The reference's generic path also still works: `net(pastiche)` is autograd
+aware, so `torch.optim.Adam([pastiche])` with the reference's own closure runs unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import sys
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, models
+
+
+def set_content_targets(net, content_image, args=None):
+    """optim.py:22-32."""
+    for i in net.content_losses:
+        i.mode = "capture"
+    net(content_image)
+    for i in net.content_losses:
+        i.mode = "none"
+
+
+def set_temporal_targets(net, warp_image, warp_weights=None, args=None):
+    """optim.py:35-47."""
+    for i in net.temporal_losses:
+        i.mode = "capture"
+        if warp_weights is not None:
+            i.weights = warp_weights.to(net.device, torch.float32).contiguous()
+    net(warp_image)
+    for i in net.temporal_losses:
+        i.mode = "none"
+
+
+def set_style_targets(net, style_images, args):
+    """optim.py:50-66."""
+    for j in net.style_losses:
+        j.reset_targets()
+        j.mode = "capture"
+    for i, image in enumerate(style_images):
+        for j in net.style_losses:
+            j.blend_weight = args.style_blend_weights[i]
+        net(image)
+    for j in net.style_losses:
+        j.mode = "none"
+
+
+def set_model_args(args, current_size):
+    """optim.py:93-108."""
+    with open(args.scaling_args, "r") as f:
+        scaling = json.load(f)
+    found = False
+    params = {}
+    for size, params in scaling.items():
+        if int(size) < current_size:
+            continue
+        if len(str(args.gpu).split(",")) < len(str(params["gpu"]).split(",")):
+            continue
+        found = True
+        break
+    if not found:
+        print("Warning: no model configuration found for this size, out of memory error is likely...")
+    for key, param in params.items():
+        args.__dict__[key] = param
+
+
+class PixelOptimizer:
+    """The Adam / L-BFGS pixel update of optim.py:180-196 as device kernels with device-resident state."""
+
+    def __init__(self, pastiche: torch.Tensor, kind: str, lr: float = 1.0, history: int = 100,
+                 tolerance_change: float = -1.0):
+        self.lib = _lib.load()
+        self.p = pastiche
+        self.kind = kind
+        self.lr = float(lr)
+        self.step_count = 0
+        self._state = None
+        n = pastiche.numel()
+        if kind == "adam":
+            self.m = torch.zeros_like(pastiche)
+            self.v = torch.zeros_like(pastiche)
+        elif kind == "lbfgs":
+            self._state = C.c_void_p()
+            with torch.cuda.device(pastiche.device):
+                _lib.check(self.lib.maua_lbfgs_create(C.c_long(n), int(history), C.c_float(1.0), C.c_float(tolerance_change),
+                                                      C.byref(self._state)), "maua_lbfgs_create")
+        else:
+            raise ValueError(f"unknown optimizer {kind!r}")
+
+    def step(self, grad: torch.Tensor) -> None:
+        self.step_count += 1
+        with torch.cuda.device(self.p.device):
+            if self.kind == "adam":
+                _lib.check(self.lib.maua_adam_step(_lib.ptr(self.p), _lib.ptr(grad), _lib.ptr(self.m), _lib.ptr(self.v),
+                                                   C.c_long(self.p.numel()), C.c_float(self.lr), C.c_float(0.9),
+                                                   C.c_float(0.999), C.c_float(1e-8), self.step_count, _lib.stream_ptr()),
+                           "maua_adam_step")
+            else:
+                _lib.check(self.lib.maua_lbfgs_step(self._state, _lib.ptr(self.p), _lib.ptr(grad), _lib.stream_ptr()),
+                           "maua_lbfgs_step")
+
+    def close(self):
+        if self._state:
+            self.lib.maua_lbfgs_destroy(self._state)
+            self._state = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def feval(net, pastiche: torch.Tensor, ones: Optional[torch.Tensor] = None):
+    """optim.py:201-221 without the host syncs: returns (loss vector on the device, pastiche gradient)."""
+    net._forward_plan(pastiche, keep=True)
+    live = net._live_slots()
+    up = torch.zeros(net._n_slots, device=net.device)
+    up[live] = 1.0
+    grad = net._backward_plan(up)
+    return net._loss_vec, grad
+
+
+def optimize(content, styles, init, num_iters, args, net=None, losses=None):
+    """optim.py:111-255 for transfer types img_img / vid_img (one window, batch 1)."""
+    if "_vid" in getattr(args, "transfer_type", "img_img"):
+        raise NotImplementedError("img_vid (windowed video-style) optimisation is out of scope for the B200 backend "
+                                  "(SURVEY.md section 8f rank 4); use the reference's torch path")
+    if net is None or losses is None:
+        set_model_args(args, max(*init.shape))
+        net, losses = models.load_model(args)
+    device = net.device
+
+    set_content_targets(net, content.to(device, torch.float32), args)
+    set_style_targets(net, [s.to(device, torch.float32) for s in styles], args)
+    for mod in losses:
+        mod.mode = "loss"
+
+    # optim.py:173: the pastiche lives on the device for the whole optimisation
+    pastiche = init.detach().to(device, torch.float32).contiguous().clone()
+
+    # optim.py:176-178 (only once, strengths are not reset)
+    if getattr(args, "normalize_weights", False):
+        for i in net.content_losses + net.style_losses + net.temporal_losses:
+            i.strength = i.strength / max(i.target.size())
+
+    if args.optimizer == "lbfgs":
+        hist = getattr(args, "lbfgs_num_correction", 100)
+        opt = PixelOptimizer(pastiche, "lbfgs", history=hist, tolerance_change=float(getattr(args, "lbfgs_tolerance_change", -1)))
+        evals = num_iters  # one step() = num_iters closure evaluations and updates
+    elif args.optimizer == "adam":
+        opt = PixelOptimizer(pastiche, "adam", lr=args.learning_rate)
+        evals = num_iters + 1  # optim.py:240 `while i[0] <= iters`
+    else:
+        raise ValueError(f"unknown optimizer {args.optimizer!r}")
+
+    print_iter = int(getattr(args, "print_iter", 0) or 0)
+    save_iter = int(getattr(args, "save_iter", 0) or 0)
+    live = None
+    up = torch.zeros(net._n_slots, device=device)
+    for it in range(1, evals + 1):
+        net._forward_plan(pastiche, keep=True)
+        if live is None:
+            live = net._live_slots()
+            up[live] = 1.0
+        grad = net._backward_plan(up)
+        if print_iter > 0 and it % print_iter == 0 and getattr(args, "verbose", False):
+            total = float(net._loss_vec[live].sum())
+            print(f"Iteration {it} / {args.num_iters}, Loss: {total}")
+        if save_iter > 0 and (it % save_iter == 0 or it == num_iters):
+            _save_intermediate(pastiche, args, it, num_iters)
+        opt.step(grad)
+    for mod in losses:
+        mod.loss = 0
+    out = pastiche.cpu()
+    opt.close()
+    return out
+
+
+def _save_intermediate(pastiche, args, it, num_iters):
+    """optim.py:230-236 hands the image to load.save_tensor_to_file (host I/O, outside the hot path)."""
+    saver = getattr(args, "save_fn", None)
+    if saver is None:
+        try:
+            import load  # the reference's I/O module, when running inside the reference tree
+
+            saver = lambda img, a, i, size: load.save_tensor_to_file(img, a, i, size)
+        except Exception:
+            return
+    saver(pastiche.detach().cpu(), args, it if it != num_iters else None, pastiche.size(3))

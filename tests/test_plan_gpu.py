@@ -1,0 +1,213 @@
+"""End-to-end parity of the CUDA path (reference-shaped API -> C ABI -> sm_100a kernels) against
+
+  (1) the golden vectors the UNMODIFIED reference produced (tests/golden/*.npz), and
+  (2) the CPU oracle on the same seeded inputs (per-tap features, Grams, losses, image gradient).
+
+Tolerances (floating point; TF32 operands with FP32 accumulate, stated per layer as north_star asks):
+  features   relative L2 <= 1e-3 at relu1_1..relu3_1, 2e-3 at relu4_1..relu5_1 (error grows ~sqrt(depth): each conv
+             rounds both operands to 10-bit mantissas, eps 2^-11)
+  Grams      relative L2 <= 2e-3 (inherits the feature error; the SYRK itself is exact in fp32 on stored features)
+  losses     relative <= 1e-2 per module (squared differences of Grams amplify the feature error twice)
+  gradient   relative L2 <= 2e-2 on the image gradient (26 TF32 GEMMs deep); compared in norm, not element-wise,
+             because max-pool argmax flips move single gradient entries
+  optimised image after N iterations: PSNR >= 40 dB against the reference's result
+"""
+import os
+
+import pytest
+import torch
+
+from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["adam_gram_64", "adam_gram_90x122", "lbfgs_gram_64", "adam_cov_2styles_96x128", "adam_nonorm_novsf_avg_64",
+         "adam_normweights_notemporal_64"]
+FEATURE_TOL = {"relu1_1": 1e-3, "relu2_1": 1e-3, "relu3_1": 1e-3, "relu4_1": 2e-3, "relu4_2": 2e-3, "relu5_1": 2e-3}
+REPORT = os.environ.get("MAUA_TEST_REPORT")  # optional path: append measured errors (used to write DESIGN.md tables)
+
+
+def report(line):
+    print(line)
+    if REPORT:
+        with open(REPORT, "a") as f:
+            f.write(line + "\n")
+
+
+@pytest.fixture(scope="module")
+def ckpt(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ckpt")
+    path = d / "vgg19-random.pth"
+    params = save_checkpoint(path)
+    return path, d, params
+
+
+def build(ckpt, meta):
+    from maua_style_b200 import models
+
+    path, d, params = ckpt
+    over = dict(meta["over"])
+    args = make_args(path, d, **over)
+    if "style_blend_weights" not in meta["over"]:
+        args.style_blend_weights = [1.0 / len(meta["style_hw"])] * len(meta["style_hw"])
+    net, losses = models.load_model(args)
+    return args, net, losses, params
+
+
+def oracle_cfg(meta):
+    over = dict(meta["over"])
+    cfg = O.StyleConfig(content_weight=5.0)
+    cfg.optimizer = over.pop("optimizer", "adam")
+    cfg.normalize_gradients = not over.pop("no_grad_norm", False)
+    if "style_blend_weights" in over:
+        cfg.style_blend_weights = [float(x) for x in over.pop("style_blend_weights").split(",")]
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_feval_matches_reference_golden_and_oracle(name, ckpt):
+    from maua_style_b200 import optim
+
+    z, meta = load_golden(name)
+    content, styles, init = golden_inputs(meta)
+    args, net, losses, params = build(ckpt, meta)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, styles, args)
+    for m in losses:
+        m.mode = "loss"
+
+    # --- oracle on the same inputs (CPU, fp32) ---
+    cfg = oracle_cfg(meta)
+    onet = O.OracleNet(params, cfg)
+    O.set_content_targets(onet, content)
+    O.set_style_targets(onet, styles, cfg.blend(len(styles)))
+    for m in onet.losses:
+        m.mode = "loss"
+
+    # blended style targets vs the reference's
+    for i, (m, om) in enumerate(zip(net.style_losses, onet.style_losses)):
+        err = rel(m.target, om.target)
+        report(f"{name} style_target[{i}] rel {err:.2e}")
+        assert err < 2e-3
+        blk = torch.from_numpy(z[f"style_target_{i}_block"])
+        assert rel(m.target[:16, :16], blk) < 5e-3
+
+    # --- feval through the reference-shaped autograd interface ---
+    x = init.clone().cuda().requires_grad_(True)
+    net(x)
+    total = 0
+    vals = []
+    for m in losses:
+        if isinstance(m.loss, int):
+            vals.append(0.0)
+            continue
+        vals.append(float(m.loss))
+        total = total + m.loss
+    total.backward()
+    for m in losses:
+        m.loss = 0
+
+    # per-tap features vs oracle
+    taps = {}
+    onet(init.clone(), taps=taps)
+    for m in onet.losses:
+        m.loss = 0
+    relu_names = O.VGG19_RELU_NAMES
+    for t, (ridx, mod) in enumerate(net.taps):
+        nm = relu_names[ridx]
+        err = rel(net.tap_feature(t), taps[nm])
+        report(f"{name} feature {nm} rel {err:.2e}")
+        assert err < FEATURE_TOL[nm], (nm, err)
+
+    # per-module losses vs the reference's golden values
+    keys = sorted([k for k in z.files if k.startswith("loss_")], key=lambda k: int(k.split("_")[1]))
+    assert len(keys) == len(vals)
+    for k, v in zip(keys, vals):
+        ref = float(z[k])
+        if ref == 0.0:
+            assert v == 0.0
+            continue
+        report(f"{name} {k} got {v:.6e} ref {ref:.6e} rel {abs(v / ref - 1):.2e}")
+        assert abs(v / ref - 1) < 1e-2, (k, v, ref)
+    g_ref = torch.from_numpy(z["grad"])
+    gerr = rel(x.grad, g_ref)
+    report(f"{name} image-gradient rel {gerr:.2e}")
+    assert gerr < 2e-2
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_optimize_matches_reference_golden(name, ckpt):
+    from maua_style_b200 import optim
+
+    z, meta = load_golden(name)
+    content, styles, init = golden_inputs(meta)
+    args, net, losses, _ = build(ckpt, meta)
+    out = optim.optimize(content, styles, init.clone(), meta["iters"], args, net, losses)
+    ref = torch.from_numpy(z["optimized"])
+    assert out.shape == ref.shape and out.device.type == "cpu"
+    p = O.psnr(out, ref)
+    report(f"{name} optimize {meta['iters']} iters PSNR {p:.1f} dB")
+    assert p > 40.0
+
+
+def test_tc_and_simt_plans_agree(ckpt):
+    """The tcgen05 plan and the naive SIMT plan (same contract, different code) produce the same gradient."""
+    from maua_style_b200 import _lib, optim
+
+    z, meta = load_golden("adam_gram_90x122")
+    content, styles, init = golden_inputs(meta)
+    grads = []
+    for impl in (_lib.MAUA_IMPL_TC, _lib.MAUA_IMPL_REF):
+        args, net, losses, _ = build(ckpt, meta)
+        net.set_impl(impl)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, styles, args)
+        for m in losses:
+            m.mode = "loss"
+        _, g = optim.feval(net, init.clone().cuda())
+        grads.append(g.clone())
+    err = rel(grads[0], grads[1])
+    report(f"tc vs simt plan gradient rel {err:.2e}")
+    assert err < 2e-3
+
+
+def test_temporal_loss_and_autograd_interface(ckpt):
+    """vid_img path: set_temporal_targets + weighted temporal ContentLoss (loss.py:46-54) through net(x).backward()."""
+    from maua_style_b200 import optim
+
+    z, meta = load_golden("adam_gram_64")
+    content, styles, init = golden_inputs(meta)
+    args, net, losses, params = build(ckpt, meta)
+    warp = O.synthetic_image(64, 64, seed=9, smooth=True)
+    wts = torch.rand(1, 1, 64, 64, generator=torch.Generator().manual_seed(3))
+    optim.set_temporal_targets(net, warp, wts, args)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, styles, args)
+    for m in losses:
+        m.mode = "loss"
+    x = init.clone().cuda().requires_grad_(True)
+    net(x)
+    total = sum(m.loss for m in losses if not isinstance(m.loss, int))
+    total.backward()
+    vals = [float(m.loss) for m in losses]
+
+    cfg = oracle_cfg(meta)
+    onet = O.OracleNet(params, cfg)
+    O.set_temporal_targets(onet, warp, wts)
+    O.set_content_targets(onet, content)
+    O.set_style_targets(onet, styles, cfg.blend(1))
+    for m in onet.losses:
+        m.mode = "loss"
+    ototal, ovals, ograd = O.feval(onet, init)
+    assert len(vals) == len(ovals)
+    for v, o in zip(vals, ovals):
+        assert abs(v / o - 1) < 1e-2, (v, o)
+    assert rel(x.grad, ograd) < 2e-2
+
+
+def test_no_gpu_fallback_message():
+    from maua_style_b200 import _lib
+
+    _lib.require_gpu()  # must not raise on the GPU box
