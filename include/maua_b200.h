@@ -227,6 +227,12 @@ MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, float* dst, int* 
                                    maua_stream_t stream);
 /* Switch the GEMM-shaped kernels of this plan between MAUA_IMPL_TC and MAUA_IMPL_REF (tests only). */
 MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
+/* Per-launch timing for roofline reports: when enabled, a CUDA event is recorded on the caller's stream after every
+ * launch of forward / backward.  maua_plan_profile_json synchronises the stream and writes a JSON array
+ * [{"name","layer","ms","flops","bytes"}...] (algorithmic FLOPs / bytes per launch) for the last forward + backward
+ * into buf; returns the number of bytes needed (> cap: nothing written) or -1. */
+MAUA_API int maua_plan_set_profile(maua_plan_t* plan, int enable);
+MAUA_API long maua_plan_profile_json(maua_plan_t* plan, char* buf, long cap, maua_stream_t stream);
 /* Number of kernel launches issued by the last forward / backward (for bench.py's gpu_launches). */
 MAUA_API int maua_plan_last_launches(const maua_plan_t* plan, int* forward, int* backward);
 

@@ -92,6 +92,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.maua_reduce_workspace_bytes.restype = C.c_size_t
     lib.maua_plan_device_bytes.restype = C.c_size_t
     lib.maua_plan_destroy.restype = None
+    lib.maua_plan_profile_json.restype = C.c_long
     lib.maua_lbfgs_destroy.restype = None
     _lib = lib
     return lib

@@ -13,7 +13,9 @@
 //   consumer is a pool     : Gp = dgrad_c(Gm_c) ; Gm_e = mask( unpool(Gp) + tap gradients at e )
 //   e is the last entry    : Gm_e = mask( tap gradients at e )            (aux-GEMM-only launch)
 // and finally pastiche.grad = conv1_1 dgrad(Gm_0) + TV + temporal terms (conv_edge.cu).
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "conv_tc.cuh"
@@ -113,7 +115,25 @@ struct maua_plan {
     maua_image_io img_io;
     float factors[MAUA_MAX_TAPS + 2];
     int launches_fwd = 0, launches_bwd = 0;
+    // optional per-launch timing (bench.py roofline): one event after every launch group on the caller's stream
+    struct Prof { const char* name; int layer; double flops, bytes; cudaEvent_t ev; };
+    bool profile = false;
+    std::vector<Prof> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
 };
+
+static void prof_mark(maua_plan* p, cudaStream_t st, const char* name, int layer, double flops, double bytes) {
+    if (!p->profile) return;
+    if (p->ev_used == p->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        p->ev_pool.push_back(ev);
+    }
+    cudaEvent_t ev = p->ev_pool[p->ev_used++];
+    cudaEventRecord(ev, st);
+    p->prof.push_back({name, layer, flops, bytes, ev});
+}
 
 namespace {
 
@@ -330,6 +350,34 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
     return MAUA_OK;
 }
 
+MAUA_API int maua_plan_set_profile(maua_plan_t* p, int enable) {
+    MAUA_REQUIRE(p, "maua_plan_set_profile: null plan");
+    p->profile = enable != 0;
+    p->prof.clear();
+    p->ev_used = 0;
+    return MAUA_OK;
+}
+
+MAUA_API long maua_plan_profile_json(maua_plan_t* p, char* buf, long cap, maua_stream_t stream) {
+    if (!p || !buf || cap < 3) return -1;
+    cudaStreamSynchronize((cudaStream_t)stream);
+    std::string out = "[";
+    for (size_t i = 1; i < p->prof.size(); ++i) {
+        const auto& r = p->prof[i];
+        if (!strncmp(r.name, "begin", 5)) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->prof[i - 1].ev, r.ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        char line[256];
+        snprintf(line, sizeof(line), "%s{\"name\":\"%s\",\"layer\":%d,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
+                 out.size() > 1 ? "," : "", r.name, r.layer, ms, r.flops, r.bytes);
+        out += line;
+    }
+    out += "]";
+    if ((long)out.size() + 1 > cap) return (long)out.size() + 1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (long)out.size() + 1;
+}
+
 MAUA_API int maua_plan_last_launches(const maua_plan_t* p, int* fwd, int* bwd) {
     MAUA_REQUIRE(p, "maua_plan_last_launches: null plan");
     if (fwd) *fwd = p->launches_fwd;
@@ -357,12 +405,16 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
     memset(p->factors, 0, sizeof(p->factors));
     if (iio) p->img_io = *iio; else memset(&p->img_io, 0, sizeof(p->img_io));
     const long img_elems = 3L * H * W;
+    p->prof.clear();
+    p->ev_used = 0;
+    prof_mark(p, st, "begin_fwd", -1, 0, 0);
 
     // ---- image-side modules: TVLoss, temporal ContentLoss ----
     if (p->img_io.tv_mode == MAUA_MODE_LOSS) {
         MAUA_REQUIRE(losses_out, "losses_out is required in loss mode");
         if ((rc = tv_value_launch(image, 3, H, W, p->img_io.tv_strength, losses_out + nt, rs, st))) return rc;
         p->launches_fwd++;
+        prof_mark(p, st, "tv_value", -1, 0, 4.0 * img_elems);
         p->factors[nt] = 1.f;
     }
     bool temporal_active = false;
@@ -379,6 +431,7 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
                                     p->img_io.temporal_strength / (float)img_elems, losses_out + nt + 1, rs, st)))
             return rc;
         p->launches_fwd++;
+        prof_mark(p, st, "temporal_value", -1, 0, 8.0 * img_elems);
         temporal_active = true;
         p->factors[nt + 1] = 2.f / (float)img_elems;
     }
@@ -414,6 +467,12 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
             if (rc) return rc;
         }
         p->launches_fwd++;
+        {
+            const double px = (double)e.H * e.W;
+            if (i == 0) prof_mark(p, st, "conv_first_fwd", i, 2.0 * 27 * e.cout * px, 4.0 * (3 + e.cout) * px);
+            else if (e.pool) prof_mark(p, st, "pool_fwd", i, 0, 4.0 * 5 * e.C * px);
+            else prof_mark(p, st, "conv_fwd", i, 2.0 * 9 * e.cin * e.cout * px, 4.0 * (e.cin + e.cout) * px);
+        }
         cur = e.out; curH = e.H; curW = e.W;
         if (e.pool) continue;
         // loss modules spliced after this ReLU (models.py:403-431)
@@ -427,6 +486,7 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
                              "style tap %d: target must be a [%d,%d] device tensor", t, tp.C, tp.C);
                 if ((rc = gram_launch(e.out, P, tp.C, tp.use_cov, tp.gram, tp.mean, tp.gram_ws, p->impl, st))) return rc;
                 p->launches_fwd += 2 + (tp.use_cov ? 2 : 0);
+                prof_mark(p, st, "gram_syrk", i, (double)tp.C * (tp.C + 1) * P, 4.0 * P * tp.C);
                 if (tp.mode == MAUA_MODE_CAPTURE) {
                     // loss.py:146-151: target (+)= blend_weight * gram   (B = 1)
                     if ((rc = axpby_launch(tp.gram, tp.target, (long)tp.C * tp.C, tio[t].capture_weight,
@@ -439,6 +499,7 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
                                                     rs, st)))
                         return rc;
                     p->launches_fwd++;
+                    prof_mark(p, st, "style_loss", i, 0, 12.0 * tp.C * tp.C);
                     tp.active = true;
                     p->factors[t] = 1.f;
                 }
@@ -454,6 +515,7 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
                                                rs, st)))
                         return rc;
                     p->launches_fwd++;
+                    prof_mark(p, st, "content_loss", i, 0, 8.0 * numel);
                     tp.active = true;
                     p->factors[t] = 2.f / (float)numel;
                 }
@@ -490,6 +552,7 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
     const int H = p->H, W = p->W;
     p->launches_bwd = 0;
     int rc;
+    prof_mark(p, st, "begin_bwd", -1, 0, 0);
 
     // scaled coefficients: content 2/numel, temporal 2/numel
     MAUA_CUDA_CHECK(cudaMemcpyAsync(p->factors_dev, p->factors, (nt + 2) * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -507,6 +570,7 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
             return rc;
         p->launches_bwd += tp.use_cov ? 2 : 1;
     }
+    prof_mark(p, st, "bwd_prep", -1, 0, 0);
 
     auto taps_at = [&](int entry, Tap*& style, Tap*& content, int& content_idx) {
         style = content = nullptr;
@@ -529,7 +593,12 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
     };
     auto run_conv = [&](ConvArgs& a) -> int {
         p->launches_bwd++;
-        return p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
+        const int r = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
+        const double px = (double)a.H * a.W;
+        // algorithmic work: dgrad GEMM + StyleLoss backward GEMM; bytes: gradient in + out, mask / feature read
+        prof_mark(p, st, a.ntaps ? "conv_dgrad" : "tap_grad", a.Cout, 2.0 * (a.ntaps * (double)a.Cin + a.K2) * a.Cout * px,
+                  4.0 * ((a.ntaps ? a.Cin : 0) + 2.0 * a.Cout) * px);
+        return r;
     };
 
     // Walk down from the last executed conv.  `gm` = Gm of the conv entry above the current position.
@@ -557,6 +626,7 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
                 a.ep.cont_f = e.out; a.ep.cont_t = content->target; a.ep.cont_coef = p->coef2 + ci;
                 if ((rc = conv_ref_launch(a, st))) return rc;
                 p->launches_bwd++;
+                prof_mark(p, st, "tap_grad", e.C, 0, 16.0 * e.C * e.H * e.W);
                 gm = a.ep.out;
             } else {
                 ConvArgs a;
@@ -608,6 +678,7 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
             if (outb == gpool || outb == addend) outb = take_buf();
             if ((rc = pool_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, 1, st))) return rc;
             p->launches_bwd++;
+            prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
             gm = outb;
         }
         c = prod;
@@ -629,6 +700,7 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
         Entry& e0 = p->entries[0];
         if ((rc = conv_first_dgrad_launch(gm, e0.w_raw, grad_image, 1, H, W, e0.cout, tail, st))) return rc;
         p->launches_bwd++;
+        prof_mark(p, st, "conv_first_dgrad", 0, 2.0 * 27 * e0.cout * H * W, 4.0 * (e0.cout + 6) * H * W);
     } else {
         // no feature-space loss is active: only TV / temporal terms (or nothing at all)
         MAUA_CUDA_CHECK(cudaMemsetAsync(p->gbuf[0], 0, (size_t)H * W * p->entries[0].cout * sizeof(float), st));

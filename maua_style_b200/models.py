@@ -167,6 +167,20 @@ class B200Net(nn.Module):
         _lib.check(self._lib.maua_plan_last_launches(self._plan, C.byref(f), C.byref(b)))
         return f.value, b.value
 
+    def set_profile(self, enable: bool):
+        _lib.check(self._lib.maua_plan_set_profile(self._plan, int(enable)), "maua_plan_set_profile")
+
+    def profile(self):
+        """Per-launch records of the last forward + backward (needs set_profile(True)); synchronises the stream."""
+        import json
+
+        cap = 1 << 16
+        buf = C.create_string_buffer(cap)
+        n = self._lib.maua_plan_profile_json(self._plan, buf, C.c_long(cap), _lib.stream_ptr())
+        if n < 0 or n > cap:
+            raise RuntimeError("maua_plan_profile_json failed")
+        return json.loads(buf.value.decode())
+
     def slot_modules(self):
         """Loss modules in plan slot order: taps..., TV, temporal (None where absent)."""
         return [m for _, m in self.taps] + [self.tv_mod, self.temporal_mod]

@@ -73,6 +73,8 @@ def test_conv3x3_fwd(lib, impl, cin, cout, h, w):
                                     _lib.stream_ptr()), "conv3x3_fwd")
     torch.cuda.synchronize()
     err = rel(nchw(y), ref)
+    exact = tf32_round(F.relu(F.conv2d(x.double(), tf32_round(wt).double(), b.double(), padding=1)).float())
+    print(f"conv fwd impl={impl} {cin}->{cout} {h}x{w}: rel vs fp32 torch {err:.2e}, vs fp64-exact-then-rounded {rel(nchw(y), exact):.2e}")
     assert err < TF32_REL, f"conv fwd rel err {err}"
 
 

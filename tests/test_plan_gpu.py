@@ -152,11 +152,16 @@ def test_optimize_matches_reference_golden(name, ckpt):
     assert p > 40.0
 
 
-def test_tc_and_simt_plans_agree(ckpt):
-    """The tcgen05 plan and the naive SIMT plan (same contract, different code) produce the same gradient."""
+@pytest.mark.parametrize("pooling", ["avg", "max"])
+def test_tc_and_simt_plans_agree(ckpt, pooling):
+    """The tcgen05 plan and the naive SIMT plan (same contract, different code) produce the same gradient.  With
+    average pooling the two agree to accumulation round-off; with max pooling the few activations that differ by one
+    TF32 ulp between the two implementations flip some arg-max decisions, which moves single gradient entries."""
     from maua_style_b200 import _lib, optim
 
     z, meta = load_golden("adam_gram_90x122")
+    meta = dict(meta)
+    meta["over"] = dict(meta["over"], pooling=pooling)
     content, styles, init = golden_inputs(meta)
     grads = []
     for impl in (_lib.MAUA_IMPL_TC, _lib.MAUA_IMPL_REF):
@@ -169,8 +174,8 @@ def test_tc_and_simt_plans_agree(ckpt):
         _, g = optim.feval(net, init.clone().cuda())
         grads.append(g.clone())
     err = rel(grads[0], grads[1])
-    report(f"tc vs simt plan gradient rel {err:.2e}")
-    assert err < 2e-3
+    report(f"tc vs simt plan gradient ({pooling} pool) rel {err:.2e}")
+    assert err < (5e-4 if pooling == "avg" else 3e-2)
 
 
 def test_temporal_loss_and_autograd_interface(ckpt):
