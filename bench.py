@@ -169,7 +169,7 @@ def cpu_baseline(size, optimizer):
 # our arm
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
@@ -180,11 +180,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and active throttle reasons of the samples taken inside [t_begin, t_end] (wall clock)."""
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -192,16 +195,24 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in open(self.path).read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), parts[4:8]))
             except ValueError:
                 continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
+        inside = [r for r in rows if t_begin is None or (t_begin - 0.05 <= r[0] <= t_end + 0.05)]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: use every sample taken under load
+            inside, window = rows, "whole run (timed region shorter than the sampling period)"
+        sm, mx, reasons = [], [], set()
+        for _, a, b, flags in inside:
+            sm.append(a); mx.append(b)
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], flags):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         try:
@@ -209,7 +220,7 @@ class ClockSampler:
         except OSError:
             pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def lbfgs_launches(calls, hist):
@@ -259,6 +270,8 @@ def run_ours(args):
         g = net._backward_plan(up)
         opt.step(g)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # set-up: fill the L-BFGS history so the timed steps run at full history (not part of warm-up or timing)
     if args.optimizer == "lbfgs":
         for _ in range(args.history_prefill):
@@ -273,17 +286,17 @@ def run_ours(args):
     # ---- device-resident timing ----
     for _ in range(W):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     calls0 = opt.step_count
+    t_begin = time.time()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

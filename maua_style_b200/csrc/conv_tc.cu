@@ -36,7 +36,7 @@ constexpr int A_BYTES = 128 * 128;
 
 struct ConvKParams {
     int B, H, W, Cin, Cout, ntaps, K2;
-    int tiles_w, tiles_h;
+    int tiles_w, tiles_h, n_tiles, total_tiles;
     ConvEpilogue ep;
 };
 
@@ -46,10 +46,16 @@ struct ConvCfg {
     static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
     static constexpr int NSTAGES_RAW = (200 * 1024) / STAGE_BYTES;
     static constexpr int NSTAGES = NSTAGES_RAW > 6 ? 6 : NSTAGES_RAW;
-    static constexpr int TMEM_COLS = MT * BN;  // 64..512, power of two
+    static constexpr int ACC_COLS = MT * BN;                      // one accumulator set: 64..512 columns
+    static constexpr int NACC = ACC_COLS <= 256 ? 2 : 1;          // double-buffered when TMEM has room
+    static constexpr int TMEM_COLS = NACC * ACC_COLS;             // power of two, <= 512
     static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Persistent, warp-specialised kernel: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// Tile index = pixel_tile * n_tiles + n_tile, so CTAs that run concurrently share the activation tile in L2.
+// Three pipelines: smem ring (TMA -> MMA), TMEM accumulators (MMA -> epilogue, double-buffered when they fit),
+// and the tile loop itself -- so the epilogue of tile i overlaps the TMA loads and MMAs of tile i+1.
 template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -57,26 +63,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const ConvKParams p) {
     using Cfg = ConvCfg<BN, MT>;
     constexpr int NST = Cfg::NSTAGES;
+    constexpr int NACC = Cfg::NACC;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + NST;
-    uint64_t* tmem_full_bar = empty_bar + NST;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + NST;     // [NACC]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [NACC]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w;
-    t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    const int b = t / p.tiles_h;
-    const int w0 = tw * TILE_W;
-    const int h0 = th * (TILE_H * MT);
-    const int n0 = blockIdx.y * BN;
 
     const int cpt = p.Cin / KCHUNK;      // channel chunks per tap
     const int nk1 = p.ntaps * cpt;       // main k-steps
@@ -96,7 +94,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < NACC; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -108,124 +109,158 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    auto decode = [&](int tile, int& b, int& h0, int& w0, int& n0) {
+        const int nt = tile % p.n_tiles;
+        int pt = tile / p.n_tiles;
+        const int tw = pt % p.tiles_w;
+        pt /= p.tiles_w;
+        const int th = pt % p.tiles_h;
+        b = pt / p.tiles_h;
+        w0 = tw * TILE_W;
+        h0 = th * (TILE_H * MT);
+        n0 = nt * BN;
+    };
+
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
-        for (int ks = 0; ks < nk; ++ks) {
-            const int stage = ks % NST;
-            const uint32_t phase = (ks / NST) & 1;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sB = sA + MT * A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (ks < nk1) {
-                const int tap = ks / cpt;
-                const int c0 = (ks - tap * cpt) * KCHUNK;
-                int dy = 0, dx = 0;
-                if (p.ntaps == 9) {
-                    dy = tap / 3 - 1;
-                    dx = tap % 3 - 1;
+        uint32_t it = 0;  // global k-step counter across tiles
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int b, h0, w0, n0;
+            decode(tile, b, h0, w0, n0);
+            for (int ks = 0; ks < nk; ++ks, ++it) {
+                const int stage = it % NST;
+                const uint32_t phase = (it / NST) & 1;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + MT * A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                if (ks < nk1) {
+                    const int tap = ks / cpt;
+                    const int c0 = (ks - tap * cpt) * KCHUNK;
+                    int dy = 0, dx = 0;
+                    if (p.ntaps == 9) {
+                        dy = tap / 3 - 1;
+                        dx = tap % 3 - 1;
+                    }
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma_load_4d(sA + m * A_BYTES, &tmA, &full_bar[stage], c0, w0 + dx, h0 + m * TILE_H + dy, b);
+                    tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.Cin + c0, n0);
+                } else {
+                    const int c0 = (ks - nk1) * KCHUNK;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tma_load_4d(sA + m * A_BYTES, &tmA2, &full_bar[stage], c0, w0, h0 + m * TILE_H, b);
+                    tma_load_2d(sB, &tmB2, &full_bar[stage], c0, n0);
                 }
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                    tma_load_4d(sA + m * A_BYTES, &tmA, &full_bar[stage], c0, w0 + dx, h0 + m * TILE_H + dy, b);
-                tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.Cin + c0, n0);
-            } else {
-                const int c0 = (ks - nk1) * KCHUNK;
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                    tma_load_4d(sA + m * A_BYTES, &tmA2, &full_bar[stage], c0, w0, h0 + m * TILE_H, b);
-                tma_load_2d(sB, &tmB2, &full_bar[stage], c0, n0);
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-        for (int ks = 0; ks < nk; ++ks) {
-            const int stage = ks % NST;
-            const uint32_t phase = (ks / NST) & 1;
-            mbar_wait(&full_bar[stage], phase);
+        uint32_t it = 0, lt = 0;  // global k-step counter, local tile counter
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt % NACC;
+            mbar_wait(&tmem_empty_bar[acc], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t sB = sA + MT * A_BYTES;
-            const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+            const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
+            for (int ks = 0; ks < nk; ++ks, ++it) {
+                const int stage = it % NST;
+                const uint32_t phase = (it / NST) & 1;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t sB = sA + MT * A_BYTES;
+                const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                const uint64_t adesc = make_smem_desc_sw128(sA + m * A_BYTES, 16, 1024);
+                for (int m = 0; m < MT; ++m) {
+                    const uint64_t adesc = make_smem_desc_sw128(sA + m * A_BYTES, 16, 1024);
 #pragma unroll
-                for (int kk = 0; kk < KCHUNK / 8; ++kk) {
-                    // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-                    umma_tf32(tmem_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc,
-                              (ks > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < KCHUNK / 8; ++kk) {
+                        // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
+                        umma_tf32(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                    }
                 }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         }
-        umma_commit(tmem_full_bar);  // accumulator complete
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;
         const int hl = row / TILE_W;
         const int wl = row % TILE_W;
         const ConvEpilogue& ep = p.ep;
         const float ccoef = ep.cont_f ? *ep.cont_coef : 0.f;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+            int b, h0, w0, n0;
+            decode(tile, b, h0, w0, n0);
+            const int acc = lt % NACC;
+            mbar_wait(&tmem_full_bar[acc], (lt / NACC) & 1);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int m = 0; m < MT; ++m) {
-            const int h = h0 + m * TILE_H + hl;
-            const int w = w0 + wl;
-            const bool valid = (h < p.H) && (w < p.W);
-            const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.Cout + n0;
+            for (int m = 0; m < MT; ++m) {
+                const int h = h0 + m * TILE_H + hl;
+                const int w = w0 + wl;
+                const bool valid = (h < p.H) && (w < p.W);
+                const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.Cout + n0;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                float v[16];
-                tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * BN + c, v);
-                if (valid) {
-                    if (ep.bias) {
+                for (int c = 0; c < BN; c += 16) {
+                    float v[16];
+                    tmem_ld_x16(t_base + m * BN + c, v);
+                    if (valid) {
+                        if (ep.bias) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n0 + c + i);
-                            v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n0 + c + i);
+                                v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+                            }
                         }
-                    }
-                    if (ep.cont_f) {
+                        if (ep.cont_f) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 f = *reinterpret_cast<const float4*>(ep.cont_f + off + c + i);
-                            const float4 tg = *reinterpret_cast<const float4*>(ep.cont_t + off + c + i);
-                            v[i] += ccoef * (f.x - tg.x); v[i + 1] += ccoef * (f.y - tg.y);
-                            v[i + 2] += ccoef * (f.z - tg.z); v[i + 3] += ccoef * (f.w - tg.w);
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 f = *reinterpret_cast<const float4*>(ep.cont_f + off + c + i);
+                                const float4 tg = *reinterpret_cast<const float4*>(ep.cont_t + off + c + i);
+                                v[i] += ccoef * (f.x - tg.x); v[i + 1] += ccoef * (f.y - tg.y);
+                                v[i + 2] += ccoef * (f.z - tg.z); v[i + 3] += ccoef * (f.w - tg.w);
+                            }
                         }
-                    }
-                    if (ep.addend) {
+                        if (ep.addend) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 a = *reinterpret_cast<const float4*>(ep.addend + off + c + i);
-                            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 a = *reinterpret_cast<const float4*>(ep.addend + off + c + i);
+                                v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+                            }
                         }
-                    }
-                    if (ep.relu) {
+                        if (ep.relu) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    if (ep.mask_src) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 mk = *reinterpret_cast<const float4*>(ep.mask_src + off + c + i);
-                            v[i] = mk.x > 0.f ? v[i] : 0.f; v[i + 1] = mk.y > 0.f ? v[i + 1] : 0.f;
-                            v[i + 2] = mk.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = mk.w > 0.f ? v[i + 3] : 0.f;
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
-                    }
-                    if (ep.round) {
+                        if (ep.mask_src) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
-                    }
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 mk = *reinterpret_cast<const float4*>(ep.mask_src + off + c + i);
+                                v[i] = mk.x > 0.f ? v[i] : 0.f; v[i + 1] = mk.y > 0.f ? v[i + 1] : 0.f;
+                                v[i + 2] = mk.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = mk.w > 0.f ? v[i + 3] : 0.f;
+                            }
+                        }
+                        if (ep.round) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(ep.out + off + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(ep.out + off + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
                 }
             }
+            // all TMEM reads of this warp are complete (tmem_ld_x16 waits): hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
 
@@ -306,6 +341,18 @@ int make_tmap_2d(CUtensorMap* m, const float* ptr, long rows, long cols, int box
 
 namespace {
 
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = cached[dev & 63];
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN, int MT>
 int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = ConvCfg<BN, MT>;
@@ -334,8 +381,10 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     p.K2 = a.K2;
     p.tiles_w = (a.W + TILE_W - 1) / TILE_W;
     p.tiles_h = (a.H + TILE_H * MT - 1) / (TILE_H * MT);
+    p.n_tiles = a.Cout / BN;
+    p.total_tiles = p.tiles_w * p.tiles_h * a.B * p.n_tiles;
     p.ep = a.ep;
-    dim3 grid(p.tiles_w * p.tiles_h * a.B, a.Cout / BN);
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();  // persistent: one CTA per SM
     conv_tc_kernel<BN, MT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
@@ -353,11 +402,22 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     MAUA_REQUIRE(a.B >= 1 && a.H >= 1 && a.W >= 1, "bad extent B=%d H=%d W=%d", a.B, a.H, a.W);
     MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
 
-    const int bn = (a.Cout % 256 == 0) ? 256 : (a.Cout % 128 == 0) ? 128 : 64;
-    // MT=2 (256 pixels per CTA) halves weight traffic per FLOP; use it when it still fills the GPU.
-    const long tiles2 = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + 2 * TILE_H - 1) / (2 * TILE_H)) * a.B *
-                        (a.Cout / bn);
-    const int mt = tiles2 >= 148 ? 2 : 1;
+    // Tile selection: prefer the largest CTA tile (256 pixels x 256 channels = 64 flop per L2 byte), but fall back to
+    // smaller tiles when the bigger one would leave SMs idle or end in a mostly empty last wave.
+    struct Cand { int bn, mt; double quality; };
+    static const Cand cands[] = {{256, 2, 1.00}, {256, 1, 0.85}, {128, 2, 0.85}, {128, 1, 0.70}, {64, 2, 0.60}, {64, 1, 0.50}};
+    const int sms = num_sms();
+    int best_bn = 64, best_mt = 1;
+    double best = -1.0;
+    for (const Cand& c : cands) {
+        if (a.Cout % c.bn) continue;
+        const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + c.mt * TILE_H - 1) / (c.mt * TILE_H)) * a.B * (a.Cout / c.bn);
+        const long waves = (tiles + sms - 1) / sms;
+        const double eff = (double)tiles / (double)(waves * sms);
+        const double score = eff * c.quality;
+        if (score > best) { best = score; best_bn = c.bn; best_mt = c.mt; }
+    }
+    const int bn = best_bn, mt = best_mt;
     if (bn == 256) return mt == 2 ? launch_cfg<256, 2>(a, st) : launch_cfg<256, 1>(a, st);
     if (bn == 128) return mt == 2 ? launch_cfg<128, 2>(a, st) : launch_cfg<128, 1>(a, st);
     return mt == 2 ? launch_cfg<64, 2>(a, st) : launch_cfg<64, 1>(a, st);

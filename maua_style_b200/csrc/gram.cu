@@ -18,6 +18,7 @@
 // the finalize kernel (deterministic, no float atomics), which also symmetrises, applies the covariance
 // rank-1 correction  sum (x-mu)(y-mu) = sum xy - P mu mu^T  and the 1/(C*P) normalisation.
 #include "gram.cuh"
+#include "reduce.cuh"
 
 namespace maua {
 
@@ -189,25 +190,8 @@ __global__ void style_loss_fwd_kernel(const float* __restrict__ gram, const floa
         diff[i] = dd;
         acc += (double)dd * dd;
     }
-    __shared__ double sh[8];
-    __shared__ bool is_last;
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
-        partials[blockIdx.x] = s;
-        __threadfence();
-        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-        if (is_last) {
-            __threadfence();
-            double tot = 0;
-            for (unsigned b = 0; b < gridDim.x; ++b) tot += partials[b];
-            *counter = 0;
-            *loss_out = scale * (float)(tot / (double)n);
-        }
-    }
+    double v[1] = {acc}, tot[1];
+    if (grid_sum<1>(v, partials, counter, tot)) *loss_out = scale * (float)(tot[0] / (double)n);
 }
 
 // aux_d = coef * 4 / (C^3 P) * diff  (TF32-rounded: it is the B operand of the backward MMA)

@@ -15,6 +15,7 @@
 // at 1024^2), so HBM traffic is the two history reads per loop: 16 k n bytes per iteration.
 #include "maua_b200.h"
 #include "pointwise.cuh"
+#include "reduce.cuh"
 
 namespace maua {
 
@@ -23,6 +24,7 @@ namespace {
 constexpr int kMaxHist = 256;
 constexpr int kLThreads = 256;
 constexpr int kLBlocks = 148 * 4;
+static_assert(kLThreads == kReduceThreads, "grid_sum assumes 256-thread blocks");
 
 struct LbfgsState {  // device resident
     int n_iter, hist_len, head, halted;
@@ -66,28 +68,9 @@ __device__ __forceinline__ void st4(float* p, long i, float4 v) { reinterpret_ca
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // returns true in exactly one thread of the grid, after all blocks have contributed; tot[] = ordered sums
-__device__ bool grid_reduce2(double a0, double a1, double* partials, unsigned int* counter, double (&tot)[2]) {
-    __shared__ double sh[2][kLThreads / 32];
-    __shared__ bool is_last;
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a0; sh[1][threadIdx.x >> 5] = a1; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s0 = 0, s1 = 0;
-        for (int i = 0; i < kLThreads / 32; ++i) { s0 += sh[0][i]; s1 += sh[1][i]; }
-        partials[2 * blockIdx.x] = s0;
-        partials[2 * blockIdx.x + 1] = s1;
-        __threadfence();
-        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!(is_last && threadIdx.x == 0)) return false;
-    __threadfence();
-    tot[0] = tot[1] = 0;
-    for (unsigned b = 0; b < gridDim.x; ++b) { tot[0] += partials[2 * b]; tot[1] += partials[2 * b + 1]; }
-    *counter = 0;
-    return true;
+__device__ __forceinline__ bool grid_reduce2(double a0, double a1, double* partials, unsigned int* counter, double (&tot)[2]) {
+    const double v[2] = {a0, a1};
+    return grid_sum<2>(v, partials, counter, tot);
 }
 
 __global__ void __launch_bounds__(kLThreads) lbfgs_pass_kernel(const PassArgs a) {

@@ -3,6 +3,7 @@
 // All are vectorised, coalesced, grid-stride kernels sized to a multiple of the SM count, with
 // warp-shuffle reductions and a deterministic last-block final reduce (no float atomics).
 #include "pointwise.cuh"
+#include "reduce.cuh"
 
 namespace maua {
 
@@ -15,49 +16,10 @@ inline int grid_for(long n_items, int per_sm = 8) {
     return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
-// --------------------------------------------------------------------------------------------
-// Block-level deterministic sum: every block writes one partial (double), the last block to finish
-// adds the partials in index order and hands the total to `fin`.
-// --------------------------------------------------------------------------------------------
-template <int NV>
-struct BlockPartials {
-    double v[NV];
-};
-
 template <int NV, class Fin>
-__device__ void block_reduce_finish(double (&acc)[NV], double* partials, unsigned int* counter, Fin fin) {
-    __shared__ double sh[NV][kThreads / 32];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double s = warp_sum(acc[k]);
-        if (lane == 0) sh[k][warp] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double s = 0;
-            for (int i = 0; i < kThreads / 32; ++i) s += sh[k][i];
-            partials[(size_t)blockIdx.x * NV + k] = s;
-        }
-        __threadfence();
-        const unsigned int done = atomicAdd(counter, 1u);
-        is_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        __threadfence();
-        double tot[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) tot[k] = 0;
-        for (unsigned int bidx = 0; bidx < gridDim.x; ++bidx)
-#pragma unroll
-            for (int k = 0; k < NV; ++k) tot[k] += partials[(size_t)bidx * NV + k];
-        *counter = 0;  // re-arm for the next launch on this stream
-        fin(tot);
-    }
+__device__ __forceinline__ void block_reduce_finish(double (&acc)[NV], double* partials, unsigned int* counter, Fin fin) {
+    double tot[NV];
+    if (grid_sum<NV>(acc, partials, counter, tot)) fin(tot);
 }
 
 // --------------------------------------------------------------------------------------------
