@@ -90,10 +90,14 @@ MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int
 MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const float* bias, float* y, int b, int h,
                                  int w, int cout, maua_stream_t stream);
 /* First layer dgrad + image-side tail: gimg NCHW [B,3,H,W] = dgrad(gy) + tv_coef * dTV/dimg
- *   + temp_coef * w * (img*w - temp_target).  tv_coef / temp_coef are device scalars (NULL = term absent). */
+ *   + temp_coef * w * (img*w - temp_target).  tv_coef / temp_coef are device scalars (NULL = term absent).
+ *   Runs as a per-pixel tensor-core contraction (64 channels -> 27 tap columns) followed by a 9-tap gather;
+ *   workspace: maua_conv_first_dgrad_workspace_bytes(b, h, w) device bytes. */
+MAUA_API size_t maua_conv_first_dgrad_workspace_bytes(int b, int h, int w);
 MAUA_API int maua_conv_first_dgrad(const float* gy, const float* w_oihw, float* gimg, int b, int h, int w, int cout,
                                    const float* img, const float* tv_coef, const float* temp_target,
-                                   const float* temp_weights, const float* temp_coef, maua_stream_t stream);
+                                   const float* temp_weights, const float* temp_coef, void* workspace,
+                                   maua_stream_t stream);
 /* 2x2/2 pooling on NHWC, floor semantics; avg = 0 max (first maximum wins ties), 1 average. */
 MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream);
 /* gx = unpool(gy) * (x > 0) [+ addend * (x > 0)]; x is the post-ReLU pre-pool activation. */

@@ -90,6 +90,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.maua_last_error.restype = C.c_char_p
     lib.maua_gram_workspace_bytes.restype = C.c_size_t
     lib.maua_reduce_workspace_bytes.restype = C.c_size_t
+    lib.maua_conv_first_dgrad_workspace_bytes.restype = C.c_size_t
     lib.maua_plan_device_bytes.restype = C.c_size_t
     lib.maua_plan_destroy.restype = None
     lib.maua_plan_profile_json.restype = C.c_long

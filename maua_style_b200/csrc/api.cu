@@ -136,14 +136,24 @@ MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const fl
 }
 MAUA_API int maua_conv_first_dgrad(const float* gy, const float* w_oihw, float* gimg, int b, int h, int w, int cout,
                                    const float* img, const float* tv_coef, const float* temp_target,
-                                   const float* temp_weights, const float* temp_coef, maua_stream_t stream) {
+                                   const float* temp_weights, const float* temp_coef, void* workspace,
+                                   maua_stream_t stream) {
     MAUA_ENTRY_GUARD();
     MAUA_REQUIRE(gy && w_oihw && gimg, "maua_conv_first_dgrad: null pointer");
     MAUA_REQUIRE(!(tv_coef || temp_coef) || img, "maua_conv_first_dgrad: TV / temporal terms need the image");
+    MAUA_REQUIRE(workspace, "maua_conv_first_dgrad: workspace (maua_conv_first_dgrad_workspace_bytes) is required");
     ImageTail t;
     t.img = img; t.tv_coef = tv_coef; t.temp_target = temp_target; t.temp_weights = temp_weights;
     t.temp_coef = temp_target ? temp_coef : nullptr;
-    return conv_first_dgrad_launch(gy, w_oihw, gimg, b, h, w, cout, t, (cudaStream_t)stream);
+    float* T = reinterpret_cast<float*>(workspace);
+    float* wt = T + (((size_t)b * h * w * 32 + 63) & ~size_t(63));
+    int rc = conv_first_dgrad_prep_weights(w_oihw, wt, cout, (cudaStream_t)stream);
+    if (rc) return rc;
+    return conv_first_dgrad_launch(gy, wt, gimg, b, h, w, cout, t, T, MAUA_IMPL_TC, (cudaStream_t)stream);
+}
+
+MAUA_API size_t maua_conv_first_dgrad_workspace_bytes(int b, int h, int w) {
+    return conv_first_dgrad_workspace_bytes(b, h, w) + 256;
 }
 
 MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream) {

@@ -398,16 +398,16 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     MAUA_REQUIRE(a.ntaps == 0 || (a.Cin % KCHUNK == 0 && a.Cin >= KCHUNK),
                  "tcgen05 conv needs Cin %% 32 == 0 (got %d); the 3-channel image layer uses conv_first_*", a.Cin);
     MAUA_REQUIRE(a.K2 % KCHUNK == 0, "aux K2 must be a multiple of 32 (got %d)", a.K2);
-    MAUA_REQUIRE(a.Cout % 64 == 0, "Cout must be a multiple of 64 (got %d)", a.Cout);
+    MAUA_REQUIRE(a.Cout % 32 == 0, "Cout must be a multiple of 32 (got %d)", a.Cout);
     MAUA_REQUIRE(a.B >= 1 && a.H >= 1 && a.W >= 1, "bad extent B=%d H=%d W=%d", a.B, a.H, a.W);
     MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
 
     // Tile selection: prefer the largest CTA tile (256 pixels x 256 channels = 64 flop per L2 byte), but fall back to
     // smaller tiles when the bigger one would leave SMs idle or end in a mostly empty last wave.
     struct Cand { int bn, mt; double quality; };
-    static const Cand cands[] = {{256, 2, 1.00}, {256, 1, 0.85}, {128, 2, 0.85}, {128, 1, 0.70}, {64, 2, 0.60}, {64, 1, 0.50}};
+    static const Cand cands[] = {{256, 2, 1.00}, {256, 1, 0.85}, {128, 2, 0.85}, {128, 1, 0.70}, {64, 2, 0.60}, {64, 1, 0.50}, {32, 2, 0.40}, {32, 1, 0.30}};
     const int sms = num_sms();
-    int best_bn = 64, best_mt = 1;
+    int best_bn = 32, best_mt = 1;
     double best = -1.0;
     for (const Cand& c : cands) {
         if (a.Cout % c.bn) continue;
@@ -420,7 +420,8 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     const int bn = best_bn, mt = best_mt;
     if (bn == 256) return mt == 2 ? launch_cfg<256, 2>(a, st) : launch_cfg<256, 1>(a, st);
     if (bn == 128) return mt == 2 ? launch_cfg<128, 2>(a, st) : launch_cfg<128, 1>(a, st);
-    return mt == 2 ? launch_cfg<64, 2>(a, st) : launch_cfg<64, 1>(a, st);
+    if (bn == 64) return mt == 2 ? launch_cfg<64, 2>(a, st) : launch_cfg<64, 1>(a, st);
+    return mt == 2 ? launch_cfg<32, 2>(a, st) : launch_cfg<32, 1>(a, st);
 }
 
 // ---------------------------------------------------------------------------------------------

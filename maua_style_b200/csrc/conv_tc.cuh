@@ -55,7 +55,10 @@ struct ImageTail {
     const float* temp_weights = nullptr;// [H][W] reliability map or null
     const float* temp_coef = nullptr;  // device scalar: coef * 2 / numel
 };
-int conv_first_dgrad_launch(const float* gout, const float* w, float* gimg, int B, int H, int W, int Cout,
-                            const ImageTail& tail, cudaStream_t st);
+// wt: [32][Cout] from conv_first_dgrad_prep_weights; T: scratch of B*H*W*32 floats (the per-pixel tap contraction)
+size_t conv_first_dgrad_workspace_bytes(int B, int H, int W);
+int conv_first_dgrad_prep_weights(const float* w_oihw, float* wt, int Cout, cudaStream_t st);
+int conv_first_dgrad_launch(const float* gout, const float* wt, float* gimg, int B, int H, int W, int Cout,
+                            const ImageTail& tail, float* T, int impl, cudaStream_t st);
 
 }  // namespace maua

@@ -37,6 +37,7 @@ struct Entry {
     float* wg = nullptr;       // forward GEMM weights  [cout][9*cin]
     float* wd = nullptr;       // dgrad GEMM weights    [cin][9*cout]
     float* bias = nullptr;
+    float* wt1 = nullptr;      // first conv only: [32][cout] tap-column weights of the dgrad contraction
     // per forward
     int H = 0, W = 0, C = 0;   // output extent
     float* out = nullptr;      // arena pointer
@@ -259,6 +260,10 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
             }
             if (e == cudaSuccess) e = cudaMemcpy(en.w_raw, d->weights[i], wn * sizeof(float), cudaMemcpyDeviceToDevice);
             if (e == cudaSuccess) e = cudaMemcpy(en.bias, d->biases[i], (size_t)en.cout * sizeof(float), cudaMemcpyDeviceToDevice);
+            if (i == 0) {
+                alloc((void**)&en.wt1, (size_t)32 * en.cout * sizeof(float));
+                if (e == cudaSuccess && conv_first_dgrad_prep_weights(en.w_raw, en.wt1, en.cout, 0)) ok = false;
+            }
             if (e == cudaSuccess && i > 0) {
                 if (prep_weights_launch(en.w_raw, en.wg, en.cout, en.cin, 0, 1, 0) ||
                     prep_weights_launch(en.w_raw, en.wd, en.cout, en.cin, 1, 1, 0))
@@ -328,7 +333,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     if (!p) return;
     DeviceGuard guard(p->device);
     for (auto& e : p->entries) {
-        cudaFree(e.w_raw); cudaFree(e.wg); cudaFree(e.wd); cudaFree(e.bias);
+        cudaFree(e.w_raw); cudaFree(e.wg); cudaFree(e.wd); cudaFree(e.bias); cudaFree(e.wt1);
     }
     for (auto& t : p->taps) {
         cudaFree(t.gram); cudaFree(t.diff); cudaFree(t.aux_d); cudaFree(t.mean); cudaFree(t.aux_bias); cudaFree(t.gram_ws);
@@ -698,15 +703,18 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
     }
     if (gm && gm_entry == 0) {
         Entry& e0 = p->entries[0];
-        if ((rc = conv_first_dgrad_launch(gm, e0.w_raw, grad_image, 1, H, W, e0.cout, tail, st))) return rc;
-        p->launches_bwd++;
+        float* T = take_buf();
+        if (T == gm) T = take_buf();
+        if ((rc = conv_first_dgrad_launch(gm, e0.wt1, grad_image, 1, H, W, e0.cout, tail, T, p->impl, st))) return rc;
+        p->launches_bwd += 2;
         prof_mark(p, st, "conv_first_dgrad", 0, 2.0 * 27 * e0.cout * H * W, 4.0 * (e0.cout + 6) * H * W);
     } else {
         // no feature-space loss is active: only TV / temporal terms (or nothing at all)
         MAUA_CUDA_CHECK(cudaMemsetAsync(p->gbuf[0], 0, (size_t)H * W * p->entries[0].cout * sizeof(float), st));
         Entry& e0 = p->entries[0];
-        if ((rc = conv_first_dgrad_launch(p->gbuf[0], e0.w_raw, grad_image, 1, H, W, e0.cout, tail, st))) return rc;
-        p->launches_bwd++;
+        if ((rc = conv_first_dgrad_launch(p->gbuf[0], e0.wt1, grad_image, 1, H, W, e0.cout, tail, p->gbuf[1], p->impl, st)))
+            return rc;
+        p->launches_bwd += 2;
     }
     return MAUA_OK;
 }

@@ -151,7 +151,7 @@ def test_conv_first_fwd_and_dgrad(lib, h, w):
     assert rel(nchw(y), tf32_round(ref)) < 2e-5  # rare 1-ulp tf32 rounding flips
 
     # dgrad + TV + temporal tail
-    gy = torch.randn(1, 64, h, w, generator=g)
+    gy = tf32_round(torch.randn(1, 64, h, w, generator=g))  # the plan hands over a TF32-rounded masked gradient
     x = img.clone().requires_grad_(True)
     warp = torch.rand(1, 3, h, w, generator=g) * 255 - 110
     wts = torch.rand(1, 1, h, w, generator=g)
@@ -163,11 +163,13 @@ def test_conv_first_fwd_and_dgrad(lib, h, w):
     gimg = torch.empty(1, 3, h, w, device="cuda")
     gyd, warpd, wtsd = nhwc(gy).cuda(), warp.cuda(), wts.cuda()
     tvd, tpd = torch.tensor([tvc]).cuda(), torch.tensor([tpc]).cuda()
+    ws = torch.empty(lib.maua_conv_first_dgrad_workspace_bytes(1, h, w), dtype=torch.uint8, device="cuda")
     _lib.check(lib.maua_conv_first_dgrad(_lib.ptr(gyd), _lib.ptr(wtd), _lib.ptr(gimg), 1, h, w, 64,
                                          _lib.ptr(imgd), _lib.ptr(tvd), _lib.ptr(warpd),
-                                         _lib.ptr(wtsd), _lib.ptr(tpd), _lib.stream_ptr()))
+                                         _lib.ptr(wtsd), _lib.ptr(tpd), _lib.ptr(ws), _lib.stream_ptr()))
     torch.cuda.synchronize()
-    assert rel(gimg, x.grad) < 1e-5
+    # the 64 -> 27 channel contraction runs on the tensor core with TF32 operands (gy, w rounded to 10-bit mantissas)
+    assert rel(gimg, x.grad) < 1e-3
 
 
 @pytest.mark.parametrize("avg", [0, 1])
