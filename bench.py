@@ -224,7 +224,7 @@ class ClockSampler:
 
 
 def lbfgs_launches(calls, hist):
-    return 1  # one cooperative kernel per L-BFGS iteration (the 2k+3 passes are separated by grid barriers)
+    return 3  # multi-dot pass, scalar recurrences, direction + update (maua_style_b200/csrc/lbfgs.cu)
 
 
 def run_ours(args):
