@@ -7,14 +7,17 @@
 //
 // GEMM view (NHWC activations):   D[pixel][n] = sum_{tap, c} A_tap[pixel][c] * Wg[n][tap*Cin + c]
 //   M = pixels.  One CTA owns MT sub-tiles of 128 pixels (16 wide x 8 high), stacked along h.
-//   N = output channels, BN in {64,128,256} per CTA.
+//   N = output channels, BN in {32,64,128,256} per CTA.
 //   K = 9 taps x Cin, walked in k-steps of 32 channels (= one 128-byte swizzle span of fp32).
-// A operand: one 4-D TMA box {32 c, 16 w, 8 h, 1 b} per (tap, channel chunk); the tap shift is
-//   applied to the box origin and out-of-bounds pixels are zero-filled by TMA, which is exactly
-//   the conv zero padding and also handles ragged right/bottom tiles for arbitrary H x W.
-// B operand: 2-D TMA box {32 k, BN n} of the K-major GEMM weights.
+// A operand: for every (dx, channel chunk) ONE 4-D TMA box {32 c, 16 w, MT*8 + 2 h, 1 b} whose origin is shifted by
+//   (dx, -1); out-of-bounds pixels are zero-filled by TMA, which is exactly the conv zero padding and also handles
+//   ragged right/bottom tiles for arbitrary H x W.  The three vertical taps dy = -1, 0, +1 re-use that box: a shift by
+//   one image row is 16 pixel-rows x 128 B = 2048 B, a multiple of the 1024-byte swizzle atom, so the UMMA descriptor
+//   simply starts 0 / 2048 / 4096 bytes into the box.  This cuts the L2 -> shared-memory traffic of the activations
+//   2.7x compared with one box per tap (horizontal shifts would break the swizzle phase, so dx stays a reload).
+// B operand: 2-D TMA box {32 k, BN n} of the K-major GEMM weights, one per (tap, chunk), in its own ring.
 // Both land in the canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms, SBO = 1024 B).
-// Accumulators: MT x [128 lanes x BN fp32 columns] in TMEM.
+// Accumulators: MT x [128 lanes x BN fp32 columns] in TMEM, double-buffered when they fit (<= 256 columns).
 // An optional second ("aux") GEMM term sum_{c2} A2[pixel][c2] * W2[n][c2] accumulates into the
 // same TMEM tile as extra k-steps: this is the StyleLoss backward 4(G-A)F/(C^3 N) (loss.py:141-157)
 // folded into the dgrad of the following layer.
@@ -32,7 +35,8 @@ namespace {
 constexpr int TILE_W = 16;
 constexpr int TILE_H = 8;   // one 128-pixel sub-tile = 16 x 8
 constexpr int KCHUNK = 32;  // fp32 channels per k-step (128 bytes)
-constexpr int A_BYTES = 128 * 128;
+constexpr int A_BYTES = 128 * 128;          // one sub-tile: 128 pixel rows x 128 B
+constexpr int ROW_BYTES = TILE_W * 128;     // one image row of the tile: 16 pixels x 128 B = 2 swizzle atoms
 
 struct ConvKParams {
     int B, H, W, Cin, Cout, ntaps, K2;
@@ -42,58 +46,69 @@ struct ConvKParams {
 
 template <int BN, int MT>
 struct ConvCfg {
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
-    static constexpr int NSTAGES_RAW = (200 * 1024) / STAGE_BYTES;
-    static constexpr int NSTAGES = NSTAGES_RAW > 6 ? 6 : NSTAGES_RAW;
-    static constexpr int ACC_COLS = MT * BN;                      // one accumulator set: 64..512 columns
-    static constexpr int NACC = ACC_COLS <= 256 ? 2 : 1;          // double-buffered when TMEM has room
-    static constexpr int TMEM_COLS = NACC * ACC_COLS;             // power of two, <= 512
-    static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int A_ROWS = MT * TILE_H + 2;                 // image rows incl. the vertical halo
+    static constexpr int A_STAGE = A_ROWS * ROW_BYTES;             // 36864 (MT=2) / 20480 (MT=1): multiples of 1024
+    static constexpr int B_STAGE = BN * 128;
+    static constexpr int BUDGET = 200 * 1024;
+    static constexpr int NA = (3 * A_STAGE + 4 * B_STAGE <= BUDGET) ? 3 : 2;
+    static constexpr int NB_RAW = (BUDGET - NA * A_STAGE) / B_STAGE;
+    static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
+    static constexpr int ACC_COLS = MT * BN;                       // one accumulator set: 32..512 columns
+    static constexpr int NACC = ACC_COLS <= 256 ? 2 : 1;           // double-buffered when TMEM has room
+    static constexpr int TMEM_COLS_RAW = NACC * ACC_COLS;
+    static constexpr int TMEM_COLS = TMEM_COLS_RAW < 32 ? 32 : TMEM_COLS_RAW;  // power of two, 32..512
+    static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
+    static_assert(NB >= 3, "weight ring too shallow");
 };
 
 // Persistent, warp-specialised kernel: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
 // Tile index = pixel_tile * n_tiles + n_tile, so CTAs that run concurrently share the activation tile in L2.
-// Three pipelines: smem ring (TMA -> MMA), TMEM accumulators (MMA -> epilogue, double-buffered when they fit),
-// and the tile loop itself -- so the epilogue of tile i overlaps the TMA loads and MMAs of tile i+1.
+// Pipelines: activation ring (TMA -> MMA), weight ring (TMA -> MMA), TMEM accumulators (MMA -> epilogue,
+// double-buffered when they fit) and the tile loop itself, so the epilogue of tile i overlaps the loads and MMAs of
+// tile i+1.
+//
+// K is walked in groups.  3x3 main term: group = (dx, channel chunk), one halo box + 3 weight tiles (dy = -1, 0, 1).
+// Pointwise main term (ntaps == 1) and the aux term: group = channel chunk, one plain box + 1 weight tile.
 template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const ConvKParams p) {
     using Cfg = ConvCfg<BN, MT>;
-    constexpr int NST = Cfg::NSTAGES;
-    constexpr int NACC = Cfg::NACC;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB, NACC = Cfg::NACC;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + NST;
-    uint64_t* tmem_full_bar = empty_bar + NST;     // [NACC]
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + NA * Cfg::A_STAGE;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smemB + NB * Cfg::B_STAGE);
+    uint64_t* a_empty = a_full + NA;
+    uint64_t* b_full = a_empty + NA;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* tmem_full_bar = b_empty + NB;        // [NACC]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [NACC]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int cpt = p.Cin / KCHUNK;      // channel chunks per tap
-    const int nk1 = p.ntaps * cpt;       // main k-steps
-    const int nk2 = p.K2 / KCHUNK;       // aux k-steps
-    const int nk = nk1 + nk2;
+    const int cpt = p.Cin / KCHUNK;                         // channel chunks of the main term
+    const bool halo = (p.ntaps == 9);
+    const int ng1 = halo ? 3 * cpt : (p.ntaps == 1 ? cpt : 0);  // main groups
+    const int ng2 = p.K2 / KCHUNK;                          // aux groups
+    const int ng = ng1 + ng2;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if (nk2 > 0) {
+        if (ng2 > 0) {
             tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmB2);
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NST; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
-        }
+        for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
@@ -123,67 +138,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer =====================
-        uint32_t it = 0;  // global k-step counter across tiles
+        uint32_t ia = 0, ib = 0;  // ring counters across tiles
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int b, h0, w0, n0;
             decode(tile, b, h0, w0, n0);
-            for (int ks = 0; ks < nk; ++ks, ++it) {
-                const int stage = it % NST;
-                const uint32_t phase = (it / NST) & 1;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-                uint8_t* sB = sA + MT * A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                if (ks < nk1) {
-                    const int tap = ks / cpt;
-                    const int c0 = (ks - tap * cpt) * KCHUNK;
-                    int dy = 0, dx = 0;
-                    if (p.ntaps == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap % 3 - 1;
+            for (int g = 0; g < ng; ++g) {
+                const int sa = ia % NA;
+                mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
+                ++ia;
+                uint8_t* sA = smemA + sa * Cfg::A_STAGE;
+                if (g < ng1 && halo) {
+                    const int dxi = g / cpt;                  // 0..2  <->  dx = -1, 0, +1
+                    const int c0 = (g - dxi * cpt) * KCHUNK;
+                    mbar_arrive_expect_tx(&a_full[sa], Cfg::A_STAGE);
+                    tma_load_4d(sA, &tmA, &a_full[sa], c0, w0 + dxi - 1, h0 - 1, b);
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        const int sb = ib % NB;
+                        mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
+                        ++ib;
+                        mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
+                        tma_load_2d(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * 3 + dxi) * p.Cin + c0, n0);
                     }
-#pragma unroll
-                    for (int m = 0; m < MT; ++m)
-                        tma_load_4d(sA + m * A_BYTES, &tmA, &full_bar[stage], c0, w0 + dx, h0 + m * TILE_H + dy, b);
-                    tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.Cin + c0, n0);
                 } else {
-                    const int c0 = (ks - nk1) * KCHUNK;
-#pragma unroll
-                    for (int m = 0; m < MT; ++m)
-                        tma_load_4d(sA + m * A_BYTES, &tmA2, &full_bar[stage], c0, w0, h0 + m * TILE_H, b);
-                    tma_load_2d(sB, &tmB2, &full_bar[stage], c0, n0);
+                    const bool aux = g >= ng1;
+                    const int c0 = (aux ? g - ng1 : g) * KCHUNK;
+                    mbar_arrive_expect_tx(&a_full[sa], MT * A_BYTES);
+                    tma_load_4d(sA, aux ? &tmA2 : &tmA, &a_full[sa], c0, w0, h0, b);
+                    const int sb = ib % NB;
+                    mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
+                    ++ib;
+                    mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
+                    tma_load_2d(smemB + sb * Cfg::B_STAGE, aux ? &tmB2 : &tmB, &b_full[sb], c0, n0);
                 }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-        uint32_t it = 0, lt = 0;  // global k-step counter, local tile counter
+        uint32_t ia = 0, ib = 0, lt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
             const int acc = lt % NACC;
             mbar_wait(&tmem_empty_bar[acc], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
-            for (int ks = 0; ks < nk; ++ks, ++it) {
-                const int stage = it % NST;
-                const uint32_t phase = (it / NST) & 1;
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                const uint32_t sB = sA + MT * A_BYTES;
-                const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+            uint32_t started = 0;  // 0 until the first MMA of this tile has been issued (per sub-tile: same flag)
+            for (int g = 0; g < ng; ++g) {
+                const int sa = ia % NA;
+                mbar_wait(&a_full[sa], (ia / NA) & 1);
+                ++ia;
+                const uint32_t sA = smem_u32(smemA + sa * Cfg::A_STAGE);
+                const bool is_halo = (g < ng1) && halo;
+                const int nsteps = is_halo ? 3 : 1;
+                for (int j = 0; j < nsteps; ++j) {
+                    const int sb = ib % NB;
+                    mbar_wait(&b_full[sb], (ib / NB) & 1);
+                    ++ib;
+                    tc_fence_after();
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + sb * Cfg::B_STAGE), 16, 1024);
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const uint64_t adesc = make_smem_desc_sw128(sA + m * A_BYTES, 16, 1024);
+                    for (int m = 0; m < MT; ++m) {
+                        // halo box: sub-tile m, vertical tap j starts (m*8 + j) image rows into the box
+                        const uint32_t a_off = is_halo ? (m * TILE_H + j) * ROW_BYTES : m * A_BYTES;
+                        const uint64_t adesc = make_smem_desc_sw128(sA + a_off, 16, 1024);
 #pragma unroll
-                    for (int kk = 0; kk < KCHUNK / 8; ++kk) {
-                        // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-                        umma_tf32(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < KCHUNK / 8; ++kk) {
+                            // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
+                            umma_tf32(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (started | kk) ? 1u : 0u);
+                        }
                     }
+                    started = 1;
+                    umma_commit(&b_empty[sb]);  // frees the weight slot once these MMAs have read it
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                umma_commit(&a_empty[sa]);      // frees the activation box
             }
-            umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+            umma_commit(&tmem_full_bar[acc]);   // accumulator complete
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -363,11 +391,12 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     const bool has_main = a.ntaps > 0;
     const bool has_aux = a.K2 > 0;
     if (has_main) {
-        if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, TILE_H))) return rc;
+        // 3x3: halo box (MT*8 + 2 image rows) shared by the three vertical taps; pointwise: plain box
+        if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, a.ntaps == 9 ? Cfg::A_ROWS : MT * TILE_H))) return rc;
         if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, BN, 0))) return rc;
     }
     if (has_aux) {
-        if ((rc = make_tmap_nhwc(&tmA2, a.in2, a.B, a.H, a.W, a.K2, TILE_W, TILE_H))) return rc;
+        if ((rc = make_tmap_nhwc(&tmA2, a.in2, a.B, a.H, a.W, a.K2, TILE_W, MT * TILE_H))) return rc;
         if ((rc = make_tmap_2d(&tmB2, a.w2, a.Cout, a.K2, BN, 0))) return rc;
     }
     if (!has_main) { tmA = tmA2; tmB = tmB2; }
