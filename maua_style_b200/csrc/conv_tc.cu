@@ -136,7 +136,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         n0 = nt * BN;
     };
 
-    if (warp == 0 && lane == 0) {
+    // The producer and MMA roles run with the whole warp converged; a single lane chosen by elect.sync issues the TMA /
+    // tcgen05 instructions.  (Entering these loops with only lane 0 active makes ptxas wrap every UTCHMMA in an
+    // ELECT / BRA.U.ANY loop, which makes the short N = 64 MMAs issue-bound.)
+    if (warp == 0) {
         // ===================== TMA producer =====================
         uint32_t ia = 0, ib = 0;  // ring counters across tiles
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -150,29 +153,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (g < ng1 && halo) {
                     const int dxi = g / cpt;                  // 0..2  <->  dx = -1, 0, +1
                     const int c0 = (g - dxi * cpt) * KCHUNK;
-                    mbar_arrive_expect_tx(&a_full[sa], Cfg::A_STAGE);
-                    tma_load_4d(sA, &tmA, &a_full[sa], c0, w0 + dxi - 1, h0 - 1, b);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&a_full[sa], Cfg::A_STAGE);
+                        tma_load_4d(sA, &tmA, &a_full[sa], c0, w0 + dxi - 1, h0 - 1, b);
+                    }
+                    __syncwarp();
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         const int sb = ib % NB;
                         mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
                         ++ib;
-                        mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
-                        tma_load_2d(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * 3 + dxi) * p.Cin + c0, n0);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
+                            tma_load_2d(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * 3 + dxi) * p.Cin + c0, n0);
+                        }
+                        __syncwarp();
                     }
                 } else {
                     const bool aux = g >= ng1;
                     const int c0 = (aux ? g - ng1 : g) * KCHUNK;
-                    mbar_arrive_expect_tx(&a_full[sa], MT * A_BYTES);
-                    tma_load_4d(sA, aux ? &tmA2 : &tmA, &a_full[sa], c0, w0, h0, b);
                     const int sb = ib % NB;
                     mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
                     ++ib;
-                    mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
-                    tma_load_2d(smemB + sb * Cfg::B_STAGE, aux ? &tmB2 : &tmB, &b_full[sb], c0, n0);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&a_full[sa], MT * A_BYTES);
+                        tma_load_4d(sA, aux ? &tmA2 : &tmA, &a_full[sa], c0, w0, h0, b);
+                        mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
+                        tma_load_2d(smemB + sb * Cfg::B_STAGE, aux ? &tmB2 : &tmB, &b_full[sb], c0, n0);
+                    }
+                    __syncwarp();
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
         uint32_t ia = 0, ib = 0, lt = 0;
@@ -194,24 +206,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&b_full[sb], (ib / NB) & 1);
                     ++ib;
                     tc_fence_after();
-                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + sb * Cfg::B_STAGE), 16, 1024);
+                    if (elect_one()) {
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + sb * Cfg::B_STAGE), 16, 1024);
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        // halo box: sub-tile m, vertical tap j starts (m*8 + j) image rows into the box
-                        const uint32_t a_off = is_halo ? (m * TILE_H + j) * ROW_BYTES : m * A_BYTES;
-                        const uint64_t adesc = make_smem_desc_sw128(sA + a_off, 16, 1024);
+                        for (int m = 0; m < MT; ++m) {
+                            // halo box: sub-tile m, vertical tap j starts (m*8 + j) image rows into the box
+                            const uint32_t a_off = is_halo ? (m * TILE_H + j) * ROW_BYTES : m * A_BYTES;
+                            const uint64_t adesc = make_smem_desc_sw128(sA + a_off, 16, 1024);
 #pragma unroll
-                        for (int kk = 0; kk < KCHUNK / 8; ++kk) {
-                            // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-                            umma_tf32(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (started | kk) ? 1u : 0u);
+                            for (int kk = 0; kk < KCHUNK / 8; ++kk) {
+                                // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
+                                umma_tf32(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (started | kk) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&b_empty[sb]);  // frees the weight slot once these MMAs have read it
+                        if (j == nsteps - 1) umma_commit(&a_empty[sa]);  // ... and the activation box after its last tap
+                        if (j == nsteps - 1 && g == ng - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
                     }
+                    __syncwarp();
                     started = 1;
-                    umma_commit(&b_empty[sb]);  // frees the weight slot once these MMAs have read it
                 }
-                umma_commit(&a_empty[sa]);      // frees the activation box
             }
-            umma_commit(&tmem_full_bar[acc]);   // accumulator complete
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================

@@ -91,37 +91,44 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0 && lane == 0) {
+    // producer / MMA roles run warp-converged; one lane chosen by elect.sync issues (see conv_tc.cu)
+    if (warp == 0) {
         for (int ks = 0; ks < nk; ++ks) {
             const int stage = ks % NST;
             const uint32_t phase = (ks / NST) & 1;
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sB = sA + Cfg::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], (boxesA + boxesB) * BOX_BYTES);
-            const int prow = (int)((st0 + ks) * GK);
-            for (int bx = 0; bx < boxesA; ++bx) tma_load_2d(sA + bx * BOX_BYTES, &tmF, &full_bar[stage], m0 + bx * 32, prow);
-            for (int bx = 0; bx < boxesB; ++bx) tma_load_2d(sB + bx * BOX_BYTES, &tmF, &full_bar[stage], n0 + bx * 32, prow);
+            if (elect_one()) {
+                uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + Cfg::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], (boxesA + boxesB) * BOX_BYTES);
+                const int prow = (int)((st0 + ks) * GK);
+                for (int bx = 0; bx < boxesA; ++bx) tma_load_2d(sA + bx * BOX_BYTES, &tmF, &full_bar[stage], m0 + bx * 32, prow);
+                for (int bx = 0; bx < boxesB; ++bx) tma_load_2d(sB + bx * BOX_BYTES, &tmF, &full_bar[stage], n0 + bx * 32, prow);
+            }
+            __syncwarp();
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_tf32(128, BN, 1, 1);  // both operands MN-major
         for (int ks = 0; ks < nk; ++ks) {
             const int stage = ks % NST;
             const uint32_t phase = (ks / NST) & 1;
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t sB = (OFFDIAG && !diag) ? sA + Cfg::A_BYTES : sA;
+            if (elect_one()) {
+                const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t sB = (OFFDIAG && !diag) ? sA + Cfg::A_BYTES : sA;
 #pragma unroll
-            for (int kk = 0; kk < GK / 8; ++kk) {
-                // MN-major TF32: layout type 1 (128B swizzle, 32-byte atoms): 4-row x 128 B atoms, SBO = 512 B
-                const uint64_t adesc = make_smem_desc(sA + kk * 1024, BOX_BYTES, 512, 1);
-                const uint64_t bdesc = make_smem_desc(sB + kk * 1024, BOX_BYTES, 512, 1);
-                umma_tf32(tmem_base, adesc, bdesc, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < GK / 8; ++kk) {
+                    // MN-major TF32: layout type 1 (128B swizzle, 32-byte atoms): 4-row x 128 B atoms, SBO = 512 B
+                    const uint64_t adesc = make_smem_desc(sA + kk * 1024, BOX_BYTES, 512, 1);
+                    const uint64_t bdesc = make_smem_desc(sB + kk * 1024, BOX_BYTES, 512, 1);
+                    umma_tf32(tmem_base, adesc, bdesc, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (ks == nk - 1) umma_commit(tmem_full_bar);
             }
-            umma_commit(&empty_bar[stage]);
+            __syncwarp();
         }
-        umma_commit(tmem_full_bar);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
