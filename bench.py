@@ -306,21 +306,21 @@ def run_ours(args):
     gpu_launches = K * (fwd_l + bwd_l) + opt_l
 
     # ---- end to end with host buffers (pinned), every step H2D pastiche + D2H result ----
-    host_in = pastiche.detach().cpu().pin_memory()
-    host_out = torch.empty_like(host_in).pin_memory()
+    host = [pastiche.detach().cpu().pin_memory(), torch.empty_like(pastiche, device="cpu").pin_memory()]
     host_loss = torch.empty(1).pin_memory()
     total_dev = torch.zeros(1, device=dev)
 
     def step_e2e():
-        pastiche.copy_(host_in, non_blocking=True)
+        host_in, host_out = host
+        pastiche.copy_(host_in, non_blocking=True)       # H2D: this step's input image from pinned host memory
         net._forward_plan(pastiche, keep=True)
         g = net._backward_plan(up)
         opt.step(g)
         torch.sum(net._loss_vec, dim=0, keepdim=True, out=total_dev)
-        host_out.copy_(pastiche, non_blocking=True)
-        host_loss.copy_(total_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller holds the result on the host
-        host_in.copy_(host_out)                    # next step's input is the previous result (host side)
+        host_out.copy_(pastiche, non_blocking=True)      # D2H: the updated image ...
+        host_loss.copy_(total_dev, non_blocking=True)    # ... and the total loss
+        torch.cuda.current_stream().synchronize()        # the caller holds the result on the host
+        host[0], host[1] = host_out, host_in             # next step's input is this step's result (host side)
 
     for _ in range(min(W, 3)):
         step_e2e()

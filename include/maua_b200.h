@@ -199,6 +199,11 @@ typedef struct maua_image_io {
 } maua_image_io;
 
 MAUA_API int maua_plan_create(int device, const maua_net_desc* desc, maua_plan_t** out);
+/* One stage of the layer-wise multidevice split (models.py:503-566 ModelParallel / setup_multi_device): a plan over
+ * entries [entry_begin, entry_end) of `desc` on `device`.  A stage must begin with a conv entry.  Tap indices stay
+ * global: taps outside the range are ignored by this stage.  Weight pointers may live on another device. */
+MAUA_API int maua_plan_create_stage(int device, const maua_net_desc* desc, int entry_begin, int entry_end,
+                                    maua_plan_t** out);
 MAUA_API void maua_plan_destroy(maua_plan_t* plan);
 /* Bytes of device memory the plan currently owns (weights + workspaces), for capacity planning. */
 MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* plan);
@@ -215,6 +220,26 @@ MAUA_API int maua_plan_forward(maua_plan_t* plan, const float* image, int h, int
  * maua_loss_grad_coefs); writes d(sum)/d(image) NCHW into grad_image. */
 MAUA_API int maua_plan_backward(maua_plan_t* plan, const float* grad_coefs, float* grad_image,
                                 maua_stream_t stream);
+/* Stage variants (models.py:517-525 ModelParallel.forward and the autograd mirror of its `.to(device)` hops).
+ *   forward : `input` is the NCHW image (entry_begin == 0) or the NHWC [h][w][C] activation handed over by the previous
+ *             stage (h, w = its extent); boundary_out (NULL for the last stage) receives this stage's last activation --
+ *             it may be memory of the NEXT stage's device (peer access enabled, maua_enable_peer_access): the producing
+ *             conv epilogue / pool kernel stores into it directly over NVLink, there is no separate copy.
+ *   backward: grad_top (NULL for the last stage) is d loss / d boundary_out as written by the next stage's backward;
+ *             grad_out is the NCHW image gradient (entry_begin == 0) or the NHWC gradient w.r.t. `input`, again possibly
+ *             peer memory (the previous stage's grad_top).
+ * Ordering between the stages' streams is the caller's job (events), exactly like the reference's stream-ordered
+ * `.to(device)`. */
+MAUA_API int maua_plan_forward_stage(maua_plan_t* plan, const float* input, int h, int w, const maua_tap_io* taps,
+                                     const maua_image_io* image_io, float* losses_out, int keep_for_backward,
+                                     float* boundary_out, maua_stream_t stream);
+MAUA_API int maua_plan_backward_stage(maua_plan_t* plan, const float* grad_coefs, const float* grad_top,
+                                      float* grad_out, maua_stream_t stream);
+/* cudaDeviceEnablePeerAccess in both directions; MAUA_STATUS_CUDA if the devices are not peers. */
+MAUA_API int maua_enable_peer_access(int device_a, int device_b);
+/* Extent of the stage's last activation for an input of h x w (what boundary_out must hold): NHWC [*oh][*ow][*oc]. */
+MAUA_API int maua_plan_stage_output_shape(const maua_plan_t* plan, int h, int w, int* oh, int* ow, int* oc);
+
 /* ScaleGradients (loss.py:10-20) + strength bookkeeping on the device: for module i with upstream gradient
  * up[i], coef[i] = sum over its loss terms of  normalize ? sg(up*term_scale)*strength^2 : up*term_scale,
  * sg(x) = x/(|x|+1e-8).  term scales: style {strength, vsf*strength (if vsf>0)}, content {strength},

@@ -297,6 +297,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4*>(ep.out + off + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (ep.out2) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(ep.out2 + off + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
                     }
                 }
             }
@@ -499,6 +504,7 @@ __global__ void conv_ref_kernel(ConvArgs a) {
         if (ep.mask_src) v = ep.mask_src[idx] > 0.f ? v : 0.f;
         if (ep.round) v = round_tf32(v);
         ep.out[idx] = v;
+        if (ep.out2) ep.out2[idx] = v;
     }
 }
 }  // namespace

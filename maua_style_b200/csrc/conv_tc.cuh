@@ -15,6 +15,8 @@ namespace maua {
 //   v  = round_tf32(v)                   (operand rounding for the consuming MMA)     if round
 struct ConvEpilogue {
     float* out = nullptr;             // NHWC [B][H][W][Cout]
+    float* out2 = nullptr;            // optional second copy of the output (layer-wise split: the next stage's input,
+                                      // usually peer memory reached over NVLink -- stored tile by tile from the epilogue)
     const float* bias = nullptr;      // [Cout]
     const float* mask_src = nullptr;  // NHWC like out
     const float* cont_f = nullptr;    // NHWC like out

@@ -32,7 +32,8 @@ namespace {
 struct Entry {
     bool pool = false;
     int cin = 0, cout = 0;     // conv only
-    int conv_index = -1;       // = relu index
+    int conv_index = -1;       // = relu index (global, counted from conv1_1)
+    bool image_layer = false;  // conv1_1: consumes the NCHW image (conv_edge.cu)
     float* w_raw = nullptr;    // OIHW copy (first conv only needs it, kept for all: 52 MB total)
     float* wg = nullptr;       // forward GEMM weights  [cout][9*cin]
     float* wd = nullptr;       // dgrad GEMM weights    [cin][9*cout]
@@ -95,6 +96,11 @@ using namespace maua;
 struct maua_plan {
     int device = 0;
     int impl = MAUA_IMPL_TC;
+    // layer-wise split (models.py:503-566): this plan covers global entries [begin, begin + entries.size())
+    int begin = 0;
+    int in_C = 3;                 // channels of the stage input (3 = the image)
+    bool last_stage = true;
+    const float* stage_input = nullptr;  // NHWC boundary activation of the last forward (begin > 0)
     std::vector<Entry> entries;
     std::vector<Tap> taps;
     int avg_pool = 0;
@@ -200,20 +206,23 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
 
 }  // namespace
 
-extern "C" {
-
-MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** out) {
+static int plan_create_impl(int device, const maua_net_desc* d, int begin, int end, maua_plan_t** out) {
     MAUA_REQUIRE(d && out, "maua_plan_create: null argument");
     MAUA_REQUIRE(d->n_entries >= 1 && d->n_entries <= MAUA_MAX_LAYERS, "maua_plan_create: bad n_entries %d", d->n_entries);
     MAUA_REQUIRE(d->n_taps >= 0 && d->n_taps <= MAUA_MAX_TAPS, "maua_plan_create: bad n_taps %d", d->n_taps);
+    MAUA_REQUIRE(begin >= 0 && begin < end && end <= d->n_entries, "maua_plan_create_stage: bad entry range [%d, %d) of %d",
+                 begin, end, d->n_entries);
     int rc = check_device_arch(device);
     if (rc) return rc;
     DeviceGuard guard(device);
     MAUA_REQUIRE(d->channels[0] > 0, "maua_plan_create: the network must start with a conv layer");
+    MAUA_REQUIRE(d->channels[begin] > 0, "maua_plan_create_stage: a stage must begin with a conv layer (entry %d is a pool)", begin);
 
     maua_plan* p = new maua_plan();
     p->device = device;
     p->avg_pool = d->avg_pool;
+    p->begin = begin;
+    p->last_stage = (end == d->n_entries);
     memset(&p->img_io, 0, sizeof(p->img_io));
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** ptr, size_t bytes) {
@@ -224,7 +233,12 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
     };
     int cin = 3, convs = 0;
     bool ok = true;
-    for (int i = 0; i < d->n_entries && ok; ++i) {
+    for (int i = 0; i < end && ok; ++i) {
+        if (i == begin) p->in_C = cin;
+        if (i < begin) {  // entries of earlier stages: only track channel / conv counters
+            if (d->channels[i] > 0) { cin = d->channels[i]; convs++; }
+            continue;
+        }
         Entry en;
         if (d->channels[i] == 0) {
             en.pool = true;
@@ -235,6 +249,7 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
             en.cout = d->channels[i];
             en.C = en.cout;
             en.conv_index = convs++;
+            en.image_layer = (i == 0);
             if (i > 0 && !(en.cin % 32 == 0 && en.cout % 64 == 0)) {
                 set_last_error("conv %d: %d -> %d channels unsupported by the tcgen05 path (need Cin %% 32 == 0, Cout %% 64 == 0); "
                                "only VGG-16/19-shaped stacks are supported", en.conv_index, en.cin, en.cout);
@@ -258,8 +273,9 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
                 alloc((void**)&en.wg, wn * sizeof(float));
                 alloc((void**)&en.wd, wn * sizeof(float));
             }
-            if (e == cudaSuccess) e = cudaMemcpy(en.w_raw, d->weights[i], wn * sizeof(float), cudaMemcpyDeviceToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(en.bias, d->biases[i], (size_t)en.cout * sizeof(float), cudaMemcpyDeviceToDevice);
+            // the checkpoint tensors may live on another device (the first stage's): peer-capable default copy
+            if (e == cudaSuccess) e = cudaMemcpy(en.w_raw, d->weights[i], wn * sizeof(float), cudaMemcpyDefault);
+            if (e == cudaSuccess) e = cudaMemcpy(en.bias, d->biases[i], (size_t)en.cout * sizeof(float), cudaMemcpyDefault);
             if (i == 0) {
                 alloc((void**)&en.wt1, (size_t)32 * en.cout * sizeof(float));
                 if (e == cudaSuccess && conv_first_dgrad_prep_weights(en.w_raw, en.wt1, en.cout, 0)) ok = false;
@@ -273,14 +289,20 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
         }
         p->entries.push_back(en);
     }
-    // taps
+    // taps (global indexing; taps that belong to another stage keep entry = -1 and are ignored by this plan)
     for (int t = 0; t < d->n_taps && ok && e == cudaSuccess; ++t) {
         Tap tp;
         tp.kind = d->tap_kind[t];
         tp.relu_index = d->tap_relu_index[t];
+        bool in_net = false;
+        {
+            int convs_seen = 0;
+            for (int i = 0; i < d->n_entries; ++i)
+                if (d->channels[i] > 0 && convs_seen++ == tp.relu_index) in_net = true;
+        }
         for (size_t i = 0; i < p->entries.size(); ++i)
             if (!p->entries[i].pool && p->entries[i].conv_index == tp.relu_index) tp.entry = (int)i;
-        if (tp.entry < 0) {
+        if (!in_net) {
             set_last_error("tap %d refers to relu index %d which is not in the network", t, tp.relu_index);
             ok = false;
             break;
@@ -291,24 +313,26 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
             break;
         }
         for (int u = 0; u < t; ++u)
-            if (p->taps[u].entry == tp.entry && p->taps[u].kind == tp.kind) {
+            if (d->tap_relu_index[u] == tp.relu_index && d->tap_kind[u] == tp.kind) {
                 set_last_error("two taps of the same kind on relu index %d", tp.relu_index);
                 ok = false;
             }
-        tp.C = p->entries[tp.entry].cout;
-        if (tp.kind == MAUA_TAP_STYLE) {
-            if (!(tp.C == 64 || tp.C % 128 == 0)) {
-                set_last_error("style tap on %d channels unsupported", tp.C);
-                ok = false;
-                break;
+        if (tp.entry >= 0) {
+            tp.C = p->entries[tp.entry].cout;
+            if (tp.kind == MAUA_TAP_STYLE) {
+                if (!(tp.C == 64 || tp.C % 128 == 0)) {
+                    set_last_error("style tap on %d channels unsupported", tp.C);
+                    ok = false;
+                    break;
+                }
+                const size_t cc = (size_t)tp.C * tp.C * sizeof(float);
+                alloc((void**)&tp.gram, cc);
+                alloc((void**)&tp.diff, cc);
+                alloc((void**)&tp.aux_d, cc);
+                alloc((void**)&tp.mean, tp.C * sizeof(float));
+                alloc((void**)&tp.aux_bias, tp.C * sizeof(float));
+                alloc(&tp.gram_ws, gram_workspace_bytes(tp.C));
             }
-            const size_t cc = (size_t)tp.C * tp.C * sizeof(float);
-            alloc((void**)&tp.gram, cc);
-            alloc((void**)&tp.diff, cc);
-            alloc((void**)&tp.aux_d, cc);
-            alloc((void**)&tp.mean, tp.C * sizeof(float));
-            alloc((void**)&tp.aux_bias, tp.C * sizeof(float));
-            alloc(&tp.gram_ws, gram_workspace_bytes(tp.C));
         }
         p->taps.push_back(tp);
     }
@@ -327,6 +351,18 @@ MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** 
     }
     *out = p;
     return MAUA_OK;
+}
+
+extern "C" {
+
+MAUA_API int maua_plan_create(int device, const maua_net_desc* d, maua_plan_t** out) {
+    MAUA_REQUIRE(d && out, "maua_plan_create: null argument");
+    return plan_create_impl(device, d, 0, d->n_entries, out);
+}
+
+MAUA_API int maua_plan_create_stage(int device, const maua_net_desc* d, int entry_begin, int entry_end, maua_plan_t** out) {
+    MAUA_REQUIRE(d && out, "maua_plan_create_stage: null argument");
+    return plan_create_impl(device, d, entry_begin, entry_end, out);
 }
 
 MAUA_API void maua_plan_destroy(maua_plan_t* p) {
@@ -390,17 +426,24 @@ MAUA_API int maua_plan_last_launches(const maua_plan_t* p, int* fwd, int* bwd) {
     return MAUA_OK;
 }
 
-MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W, const maua_tap_io* tio,
-                               const maua_image_io* iio, float* losses_out, int keep_for_backward,
-                               maua_stream_t stream) {
+}  // extern "C"
+
+// `image` is the NCHW image for a plan that starts at conv1_1, else the NHWC [H][W][in_C] boundary activation produced
+// by the previous stage.  boundary_out (optional, may be peer memory) additionally receives the last entry's output.
+static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, const maua_tap_io* tio,
+                             const maua_image_io* iio, float* losses_out, int keep_for_backward, float* boundary_out,
+                             maua_stream_t stream) {
     MAUA_REQUIRE(p && image && H >= 1 && W >= 1, "maua_plan_forward: bad arguments");
     MAUA_REQUIRE(p->taps.empty() || tio, "maua_plan_forward: tap io missing");
+    MAUA_REQUIRE(p->begin == 0 || (reinterpret_cast<uintptr_t>(image) & 15) == 0, "stage input must be 16-byte aligned");
     DeviceGuard guard(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_workspaces(p, H, W);
     if (rc) return rc;
     p->can_backward = false;
     p->H = H; p->W = W; p->image = image;
+    p->stage_input = p->begin > 0 ? image : nullptr;
+    if (p->begin > 0) iio = nullptr;  // TVLoss / temporal ContentLoss sit on the image: first stage only
     p->launches_fwd = 0;
     const int nt = (int)p->taps.size();
     ReduceScratch rs = scratch_from_workspace(p->reduce_ws);
@@ -446,35 +489,43 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
     int last_needed = -1;
     for (int t = 0; t < nt; ++t) {
         Tap& tp = p->taps[t];
-        tp.mode = tio[t].mode;
+        tp.mode = tp.entry >= 0 ? tio[t].mode : MAUA_MODE_NONE;
         tp.active = false;
         tp.use_cov = tio[t].use_covariance;
         tp.target = tio[t].target;
         if (tp.mode != MAUA_MODE_NONE) last_needed = tp.entry > last_needed ? tp.entry : last_needed;
     }
+    const int n_ent = (int)p->entries.size();
+    if (boundary_out) last_needed = n_ent - 1;  // the next stage consumes this stage's last activation
     p->last_entry = last_needed;
 
     // ---- feature stack ----
-    const float* cur = nullptr;
+    const float* cur = p->stage_input;
     int curH = H, curW = W;
     for (int i = 0; i <= last_needed; ++i) {
         Entry& e = p->entries[i];
-        if (i == 0) {
+        float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
+        if (e.image_layer) {
             if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, 1, H, W, e.cout, 1, st))) return rc;
+            if (hand_off)
+                MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
         } else if (e.pool) {
-            if ((rc = pool_fwd_launch(cur, e.out, 1, curH, curW, e.C, p->avg_pool, st))) return rc;
+            // a pooled map is not needed again by this stage (the backward pass reads the pre-pool activation), so at a
+            // stage boundary it is written straight into the next stage's memory
+            if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, st))) return rc;
         } else {
             ConvArgs a;
             a.B = 1; a.H = e.H; a.W = e.W; a.Cin = e.cin; a.Cout = e.cout; a.ntaps = 9;
             a.in = cur; a.wg = e.wg;
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = 1;
+            a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             rc = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
             if (rc) return rc;
         }
         p->launches_fwd++;
         {
             const double px = (double)e.H * e.W;
-            if (i == 0) prof_mark(p, st, "conv_first_fwd", i, 2.0 * 27 * e.cout * px, 4.0 * (3 + e.cout) * px);
+            if (e.image_layer) prof_mark(p, st, "conv_first_fwd", i, 2.0 * 27 * e.cout * px, 4.0 * (3 + e.cout) * px);
             else if (e.pool) prof_mark(p, st, "pool_fwd", i, 0, 4.0 * 5 * e.C * px);
             else prof_mark(p, st, "conv_fwd", i, 2.0 * 9 * e.cin * e.cout * px, 4.0 * (e.cin + e.cout) * px);
         }
@@ -531,6 +582,23 @@ MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W,
     return MAUA_OK;
 }
 
+extern "C" {
+
+MAUA_API int maua_plan_forward(maua_plan_t* p, const float* image, int H, int W, const maua_tap_io* tio,
+                               const maua_image_io* iio, float* losses_out, int keep_for_backward,
+                               maua_stream_t stream) {
+    MAUA_REQUIRE(p && p->begin == 0 && p->last_stage,
+                 "maua_plan_forward: this plan is one stage of a layer-wise split, use maua_plan_forward_stage");
+    return plan_forward_impl(p, image, H, W, tio, iio, losses_out, keep_for_backward, nullptr, stream);
+}
+
+MAUA_API int maua_plan_forward_stage(maua_plan_t* p, const float* input, int H, int W, const maua_tap_io* tio,
+                                     const maua_image_io* iio, float* losses_out, int keep_for_backward,
+                                     float* boundary_out, maua_stream_t stream) {
+    MAUA_REQUIRE(p, "maua_plan_forward_stage: null plan");
+    return plan_forward_impl(p, input, H, W, tio, iio, losses_out, keep_for_backward, boundary_out, stream);
+}
+
 MAUA_API int maua_loss_grad_coefs(const float* upstream, float* coefs, int n, const float* strength, const float* vsf,
                                   const int* normalize, const int* kind, maua_stream_t stream) {
     MAUA_REQUIRE(upstream && coefs && strength && vsf && normalize && kind && n >= 1 && n <= MAUA_MAX_TAPS + 2,
@@ -545,7 +613,13 @@ MAUA_API int maua_loss_grad_coefs(const float* upstream, float* coefs, int n, co
     return MAUA_OK;
 }
 
-MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* grad_image, maua_stream_t stream) {
+}  // extern "C"
+
+// grad_top (optional): d(sum of the later stages' losses) / d(this stage's last activation), produced by the next stage
+// of a layer-wise split.  grad_image: NCHW image gradient for a plan that starts at conv1_1, else the NHWC gradient
+// w.r.t. the stage input (unmasked, unrounded: the previous stage owns the activation and applies the ReLU mask).
+static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const float* grad_top, float* grad_image,
+                              maua_stream_t stream) {
     MAUA_REQUIRE(p && grad_coefs && grad_image, "maua_plan_backward: null argument");
     if (!p->can_backward) {
         set_last_error("maua_plan_backward: no forward pass with keep_for_backward is pending");
@@ -615,32 +689,53 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
     int e_idx = -1;  // highest entry with a live loss module
     for (int t = 0; t < nt; ++t)
         if (p->taps[t].active && p->taps[t].entry > e_idx) e_idx = p->taps[t].entry;
-    if (e_idx >= 0) {
-        // top of the stack: only tap gradients
+    if (grad_top) {
+        MAUA_REQUIRE(p->last_entry == (int)p->entries.size() - 1, "maua_plan_backward_stage: grad_top given but the last "
+                     "forward did not run to the end of the stage");
+        e_idx = p->last_entry;
+    }
+    if (e_idx >= 0 && p->entries[e_idx].pool) {
+        // (stage boundary after a pool) grad_top is the gradient w.r.t. the pooled map: un-pool + mask (+ tap gradients)
+        const int prod = e_idx - 1;
+        MAUA_REQUIRE(prod >= 0 && !p->entries[prod].pool, "unsupported network: two pools in a row");
+        Entry& ep_ = p->entries[prod];
+        Tap *style, *content; int ci;
+        taps_at(prod, style, content, ci);
+        float* addend = nullptr;
+        if (style || content) {
+            ConvArgs t;
+            t.B = 1; t.H = ep_.H; t.W = ep_.W; t.Cin = 32; t.Cout = ep_.C; t.ntaps = 0;
+            add_taps(t, ep_, style, content, ci);
+            t.ep.out = take_buf(); t.ep.round = 0;
+            if (style) { if ((rc = run_conv(t))) return rc; }
+            else { if ((rc = conv_ref_launch(t, st))) return rc; p->launches_bwd++; }
+            addend = t.ep.out;
+        }
+        float* outb = take_buf();
+        if ((rc = pool_bwd_launch(ep_.out, grad_top, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, 1, st))) return rc;
+        p->launches_bwd++;
+        prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
+        gm = outb;
+        gm_entry = prod;
+    } else if (e_idx >= 0) {
+        // top of the stack: only tap gradients (+ the gradient handed down by the next stage)
         Entry& e = p->entries[e_idx];
         Tap *style, *content; int ci;
         taps_at(e_idx, style, content, ci);
-        if (style || content) {
-            if (!style) {
-                // content only: needs a GEMM-free path; express it as aux GEMM with a zero matrix is wasteful, so
-                // use the reference-kernel epilogue path via ntaps = 0, K2 = 0 is not allowed -> fall through to
-                // the generic SIMT kernel which handles an empty GEMM.
-                ConvArgs a;
-                a.B = 1; a.H = e.H; a.W = e.W; a.Cin = 32; a.Cout = e.C; a.ntaps = 0; a.K2 = 0;
-                a.ep.out = take_buf(); a.ep.mask_src = e.out; a.ep.round = 1;
-                a.ep.cont_f = e.out; a.ep.cont_t = content->target; a.ep.cont_coef = p->coef2 + ci;
+        if (style || content || grad_top) {
+            ConvArgs a;
+            a.B = 1; a.H = e.H; a.W = e.W; a.Cin = 32; a.Cout = e.C; a.ntaps = 0; a.K2 = 0;
+            add_taps(a, e, style, content, ci);
+            a.ep.out = take_buf(); a.ep.mask_src = e.out; a.ep.round = 1; a.ep.addend = grad_top;
+            if (style) {
+                if ((rc = run_conv(a))) return rc;
+            } else {
+                // no GEMM term (content-only tap and / or a handed-down gradient): element-wise SIMT epilogue
                 if ((rc = conv_ref_launch(a, st))) return rc;
                 p->launches_bwd++;
                 prof_mark(p, st, "tap_grad", e.C, 0, 16.0 * e.C * e.H * e.W);
-                gm = a.ep.out;
-            } else {
-                ConvArgs a;
-                a.B = 1; a.H = e.H; a.W = e.W; a.Cin = 32; a.Cout = e.C; a.ntaps = 0;
-                add_taps(a, e, style, content, ci);
-                a.ep.out = take_buf(); a.ep.mask_src = e.out; a.ep.round = 1;
-                if ((rc = run_conv(a))) return rc;
-                gm = a.ep.out;
             }
+            gm = a.ep.out;
             gm_entry = e_idx;
         }
     }
@@ -690,6 +785,22 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
         gm_entry = prod;
     }
 
+    if (p->begin > 0) {
+        // stage of a layer-wise split: hand d/d(stage input) to the previous stage (may be a peer-memory store)
+        Entry& e0 = p->entries[0];
+        const size_t in_elems = (size_t)e0.H * e0.W * e0.cin;
+        if (gm && gm_entry == 0) {
+            ConvArgs a;
+            a.B = 1; a.H = e0.H; a.W = e0.W; a.Cin = e0.cout; a.Cout = e0.cin; a.ntaps = 9;
+            a.in = gm; a.wg = e0.wd;
+            a.ep.out = grad_image; a.ep.round = 0;
+            if ((rc = run_conv(a))) return rc;
+        } else {
+            MAUA_CUDA_CHECK(cudaMemsetAsync(grad_image, 0, in_elems * sizeof(float), st));
+        }
+        return MAUA_OK;
+    }
+
     // image-side tail
     ImageTail tail;
     const bool tv = p->img_io.tv_mode == MAUA_MODE_LOSS;
@@ -701,8 +812,8 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
         tail.temp_weights = p->img_io.temporal_weights;
         tail.temp_coef = p->coef2 + nt + 1;
     }
+    Entry& e0 = p->entries[0];
     if (gm && gm_entry == 0) {
-        Entry& e0 = p->entries[0];
         float* T = take_buf();
         if (T == gm) T = take_buf();
         if ((rc = conv_first_dgrad_launch(gm, e0.wt1, grad_image, 1, H, W, e0.cout, tail, T, p->impl, st))) return rc;
@@ -710,12 +821,65 @@ MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* 
         prof_mark(p, st, "conv_first_dgrad", 0, 2.0 * 27 * e0.cout * H * W, 4.0 * (e0.cout + 6) * H * W);
     } else {
         // no feature-space loss is active: only TV / temporal terms (or nothing at all)
-        MAUA_CUDA_CHECK(cudaMemsetAsync(p->gbuf[0], 0, (size_t)H * W * p->entries[0].cout * sizeof(float), st));
-        Entry& e0 = p->entries[0];
+        MAUA_CUDA_CHECK(cudaMemsetAsync(p->gbuf[0], 0, (size_t)H * W * e0.cout * sizeof(float), st));
         if ((rc = conv_first_dgrad_launch(p->gbuf[0], e0.wt1, grad_image, 1, H, W, e0.cout, tail, p->gbuf[1], p->impl, st)))
             return rc;
         p->launches_bwd += 2;
     }
+    return MAUA_OK;
+}
+
+extern "C" {
+
+MAUA_API int maua_plan_backward(maua_plan_t* p, const float* grad_coefs, float* grad_image, maua_stream_t stream) {
+    MAUA_REQUIRE(p && p->begin == 0 && p->last_stage,
+                 "maua_plan_backward: this plan is one stage of a layer-wise split, use maua_plan_backward_stage");
+    return plan_backward_impl(p, grad_coefs, nullptr, grad_image, stream);
+}
+
+MAUA_API int maua_plan_backward_stage(maua_plan_t* p, const float* grad_coefs, const float* grad_top, float* grad_out,
+                                      maua_stream_t stream) {
+    MAUA_REQUIRE(p, "maua_plan_backward_stage: null plan");
+    return plan_backward_impl(p, grad_coefs, grad_top, grad_out, stream);
+}
+
+MAUA_API int maua_enable_peer_access(int a, int b) {
+    if (a == b) return MAUA_OK;
+    int prev = 0;
+    MAUA_CUDA_CHECK(cudaGetDevice(&prev));
+    for (int k = 0; k < 2; ++k) {
+        const int from = k ? b : a, to = k ? a : b;
+        int can = 0;
+        MAUA_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, from, to));
+        if (!can) {
+            cudaSetDevice(prev);
+            set_last_error("devices %d and %d are not peers (no NVLink / P2P path)", from, to);
+            return MAUA_ERR_CUDA;
+        }
+        MAUA_CUDA_CHECK(cudaSetDevice(from));
+        cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) {
+            cudaSetDevice(prev);
+            set_last_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", from, to, cudaGetErrorString(e));
+            return MAUA_ERR_CUDA;
+        }
+    }
+    MAUA_CUDA_CHECK(cudaSetDevice(prev));
+    return MAUA_OK;
+}
+
+MAUA_API int maua_plan_stage_output_shape(const maua_plan_t* p, int h, int w, int* oh, int* ow, int* oc) {
+    MAUA_REQUIRE(p && h >= 1 && w >= 1, "maua_plan_stage_output_shape: bad arguments");
+    int c = p->in_C;
+    for (const auto& e : p->entries) {
+        if (e.pool) { h /= 2; w /= 2; }
+        c = e.C;
+    }
+    MAUA_REQUIRE(h >= 1 && w >= 1, "image too small for this stage");
+    if (oh) *oh = h;
+    if (ow) *ow = w;
+    if (oc) *oc = c;
     return MAUA_OK;
 }
 

@@ -108,11 +108,12 @@ class _PlanFunction(torch.autograd.Function):
 class B200Net(nn.Module):
     """The truncated feature stack with its loss modules, executed by libmaua_b200 (csrc/plan.cu)."""
 
-    def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device):
+    def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device,
+                 stage_bounds: Optional[List[int]] = None, devices: Optional[List[torch.device]] = None):
         super().__init__()
         _lib.require_gpu()
         self._lib = _lib.load()
-        self.device = device
+        self.device = device  # device of the image side (stage 0); losses and the image gradient are delivered there
         self.entries = entries
         self.taps = taps  # [(relu_index, module)] ordered by relu index
         self.tv_mod = tv_mod
@@ -134,38 +135,72 @@ class B200Net(nn.Module):
         for t, (ridx, mod) in enumerate(taps):
             desc.tap_relu_index[t] = ridx
             desc.tap_kind[t] = _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT
-        self._plan = C.c_void_p()
-        with torch.cuda.device(device):
-            _lib.check(self._lib.maua_plan_create(device.index or 0, C.byref(desc), C.byref(self._plan)), "maua_plan_create")
         self._n_slots = len(taps) + 2
+        # stages of the layer-wise split (models.py:503-566); the common case is ONE stage = the whole stack
+        bounds = list(stage_bounds) if stage_bounds else [0, len(entries)]
+        devs = list(devices) if devices else [device]
+        if len(devs) != len(bounds) - 1 or bounds[0] != 0 or bounds[-1] != len(entries) or sorted(set(bounds)) != bounds:
+            raise ValueError(f"bad stage layout: bounds {bounds} for {len(devs)} device(s) and {len(entries)} entries")
+        self._stages = []
+        torch.cuda.synchronize(device)  # the weight uploads above are consumed by plan creation on other devices
+        for k, dv in enumerate(devs):
+            plan = C.c_void_p()
+            with torch.cuda.device(dv):
+                if len(devs) == 1:
+                    _lib.check(self._lib.maua_plan_create(dv.index or 0, C.byref(desc), C.byref(plan)), "maua_plan_create")
+                else:
+                    if k > 0:
+                        _lib.check(self._lib.maua_enable_peer_access(devs[k - 1].index, dv.index), "maua_enable_peer_access")
+                    _lib.check(self._lib.maua_plan_create_stage(dv.index or 0, C.byref(desc), bounds[k], bounds[k + 1],
+                                                                C.byref(plan)), "maua_plan_create_stage")
+            self._stages.append({"plan": plan, "device": dv, "begin": bounds[k], "end": bounds[k + 1],
+                                 "loss_vec": torch.zeros(self._n_slots, device=dv),
+                                 "coefs": torch.zeros(self._n_slots, device=dv), "x_in": None, "g_top": None})
+        self._plan = self._stages[0]["plan"]
         self._loss_vec = torch.zeros(self._n_slots, device=device)
-        self._coefs = torch.zeros(self._n_slots, device=device)
+        self._coefs = self._stages[0]["coefs"]
         self._fwd_token = 0
         self._tap_channels = []
+        self._tap_stage = []
         ch = [c for c in entries if c > 0]
+        conv_entry = [i for i, c in enumerate(entries) if c > 0]
         for ridx, _ in taps:
             self._tap_channels.append(ch[ridx])
+            e = conv_entry[ridx]
+            self._tap_stage.append(next(k for k, st in enumerate(self._stages) if st["begin"] <= e < st["end"]))
         self.content_losses, self.style_losses, self.tv_losses, self.temporal_losses = [], [], [], []
 
     def __del__(self):
-        plan, self._plan = getattr(self, "_plan", None), None
-        if plan:
+        stages, self._stages = getattr(self, "_stages", []), []
+        self._plan = None
+        for st in stages:
             try:
-                self._lib.maua_plan_destroy(plan)
+                self._lib.maua_plan_destroy(st["plan"])
             except Exception:
                 pass
 
+    @property
+    def n_stages(self) -> int:
+        return len(self._stages)
+
+    def _tap_device(self, t: int) -> torch.device:
+        return self._stages[self._tap_stage[t]]["device"]
+
     # ------------------------------------------------------------------------------------------------
     def set_impl(self, impl: int):
-        _lib.check(self._lib.maua_plan_set_impl(self._plan, impl), "maua_plan_set_impl")
+        for st in self._stages:
+            _lib.check(self._lib.maua_plan_set_impl(st["plan"], impl), "maua_plan_set_impl")
 
     def device_bytes(self) -> int:
-        return int(self._lib.maua_plan_device_bytes(self._plan))
+        return sum(int(self._lib.maua_plan_device_bytes(st["plan"])) for st in self._stages)
 
     def last_launches(self):
-        f, b = C.c_int(), C.c_int()
-        _lib.check(self._lib.maua_plan_last_launches(self._plan, C.byref(f), C.byref(b)))
-        return f.value, b.value
+        tf = tb = 0
+        for st in self._stages:
+            f, b = C.c_int(), C.c_int()
+            _lib.check(self._lib.maua_plan_last_launches(st["plan"], C.byref(f), C.byref(b)))
+            tf, tb = tf + f.value, tb + b.value
+        return tf, tb
 
     def set_profile(self, enable: bool):
         _lib.check(self._lib.maua_plan_set_profile(self._plan, int(enable)), "maua_plan_set_profile")
@@ -209,6 +244,7 @@ class B200Net(nn.Module):
             io = tio[t]
             io.mode = _MODES[mod.mode]
             C_ = self._tap_channels[t]
+            tdev = self._tap_device(t)
             if isinstance(mod, StyleLoss):
                 io.use_covariance = int(bool(mod.use_covariance))
                 vsf = float(mod.video_style_factor)
@@ -216,14 +252,14 @@ class B200Net(nn.Module):
                 if mod.mode == "capture":
                     fresh = mod.target.nelement() == 0
                     if fresh:
-                        mod.target = torch.zeros(C_, C_, device=self.device)
+                        mod.target = torch.zeros(C_, C_, device=tdev)
                     mod.video_target = mod.target  # identical for B = 1 (loss.py:164-175)
                     mod.loss = 0
                     io.capture_weight = float(mod.blend_weight)
                     io.capture_accumulate = 0 if fresh else 1
                 if mod.mode != "none":
-                    if not (mod.target.is_cuda and mod.target.dtype == torch.float32 and mod.target.is_contiguous()):
-                        mod.target = mod.target.to(self.device, torch.float32).contiguous()
+                    if not (mod.target.device == tdev and mod.target.dtype == torch.float32 and mod.target.is_contiguous()):
+                        mod.target = mod.target.to(tdev, torch.float32).contiguous()
                     io.target = mod.target.data_ptr()
                     io.target_elems = mod.target.numel()
             else:
@@ -231,12 +267,12 @@ class B200Net(nn.Module):
                 h, w = self._tap_hw(H, W, ridx)
                 if mod.mode == "capture":
                     # NCHW-shaped view over NHWC memory (channels_last): .size() matches the reference's target
-                    mod.target = torch.empty(1, h, w, C_, device=self.device).permute(0, 3, 1, 2)
+                    mod.target = torch.empty(1, h, w, C_, device=tdev).permute(0, 3, 1, 2)
                 if mod.mode != "none" and mod.target.nelement() != 0:
                     tgt = mod.target
                     if tuple(tgt.shape[1:]) == (C_, h, w):
-                        if not (tgt.is_cuda and tgt.permute(0, 2, 3, 1).is_contiguous()):
-                            tgt = tgt.to(self.device, torch.float32).contiguous(memory_format=torch.channels_last)
+                        if not (tgt.device == tdev and tgt.permute(0, 2, 3, 1).is_contiguous()):
+                            tgt = tgt.to(tdev, torch.float32).contiguous(memory_format=torch.channels_last)
                             mod.target = tgt
                         io.target = tgt.data_ptr()
                         io.target_elems = tgt.numel()
@@ -265,11 +301,54 @@ class B200Net(nn.Module):
                         tm.weights = wts
                     iio.temporal_weights = wts.data_ptr()
         self._keepalive = (x, tio, iio)
-        with torch.cuda.device(self.device):
-            _lib.check(self._lib.maua_plan_forward(self._plan, _lib.ptr(x), H, W, tio, C.byref(iio), _lib.ptr(self._loss_vec),
-                                                   int(keep), _lib.stream_ptr()), "maua_plan_forward")
+        if len(self._stages) == 1:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.maua_plan_forward(self._plan, _lib.ptr(x), H, W, tio, C.byref(iio), _lib.ptr(self._loss_vec),
+                                                       int(keep), _lib.stream_ptr()), "maua_plan_forward")
+        else:
+            self._forward_stages(x, H, W, tio, iio, keep)
         self._fwd_token += 1
         return self._fwd_token
+
+    def _forward_stages(self, x, H, W, tio, iio, keep):
+        """models.py:517-525 ModelParallel.forward: the stages run one after the other, each on its own device and stream.
+        The hand-over tensor lives on the CONSUMING device and is written there directly by the producing stage's last
+        kernel (peer stores over NVLink); an event orders the two streams, like the reference's `.to(device)`."""
+        last_live = max([self._tap_stage[t] for t, (_, m) in enumerate(self.taps) if m.mode != "none"], default=0)
+        self._last_live_stage = last_live
+        inp, h, w = x, H, W
+        prev_event = None
+        for k, st in enumerate(self._stages[:last_live + 1]):
+            dv = st["device"]
+            with torch.cuda.device(dv):
+                stream = torch.cuda.current_stream(dv)
+                if prev_event is not None:
+                    stream.wait_event(prev_event)
+                boundary = None
+                if k < last_live:
+                    oh, ow, oc = C.c_int(), C.c_int(), C.c_int()
+                    _lib.check(self._lib.maua_plan_stage_output_shape(st["plan"], h, w, C.byref(oh), C.byref(ow), C.byref(oc)))
+                    nxt = self._stages[k + 1]
+                    shape = (oh.value, ow.value, oc.value)
+                    if nxt["x_in"] is None or tuple(nxt["x_in"].shape) != shape:
+                        nxt["x_in"] = torch.empty(shape, device=nxt["device"])          # input of stage k+1, on ITS device
+                        st["g_top"] = torch.empty(shape, device=dv)                    # its gradient, on THIS device
+                    boundary = nxt["x_in"]
+                _lib.check(self._lib.maua_plan_forward_stage(st["plan"], _lib.ptr(inp), h, w, tio, C.byref(iio),
+                                                             _lib.ptr(st["loss_vec"]), int(keep), _lib.ptr(boundary),
+                                                             C.c_void_p(stream.cuda_stream)), "maua_plan_forward_stage")
+                prev_event = torch.cuda.Event()
+                prev_event.record(stream)
+            if boundary is not None:
+                inp, h, w = boundary, boundary.shape[0], boundary.shape[1]
+        # the module losses are collected on the image-side device (optim.py:211 `mod.loss.to(backward_device)`)
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(prev_event)
+            total = self._stages[0]["loss_vec"].clone()
+            for st in self._stages[1:last_live + 1]:
+                total += st["loss_vec"].to(self.device, non_blocking=True)
+            self._loss_vec.copy_(total)
 
     def _backward_plan(self, grad_losses: torch.Tensor) -> torch.Tensor:
         x = self._keepalive[0]
@@ -290,11 +369,36 @@ class B200Net(nn.Module):
                 kind[i] = 2
         up = grad_losses.detach().to(self.device, torch.float32).contiguous()
         grad = torch.empty_like(x)
-        with torch.cuda.device(self.device):
-            _lib.check(self._lib.maua_loss_grad_coefs(_lib.ptr(up), _lib.ptr(self._coefs), n, strength, vsf, normalize, kind,
-                                                      _lib.stream_ptr()), "maua_loss_grad_coefs")
-            _lib.check(self._lib.maua_plan_backward(self._plan, _lib.ptr(self._coefs), _lib.ptr(grad), _lib.stream_ptr()),
-                       "maua_plan_backward")
+        if len(self._stages) == 1:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.maua_loss_grad_coefs(_lib.ptr(up), _lib.ptr(self._coefs), n, strength, vsf, normalize, kind,
+                                                          _lib.stream_ptr()), "maua_loss_grad_coefs")
+                _lib.check(self._lib.maua_plan_backward(self._plan, _lib.ptr(self._coefs), _lib.ptr(grad), _lib.stream_ptr()),
+                           "maua_plan_backward")
+            return grad
+        # layer-wise split: last live stage first; each stage stores d/d(its input) straight into the previous stage's
+        # g_top buffer (peer memory) and an event hands the stream order over
+        last_live = self._last_live_stage
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)  # `up` (and the forward) are ordered on the image-side stream
+        prev_event = ready
+        for k in range(last_live, -1, -1):
+            st = self._stages[k]
+            dv = st["device"]
+            with torch.cuda.device(dv):
+                stream = torch.cuda.current_stream(dv)
+                stream.wait_event(prev_event)
+                up_k = up if dv == self.device else up.to(dv, non_blocking=True)
+                _lib.check(self._lib.maua_loss_grad_coefs(_lib.ptr(up_k), _lib.ptr(st["coefs"]), n, strength, vsf, normalize, kind,
+                                                          C.c_void_p(stream.cuda_stream)), "maua_loss_grad_coefs")
+                g_top = st["g_top"] if k < last_live else None
+                out = grad if k == 0 else self._stages[k - 1]["g_top"]
+                _lib.check(self._lib.maua_plan_backward_stage(st["plan"], _lib.ptr(st["coefs"]), _lib.ptr(g_top), _lib.ptr(out),
+                                                              C.c_void_p(stream.cuda_stream)), "maua_plan_backward_stage")
+                st["_keep"] = up_k
+                prev_event = torch.cuda.Event()
+                prev_event.record(stream)
         return grad
 
     def _live_slots(self):
@@ -339,18 +443,22 @@ class B200Net(nn.Module):
         """Feature map of tap t from the last forward as an NCHW tensor (copy)."""
         h, w, c = C.c_int(), C.c_int(), C.c_int()
         null = C.c_void_p(0)
-        _lib.check(self._lib.maua_plan_tap_feature(self._plan, t, null, C.byref(h), C.byref(w), C.byref(c), _lib.stream_ptr()))
-        out = torch.empty(1, h.value, w.value, c.value, device=self.device)
-        _lib.check(self._lib.maua_plan_tap_feature(self._plan, t, _lib.ptr(out), C.byref(h), C.byref(w), C.byref(c),
-                                                   _lib.stream_ptr()))
+        st = self._stages[self._tap_stage[t]]
+        with torch.cuda.device(st["device"]):
+            _lib.check(self._lib.maua_plan_tap_feature(st["plan"], t, null, C.byref(h), C.byref(w), C.byref(c), _lib.stream_ptr()))
+            out = torch.empty(1, h.value, w.value, c.value, device=st["device"])
+            _lib.check(self._lib.maua_plan_tap_feature(st["plan"], t, _lib.ptr(out), C.byref(h), C.byref(w), C.byref(c),
+                                                       _lib.stream_ptr()))
         return out.permute(0, 3, 1, 2).contiguous()
 
     def tap_gram(self, t: int) -> torch.Tensor:
         """Normalised Gram / covariance matrix of style tap t from the last forward (copy)."""
         c = C.c_int()
-        _lib.check(self._lib.maua_plan_tap_gram(self._plan, t, C.c_void_p(0), C.byref(c), _lib.stream_ptr()))
-        out = torch.empty(c.value, c.value, device=self.device)
-        _lib.check(self._lib.maua_plan_tap_gram(self._plan, t, _lib.ptr(out), C.byref(c), _lib.stream_ptr()))
+        st = self._stages[self._tap_stage[t]]
+        with torch.cuda.device(st["device"]):
+            _lib.check(self._lib.maua_plan_tap_gram(st["plan"], t, C.c_void_p(0), C.byref(c), _lib.stream_ptr()))
+            out = torch.empty(c.value, c.value, device=st["device"])
+            _lib.check(self._lib.maua_plan_tap_gram(st["plan"], t, _lib.ptr(out), C.byref(c), _lib.stream_ptr()))
         return out
 
 
