@@ -135,6 +135,10 @@ MAUA_API size_t maua_reduce_workspace_bytes(void);
  * ---------------------------------------------------------------------------------------------- */
 MAUA_API int maua_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
                             float beta1, float beta2, float eps, int step, maua_stream_t stream);
+/* Same update with the 1-based step number read from device memory (*step_dev), so that a CUDA-graph replay of the
+ * optimisation loop (optim.py:240) sees a fresh bias correction every iteration. */
+MAUA_API int maua_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
+                                float beta1, float beta2, float eps, const int* step_dev, maua_stream_t stream);
 
 typedef struct maua_lbfgs maua_lbfgs_t;
 /* L-BFGS state for one n-element parameter vector (torch.optim.LBFGS semantics without line search:

@@ -6,5 +6,5 @@ SYRK for the Gram matrix, fused memory-bound kernels for TV / content / Adam / L
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "loss", "models", "optim", "shard", "parallel"]
+__all__ = ["_lib", "loss", "models", "optim", "shard", "parallel", "synthetic"]
 __version__ = "0.1.0"

@@ -214,7 +214,13 @@ MAUA_API int maua_adam_step(float* param, const float* grad, float* exp_avg, flo
                             float beta1, float beta2, float eps, int step, maua_stream_t stream) {
     MAUA_ENTRY_GUARD();
     MAUA_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "maua_adam_step: bad arguments");
-    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr, (cudaStream_t)stream);
+}
+MAUA_API int maua_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
+                                float beta1, float beta2, float eps, const int* step_dev, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "maua_adam_step_dev: bad arguments");
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -174,17 +174,62 @@ __global__ void gram_ref_kernel(const float* __restrict__ f, long P, int C, floa
     if (c < C && d < C) out[(size_t)c * C + d] = acc;
 }
 
-__global__ void gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long P, int full,
-                                     const float* __restrict__ mean, float* __restrict__ gram) {
+// Sums the split-K partials in a fixed order (deterministic), mirrors the upper-triangular tiles into the lower ones,
+// applies the covariance correction and the 1/(C P) normalisation.  Block = (256 / G) consecutive outputs x G interleaved
+// groups of partials (G grows with the split count so that short and long reductions both keep the loads coalesced and
+// the threads busy).  Optionally fused with the StyleLoss value (loss.py:153-157): diff = gram - target,
+// *loss_out = scale * mean(diff^2).
+template <int G>
+__global__ void __launch_bounds__(kReduceThreads)
+gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long P, int full, const float* __restrict__ mean,
+                     float* __restrict__ gram, const float* __restrict__ target, float* __restrict__ diff, float scale,
+                     float* __restrict__ loss_out, double* red_partials, unsigned int* counter) {
+    constexpr int NO = kReduceThreads / G;  // outputs per block round
+    __shared__ float sh[G][NO + 1];
+    const int tx = threadIdx.x % NO, ty = threadIdx.x / NO;
     const long total = (long)C * C;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = i / C, d = i % C;
-        const bool up = full || ((c >> 7) <= (d >> 7));
-        const size_t src = up ? (size_t)c * C + d : (size_t)d * C + c;
+    double acc = 0.0;
+    for (long base = (long)blockIdx.x * NO; base < total; base += (long)gridDim.x * NO) {
+        const long i = base + tx;
+        const int c = (int)(i / C), d = (int)(i % C);
+        // only the upper-triangular 128x128 tiles were computed; the source read stays coalesced, the mirror is a write
+        const bool live = i < total && (full || ((c >> 7) <= (d >> 7)));
         float s = 0.f;
-        for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * total + src];
-        if (mean) s -= (float)P * mean[c] * mean[d];
-        gram[i] = s / ((float)C * (float)P);
+        if (live)
+            for (int k = ty; k < nsplit; k += G) s += partial[(size_t)k * total + i];
+        if (G > 1) {
+            sh[ty][tx] = s;
+            __syncthreads();
+        }
+        if (ty == 0 && live) {
+            float t = s;
+            if (G > 1) {
+                t = 0.f;
+#pragma unroll
+                for (int y = 0; y < G; ++y) t += sh[y][tx];
+            }
+            if (mean) t -= (float)P * mean[c] * mean[d];
+            const float g = t / ((float)C * (float)P);
+            const bool mirror = !full && ((c >> 7) != (d >> 7));
+            const long im = (long)d * C + c;
+            gram[i] = g;
+            if (mirror) gram[im] = g;
+            if (target) {
+                const float dd = g - target[i];
+                diff[i] = dd;
+                acc += (double)dd * dd;
+                if (mirror) {
+                    const float dm = g - target[im];
+                    diff[im] = dm;
+                    acc += (double)dm * dm;
+                }
+            }
+        }
+        if (G > 1) __syncthreads();
+    }
+    if (target) {
+        double v[1] = {acc}, tot[1];
+        if (grid_sum<1>(v, red_partials, counter, tot)) *loss_out = scale * (float)(tot[0] / (double)total);
     }
 }
 
@@ -252,7 +297,7 @@ size_t gram_workspace_bytes(int C) {
 }
 
 int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* mean_out, void* workspace, int impl,
-                cudaStream_t st) {
+                cudaStream_t st, const GramLossFuse* fuse) {
     MAUA_REQUIRE(C >= 64 && (C == 64 || C % 128 == 0) && C <= 1024,
                  "gram: channel count %d unsupported (need 64 or a multiple of 128, <= 1024)", C);
     MAUA_REQUIRE(P >= 1 && P < (1L << 31), "gram: bad pixel count %ld", P);
@@ -287,8 +332,20 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
         if (rc) return rc;
     }
     const long total = (long)C * C;
-    gram_finalize_kernel<<<(int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256), 256, 0, st>>>(
-        partial, nsplit, C, P, full, use_cov ? mean_out : nullptr, gram);
+    const int G = nsplit >= 64 ? 8 : (nsplit >= 24 ? 4 : (nsplit >= 8 ? 2 : 1));
+    const long per_block = kReduceThreads / G;
+    const int fgrid = (int)((total + per_block - 1) / per_block > 148 * 8 ? 148 * 8 : (total + per_block - 1) / per_block);
+    const float* tgt = nullptr; float* dif = nullptr; float* lout = nullptr; float sc = 0.f;
+    double* rp = nullptr; unsigned int* cnt = nullptr;
+    if (fuse) {
+        MAUA_REQUIRE(fuse->target && fuse->diff && fuse->loss_out && fgrid <= fuse->rs.max_blocks, "gram: bad fused-loss arguments");
+        tgt = fuse->target; dif = fuse->diff; lout = fuse->loss_out; sc = fuse->value_scale;
+        rp = fuse->rs.partials; cnt = fuse->rs.counter;
+    }
+    const float* mu = use_cov ? mean_out : nullptr;
+#define MAUA_FINALIZE(GG) gram_finalize_kernel<GG><<<fgrid, kReduceThreads, 0, st>>>(partial, nsplit, C, P, full, mu, gram, tgt, dif, sc, lout, rp, cnt)
+    if (G == 8) MAUA_FINALIZE(8); else if (G == 4) MAUA_FINALIZE(4); else if (G == 2) MAUA_FINALIZE(2); else MAUA_FINALIZE(1);
+#undef MAUA_FINALIZE
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
@@ -313,6 +370,12 @@ int style_loss_bwd_prep_launch(const float* diff, const float* mean, int C, long
         style_bwd_bias_kernel<<<C, 128, 0, st>>>(aux_d, mean, C, aux_bias);
         MAUA_CUDA_CHECK(cudaGetLastError());
     }
+    return MAUA_OK;
+}
+
+int style_loss_bwd_bias_launch(const float* aux_d, const float* mean, int C, float* aux_bias, cudaStream_t st) {
+    style_bwd_bias_kernel<<<C, 128, 0, st>>>(aux_d, mean, C, aux_bias);
+    MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
 

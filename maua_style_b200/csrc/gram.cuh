@@ -7,12 +7,21 @@ namespace maua {
 
 size_t gram_workspace_bytes(int C);
 // gram[c][d] = (sum_p f[p][c] f[p][d] - [cov] P mu_c mu_d) / (C * P);   f is NHWC-flattened [P][C].
+// Optional fusion of the StyleLoss value into the finalize kernel: diff = gram - target, *loss_out = scale * mse.
+struct GramLossFuse {
+    const float* target = nullptr;
+    float* diff = nullptr;
+    float* loss_out = nullptr;
+    float value_scale = 1.f;
+    ReduceScratch rs;
+};
 int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* mean_out, void* workspace, int impl,
-                cudaStream_t st);
+                cudaStream_t st, const GramLossFuse* fuse = nullptr);
 int style_loss_fwd_launch(const float* gram, const float* target, int C, float value_scale, float* loss_out,
                           float* diff, ReduceScratch rs, cudaStream_t st);
 int style_loss_bwd_prep_launch(const float* diff, const float* mean, int C, long P, const float* coef, float* aux_d,
                                float* aux_bias, cudaStream_t st);
+int style_loss_bwd_bias_launch(const float* aux_d, const float* mean, int C, float* aux_bias, cudaStream_t st);
 // target = (accumulate ? target : 0) + weight * gram     (StyleLoss capture, loss.py:146-151)
 int axpby_launch(const float* x, float* y, long n, float a, int accumulate, cudaStream_t st);
 

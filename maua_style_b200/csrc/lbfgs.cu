@@ -1,4 +1,4 @@
-// L-BFGS pixel update, fully device-resident: three launches per iteration, two streaming passes over the history.
+// L-BFGS pixel update, fully device-resident: four launches per iteration, two streaming passes over the history.
 //
 // Replaces torch.optim.LBFGS as the reference drives it (optim.py:180-191: max_iter = num_iters,
 // tolerance_grad = tolerance_change = -1, history 100, lr 1, NO line search), i.e. per iteration:
@@ -12,16 +12,20 @@
 //     SG_i = s_i.g   YG_i = y_i.g   SY_ij = s_i.y_j   YY_ij = y_i.y_j   GG = g.g
 // the loop-1 dots are  s_i.q_i = -SG_i - sum_{j>i} al_j SY_ij  and the loop-2 dots are
 //     y_i.r_i = H (-YG_i - sum_j al_j YY_ij) + sum_{j<i} (al_j - be_j) SY_ji,
-// so al / be follow from O(k^2) scalar work (one CTA, double precision) and the direction is one linear combination
+// so al / be follow from O(k^2) scalar work and the direction is one linear combination
 //     d = -H g - H sum_j al_j y_j + sum_j (al_j - be_j) s_j.
 // SY / YY are kept on the device and extended by one row/column per accepted pair.  Per iteration:
 //   1. lbfgs_dots_kernel   : forms y, s into the ring, streams every history vector ONCE and takes all its dot products
-//                            with g, y_new, s_new at the same time (multi-dot), per-CTA partials;
-//   2. lbfgs_scalar_kernel : reduces the partials in a fixed order (deterministic), applies the y.s gate, updates
-//                            SY / YY / ro / H, runs both recurrences, computes g.d, t and the halt flag;
-//   3. lbfgs_update_kernel : streams the history a second time:  d = combination,  x += t d.
-// HBM traffic = 2 reads of the 2k history vectors = 16 k n bytes per iteration, the same as the
-// two-loop form, but as two bandwidth-bound sweeps instead of 2k latency-bound ones.
+//                            with g, y_new, s_new at the same time (multi-dot).  Persistent grid sized to the SM count,
+//                            every CTA owns an equal contiguous span of the vectors (no wave quantisation), partial
+//                            sums accumulate in shared memory and are written once per CTA;
+//   2. lbfgs_reduce_kernel : one warp per dot product sums the per-CTA partials in a fixed order (deterministic);
+//   3. lbfgs_scalar_kernel : applies the y.s gate, updates SY / YY / ro / H, runs both recurrences (triangular solves,
+//                            column-oriented inside ONE warp so a step costs a shuffle, not a block barrier),
+//                            computes g.d, t and the halt flag;
+//   4. lbfgs_update_kernel : streams the history a second time:  d = combination,  x += t d  (same balanced spans).
+// HBM traffic = 2 reads of the 2k history vectors = 16 k n bytes per iteration: the floor of the
+// algorithm (the first pass needs the new gradient, the second needs the coefficients the first one produces).
 #include "maua_b200.h"
 #include "pointwise.cuh"
 
@@ -32,8 +36,9 @@ namespace {
 constexpr int kMaxHist = 256;
 constexpr int kRing = kMaxHist + 1;
 constexpr int kThreads = 256;
-constexpr int kChunk = 2048;  // floats of the vector handled by one CTA in the multi-dot pass (2 float4 per thread)
-constexpr int kNV = 5;        // dot products per history slot
+constexpr int kSub4 = 2 * kThreads;  // float4 elements of one sub-chunk (2 per thread)
+constexpr int kNV = 5;               // dot products per history slot
+constexpr int kNG = 8;               // global dot products (6 used)
 
 struct LbfgsState {  // device resident scalars
     int n_iter, hist_len, head, halted;
@@ -50,7 +55,8 @@ struct Args {
     int K;
     int first;
     long n, ld;
-    int nchunks;
+    int grid;         // CTAs of the two streaming kernels
+    int mats_in_smem; // 2: SY and YY cached in shared memory by the scalar kernel, 1: SY only, 0: neither
     float* param;
     const float* g;
     float* prev_g;
@@ -58,7 +64,8 @@ struct Args {
     float* S;  // [(K+1)][ld]
     float* Y;
     LbfgsState* st;
-    float* partials;  // [nchunks][stride]  stride = kNV * ring + 8
+    float* partials;  // [nacc][grid]  (transposed: the reduce kernel reads one row per dot product, coalesced)
+    double* reduced;  // [nacc]        nacc = kNV * ring + kNG
     double* SY;       // [ring][ring]  s_i . y_j
     double* YY;       // [ring][ring]  y_i . y_j
 };
@@ -66,101 +73,147 @@ struct Args {
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 1. multi-dot pass.  CTA c owns elements [c*kChunk, (c+1)*kChunk).  partial layout per CTA:
+// 1. multi-dot pass.  CTA b owns the float4 elements [n4 b / G, n4 (b+1) / G).  Accumulator layout:
 //    [slot*kNV + {0: s.g, 1: y.g, 2: s.y_new, 3: y.y_new, 4: y.s_new}] for every ring slot, then the globals
 //    [G0 + {0: y_new.s_new, 1: y_new.y_new, 2: g.g, 3: |g|_1, 4: s_new.g, 5: y_new.g}].
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(const Args a) {
-    __shared__ float red[kThreads / 32][8];
+    extern __shared__ float acc[];  // [nacc]
+    __shared__ float red[kThreads / 32][2 * kNV];
     const LbfgsState* st = a.st;
     if (st->halted) return;
     const int ring = a.K + 1;
+    const int nacc = kNV * ring + kNG;
     const int len = st->hist_len, head = st->head;
     const int cand = a.first ? -1 : (head + len) % ring;
     const float t = st->t;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long base = (long)blockIdx.x * kChunk;
-    float* part = a.partials + (size_t)blockIdx.x * (kNV * ring + 8);
+    for (int i = threadIdx.x; i < nacc; i += kThreads) acc[i] = 0.f;
 
-    // this thread's elements: 2 float4 (or scalar tail elements) of g, y_new, s_new stay in registers
-    float4 g4[2], y4[2], s4[2];
-    bool ok[2];
+    // warp shuffle -> per-warp slots -> one thread per value adds the block total to its shared accumulator
+    auto block_acc = [&](float (&v)[2 * kNV], int nv, int dst) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const long e = base + (long)(u * kThreads + threadIdx.x) * 4;
-        ok[u] = e < a.n;  // n is padded to ld (multiple of 4) with zeros in every vector, so float4 access is safe
-        g4[u] = y4[u] = s4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!ok[u]) continue;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e + 3 < a.n) g = *reinterpret_cast<const float4*>(a.g + e);
-        else { g.x = a.g[e]; if (e + 1 < a.n) g.y = a.g[e + 1]; if (e + 2 < a.n) g.z = a.g[e + 2]; }
-        g4[u] = g;
-        if (a.first) {
-            *reinterpret_cast<float4*>(a.prev_g + e) = g;
-        } else {
-            const float4 pg = *reinterpret_cast<const float4*>(a.prev_g + e);
-            const float4 dd = *reinterpret_cast<const float4*>(a.d + e);
-            y4[u] = make_float4(g.x - pg.x, g.y - pg.y, g.z - pg.z, g.w - pg.w);
-            s4[u] = make_float4(dd.x * t, dd.y * t, dd.z * t, dd.w * t);
-            *reinterpret_cast<float4*>(a.Y + (size_t)cand * a.ld + e) = y4[u];
-            *reinterpret_cast<float4*>(a.S + (size_t)cand * a.ld + e) = s4[u];
-            *reinterpret_cast<float4*>(a.prev_g + e) = g;
-        }
-    }
-    auto block_out = [&](float (&v)[8], int nv, float* dst) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 2 * kNV; ++k)
             if (k < nv) v[k] = warp_sum(v[k]);
-        __syncthreads();
+        __syncthreads();  // previous use of red[] is complete (also orders the zero-fill of acc[] the first time)
         if (lane == 0)
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 2 * kNV; ++k)
                 if (k < nv) red[warp][k] = v[k];
         __syncthreads();
         if (threadIdx.x < nv) {
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
-            dst[threadIdx.x] = s;
+            acc[dst + threadIdx.x] += s;
         }
     };
-    {
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    const long n4 = a.ld >> 2;
+    const long b0 = n4 * blockIdx.x / gridDim.x, b1 = n4 * (blockIdx.x + 1) / gridDim.x;
+    for (long c0 = b0; c0 < b1; c0 += kSub4) {
+        // this thread's elements of the sub-chunk: 2 float4 of g, y_new, s_new stay in registers
+        float4 g4[2], y4[2], s4[2];
+        bool ok[2];
+        long off[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            v[0] += dot4(y4[u], s4[u]);
-            v[1] += dot4(y4[u], y4[u]);
-            v[2] += dot4(g4[u], g4[u]);
-            v[3] += fabsf(g4[u].x) + fabsf(g4[u].y) + fabsf(g4[u].z) + fabsf(g4[u].w);
-            v[4] += dot4(s4[u], g4[u]);
-            v[5] += dot4(y4[u], g4[u]);
-        }
-        block_out(v, 6, part + kNV * ring);
-    }
-    // stream the history: every row's chunk is read exactly once
-    for (int e = 0; e < len; ++e) {
-        const int slot = (head + e) % ring;
-        const float* sr = a.S + (size_t)slot * a.ld + base;
-        const float* yr = a.Y + (size_t)slot * a.ld + base;
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
+            const long i4 = c0 + u * kThreads + threadIdx.x;
+            const long e = i4 * 4;
+            off[u] = e;
+            ok[u] = i4 < b1;
+            g4[u] = y4[u] = s4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!ok[u]) continue;
-            const long o = (long)(u * kThreads + threadIdx.x) * 4;
-            const float4 sv = __ldcs(reinterpret_cast<const float4*>(sr + o));
-            const float4 yv = __ldcs(reinterpret_cast<const float4*>(yr + o));
-            v[0] += dot4(sv, g4[u]);
-            v[1] += dot4(yv, g4[u]);
-            v[2] += dot4(sv, y4[u]);
-            v[3] += dot4(yv, y4[u]);
-            v[4] += dot4(yv, s4[u]);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);  // the gradient is n long, every other vector is padded to ld
+            if (e + 3 < a.n) g = *reinterpret_cast<const float4*>(a.g + e);
+            else { g.x = a.g[e]; if (e + 1 < a.n) g.y = a.g[e + 1]; if (e + 2 < a.n) g.z = a.g[e + 2]; }
+            g4[u] = g;
+            if (!a.first) {
+                const float4 pg = *reinterpret_cast<const float4*>(a.prev_g + e);
+                const float4 dd = *reinterpret_cast<const float4*>(a.d + e);
+                y4[u] = make_float4(g.x - pg.x, g.y - pg.y, g.z - pg.z, g.w - pg.w);
+                s4[u] = make_float4(dd.x * t, dd.y * t, dd.z * t, dd.w * t);
+                *reinterpret_cast<float4*>(a.Y + (size_t)cand * a.ld + e) = y4[u];
+                *reinterpret_cast<float4*>(a.S + (size_t)cand * a.ld + e) = s4[u];
+            }
+            *reinterpret_cast<float4*>(a.prev_g + e) = g;
         }
-        block_out(v, kNV, part + slot * kNV);
+        {
+            float v[2 * kNV] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                v[0] += dot4(y4[u], s4[u]);
+                v[1] += dot4(y4[u], y4[u]);
+                v[2] += dot4(g4[u], g4[u]);
+                v[3] += fabsf(g4[u].x) + fabsf(g4[u].y) + fabsf(g4[u].z) + fabsf(g4[u].w);
+                v[4] += dot4(s4[u], g4[u]);
+                v[5] += dot4(y4[u], g4[u]);
+            }
+            block_acc(v, 6, kNV * ring);
+        }
+        // stream the history, two slots (8 independent 16-byte loads per thread) per round
+        for (int e = 0; e < len; e += 2) {
+            const int slot0 = (head + e) % ring;
+            const bool two = e + 1 < len;
+            const int slot1 = two ? (head + e + 1) % ring : slot0;
+            float4 sv[2][2], yv[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                sv[0][u] = sv[1][u] = yv[0][u] = yv[1][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!ok[u]) continue;
+                sv[0][u] = __ldcs(reinterpret_cast<const float4*>(a.S + (size_t)slot0 * a.ld + off[u]));
+                yv[0][u] = __ldcs(reinterpret_cast<const float4*>(a.Y + (size_t)slot0 * a.ld + off[u]));
+                if (two) {
+                    sv[1][u] = __ldcs(reinterpret_cast<const float4*>(a.S + (size_t)slot1 * a.ld + off[u]));
+                    yv[1][u] = __ldcs(reinterpret_cast<const float4*>(a.Y + (size_t)slot1 * a.ld + off[u]));
+                }
+            }
+            float v[2 * kNV] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    v[q * kNV + 0] += dot4(sv[q][u], g4[u]);
+                    v[q * kNV + 1] += dot4(yv[q][u], g4[u]);
+                    v[q * kNV + 2] += dot4(sv[q][u], y4[u]);
+                    v[q * kNV + 3] += dot4(yv[q][u], y4[u]);
+                    v[q * kNV + 4] += dot4(yv[q][u], s4[u]);
+                }
+            if (two && slot1 == slot0 + 1) {
+                block_acc(v, 2 * kNV, slot0 * kNV);  // adjacent ring slots: one reduction for both
+            } else {
+                block_acc(v, kNV, slot0 * kNV);
+                if (two) {
+                    float w[2 * kNV];
+#pragma unroll
+                    for (int k = 0; k < kNV; ++k) { w[k] = v[kNV + k]; w[kNV + k] = 0.f; }
+                    block_acc(w, kNV, slot1 * kNV);
+                }
+            }
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nacc; i += kThreads) a.partials[(size_t)i * gridDim.x + blockIdx.x] = acc[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 2. scalar phase (one CTA)
+// 2. deterministic reduction of the per-CTA partials: one warp per dot product, fixed lane / shuffle order
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) lbfgs_reduce_kernel(const Args a) {
+    if (a.st->halted) return;
+    const int nacc = kNV * (a.K + 1) + kNG;
+    const int idx = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (idx >= nacc) return;
+    const int lane = threadIdx.x & 31;
+    const float* row = a.partials + (size_t)idx * a.grid;
+    double s = 0.0;
+    for (int c = lane; c < a.grid; c += 32) s += (double)__ldcg(row + c);
+    s = warp_sum(s);
+    if (lane == 0) a.reduced[idx] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. scalar phase (one CTA; the two triangular solves run inside warp 0)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum(double v, double* sh) {
     v = warp_sum(v);
@@ -173,22 +226,23 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return s;
 }
 
+constexpr int kPerLane = (kMaxHist + 31) / 32;  // history entries owned by one lane of the solver warp
+
 __global__ void __launch_bounds__(kThreads) lbfgs_scalar_kernel(const Args a) {
+    extern __shared__ double mats[];  // optional cache of SY (and YY): [ring][ring] each
     __shared__ double sh[kThreads / 32];
-    __shared__ double SG[kRing], YG[kRing], SYn[kRing], YYn[kRing], YSn[kRing], al[kRing], be[kRing], ro[kRing];
-    __shared__ double glob[8];
+    __shared__ double SG[kRing], YG[kRing], SYn[kRing], YYn[kRing], YSn[kRing], al[kRing], be[kRing], ro[kRing], wv[kRing];
+    __shared__ double glob[kNG];
+    __shared__ int slot_of[kRing];
     LbfgsState* st = a.st;
     if (st->halted) return;
     const int ring = a.K + 1;
-    const int stride = kNV * ring + 8;
     int len = st->hist_len, head = st->head, n_iter = st->n_iter;
     double H = st->H_diag;
     const int tid = threadIdx.x;
 
-    // deterministic reduction of the per-CTA partials (fixed order over CTAs), one (slot, value) per thread
     for (int idx = tid; idx < kNV * ring + 6; idx += kThreads) {
-        double s = 0;
-        for (int c = 0; c < a.nchunks; ++c) s += (double)a.partials[(size_t)c * stride + idx];
+        const double s = a.reduced[idx];
         if (idx >= kNV * ring) glob[idx - kNV * ring] = s;
         else {
             const int slot = idx / kNV, k = idx % kNV;
@@ -225,40 +279,94 @@ __global__ void __launch_bounds__(kThreads) lbfgs_scalar_kernel(const Args a) {
             if (len == a.K) head = (head + 1) % ring; else len += 1;
             H = (double)((float)ys / (float)yy);
         }
-        __syncthreads();
-        __threadfence_block();
+    }
+    __syncthreads();  // block-scope ordering of the global SY / YY writes above with the reads below
+
+    // chronological index -> ring slot, and the matrices staged in shared memory when they fit
+    for (int e = tid; e < len; e += kThreads) slot_of[e] = (head + e) % ring;
+    const double* SYm = a.SY;
+    const double* YYm = a.YY;
+    if (a.mats_in_smem >= 1) {
+        for (int i = tid; i < ring * ring; i += kThreads) mats[i] = a.SY[i];
+        SYm = mats;
+        if (a.mats_in_smem >= 2) {
+            for (int i = tid; i < ring * ring; i += kThreads) mats[ring * ring + i] = a.YY[i];
+            YYm = mats + ring * ring;
+        }
     }
     __syncthreads();
 
-    // loop 1 (newest -> oldest):  al_e = ro_e * ( -SG_e - sum_{f>e} al_f SY[e][f] )
-    for (int e = len - 1; e >= 0; --e) {
-        const int se = (head + e) % ring;
-        double term = 0;
-        for (int f = e + 1 + tid; f < len; f += kThreads) {
-            const int sf = (head + f) % ring;
-            term += al[sf] * a.SY[(size_t)se * ring + sf];
+    // loop 1 (newest -> oldest):  al_e = ro_e * ( -SG_e - sum_{f>e} al_f SY[e][f] ).  Column-oriented: lane l of warp 0
+    // keeps the running right-hand sides of its entries e = l, l+32, ...; finishing al_e costs one broadcast.
+    if (tid < 32) {
+        const int lane = tid;
+        double r[kPerLane];
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const int e = lane + 32 * j;
+            r[j] = e < len ? -SG[slot_of[e]] : 0.0;
         }
-        const double sum = block_sum(term, sh);
-        if (tid == 0) al[se] = (double)(float)(ro[se] * (-SG[se] - sum));
-        __syncthreads();
-    }
-    // loop 2 (oldest -> newest):  be_e = ro_e * ( H (-YG_e - sum_f al_f YY[e][f]) + sum_{f<e} (al_f - be_f) SY[f][e] )
-    for (int e = 0; e < len; ++e) {
-        const int se = (head + e) % ring;
-        double term = 0;
-        for (int f = tid; f < len; f += kThreads) {
-            const int sf = (head + f) % ring;
-            term += -H * al[sf] * a.YY[(size_t)se * ring + sf];
-            if (f < e) term += (al[sf] - be[sf]) * a.SY[(size_t)sf * ring + se];
+        // the outer loop over 32-entry blocks is unrolled so that r[] is only ever indexed statically (registers)
+#pragma unroll
+        for (int jb = kPerLane - 1; jb >= 0; --jb) {
+            if (jb * 32 >= len) continue;
+            const int top = min(len - 1 - jb * 32, 31);
+            for (int l = top; l >= 0; --l) {
+                const int e = jb * 32 + l;
+                const int se = slot_of[e];
+                double ae = (double)(float)(ro[se] * r[jb]);
+                ae = __shfl_sync(0xffffffffu, ae, l);
+                if (lane == l) al[se] = ae;
+#pragma unroll
+                for (int j = 0; j < kPerLane; ++j) {
+                    const int f = lane + 32 * j;  // entries older than e still wait for this term
+                    if (j <= jb && f < e) r[j] -= ae * SYm[(size_t)slot_of[f] * ring + se];
+                }
+            }
         }
-        const double sum = block_sum(term, sh);
-        if (tid == 0) be[se] = (double)(float)(ro[se] * (-H * YG[se] + sum));
-        __syncthreads();
     }
+    __syncthreads();
+    // w_e = -H ( YG_e + sum_f al_f YY[e][f] )   (independent of be: all threads)
+    for (int e = tid; e < len; e += kThreads) {
+        const int se = slot_of[e];
+        double s = YG[se];
+        for (int f = 0; f < len; ++f) s += al[slot_of[f]] * YYm[(size_t)se * ring + slot_of[f]];
+        wv[se] = -H * s;
+    }
+    __syncthreads();
+    // loop 2 (oldest -> newest):  be_e = ro_e * ( w_e + sum_{f<e} (al_f - be_f) SY[f][e] )
+    if (tid < 32) {
+        const int lane = tid;
+        double u[kPerLane];
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const int e = lane + 32 * j;
+            u[j] = e < len ? wv[slot_of[e]] : 0.0;
+        }
+#pragma unroll
+        for (int jb = 0; jb < kPerLane; ++jb) {
+            if (jb * 32 >= len) continue;
+            const int top = min(len - jb * 32, 32);
+            for (int l = 0; l < top; ++l) {
+                const int e = jb * 32 + l;
+                const int se = slot_of[e];
+                double b = (double)(float)(ro[se] * u[jb]);
+                b = __shfl_sync(0xffffffffu, b, l);
+                if (lane == l) be[se] = b;
+                const double c = al[se] - b;
+#pragma unroll
+                for (int j = 0; j < kPerLane; ++j) {
+                    const int f = lane + 32 * j;  // newer entries
+                    if (j >= jb && f > e && f < len) u[j] += c * SYm[(size_t)se * ring + slot_of[f]];
+                }
+            }
+        }
+    }
+    __syncthreads();
     // coefficients of the direction and the directional derivative g.d
     double term = 0;
     for (int e = tid; e < len; e += kThreads) {
-        const int se = (head + e) % ring;
+        const int se = slot_of[e];
         const double cy = -H * al[se], cs = al[se] - be[se];
         st->cy[se] = (float)cy;
         st->cs[se] = (float)cs;
@@ -278,7 +386,7 @@ __global__ void __launch_bounds__(kThreads) lbfgs_scalar_kernel(const Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 3. direction + parameter update:  d = cg g + sum cy_j y_j + sum cs_j s_j ;  x += t d
+// 4. direction + parameter update:  d = cg g + sum cy_j y_j + sum cs_j s_j ;  x += t d
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(const Args a) {
     __shared__ float cy[kRing], cs[kRing];
@@ -294,7 +402,8 @@ __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(const Args a) {
     __syncthreads();
     const float cg = st->cg, t = st->t;
     const long n4 = a.ld >> 2;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const long b0 = n4 * blockIdx.x / gridDim.x, b1 = n4 * (blockIdx.x + 1) / gridDim.x;  // equal contiguous spans
+    for (long i = b0 + threadIdx.x; i < b1; i += kThreads) {
         const long e0 = i * 4;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e0 + 3 < a.n) g = *reinterpret_cast<const float4*>(a.g + e0);
@@ -332,9 +441,10 @@ struct maua_lbfgs {
     int K = 0;
     long calls = 0;
     int device = 0;
-    int nchunks = 0;
+    int grid_dots = 0, grid_update = 0, mats_in_smem = 0;
+    size_t scalar_smem = 0;
     float *prev_g = nullptr, *d = nullptr, *S = nullptr, *Y = nullptr, *partials = nullptr;
-    double *SY = nullptr, *YY = nullptr;
+    double *SY = nullptr, *YY = nullptr, *reduced = nullptr;
     LbfgsState* st = nullptr;
 };
 
@@ -346,29 +456,46 @@ MAUA_API int maua_lbfgs_create(long n, int history, float lr, float tolerance_ch
     maua_lbfgs* s = new maua_lbfgs();
     s->n = n; s->K = history;
     s->ld = (n + 3) & ~3L;
-    s->nchunks = (int)((s->ld + kChunk - 1) / kChunk);
     cudaGetDevice(&s->device);
     const int ring = history + 1;
+    const int nacc = kNV * ring + kNG;
     cudaError_t e = cudaSuccess;
+    // persistent grids: (CTAs that fit on one SM) x (SM count), every CTA gets an equal contiguous span
+    int sms = 148, occ_dots = 1, occ_upd = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    if (sms <= 0) sms = 148;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dots, lbfgs_dots_kernel, kThreads, nacc * sizeof(float));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, lbfgs_update_kernel, kThreads, 0);
+    if (occ_dots < 1) occ_dots = 1;
+    if (occ_upd < 1) occ_upd = 1;
+    const long n4 = s->ld >> 2;
+    const long max_useful = (n4 + kThreads - 1) / kThreads;  // at least one float4 per thread
+    s->grid_dots = (int)(sms * (long)occ_dots < max_useful ? sms * (long)occ_dots : max_useful);
+    s->grid_update = (int)(sms * (long)occ_upd < max_useful ? sms * (long)occ_upd : max_useful);
+    const size_t mat = (size_t)ring * ring * sizeof(double);
+    s->mats_in_smem = 2 * mat <= 180 * 1024 ? 2 : (mat <= 180 * 1024 ? 1 : 0);
+    s->scalar_smem = s->mats_in_smem * mat;
+    if (e == cudaSuccess && s->scalar_smem > 0)
+        e = cudaFuncSetAttribute(lbfgs_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->scalar_smem);
     auto alloc = [&](void** p, size_t bytes) {
         if (e == cudaSuccess) e = cudaMalloc(p, bytes);
         if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
     };
-    // every vector is padded to a multiple of kChunk floats so the multi-dot pass can use unguarded float4 access
-    const size_t padded = (size_t)s->nchunks * kChunk;
-    alloc((void**)&s->prev_g, padded * sizeof(float));
-    alloc((void**)&s->d, padded * sizeof(float));
-    alloc((void**)&s->S, ((size_t)ring * s->ld + kChunk) * sizeof(float));
-    alloc((void**)&s->Y, ((size_t)ring * s->ld + kChunk) * sizeof(float));
-    alloc((void**)&s->partials, (size_t)s->nchunks * (kNV * ring + 8) * sizeof(float));
-    alloc((void**)&s->SY, (size_t)ring * ring * sizeof(double));
-    alloc((void**)&s->YY, (size_t)ring * ring * sizeof(double));
+    // every vector is padded to ld (a multiple of 4 floats) with zeros so the streaming passes use float4 access
+    alloc((void**)&s->prev_g, (size_t)s->ld * sizeof(float));
+    alloc((void**)&s->d, (size_t)s->ld * sizeof(float));
+    alloc((void**)&s->S, (size_t)ring * s->ld * sizeof(float));
+    alloc((void**)&s->Y, (size_t)ring * s->ld * sizeof(float));
+    alloc((void**)&s->partials, (size_t)nacc * s->grid_dots * sizeof(float));
+    alloc((void**)&s->reduced, (size_t)nacc * sizeof(double));
+    alloc((void**)&s->SY, mat);
+    alloc((void**)&s->YY, mat);
     alloc((void**)&s->st, sizeof(LbfgsState));
     if (e != cudaSuccess) {
-        set_last_error("maua_lbfgs_create: cudaMalloc failed (%s) for n=%ld history=%d", cudaGetErrorString(e), n, history);
+        set_last_error("maua_lbfgs_create: CUDA failure (%s) for n=%ld history=%d", cudaGetErrorString(e), n, history);
         cudaGetLastError();
         maua_lbfgs_destroy(s);
-        return MAUA_ERR_OOM;
+        return e == cudaErrorMemoryAllocation ? MAUA_ERR_OOM : MAUA_ERR_CUDA;
     }
     LbfgsState h;
     memset(&h, 0, sizeof(h));
@@ -380,7 +507,7 @@ MAUA_API int maua_lbfgs_create(long n, int history, float lr, float tolerance_ch
 
 MAUA_API void maua_lbfgs_destroy(maua_lbfgs_t* s) {
     if (!s) return;
-    cudaFree(s->prev_g); cudaFree(s->d); cudaFree(s->S); cudaFree(s->Y); cudaFree(s->partials);
+    cudaFree(s->prev_g); cudaFree(s->d); cudaFree(s->S); cudaFree(s->Y); cudaFree(s->partials); cudaFree(s->reduced);
     cudaFree(s->SY); cudaFree(s->YY); cudaFree(s->st);
     delete s;
 }
@@ -390,17 +517,18 @@ MAUA_API int maua_lbfgs_step(maua_lbfgs_t* s, float* param, const float* grad, m
     MAUA_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0,
                  "maua_lbfgs_step: pointers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    const int nacc = kNV * (s->K + 1) + kNG;
     Args a;
-    a.K = s->K; a.first = s->calls == 0; a.n = s->n; a.ld = s->ld; a.nchunks = s->nchunks;
+    a.K = s->K; a.first = s->calls == 0; a.n = s->n; a.ld = s->ld; a.grid = s->grid_dots; a.mats_in_smem = s->mats_in_smem;
     a.param = param; a.g = grad; a.prev_g = s->prev_g; a.d = s->d; a.S = s->S; a.Y = s->Y;
-    a.st = s->st; a.partials = s->partials; a.SY = s->SY; a.YY = s->YY;
-    lbfgs_dots_kernel<<<s->nchunks, kThreads, 0, st>>>(a);
+    a.st = s->st; a.partials = s->partials; a.reduced = s->reduced; a.SY = s->SY; a.YY = s->YY;
+    lbfgs_dots_kernel<<<s->grid_dots, kThreads, nacc * sizeof(float), st>>>(a);
     MAUA_CUDA_CHECK(cudaGetLastError());
-    lbfgs_scalar_kernel<<<1, kThreads, 0, st>>>(a);
+    lbfgs_reduce_kernel<<<(nacc + kThreads / 32 - 1) / (kThreads / 32), kThreads, 0, st>>>(a);
     MAUA_CUDA_CHECK(cudaGetLastError());
-    long blocks = ((s->ld >> 2) + kThreads - 1) / kThreads;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    lbfgs_update_kernel<<<(int)blocks, kThreads, 0, st>>>(a);
+    lbfgs_scalar_kernel<<<1, kThreads, s->scalar_smem, st>>>(a);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    lbfgs_update_kernel<<<s->grid_update, kThreads, 0, st>>>(a);
     MAUA_CUDA_CHECK(cudaGetLastError());
     s->calls += 1;
     return MAUA_OK;

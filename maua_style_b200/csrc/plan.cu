@@ -58,9 +58,29 @@ struct Tap {
     float* target = nullptr;
 };
 
-__global__ void coef_prep_kernel(const float* __restrict__ coefs, float* __restrict__ out, int n, const float* factors_dev) {
-    const int i = threadIdx.x;
-    if (i < n) out[i] = coefs[i] * factors_dev[i];
+// Backward prologue in ONE launch: coef2[i] = coefs[i] * factor[i] for every module slot (block (0,0)), and for every live
+// style tap (blockIdx.y) the backward coefficient matrix  aux_d = coef * 4 / (C^3 P) * (G - A), TF32-rounded because it is
+// the B operand of the folded StyleLoss-backward MMA (loss.py:141-157).
+struct BwdPrep {
+    int n_slots, n_style;
+    float factors[MAUA_MAX_TAPS + 2];
+    const float* diff[MAUA_MAX_TAPS];
+    float* aux_d[MAUA_MAX_TAPS];
+    int C[MAUA_MAX_TAPS];
+    float inv_c3p[MAUA_MAX_TAPS];  // 4 / (C^3 P)
+    int slot[MAUA_MAX_TAPS];
+};
+__global__ void bwd_prep_kernel(const float* __restrict__ coefs, float* __restrict__ coef2, const BwdPrep bp) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < bp.n_slots)
+        coef2[threadIdx.x] = coefs[threadIdx.x] * bp.factors[threadIdx.x];
+    if ((int)blockIdx.y >= bp.n_style) return;
+    const int j = blockIdx.y;
+    const long total = (long)bp.C[j] * bp.C[j];
+    const float k = coefs[bp.slot[j]] * bp.factors[bp.slot[j]] * bp.inv_c3p[j];
+    const float* __restrict__ diff = bp.diff[j];
+    float* __restrict__ aux = bp.aux_d[j];
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        aux[i] = round_tf32(k * diff[i]);
 }
 
 struct CoefParams {
@@ -112,7 +132,6 @@ struct maua_plan {
     size_t gbuf_elems = 0;
     void* reduce_ws = nullptr;
     float* coef2 = nullptr;       // [n_taps + 2] scaled coefficients
-    float* factors_dev = nullptr; // [n_taps + 2]
     size_t tap_bytes = 0;
     // last forward
     int H = 0, W = 0;
@@ -338,7 +357,6 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     }
     alloc(&p->reduce_ws, maua_reduce_workspace_bytes());
     alloc((void**)&p->coef2, (MAUA_MAX_TAPS + 2) * sizeof(float));
-    alloc((void**)&p->factors_dev, (MAUA_MAX_TAPS + 2) * sizeof(float));
     if (e == cudaSuccess && ok) e = cudaMemset(p->reduce_ws, 0, maua_reduce_workspace_bytes());
     if (e == cudaSuccess && ok) e = cudaDeviceSynchronize();
     if (e != cudaSuccess || !ok) {
@@ -376,7 +394,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     }
     cudaFree(p->arena);
     for (int i = 0; i < 3; ++i) cudaFree(p->gbuf[i]);
-    cudaFree(p->reduce_ws); cudaFree(p->coef2); cudaFree(p->factors_dev);
+    cudaFree(p->reduce_ws); cudaFree(p->coef2);
     delete p;
 }
 
@@ -540,22 +558,26 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             if (tp.kind == MAUA_TAP_STYLE) {
                 MAUA_REQUIRE(tp.target && tio[t].target_elems == (long)tp.C * tp.C,
                              "style tap %d: target must be a [%d,%d] device tensor", t, tp.C, tp.C);
-                if ((rc = gram_launch(e.out, P, tp.C, tp.use_cov, tp.gram, tp.mean, tp.gram_ws, p->impl, st))) return rc;
+                GramLossFuse fuse;
+                const bool loss_mode = tp.mode != MAUA_MODE_CAPTURE;
+                if (loss_mode) {
+                    MAUA_REQUIRE(losses_out, "losses_out is required in loss mode");
+                    fuse.target = tp.target; fuse.diff = tp.diff; fuse.loss_out = losses_out + t;
+                    fuse.value_scale = tio[t].value_scale; fuse.rs = rs;
+                }
+                // one SYRK + one finalize kernel (which also produces G - A and the loss value in loss mode)
+                if ((rc = gram_launch(e.out, P, tp.C, tp.use_cov, tp.gram, tp.mean, tp.gram_ws, p->impl, st,
+                                      loss_mode ? &fuse : nullptr)))
+                    return rc;
                 p->launches_fwd += 2 + (tp.use_cov ? 2 : 0);
                 prof_mark(p, st, "gram_syrk", i, (double)tp.C * (tp.C + 1) * P, 4.0 * P * tp.C);
-                if (tp.mode == MAUA_MODE_CAPTURE) {
+                if (!loss_mode) {
                     // loss.py:146-151: target (+)= blend_weight * gram   (B = 1)
                     if ((rc = axpby_launch(tp.gram, tp.target, (long)tp.C * tp.C, tio[t].capture_weight,
                                            tio[t].capture_accumulate, st)))
                         return rc;
                     p->launches_fwd++;
                 } else {
-                    MAUA_REQUIRE(losses_out, "losses_out is required in loss mode");
-                    if ((rc = style_loss_fwd_launch(tp.gram, tp.target, tp.C, tio[t].value_scale, losses_out + t, tp.diff,
-                                                    rs, st)))
-                        return rc;
-                    p->launches_fwd++;
-                    prof_mark(p, st, "style_loss", i, 0, 12.0 * tp.C * tp.C);
                     tp.active = true;
                     p->factors[t] = 1.f;
                 }
@@ -633,21 +655,29 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     int rc;
     prof_mark(p, st, "begin_bwd", -1, 0, 0);
 
-    // scaled coefficients: content 2/numel, temporal 2/numel
-    MAUA_CUDA_CHECK(cudaMemcpyAsync(p->factors_dev, p->factors, (nt + 2) * sizeof(float), cudaMemcpyHostToDevice, st));
-    coef_prep_kernel<<<1, 32, 0, st>>>(grad_coefs, p->coef2, nt + 2, p->factors_dev);
-    MAUA_CUDA_CHECK(cudaGetLastError());
-    p->launches_bwd++;
-
-    // style taps: scaled (G - A) matrices (+ covariance bias)
-    for (int t = 0; t < nt; ++t) {
-        Tap& tp = p->taps[t];
-        if (!tp.active || tp.kind != MAUA_TAP_STYLE) continue;
-        const Entry& e = p->entries[tp.entry];
-        if ((rc = style_loss_bwd_prep_launch(tp.diff, tp.use_cov ? tp.mean : nullptr, tp.C, (long)e.H * e.W, p->coef2 + t,
-                                             tp.aux_d, tp.use_cov ? tp.aux_bias : nullptr, st)))
-            return rc;
-        p->launches_bwd += tp.use_cov ? 2 : 1;
+    // scaled coefficients (content / temporal: 2/numel) and the style taps' scaled (G - A) matrices, one launch
+    {
+        BwdPrep bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.n_slots = nt + 2;
+        for (int i = 0; i < nt + 2; ++i) bp.factors[i] = p->factors[i];
+        for (int t = 0; t < nt; ++t) {
+            Tap& tp = p->taps[t];
+            if (!tp.active || tp.kind != MAUA_TAP_STYLE) continue;
+            const Entry& e = p->entries[tp.entry];
+            const int j = bp.n_style++;
+            bp.diff[j] = tp.diff; bp.aux_d[j] = tp.aux_d; bp.C[j] = tp.C; bp.slot[j] = t;
+            bp.inv_c3p[j] = 4.f / ((float)tp.C * (float)tp.C * (float)tp.C * (float)((long)e.H * e.W));
+        }
+        bwd_prep_kernel<<<dim3(128, bp.n_style > 0 ? bp.n_style : 1), 256, 0, st>>>(grad_coefs, p->coef2, bp);
+        MAUA_CUDA_CHECK(cudaGetLastError());
+        p->launches_bwd++;
+        for (int t = 0; t < nt; ++t) {  // covariance: aux_bias = -aux_d @ mean (loss.py:87-89)
+            Tap& tp = p->taps[t];
+            if (!tp.active || tp.kind != MAUA_TAP_STYLE || !tp.use_cov) continue;
+            if ((rc = style_loss_bwd_bias_launch(tp.aux_d, tp.mean, tp.C, tp.aux_bias, st))) return rc;
+            p->launches_bwd++;
+        }
     }
     prof_mark(p, st, "bwd_prep", -1, 0, 0);
 

@@ -290,10 +290,17 @@ __global__ void channel_sum_final_kernel(const double* __restrict__ partial, int
 // Adam (torch.optim.Adam single-tensor math, reference optim.py:192-196): 28 bytes / element.
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 // --------------------------------------------------------------------------------------------
+// step_dev (optional): the step number lives on the device (graph-captured loops replay the same launch), and the
+// bias corrections are derived from it here instead of on the host.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2_sqrt) {
+                            float bc2_sqrt, const int* __restrict__ step_dev) {
     const long n4 = n / 4;
+    if (step_dev) {
+        const int t = *step_dev;
+        bc1 = (float)(1.0 - pow((double)b1, (double)t));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)t));
+    }
     const float step = lr / bc1;
     float4* p4 = reinterpret_cast<float4*>(p);
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -401,14 +408,15 @@ int channel_mean_launch(const float* x, long P, int C, float* mean_out, double* 
     return MAUA_OK;
 }
 int adam_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
-                int step, cudaStream_t st) {
-    MAUA_REQUIRE(step >= 1, "adam step must be >= 1");
+                int step, const int* step_dev, cudaStream_t st) {
+    MAUA_REQUIRE(step >= 1 || step_dev, "adam step must be >= 1");
+    if (step < 1) step = 1;
     MAUA_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                    reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam: pointers must be 16-byte aligned");
     const double bc1 = 1.0 - pow((double)b1, step);
     const double bc2 = 1.0 - pow((double)b2, step);
     adam_kernel<<<grid_for(n / 4 + 1, 8), kThreads, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1,
-                                                             (float)sqrt(bc2));
+                                                             (float)sqrt(bc2), step_dev);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

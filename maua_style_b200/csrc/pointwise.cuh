@@ -26,6 +26,6 @@ int wmse_value_launch(const float* x, const float* wts, const float* t, long n, 
 int channel_mean_launch(const float* x, long P, int C, float* mean_out, double* scratch, int scratch_blocks,
                         cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
-                int step, cudaStream_t st);
+                int step, const int* step_dev, cudaStream_t st);
 
 }  // namespace maua

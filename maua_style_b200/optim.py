@@ -93,6 +93,7 @@ class PixelOptimizer:
         if kind == "adam":
             self.m = torch.zeros_like(pastiche)
             self.v = torch.zeros_like(pastiche)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=pastiche.device)  # device-resident step number
         elif kind == "lbfgs":
             self._state = C.c_void_p()
             with torch.cuda.device(pastiche.device):
@@ -105,10 +106,11 @@ class PixelOptimizer:
         self.step_count += 1
         with torch.cuda.device(self.p.device):
             if self.kind == "adam":
-                _lib.check(self.lib.maua_adam_step(_lib.ptr(self.p), _lib.ptr(grad), _lib.ptr(self.m), _lib.ptr(self.v),
-                                                   C.c_long(self.p.numel()), C.c_float(self.lr), C.c_float(0.9),
-                                                   C.c_float(0.999), C.c_float(1e-8), self.step_count, _lib.stream_ptr()),
-                           "maua_adam_step")
+                self.step_dev.add_(1)  # on the stream: a graph replay advances it too
+                _lib.check(self.lib.maua_adam_step_dev(_lib.ptr(self.p), _lib.ptr(grad), _lib.ptr(self.m), _lib.ptr(self.v),
+                                                       C.c_long(self.p.numel()), C.c_float(self.lr), C.c_float(0.9),
+                                                       C.c_float(0.999), C.c_float(1e-8), _lib.ptr(self.step_dev),
+                                                       _lib.stream_ptr()), "maua_adam_step_dev")
             else:
                 _lib.check(self.lib.maua_lbfgs_step(self._state, _lib.ptr(self.p), _lib.ptr(grad), _lib.stream_ptr()),
                            "maua_lbfgs_step")
@@ -123,6 +125,54 @@ class PixelOptimizer:
             self.close()
         except Exception:
             pass
+
+
+class GraphedIteration:
+    """One whole reference iteration -- feval (optim.py:201-221) + pixel update (optim.py:240) -- captured once into a CUDA
+    graph and replayed: ~65 kernel launches become one graph launch, which removes the host launch cost and the gaps
+    between kernels (what bounds the iteration at <= 512^2).  Everything the iteration touches is device-resident and
+    address-stable (plan arena, targets, optimizer state, the step number), so a replay is exactly the eager iteration.
+    Falls back to eager launches when capture is impossible (layer-wise split over several devices, MAUA_NO_GRAPH=1).
+    """
+
+    def __init__(self, net, pastiche: torch.Tensor, opt: "PixelOptimizer", up: torch.Tensor, warmup: int = 2):
+        import os
+
+        self.net, self.pastiche, self.opt, self.up = net, pastiche, opt, up
+        self.graph = None
+        self.eager_calls = 0
+        self.enabled = net.n_stages == 1 and os.environ.get("MAUA_NO_GRAPH", "0") != "1"
+        self.warmup = warmup  # eager iterations first: workspaces get sized, the L-BFGS "first call" path is taken eagerly
+
+    def _eager(self):
+        self.net._forward_plan(self.pastiche, keep=True)
+        grad = self.net._backward_plan(self.up)
+        self.opt.step(grad)
+
+    def __call__(self):
+        if not self.enabled or self.eager_calls < self.warmup:
+            self._eager()
+            self.eager_calls += 1
+            return
+        if self.graph is None:
+            dev = self.pastiche.device
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            count = self.opt.step_count
+            try:
+                with torch.cuda.graph(g):
+                    self._eager()
+            except Exception:
+                # capture unsupported in this environment: stay eager (the capture launched nothing)
+                self.enabled = False
+                self.opt.step_count = count
+                torch.cuda.synchronize(dev)
+                self._eager()
+                return
+            self.opt.step_count = count  # the capture itself does not execute
+            self.graph = g
+        self.graph.replay()
+        self.opt.step_count += 1
 
 
 def feval(net, pastiche: torch.Tensor, ones: Optional[torch.Tensor] = None):
@@ -170,20 +220,20 @@ def optimize(content, styles, init, num_iters, args, net=None, losses=None):
 
     print_iter = int(getattr(args, "print_iter", 0) or 0)
     save_iter = int(getattr(args, "save_iter", 0) or 0)
-    live = None
+    live = net._live_slots()  # modules in loss mode with a target (a shape mismatch just contributes 0, loss.py:44)
     up = torch.zeros(net._n_slots, device=device)
+    up[live] = 1.0
+    iteration = GraphedIteration(net, pastiche, opt, up)
     for it in range(1, evals + 1):
-        net._forward_plan(pastiche, keep=True)
-        if live is None:
-            live = net._live_slots()
-            up[live] = 1.0
-        grad = net._backward_plan(up)
-        if print_iter > 0 and it % print_iter == 0 and getattr(args, "verbose", False):
-            total = float(net._loss_vec[live].sum())
-            print(f"Iteration {it} / {args.num_iters}, Loss: {total}")
-        if save_iter > 0 and (it % save_iter == 0 or it == num_iters):
+        want_print = print_iter > 0 and it % print_iter == 0 and getattr(args, "verbose", False)
+        want_save = save_iter > 0 and (it % save_iter == 0 or it == num_iters)
+        if want_save:
+            # optim.py:230-236 saves the image the closure was evaluated on, i.e. before this iteration's update
             _save_intermediate(pastiche, args, it, num_iters)
-        opt.step(grad)
+        iteration()
+        if want_print:
+            total = float(net._loss_vec[live].sum())  # the losses of the image before the update, like optim.py:228-229
+            print(f"Iteration {it} / {args.num_iters}, Loss: {total}")
     for mod in losses:
         mod.loss = 0
     out = pastiche.cpu()
