@@ -86,6 +86,15 @@ MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int
                                 const float* mask_src, const float* aux_f, const float* aux_d,
                                 const float* aux_bias, const float* cont_f, const float* cont_t,
                                 const float* cont_coef, int round_tf32, int impl, maua_stream_t stream);
+/* Sign bitmap of an NHWC activation x [npix][c] (c % 32 == 0): bits[pixel * (c/32) + ch/32] bit (ch % 32) = x > 0.  The
+ * plan keeps one per conv layer (written by the forward epilogue) as the ReLU mask of the backward pass: autograd's
+ * threshold_backward reads the fp32 activation instead (models.py:130 ReLU(inplace)), 32x the bytes. */
+MAUA_API int maua_relu_mask_bits(const float* x, uint32_t* bits, long npix, int c, maua_stream_t stream);
+/* maua_conv3x3_dgrad with the ReLU mask given as a sign bitmap; this variant runs the TMA-store epilogue
+ * (registers -> swizzled shared-memory box -> cp.async.bulk.tensor store). */
+MAUA_API int maua_conv3x3_dgrad_bits(const float* gy, const float* wd, float* gx, int b, int h, int w, int cout, int cin,
+                                     const uint32_t* mask_bits, const float* aux_f, const float* aux_d,
+                                     const float* aux_bias, int round_tf32, int impl, maua_stream_t stream);
 /* First layer (Cin = 3): image NCHW [B,3,H,W] -> NHWC [B,H,W,Cout], bias + ReLU; w is plain OIHW fp32. */
 MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const float* bias, float* y, int b, int h,
                                  int w, int cout, maua_stream_t stream);

@@ -128,11 +128,36 @@ MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int
     return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
 }
 
+MAUA_API int maua_relu_mask_bits(const float* x, uint32_t* bits, long npix, int c, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && bits && npix > 0 && c > 0, "maua_relu_mask_bits: bad arguments");
+    return relu_mask_bits_launch(x, bits, npix, c, (cudaStream_t)stream);
+}
+
+MAUA_API int maua_conv3x3_dgrad_bits(const float* gy, const float* wd, float* gx, int b, int h, int w, int cout, int cin,
+                                     const uint32_t* mask_bits, const float* aux_f, const float* aux_d,
+                                     const float* aux_bias, int round_tf32, int impl, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(gx, "maua_conv3x3_dgrad_bits: null output");
+    MAUA_REQUIRE((gy != nullptr) == (wd != nullptr), "maua_conv3x3_dgrad_bits: gy and wd must both be given or both NULL");
+    MAUA_REQUIRE((aux_f != nullptr) == (aux_d != nullptr), "maua_conv3x3_dgrad_bits: aux_f and aux_d go together");
+    MAUA_REQUIRE(gy || aux_f, "maua_conv3x3_dgrad_bits: nothing to compute (no gy and no aux term)");
+    ConvArgs a;
+    a.B = b; a.H = h; a.W = w;
+    a.Cin = cout; a.Cout = cin;
+    a.ntaps = gy ? 9 : 0;
+    a.in = gy; a.wg = wd;
+    if (aux_f) { a.K2 = cin; a.in2 = aux_f; a.w2 = aux_d; }
+    a.ep.out = gx; a.ep.bias = aux_bias; a.ep.mask_bits = mask_bits;
+    a.ep.relu = 0; a.ep.round = round_tf32;
+    return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
+}
+
 MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const float* bias, float* y, int b, int h,
                                  int w, int cout, maua_stream_t stream) {
     MAUA_ENTRY_GUARD();
     MAUA_REQUIRE(img && w_oihw && y, "maua_conv_first_fwd: null pointer");
-    return conv_first_fwd_launch(img, w_oihw, bias, y, b, h, w, cout, 1, (cudaStream_t)stream);
+    return conv_first_fwd_launch(img, w_oihw, bias, y, nullptr, b, h, w, cout, 1, (cudaStream_t)stream);
 }
 MAUA_API int maua_conv_first_dgrad(const float* gy, const float* w_oihw, float* gimg, int b, int h, int w, int cout,
                                    const float* img, const float* tv_coef, const float* temp_target,

@@ -29,7 +29,7 @@ constexpr int FI_W = 68;       // staged image row: 64 + 2 halo, padded to a flo
 
 __global__ void __launch_bounds__(256)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
-                      float* __restrict__ out, int B, int H, int W, int do_round) {
+                      float* __restrict__ out, uint16_t* __restrict__ mask16, int B, int H, int W, int do_round) {
     constexpr int Cout = 64, G = 4;
     __shared__ __align__(16) float ws[27 * G * FG_STRIDE];
     __shared__ float bs[Cout];
@@ -97,7 +97,9 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
             for (int j = 0; j < 4; ++j) {
                 const int x = w0 + 4 * quad + j;
                 if (x >= W) continue;
-                float4* op = reinterpret_cast<float4*>(out + (((long)b * H + h) * W + x) * Cout + g * 16);
+                const long pix = ((long)b * H + h) * W + x;
+                float4* op = reinterpret_cast<float4*>(out + pix * Cout + g * 16);
+                uint32_t bits = 0;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
                     float4 o;
@@ -105,7 +107,10 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
                     o.z = fmaxf(acc[j][4 * c4 + 2], 0.f); o.w = fmaxf(acc[j][4 * c4 + 3], 0.f);
                     if (do_round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
                     op[c4] = o;
+                    bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << (4 * c4);
                 }
+                // sign bitmap of the output (16 channels of this thread = one half-word): the ReLU mask dgrad reads
+                if (mask16) mask16[pix * (Cout / 16) + g] = (uint16_t)bits;
             }
         }
     }
@@ -196,12 +201,12 @@ conv_first_gather_kernel(const float* __restrict__ T /*NHWC [B][H][W][32]*/, flo
 
 }  // namespace
 
-int conv_first_fwd_launch(const float* img, const float* w, const float* bias, float* out, int B, int H, int W,
-                          int Cout, int round, cudaStream_t st) {
+int conv_first_fwd_launch(const float* img, const float* w, const float* bias, float* out, uint32_t* mask_out, int B,
+                          int H, int W, int Cout, int round, cudaStream_t st) {
     MAUA_REQUIRE(Cout == 64, "conv_first_fwd: the image layer must have 64 output channels (got %d)", Cout);
     const long ntiles = (long)B * ((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H);
     long blocks = ntiles > 148L * 8 ? 148L * 8 : ntiles;
-    conv_first_fwd_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, B, H, W, round);
+    conv_first_fwd_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

@@ -41,15 +41,19 @@ constexpr int ROW_BYTES = TILE_W * 128;     // one image row of the tile: 16 pix
 struct ConvKParams {
     int B, H, W, Cin, Cout, ntaps, K2;
     int tiles_w, tiles_h, n_tiles, total_tiles;
+    int direct;  // 1: register -> global epilogue (needed for the content / addend / fp32-mask terms), 0: TMA-store epilogue
     ConvEpilogue ep;
 };
+
+constexpr int STAGE_BOX_BYTES = 128 * 128;  // epilogue staging: one {32 ch, 16 w, 8 h} output box
+constexpr int N_STAGE_BOX = 2;
 
 template <int BN, int MT>
 struct ConvCfg {
     static constexpr int A_ROWS = MT * TILE_H + 2;                 // image rows incl. the vertical halo
     static constexpr int A_STAGE = A_ROWS * ROW_BYTES;             // 36864 (MT=2) / 20480 (MT=1): multiples of 1024
     static constexpr int B_STAGE = BN * 128;
-    static constexpr int BUDGET = 200 * 1024;
+    static constexpr int BUDGET = 192 * 1024;                      // operand rings; 32 KB more go to the epilogue staging
     static constexpr int NA = (3 * A_STAGE + 4 * B_STAGE <= BUDGET) ? 3 : 2;
     static constexpr int NB_RAW = (BUDGET - NA * A_STAGE) / B_STAGE;
     static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
@@ -57,7 +61,8 @@ struct ConvCfg {
     static constexpr int NACC = ACC_COLS <= 256 ? 2 : 1;           // double-buffered when TMEM has room
     static constexpr int TMEM_COLS_RAW = NACC * ACC_COLS;
     static constexpr int TMEM_COLS = TMEM_COLS_RAW < 32 ? 32 : TMEM_COLS_RAW;  // power of two, 32..512
-    static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
+    static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ +
+                                      N_STAGE_BOX * STAGE_BOX_BYTES;
     static_assert(NB >= 3, "weight ring too shallow");
 };
 
@@ -73,6 +78,7 @@ template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                const ConvKParams p) {
     using Cfg = ConvCfg<BN, MT>;
     constexpr int NA = Cfg::NA, NB = Cfg::NB, NACC = Cfg::NACC;
@@ -88,6 +94,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full_bar = b_empty + NB;        // [NACC]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [NACC]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint8_t* stage_box = smemB + NB * Cfg::B_STAGE + 1024;  // 1024-byte aligned (ring sizes are multiples of 1024)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -105,6 +112,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmB2);
         }
+        if (!p.direct) tma_prefetch_desc(&tmOut);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -236,7 +244,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int wl = row % TILE_W;
         const ConvEpilogue& ep = p.ep;
         const float ccoef = ep.cont_f ? *ep.cont_coef : 0.f;
-        uint32_t lt = 0;
+        const int words = p.Cout >> 5;  // 32-channel words of the sign bitmaps per pixel
+        const bool issuer = (threadIdx.x == 128);
+        uint32_t lt = 0, box = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
             int b, h0, w0, n0;
             decode(tile, b, h0, w0, n0);
@@ -244,12 +254,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_full_bar[acc], (lt / NACC) & 1);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            if (!p.direct) {
+                // TMEM -> registers -> fused epilogue -> swizzled staging box in shared memory -> TMA store.  A warp-wide
+                // 16-byte store straight to global would touch 32 different lines (the lanes are 32 different pixels): the
+                // LSU retires it at one line per cycle, which is what kept the epilogue of the wide tiles on the critical
+                // path.  The TMA engine writes whole lines and clips ragged tiles by itself.
+#pragma unroll 1
+                for (int m = 0; m < MT; ++m) {
+                    const int h = h0 + m * TILE_H + hl;
+                    const int w = w0 + wl;
+                    const bool valid = (h < p.H) && (w < p.W);
+                    const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 32, ++box) {
+                        float v[32];
+                        tmem_ld_x32(t_base + m * BN + c, v);
+                        if (ep.bias) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c + i));
+                                v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+                            }
+                        }
+                        if (ep.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (ep.mask_bits) {
+                            const uint32_t mk = valid ? __ldg(ep.mask_bits + pix * words + ((n0 + c) >> 5)) : 0u;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
+                        }
+                        if (ep.round) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
+                        }
+                        if (ep.mask_out && valid) {
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+                            ep.mask_out[pix * words + ((n0 + c) >> 5)] = bits;
+                        }
+                        uint8_t* sbox = stage_box + (box & 1) * STAGE_BOX_BYTES;
+                        // the store that last read this staging box (two boxes ago) must have drained it
+                        if (issuer) bulk_wait_group_read<1>();
+                        named_bar_sync(1, 128);
+                        uint8_t* srow = sbox + row * 128;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)  // 128B swizzle: 16-byte chunk k of row r lives at chunk k ^ (r % 8)
+                            *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
+                                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        fence_proxy_async_smem();
+                        named_bar_sync(2, 128);
+                        if (issuer) {
+                            tma_store_4d(&tmOut, sbox, n0 + c, w0, h0 + m * TILE_H, b);
+                            if (ep.out2) tma_store_4d(&tmOut2, sbox, n0 + c, w0, h0 + m * TILE_H, b);
+                            bulk_commit_group();
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int m = 0; m < MT; ++m) {
                 const int h = h0 + m * TILE_H + hl;
                 const int w = w0 + wl;
                 const bool valid = (h < p.H) && (w < p.W);
-                const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.Cout + n0;
+                const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
+                const size_t off = pix * p.Cout + n0;
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 16) {
                     float v[16];
@@ -290,9 +361,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 v[i + 2] = mk.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = mk.w > 0.f ? v[i + 3] : 0.f;
                             }
                         }
+                        if (ep.mask_bits) {
+                            const uint32_t mk = ep.mask_bits[pix * words + ((n0 + c) >> 5)] >> ((n0 + c) & 31);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
+                        }
                         if (ep.round) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                        }
+                        if (ep.mask_out) {
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+                            reinterpret_cast<uint16_t*>(ep.mask_out)[pix * (2 * words) + ((n0 + c) >> 4)] = (uint16_t)bits;
                         }
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
@@ -305,11 +387,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            // all TMEM reads of this warp are complete (tmem_ld_x16 waits): hand the accumulator back to the MMA warp
+            }
+            // all TMEM reads of this warp are complete (the loads wait): hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (issuer && !p.direct) bulk_wait_group<0>();  // outstanding output stores must land before the CTA retires
     }
 
     tc_fence_before();
@@ -421,6 +505,17 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     }
     if (!has_main) { tmA = tmA2; tmB = tmB2; }
     if (!has_aux) { tmA2 = tmA; tmB2 = tmB; }
+    // epilogue flavour: the TMA-store path covers bias / ReLU / bitmap mask / rounding; the content, addend and
+    // fp32-mask terms need per-element global loads and keep the register -> global path
+    const bool direct = a.ep.cont_f || a.ep.addend || a.ep.mask_src;
+    CUtensorMap tmOut, tmOut2;
+    if (!direct) {
+        if ((rc = make_tmap_nhwc(&tmOut, a.ep.out, a.B, a.H, a.W, a.Cout, TILE_W, TILE_H))) return rc;
+        if (a.ep.out2) { if ((rc = make_tmap_nhwc(&tmOut2, a.ep.out2, a.B, a.H, a.W, a.Cout, TILE_W, TILE_H))) return rc; }
+        else tmOut2 = tmOut;
+    } else {
+        tmOut = tmA; tmOut2 = tmA;
+    }
 
     ConvKParams p;
     p.B = a.B; p.H = a.H; p.W = a.W;
@@ -433,8 +528,9 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     p.n_tiles = a.Cout / BN;
     p.total_tiles = p.tiles_w * p.tiles_h * a.B * p.n_tiles;
     p.ep = a.ep;
+    p.direct = direct ? 1 : 0;
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();  // persistent: one CTA per SM
-    conv_tc_kernel<BN, MT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
+    conv_tc_kernel<BN, MT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
@@ -448,6 +544,7 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
                  "tcgen05 conv needs Cin %% 32 == 0 (got %d); the 3-channel image layer uses conv_first_*", a.Cin);
     MAUA_REQUIRE(a.K2 % KCHUNK == 0, "aux K2 must be a multiple of 32 (got %d)", a.K2);
     MAUA_REQUIRE(a.Cout % 32 == 0, "Cout must be a multiple of 32 (got %d)", a.Cout);
+    MAUA_REQUIRE((reinterpret_cast<uintptr_t>(a.ep.out) & 15) == 0, "output pointer must be 16-byte aligned");
     MAUA_REQUIRE(a.B >= 1 && a.H >= 1 && a.W >= 1, "bad extent B=%d H=%d W=%d", a.B, a.H, a.W);
     MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
 
@@ -502,6 +599,7 @@ __global__ void conv_ref_kernel(ConvArgs a) {
         if (ep.addend) v += ep.addend[idx];
         if (ep.relu) v = fmaxf(v, 0.f);
         if (ep.mask_src) v = ep.mask_src[idx] > 0.f ? v : 0.f;
+        if (ep.mask_bits) v = ((ep.mask_bits[pix * (a.Cout >> 5) + (n >> 5)] >> (n & 31)) & 1u) ? v : 0.f;
         if (ep.round) v = round_tf32(v);
         ep.out[idx] = v;
         if (ep.out2) ep.out2[idx] = v;
@@ -515,6 +613,7 @@ int conv_ref_launch(const ConvArgs& a, cudaStream_t st) {
     const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
     conv_ref_kernel<<<blocks, 256, 0, st>>>(a);
     MAUA_CUDA_CHECK(cudaGetLastError());
+    if (a.ep.mask_out) return relu_mask_bits_launch(a.ep.out, a.ep.mask_out, (long)a.B * a.H * a.W, a.Cout, st);
     return MAUA_OK;
 }
 

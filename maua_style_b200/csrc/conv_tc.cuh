@@ -11,14 +11,19 @@ namespace maua {
 //   v += *cont_coef * (cont_f - cont_t)  (ContentLoss gradient, loss.py:53-59)
 //   v += addend                          (gradient arriving from another branch, e.g. un-pooled)
 //   v  = max(v, 0)                       (ReLU, models.py:130)                       if relu
-//   v  = mask_src > 0 ? v : 0            (ReLU backward through the *previous* layer) if mask_src
+//   v  = mask_src > 0 ? v : 0            (ReLU backward through the *previous* layer) if mask_src / mask_bits
 //   v  = round_tf32(v)                   (operand rounding for the consuming MMA)     if round
+// and, for forward layers, mask_out receives the sign bitmap (v > 0) of the result: 1 bit per element, word
+// [pixel * (Cout/32) + n/32], bit n % 32 -- what the dgrad of the layer above reads as mask_bits instead of re-reading
+// the fp32 activation (32x less mask traffic in the backward pass).
 struct ConvEpilogue {
     float* out = nullptr;             // NHWC [B][H][W][Cout]
     float* out2 = nullptr;            // optional second copy of the output (layer-wise split: the next stage's input,
                                       // usually peer memory reached over NVLink -- stored tile by tile from the epilogue)
     const float* bias = nullptr;      // [Cout]
-    const float* mask_src = nullptr;  // NHWC like out
+    const float* mask_src = nullptr;  // NHWC like out (fp32 activation; slower than mask_bits)
+    const uint32_t* mask_bits = nullptr;  // sign bitmap of the activation being masked (see above)
+    uint32_t* mask_out = nullptr;     // sign bitmap of this launch's output
     const float* cont_f = nullptr;    // NHWC like out
     const float* cont_t = nullptr;    // NHWC like out
     const float* cont_coef = nullptr; // device scalar
@@ -41,12 +46,16 @@ struct ConvArgs {
     ConvEpilogue ep;
 };
 
+// sign bitmap of an NHWC activation: bits[pixel * (C/32) + c/32] bit (c % 32) = x[pixel][c] > 0   (C % 32 == 0)
+int relu_mask_bits_launch(const float* x, uint32_t* bits, long npix, int C, cudaStream_t st);
+
 int conv_tc_launch(const ConvArgs& a, cudaStream_t st);   // tcgen05 / TMEM / TMA path
 int conv_ref_launch(const ConvArgs& a, cudaStream_t st);  // naive SIMT cross-check (debug only)
 
 // conv1_1 forward: NCHW 3-channel image -> NHWC Cout, bias + ReLU, fp32 FFMA (K = 27).
 int conv_first_fwd_launch(const float* img, const float* w /*[Cout][3][3][3]*/, const float* bias, float* out,
-                          int B, int H, int W, int Cout, int round, cudaStream_t st);
+                          uint32_t* mask_out /*optional sign bitmap*/, int B, int H, int W, int Cout, int round,
+                          cudaStream_t st);
 
 // conv1_1 dgrad (+ fused image-side tail): NHWC Cout gradient -> NCHW 3-channel image gradient,
 // plus TV gradient and temporal ContentLoss gradient.

@@ -42,6 +42,7 @@ struct Entry {
     // per forward
     int H = 0, W = 0, C = 0;   // output extent
     float* out = nullptr;      // arena pointer
+    uint32_t* bits = nullptr;  // conv only: sign bitmap of `out` (1 bit / element), the ReLU mask of the backward pass
 };
 
 struct Tap {
@@ -128,6 +129,8 @@ struct maua_plan {
     // workspaces
     float* arena = nullptr;
     size_t arena_elems = 0;
+    uint32_t* bits_arena = nullptr;
+    size_t bits_words = 0;
     float* gbuf[3] = {nullptr, nullptr, nullptr};
     size_t gbuf_elems = 0;
     void* reduce_ws = nullptr;
@@ -177,7 +180,7 @@ struct DeviceGuard {
 
 int ensure_workspaces(maua_plan* p, int H, int W) {
     // extents per entry
-    size_t need = 0, max_act = 0;
+    size_t need = 0, max_act = 0, need_bits = 0;
     int h = H, w = W;
     for (auto& e : p->entries) {
         if (e.pool) {
@@ -187,7 +190,19 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         e.H = h; e.W = w;
         const size_t n = (size_t)h * w * e.C;
         need += (n + 63) & ~size_t(63);
+        if (!e.pool) need_bits += (n / 32 + 63) & ~size_t(63);
         if (n > max_act) max_act = n;
+    }
+    if (need_bits > p->bits_words) {
+        if (p->bits_arena) cudaFree(p->bits_arena);
+        p->bits_arena = nullptr;
+        p->bits_words = 0;
+        if (cudaMalloc(&p->bits_arena, need_bits * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            set_last_error("out of device memory allocating the ReLU sign bitmaps for %dx%d", H, W);
+            return MAUA_ERR_OOM;
+        }
+        p->bits_words = need_bits;
     }
     if (need > p->arena_elems) {
         if (p->arena) cudaFree(p->arena);
@@ -215,10 +230,15 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         }
         p->gbuf_elems = max_act;
     }
-    size_t off = 0;
+    size_t off = 0, boff = 0;
     for (auto& e : p->entries) {
         e.out = p->arena + off;
         off += ((size_t)e.H * e.W * e.C + 63) & ~size_t(63);
+        e.bits = nullptr;
+        if (!e.pool) {
+            e.bits = p->bits_arena + boff;
+            boff += ((size_t)e.H * e.W * e.C / 32 + 63) & ~size_t(63);
+        }
     }
     return MAUA_OK;
 }
@@ -393,6 +413,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
         cudaFree(t.gram); cudaFree(t.diff); cudaFree(t.aux_d); cudaFree(t.mean); cudaFree(t.aux_bias); cudaFree(t.gram_ws);
     }
     cudaFree(p->arena);
+    cudaFree(p->bits_arena);
     for (int i = 0; i < 3; ++i) cudaFree(p->gbuf[i]);
     cudaFree(p->reduce_ws); cudaFree(p->coef2);
     delete p;
@@ -400,7 +421,8 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
 
 MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* p) {
     if (!p) return 0;
-    return p->weight_bytes + p->arena_elems * sizeof(float) + 3 * p->gbuf_elems * sizeof(float);
+    return p->weight_bytes + p->arena_elems * sizeof(float) + p->bits_words * sizeof(uint32_t) +
+           3 * p->gbuf_elems * sizeof(float);
 }
 
 MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
@@ -524,7 +546,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
         Entry& e = p->entries[i];
         float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
         if (e.image_layer) {
-            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, 1, H, W, e.cout, 1, st))) return rc;
+            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, 1, st))) return rc;
             if (hand_off)
                 MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
         } else if (e.pool) {
@@ -536,6 +558,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.B = 1; a.H = e.H; a.W = e.W; a.Cin = e.cin; a.Cout = e.cout; a.ntaps = 9;
             a.in = cur; a.wg = e.wg;
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = 1;
+            a.ep.mask_out = e.bits;
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             rc = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
             if (rc) return rc;
@@ -756,7 +779,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             ConvArgs a;
             a.B = 1; a.H = e.H; a.W = e.W; a.Cin = 32; a.Cout = e.C; a.ntaps = 0; a.K2 = 0;
             add_taps(a, e, style, content, ci);
-            a.ep.out = take_buf(); a.ep.mask_src = e.out; a.ep.round = 1; a.ep.addend = grad_top;
+            a.ep.out = take_buf(); a.ep.mask_bits = e.bits; a.ep.round = 1; a.ep.addend = grad_top;
             if (style) {
                 if ((rc = run_conv(a))) return rc;
             } else {
@@ -786,7 +809,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         a.in = gm; a.wg = ec.wd;
         if (!through_pool) {
             add_taps(a, ep_, style, content, ci);
-            a.ep.out = take_buf(); a.ep.mask_src = ep_.out; a.ep.round = 1;
+            a.ep.out = take_buf(); a.ep.mask_bits = ep_.bits; a.ep.round = 1;
             if ((rc = run_conv(a))) return rc;
             gm = a.ep.out;
         } else {

@@ -3,6 +3,7 @@
 // All are vectorised, coalesced, grid-stride kernels sized to a multiple of the SM count, with
 // warp-shuffle reductions and a deterministic last-block final reduce (no float atomics).
 #include "pointwise.cuh"
+#include "conv_tc.cuh"
 #include "reduce.cuh"
 
 namespace maua {
@@ -77,6 +78,17 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
             if (c < C && p < HW) dst[((long)b * C + c) * HW + p] = tile[tx][j];
         }
         __syncthreads();
+    }
+}
+
+// sign bitmap of an NHWC activation (one warp per 32-channel word group: lane = channel, ballot = word)
+__global__ void relu_mask_bits_kernel(const float* __restrict__ x, uint32_t* __restrict__ bits, long nwords) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long wd = warp0; wd < nwords; wd += nwarps) {
+        const uint32_t b = __ballot_sync(0xffffffffu, x[wd * 32 + lane] > 0.f);
+        if (lane == 0) bits[wd] = b;
     }
 }
 
@@ -343,6 +355,13 @@ int nhwc_to_nchw_launch(const float* src, float* dst, int B, int C, int H, int W
     const long HW = (long)H * W;
     const long ntiles = ((HW + 31) / 32) * ((C + 31) / 32) * B;
     nhwc_to_nchw_kernel<<<(int)(ntiles > 148 * 16 ? 148 * 16 : ntiles), 256, 0, st>>>(src, dst, B, C, HW);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+int relu_mask_bits_launch(const float* x, uint32_t* bits, long npix, int C, cudaStream_t st) {
+    MAUA_REQUIRE(C % 32 == 0, "mask bitmap: C %% 32 != 0");
+    const long nwords = npix * (C / 32);
+    relu_mask_bits_kernel<<<grid_for(nwords * 32, 8), kThreads, 0, st>>>(x, bits, nwords);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

@@ -102,6 +102,36 @@ def test_conv3x3_dgrad_with_mask(lib, impl, cin, cout, h, w):
 
 
 @IMPLS
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 64, 32, 48), (64, 128, 17, 23), (256, 512, 12, 20), (512, 256, 9, 7)])
+def test_conv3x3_dgrad_with_bitmap_mask(lib, impl, cin, cout, h, w):
+    """Same contract as above with the ReLU mask as a sign bitmap (what the plan uses): the tcgen05 path then takes the
+    TMA-store epilogue.  Also checks maua_relu_mask_bits itself, bit for bit."""
+    g = torch.Generator().manual_seed(cin * 5 + cout + w)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    gy = tf32_round(torch.randn(1, cout, h, w, generator=g))
+    act = torch.randn(1, cin, h, w, generator=g)
+    x = torch.zeros(1, cin, h, w, requires_grad=True)
+    F.conv2d(x, tf32_round(wt), None, padding=1).backward(gy)
+    ref = x.grad * (act > 0)
+    wdg = prep(lib, wt.cuda(), True)
+    gyd, actd = nhwc(gy).cuda(), nhwc(act).cuda()
+    bits = torch.zeros(h * w * cin // 32, dtype=torch.int32, device="cuda")
+    _lib.check(lib.maua_relu_mask_bits(_lib.ptr(actd), _lib.ptr(bits), C.c_long(h * w), cin, _lib.stream_ptr()), "mask_bits")
+    torch.cuda.synchronize()
+    want = (nhwc(act).reshape(-1, 32) > 0).to(torch.int64)
+    want = (want << torch.arange(32)).sum(1)
+    got = bits.cpu().to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(got, want)
+    gx = torch.empty(1, h, w, cin, device="cuda")
+    null = C.c_void_p(0)
+    _lib.check(lib.maua_conv3x3_dgrad_bits(_lib.ptr(gyd), _lib.ptr(wdg), _lib.ptr(gx), 1, h, w, cout, cin, _lib.ptr(bits),
+                                           null, null, null, 0, impl, _lib.stream_ptr()), "conv3x3_dgrad_bits")
+    torch.cuda.synchronize()
+    err = rel(nchw(gx), ref)
+    assert err < TF32_REL, f"dgrad (bitmap mask) rel err {err}"
+
+
+@IMPLS
 @pytest.mark.parametrize("with_main", [True, False])
 def test_dgrad_with_style_and_content_terms(lib, impl, with_main):
     """gx = (dgrad(gy) + F @ D + bias + coef (F - T)) * (F > 0)  -- the fused tap-gradient epilogue."""
