@@ -47,6 +47,10 @@ typedef enum maua_status {
  * 1 = naive SIMT cross-check (tests / debugging only; never selected by the library itself). */
 #define MAUA_IMPL_TC 0
 #define MAUA_IMPL_REF 1
+/* tests only: tcgen05 path with the CTA grouping forced -- single CTAs (cta_group::1) or CTA pairs (cta_group::2);
+ * MAUA_IMPL_TC picks per launch. */
+#define MAUA_IMPL_TC_1CTA 2
+#define MAUA_IMPL_TC_2CTA 3
 
 MAUA_API int maua_abi_version(void);
 MAUA_API const char* maua_last_error(void);

@@ -16,6 +16,8 @@ HEADER_PATH = _HERE.parent / "include" / "maua_b200.h"
 
 MAUA_IMPL_TC = 0
 MAUA_IMPL_REF = 1
+MAUA_IMPL_TC_1CTA = 2
+MAUA_IMPL_TC_2CTA = 3
 MAUA_MAX_LAYERS = 32
 MAUA_MAX_TAPS = 16
 MODE_NONE, MODE_CAPTURE, MODE_LOSS = 0, 1, 2

@@ -100,6 +100,7 @@ MAUA_API int maua_conv3x3_fwd(const float* x, const float* wg, const float* bias
     a.B = b; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ntaps = 9;
     a.in = x; a.wg = wg;
     a.ep.out = y; a.ep.bias = bias; a.ep.relu = relu; a.ep.round = 1;
+    a.force_cg = impl == MAUA_IMPL_TC_1CTA ? 1 : (impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
     return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
 }
 
@@ -122,6 +123,7 @@ MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int
     a.ep.out = gx; a.ep.bias = aux_bias; a.ep.mask_src = mask_src;
     a.ep.cont_f = cont_f; a.ep.cont_t = cont_t; a.ep.cont_coef = cont_coef;
     a.ep.relu = 0; a.ep.round = round_tf32;
+    a.force_cg = impl == MAUA_IMPL_TC_1CTA ? 1 : (impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
     if (!gy && !aux_f) {
         MAUA_REQUIRE(false, "maua_conv3x3_dgrad: nothing to compute (no gy and no aux term)");
     }
@@ -150,6 +152,7 @@ MAUA_API int maua_conv3x3_dgrad_bits(const float* gy, const float* wd, float* gx
     if (aux_f) { a.K2 = cin; a.in2 = aux_f; a.w2 = aux_d; }
     a.ep.out = gx; a.ep.bias = aux_bias; a.ep.mask_bits = mask_bits;
     a.ep.relu = 0; a.ep.round = round_tf32;
+    a.force_cg = impl == MAUA_IMPL_TC_1CTA ? 1 : (impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
     return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
 }
 

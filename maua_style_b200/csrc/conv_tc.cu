@@ -26,6 +26,9 @@
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused epilogue -> global).
 #include "conv_tc.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace maua {
@@ -48,11 +51,12 @@ struct ConvKParams {
 constexpr int STAGE_BOX_BYTES = 128 * 128;  // epilogue staging: one {32 ch, 16 w, 8 h} output box
 constexpr int N_STAGE_BOX = 2;
 
-template <int BN, int MT>
+template <int BN, int MT, int CG>
 struct ConvCfg {
+    static constexpr int BNL = BN / CG;                            // weight rows this CTA keeps (half the tile in a pair)
     static constexpr int A_ROWS = MT * TILE_H + 2;                 // image rows incl. the vertical halo
     static constexpr int A_STAGE = A_ROWS * ROW_BYTES;             // 36864 (MT=2) / 20480 (MT=1): multiples of 1024
-    static constexpr int B_STAGE = BN * 128;
+    static constexpr int B_STAGE = BNL * 128;
     static constexpr int BUDGET = 192 * 1024;                      // operand rings; 32 KB more go to the epilogue staging
     static constexpr int NA = (3 * A_STAGE + 4 * B_STAGE <= BUDGET) ? 3 : 2;
     static constexpr int NB_RAW = (BUDGET - NA * A_STAGE) / B_STAGE;
@@ -64,6 +68,8 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ +
                                       N_STAGE_BOX * STAGE_BOX_BYTES;
     static_assert(NB >= 3, "weight ring too shallow");
+    static_assert(CG == 1 || CG == 2, "CTA group size");
+    static_assert(BNL % 16 == 0 && BNL >= 16, "per-CTA weight rows");
 };
 
 // Persistent, warp-specialised kernel: each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -74,14 +80,21 @@ struct ConvCfg {
 //
 // K is walked in groups.  3x3 main term: group = (dx, channel chunk), one halo box + 3 weight tiles (dy = -1, 0, 1).
 // Pointwise main term (ntaps == 1) and the aux term: group = channel chunk, one plain box + 1 weight tile.
-template <int BN, int MT>
+//
+// CG = 2 runs the same pipeline on CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2): a pair owns a tile of 2*MT sub-tiles
+// (this CTA the ones at rows h0 + rank*MT*8 ...), every MMA is M = 256 across both CTAs, and each CTA loads its own
+// activation boxes but only HALF of every weight tile.  All TMA loads complete on the even CTA's barriers (its producer
+// arms them for both CTAs' bytes), the even CTA's MMA warp issues for the pair and its commits arrive in both CTAs.
+template <int BN, int MT, int CG>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                const ConvKParams p) {
-    using Cfg = ConvCfg<BN, MT>;
+    using Cfg = ConvCfg<BN, MT, CG>;
     constexpr int NA = Cfg::NA, NB = Cfg::NB, NACC = Cfg::NACC;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 leads
+    const int cta_tile0 = blockIdx.x / CG, cta_tile_step = gridDim.x / CG;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -119,16 +132,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[i], 4 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before any TMA / commit targets them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -140,17 +154,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int th = pt % p.tiles_h;
         b = pt / p.tiles_h;
         w0 = tw * TILE_W;
-        h0 = th * (TILE_H * MT);
+        h0 = th * (TILE_H * MT * CG) + (int)rank * (TILE_H * MT);  // this CTA's rows of the (pair) tile
         n0 = nt * BN;
     };
+    const int nb0 = (int)rank * Cfg::BNL;  // this CTA's rows of every weight tile
 
     // The producer and MMA roles run with the whole warp converged; a single lane chosen by elect.sync issues the TMA /
     // tcgen05 instructions.  (Entering these loops with only lane 0 active makes ptxas wrap every UTCHMMA in an
     // ELECT / BRA.U.ANY loop, which makes the short N = 64 MMAs issue-bound.)
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // In a pair both CTAs load (own activations, own half of the weights) but only the even CTA arms the barriers,
+        // for the bytes of both.
+        auto arm = [&](uint64_t* bar, uint32_t bytes) { if (rank == 0) mbar_arrive_expect_tx(bar, bytes * CG); };
+        auto load_a = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+            if (CG == 2) tma_load_4d_2sm(dst, m, bar, c0, c1, c2, c3); else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+        };
+        auto load_b = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+            if (CG == 2) tma_load_2d_2sm(dst, m, bar, c0, c1); else tma_load_2d(dst, m, bar, c0, c1);
+        };
         uint32_t ia = 0, ib = 0;  // ring counters across tiles
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = cta_tile0; tile < p.total_tiles; tile += cta_tile_step) {
             int b, h0, w0, n0;
             decode(tile, b, h0, w0, n0);
             for (int g = 0; g < ng; ++g) {
@@ -162,8 +186,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int dxi = g / cpt;                  // 0..2  <->  dx = -1, 0, +1
                     const int c0 = (g - dxi * cpt) * KCHUNK;
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&a_full[sa], Cfg::A_STAGE);
-                        tma_load_4d(sA, &tmA, &a_full[sa], c0, w0 + dxi - 1, h0 - 1, b);
+                        arm(&a_full[sa], Cfg::A_STAGE);
+                        load_a(sA, &tmA, &a_full[sa], c0, w0 + dxi - 1, h0 - 1, b);
                     }
                     __syncwarp();
                     for (int dyi = 0; dyi < 3; ++dyi) {
@@ -171,8 +195,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
                         ++ib;
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
-                            tma_load_2d(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * 3 + dxi) * p.Cin + c0, n0);
+                            arm(&b_full[sb], Cfg::B_STAGE);
+                            load_b(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * 3 + dxi) * p.Cin + c0, n0 + nb0);
                         }
                         __syncwarp();
                     }
@@ -183,20 +207,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
                     ++ib;
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&a_full[sa], MT * A_BYTES);
-                        tma_load_4d(sA, aux ? &tmA2 : &tmA, &a_full[sa], c0, w0, h0, b);
-                        mbar_arrive_expect_tx(&b_full[sb], Cfg::B_STAGE);
-                        tma_load_2d(smemB + sb * Cfg::B_STAGE, aux ? &tmB2 : &tmB, &b_full[sb], c0, n0);
+                        arm(&a_full[sa], MT * A_BYTES);
+                        load_a(sA, aux ? &tmA2 : &tmA, &a_full[sa], c0, w0, h0, b);
+                        arm(&b_full[sb], Cfg::B_STAGE);
+                        load_b(smemB + sb * Cfg::B_STAGE, aux ? &tmB2 : &tmB, &b_full[sb], c0, n0 + nb0);
                     }
                     __syncwarp();
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (the even CTA issues for the pair) =====================
+        constexpr uint32_t idesc = make_idesc_tf32(128 * CG, BN, 0, 0);
+        auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accumulate) {
+            if (CG == 2) umma_tf32_2sm(d, ad, bd, idesc, accumulate); else umma_tf32(d, ad, bd, idesc, accumulate);
+        };
+        auto commit = [&](uint64_t* bar) { if (CG == 2) umma_commit_2sm(bar); else umma_commit(bar); };
         uint32_t ia = 0, ib = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = cta_tile0; tile < p.total_tiles; tile += cta_tile_step, ++lt) {
             const int acc = lt % NACC;
             mbar_wait(&tmem_empty_bar[acc], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
@@ -224,12 +252,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int kk = 0; kk < KCHUNK / 8; ++kk) {
                                 // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-                                umma_tf32(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (started | kk) ? 1u : 0u);
+                                mma(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, (started | kk) ? 1u : 0u);
                             }
                         }
-                        umma_commit(&b_empty[sb]);  // frees the weight slot once these MMAs have read it
-                        if (j == nsteps - 1) umma_commit(&a_empty[sa]);  // ... and the activation box after its last tap
-                        if (j == nsteps - 1 && g == ng - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+                        commit(&b_empty[sb]);  // frees the weight slot (in both CTAs) once these MMAs have read it
+                        if (j == nsteps - 1) commit(&a_empty[sa]);  // ... and the activation box after its last tap
+                        if (j == nsteps - 1 && g == ng - 1) commit(&tmem_full_bar[acc]);  // accumulator complete
                     }
                     __syncwarp();
                     started = 1;
@@ -247,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int words = p.Cout >> 5;  // 32-channel words of the sign bitmaps per pixel
         const bool issuer = (threadIdx.x == 128);
         uint32_t lt = 0, box = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = cta_tile0; tile < p.total_tiles; tile += cta_tile_step, ++lt) {
             int b, h0, w0, n0;
             decode(tile, b, h0, w0, n0);
             const int acc = lt % NACC;
@@ -391,14 +419,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // all TMEM reads of this warp are complete (the loads wait): hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
         }
         if (issuer && !p.direct) bulk_wait_group<0>();  // outstanding output stores must land before the CTA retires
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) {
+        cluster_sync_all();  // the peer may still be reading this CTA's shared memory / signalling its barriers
+        if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -485,11 +518,11 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int CG>
 int launch_cfg(const ConvArgs& a, cudaStream_t st) {
-    using Cfg = ConvCfg<BN, MT>;
-    static unsigned long long attr_done = 0;  // per (BN, MT) instantiation; benign race (idempotent call)
-    MAUA_CUDA_CHECK(ensure_dynamic_smem(conv_tc_kernel<BN, MT>, Cfg::SMEM_BYTES, &attr_done));
+    using Cfg = ConvCfg<BN, MT, CG>;
+    static unsigned long long attr_done = 0;  // per (BN, MT, CG) instantiation; benign race (idempotent call)
+    MAUA_CUDA_CHECK(ensure_dynamic_smem(conv_tc_kernel<BN, MT, CG>, Cfg::SMEM_BYTES, &attr_done));
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
     const bool has_main = a.ntaps > 0;
@@ -497,11 +530,11 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     if (has_main) {
         // 3x3: halo box (MT*8 + 2 image rows) shared by the three vertical taps; pointwise: plain box
         if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, a.ntaps == 9 ? Cfg::A_ROWS : MT * TILE_H))) return rc;
-        if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, BN, 0))) return rc;
+        if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, Cfg::BNL, 0))) return rc;
     }
     if (has_aux) {
         if ((rc = make_tmap_nhwc(&tmA2, a.in2, a.B, a.H, a.W, a.K2, TILE_W, MT * TILE_H))) return rc;
-        if ((rc = make_tmap_2d(&tmB2, a.w2, a.Cout, a.K2, BN, 0))) return rc;
+        if ((rc = make_tmap_2d(&tmB2, a.w2, a.Cout, a.K2, Cfg::BNL, 0))) return rc;
     }
     if (!has_main) { tmA = tmA2; tmB = tmB2; }
     if (!has_aux) { tmA2 = tmA; tmB2 = tmB; }
@@ -524,15 +557,31 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     p.ntaps = has_main ? a.ntaps : 0;
     p.K2 = a.K2;
     p.tiles_w = (a.W + TILE_W - 1) / TILE_W;
-    p.tiles_h = (a.H + TILE_H * MT - 1) / (TILE_H * MT);
+    p.tiles_h = (a.H + TILE_H * MT * CG - 1) / (TILE_H * MT * CG);  // (pair) tiles
     p.n_tiles = a.Cout / BN;
     p.total_tiles = p.tiles_w * p.tiles_h * a.B * p.n_tiles;
     p.ep = a.ep;
     p.direct = direct ? 1 : 0;
-    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();  // persistent: one CTA per SM
-    conv_tc_kernel<BN, MT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
+    const int grid = CG * (p.total_tiles < units ? p.total_tiles : units);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    MAUA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p));
     return MAUA_OK;
+}
+
+template <int BN, int MT>
+int launch_cg(const ConvArgs& a, int cg, cudaStream_t st) {
+    return cg == 2 ? launch_cfg<BN, MT, 2>(a, st) : launch_cfg<BN, MT, 1>(a, st);
 }
 
 }  // namespace
@@ -548,26 +597,52 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     MAUA_REQUIRE(a.B >= 1 && a.H >= 1 && a.W >= 1, "bad extent B=%d H=%d W=%d", a.B, a.H, a.W);
     MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
 
-    // Tile selection: prefer the largest CTA tile (256 pixels x 256 channels = 64 flop per L2 byte), but fall back to
-    // smaller tiles when the bigger one would leave SMs idle or end in a mostly empty last wave.
-    struct Cand { int bn, mt; double quality; };
-    static const Cand cands[] = {{256, 2, 1.00}, {256, 1, 0.85}, {128, 2, 0.85}, {128, 1, 0.70}, {64, 2, 0.60}, {64, 1, 0.50}, {32, 2, 0.40}, {32, 1, 0.30}};
+    // Tile selection: relative MAC rates of the tile shapes measured on B200 (tools/sweep_conv.sh, profiles/ round 1) times
+    // the occupancy of the last wave.  What the sweep shows: with both operands in shared memory an MMA is paced by the
+    // operand read (4 KB of activations + 32 B per weight row the CTA holds), so wide tiles and CTA pairs (cta_group::2,
+    // each CTA holds half of the weight rows) win, and a tile needs its accumulator double-buffered in TMEM (MT * BN <= 256)
+    // to keep the epilogue off the critical path.
+    auto shape_rate = [](int bn, int mt, int cg) -> double {
+        if (cg == 2) {
+            if (bn == 256) return mt == 1 ? 1.00 : 0.88;
+            if (bn == 128) return mt == 2 ? 1.00 : 0.80;
+            if (bn == 64) return mt == 2 ? 0.75 : 0.47;
+            return mt == 2 ? 0.36 : 0.30;
+        }
+        if (bn == 256) return mt == 1 ? 0.90 : 0.85;
+        if (bn == 128) return mt == 2 ? 0.73 : 0.66;
+        if (bn == 64) return mt == 2 ? 0.52 : 0.40;
+        return mt == 2 ? 0.30 : 0.25;
+    };
     const int sms = num_sms();
-    int best_bn = 32, best_mt = 1;
+    int best_bn = 32, best_mt = 1, best_cg = 1;
     double best = -1.0;
-    for (const Cand& c : cands) {
-        if (a.Cout % c.bn) continue;
-        const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + c.mt * TILE_H - 1) / (c.mt * TILE_H)) * a.B * (a.Cout / c.bn);
-        const long waves = (tiles + sms - 1) / sms;
-        const double eff = (double)tiles / (double)(waves * sms);
-        const double score = eff * c.quality;
-        if (score > best) { best = score; best_bn = c.bn; best_mt = c.mt; }
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+        if (a.Cout % bn) continue;
+        for (int mt = 2; mt >= 1; --mt)
+            for (int cg = 2; cg >= 1; --cg) {
+                if (a.force_cg && cg != a.force_cg) continue;
+                const int units = sms / cg;
+                const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) *
+                                   ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
+                const long waves = (tiles + units - 1) / units;
+                const double eff = (double)tiles / (double)(waves * units);
+                // rows of the (pair) tile that exist: ragged bottoms waste MMA work
+                const double rows = (double)a.H / (double)(((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * cg * mt * TILE_H);
+                const double score = eff * rows * shape_rate(bn, mt, cg);
+                if (score > best) { best = score; best_bn = bn; best_mt = mt; best_cg = cg; }
+            }
     }
-    const int bn = best_bn, mt = best_mt;
-    if (bn == 256) return mt == 2 ? launch_cfg<256, 2>(a, st) : launch_cfg<256, 1>(a, st);
-    if (bn == 128) return mt == 2 ? launch_cfg<128, 2>(a, st) : launch_cfg<128, 1>(a, st);
-    if (bn == 64) return mt == 2 ? launch_cfg<64, 2>(a, st) : launch_cfg<64, 1>(a, st);
-    return mt == 2 ? launch_cfg<32, 2>(a, st) : launch_cfg<32, 1>(a, st);
+    int bn = best_bn, mt = best_mt, cg = best_cg;
+    if (const char* f = getenv("MAUA_CONV_FORCE")) {  // developer override for tile-shape experiments: "bn,mt,cg"
+        int fb = 0, fm = 0, fc = 0;
+        if (sscanf(f, "%d,%d,%d", &fb, &fm, &fc) == 3 && a.Cout % fb == 0 && (fm == 1 || fm == 2) && (fc == 1 || fc == 2) &&
+            (fb == 32 || fb == 64 || fb == 128 || fb == 256)) { bn = fb; mt = fm; cg = fc; }
+    }
+    if (bn == 256) return mt == 2 ? launch_cg<256, 2>(a, cg, st) : launch_cg<256, 1>(a, cg, st);
+    if (bn == 128) return mt == 2 ? launch_cg<128, 2>(a, cg, st) : launch_cg<128, 1>(a, cg, st);
+    if (bn == 64) return mt == 2 ? launch_cg<64, 2>(a, cg, st) : launch_cg<64, 1>(a, cg, st);
+    return mt == 2 ? launch_cg<32, 2>(a, cg, st) : launch_cg<32, 1>(a, cg, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -38,6 +38,7 @@ struct ConvEpilogue {
 struct ConvArgs {
     int B = 1, H = 0, W = 0;
     int Cin = 0, Cout = 0, ntaps = 9;
+    int force_cg = 0;            // 0: pick single CTAs or CTA pairs per launch; 1 / 2: force (tests)
     const float* in = nullptr;   // NHWC [B][H][W][Cin], values tf32-representable
     const float* wg = nullptr;   // [Cout][ntaps*Cin], tf32-rounded
     int K2 = 0;

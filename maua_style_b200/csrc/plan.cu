@@ -426,7 +426,7 @@ MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* p) {
 }
 
 MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
-    MAUA_REQUIRE(p && (impl == MAUA_IMPL_TC || impl == MAUA_IMPL_REF), "maua_plan_set_impl: bad arguments");
+    MAUA_REQUIRE(p && impl >= MAUA_IMPL_TC && impl <= MAUA_IMPL_TC_2CTA, "maua_plan_set_impl: bad arguments");
     p->impl = impl;
     return MAUA_OK;
 }
@@ -559,6 +559,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.in = cur; a.wg = e.wg;
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = 1;
             a.ep.mask_out = e.bits;
+            a.force_cg = p->impl == MAUA_IMPL_TC_1CTA ? 1 : (p->impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             rc = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
             if (rc) return rc;
@@ -725,6 +726,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     };
     auto run_conv = [&](ConvArgs& a) -> int {
         p->launches_bwd++;
+        a.force_cg = p->impl == MAUA_IMPL_TC_1CTA ? 1 : (p->impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
         const int r = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
         const double px = (double)a.H * a.W;
         // algorithmic work: dgrad GEMM + StyleLoss backward GEMM; bytes: gradient in + out, mask / feature read

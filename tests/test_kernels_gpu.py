@@ -30,7 +30,9 @@ def tf32_round(x):
     return i.view(torch.float32)
 
 
-IMPLS = pytest.mark.parametrize("impl", [pytest.param(_lib.MAUA_IMPL_REF, id="ref"), pytest.param(_lib.MAUA_IMPL_TC, id="tc")])
+IMPLS = pytest.mark.parametrize("impl", [pytest.param(_lib.MAUA_IMPL_REF, id="ref"), pytest.param(_lib.MAUA_IMPL_TC, id="tc"),
+                                         pytest.param(_lib.MAUA_IMPL_TC_1CTA, id="tc1cta"),
+                                         pytest.param(_lib.MAUA_IMPL_TC_2CTA, id="tc2cta")])
 
 
 @pytest.fixture(scope="module")

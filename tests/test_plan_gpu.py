@@ -216,6 +216,32 @@ def test_tc_and_simt_plans_agree(ckpt, pooling):
     assert err < (5e-4 if pooling == "avg" else 3e-2)
 
 
+def test_cta_pair_and_single_cta_plans_agree(ckpt):
+    """The same plan with every conv forced onto CTA pairs (cta_group::2, M = 256 MMAs) or onto single CTAs computes the
+    same sums in a different tiling: with average pooling (no arg-max flips) the gradients agree to accumulation round-off."""
+    from maua_style_b200 import _lib, optim
+
+    z, meta = load_golden("adam_gram_90x122")
+    meta = dict(meta)
+    meta["over"] = dict(meta["over"], pooling="avg")
+    content, styles, init = golden_inputs(meta)
+    grads, vecs = [], []
+    for impl in (_lib.MAUA_IMPL_TC_1CTA, _lib.MAUA_IMPL_TC_2CTA):
+        args, net, losses, _ = build(ckpt, meta)
+        net.set_impl(impl)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, styles, args)
+        for m in losses:
+            m.mode = "loss"
+        v, g = optim.feval(net, init.clone().cuda())
+        grads.append(g.clone())
+        vecs.append(v.clone())
+    err = rel(grads[0], grads[1])
+    report(f"1-CTA vs CTA-pair plan gradient (avg pool) rel {err:.2e}")
+    assert err < 5e-4
+    assert torch.allclose(vecs[0], vecs[1], rtol=1e-4)
+
+
 def test_temporal_loss_and_autograd_interface(ckpt):
     """vid_img path: set_temporal_targets + weighted temporal ContentLoss (loss.py:46-54) through net(x).backward()."""
     from maua_style_b200 import optim
