@@ -153,6 +153,29 @@ MAUA_API int maua_adam_step(float* param, const float* grad, float* exp_avg, flo
 MAUA_API int maua_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr,
                                 float beta1, float beta2, float eps, const int* step_dev, maua_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Image-side operations either side of the loop: with these the pastiche stays in
+ * HBM from one scale / frame to the next and only 8-bit RGB crosses PCIe.  Images are NCHW planes [planes][H][W].
+ * ---------------------------------------------------------------------------------------------- */
+/* F.interpolate(x, mode="bilinear", align_corners=False) -- style.py:38-41, :47-49, :57-66 (img_img scale
+ * transition), :205-212, :241-255, :284-286 (vid_img), load.py:211-213.  scale_h / scale_w: the `scale_factor` the
+ * caller passed to F.interpolate (the source step is then 1/scale_factor, like ATen), or 0 when it passed `size`
+ * (step = in/out).  The caller computes h_out = floor(h_in * scale_factor) itself. */
+MAUA_API int maua_resize_bilinear(const float* src, float* dst, int planes, int h_in, int w_in, int h_out, int w_out,
+                                  double scale_h, double scale_w, maua_stream_t stream);
+/* F.grid_sample(x, grid, padding_mode="border") (bilinear, align_corners=False) -- style.py:223, :279: warps the
+ * previous frame's pastiche along the optical flow.  grid: [h_out][w_out][2] normalised (x, y) in [-1, 1]. */
+MAUA_API int maua_grid_sample_border(const float* src, const float* grid, float* dst, int planes, int h_in, int w_in,
+                                     int h_out, int w_out, maua_stream_t stream);
+/* load.preprocess (load.py:21-32): RGB -> BGR, 0-255, minus the mean pixel (103.939, 116.779, 123.68).
+ * _u8: from a PIL image's bytes (HWC uint8, device memory); _f32: from a ToTensor()-style CHW float image in [0,1]. */
+MAUA_API int maua_preprocess_u8(const uint8_t* rgb_hwc, float* bgr_chw, int h, int w, maua_stream_t stream);
+MAUA_API int maua_preprocess_f32(const float* rgb_chw, float* bgr_chw, int h, int w, maua_stream_t stream);
+/* load.deprocess (load.py:47-52) down to the bytes ToPILImage would hold: HWC uint8 RGB (device memory). */
+MAUA_API int maua_deprocess_u8(const float* bgr_chw, uint8_t* rgb_hwc, int h, int w, maua_stream_t stream);
+/* out = a * x + b * y -- style.py:290 `(1 - temporal_blend) * blend_image + temporal_blend * pastiche`.  out may alias. */
+MAUA_API int maua_blend(const float* x, const float* y, float* out, long n, float a, float b, maua_stream_t stream);
+
 typedef struct maua_lbfgs maua_lbfgs_t;
 /* L-BFGS state for one n-element parameter vector (torch.optim.LBFGS semantics without line search:
  * history ring of `history` (s, y) pairs, lr, first-step t = min(1, 1/|g|_1) * lr, ys > 1e-10 update gate,

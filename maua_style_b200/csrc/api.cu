@@ -251,4 +251,45 @@ MAUA_API int maua_adam_step_dev(float* param, const float* grad, float* exp_avg,
     return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev, (cudaStream_t)stream);
 }
 
+// ---- image-side operations either side of the loop (image_ops.cu) ----
+MAUA_API int maua_resize_bilinear(const float* src, float* dst, int planes, int h_in, int w_in, int h_out, int w_out,
+                                  double scale_h, double scale_w, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(src && dst && planes > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0,
+                 "maua_resize_bilinear: bad arguments (planes=%d %dx%d -> %dx%d)", planes, h_in, w_in, h_out, w_out);
+    // ATen compute_scales_value: 1 / scale_factor when the caller gave one (F.interpolate(scale_factor=...) without
+    // recompute_scale_factor), else in / out
+    const float rh = scale_h > 0.0 ? (float)(1.0 / scale_h) : (float)h_in / (float)h_out;
+    const float rw = scale_w > 0.0 ? (float)(1.0 / scale_w) : (float)w_in / (float)w_out;
+    return resize_bilinear_launch(src, dst, planes, h_in, w_in, h_out, w_out, rh, rw, (cudaStream_t)stream);
+}
+MAUA_API int maua_grid_sample_border(const float* src, const float* grid, float* dst, int planes, int h_in, int w_in,
+                                     int h_out, int w_out, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(src && grid && dst && planes > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0,
+                 "maua_grid_sample_border: bad arguments");
+    MAUA_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 7) == 0, "maua_grid_sample_border: grid must be 8-byte aligned");
+    return grid_sample_border_launch(src, grid, dst, planes, h_in, w_in, h_out, w_out, (cudaStream_t)stream);
+}
+MAUA_API int maua_preprocess_u8(const uint8_t* rgb_hwc, float* bgr_chw, int h, int w, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(rgb_hwc && bgr_chw && h > 0 && w > 0, "maua_preprocess_u8: bad arguments");
+    return preprocess_u8_launch(rgb_hwc, bgr_chw, (long)h * w, (cudaStream_t)stream);
+}
+MAUA_API int maua_preprocess_f32(const float* rgb_chw, float* bgr_chw, int h, int w, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(rgb_chw && bgr_chw && h > 0 && w > 0, "maua_preprocess_f32: bad arguments");
+    return preprocess_f32_launch(rgb_chw, bgr_chw, (long)h * w, (cudaStream_t)stream);
+}
+MAUA_API int maua_deprocess_u8(const float* bgr_chw, uint8_t* rgb_hwc, int h, int w, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(rgb_hwc && bgr_chw && h > 0 && w > 0, "maua_deprocess_u8: bad arguments");
+    return deprocess_u8_launch(bgr_chw, rgb_hwc, (long)h * w, (cudaStream_t)stream);
+}
+MAUA_API int maua_blend(const float* x, const float* y, float* out, long n, float a, float b, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && y && out && n > 0, "maua_blend: bad arguments");
+    return blend_launch(x, y, out, n, a, b, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -25,6 +25,15 @@ int wmse_value_launch(const float* x, const float* wts, const float* t, long n, 
                       float* loss_out, ReduceScratch rs, cudaStream_t st);
 int channel_mean_launch(const float* x, long P, int C, float* mean_out, double* scratch, int scratch_blocks,
                         cudaStream_t st);
+// image_ops.cu: scale transition, video warp, pre/post-processing
+int resize_bilinear_launch(const float* src, float* dst, int planes, int Hin, int Win, int Hout, int Wout, float rh,
+                           float rw, cudaStream_t st);
+int grid_sample_border_launch(const float* src, const float* grid, float* dst, int planes, int Hin, int Win, int Hout,
+                              int Wout, cudaStream_t st);
+int preprocess_u8_launch(const uint8_t* rgb, float* out, long npix, cudaStream_t st);
+int preprocess_f32_launch(const float* rgb, float* out, long npix, cudaStream_t st);
+int deprocess_u8_launch(const float* bgr, uint8_t* rgb, long npix, cudaStream_t st);
+int blend_launch(const float* x, const float* y, float* out, long n, float a, float b, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
                 int step, const int* step_dev, cudaStream_t st);
 

@@ -15,7 +15,10 @@ in-place ReLU overwrites (SURVEY.md section 8a hazard 1), so they never meant wh
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import os
+import weakref
 from typing import List, Optional
 
 import torch
@@ -52,8 +55,8 @@ vgg19_dict = _layer_names(channel_list["VGG-19"])
 _MODES = {"none": _lib.MODE_NONE, "capture": _lib.MODE_CAPTURE, "loss": _lib.MODE_LOSS}
 
 
-def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bool):
-    """models.py:246-347 for the architectures this backend accelerates.  Returns (channels, layer names, state dict)."""
+def _architecture(model_file: str, pooling: str):
+    """models.py:246-347 for the architectures this backend accelerates: (channels, layer names) from the file name."""
     name = str(model_file).lower()
     if "vgg19" in name or "vgg-19" in name:
         channels, layer_list = channel_list["VGG-19"], vgg19_dict
@@ -65,6 +68,12 @@ def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bo
             "use the reference's torch modules for other model families")
     if pooling not in ("max", "avg"):
         raise ValueError("Unrecognized pooling argseter")  # models.py:124
+    return channels, layer_list
+
+
+def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bool):
+    """Returns (channels, layer names, state dict) -- the checkpoint is read with torch.load like models.py:343."""
+    channels, layer_list = _architecture(model_file, pooling)
     sd = torch.load(model_file, map_location="cpu")
     return channels, layer_list, sd
 
@@ -105,20 +114,17 @@ class _PlanFunction(torch.autograd.Function):
         return net._backward_plan(grad_losses), None
 
 
-class B200Net(nn.Module):
-    """The truncated feature stack with its loss modules, executed by libmaua_b200 (csrc/plan.cu)."""
+class _PlanCore:
+    """What survives from one `load_model` call to the next: the frozen weights on the device(s) and the plan(s) built
+    from them (GEMM-layout weight copies, tensor maps, arena).  The reference reloads the checkpoint and rebuilds the
+    network for every scale and every video pass (optim.py:128-129 -> models.py:351-453: torch.load + deepcopy + .cuda());
+    SURVEY.md section 8f rank 1 asks for this to be cached.  A core is keyed by everything the plan depends on and is
+    only handed to one live network at a time."""
 
-    def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device,
-                 stage_bounds: Optional[List[int]] = None, devices: Optional[List[torch.device]] = None):
-        super().__init__()
-        _lib.require_gpu()
-        self._lib = _lib.load()
-        self.device = device  # device of the image side (stage 0); losses and the image gradient are delivered there
-        self.entries = entries
-        self.taps = taps  # [(relu_index, module)] ordered by relu index
-        self.tv_mod = tv_mod
-        self.temporal_mod = temporal_mod
-        # parameters are kept (frozen) so that net.parameters() / state inspection behave like the reference's net
+    def __init__(self, entries, params, avg_pool, tap_sig, device, bounds, devs):
+        lib = _lib.load()
+        self._lib = lib
+        self.device = device
         self.weights = nn.ParameterList([nn.Parameter(w.to(device).contiguous(), requires_grad=False) for w, _ in params])
         self.biases = nn.ParameterList([nn.Parameter(b.to(device).contiguous(), requires_grad=False) for _, b in params])
         desc = _lib.NetDesc()
@@ -131,31 +137,83 @@ class B200Net(nn.Module):
                 desc.biases[i] = self.biases[ci].data_ptr()
                 ci += 1
         desc.avg_pool = int(avg_pool)
-        desc.n_taps = len(taps)
-        for t, (ridx, mod) in enumerate(taps):
+        desc.n_taps = len(tap_sig)
+        for t, (ridx, kind) in enumerate(tap_sig):
             desc.tap_relu_index[t] = ridx
-            desc.tap_kind[t] = _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT
+            desc.tap_kind[t] = kind
+        n_slots = len(tap_sig) + 2
+        self.stages = []
+        self.owner = None  # weakref to the network currently using this core
+        torch.cuda.synchronize(device)  # the weight uploads above are consumed by plan creation on other devices
+        for k, dv in enumerate(devs):
+            plan = C.c_void_p()
+            with torch.cuda.device(dv):
+                if len(devs) == 1:
+                    _lib.check(lib.maua_plan_create(dv.index or 0, C.byref(desc), C.byref(plan)), "maua_plan_create")
+                else:
+                    if k > 0:
+                        _lib.check(lib.maua_enable_peer_access(devs[k - 1].index, dv.index), "maua_enable_peer_access")
+                    _lib.check(lib.maua_plan_create_stage(dv.index or 0, C.byref(desc), bounds[k], bounds[k + 1],
+                                                          C.byref(plan)), "maua_plan_create_stage")
+            self.stages.append({"plan": plan, "device": dv, "begin": bounds[k], "end": bounds[k + 1],
+                                "loss_vec": torch.zeros(n_slots, device=dv),
+                                "coefs": torch.zeros(n_slots, device=dv), "x_in": None, "g_top": None})
+
+    def in_use(self) -> bool:
+        return self.owner is not None and self.owner() is not None
+
+    def __del__(self):
+        stages, self.stages = getattr(self, "stages", []), []
+        for st in stages:
+            try:
+                self._lib.maua_plan_destroy(st["plan"])
+            except Exception:
+                pass
+
+
+_CORE_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_CORE_CACHE_MAX = 2
+cache_stats = {"hits": 0, "misses": 0}
+
+
+def clear_model_cache() -> None:
+    """Drop the cached weights / plans (frees their device memory once no network uses them)."""
+    _CORE_CACHE.clear()
+
+
+
+class B200Net(nn.Module):
+    """The truncated feature stack with its loss modules, executed by libmaua_b200 (csrc/plan.cu)."""
+
+    def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device,
+                 stage_bounds: Optional[List[int]] = None, devices: Optional[List[torch.device]] = None,
+                 core: Optional[_PlanCore] = None):
+        super().__init__()
+        _lib.require_gpu()
+        self._lib = _lib.load()
+        self.device = device  # device of the image side (stage 0); losses and the image gradient are delivered there
+        self.entries = entries
+        self.taps = taps  # [(relu_index, module)] ordered by relu index
+        self.tv_mod = tv_mod
+        self.temporal_mod = temporal_mod
         self._n_slots = len(taps) + 2
         # stages of the layer-wise split (models.py:503-566); the common case is ONE stage = the whole stack
         bounds = list(stage_bounds) if stage_bounds else [0, len(entries)]
         devs = list(devices) if devices else [device]
         if len(devs) != len(bounds) - 1 or bounds[0] != 0 or bounds[-1] != len(entries) or sorted(set(bounds)) != bounds:
             raise ValueError(f"bad stage layout: bounds {bounds} for {len(devs)} device(s) and {len(entries)} entries")
-        self._stages = []
-        torch.cuda.synchronize(device)  # the weight uploads above are consumed by plan creation on other devices
-        for k, dv in enumerate(devs):
-            plan = C.c_void_p()
-            with torch.cuda.device(dv):
-                if len(devs) == 1:
-                    _lib.check(self._lib.maua_plan_create(dv.index or 0, C.byref(desc), C.byref(plan)), "maua_plan_create")
-                else:
-                    if k > 0:
-                        _lib.check(self._lib.maua_enable_peer_access(devs[k - 1].index, dv.index), "maua_enable_peer_access")
-                    _lib.check(self._lib.maua_plan_create_stage(dv.index or 0, C.byref(desc), bounds[k], bounds[k + 1],
-                                                                C.byref(plan)), "maua_plan_create_stage")
-            self._stages.append({"plan": plan, "device": dv, "begin": bounds[k], "end": bounds[k + 1],
-                                 "loss_vec": torch.zeros(self._n_slots, device=dv),
-                                 "coefs": torch.zeros(self._n_slots, device=dv), "x_in": None, "g_top": None})
+        if core is None:
+            tap_sig = [(ridx, _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT) for ridx, mod in taps]
+            core = _PlanCore(entries, params, avg_pool, tap_sig, device, bounds, devs)
+        core.owner = weakref.ref(self)
+        self._core = core
+        # parameters are kept (frozen) so that net.parameters() / state inspection behave like the reference's net
+        self.weights, self.biases = core.weights, core.biases
+        self._stages = core.stages
+        for st in self._stages:  # a re-used core starts from the library defaults
+            st["loss_vec"].zero_()
+            _lib.check(self._lib.maua_plan_set_impl(st["plan"], _lib.MAUA_IMPL_TC), "maua_plan_set_impl")
+            _lib.check(self._lib.maua_plan_set_profile(st["plan"], 0), "maua_plan_set_profile")
         self._plan = self._stages[0]["plan"]
         self._loss_vec = torch.zeros(self._n_slots, device=device)
         self._coefs = self._stages[0]["coefs"]
@@ -171,13 +229,8 @@ class B200Net(nn.Module):
         self.content_losses, self.style_losses, self.tv_losses, self.temporal_losses = [], [], [], []
 
     def __del__(self):
-        stages, self._stages = getattr(self, "_stages", []), []
-        self._plan = None
-        for st in stages:
-            try:
-                self._lib.maua_plan_destroy(st["plan"])
-            except Exception:
-                pass
+        # the plans belong to the core (shared with the model cache); dropping the last reference destroys them
+        self._stages, self._plan, self._core = [], None, None
 
     @property
     def n_stages(self) -> int:
@@ -469,11 +522,41 @@ def _device_from_args(args) -> torch.device:
     return torch.device("cuda", int(gpu.split(",")[0]))
 
 
+def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stage_bounds=None, devices=None) -> "B200Net":
+    """A B200Net on a cached plan core when one exists for (checkpoint file, layer layout, taps, pooling, devices) and no
+    live network is using it; otherwise on a new core built from `params_fn()` (which reads the checkpoint)."""
+    bounds = list(stage_bounds) if stage_bounds else [0, len(entries)]
+    devs = list(devices) if devices else [device]
+    avg = args.pooling == "avg"
+    tap_sig = tuple((ridx, _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT) for ridx, mod in taps)
+    key = None
+    if os.environ.get("MAUA_NO_MODEL_CACHE", "0") != "1":
+        try:
+            st = os.stat(str(args.model_file))
+            key = (os.path.realpath(str(args.model_file)), st.st_mtime_ns, st.st_size, avg, tuple(entries), tap_sig,
+                   tuple(bounds), tuple(str(d) for d in devs))
+        except OSError:
+            key = None
+    core = _CORE_CACHE.get(key) if key is not None else None
+    if core is not None and core.in_use():
+        core, key = None, None  # somebody still holds a network on it: build a private core, leave the cache alone
+    if core is None:
+        cache_stats["misses"] += 1
+        _lib.require_gpu()
+        core = _PlanCore(entries, params_fn(), avg, list(tap_sig), device, bounds, devs)
+        if key is not None:
+            _CORE_CACHE[key] = core
+            while len(_CORE_CACHE) > _CORE_CACHE_MAX:
+                _CORE_CACHE.popitem(last=False)
+    else:
+        cache_stats["hits"] += 1
+        _CORE_CACHE.move_to_end(key)
+    return B200Net(entries, None, avg, taps, tv_mod, temporal_mod, device, stage_bounds=bounds, devices=devs, core=core)
+
+
 def load_model(args):
     """models.py:351-453."""
-    channels, layer_list, sd = select_model(str(args.model_file), args.pooling,
-                                            getattr(args, "verbose", False), getattr(args, "disable_check", False))
-    params_all = _conv_params(sd, channels, getattr(args, "disable_check", False))
+    channels, layer_list = _architecture(str(args.model_file), args.pooling)
     device = _device_from_args(args)
     content_layers = args.content_layers.split(",")
     style_layers = args.style_layers.split(",")
@@ -496,7 +579,7 @@ def load_model(args):
         n_modules += 1
         temporal_losses.append(temporal_mod)
 
-    entries, taps, params = [], [], []
+    entries, taps = [], []
     next_content_idx, next_style_idx, r, conv_i = 1, 1, 0, 0
     for c in channels:
         if not (next_content_idx <= len(content_layers) or next_style_idx <= len(style_layers)):
@@ -506,7 +589,6 @@ def load_model(args):
             n_modules += 1
             continue
         entries.append(c)
-        params.append(params_all[conv_i])
         conv_i += 1
         n_modules += 2  # conv + relu
         name = layer_list["R"][r]
@@ -533,13 +615,20 @@ def load_model(args):
     while entries and entries[-1] == 0:
         entries.pop()  # a trailing pool feeds nothing
 
+    n_convs = conv_i
+
+    def params():
+        """The checkpoint's conv weights up to the last tapped layer -- only read when no cached core exists."""
+        sd = torch.load(str(args.model_file), map_location="cpu")  # models.py:343
+        return _conv_params(sd, channels, getattr(args, "disable_check", False))[:n_convs]
+
     if getattr(args, "multidevice", False):
         from .parallel import setup_multi_device  # layer-wise split over NVLink peers (models.py:537-566)
 
         return setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses,
                                   tv_losses, temporal_losses)
 
-    net = B200Net(entries, params, args.pooling == "avg", taps, tv_mod, temporal_mod, device)
+    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device)
     net.content_losses = content_losses
     net.style_losses = style_losses
     net.tv_losses = tv_losses

@@ -46,8 +46,29 @@ def set_temporal_targets(net, warp_image, warp_weights=None, args=None):
         i.mode = "none"
 
 
+def _style_signature(net, style_images, args):
+    """Everything the captured style targets depend on: the image tensors themselves (identity, storage, in-place version,
+    shape) and the capture settings."""
+    imgs = tuple((id(t), t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in style_images)
+    mods = tuple((bool(j.use_covariance), id(j)) for j in net.style_losses)
+    return imgs, tuple(float(w) for w in args.style_blend_weights[:len(style_images)]), mods
+
+
 def set_style_targets(net, style_images, args):
-    """optim.py:50-66."""
+    """optim.py:50-66.  The reference re-captures the style targets on every `optimize` call -- for vid_img that is one
+    forward per style image per frame although the style images do not change within a scale (style.py:170-177,
+    SURVEY.md section 8f rank 1).  Here a capture is skipped when the same tensors (unmodified) were captured into the
+    same modules with the same blend weights; MAUA_NO_TARGET_CACHE=1 restores the unconditional behaviour."""
+    import os
+
+    sig = _style_signature(net, style_images, args)
+    cached = getattr(net, "_style_cache", None)
+    if (cached is not None and cached[0] == sig and os.environ.get("MAUA_NO_TARGET_CACHE", "0") != "1"
+            and all(j.target.nelement() != 0 for j in net.style_losses)):
+        net.style_cache_hits = getattr(net, "style_cache_hits", 0) + 1
+        for j in net.style_losses:
+            j.mode = "none"
+        return
     for j in net.style_losses:
         j.reset_targets()
         j.mode = "capture"
@@ -57,6 +78,8 @@ def set_style_targets(net, style_images, args):
         net(image)
     for j in net.style_losses:
         j.mode = "none"
+    # keep the images alive while their signature is cached, so neither id() nor the storage address can be re-used
+    net._style_cache = (sig, list(style_images))
 
 
 def set_model_args(args, current_size):
@@ -186,7 +209,14 @@ def feval(net, pastiche: torch.Tensor, ones: Optional[torch.Tensor] = None):
 
 
 def optimize(content, styles, init, num_iters, args, net=None, losses=None):
-    """optim.py:111-255 for transfer types img_img / vid_img (one window, batch 1)."""
+    """optim.py:111-255 for transfer types img_img / vid_img (one window, batch 1): returns the CPU tensor the reference
+    returns (optim.py:249)."""
+    return optimize_device(content, styles, init, num_iters, args, net, losses).cpu()
+
+
+def optimize_device(content, styles, init, num_iters, args, net=None, losses=None):
+    """`optimize` without the final device->host copy: the result stays in HBM for the next scale / frame
+    (maua_style_b200/style.py keeps the whole multi-resolution schedule on the device)."""
     if "_vid" in getattr(args, "transfer_type", "img_img"):
         raise NotImplementedError("img_vid (windowed video-style) optimisation is out of scope for the B200 backend "
                                   "(SURVEY.md section 8f rank 4); use the reference's torch path")
@@ -196,7 +226,7 @@ def optimize(content, styles, init, num_iters, args, net=None, losses=None):
     device = net.device
 
     set_content_targets(net, content.to(device, torch.float32), args)
-    set_style_targets(net, [s.to(device, torch.float32) for s in styles], args)
+    set_style_targets(net, styles, args)  # (the network moves host tensors itself; identity is kept for the target cache)
     for mod in losses:
         mod.mode = "loss"
 
@@ -236,9 +266,8 @@ def optimize(content, styles, init, num_iters, args, net=None, losses=None):
             print(f"Iteration {it} / {args.num_iters}, Loss: {total}")
     for mod in losses:
         mod.loss = 0
-    out = pastiche.cpu()
     opt.close()
-    return out
+    return pastiche
 
 
 def _save_intermediate(pastiche, args, it, num_iters):

@@ -1,0 +1,176 @@
+"""CPU oracle for the image-side steps either side of the maua-style optimisation loop.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE (same rule as oracle/maua_oracle.py: only tests/, smoke() and
+bench.py's CPU legs may import it).
+
+Plain numpy fp32 restatements, operation by operation, of what the reference calls (citations relative to the
+reference repo root, JCBrouwer/maua-style @ 316c552):
+
+    resize_bilinear ...... F.interpolate(x, scale_factor=s | size=hw, mode="bilinear", align_corners=False)
+                           style.py:38-41, :47-49, :57-66, :205-212, :241-255, :284-286; load.py:211-213
+    grid_sample_border ... F.grid_sample(x, grid, padding_mode="border")            style.py:223, :279
+    preprocess_u8 / _f32 . load.preprocess                                          load.py:21-32
+    deprocess_u8 ......... load.deprocess + T.ToPILImage                             load.py:47-52
+    blend ................ (1 - temporal_blend) * blend_image + temporal_blend * p   style.py:290
+    img_img .............. the multi-resolution driver                               style.py:22-73
+
+The arithmetic of interpolate / grid_sample lives in the third-party dependency PyTorch (pinned torch==1.8.1,
+requirements.txt:1; ATen UpSampleBilinear2d / GridSampler, not in the reference tree); the published algorithm is
+restated here: source index = fma(scale, dst+0.5, -0.5) clamped at 0 with scale = 1/scale_factor when a scale
+factor was given, else in/out, value = fma(v0, w0, v1*w1) along w then h; grid_sample un-normalises with
+fma(g+1, size/2, -0.5), clips to [0,size-1] and accumulates the four neighbours times the "opposite corner" areas
+with fused multiply-adds.  The placement of the fused operations is that of the ATen CPU kernels (it was found by
+matching torch 2.11's outputs bit for bit; with it the restatement is bit-exact on every golden).
+
+Pinning: tests/golden/make_golden_image.py runs torch's own F.interpolate / F.grid_sample (the ops the reference
+calls), the UNMODIFIED reference load.preprocess / load.deprocess and the UNMODIFIED reference style.img_img on
+seeded inputs and commits the outputs (tests/golden/image_ops.npz, img_img_64_96.npz); tests/test_image_oracle.py
+checks this file against them.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+BGR_MEAN = np.array([103.939, 116.779, 123.68], dtype=np.float32)  # load.py:30
+f32 = np.float32
+
+
+def interp_out_size(n_in: int, scale_factor: float) -> int:
+    """torch.nn.functional.interpolate: floor(float(in * scale_factor))."""
+    return int(math.floor(float(n_in * scale_factor)))
+
+
+def _src_index(scale: np.float32, n_out: int, n_in: int):
+    dst = np.arange(n_out, dtype=np.float32)
+    # one fused multiply-add (the ATen build contracts scale*(dst+0.5)-0.5; float64 holds the product exactly)
+    real = (np.float64(scale) * (dst + f32(0.5)).astype(np.float64) - 0.5).astype(np.float32)
+    real = np.where(real < 0, f32(0), real).astype(np.float32)
+    i0 = np.minimum(np.floor(real).astype(np.int64), n_in - 1)
+    lam = np.clip(real - i0.astype(np.float32), f32(0), f32(1)).astype(np.float32)
+    i1 = np.minimum(i0 + 1, n_in - 1)
+    return i0, i1, (f32(1) - lam).astype(np.float32), lam
+
+
+def resize_bilinear(x: np.ndarray, size: Optional[Tuple[int, int]] = None, scale_factor: Optional[float] = None) -> np.ndarray:
+    """x: [..., H, W] float32.  Exactly one of size / scale_factor."""
+    x = np.asarray(x, dtype=np.float32)
+    hin, win = x.shape[-2:]
+    if scale_factor is not None:
+        hout, wout = interp_out_size(hin, scale_factor), interp_out_size(win, scale_factor)
+        rh = rw = f32(1.0 / float(scale_factor))
+    else:
+        hout, wout = int(size[0]), int(size[1])
+        rh, rw = f32(hin) / f32(hout), f32(win) / f32(wout)
+    h0, h1, hl0, hl1 = _src_index(rh, hout, hin)
+    w0, w1, wl0, wl1 = _src_index(rw, wout, win)
+
+    def lerp(a, b, wa, wb):  # fma(a, wa, round(b * wb)) -- ATen's contraction of wa*a + wb*b
+        return (a.astype(np.float64) * wa + (b * wb).astype(np.float32).astype(np.float64)).astype(np.float32)
+
+    r0, r1 = x[..., h0, :], x[..., h1, :]
+    if hout + wout <= 128:
+        # ATen routes small outputs (_use_vectorized_kernel_cond_2d: out_h + out_w <= 128) to its vectorised kernel, which
+        # multiplies the weights out first: w00*a + w01*b + w10*c + w11*d, contracted as fma(d,w11,fma(c,w10,fma(a,w00,b*w01)))
+        a, b, c, d = r0[..., :, w0], r0[..., :, w1], r1[..., :, w0], r1[..., :, w1]
+        w00, w01 = (hl0[:, None] * wl0[None, :]).astype(np.float32), (hl0[:, None] * wl1[None, :]).astype(np.float32)
+        w10, w11 = (hl1[:, None] * wl0[None, :]).astype(np.float32), (hl1[:, None] * wl1[None, :]).astype(np.float32)
+        acc = (a.astype(np.float64) * w00 + (b * w01).astype(np.float32).astype(np.float64)).astype(np.float32)
+        acc = (c.astype(np.float64) * w10 + acc.astype(np.float64)).astype(np.float32)
+        return (d.astype(np.float64) * w11 + acc.astype(np.float64)).astype(np.float32)
+    top = lerp(r0[..., :, w0], r0[..., :, w1], wl0, wl1)
+    bot = lerp(r1[..., :, w0], r1[..., :, w1], wl0, wl1)
+    return lerp(top, bot, hl0[:, None], hl1[:, None])
+
+
+def grid_sample_border(x: np.ndarray, grid: np.ndarray) -> np.ndarray:
+    """x: [planes, H, W]; grid: [Ho, Wo, 2] normalised (x, y).  Bilinear, border padding, align_corners=False."""
+    x = np.asarray(x, dtype=np.float32)
+    g = np.asarray(grid, dtype=np.float32)
+    hin, win = x.shape[-2:]
+    # ATen CPU GridSampler: (g + 1) * (size / 2) - 0.5 as one fused multiply-add
+    ix = ((g[..., 0] + f32(1)).astype(np.float64) * np.float64(f32(win) / f32(2)) - 0.5).astype(np.float32)
+    iy = ((g[..., 1] + f32(1)).astype(np.float64) * np.float64(f32(hin) / f32(2)) - 0.5).astype(np.float32)
+    ix = np.minimum(f32(win - 1), np.maximum(ix, f32(0)))
+    iy = np.minimum(f32(hin - 1), np.maximum(iy, f32(0)))
+    x0 = np.floor(ix).astype(np.int64)
+    y0 = np.floor(iy).astype(np.int64)
+    x1, y1 = x0 + 1, y0 + 1
+    w = ix - x0.astype(np.float32)
+    e = f32(1) - w
+    n = iy - y0.astype(np.float32)
+    s = f32(1) - n
+    nw, ne, sw, se = s * e, s * w, n * e, n * w
+    bx1, by1 = x1 < win, y1 < hin
+    x1c, y1c = np.minimum(x1, win - 1), np.minimum(y1, hin - 1)
+    out = (x[:, y0, x0] * nw).astype(np.float32)
+    for val, wt in ((np.where(bx1, x[:, y0, x1c], f32(0)), ne), (np.where(by1, x[:, y1c, x0], f32(0)), sw),
+                    (np.where(bx1 & by1, x[:, y1c, x1c], f32(0)), se)):
+        out = (val.astype(np.float64) * wt + out.astype(np.float64)).astype(np.float32)  # acc = fma(val, wt, acc)
+    return out
+
+
+def preprocess_u8(rgb_hwc: np.ndarray) -> np.ndarray:
+    """uint8 [H,W,3] RGB -> float32 [1,3,H,W] BGR, 0-255, mean-subtracted (ToTensor's /255 and the reference's *255 kept)."""
+    t = (rgb_hwc.astype(np.float32) / f32(255)).transpose(2, 0, 1) * f32(255)
+    return (t[[2, 1, 0]] - BGR_MEAN[:, None, None]).astype(np.float32)[None]
+
+
+def preprocess_f32(rgb_chw: np.ndarray) -> np.ndarray:
+    t = np.asarray(rgb_chw, dtype=np.float32) * f32(255)
+    return (t[[2, 1, 0]] - BGR_MEAN[:, None, None]).astype(np.float32)[None]
+
+
+def deprocess_u8(bgr: np.ndarray) -> np.ndarray:
+    """float32 [1,3,H,W] or [3,H,W] -> uint8 [H,W,3] RGB, the bytes of the PIL image load.deprocess returns."""
+    t = np.asarray(bgr, dtype=np.float32).reshape(3, *bgr.shape[-2:])
+    t = (t - (-BGR_MEAN)[:, None, None]).astype(np.float32)
+    t = (t[[2, 1, 0]] / f32(255)).astype(np.float32)
+    t = np.clip(t, f32(0), f32(1))
+    return (t * f32(255)).astype(np.float32).astype(np.uint8).transpose(1, 2, 0)  # .byte() truncates
+
+
+def blend(x: np.ndarray, y: np.ndarray, a: float, b: float) -> np.ndarray:
+    return (f32(a) * np.asarray(x, np.float32) + f32(b) * np.asarray(y, np.float32)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# style.py:22-73 img_img on tensors (no files, no histogram matching: match_histogram is a no-op on torch >= 2
+# because th.symeig is gone -- SURVEY.md section 2 row 11 -- and goldens are generated with it disabled)
+# ---------------------------------------------------------------------------------------------------------------
+def img_img_plan(content_hw: Tuple[int, int], style_hws: Sequence[Tuple[int, int]], image_sizes: Sequence[int],
+                 style_scale: float = 1.0):
+    """Per scale: (content (h, w), content scale factor, [(style (h, w), style scale factor)]) -- style.py:36-50."""
+    plan = []
+    for size in image_sizes:
+        cs = size / max(*content_hw)
+        ch, cw = interp_out_size(content_hw[0], cs), interp_out_size(content_hw[1], cs)
+        styles = []
+        for sh, sw in style_hws:
+            ss = math.sqrt((ch * cw) / (sw * sh)) * style_scale
+            styles.append(((interp_out_size(sh, ss), interp_out_size(sw, ss)), ss))
+        plan.append(((ch, cw), cs, styles))
+    return plan
+
+
+def img_img(content_big: np.ndarray, styles_big: List[np.ndarray], image_sizes: Sequence[int], num_iters: Sequence[int],
+            optimize_fn, init: str = "content", style_scale: float = 1.0):
+    """Drives `optimize_fn(content, styles, pastiche, num_iters) -> pastiche` over the scales.  Arrays are [1,3,H,W].
+    Returns the list of per-scale results."""
+    assert init == "content", "random init draws unseeded noise in the reference (style.py:55); goldens use init=content"
+    outs, pastiche = [], None
+    for size, iters in zip(image_sizes, num_iters):
+        cs = size / max(*content_big.shape[-2:])
+        content = resize_bilinear(content_big, scale_factor=cs)
+        area = content.shape[2] * content.shape[3]
+        styles = []
+        for s in styles_big:
+            ss = math.sqrt(area / (s.shape[3] * s.shape[2])) * style_scale
+            styles.append(resize_bilinear(s, scale_factor=ss))
+        src = content_big if pastiche is None else pastiche
+        pastiche = resize_bilinear(src, size=content.shape[2:])
+        pastiche = np.asarray(optimize_fn(content, styles, pastiche, iters), dtype=np.float32)
+        outs.append(pastiche)
+    return outs

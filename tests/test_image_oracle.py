@@ -1,0 +1,90 @@
+"""oracle/image_oracle.py against the golden vectors produced by torch's own ops and the unmodified reference
+(tests/golden/make_golden_image.py).  CPU only.  Bit-exact: these are gathers, fused multiply-adds and casts."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, O, save_checkpoint
+from oracle import image_oracle as I
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN / "image_ops.npz", allow_pickle=False)
+
+
+def seeded(shape, seed, lo=-120.0, hi=140.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * (hi - lo) + lo).numpy()
+
+
+def resize_cases(gold):
+    return [(i, *c) for i, c in enumerate(json.loads(str(gold["resize_cases"])))]
+
+
+def test_resize_bilinear_bit_exact(gold):
+    for i, h, w, sf, size, seed in resize_cases(gold):
+        x = seeded((1, 3, h, w), seed)
+        y = I.resize_bilinear(x, size=size, scale_factor=sf)
+        ref = gold[f"resize_{i}"]
+        assert y.shape == ref.shape, (i, y.shape, ref.shape)
+        assert np.array_equal(y, ref), (i, h, w, sf, size, float(np.abs(y - ref).max()))
+
+
+def test_interp_out_size_matches_torch():
+    import torch.nn.functional as F
+
+    for n, s in [(1024, 724 / 1024), (724, 1448 / 724), (122, 0.37), (90, 1.9999), (256, 2.0), (181, 4 / 3)]:
+        assert I.interp_out_size(n, s) == F.interpolate(torch.zeros(1, 1, n, 8), scale_factor=s, mode="bilinear",
+                                                         align_corners=False).shape[2]
+
+
+def test_grid_sample_border_bit_exact(gold):
+    y = I.grid_sample_border(gold["grid_x"][0], gold["grid_g"][0])
+    assert np.array_equal(y, gold["grid_y"][0]), float(np.abs(y - gold["grid_y"][0]).max())
+
+
+def test_preprocess_deprocess_bit_exact(gold):
+    assert np.array_equal(I.preprocess_u8(gold["pre_rgb"]), gold["pre_out"])
+    assert np.array_equal(I.deprocess_u8(gold["de_in"]), gold["de_out"])
+    # ToTensor()-layout float input gives the same image as the uint8 route
+    f = (gold["pre_rgb"].astype(np.float32) / np.float32(255)).transpose(2, 0, 1)
+    assert np.array_equal(I.preprocess_f32(f), gold["pre_out"])
+
+
+def test_blend_and_flow_grid(gold):
+    assert np.array_equal(I.blend(gold["blend_a"], gold["blend_b"], 1 - 0.35, 0.35), gold["blend_out"])
+    fs = gold["flow_smooth"]
+    h, w = fs.shape[:2]
+    neutral = np.rollaxis(np.array(np.meshgrid(np.linspace(-1, 1, w), np.linspace(-1, 1, h))), 0, 3)
+    warp = (neutral + fs).astype(np.float32)
+    grid = I.resize_bilinear(warp.transpose(2, 0, 1)[None], size=gold["flow_grid"].shape[1:3])[0].transpose(1, 2, 0)
+    assert np.array_equal(grid, gold["flow_grid"][0])
+
+
+def test_img_img_driver_matches_reference_pngs(tmp_path):
+    """style.py:22-73 end to end: the oracle's driver + the oracle's Adam must reproduce the PNGs the unmodified
+    reference wrote (fp32 CPU arithmetic on both sides; summation order inside torch ops is the only freedom)."""
+    z = np.load(GOLDEN / "img_img_64_96.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        optimizer=meta["optimizer"], style_blend_weights=meta["blend"])
+    torch.set_flush_denormal(True)
+
+    def optimize_fn(content, styles, pastiche, iters):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        return O.optimize(t(content), [t(s) for s in styles], t(pastiche), iters, cfg, params).detach().numpy()
+
+    outs = I.img_img(I.preprocess_u8(z["content"]), [I.preprocess_u8(z["style1"]), I.preprocess_u8(z["style2"])],
+                     meta["sizes"], meta["iters"], optimize_fn)
+    for size, out in zip(meta["sizes"], outs):
+        ref = z[f"out_{size}"]
+        got = I.deprocess_u8(out)
+        assert got.shape == ref.shape
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        mse = float((diff.astype(np.float64) ** 2).mean())
+        psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+        assert psnr > 45.0, (size, psnr, int(diff.max()))
