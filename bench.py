@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--history-prefill", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch profile JSON here")
+    ap.add_argument("--no-multires", action="store_true", help="skip the 256->512->1024 multi-resolution job (configs[1] whole)")
     return ap.parse_args()
 
 
@@ -62,6 +63,17 @@ def peaks():
         return dict(hbm=float(d["hbm_gbs"]), bf16=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
                     bf16_burst=float(d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+def conv_traffic_per_launch(size):
+    """Average DRAM bytes per conv_tc launch from the committed `ncu --set full` capture of the same workload
+    (tools/ncu_table.py --traffic writes profiles/conv_traffic.json); None when no capture exists for this size."""
+    f = ROOT / "profiles" / "conv_traffic.json"
+    try:
+        d = json.loads(f.read_text())
+        return d.get(str(size), {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def workload_config(size, optimizer):
@@ -329,7 +341,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32 operands / f32 accumulate (f32 storage)", "data": "synthetic",
+        "dtype": "tf32", "dtype_detail": "TF32 tensor-core operands, fp32 accumulate, fp32 storage", "data": "synthetic",
         "config": workload_config(size, args.optimizer), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 4},
         "gpu_launches": gpu_launches,
@@ -359,7 +371,9 @@ def run_ours(args):
             "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
             "peak_source": f"{pk['source']}: bf16_tflops_sustained {pk['bf16']:.1f} / 2 -- TF32 MMA issues at half the bf16 rate",
             "frac_of_bf16_peak": achieved / pk["bf16"],
-            "traffic": None,
+            "traffic": conv_traffic_per_launch(size),
+            "traffic_source": "profiles/conv_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch, ncu --set full)",
+            "achieved_per_launch_flops": conv_flops / max(len(conv), 1), "launches_per_iteration": len(conv),
             "share_of_feval": conv_ms / iter_ms if iter_ms > 0 else None,
             "algorithmic_flops_per_iteration": conv_flops,
         }
@@ -373,12 +387,55 @@ def run_ours(args):
         line["hbm_peak_gbs"] = pk["hbm"]
         if args.profile_out:
             Path(args.profile_out).write_text(json.dumps({"per_launch": prof, "summary": by}, indent=1))
+        if world == 1 and not args.no_multires and size == 1024:
+            line["multires_e2e"] = multires_job(a, dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(size, args.optimizer)
         print(json.dumps(line), flush=True)
     opt.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def multires_job(a, dev):
+    """BASELINE.json configs[1] as a whole job through the public driver (maua_style_b200.style.img_img_tensors): 8-bit
+    RGB content + style images in pinned host memory -> preprocess -> 256 -> 512 -> 1024 with the reference's default
+    iteration counts for those sizes (config.py:23-24: 500, 400, 200), L-BFGS, pastiche resident between scales ->
+    deprocessed 8-bit result copied back to the host.  Wall clock around the whole call, device synchronised."""
+    import copy
+
+    import numpy as np
+
+    from maua_style_b200 import image_ops, style
+
+    b = copy.copy(a)
+    b.image_sizes, b.num_iters, b.init, b.style_scale = [256, 512, 1024], [500, 400, 200], "content", 1.0
+    rs = np.random.RandomState(0)
+
+    def host_image(h, w, seed):  # smooth 8-bit RGB image (what a decoded photo looks like to the pipeline)
+        g = torch.Generator().manual_seed(seed)
+        low = torch.rand(1, 3, h // 8, w // 8, generator=g)
+        img = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)[0]
+        return (img * 255).clamp(0, 255).byte().permute(1, 2, 0).contiguous().pin_memory()
+
+    content_u8, style_u8 = host_image(1024, 1024, 101), host_image(1024, 1024, 102)
+    result = torch.empty(1024, 1024, 3, dtype=torch.uint8).pin_memory()
+
+    def job():
+        content = image_ops.preprocess(content_u8, dev)
+        sty = image_ops.preprocess(style_u8, dev)
+        outs = style.img_img_tensors(content, [sty], b)
+        result.copy_(image_ops.deprocess_u8(outs[-1]), non_blocking=True)
+        torch.cuda.synchronize()
+
+    job()  # warm-up (plan core, arenas, graphs)
+    t0 = time.perf_counter()
+    job()
+    dt = time.perf_counter() - t0
+    iters = sum(b.num_iters)
+    return {"workload": "multi-res 256->512->1024, L-BFGS 500/400/200 iterations, 1 style, host u8 in -> host u8 out",
+            "seconds": dt, "iterations": iters, "value": iters / dt, "unit": UNIT, "images_per_min": 60.0 / dt,
+            "h2d_bytes": int(content_u8.numel() + style_u8.numel()), "d2h_bytes": int(result.numel())}
 
 
 def main():

@@ -539,7 +539,8 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
             key = None
     core = _CORE_CACHE.get(key) if key is not None else None
     if core is not None and core.in_use():
-        core, key = None, None  # somebody still holds a network on it: build a private core, leave the cache alone
+        core = None  # a live network still runs on it: build a fresh core (it takes the cache slot; the old one lives on
+        #              with its network)
     if core is None:
         cache_stats["misses"] += 1
         _lib.require_gpu()

@@ -7,7 +7,7 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 TAG=${1:-r01}
 OUT=gpurun_out/prof_${TAG}
 mkdir -p $OUT
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-multires"
 
 echo "== launch list (same command as the bench, L-BFGS at full history) =="
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file /tmp/launches_all.csv \

@@ -1,10 +1,22 @@
-"""Compact per-launch table from an `ncu --page raw --csv` export:  python tools/ncu_table.py file_raw.csv [name-filter]"""
+"""Compact per-launch table from an `ncu --page raw --csv` export:  python tools/ncu_table.py file_raw.csv [name-filter]
+(`--traffic <size>`: the conv_tc DRAM-traffic summary bench.py reports as roofline.traffic)"""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-flt = sys.argv[2] if len(sys.argv) > 2 else ""
+flt = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else ""
 hdr, units, data = rows[0], rows[1], rows[2:]
+if "--traffic" in sys.argv:  # python tools/ncu_table.py raw.csv --traffic <size>: JSON for profiles/conv_traffic.json (bench.py reads it)
+    import json
+
+    size = sys.argv[sys.argv.index("--traffic") + 1]
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = [float(r[ir].replace(",", "")) * scale.get(units[ir], 1) + float(r[iw].replace(",", "")) * scale.get(units[iw], 1)
+           for r in data if "conv_tc_kernel" in r[ik]]
+    print(json.dumps({size: {"dram_bytes_per_launch": sum(tot) / max(len(tot), 1), "launches": len(tot),
+                             "dram_bytes_per_iteration": sum(tot), "source": "ncu --set full, every conv_tc launch of one feval"}}))
+    sys.exit(0)
 cols = [("Kernel Name", "kernel", 34), ("gpu__time_duration.sum", "us", 9),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%", 8),
         ("dram__bytes_read.sum", "rdMB", 9), ("dram__bytes_write.sum", "wrMB", 9),
