@@ -175,6 +175,21 @@ MAUA_API int maua_preprocess_f32(const float* rgb_chw, float* bgr_chw, int h, in
 MAUA_API int maua_deprocess_u8(const float* bgr_chw, uint8_t* rgb_hwc, int h, int w, maua_stream_t stream);
 /* out = a * x + b * y -- style.py:290 `(1 - temporal_blend) * blend_image + temporal_blend * pastiche`.  out may alias. */
 MAUA_API int maua_blend(const float* x, const float* y, float* out, long n, float a, float b, maua_stream_t stream);
+/* utils.match_histogram (utils.py:88-151; called at style.py:24, :67, :71 and the video drivers): transfer of the
+ * channel means and covariances of the style image(s) onto an image, `mean_s [ Qs Qt^-1 (x - mu_t) + mu_s ]` with
+ * Q = the symmetric square root of the 3x3 channel covariance + eps*I (utils.get_histogram, utils.py:88-93).  Three
+ * asynchronous steps, no host round trip:
+ *   maua_image_moments      one pass over a CHW [3][h][w] image: moments[10] = { N, sum x_c (3), sum x_c x_d (6, upper
+ *                           triangle row-major) } in fp64, reduced in a fixed order (workspace: maua_reduce_workspace_bytes)
+ *   maua_hist_match_coefs   target moments + n_sources consecutive source moment sets -> affine[12] = { M (3x3 row-major),
+ *                           b (3) } (replaces the two th.symeig / th.inverse / th.mm chains, utils.py:124-135)
+ *   maua_color_affine       dst_c = sum_d M[c][d] src_d + b_c over the image (utils.py:135-138); dst may alias src
+ * The reference also perturbs its inputs with 1e-3 * randn (utils.py:120-121); callers reproduce the effect on the
+ * statistics by passing eps + 1e-6, the per-pixel output noise is not reproduced. */
+MAUA_API int maua_image_moments(const float* img_chw, int h, int w, double* moments, void* workspace, maua_stream_t stream);
+MAUA_API int maua_hist_match_coefs(const double* target_moments, const double* source_moments, int n_sources, double eps,
+                                   float* affine, maua_stream_t stream);
+MAUA_API int maua_color_affine(const float* src_chw, float* dst_chw, int h, int w, const float* affine, maua_stream_t stream);
 
 typedef struct maua_lbfgs maua_lbfgs_t;
 /* L-BFGS state for one n-element parameter vector (torch.optim.LBFGS semantics without line search:

@@ -291,5 +291,23 @@ MAUA_API int maua_blend(const float* x, const float* y, float* out, long n, floa
     MAUA_REQUIRE(x && y && out && n > 0, "maua_blend: bad arguments");
     return blend_launch(x, y, out, n, a, b, (cudaStream_t)stream);
 }
+MAUA_API int maua_image_moments(const float* img_chw, int h, int w, double* moments, void* workspace, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(img_chw && moments && workspace && h > 0 && w > 0, "maua_image_moments: bad arguments");
+    MAUA_REQUIRE((reinterpret_cast<uintptr_t>(moments) & 7) == 0, "maua_image_moments: moments must be 8-byte aligned");
+    return image_moments_launch(img_chw, (long)h * w, moments, scratch_from_workspace(workspace), (cudaStream_t)stream);
+}
+MAUA_API int maua_hist_match_coefs(const double* target_moments, const double* source_moments, int n_sources, double eps,
+                                   float* affine, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(target_moments && source_moments && affine && n_sources > 0 && eps >= 0.0,
+                 "maua_hist_match_coefs: bad arguments (n_sources=%d eps=%g)", n_sources, eps);
+    return hist_match_coefs_launch(target_moments, source_moments, n_sources, eps, affine, (cudaStream_t)stream);
+}
+MAUA_API int maua_color_affine(const float* src_chw, float* dst_chw, int h, int w, const float* affine, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(src_chw && dst_chw && affine && h > 0 && w > 0, "maua_color_affine: bad arguments");
+    return color_affine_launch(src_chw, dst_chw, (long)h * w, affine, (cudaStream_t)stream);
+}
 
 }  // extern "C"

@@ -9,12 +9,17 @@
 //   preprocess        load.py:21-32  (ToTensor()*255 -> RGB->BGR -> subtract the BGR mean)
 //   deprocess         load.py:47-52  (add the mean -> BGR->RGB -> /255 -> clamp -> ToPILImage's mul(255).byte())
 //   blend             style.py:290   pastiche = (1 - temporal_blend) * blend_image + temporal_blend * pastiche
+//   match_histogram   utils.py:88-151  colour-statistics transfer (section 8f rank 3) as three launches:
+//                     image_moments (one HBM pass per image: N, sum x_c, sum x_c x_d in fp64, deterministic),
+//                     hist_match_coefs (one thread: 3x3 symmetric eigen-decompositions -> the affine map),
+//                     color_affine (one HBM pass: y = M x + b)
 //
 // All are memory-bound, one thread per output pixel (x fastest => coalesced stores, gathers with 2-D locality), grid
 // capped at a multiple of the SM count with a grid-stride loop.  The arithmetic follows ATen's published kernels
 // (UpSampleBilinear2d / GridSampler) operation by operation in fp32 with explicit rounding intrinsics; the fused
 // multiply-adds sit where the ATen CPU build has them, which makes the results bit-identical to torch's CPU ops.
 #include "pointwise.cuh"
+#include "reduce.cuh"
 
 namespace maua {
 
@@ -147,6 +152,153 @@ blend_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __
         out[i] = __fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(b, y[i]));
 }
 
+// ---- utils.match_histogram (utils.py:88-151) ---------------------------------------------------------------------
+// moments[10] = { N, S0, S1, S2, S00, S01, S02, S11, S12, S22 } of a CHW 3-plane image, accumulated in fp64 (exact
+// products of fp32 values) and reduced in a fixed order (reduce.cuh), so the result is run-to-run identical.
+__global__ void __launch_bounds__(kReduceThreads)
+image_moments_kernel(const float* __restrict__ img, long npix, int vec4, double* __restrict__ moments, double* partials,
+                     unsigned int* counter) {
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = 0.0;
+    auto add = [&](float x0, float x1, float x2) {
+        const double d0 = x0, d1 = x1, d2 = x2;
+        a[0] += d0; a[1] += d1; a[2] += d2;
+        a[3] = fma(d0, d0, a[3]); a[4] = fma(d0, d1, a[4]); a[5] = fma(d0, d2, a[5]);
+        a[6] = fma(d1, d1, a[6]); a[7] = fma(d1, d2, a[7]); a[8] = fma(d2, d2, a[8]);
+    };
+    const long stride = (long)gridDim.x * blockDim.x, first = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (vec4) {
+        const float4* p0 = reinterpret_cast<const float4*>(img);
+        const float4* p1 = reinterpret_cast<const float4*>(img + npix);
+        const float4* p2 = reinterpret_cast<const float4*>(img + 2 * npix);
+        for (long i = first; i < npix / 4; i += stride) {
+            const float4 u = __ldg(p0 + i), v = __ldg(p1 + i), w = __ldg(p2 + i);
+            add(u.x, v.x, w.x); add(u.y, v.y, w.y); add(u.z, v.z, w.z); add(u.w, v.w, w.w);
+        }
+    } else {
+        for (long i = first; i < npix; i += stride) add(__ldg(img + i), __ldg(img + npix + i), __ldg(img + 2 * npix + i));
+    }
+    double tot[9];
+    if (grid_sum<9>(a, partials, counter, tot)) {
+        moments[0] = (double)npix;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) moments[1 + k] = tot[k];
+    }
+}
+
+// cyclic Jacobi for a symmetric 3x3 matrix: a -> eigenvalues w, eigenvectors in the columns of v (fp64, one thread)
+__device__ void sym3_eigen(const double (&c)[3][3], double (&w)[3], double (&v)[3][3]) {
+    double a[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { a[i][j] = c[i][j]; v[i][j] = i == j ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 32; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < 3; ++k) {  // A <- A J
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = cs * akp - sn * akq;
+                    a[k][q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < 3; ++k) {  // A <- J^T A
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = cs * apk - sn * aqk;
+                    a[q][k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {  // V <- V J
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = cs * vkp - sn * vkq;
+                    v[k][q] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = a[i][i];
+}
+
+// mean and covariance (+ eps on the diagonal) from the raw moments: utils.get_histogram (utils.py:88-93)
+__device__ void stats_from_moments(const double* m, double eps, double (&mu)[3], double (&c)[3][3]) {
+    const double n = m[0];
+    for (int i = 0; i < 3; ++i) mu[i] = m[1 + i] / n;
+    const double s[3][3] = {{m[4], m[5], m[6]}, {m[5], m[7], m[8]}, {m[6], m[8], m[9]}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c[i][j] = s[i][j] / n - mu[i] * mu[j] + (i == j ? eps : 0.0);
+}
+
+// f(C) = V diag(f(w)) V^T with f = sqrt (inverse = 0) or 1/sqrt (inverse = 1); negative eigenvalues count as 0
+// (utils.py:125-126 `Et[Et != Et] = 0`), and are floored for the inverse
+__device__ void sym3_sqrt(const double (&c)[3][3], int inverse, double (&q)[3][3]) {
+    double w[3], v[3][3];
+    sym3_eigen(c, w, v);
+    for (int k = 0; k < 3; ++k) {
+        const double r = sqrt(w[k] > 0.0 ? w[k] : 0.0);
+        w[k] = inverse ? 1.0 / (r > 1e-150 ? r : 1e-150) : r;
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) q[i][j] = v[i][0] * w[0] * v[j][0] + v[i][1] * w[1] * v[j][1] + v[i][2] * w[2] * v[j][2];
+}
+
+// affine[12] = { M row-major, b }: mean over the sources of  Qs Qt^-1 (x - mu_t) + mu_s  (utils.py:112-143)
+__global__ void hist_match_coefs_kernel(const double* __restrict__ target_m, const double* __restrict__ source_m,
+                                        int n_sources, double eps, float* __restrict__ affine) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double mu_t[3], ct[3][3], qti[3][3], mbar[3][3] = {}, bbar[3] = {};
+    stats_from_moments(target_m, eps, mu_t, ct);
+    sym3_sqrt(ct, 1, qti);
+    for (int s = 0; s < n_sources; ++s) {
+        double mu_s[3], cs[3][3], qs[3][3];
+        stats_from_moments(source_m + 10 * s, eps, mu_s, cs);
+        sym3_sqrt(cs, 0, qs);
+        for (int i = 0; i < 3; ++i) {
+            double row[3], dot = 0.0;
+            for (int j = 0; j < 3; ++j) {
+                row[j] = qs[i][0] * qti[0][j] + qs[i][1] * qti[1][j] + qs[i][2] * qti[2][j];
+                mbar[i][j] += row[j] / n_sources;
+                dot += row[j] * mu_t[j];
+            }
+            bbar[i] += (mu_s[i] - dot) / n_sources;
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) affine[3 * i + j] = (float)mbar[i][j];
+        affine[9 + i] = (float)bbar[i];
+    }
+}
+
+// y_c = M[c][0] x_0 + M[c][1] x_1 + M[c][2] x_2 + b_c on CHW planes (dst may alias src)
+__global__ void __launch_bounds__(kThreads)
+color_affine_kernel(const float* src, float* dst, long npix, int vec4, const float* __restrict__ affine) {
+    float m[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m[k] = __ldg(affine + k);
+    auto map = [&](float x0, float x1, float x2, int c) {
+        return __fmaf_rn(m[3 * c + 2], x2, __fmaf_rn(m[3 * c + 1], x1, __fmaf_rn(m[3 * c], x0, m[9 + c])));
+    };
+    const long stride = (long)gridDim.x * blockDim.x, first = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (vec4) {
+        for (long i = first; i < npix / 4; i += stride) {
+            const float4 u = reinterpret_cast<const float4*>(src)[i], v = reinterpret_cast<const float4*>(src + npix)[i],
+                         w = reinterpret_cast<const float4*>(src + 2 * npix)[i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                reinterpret_cast<float4*>(dst + c * npix)[i] =
+                    make_float4(map(u.x, v.x, w.x, c), map(u.y, v.y, w.y, c), map(u.z, v.z, w.z, c), map(u.w, v.w, w.w, c));
+        }
+    } else {
+        for (long i = first; i < npix; i += stride) {
+            const float x0 = src[i], x1 = src[npix + i], x2 = src[2 * npix + i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dst[c * npix + i] = map(x0, x1, x2, c);
+        }
+    }
+}
+
 }  // namespace
 
 int resize_bilinear_launch(const float* src, float* dst, int planes, int Hin, int Win, int Hout, int Wout, float rh,
@@ -178,6 +330,29 @@ int deprocess_u8_launch(const float* bgr, uint8_t* rgb, long npix, cudaStream_t 
 }
 int blend_launch(const float* x, const float* y, float* out, long n, float a, float b, cudaStream_t st) {
     blend_kernel<<<grid_for(n), kThreads, 0, st>>>(x, y, out, n, a, b);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+int image_moments_launch(const float* img, long npix, double* moments, ReduceScratch rs, cudaStream_t st) {
+    const int vec4 = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    long blocks = ((vec4 ? npix / 4 : npix) + kReduceThreads - 1) / kReduceThreads;
+    const long cap = 148L * 3;  // 9 partial sums per block must fit the shared reduce scratch (4 per block x 148 x 8)
+    const int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+    MAUA_REQUIRE((long)grid * 9 <= (long)rs.max_blocks * 4, "reduce scratch too small");
+    image_moments_kernel<<<grid, kReduceThreads, 0, st>>>(img, npix, vec4, moments, rs.partials, rs.counter);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+int hist_match_coefs_launch(const double* target_m, const double* source_m, int n_sources, double eps, float* affine,
+                            cudaStream_t st) {
+    hist_match_coefs_kernel<<<1, 32, 0, st>>>(target_m, source_m, n_sources, eps, affine);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+int color_affine_launch(const float* src, float* dst, long npix, const float* affine, cudaStream_t st) {
+    const int vec4 = (npix % 4 == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
+    color_affine_kernel<<<grid_for(vec4 ? npix / 4 : npix), kThreads, 0, st>>>(src, dst, npix, vec4, affine);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

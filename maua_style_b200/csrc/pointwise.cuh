@@ -34,6 +34,11 @@ int preprocess_u8_launch(const uint8_t* rgb, float* out, long npix, cudaStream_t
 int preprocess_f32_launch(const float* rgb, float* out, long npix, cudaStream_t st);
 int deprocess_u8_launch(const float* bgr, uint8_t* rgb, long npix, cudaStream_t st);
 int blend_launch(const float* x, const float* y, float* out, long n, float a, float b, cudaStream_t st);
+// utils.match_histogram as moments -> 3x3 coefficient solve -> affine colour map
+int image_moments_launch(const float* img, long npix, double* moments, ReduceScratch rs, cudaStream_t st);
+int hist_match_coefs_launch(const double* target_m, const double* source_m, int n_sources, double eps, float* affine,
+                            cudaStream_t st);
+int color_affine_launch(const float* src, float* dst, long npix, const float* affine, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, long n, float lr, float b1, float b2, float eps,
                 int step, const int* step_dev, cudaStream_t st);
 

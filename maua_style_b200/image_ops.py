@@ -7,6 +7,7 @@ reference uses, so `style.py`-like drivers read the same:
     grid_sample(x, grid)                           F.grid_sample(x, grid, padding_mode="border")   style.py:223, :279
     preprocess(img) / deprocess_u8(t)              load.py:21-32 / :47-52
     blend(x, y, a, b)                              style.py:290
+    match_histogram(target, sources, eps, mode)    utils.match_histogram   utils.py:88-151 (style.py:24, :67, :71)
 
 Everything runs on the tensor's CUDA device on the current stream; there is no CPU path.
 """
@@ -141,6 +142,77 @@ def blend(x: torch.Tensor, y: torch.Tensor, a: float, b: float, out: Optional[to
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().maua_blend(_lib.ptr(x), _lib.ptr(y), _lib.ptr(out), C.c_long(x.numel()), C.c_float(a), C.c_float(b),
                                           _lib.stream_ptr()), "maua_blend")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# utils.match_histogram (utils.py:88-151) -- SURVEY.md section 8f rank 3
+# ---------------------------------------------------------------------------------------------------------------------
+_REDUCE_WS = {}
+MOMENT_NOISE_VAR = 1e-6  # variance of the `1e-3 * randn` perturbation of utils.py:120-121, as it enters the covariances
+
+
+def _reduce_ws(dev: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch of the deterministic grid reductions, one per device (its counter re-arms itself)."""
+    key = (dev.type, dev.index)
+    if key not in _REDUCE_WS:
+        _REDUCE_WS[key] = torch.zeros(_lib.load().maua_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+    return _REDUCE_WS[key]
+
+
+def image_moments(img: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """{N, sum x_c, sum x_c x_d (upper triangle)} of one [1,3,H,W] / [3,H,W] image as 10 float64 values on the device: the
+    sufficient statistics of utils.get_histogram (utils.py:88-93).  One pass over the image, deterministic."""
+    if img.dim() == 4:
+        if img.shape[0] != 1:
+            raise NotImplementedError("image_moments takes one frame (the reference's B > 1 video paths are out of scope)")
+        img = img[0]
+    if img.dim() != 3 or img.shape[0] != 3:
+        raise ValueError(f"expected a [1,3,H,W] / [3,H,W] image, got {tuple(img.shape)}")
+    img = _dev_f32(img)
+    if out is None:
+        out = torch.empty(10, device=img.device, dtype=torch.float64)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.load().maua_image_moments(_lib.ptr(img), int(img.shape[1]), int(img.shape[2]), _lib.ptr(out),
+                                                  _lib.ptr(_reduce_ws(img.device)), _lib.stream_ptr()), "maua_image_moments")
+    return out
+
+
+def match_histogram(target_tensor: torch.Tensor, source_tensor, eps: float = 1e-2, mode="avg",
+                    source_moments: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils.match_histogram(target_tensor, source_tensor, eps, mode) for single-frame images, on the device: the target's
+    channel means / covariances are mapped onto each source's and the results averaged (utils.py:112-143).  A falsy
+    `mode` returns the target unchanged (utils.py:97-98); for one frame "avg" and the random-frame mode coincide.
+
+    Two passes over the target (moments, affine map) + one per source; the 3x3 eigen-decompositions run in one device
+    thread, so nothing returns to the host.  `source_moments` ([n,10] float64 from `image_moments`) skips the source
+    passes when the same style images are matched against repeatedly (every scale of style.py:67-71).  The statistics
+    include the variance of the reference's `1e-3 * randn` input perturbation (utils.py:120-121); its unseeded per-pixel
+    effect on the output is not reproduced."""
+    if not mode:
+        return target_tensor
+    if target_tensor.dim() != 4 or target_tensor.shape[0] != 1 or target_tensor.shape[1] != 3:
+        raise NotImplementedError(f"match_histogram takes one [1,3,H,W] frame, got {tuple(target_tensor.shape)}")
+    target = _dev_f32(target_tensor)
+    dev = target.device
+    if source_moments is None:
+        sources = source_tensor if isinstance(source_tensor, (list, tuple)) else [source_tensor]
+        source_moments = torch.empty(len(sources), 10, device=dev, dtype=torch.float64)
+        for i, s in enumerate(sources):
+            image_moments(_dev_f32(s, dev), out=source_moments[i])
+    source_moments = source_moments.to(dev, torch.float64).contiguous().view(-1, 10)
+    h, w = int(target.shape[2]), int(target.shape[3])
+    if out is None:
+        out = torch.empty_like(target)
+    affine = torch.empty(12, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        lib = _lib.load()
+        tm = image_moments(target)
+        _lib.check(lib.maua_hist_match_coefs(_lib.ptr(tm), _lib.ptr(source_moments), int(source_moments.shape[0]),
+                                             C.c_double(eps + MOMENT_NOISE_VAR), _lib.ptr(affine), _lib.stream_ptr()),
+                   "maua_hist_match_coefs")
+        _lib.check(lib.maua_color_affine(_lib.ptr(target), _lib.ptr(out), h, w, _lib.ptr(affine), _lib.stream_ptr()),
+                   "maua_color_affine")
     return out
 
 

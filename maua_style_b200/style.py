@@ -13,9 +13,11 @@ module is what it looks like when the steps *around* `optim.optimize` stop bounc
   load.save_tensor_to_file: fp32 D2H, deprocess on the CPU    deprocess on the device, 3 B/pixel D2H (image_ops.deprocess)
 
 `img_img_tensors` / `stylize_frame` work on tensors (what benchmarks and the sharded runner call); `img_img(args)` is
-the file-level entry with the reference's argument names.  Histogram matching (utils.match_histogram) is not applied:
-on torch >= 2 the reference's own call is a no-op because `th.symeig` no longer exists, and
-SURVEY.md section 8f ranks it after this work.
+the file-level entry with the reference's argument names.  Histogram matching (utils.match_histogram, style.py:24, :67,
+:71) runs on the device when `args.match_histograms` is set (image_ops.match_histogram: the style images' colour
+moments are taken once, each call is two passes over the pastiche).  Note that on torch >= 2 the reference's own call
+silently does nothing because `th.symeig` no longer exists; with the flag on, this driver
+does what the reference did under its pinned torch 1.8.1.
 """
 from __future__ import annotations
 
@@ -56,6 +58,12 @@ def img_img_tensors(content_big: torch.Tensor, styles_big: Sequence[torch.Tensor
     with torch.cuda.device(dev):
         content_big = content_big.to(dev, torch.float32).contiguous()
         styles_big = [s.to(dev, torch.float32).contiguous() for s in styles_big]
+        # style.py:24 -- the content image takes the colour statistics of the style images (moments taken once)
+        hist = getattr(args, "match_histograms", False)
+        style_moments = None
+        if hist:
+            style_moments = torch.stack([image_ops.image_moments(s) for s in styles_big])
+            content_big = image_ops.match_histogram(content_big, None, mode=hist, source_moments=style_moments)
         init = getattr(args, "init", "content")
         pastiche = None
         if init not in ("content", "random"):
@@ -81,8 +89,12 @@ def img_img_tensors(content_big: torch.Tensor, styles_big: Sequence[torch.Tensor
                 pastiche = image_ops.interpolate(content_big, size=tuple(content_image.shape[2:]))
             else:
                 pastiche = image_ops.interpolate(pastiche, size=tuple(content_image.shape[2:]))
+            if hist:  # style.py:67
+                pastiche = image_ops.match_histogram(pastiche, None, mode=hist, source_moments=style_moments, out=pastiche)
             # style.py:69 -- per-size model args + (cached) model + targets + the optimisation loop, result stays in HBM
             pastiche = optim.optimize_device(content_image, style_images, pastiche, num_iters, args)
+            if hist:  # style.py:71
+                pastiche = image_ops.match_histogram(pastiche, None, mode=hist, source_moments=style_moments, out=pastiche)
             outs.append(pastiche)
             if on_scale is not None:
                 on_scale(current_size, pastiche)

@@ -12,6 +12,7 @@ reference repo root, JCBrouwer/maua-style @ 316c552):
     preprocess_u8 / _f32 . load.preprocess                                          load.py:21-32
     deprocess_u8 ......... load.deprocess + T.ToPILImage                             load.py:47-52
     blend ................ (1 - temporal_blend) * blend_image + temporal_blend * p   style.py:290
+    match_histogram ...... utils.match_histogram (colour-statistics transfer)       utils.py:88-151
     img_img .............. the multi-resolution driver                               style.py:22-73
 
 The arithmetic of interpolate / grid_sample lives in the third-party dependency PyTorch (pinned torch==1.8.1,
@@ -134,6 +135,53 @@ def deprocess_u8(bgr: np.ndarray) -> np.ndarray:
 
 def blend(x: np.ndarray, y: np.ndarray, a: float, b: float) -> np.ndarray:
     return (f32(a) * np.asarray(x, np.float32) + f32(b) * np.asarray(y, np.float32)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# utils.match_histogram (utils.py:88-151): colour-statistics transfer, SURVEY.md section 8f rank 3
+# ---------------------------------------------------------------------------------------------------------------
+def _sym_sqrt(c: np.ndarray) -> np.ndarray:
+    """utils.py:124-127: Q = V sqrt(diag(w)) V^T of a symmetric matrix, NaNs of sqrt(negative eigenvalue) set to 0."""
+    w, v = np.linalg.eigh(c)
+    with np.errstate(invalid="ignore"):
+        e = np.sqrt(w)
+    e[np.isnan(e)] = 0
+    return (v * e[None, :]) @ v.T
+
+
+def channel_stats(img: np.ndarray, eps: float):
+    """utils.get_histogram (utils.py:88-93) for one [1,3,H,W] image: per-channel mean over every pixel and the channel
+    covariance h h^T / N + eps * I of the mean-centred values."""
+    x = np.asarray(img, dtype=np.float64).reshape(3, -1)
+    mu = x.mean(axis=1)
+    h = x - mu[:, None]
+    return mu, h @ h.T / h.shape[1] + eps * np.eye(3)
+
+
+def match_histogram_affine(target: np.ndarray, sources: Sequence[np.ndarray], eps: float = 1e-2, noise_var: float = 1e-6):
+    """(M, b) of the affine colour map `y = M x + b` that utils.match_histogram(target, sources, mode=True or "avg")
+    applies to every pixel of a single-frame [1,3,H,W] target, in expectation over its noise: per source s,
+    `Qs Qt^-1 (x - mu_t) + mu_s` with Q = sqrt of the channel covariance (+ eps I); the per-source results are averaged
+    (utils.py:112-143).  The reference perturbs both images with 1e-3 * randn first (utils.py:120-121): that adds
+    `noise_var` = 1e-6 to the covariance diagonals, which is kept here.  float64."""
+    mu_t, ct = channel_stats(target, eps + noise_var)
+    qt_inv = np.linalg.inv(_sym_sqrt(ct))
+    m_bar, b_bar = np.zeros((3, 3)), np.zeros(3)
+    for s in sources:
+        mu_s, cs = channel_stats(s, eps + noise_var)
+        m = _sym_sqrt(cs) @ qt_inv
+        m_bar += m / len(sources)
+        b_bar += (mu_s - m @ mu_t) / len(sources)
+    return m_bar, b_bar
+
+
+def match_histogram(target: np.ndarray, sources: Sequence[np.ndarray], eps: float = 1e-2, noise_var: float = 1e-6) -> np.ndarray:
+    """utils.match_histogram without its unseeded per-pixel output perturbation (`1e-3 * M * randn`, the noise the
+    reference adds to the image it transforms): `M x + b` in float64, returned as float32."""
+    target = np.asarray(target, dtype=np.float32)
+    m_bar, b_bar = match_histogram_affine(target, sources, eps, noise_var)
+    x = target.astype(np.float64).reshape(3, -1)
+    return (m_bar @ x + b_bar[:, None]).reshape(target.shape).astype(np.float32)
 
 
 # ---------------------------------------------------------------------------------------------------------------

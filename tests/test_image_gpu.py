@@ -224,3 +224,82 @@ def test_stylize_frame_matches_oracle(tmp_path):
     # second frame on the same net: style targets are not re-captured
     style.stylize_frame(net, losses, content, styles, a, 1, prev_pastiche=out, flow_grid=grid, reliable_flow=reliable)
     assert net.style_cache_hits == 1
+
+
+# ---- utils.match_histogram on the device ----
+def test_match_histogram_vs_reference_outputs_and_oracle():
+    """Against the outputs of the reference's own utils.match_histogram (tests/golden/make_golden_hist.py): the residual
+    must be the reference's `1e-3 * randn` input noise pushed through the colour map, nothing more; against the
+    float64 oracle (no noise): fp32 rounding of the affine map only."""
+    from maua_style_b200 import image_ops
+    from test_image_oracle import check_hist_match, hist_cases
+
+    for name, target, sources, ref in hist_cases():
+        y = image_ops.match_histogram(torch.from_numpy(target).cuda(), [torch.from_numpy(s).cuda() for s in sources], mode=True)
+        y = y.cpu().numpy()
+        check_hist_match(name, y, target, sources, ref)
+        m, _ = I.match_histogram_affine(target, sources)
+        tol = 4e-7 * float(np.abs(m).sum(axis=1).max()) * 260.0 + 1e-5  # |M| |x| eps_fp32 with a small constant
+        want = I.match_histogram(target, sources)
+        assert float(np.abs(y - want).max()) < tol, (name, float(np.abs(y - want).max()), tol)
+
+
+def test_image_moments_exact_on_integers():
+    """Integer-valued images: every sum and product is exact in fp64, so the moments must equal numpy's int64 sums."""
+    from maua_style_b200 import image_ops
+
+    for h, w, seed in [(37, 53, 1), (64, 64, 2), (1024, 1024, 3), (1, 1, 4), (3, 5, 5)]:
+        rs = np.random.RandomState(seed)
+        x = rs.randint(-124, 152, size=(1, 3, h, w)).astype(np.int64)
+        m = image_ops.image_moments(torch.from_numpy(x.astype(np.float32)).cuda()).cpu().numpy()
+        p = x.reshape(3, -1)
+        want = [h * w, *p.sum(axis=1), (p[0] * p[0]).sum(), (p[0] * p[1]).sum(), (p[0] * p[2]).sum(), (p[1] * p[1]).sum(),
+                (p[1] * p[2]).sum(), (p[2] * p[2]).sum()]
+        assert np.array_equal(m, np.array(want, dtype=np.float64)), (h, w, m, want)
+
+
+@pytest.mark.parametrize("h,w", [(1024, 1024), (2048, 2048), (1448, 1086), (1023, 769)])
+def test_match_histogram_full_size_properties(h, w):
+    """BASELINE.json's sizes: the matched image takes the sources' channel means and (one source) covariance; matching
+    an image against itself is the identity; repeated launches are bit-identical (fixed-order reduction); the in-place
+    form and pre-computed source moments give the same bits."""
+    from maua_style_b200 import image_ops
+
+    g = torch.Generator().manual_seed(h + w)
+    low = torch.rand(1, 3, h // 8, w // 8, generator=g)
+    t = (torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False) * 255 - 110).cuda()
+    s = (torch.rand(1, 3, 700, 900, generator=g) * torch.tensor([200.0, 120.0, 60.0]).view(1, 3, 1, 1) - 90).cuda()
+    y = image_ops.match_histogram(t, [s], mode=True)
+    assert torch.equal(y, image_ops.match_histogram(t, [s], mode="avg"))
+    sm = image_ops.image_moments(s).view(1, 10)
+    y2 = image_ops.match_histogram(t.clone(), None, mode=True, source_moments=sm)
+    assert torch.equal(y, y2)
+    tc = t.clone()
+    assert torch.equal(image_ops.match_histogram(tc, [s], mode=True, out=tc), y)
+    my, ms = image_ops.image_moments(y).cpu().numpy(), sm[0].cpu().numpy()
+    n = my[0]
+    mean_y, mean_s = my[1:4] / n, ms[1:4] / ms[0]
+    assert np.allclose(mean_y, mean_s, atol=2e-3), (mean_y, mean_s)
+    var_y = my[[4, 7, 9]] / n - mean_y ** 2
+    var_s = ms[[4, 7, 9]] / ms[0] - mean_s ** 2
+    assert np.allclose(var_y, var_s, rtol=1e-3), (var_y, var_s)
+    ident = image_ops.match_histogram(t, [t], mode=True)
+    assert float((ident - t).abs().max()) < 2e-3
+    assert image_ops.match_histogram(t, [s], mode=False) is t  # utils.py:97-98
+
+
+def test_img_img_driver_with_histogram_matching(tmp_path):
+    """style.py:24/:67/:71 with match_histograms on: every scale's result carries the style image's colour statistics."""
+    from maua_style_b200 import image_ops, style
+
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    args = make_args(ckpt, tmp_path, image_sizes=[64, 96], num_iters=[4, 3], init="content", style_scale=1.0, match_histograms=True)
+    content = O.synthetic_image(80, 112, seed=1, smooth=True).cuda()
+    sty = (O.synthetic_image(70, 90, seed=2, smooth=True) * 0.5 + 20).cuda()
+    outs = style.img_img_tensors(content, [sty], args)
+    ms = image_ops.image_moments(sty).cpu().numpy()
+    for o in outs:
+        mo = image_ops.image_moments(o).cpu().numpy()
+        assert np.allclose(mo[1:4] / mo[0], ms[1:4] / ms[0], atol=1e-2)
+        assert np.allclose(mo[[4, 7, 9]] / mo[0] - (mo[1:4] / mo[0]) ** 2, ms[[4, 7, 9]] / ms[0] - (ms[1:4] / ms[0]) ** 2, rtol=5e-3)

@@ -88,3 +88,47 @@ def test_img_img_driver_matches_reference_pngs(tmp_path):
         mse = float((diff.astype(np.float64) ** 2).mean())
         psnr = float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
         assert psnr > 45.0, (size, psnr, int(diff.max()))
+
+
+def hist_cases():
+    g = np.load(GOLDEN / "hist_match.npz", allow_pickle=False)
+    for name, thw, shws, mode, seed in json.loads(str(g["cases"])):
+        yield name, g[f"{name}_target"], [g[f"{name}_source{i}"] for i in range(len(shws))], g[f"{name}_out"]
+
+
+def check_hist_match(name, y, target, sources, ref):
+    """`y` against the output of the reference's utils.match_histogram: the reference transforms `target + 1e-3 * randn`
+    (utils.py:120), so the residual must be exactly that noise pushed through the colour map -- zero-mean with a
+    per-channel standard deviation of 1e-3 * |row of M| (averaged over the sources, each with its own draw)."""
+    eps = 1e-2 + 1e-6
+    mu_t, ct = I.channel_stats(target, eps)
+    qt_inv = np.linalg.inv(I._sym_sqrt(ct))
+    ms = [I._sym_sqrt(I.channel_stats(s, eps)[1]) @ qt_inv for s in sources]
+    sigma = 1e-3 * np.sqrt(sum(np.linalg.norm(m, axis=1) ** 2 for m in ms)) / len(ms)
+    d = (np.asarray(y, dtype=np.float64) - ref)[0]
+    n = d[0].size
+    for c in range(3):
+        rms = float(np.sqrt((d[c] ** 2).mean()))
+        assert 0.85 * sigma[c] < rms < 1.15 * sigma[c], (name, c, rms, sigma[c])
+        assert float(np.abs(d[c]).max()) < 5.5 * sigma[c], (name, c, float(np.abs(d[c]).max()), sigma[c])
+        assert abs(float(d[c].mean())) < 5 * sigma[c] / np.sqrt(n) + 2e-5, (name, c, float(d[c].mean()))
+
+
+def test_match_histogram_against_reference_outputs():
+    for name, target, sources, ref in hist_cases():
+        check_hist_match(name, I.match_histogram(target, sources), target, sources, ref)
+
+
+def test_match_histogram_properties():
+    """Size-independent properties: the matched image has the sources' mean and (single source) covariance up to eps;
+    matching an image to itself is the identity; two identical sources equal one."""
+    for name, target, sources, _ in hist_cases():
+        y = I.match_histogram(target, sources)
+        mu_y, c_y = I.channel_stats(y, 0.0)
+        mu_s = np.mean([I.channel_stats(s, 0.0)[0] for s in sources], axis=0)
+        assert np.allclose(mu_y, mu_s, atol=2e-4), (name, mu_y, mu_s)
+        if len(sources) == 1 and name != "flat_target":
+            c_s = I.channel_stats(sources[0], 0.0)[1]
+            assert np.allclose(c_y, c_s, rtol=2e-3, atol=0.05), (name, np.abs(c_y - c_s).max())
+        assert np.allclose(I.match_histogram(target, [target]), target, atol=2e-4)
+        assert np.allclose(I.match_histogram(target, [sources[0], sources[0]]), I.match_histogram(target, [sources[0]]), atol=1e-4)

@@ -10,7 +10,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
 
 echo "== pytest -m gpu (whole suite, one process, like the driver runs it) =="
-MAUA_TEST_REPORT=$OUT/plan_report.txt timeout -k 10 1500 python -m pytest tests -x -q -m gpu --timeout 600 -p no:cacheprovider -s > $OUT/pytest_gpu.log 2>&1
+MAUA_TEST_REPORT=$OUT/plan_report.txt timeout -k 10 700 python -m pytest tests -x -q -m gpu --timeout 300 -p no:cacheprovider -s > $OUT/pytest_gpu.log 2>&1
 echo "exit $?"; grep -E "passed|failed|FAILED|Error|PSNR|cache" $OUT/pytest_gpu.log | tail -25
 
 echo "== smoke =="
