@@ -1,0 +1,236 @@
+"""Parity at BASELINE.json's full sizes (1024x1024; configs[1] final scale and configs[2]), where the CPU oracle would
+take minutes per evaluation:
+
+  (1) against the oracle's arithmetic executed by torch on the device in full fp32 (cuDNN / cuBLAS TF32 switched off) --
+      the same `oracle.maua_oracle` code, fed CUDA tensors -- per-tap features, blended style targets, per-module losses
+      and the image gradient, with the tolerances of tests/test_plan_gpu.py;
+  (2) through size-independent properties of the path:
+        * self-target: targets captured from X, evaluated at X  =>  content / style losses and their gradients vanish
+          (F - T = 0 and G - A = 0 exactly, because every kernel on the path is deterministic);
+        * determinism: two evaluations are bit-identical (no float atomics anywhere on the path);
+        * linearity of the blended style target in the blend weights (loss.py:148-151);
+        * the stored Gram of a tap equals X X^T / (C N) of the stored tap feature to fp32 accumulation error;
+        * strength scaling: loss value ~ strength, gradient ~ strength^2 under ScaleGradients (loss.py:10-20, :153-157).
+"""
+import pytest
+import torch
+
+from helpers import O, make_args, rel, save_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+S = 1024
+FEATURE_TOL = {"relu1_1": 1e-3, "relu2_1": 1e-3, "relu3_1": 1e-3, "relu4_1": 2e-3, "relu4_2": 2e-3, "relu5_1": 2e-3}
+
+
+@pytest.fixture(scope="module")
+def ckpt(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ckpt_full")
+    path = d / "vgg19-random.pth"
+    params = save_checkpoint(path)
+    return path, d, params
+
+
+@pytest.fixture(autouse=True)
+def full_fp32_torch():
+    """The device-side checker must be real fp32: no TF32 in cuDNN convolutions or cuBLAS matmuls."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def inputs(style_hws):
+    content = O.synthetic_image(S, S, seed=1, smooth=True).cuda()
+    styles = [O.synthetic_image(h, w, seed=2 + i, smooth=(i % 2 == 1)).cuda() for i, (h, w) in enumerate(style_hws)]
+    init = (O.synthetic_image(S, S, seed=4) * 0.25).cuda()
+    return content, styles, init
+
+
+def ours(ckpt, **over):
+    from maua_style_b200 import models
+
+    path, d, _ = ckpt
+    args = make_args(path, d, temporal_weight=0.0, **over)
+    net, losses = models.load_model(args)
+    return args, net, losses
+
+
+def module_values(losses):
+    return [0.0 if isinstance(m.loss, int) else float(m.loss) for m in losses]
+
+
+@pytest.mark.parametrize("case", ["gram_1style_max", "cov_2styles_avg", "cov_2styles_max"])
+def test_full_size_feval_vs_fp32_torch_on_device(case, ckpt):
+    """configs[1] final scale (Gram, 1 style) and configs[2] (covariance, 2 blended styles of different aspect) at 1024^2."""
+    from maua_style_b200 import optim
+
+    cov = case.startswith("cov")
+    pooling = "avg" if case.endswith("avg") else "max"
+    style_hws = [(896, 1152), (1152, 896)] if cov else [(S, S)]
+    over = dict(use_covariance=cov, pooling=pooling)
+    if cov:
+        over["style_blend_weights"] = "3,1"
+    content, styles, init = inputs(style_hws)
+    args, net, losses = ours(ckpt, **over)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, styles, args)
+    for m in losses:
+        m.mode = "loss"
+
+    cfg = O.StyleConfig(content_weight=5.0, temporal_weight=0.0, use_covariance=cov, pooling=pooling,
+                        style_blend_weights=[3.0, 1.0] if cov else None)
+    params = [(w.cuda(), b.cuda()) for w, b in ckpt[2]]
+    onet = O.OracleNet(params, cfg)
+    O.set_content_targets(onet, content)
+    O.set_style_targets(onet, styles, cfg.blend(len(styles)))
+    for m in onet.losses:
+        m.mode = "loss"
+
+    for i, (m, om) in enumerate(zip(net.style_losses, onet.style_losses)):
+        err = rel(m.target, om.target)
+        print(f"{case} {S}^2 style_target[{i}] rel {err:.2e}")
+        assert err < 2e-3
+    assert rel(net.content_losses[0].target, onet.content_losses[0].target) < 2e-3
+
+    x = init.clone().requires_grad_(True)
+    net(x)
+    vals = module_values(losses)
+    total = sum(m.loss for m in losses if not isinstance(m.loss, int))
+    total.backward()
+    for m in losses:
+        m.loss = 0
+
+    taps = {}
+    with torch.no_grad():
+        onet(init.clone(), taps=taps)
+    for m in onet.losses:
+        m.loss = 0
+    for t, (ridx, _) in enumerate(net.taps):
+        nm = O.VGG19_RELU_NAMES[ridx]
+        err = rel(net.tap_feature(t), taps[nm])
+        print(f"{case} {S}^2 feature {nm} rel {err:.2e}")
+        assert err < FEATURE_TOL[nm], (nm, err)
+    del taps
+
+    _, ovals, ograd = O.feval(onet, init)
+    assert len(vals) == len(ovals)
+    for m, v, o in zip(losses, vals, ovals):
+        print(f"{case} {S}^2 loss {m.name}: ours {v:.6e} fp32 {o:.6e} rel {abs(v / o - 1):.2e}")
+        assert abs(v / o - 1) < 1e-2, (m.name, v, o)
+    gerr = rel(x.grad, ograd)
+    print(f"{case} {S}^2 image-gradient rel {gerr:.2e}")
+    assert gerr < (3e-3 if pooling == "avg" else 4e-2)
+
+
+def test_self_target_losses_and_gradient_vanish(ckpt):
+    from maua_style_b200 import optim
+
+    content, styles, init = inputs([(S, S)])
+    args, net, losses = ours(ckpt, tv_weight=0.0)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, [content], args)
+    for m in losses:
+        m.mode = "loss"
+    vec0, g0 = optim.feval(net, init.clone())  # scale of the quantities at an unrelated image
+    vec0, g0 = vec0.clone(), g0.clone()
+    vec, g = optim.feval(net, content.clone())
+    live = net._live_slots()
+    assert len(live) == 6
+    for i in live:
+        assert float(vec0[i]) > 0
+        assert abs(float(vec[i])) <= 1e-10 * float(vec0[i]), (i, float(vec[i]), float(vec0[i]))
+    assert float(g.abs().max()) <= 1e-7 * float(g0.abs().max())
+
+
+def test_full_size_iteration_is_bit_deterministic(ckpt):
+    from maua_style_b200 import optim
+
+    content, styles, init = inputs([(S, S)])
+    args, net, losses = ours(ckpt)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, styles, args)
+    for m in losses:
+        m.mode = "loss"
+    outs = []
+    for _ in range(2):
+        vec, g = optim.feval(net, init.clone())
+        outs.append((vec.clone(), g.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    # and so are the pixel updates: two L-BFGS runs of 12 iterations from the same start end in the same image
+    res = []
+    for _ in range(2):
+        a2, n2, l2 = ours(ckpt, optimizer="lbfgs")
+        res.append(optim.optimize_device(content, styles, init.clone(), 12, a2, n2, l2).clone())
+        del n2, l2
+    assert torch.equal(res[0], res[1])
+    assert torch.isfinite(res[0]).all()
+
+
+def test_blended_target_is_linear_in_the_blend_weights(ckpt):
+    from maua_style_b200 import optim
+
+    _, styles, _ = inputs([(896, 1152), (1152, 896)])
+    singles = []
+    for s in styles:
+        args, net, losses = ours(ckpt, use_covariance=True)
+        optim.set_style_targets(net, [s], args)
+        singles.append([m.target.clone() for m in net.style_losses])
+        del net, losses
+    args, net, losses = ours(ckpt, use_covariance=True, style_blend_weights="3,1")
+    optim.set_style_targets(net, styles, args)
+    for i, m in enumerate(net.style_losses):
+        want = 0.75 * singles[0][i] + 0.25 * singles[1][i]
+        err = rel(m.target, want)
+        print(f"blend linearity style[{i}] rel {err:.2e}")
+        assert err < 1e-5
+
+
+@pytest.mark.parametrize("cov", [False, True])
+def test_stored_gram_matches_fp32_product_of_stored_feature(cov, ckpt):
+    """The SYRK works on the stored (TF32-rounded) tap features, so against X X^T of exactly those features only fp32
+    accumulation (order, and the tensor core's truncating adds) separates it from an fp64 product -- N = 1,048,576 pixels
+    at relu1_1.  Covariance subtracts P mu mu^T from the raw sums, which amplifies that error by the cancellation."""
+    from maua_style_b200 import optim
+
+    _, styles, _ = inputs([(S, S)])
+    args, net, losses = ours(ckpt, use_covariance=cov)
+    optim.set_style_targets(net, styles, args)  # capture forward: targets = Gram of the style image
+    k = 0
+    for t, (ridx, mod) in enumerate(net.taps):
+        if mod not in net.style_losses:
+            continue
+        f = net.tap_feature(t)[0]
+        c = f.shape[0]
+        x = f.reshape(c, -1).double()
+        if cov:
+            x = x - x.mean(1, keepdim=True)
+        want = (x @ x.t()) / f.numel()
+        err = rel(mod.target, want)
+        print(f"stored Gram (cov={cov}) {O.VGG19_RELU_NAMES[ridx]} rel {err:.2e}")
+        assert err < (5e-4 if cov else 2e-4)
+        k += 1
+    assert k == 5
+
+
+def test_strength_scaling_of_loss_and_gradient(ckpt):
+    """loss.py:153-157 with ScaleGradients (loss.py:10-20): value ~ strength, gradient ~ strength^2."""
+    from maua_style_b200 import optim
+
+    content, styles, init = inputs([(S, S)])
+    res = []
+    for sw in (100.0, 200.0):
+        args, net, losses = ours(ckpt, tv_weight=0.0, content_weight=0.0, style_weight=sw)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, styles, args)
+        for m in losses:
+            m.mode = "loss"
+        vec, g = optim.feval(net, init.clone())
+        res.append((vec.clone(), g.clone()))
+        del net, losses
+    style_slots = [i for i in range(6) if i != 4]  # taps in relu order: relu1_1 .. relu4_1, relu4_2 (content), relu5_1
+    for i in style_slots:
+        assert abs(float(res[1][0][i]) / float(res[0][0][i]) - 2.0) < 1e-5
+    assert rel(res[1][1], 4.0 * res[0][1]) < 1e-5
