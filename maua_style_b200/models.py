@@ -55,17 +55,32 @@ vgg19_dict = _layer_names(channel_list["VGG-19"])
 _MODES = {"none": _lib.MODE_NONE, "capture": _lib.MODE_CAPTURE, "loss": _lib.MODE_LOSS}
 
 
-def _architecture(model_file: str, pooling: str):
-    """models.py:246-347 for the architectures this backend accelerates: (channels, layer names) from the file name."""
-    name = str(model_file).lower()
+def _match_architecture(name: str):
+    if "prun" in name:  # models.py:249-258: channel list "VGG-16p" (24, 22, 41, 51, 108, ...)
+        return "VGG-16p"
     if "vgg19" in name or "vgg-19" in name:
-        channels, layer_list = channel_list["VGG-19"], vgg19_dict
-    elif "vgg16" in name or "vgg-16" in name:
-        channels, layer_list = channel_list["VGG-16"], vgg16_dict
-    else:
+        return "VGG-19"
+    # models.py:259-288, :334-347: the fcn32s / nyud / sod checkpoints are VGG-16 feature stacks with other heads
+    if any(k in name for k in ("vgg16", "vgg-16", "fcn32s", "nyud", "sod")):
+        return "VGG-16"
+    return None
+
+
+def _architecture(model_file: str, pooling: str):
+    """models.py:246-347 for the architectures this backend accelerates: (channels, layer names) from the file name (the
+    reference matches substrings of the whole path; the file name is tried first here so that a directory called
+    e.g. "episode" does not select the SOD model)."""
+    full = str(model_file).lower()
+    arch = _match_architecture(os.path.basename(full)) or _match_architecture(full)
+    if arch == "VGG-16p":
+        raise ValueError(
+            f"maua_style_b200: the channel-pruned VGG-16 ({model_file!r}) has channel counts that are not multiples of 32, "
+            "which the tcgen05 conv kernels require; use the reference's torch modules for it")
+    if arch is None:
         raise ValueError(
             f"maua_style_b200 accelerates the VGG-19 / VGG-16 feature stacks only (model_file={model_file!r}); "
             "use the reference's torch modules for other model families")
+    channels, layer_list = channel_list[arch], (vgg19_dict if arch == "VGG-19" else vgg16_dict)
     if pooling not in ("max", "avg"):
         raise ValueError("Unrecognized pooling argseter")  # models.py:124
     return channels, layer_list

@@ -41,6 +41,22 @@ VGG19_CHANNELS = [64, 64, "P", 128, 128, "P", 256, 256, 256, 256, "P", 512, 512,
 # models.py:205-243 (names of the ReLU layers, in order)
 VGG19_RELU_NAMES = ["relu1_1", "relu1_2", "relu2_1", "relu2_2", "relu3_1", "relu3_2", "relu3_3", "relu3_4",
                     "relu4_1", "relu4_2", "relu4_3", "relu4_4", "relu5_1", "relu5_2", "relu5_3", "relu5_4"]
+# models.py:137 and :140-203 (VGG-16: three convs in blocks 3-5)
+VGG16_CHANNELS = [64, 64, "P", 128, 128, "P", 256, 256, 256, "P", 512, 512, 512, "P", 512, 512, 512, "P"]
+
+
+def relu_names(channels) -> List[str]:
+    """models.py:140-243 (vgg16_dict / vgg19_dict "R" lists): relu{block}_{index} in network order."""
+    names, block, idx = [], 1, 1
+    for c in channels:
+        if c == "P":
+            block, idx = block + 1, 1
+        else:
+            names.append(f"relu{block}_{idx}")
+            idx += 1
+    return names
+
+
 # load.py:30 -- BGR channel means subtracted from the 0-255 image
 BGR_MEAN = (103.939, 116.779, 123.68)
 
@@ -211,9 +227,11 @@ class OracleNet:
     """models.py:351-453: TVLoss, temporal ContentLoss, then conv/relu/pool with loss modules spliced after the
     named ReLUs; the stack stops after the last requested tap (models.py:382)."""
 
-    def __init__(self, params, cfg: StyleConfig):
+    def __init__(self, params, cfg: StyleConfig, channels=VGG19_CHANNELS):
         self.cfg = cfg
         self.params = params
+        self.channels = channels
+        self.relu_names = relu_names(channels)
         content_layers = cfg.content_layers.split(",")
         style_layers = cfg.style_layers.split(",")
         self.tv_losses, self.temporal_losses, self.content_losses, self.style_losses = [], [], [], []
@@ -225,7 +243,7 @@ class OracleNet:
             m = LossModule("temporal", cfg.temporal_weight, name=f"temporal {len(self.seq)}", normalize=cfg.normalize_gradients)
             self.seq.append(("loss", m)); self.temporal_losses.append(m)
         next_c, next_s, conv_i, relu_i = 1, 1, 0, 0
-        for c in VGG19_CHANNELS:
+        for c in channels:
             if not (next_c <= len(content_layers) or next_s <= len(style_layers)):
                 break
             if c == "P":
@@ -233,7 +251,7 @@ class OracleNet:
                 continue
             self.seq.append(("conv", conv_i)); conv_i += 1
             self.seq.append(("relu", None))
-            name = VGG19_RELU_NAMES[relu_i]; relu_i += 1
+            name = self.relu_names[relu_i]; relu_i += 1
             if name in content_layers:
                 m = LossModule("content", cfg.content_weight, name=f"cont {len(self.seq)}", normalize=cfg.normalize_gradients)
                 self.seq.append(("loss", m)); self.content_losses.append(m); next_c += 1
@@ -252,7 +270,7 @@ class OracleNet:
             elif kind == "relu":
                 x = F.relu(x)
                 if taps is not None:
-                    taps[VGG19_RELU_NAMES[relu_i]] = x
+                    taps[self.relu_names[relu_i]] = x
                 relu_i += 1
             elif kind == "pool":
                 x = F.max_pool2d(x, 2, 2) if self.cfg.pooling == "max" else F.avg_pool2d(x, 2, 2)
@@ -369,10 +387,10 @@ def lbfgs_optimize(p: torch.Tensor, closure: Callable, max_iter: int, lr: float 
     return p
 
 
-def optimize(content, styles, init, num_iters, cfg: StyleConfig, params, temporal=None):
+def optimize(content, styles, init, num_iters, cfg: StyleConfig, params, temporal=None, channels=VGG19_CHANNELS):
     """optim.py:111-255 for transfer_type img_img (one window): capture targets, then Adam (num_iters + 1 steps,
     the reference's off-by-one at :240) or one L-BFGS step() of num_iters iterations."""
-    net = OracleNet(params, cfg)
+    net = OracleNet(params, cfg, channels)
     set_content_targets(net, content)
     if temporal is not None:
         set_temporal_targets(net, *temporal)

@@ -63,12 +63,13 @@ def reference_args(rconfig, workdir: Path, ckpt: Path, **over):
     return args
 
 
-def save_checkpoint(rmodels, path: Path, seed: int = 0):
-    params = O.he_init_vgg19(seed)
-    seq = rmodels.build_sequential(rmodels.channel_list["VGG-19"], "max")
+def save_checkpoint(rmodels, path: Path, seed: int = 0, arch: str = "VGG-19"):
+    channels = O.VGG19_CHANNELS if arch == "VGG-19" else O.VGG16_CHANNELS
+    params = O.he_init_vgg19(seed, channels)
+    seq = rmodels.build_sequential(rmodels.channel_list[arch], "max")
     sd = seq.state_dict()
     keys = [k for k in sd if k.endswith(".weight")]
-    assert len(keys) == 16
+    assert len(keys) == len(params)
     # only the 13 convs up to conv5_1 matter (the net is truncated at relu5_1); the rest keep their default init
     for (w, b), k in zip(params, keys):
         sd[k] = w.clone()
@@ -84,7 +85,7 @@ def sample(t: torch.Tensor, n: int = 512) -> np.ndarray:
     return flat[idx].numpy().astype(np.float32)
 
 
-def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iters, **over):
+def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iters, relu_names=None, meta_extra=None, **over):
     torch.manual_seed(0)
     torch.set_flush_denormal(True)
     n_styles = len(style_hw)
@@ -93,8 +94,9 @@ def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iter
     styles = [O.synthetic_image(sh, sw, seed=2 + i, smooth=(i % 2 == 1)) for i, (sh, sw) in enumerate(style_hw)]
     init = O.synthetic_image(h, w, seed=4) * 0.25
 
+    relu_names = relu_names or O.VGG19_RELU_NAMES
     out = {"meta": json.dumps(dict(name=name, h=h, w=w, style_hw=style_hw, iters=iters, over=over,
-                                   blend=[float(x) for x in args.style_blend_weights]))}
+                                   blend=[float(x) for x in args.style_blend_weights], **(meta_extra or {})))}
     # --- one feval: per-module losses, targets, image gradient -------------------------------------------
     net, losses = rmodels.load_model(args)
     roptim.set_content_targets(net, content, args)
@@ -107,7 +109,7 @@ def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iter
     import torch.nn as nn
     for mod in net:
         if isinstance(mod, nn.ReLU):
-            nm = O.VGG19_RELU_NAMES[relu_i]
+            nm = relu_names[relu_i]
             relu_i += 1
             hooks.append(mod.register_forward_hook(lambda m, i, o, nm=nm: taps.__setitem__(nm, o.detach().clone())))
     x = init.clone().requires_grad_(True)

@@ -1,0 +1,42 @@
+"""Golden vectors for the architecture / layer-list variants of the hot path, produced by the UNMODIFIED reference on the
+CPU (same recipe as make_golden.py, whose helpers this script re-uses):
+
+    python tests/golden/make_golden_arch.py
+
+  vgg16_adam_gram_72x88 ........ `--model_file *vgg16*` (models.py:334-347: VGG-16 channel list, vgg16_dict names), default
+                                 layers, 3 Adam iterations
+  vgg19_taps_lbfgs_80x64 ....... VGG-19 with `--style_layers relu1_2,relu3_3 --content_layers relu2_2`: taps that sit
+                                 directly before a pool, truncation after relu3_3 (models.py:382), 4 L-BFGS iterations
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+import make_golden as mg  # noqa: E402
+
+O = mg.O
+
+
+def main():
+    rconfig, rloss, rmodels, roptim = mg.import_reference()
+    with tempfile.TemporaryDirectory() as td:
+        workdir = Path(td)
+        os.chdir(workdir)
+        ckpt16 = workdir / "vgg16-random.pth"
+        mg.save_checkpoint(rmodels, ckpt16, arch="VGG-16")
+        common = dict(rconfig=rconfig, rmodels=rmodels, roptim=roptim, workdir=workdir)
+        mg.run_case("vgg16_adam_gram_72x88", ckpt=ckpt16, h=72, w=88, style_hw=[(64, 96)], iters=3,
+                    relu_names=O.relu_names(O.VGG16_CHANNELS), meta_extra={"arch": "VGG-16"}, **common)
+        ckpt19 = workdir / "vgg19-random.pth"
+        mg.save_checkpoint(rmodels, ckpt19)
+        mg.run_case("vgg19_taps_lbfgs_80x64", ckpt=ckpt19, h=80, w=64, style_hw=[(72, 72)], iters=4, optimizer="lbfgs",
+                    style_layers="relu1_2,relu3_3", content_layers="relu2_2", meta_extra={"arch": "VGG-19"}, **common)
+
+
+if __name__ == "__main__":
+    main()

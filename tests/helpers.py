@@ -42,11 +42,11 @@ def make_args(ckpt_path, tmpdir, **over):
     return a
 
 
-def save_checkpoint(path, seed=0):
-    """torchvision-style state dict (features.N.weight / bias) with the seeded He-normal VGG-19 weights."""
-    params = O.he_init_vgg19(seed)
+def save_checkpoint(path, seed=0, channels=O.VGG19_CHANNELS):
+    """torchvision-style state dict (features.N.weight / bias) with the seeded He-normal VGG-19 (or VGG-16) weights."""
+    params = O.he_init_vgg19(seed, channels)
     sd, k, ci = {}, 0, 0
-    for c in O.VGG19_CHANNELS:
+    for c in channels:
         if c == "P":
             k += 1
             continue

@@ -1,0 +1,98 @@
+"""Host-side logic of the reference-shaped modules that needs no GPU: architecture selection from the checkpoint name,
+layer-name tables, per-size scaling args, the multi-resolution schedule and the bench line of the reference arm."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+from maua_style_b200 import models, optim
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_vgg16_family_names_and_pruned_model_is_rejected():
+    """models.py:246-347: fcn32s / sod / nyud checkpoints are VGG-16 stacks; the channel-pruned VGG-16 has channel counts
+    that are not multiples of 32 and is refused loudly instead of silently computing something else."""
+    for nm in ("vgg16-sod.pth", "fcn32s-heavy-pascal.pth", "modelzoo/nyud-fcn32s-color-heavy.pth", "vgg16-00b39a1b.pth"):
+        ch, names = models._architecture(nm, "max")
+        assert ch == models.channel_list["VGG-16"] and names["R"][7] == "relu4_1"
+    assert models._architecture("modelzoo/vgg19-d01eb7cb.pth", "avg")[0] == models.channel_list["VGG-19"]
+    assert models._architecture("/tmp/episode-3/vgg19-random.pth", "max")[0] == models.channel_list["VGG-19"]
+    for bad in ("modelzoo/vgg16-prune.pth", "modelzoo/nin.pth", "resnet50.pth"):
+        with pytest.raises(ValueError):
+            models._architecture(bad, "max")
+    with pytest.raises(ValueError):
+        models._architecture("vgg19.pth", "median")  # models.py:124
+
+
+def test_layer_name_tables_match_the_reference_dicts():
+    """models.py:140-243: 13 / 16 convs, names conv{b}_{i} / relu{b}_{i} / pool{b}."""
+    assert len(models.vgg16_dict["C"]) == 13 and len(models.vgg19_dict["C"]) == 16
+    assert models.vgg19_dict["R"][:3] == ["relu1_1", "relu1_2", "relu2_1"] and models.vgg19_dict["R"][-1] == "relu5_4"
+    assert models.vgg16_dict["R"][-1] == "relu5_3" and models.vgg16_dict["P"] == [f"pool{i}" for i in range(1, 6)]
+    assert models.vgg19_dict["C"][8] == "conv4_1" and models.vgg16_dict["C"][7] == "conv4_1"
+
+
+def test_set_model_args_picks_the_first_size_that_fits(tmp_path):
+    """optim.py:93-108: first entry with size >= current size whose gpu list is not longer than the user's."""
+    import argparse
+
+    scaling = {"512": {"model_file": "a-vgg19.pth", "optimizer": "lbfgs", "gpu": "0"},
+               "1024": {"model_file": "b-vgg19.pth", "optimizer": "adam", "gpu": "0"},
+               "4096": {"model_file": "c-vgg19.pth", "optimizer": "adam", "gpu": "0,1", "multidevice": True}}
+    f = tmp_path / "scaling.json"
+    f.write_text(json.dumps(scaling))
+    a = argparse.Namespace(scaling_args=str(f), gpu="0")
+    optim.set_model_args(a, 256)
+    assert a.model_file == "a-vgg19.pth" and a.optimizer == "lbfgs"
+    optim.set_model_args(a, 513)
+    assert a.model_file == "b-vgg19.pth" and a.optimizer == "adam"
+    a = argparse.Namespace(scaling_args=str(f), gpu="0,1")
+    optim.set_model_args(a, 2048)
+    assert a.model_file == "c-vgg19.pth" and a.multidevice is True
+    # one gpu only: the two-gpu entry is skipped, nothing fits -> the reference warns and applies the last entry read
+    a = argparse.Namespace(scaling_args=str(f), gpu="0")
+    optim.set_model_args(a, 2048)
+    assert a.model_file == "c-vgg19.pth"
+
+
+def test_scale_schedule_matches_the_reference_arithmetic():
+    """style.py:36-50: content scaled so that its longer side is `size`; styles area-matched to the scaled content."""
+    import math
+
+    from maua_style_b200 import style
+
+    sched = style.scale_schedule((600, 800), [(512, 512), (300, 900)], [256, 512], style_scale=1.0)
+    assert [s["size"] for s in sched] == [256, 512]
+    s0 = sched[0]
+    assert s0["content_scale"] == 256 / 800 and s0["content_hw"] == (int(math.floor(600 * 256 / 800)), 256)
+    area = s0["content_hw"][0] * s0["content_hw"][1]
+    for (sh, sw), (ss, (oh, ow)) in zip([(512, 512), (300, 900)], s0["styles"]):
+        assert ss == math.sqrt(area / (sw * sh))
+        assert (oh, ow) == (int(math.floor(sh * ss)), int(math.floor(sw * ss)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores): one JSON line with the contract's keys."""
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--size", "64", "--steps", "1",
+                          "--warmup", "0", "--optimizer", "adam"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    import os
+
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "64",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -1,0 +1,102 @@
+"""Architecture / layer-list variants of the hot path, against golden vectors produced by
+the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
+
+  vgg16_adam_gram_72x88 ...... `--model_file *vgg16*`: the VGG-16 channel list and layer names (models.py:137, :140-203)
+  vgg19_taps_lbfgs_80x64 ..... style taps relu1_2 / relu3_3 and content tap relu2_2: loss modules directly in front of a
+                               pool (their gradient joins the un-pooled gradient) and truncation after relu3_3
+
+(The file sorts last on purpose: it was written after the round's GPU budget was spent, so under `pytest -x` a surprise
+here cannot hide the results of the suites that were verified on the B200.)
+"""
+import pytest
+import torch
+
+from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["vgg16_adam_gram_72x88", "vgg19_taps_lbfgs_80x64"]
+
+
+def setup_case(name, tmp_path):
+    from maua_style_b200 import models
+
+    z, meta = load_golden(name)
+    vgg16 = meta.get("arch") == "VGG-16"
+    channels = O.VGG16_CHANNELS if vgg16 else O.VGG19_CHANNELS
+    path = tmp_path / ("vgg16-random.pth" if vgg16 else "vgg19-random.pth")
+    params = save_checkpoint(path, channels=channels)
+    over = dict(meta["over"])
+    args = make_args(path, tmp_path, **over)
+    net, losses = models.load_model(args)
+    cfg = O.StyleConfig(content_weight=5.0)
+    cfg.optimizer = over.pop("optimizer", "adam")
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return z, meta, args, net, losses, params, cfg, channels
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_variant_feval_matches_reference_golden_and_oracle(name, tmp_path):
+    from maua_style_b200 import optim
+
+    z, meta, args, net, losses, params, cfg, channels = setup_case(name, tmp_path)
+    content, styles, init = golden_inputs(meta)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, styles, args)
+    for m in losses:
+        m.mode = "loss"
+    onet = O.OracleNet(params, cfg, channels)
+    O.set_content_targets(onet, content)
+    O.set_style_targets(onet, styles, cfg.blend(len(styles)))
+    for m in onet.losses:
+        m.mode = "loss"
+    assert len(net.style_losses) == len(onet.style_losses) and len(net.content_losses) == len(onet.content_losses)
+    for i, (m, om) in enumerate(zip(net.style_losses, onet.style_losses)):
+        err = rel(m.target, om.target)
+        print(f"{name} style_target[{i}] rel {err:.2e}")
+        assert err < 2e-3
+        assert rel(m.target[:16, :16], torch.from_numpy(z[f"style_target_{i}_block"])) < 5e-3
+
+    x = init.clone().cuda().requires_grad_(True)
+    net(x)
+    vals = [0.0 if isinstance(m.loss, int) else float(m.loss) for m in losses]
+    total = sum(m.loss for m in losses if not isinstance(m.loss, int))
+    total.backward()
+    for m in losses:
+        m.loss = 0
+
+    taps = {}
+    onet(init.clone(), taps=taps)
+    for m in onet.losses:
+        m.loss = 0
+    names = O.relu_names(channels)
+    for t, (ridx, _) in enumerate(net.taps):
+        err = rel(net.tap_feature(t), taps[names[ridx]])
+        print(f"{name} feature {names[ridx]} rel {err:.2e}")
+        assert err < 2e-3, (names[ridx], err)
+
+    keys = sorted([k for k in z.files if k.startswith("loss_")], key=lambda k: int(k.split("_")[1]))
+    assert len(keys) == len(vals)
+    for k, v in zip(keys, vals):
+        ref = float(z[k])
+        if ref == 0.0:
+            assert v == 0.0
+            continue
+        print(f"{name} {k} got {v:.6e} ref {ref:.6e} rel {abs(v / ref - 1):.2e}")
+        assert abs(v / ref - 1) < 1e-2, (k, v, ref)
+    gerr = rel(x.grad, torch.from_numpy(z["grad"]))
+    print(f"{name} image-gradient rel {gerr:.2e}")
+    assert gerr < 4e-2
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_variant_optimize_matches_reference_golden(name, tmp_path):
+    from maua_style_b200 import optim
+
+    z, meta, args, net, losses, _, _, _ = setup_case(name, tmp_path)
+    content, styles, init = golden_inputs(meta)
+    out = optim.optimize(content, styles, init.clone(), meta["iters"], args, net, losses)
+    p = O.psnr(out, torch.from_numpy(z["optimized"]))
+    print(f"{name} optimize {meta['iters']} iters PSNR {p:.1f} dB")
+    assert p > 40.0
