@@ -85,7 +85,15 @@ def sample(t: torch.Tensor, n: int = 512) -> np.ndarray:
     return flat[idx].numpy().astype(np.float32)
 
 
-def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iters, relu_names=None, meta_extra=None, **over):
+def temporal_inputs(h, w):
+    """Stand-ins for the warped previous frame and the flow-reliability map of vid_img (style.py:279-288)."""
+    warp = O.synthetic_image(h, w, seed=9, smooth=True)
+    weights = torch.rand(1, 1, h, w, generator=torch.Generator().manual_seed(3))
+    return warp, weights
+
+
+def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iters, relu_names=None, meta_extra=None,
+             temporal=False, **over):
     torch.manual_seed(0)
     torch.set_flush_denormal(True)
     n_styles = len(style_hw)
@@ -99,6 +107,8 @@ def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iter
                                    blend=[float(x) for x in args.style_blend_weights], **(meta_extra or {})))}
     # --- one feval: per-module losses, targets, image gradient -------------------------------------------
     net, losses = rmodels.load_model(args)
+    if temporal:  # style.py:288 (vid_img): the temporal target is captured before optimize() is called with net / losses
+        roptim.set_temporal_targets(net, *temporal_inputs(h, w), args=args)
     roptim.set_content_targets(net, content, args)
     roptim.set_style_targets(net, styles, args)
     for m in losses:
@@ -136,7 +146,12 @@ def run_case(name, rconfig, rmodels, roptim, workdir, ckpt, h, w, style_hw, iter
     for m in losses:
         m.loss = 0
     # --- N iterations through optim.optimize (fresh model, as style.py:69 does) --------------------------
-    if iters > 0:
+    if iters > 0 and temporal:  # style.py:176-177, :288-294: load_model once, temporal target, optimize(..., net, losses)
+        net2, losses2 = rmodels.load_model(args)
+        roptim.set_temporal_targets(net2, *temporal_inputs(h, w), args=args)
+        res = roptim.optimize(content, styles, init.clone(), iters, args, net2, losses2)
+        out["optimized"] = res.detach().numpy().astype(np.float32)
+    elif iters > 0:
         res = roptim.optimize(content, styles, init.clone(), iters, args)
         out["optimized"] = res.detach().numpy().astype(np.float32)
     np.savez_compressed(HERE / f"{name}.npz", **out)

@@ -5,6 +5,8 @@ CPU (same recipe as make_golden.py, whose helpers this script re-uses):
 
   vgg16_adam_gram_72x88 ........ `--model_file *vgg16*` (models.py:334-347: VGG-16 channel list, vgg16_dict names), default
                                  layers, 3 Adam iterations
+  vid_frame_temporal_64x80 ..... one vid_img frame (style.py:276-294): temporal target + flow-reliability weights captured
+                                 with optim.set_temporal_targets, then optimize(content, styles, init, n, args, net, losses)
   vgg19_taps_lbfgs_80x64 ....... VGG-19 with `--style_layers relu1_2,relu3_3 --content_layers relu2_2`: taps that sit
                                  directly before a pool, truncation after relu3_3 (models.py:382), 4 L-BFGS iterations
 """
@@ -34,6 +36,8 @@ def main():
                     relu_names=O.relu_names(O.VGG16_CHANNELS), meta_extra={"arch": "VGG-16"}, **common)
         ckpt19 = workdir / "vgg19-random.pth"
         mg.save_checkpoint(rmodels, ckpt19)
+        mg.run_case("vid_frame_temporal_64x80", ckpt=ckpt19, h=64, w=80, style_hw=[(72, 72)], iters=4, temporal=True,
+                    meta_extra={"arch": "VGG-19", "temporal": True}, **common)
         mg.run_case("vgg19_taps_lbfgs_80x64", ckpt=ckpt19, h=80, w=64, style_hw=[(72, 72)], iters=4, optimizer="lbfgs",
                     style_layers="relu1_2,relu3_3", content_layers="relu2_2", meta_extra={"arch": "VGG-19"}, **common)
 

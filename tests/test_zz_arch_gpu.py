@@ -2,6 +2,9 @@
 the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
 
   vgg16_adam_gram_72x88 ...... `--model_file *vgg16*`: the VGG-16 channel list and layer names (models.py:137, :140-203)
+  vid_frame_temporal_64x80 ... one vid_img frame (style.py:276-294): optim.set_temporal_targets with a flow-reliability map,
+                               then optimize(content, styles, init, n, args, net, losses) -- the weighted temporal
+                               ContentLoss on the image (loss.py:46-54) pinned to the reference's own numbers
   vgg19_taps_lbfgs_80x64 ..... style taps relu1_2 / relu3_3 and content tap relu2_2: loss modules directly in front of a
                                pool (their gradient joins the un-pooled gradient) and truncation after relu3_3
 
@@ -15,7 +18,16 @@ from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoi
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["vgg16_adam_gram_72x88", "vgg19_taps_lbfgs_80x64"]
+CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64"]
+
+
+def temporal_inputs(meta):
+    """make_golden.temporal_inputs: stand-ins for the warped previous frame and the flow-reliability map."""
+    if not meta.get("temporal"):
+        return None
+    warp = O.synthetic_image(meta["h"], meta["w"], seed=9, smooth=True)
+    weights = torch.rand(1, 1, meta["h"], meta["w"], generator=torch.Generator().manual_seed(3))
+    return warp, weights
 
 
 def setup_case(name, tmp_path):
@@ -42,11 +54,16 @@ def test_variant_feval_matches_reference_golden_and_oracle(name, tmp_path):
 
     z, meta, args, net, losses, params, cfg, channels = setup_case(name, tmp_path)
     content, styles, init = golden_inputs(meta)
+    temporal = temporal_inputs(meta)
+    if temporal:
+        optim.set_temporal_targets(net, temporal[0], temporal[1], args)
     optim.set_content_targets(net, content, args)
     optim.set_style_targets(net, styles, args)
     for m in losses:
         m.mode = "loss"
     onet = O.OracleNet(params, cfg, channels)
+    if temporal:
+        O.set_temporal_targets(onet, *temporal)
     O.set_content_targets(onet, content)
     O.set_style_targets(onet, styles, cfg.blend(len(styles)))
     for m in onet.losses:
@@ -96,6 +113,9 @@ def test_variant_optimize_matches_reference_golden(name, tmp_path):
 
     z, meta, args, net, losses, _, _, _ = setup_case(name, tmp_path)
     content, styles, init = golden_inputs(meta)
+    temporal = temporal_inputs(meta)
+    if temporal:
+        optim.set_temporal_targets(net, temporal[0], temporal[1], args)
     out = optim.optimize(content, styles, init.clone(), meta["iters"], args, net, losses)
     p = O.psnr(out, torch.from_numpy(z["optimized"]))
     print(f"{name} optimize {meta['iters']} iters PSNR {p:.1f} dB")
