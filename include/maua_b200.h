@@ -311,6 +311,10 @@ MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, float* dst, int* 
                                    maua_stream_t stream);
 /* Switch the GEMM-shaped kernels of this plan between MAUA_IMPL_TC and MAUA_IMPL_REF (tests only). */
 MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
+/* Fused pooling: when enabled, MaxPool2d / AvgPool2d(2,2) (models.py:119-122) is computed in the epilogue of the
+ * convolution that produces its input instead of a separate pass over the activation (same arithmetic, bit for bit).
+ * Off by default in this release (also switched on by MAUA_FUSE_POOL=1 in the environment at plan creation). */
+MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* plan, int enable);
 /* Per-launch timing for roofline reports: when enabled, a CUDA event is recorded on the caller's stream after every
  * launch of forward / backward.  maua_plan_profile_json synchronises the stream and writes a JSON array
  * [{"name","layer","ms","flops","bytes"}...] (algorithmic FLOPs / bytes per launch) for the last forward + backward

@@ -25,6 +25,7 @@
 // Warp roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused epilogue -> global).
 #include "conv_tc.cuh"
+#include "pointwise.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -85,7 +86,7 @@ struct ConvCfg {
 // (this CTA the ones at rows h0 + rank*MT*8 ...), every MMA is M = 256 across both CTAs, and each CTA loads its own
 // activation boxes but only HALF of every weight tile.  All TMA loads complete on the even CTA's barriers (its producer
 // arms them for both CTAs' bytes), the even CTA's MMA warp issues for the pair and its commits arrive in both CTAs.
-template <int BN, int MT, int CG>
+template <int BN, int MT, int CG, bool POOL = false>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -323,6 +324,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
                             ep.mask_out[pix * words + ((n0 + c) >> 5)] = bits;
                         }
+                        if (POOL) {
+                            // (compiled into the POOL = true instantiations only: the default kernels are unchanged)
+                            // 2x2 window = lanes {l, l^1, l^16, l^17}: w and w+1 are neighbouring lanes, h and h+1 are the
+                            // two half-warps (this warp holds tile rows 2q and 2q+1).  Every lane takes part in the
+                            // shuffles; the lane of the window's top-left pixel stores the pooled pixel (32 channels =
+                            // one 128-byte line).  Windows that hang over the image edge are dropped (floor semantics).
+                            const bool writer = (lane & 17) == 0;
+                            const int PH = p.H >> 1, PW = p.W >> 1;
+                            const int ph = h >> 1, pw = w >> 1;
+                            const bool pvalid = writer && ph < PH && pw < PW;
+                            float* pdst = ep.pool_out + ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + n0 + c;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float o[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float a0 = v[i + j];
+                                    if (ep.pool_avg) {
+                                        const float a1 = __shfl_xor_sync(0xffffffffu, a0, 1);
+                                        const float a2 = __shfl_xor_sync(0xffffffffu, a0, 16);
+                                        const float a3 = __shfl_xor_sync(0xffffffffu, a0, 17);
+                                        o[j] = round_tf32(0.25f * (a0 + a1 + a2 + a3));
+                                    } else {
+                                        const float m = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, 1));
+                                        o[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                                    }
+                                }
+                                if (pvalid) *reinterpret_cast<float4*>(pdst + i) = make_float4(o[0], o[1], o[2], o[3]);
+                            }
+                        }
                         uint8_t* sbox = stage_box + (box & 1) * STAGE_BOX_BYTES;
                         // the store that last read this staging box (two boxes ago) must have drained it
                         if (issuer) bulk_wait_group_read<1>();
@@ -518,11 +549,11 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int MT, int CG>
+template <int BN, int MT, int CG, bool POOL>
 int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = ConvCfg<BN, MT, CG>;
-    static unsigned long long attr_done = 0;  // per (BN, MT, CG) instantiation; benign race (idempotent call)
-    MAUA_CUDA_CHECK(ensure_dynamic_smem(conv_tc_kernel<BN, MT, CG>, Cfg::SMEM_BYTES, &attr_done));
+    static unsigned long long attr_done = 0;  // per (BN, MT, CG, POOL) instantiation; benign race (idempotent call)
+    MAUA_CUDA_CHECK((ensure_dynamic_smem(conv_tc_kernel<BN, MT, CG, POOL>, Cfg::SMEM_BYTES, &attr_done)));
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
     const bool has_main = a.ntaps > 0;
@@ -541,6 +572,7 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     // epilogue flavour: the TMA-store path covers bias / ReLU / bitmap mask / rounding; the content, addend and
     // fp32-mask terms need per-element global loads and keep the register -> global path
     const bool direct = a.ep.cont_f || a.ep.addend || a.ep.mask_src;
+    MAUA_REQUIRE(!(a.ep.pool_out && direct), "fused pooling needs the TMA-store epilogue (no content / addend / fp32-mask terms)");
     CUtensorMap tmOut, tmOut2;
     if (!direct) {
         if ((rc = make_tmap_nhwc(&tmOut, a.ep.out, a.B, a.H, a.W, a.Cout, TILE_W, TILE_H))) return rc;
@@ -575,13 +607,14 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CG > 1 ? 1 : 0;
-    MAUA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p));
+    MAUA_CUDA_CHECK((cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG, POOL>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p)));
     return MAUA_OK;
 }
 
 template <int BN, int MT>
 int launch_cg(const ConvArgs& a, int cg, cudaStream_t st) {
-    return cg == 2 ? launch_cfg<BN, MT, 2>(a, st) : launch_cfg<BN, MT, 1>(a, st);
+    if (a.ep.pool_out) return cg == 2 ? launch_cfg<BN, MT, 2, true>(a, st) : launch_cfg<BN, MT, 1, true>(a, st);
+    return cg == 2 ? launch_cfg<BN, MT, 2, false>(a, st) : launch_cfg<BN, MT, 1, false>(a, st);
 }
 
 }  // namespace
@@ -688,7 +721,11 @@ int conv_ref_launch(const ConvArgs& a, cudaStream_t st) {
     const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
     conv_ref_kernel<<<blocks, 256, 0, st>>>(a);
     MAUA_CUDA_CHECK(cudaGetLastError());
-    if (a.ep.mask_out) return relu_mask_bits_launch(a.ep.out, a.ep.mask_out, (long)a.B * a.H * a.W, a.Cout, st);
+    if (a.ep.mask_out) {
+        const int rc = relu_mask_bits_launch(a.ep.out, a.ep.mask_out, (long)a.B * a.H * a.W, a.Cout, st);
+        if (rc) return rc;
+    }
+    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, st);
     return MAUA_OK;
 }
 

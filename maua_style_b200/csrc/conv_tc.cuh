@@ -13,7 +13,8 @@ namespace maua {
 //   v  = max(v, 0)                       (ReLU, models.py:130)                       if relu
 //   v  = mask_src > 0 ? v : 0            (ReLU backward through the *previous* layer) if mask_src / mask_bits
 //   v  = round_tf32(v)                   (operand rounding for the consuming MMA)     if round
-// and, for forward layers, mask_out receives the sign bitmap (v > 0) of the result: 1 bit per element, word
+// optionally followed by the 2x2 / stride-2 pooling of the finished tile (models.py:119-122; pool_out, opt-in), and,
+// for forward layers, mask_out receives the sign bitmap (v > 0) of the result: 1 bit per element, word
 // [pixel * (Cout/32) + n/32], bit n % 32 -- what the dgrad of the layer above reads as mask_bits instead of re-reading
 // the fp32 activation (32x less mask traffic in the backward pass).
 struct ConvEpilogue {
@@ -30,6 +31,11 @@ struct ConvEpilogue {
     const float* addend = nullptr;    // NHWC like out
     int relu = 0;
     int round = 1;
+    // Fused 2x2 pooling (tcgen05 path with the TMA-store epilogue only): the pooled map [B][H/2][W/2][Cout] is written
+    // next to the full-resolution output from the same registers (max: the window's four pixels sit in lanes l, l^1,
+    // l^16, l^17 of one epilogue warp).  Same arithmetic as pool_fwd_kernel, bit for bit.
+    float* pool_out = nullptr;
+    int pool_avg = 0;
 };
 
 // out[b][h][w][n] = epilogue( sum_{tap,c} in[b][h+dy][w+dx][c] * wg[n][tap*Cin + c]

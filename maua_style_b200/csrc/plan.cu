@@ -14,6 +14,7 @@
 //   e is the last entry    : Gm_e = mask( tap gradients at e )            (aux-GEMM-only launch)
 // and finally pastiche.grad = conv1_1 dgrad(Gm_0) + TV + temporal terms (conv_edge.cu).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -125,6 +126,7 @@ struct maua_plan {
     std::vector<Entry> entries;
     std::vector<Tap> taps;
     int avg_pool = 0;
+    bool fuse_pool = false;       // pool inside the producing conv's epilogue (opt-in: MAUA_FUSE_POOL=1 at plan creation)
     size_t weight_bytes = 0;
     // workspaces
     float* arena = nullptr;
@@ -260,6 +262,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     maua_plan* p = new maua_plan();
     p->device = device;
     p->avg_pool = d->avg_pool;
+    if (const char* f = getenv("MAUA_FUSE_POOL")) p->fuse_pool = atoi(f) != 0;
     p->begin = begin;
     p->last_stage = (end == d->n_entries);
     memset(&p->img_io, 0, sizeof(p->img_io));
@@ -431,6 +434,12 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
     return MAUA_OK;
 }
 
+MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* p, int enable) {
+    MAUA_REQUIRE(p, "maua_plan_set_fuse_pool: null plan");
+    p->fuse_pool = enable != 0;
+    return MAUA_OK;
+}
+
 MAUA_API int maua_plan_set_profile(maua_plan_t* p, int enable) {
     MAUA_REQUIRE(p, "maua_plan_set_profile: null plan");
     p->profile = enable != 0;
@@ -542,6 +551,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     // ---- feature stack ----
     const float* cur = p->stage_input;
     int curH = H, curW = W;
+    bool pool_done = false;
     for (int i = 0; i <= last_needed; ++i) {
         Entry& e = p->entries[i];
         float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
@@ -550,6 +560,11 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             if (hand_off)
                 MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
         } else if (e.pool) {
+            if (pool_done) {  // produced by the epilogue of the conv below (fused pooling)
+                pool_done = false;
+                cur = e.out; curH = e.H; curW = e.W;
+                continue;
+            }
             // a pooled map is not needed again by this stage (the backward pass reads the pre-pool activation), so at a
             // stage boundary it is written straight into the next stage's memory
             if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, st))) return rc;
@@ -561,6 +576,11 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.ep.mask_out = e.bits;
             a.force_cg = p->impl == MAUA_IMPL_TC_1CTA ? 1 : (p->impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
+            if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && e.H >= 2 && e.W >= 2) {
+                a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
+                a.ep.pool_avg = p->avg_pool;
+                pool_done = true;
+            }
             rc = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
             if (rc) return rc;
         }

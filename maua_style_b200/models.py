@@ -229,6 +229,8 @@ class B200Net(nn.Module):
             st["loss_vec"].zero_()
             _lib.check(self._lib.maua_plan_set_impl(st["plan"], _lib.MAUA_IMPL_TC), "maua_plan_set_impl")
             _lib.check(self._lib.maua_plan_set_profile(st["plan"], 0), "maua_plan_set_profile")
+            _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(os.environ.get("MAUA_FUSE_POOL", "0") == "1")),
+                       "maua_plan_set_fuse_pool")
         self._plan = self._stages[0]["plan"]
         self._loss_vec = torch.zeros(self._n_slots, device=device)
         self._coefs = self._stages[0]["coefs"]
@@ -258,6 +260,11 @@ class B200Net(nn.Module):
     def set_impl(self, impl: int):
         for st in self._stages:
             _lib.check(self._lib.maua_plan_set_impl(st["plan"], impl), "maua_plan_set_impl")
+
+    def set_fuse_pool(self, enable: bool):
+        """Pool inside the producing conv's epilogue instead of a separate pass (csrc/conv_tc.cu; off by default)."""
+        for st in self._stages:
+            _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(enable)), "maua_plan_set_fuse_pool")
 
     def device_bytes(self) -> int:
         return sum(int(self._lib.maua_plan_device_bytes(st["plan"])) for st in self._stages)

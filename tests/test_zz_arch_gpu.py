@@ -120,3 +120,48 @@ def test_variant_optimize_matches_reference_golden(name, tmp_path):
     p = O.psnr(out, torch.from_numpy(z["optimized"]))
     print(f"{name} optimize {meta['iters']} iters PSNR {p:.1f} dB")
     assert p > 40.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Opt-in code paths that have not run on a B200 yet (written after the round's GPU budget was spent).  They are off by
+# default in the product and their tests only run with MAUA_TEST_EXPERIMENTAL=1.
+# ---------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+experimental = pytest.mark.skipif(os.environ.get("MAUA_TEST_EXPERIMENTAL", "0") != "1",
+                                  reason="opt-in paths not yet verified on hardware: set MAUA_TEST_EXPERIMENTAL=1")
+
+
+@experimental
+@pytest.mark.parametrize("pooling", ["max", "avg"])
+@pytest.mark.parametrize("hw", [(90, 122), (64, 64), (257, 131)])
+def test_fused_pool_epilogue_is_bit_identical_to_the_pool_kernel(pooling, hw, tmp_path):
+    """conv epilogue pooling (conv_tc_kernel<.., POOL = true>) against the separate pool_fwd_kernel: same arithmetic, so
+    features, losses and the image gradient must be bit-identical, including odd extents (floor semantics)."""
+    from maua_style_b200 import models, optim
+
+    path = tmp_path / "vgg19-random.pth"
+    save_checkpoint(path)
+    h, w = hw
+    content = O.synthetic_image(h, w, seed=1, smooth=True)
+    style = O.synthetic_image(h, w, seed=2)
+    init = (O.synthetic_image(h, w, seed=4) * 0.25).cuda()
+    res = []
+    for fuse in (False, True):
+        args = make_args(path, tmp_path, pooling=pooling, temporal_weight=0.0)
+        net, losses = models.load_model(args)
+        net.set_fuse_pool(fuse)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, [style], args)
+        for m in losses:
+            m.mode = "loss"
+        vec, g = optim.feval(net, init.clone())
+        feats = [net.tap_feature(t) for t in range(len(net.taps))]
+        fwd, bwd = net.last_launches()
+        res.append((vec.clone(), g.clone(), feats, fwd))
+        del net, losses
+    assert res[1][3] == res[0][3] - 4  # four pool launches fewer
+    for a, b in zip(res[0][2], res[1][2]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
