@@ -17,6 +17,8 @@
 // HBM-bound (intensity C/2 flop/B).  Partials are written to a workspace and summed in a fixed order by
 // the finalize kernel (deterministic, no float atomics), which also symmetrises, applies the covariance
 // rank-1 correction  sum (x-mu)(y-mu) = sum xy - P mu mu^T  and the 1/(C*P) normalisation.
+#include <cstdlib>
+
 #include "gram.cuh"
 #include "reduce.cuh"
 
@@ -45,9 +47,14 @@ struct GramCfg {
     static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN, bool OFFDIAG>
+// NACC > 1 (opt-in, MAUA_GRAM_NACC=4): pipeline stage ks accumulates into TMEM accumulator ks % NACC and the epilogue adds
+// the NACC accumulators.  The tensor core's fp32 accumulate truncates, so the error of a sum grows linearly with the
+// length of the accumulation chain (measured: 2.6e-5 relative at relu1_1 / 1024^2, ~890 dependent MMAs per CTA);
+// NACC interleaved chains are NACC times shorter.  This matters for the covariance, where sum(xy) - P mu mu^T cancels.
+template <int BN, bool OFFDIAG, int NACC = 1>
 __global__ void __launch_bounds__(256, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
+    static_assert(BN * NACC <= 512, "TMEM has 512 columns");
     using Cfg = GramCfg<BN, OFFDIAG>;
     constexpr int NST = Cfg::NSTAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -85,7 +92,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_ptr_smem, BN); tmem_relinquish(); }
+    if (warp == 2) { tmem_alloc(tmem_ptr_smem, BN * NACC); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -122,7 +129,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
                     // MN-major TF32: layout type 1 (128B swizzle, 32-byte atoms): 4-row x 128 B atoms, SBO = 512 B
                     const uint64_t adesc = make_smem_desc(sA + kk * 1024, BOX_BYTES, 512, 1);
                     const uint64_t bdesc = make_smem_desc(sB + kk * 1024, BOX_BYTES, 512, 1);
-                    umma_tf32(tmem_base, adesc, bdesc, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base + (NACC > 1 ? (ks % NACC) * BN : 0), adesc, bdesc, idesc,
+                              (ks >= NACC || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);
                 if (ks == nk - 1) umma_commit(tmem_full_bar);
@@ -141,6 +149,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
             for (int col = 0; col < BN; col += 16) {
                 float v[16];
                 tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+                if (NACC > 1) {
+                    const int used = nk < NACC ? nk : NACC;  // accumulators that received at least one stage
+#pragma unroll 1
+                    for (int a = 1; a < used; ++a) {
+                        float u[16];
+                        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + col, u);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += u[i];
+                    }
+                }
                 if (c < p.C) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
@@ -153,7 +171,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, BN);
+    if (warp == 2) tmem_dealloc(tmem_base, BN * NACC);
 }
 
 // naive SIMT cross-check: partial slot 0 = full (upper + lower) raw Gram
@@ -276,14 +294,21 @@ __global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y,
         y[i] = (accumulate ? y[i] : 0.f) + a * x[i];
 }
 
-template <int BN, bool OFFDIAG>
-int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, int ntiles, cudaStream_t st) {
+template <int BN, bool OFFDIAG, int NACC>
+int launch_gram_nacc(const CUtensorMap& tm, const GramParams& p, int ntiles, cudaStream_t st) {
     using Cfg = GramCfg<BN, OFFDIAG>;
     static unsigned long long attr_done = 0;
-    MAUA_CUDA_CHECK(ensure_dynamic_smem(gram_tc_kernel<BN, OFFDIAG>, Cfg::SMEM_BYTES, &attr_done));
-    gram_tc_kernel<BN, OFFDIAG><<<dim3(ntiles, p.nsplit), 256, Cfg::SMEM_BYTES, st>>>(tm, p);
+    MAUA_CUDA_CHECK((ensure_dynamic_smem(gram_tc_kernel<BN, OFFDIAG, NACC>, Cfg::SMEM_BYTES, &attr_done)));
+    gram_tc_kernel<BN, OFFDIAG, NACC><<<dim3(ntiles, p.nsplit), 256, Cfg::SMEM_BYTES, st>>>(tm, p);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
+}
+
+template <int BN, bool OFFDIAG>
+int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, int ntiles, cudaStream_t st) {
+    const char* f = getenv("MAUA_GRAM_NACC");  // opt-in: interleaved accumulation chains (see gram_tc_kernel)
+    if (f && atoi(f) == 4) return launch_gram_nacc<BN, OFFDIAG, 4>(tm, p, ntiles, st);
+    return launch_gram_nacc<BN, OFFDIAG, 1>(tm, p, ntiles, st);
 }
 
 }  // namespace

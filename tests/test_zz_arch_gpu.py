@@ -165,3 +165,37 @@ def test_fused_pool_epilogue_is_bit_identical_to_the_pool_kernel(pooling, hw, tm
         assert torch.equal(a, b)
     assert torch.equal(res[0][0], res[1][0])
     assert torch.equal(res[0][1], res[1][1])
+
+
+@experimental
+@pytest.mark.parametrize("cov", [False, True])
+def test_interleaved_gram_accumulators_reduce_the_accumulation_error(cov, tmp_path, monkeypatch):
+    """MAUA_GRAM_NACC=4 (gram_tc_kernel<.., NACC = 4>): four interleaved TMEM accumulation chains instead of one.  Against
+    the fp64 product of the stored 1024^2 tap features the error must not grow, and for the covariance (where the one-pass
+    form cancels) it should drop by about the chain-length ratio."""
+    from maua_style_b200 import models, optim
+
+    path = tmp_path / "vgg19-random.pth"
+    save_checkpoint(path)
+    style = O.synthetic_image(1024, 1024, seed=2).cuda()
+    errs = {}
+    for nacc in ("1", "4"):
+        monkeypatch.setenv("MAUA_GRAM_NACC", nacc)
+        args = make_args(path, tmp_path, use_covariance=cov, temporal_weight=0.0)
+        net, losses = models.load_model(args)
+        optim.set_style_targets(net, [style], args)
+        e = []
+        for t, (ridx, mod) in enumerate(net.taps):
+            if mod not in net.style_losses:
+                continue
+            f = net.tap_feature(t)[0]
+            x = f.reshape(f.shape[0], -1).double()
+            if cov:
+                x = x - x.mean(1, keepdim=True)
+            e.append(rel(mod.target, (x @ x.t()) / f.numel()))
+        errs[nacc] = e
+        del net, losses
+    print(f"stored Gram error (cov={cov}) NACC=1 {['%.2e' % v for v in errs['1']]} NACC=4 {['%.2e' % v for v in errs['4']]}")
+    for a, b in zip(errs["1"], errs["4"]):
+        assert b <= a * 1.05 + 1e-7
+    assert max(errs["4"]) < (1e-3 if cov else 1e-4)
