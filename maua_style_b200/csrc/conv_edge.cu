@@ -13,6 +13,8 @@
 //           and is also the fused "image-side tail" (SURVEY.md A.4 item 5): it adds the TVLoss gradient (loss.py:224-233)
 //           and the temporal ContentLoss gradient (loss.py:46-54) while the image gradient is in registers, so
 //           pastiche.grad is written exactly once.
+#include <cstdlib>
+
 #include "conv_tc.cuh"
 
 namespace maua {
@@ -116,6 +118,98 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
     }
 }
 
+// Same kernel with the 27 x 64 multiply-adds issued as packed FFMA2 (fma.rn.f32x2, sm_100): two independent
+// round-to-nearest FMAs per instruction, i.e. the same results bit for bit at half the fma-pipe issue slots (the plain
+// kernel is bound by them: 1728 FFMA per thread and tile, 62 % of the scalar-FFMA peak in the round-1 ncu capture).
+// Opt-in (MAUA_CONV1_FFMA2=1) until it has been verified on hardware.
+__global__ void __launch_bounds__(256)
+conv_first_fwd_f2_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out, uint16_t* __restrict__ mask16, int B, int H, int W, int do_round) {
+    constexpr int Cout = 64, G = 4;
+    __shared__ __align__(16) float ws[27 * G * FG_STRIDE];
+    __shared__ float bs[Cout];
+    __shared__ __align__(16) float inp[3][FT_H + 2][FI_W];
+    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+        const int co = i / 27, k = i % 27;
+        ws[(k * G + co / 16) * FG_STRIDE + (co % 16)] = w[i];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+
+    const int g = threadIdx.x & 3;
+    const int quad = (threadIdx.x >> 2) & 15;
+    const int row = threadIdx.x >> 6;
+    const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
+    const long ntiles = (long)B * tiles_w * tiles_h;
+    const long HW = (long)H * W;
+
+    for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tw = t % tiles_w;
+        const int th = (t / tiles_w) % tiles_h;
+        const int b = t / ((long)tiles_w * tiles_h);
+        const int h0 = th * FT_H, w0 = tw * FT_W;
+        __syncthreads();  // previous tile consumed (and, first time, weights staged)
+        for (int i = threadIdx.x; i < 3 * (FT_H + 2) * (FT_W + 2); i += blockDim.x) {
+            const int x = i % (FT_W + 2);
+            const int r = (i / (FT_W + 2)) % (FT_H + 2);
+            const int ci = i / ((FT_W + 2) * (FT_H + 2));
+            const int hh = h0 + r - 1, ww = w0 + x - 1;
+            inp[ci][r][x] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + ((long)b * 3 + ci) * HW + (long)hh * W + ww) : 0.f;
+        }
+        __syncthreads();
+
+        float2 acc[4][8];  // [pixel][channel pair]: FFMA2 operands are 64-bit register pairs
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(bs[g * 16 + 2 * c], bs[g * 16 + 2 * c + 1]);
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float* ip = &inp[ci][row + ky][4 * quad];
+                const float4 x0 = *reinterpret_cast<const float4*>(ip);
+                const float2 x1 = *reinterpret_cast<const float2*>(ip + 4);
+                const float2 xin[6] = {make_float2(x0.x, x0.x), make_float2(x0.y, x0.y), make_float2(x0.z, x0.z),
+                                       make_float2(x0.w, x0.w), make_float2(x1.x, x1.x), make_float2(x1.y, x1.y)};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 9 + ky * 3 + kx) * G + g) * FG_STRIDE);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 wv = wp[c4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[j][2 * c4 + 0] = __ffma2_rn(xin[j + kx], make_float2(wv.x, wv.y), acc[j][2 * c4 + 0]);
+                            acc[j][2 * c4 + 1] = __ffma2_rn(xin[j + kx], make_float2(wv.z, wv.w), acc[j][2 * c4 + 1]);
+                        }
+                    }
+                }
+            }
+        const int h = h0 + row;
+        if (h < H) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = w0 + 4 * quad + j;
+                if (x >= W) continue;
+                const long pix = ((long)b * H + h) * W + x;
+                float4* op = reinterpret_cast<float4*>(out + pix * Cout + g * 16);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float4 o;
+                    o.x = fmaxf(acc[j][2 * c4].x, 0.f); o.y = fmaxf(acc[j][2 * c4].y, 0.f);
+                    o.z = fmaxf(acc[j][2 * c4 + 1].x, 0.f); o.w = fmaxf(acc[j][2 * c4 + 1].y, 0.f);
+                    if (do_round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    op[c4] = o;
+                    bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << (4 * c4);
+                }
+                // sign bitmap of the output (16 channels of this thread = one half-word): the ReLU mask dgrad reads
+                if (mask16) mask16[pix * (Cout / 16) + g] = (uint16_t)bits;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -206,7 +300,11 @@ int conv_first_fwd_launch(const float* img, const float* w, const float* bias, f
     MAUA_REQUIRE(Cout == 64, "conv_first_fwd: the image layer must have 64 output channels (got %d)", Cout);
     const long ntiles = (long)B * ((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H);
     long blocks = ntiles > 148L * 8 ? 148L * 8 : ntiles;
-    conv_first_fwd_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
+    const char* f2 = getenv("MAUA_CONV1_FFMA2");
+    if (f2 && atoi(f2) != 0)
+        conv_first_fwd_f2_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
+    else
+        conv_first_fwd_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

@@ -199,3 +199,25 @@ def test_interleaved_gram_accumulators_reduce_the_accumulation_error(cov, tmp_pa
     for a, b in zip(errs["1"], errs["4"]):
         assert b <= a * 1.05 + 1e-7
     assert max(errs["4"]) < (1e-3 if cov else 1e-4)
+
+
+@experimental
+@pytest.mark.parametrize("h,w", [(32, 32), (37, 53), (5, 3), (1024, 1024)])
+def test_conv1_1_ffma2_kernel_is_bit_identical(h, w, monkeypatch):
+    """MAUA_CONV1_FFMA2=1 (conv_first_fwd_f2_kernel): the same 27 x 64 round-to-nearest FMAs per pixel, issued as packed
+    FFMA2 -- the output must equal the scalar-FFMA kernel's bit for bit."""
+    from maua_style_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(h)
+    img = (torch.rand(1, 3, h, w, generator=g) * 255 - 110).cuda()
+    wt = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MAUA_CONV1_FFMA2", flag)
+        y = torch.empty(1, h, w, 64, device="cuda")
+        _lib.check(lib.maua_conv_first_fwd(_lib.ptr(img), _lib.ptr(wt), _lib.ptr(b), _lib.ptr(y), 1, h, w, 64, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
