@@ -5,6 +5,8 @@ the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
   vid_frame_temporal_64x80 ... one vid_img frame (style.py:276-294): optim.set_temporal_targets with a flow-reliability map,
                                then optimize(content, styles, init, n, args, net, losses) -- the weighted temporal
                                ContentLoss on the image (loss.py:46-54) pinned to the reference's own numbers
+  vgg19_deep_taps_avg_64x96 .. two content taps (relu3_2, relu5_2), style taps relu2_2 / relu4_3, the stack one layer past
+                               relu5_1, average pooling
   vgg19_taps_lbfgs_80x64 ..... style taps relu1_2 / relu3_3 and content tap relu2_2: loss modules directly in front of a
                                pool (their gradient joins the un-pooled gradient) and truncation after relu3_3
 
@@ -18,7 +20,7 @@ from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoi
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64"]
+CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96"]
 
 
 def temporal_inputs(meta):
@@ -104,7 +106,7 @@ def test_variant_feval_matches_reference_golden_and_oracle(name, tmp_path):
         assert abs(v / ref - 1) < 1e-2, (k, v, ref)
     gerr = rel(x.grad, torch.from_numpy(z["grad"]))
     print(f"{name} image-gradient rel {gerr:.2e}")
-    assert gerr < 4e-2
+    assert gerr < (3e-3 if meta["over"].get("pooling") == "avg" else 4e-2)
 
 
 @pytest.mark.parametrize("name", CASES)
