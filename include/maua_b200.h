@@ -225,8 +225,8 @@ typedef struct maua_net_desc {
     const float* biases[MAUA_MAX_LAYERS];
     int n_taps;
     int tap_relu_index[MAUA_MAX_TAPS];  /* 0-based index of the ReLU (= conv count - 1) the loss module follows */
-    int tap_kind[MAUA_MAX_TAPS];        /* maua_tap_kind; taps must be ordered by relu index (style before content
-                                           at the same index, as models.py:403-431 inserts them) */
+    int tap_kind[MAUA_MAX_TAPS];        /* maua_tap_kind; taps must be ordered by relu index (content before style
+                                           at the same index, as models.py:411-431 inserts them) */
 } maua_net_desc;
 
 /* Per-call, per-tap state: targets are caller-owned tensors so the Python loss modules can expose them

@@ -9,6 +9,8 @@ CPU (same recipe as make_golden.py, whose helpers this script re-uses):
                                  with optim.set_temporal_targets, then optimize(content, styles, init, n, args, net, losses)
   vgg19_deep_taps_avg_64x96 .... two content taps (relu3_2, relu5_2) and style taps relu2_2 / relu4_3: the stack runs one
                                  layer past relu5_1, average pooling, 3 Adam iterations
+  vgg19_same_layer_taps_64x64 .. ContentLoss and StyleLoss on the same ReLU (relu4_2; models.py:411-431 inserts the content
+                                 module first)
   vgg19_taps_lbfgs_80x64 ....... VGG-19 with `--style_layers relu1_2,relu3_3 --content_layers relu2_2`: taps that sit
                                  directly before a pool, truncation after relu3_3 (models.py:382), 4 L-BFGS iterations
 """
@@ -43,6 +45,8 @@ def main():
         mg.run_case("vgg19_deep_taps_avg_64x96", ckpt=ckpt19, h=64, w=96, style_hw=[(80, 80)], iters=3,
                     style_layers="relu2_2,relu4_3", content_layers="relu3_2,relu5_2", pooling="avg",
                     meta_extra={"arch": "VGG-19"}, **common)
+        mg.run_case("vgg19_same_layer_taps_64x64", ckpt=ckpt19, h=64, w=64, style_hw=[(64, 64)], iters=3,
+                    style_layers="relu1_1,relu4_2", content_layers="relu4_2", meta_extra={"arch": "VGG-19"}, **common)
         mg.run_case("vgg19_taps_lbfgs_80x64", ckpt=ckpt19, h=80, w=64, style_hw=[(72, 72)], iters=4, optimizer="lbfgs",
                     style_layers="relu1_2,relu3_3", content_layers="relu2_2", meta_extra={"arch": "VGG-19"}, **common)
 

@@ -7,6 +7,7 @@ the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
                                ContentLoss on the image (loss.py:46-54) pinned to the reference's own numbers
   vgg19_deep_taps_avg_64x96 .. two content taps (relu3_2, relu5_2), style taps relu2_2 / relu4_3, the stack one layer past
                                relu5_1, average pooling
+  vgg19_same_layer_taps_64x64  ContentLoss and StyleLoss spliced after the same ReLU (relu4_2)
   vgg19_taps_lbfgs_80x64 ..... style taps relu1_2 / relu3_3 and content tap relu2_2: loss modules directly in front of a
                                pool (their gradient joins the un-pooled gradient) and truncation after relu3_3
 
@@ -20,7 +21,8 @@ from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoi
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96"]
+CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96",
+         "vgg19_same_layer_taps_64x64"]
 
 
 def temporal_inputs(meta):
