@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch profile JSON here")
     ap.add_argument("--no-multires", action="store_true", help="skip the 256->512->1024 multi-resolution job (configs[1] whole)")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="experimental: S independent images per GPU on S streams (batch jobs, BASELINE.json configs[4]); "
+                         "prints its own JSON line, the default line is unchanged")
     return ap.parse_args()
 
 
@@ -438,10 +441,71 @@ def multires_job(a, dev):
             "h2d_bytes": int(content_u8.numel() + style_u8.numel()), "d2h_bytes": int(result.numel())}
 
 
+def run_streams(args):
+    """Experimental (batch jobs): S independent images on ONE GPU, each with its own plan, optimizer
+    state, captured graph and stream, so that one image's HBM-bound phase (L-BFGS history sweeps, pools, Grams) can run
+    under another image's tensor-bound convolutions.  Reports the aggregate iterations/sec next to the single-stream rate
+    measured in the same process.  Single process / single GPU only."""
+    from maua_style_b200 import _lib, models, optim, synthetic as O
+
+    _lib.require_gpu()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    size, K, W, S = args.size, args.steps, args.warmup, args.streams
+    tmp = tempfile.mkdtemp(prefix="maua_bench_streams_")
+    ckpt = Path(tmp) / "vgg19-random.pth"
+    O.save_random_checkpoint(ckpt)
+    style = O.synthetic_image(size, size, seed=2).to(dev)
+    jobs = []
+    for k in range(S):
+        a = O.reference_args(ckpt, tmp, optimizer=args.optimizer, gpu="0")
+        stream = torch.cuda.Stream(dev)
+        with torch.cuda.stream(stream):
+            net, losses = models.load_model(a)  # a plan core is handed to one live network at a time: S cores
+            optim.set_content_targets(net, O.synthetic_image(size, size, seed=1 + 10 * k, smooth=True).to(dev), a)
+            optim.set_style_targets(net, [style], a)
+            for m in losses:
+                m.mode = "loss"
+            pastiche = (O.synthetic_image(size, size, seed=4 + 10 * k) * 0.25).to(dev).contiguous()
+            opt = optim.PixelOptimizer(pastiche, args.optimizer, lr=1.0, history=100)
+            up = torch.zeros(net._n_slots, device=dev)
+            up[net._live_slots()] = 1.0
+            step = optim.GraphedIteration(net, pastiche, opt, up)
+            for _ in range(args.history_prefill if args.optimizer == "lbfgs" else 3):
+                step()
+        stream.synchronize()
+        jobs.append((stream, step, net, losses, opt, pastiche))
+
+    def timed(active):
+        for _ in range(W):
+            for stream, step, *_ in active:
+                with torch.cuda.stream(stream):
+                    step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            for stream, step, *_ in active:  # round-robin submission: one graph launch per image and iteration
+                with torch.cuda.stream(stream):
+                    step()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    single = K / timed(jobs[:1])
+    multi = S * K / timed(jobs)
+    print(json.dumps({"metric": METRIC, "experimental": "streams", "streams": S, "value": multi, "unit": UNIT,
+                      "single_stream_value": single, "speedup": multi / single, "steps": K, "warmup": W,
+                      "config": workload_config(size, args.optimizer),
+                      "timing": "wall clock around K round-robin graph launches per stream, device synchronised"}), flush=True)
+    for _, _, _, _, opt, _ in jobs:
+        opt.close()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.streams > 1:
+        run_streams(args)
     else:
         run_ours(args)
 

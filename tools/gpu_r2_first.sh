@@ -48,6 +48,10 @@ for f in sorted(glob.glob(sys.argv[1] + '/bench_*.json')):
     except Exception as e:
         print(f, 'parse failed', e)
 PY
+stamp "3b. two / three images per GPU on separate streams (experimental, DESIGN.md section 6)"
+for S in 2 3; do
+  timeout -k 5 150 python bench.py --streams $S > $OUT/bench_streams$S.json 2> $OUT/bench_streams$S.err; echo "streams $S exit $?"; cat $OUT/bench_streams$S.json | cut -c1-400
+done
 stamp "4. launch list at 512^2 (short history so that the pass stays under 2 minutes)"
 timeout -k 5 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file /tmp/launches_512.csv \
   python bench.py --size 512 --steps 2 --warmup 3 --no-cpu-baseline --no-multires --history-prefill 2 > $OUT/ncu_launches_512.log 2>&1
