@@ -25,6 +25,19 @@ CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_
          "vgg19_same_layer_taps_64x64"]
 
 
+# (image-gradient bound, PSNR bound) per case.  oracle/tf32_emulation.py predicts, on the CPU, what TF32 operands do to each
+# case (emulated gradient error / PSNR in the comments); the bounds leave ~1.6x / 10 dB of room for a different realisation
+# of the rounding noise.  The 4-iteration L-BFGS case is the sensitive one: its first curvature pair is rounding noise
+# (DESIGN.md section 2), so the step lengths of iterations 2-4 differ visibly between any two arithmetics.
+BOUNDS = {
+    "vgg16_adam_gram_72x88": (5e-2, 40.0),        # 3.0e-2, 56.0 dB
+    "vid_frame_temporal_64x80": (4e-2, 40.0),     # 2.2e-2, 56.1 dB
+    "vgg19_taps_lbfgs_80x64": (4e-2, 25.0),       # 2.5e-2, 34.7 dB
+    "vgg19_deep_taps_avg_64x96": (1.5e-2, 40.0),  # 6.9e-3, 62.0 dB (ReLU-sign flips remain with average pooling, 18 layers deep)
+    "vgg19_same_layer_taps_64x64": (7e-2, 40.0),  # 4.3e-2, 55.5 dB
+}
+
+
 def temporal_inputs(meta):
     """make_golden.temporal_inputs: stand-ins for the warped previous frame and the flow-reliability map."""
     if not meta.get("temporal"):
@@ -108,7 +121,7 @@ def test_variant_feval_matches_reference_golden_and_oracle(name, tmp_path):
         assert abs(v / ref - 1) < 1e-2, (k, v, ref)
     gerr = rel(x.grad, torch.from_numpy(z["grad"]))
     print(f"{name} image-gradient rel {gerr:.2e}")
-    assert gerr < (3e-3 if meta["over"].get("pooling") == "avg" else 4e-2)
+    assert gerr < BOUNDS[name][0]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -123,7 +136,7 @@ def test_variant_optimize_matches_reference_golden(name, tmp_path):
     out = optim.optimize(content, styles, init.clone(), meta["iters"], args, net, losses)
     p = O.psnr(out, torch.from_numpy(z["optimized"]))
     print(f"{name} optimize {meta['iters']} iters PSNR {p:.1f} dB")
-    assert p > 40.0
+    assert p > BOUNDS[name][1]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
