@@ -132,3 +132,45 @@ def test_match_histogram_properties():
             assert np.allclose(c_y, c_s, rtol=2e-3, atol=0.05), (name, np.abs(c_y - c_s).max())
         assert np.allclose(I.match_histogram(target, [target]), target, atol=2e-4)
         assert np.allclose(I.match_histogram(target, [sources[0], sources[0]]), I.match_histogram(target, [sources[0]]), atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Randomised pinning: the numpy oracle against the torch CPU ops the reference calls (style.py:38-66 F.interpolate,
+# style.py:279 F.grid_sample) on shapes and scale factors the fixtures do not contain.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(12))
+def test_resize_bilinear_random_shapes_bit_exact_vs_torch(seed):
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import image_oracle as IO
+
+    rs = np.random.RandomState(seed)
+    h, w = int(rs.randint(3, 97)), int(rs.randint(3, 97))
+    x = (rs.rand(1, 3, h, w).astype(np.float32) * 255.0 - 110.0)
+    if seed % 2 == 0:
+        sf = float(rs.uniform(0.3, 2.7))
+        ref = F.interpolate(torch.from_numpy(x), scale_factor=sf, mode="bilinear", align_corners=False).numpy()
+        out = IO.resize_bilinear(x, scale_factor=sf)
+    else:
+        size = (int(rs.randint(2, 130)), int(rs.randint(2, 130)))
+        ref = F.interpolate(torch.from_numpy(x), size=size, mode="bilinear", align_corners=False).numpy()
+        out = IO.resize_bilinear(x, size=size)
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref), float(np.abs(out - ref).max())
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_grid_sample_border_random_bit_exact_vs_torch(seed):
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import image_oracle as IO
+
+    rs = np.random.RandomState(100 + seed)
+    h, w = int(rs.randint(4, 70)), int(rs.randint(4, 70))
+    x = (rs.rand(1, 3, h, w).astype(np.float32) * 255.0 - 110.0)
+    grid = (rs.rand(1, h, w, 2).astype(np.float32) * 2.4 - 1.2)  # some samples fall outside: padding_mode="border"
+    ref = F.grid_sample(torch.from_numpy(x), torch.from_numpy(grid), padding_mode="border", align_corners=False).numpy()
+    out = IO.grid_sample_border(x[0], grid[0])
+    assert np.array_equal(out, ref[0]), float(np.abs(out - ref).max())
