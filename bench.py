@@ -390,10 +390,17 @@ def run_ours(args):
         line["hbm_peak_gbs"] = pk["hbm"]
         if args.profile_out:
             Path(args.profile_out).write_text(json.dumps({"per_launch": prof, "summary": by}, indent=1))
+        # the extras must never cost the line itself: a failure is reported inside the line
         if world == 1 and not args.no_multires and size == 1024:
-            line["multires_e2e"] = multires_job(a, dev)
+            try:
+                line["multires_e2e"] = multires_job(a, dev)
+            except Exception as e:  # noqa: BLE001
+                line["multires_e2e"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(size, args.optimizer)
+            try:
+                line["cpu_baseline"] = cpu_baseline(size, args.optimizer)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
     opt.close()
     if world > 1:
