@@ -32,7 +32,8 @@ CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_
 BOUNDS = {
     "vgg16_adam_gram_72x88": (5e-2, 40.0),        # 3.0e-2, 56.0 dB
     "vid_frame_temporal_64x80": (4e-2, 40.0),     # 2.2e-2, 56.1 dB
-    "vgg19_taps_lbfgs_80x64": (4e-2, 25.0),       # 2.5e-2, 34.7 dB
+    "vgg19_taps_lbfgs_80x64": (4e-2, 20.0),       # 2.5e-2, 34.7 dB (fp32 leaps by 7.5 grey levels rms in iteration 3, the
+                                                  # TF32 arithmetic crawls by 3.1: the two can differ by at most ~24 dB)
     "vgg19_deep_taps_avg_64x96": (1.5e-2, 40.0),  # 6.9e-3, 62.0 dB (ReLU-sign flips remain with average pooling, 18 layers deep)
     "vgg19_same_layer_taps_64x64": (7e-2, 40.0),  # 4.3e-2, 55.5 dB
 }
