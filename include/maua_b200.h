@@ -51,6 +51,14 @@ typedef enum maua_status {
  * MAUA_IMPL_TC picks per launch. */
 #define MAUA_IMPL_TC_1CTA 2
 #define MAUA_IMPL_TC_2CTA 3
+/* Exact-arithmetic mode: every GEMM-shaped launch runs with un-rounded FP32 operands on the CUDA cores (chunk sums in
+ * fp32 FFMA, chunks added in fp64 -- csrc/conv_fp32.cu), the Gram / covariance is centred like loss.py:87-89 and summed
+ * in fp64, and no activation / gradient / weight is rounded to TF32 anywhere.  Everything else -- plan logic, ReLU sign
+ * bitmaps, max-pool arg-max recomputation, folded StyleLoss backward, pooling, image-side tail, optimizers -- is the
+ * code the product path runs.  ~30x slower than MAUA_IMPL_TC; it exists to show (tests) that the product path differs
+ * from the reference's fp32 results by TF32 operand rounding and nothing else, and as a "reference-grade" option
+ * (MAUA_PRECISION=fp32). */
+#define MAUA_IMPL_FP32 4
 
 MAUA_API int maua_abi_version(void);
 MAUA_API const char* maua_last_error(void);
@@ -66,6 +74,9 @@ MAUA_API int maua_device_check(int device);
  *   dgrad = 1: out[ci][tap*Cout + co] = w[co][ci][2-ky][2-kx]  (input-gradient: rotated + transposed) */
 MAUA_API int maua_prep_conv_weights(const float* w_oihw, float* out, int cout, int cin, int dgrad,
                                     maua_stream_t stream);
+/* Same layouts with the TF32 rounding optional (round_tf32 = 0: the operands of MAUA_IMPL_FP32). */
+MAUA_API int maua_prep_conv_weights_ex(const float* w_oihw, float* out, int cout, int cin, int dgrad, int round_tf32,
+                                       maua_stream_t stream);
 MAUA_API int maua_nchw_to_nhwc(const float* src, float* dst, int b, int c, int h, int w, int round_tf32,
                                maua_stream_t stream);
 MAUA_API int maua_nhwc_to_nchw(const float* src, float* dst, int b, int c, int h, int w, maua_stream_t stream);
@@ -309,7 +320,13 @@ MAUA_API int maua_plan_tap_gram(maua_plan_t* plan, int tap, float* dst, int* c, 
 /* Copy the feature map of tap `tap` from the last forward (NHWC [H_l][W_l][C]) into dst (NULL: query the shape). */
 MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, float* dst, int* h, int* w, int* c,
                                    maua_stream_t stream);
-/* Switch the GEMM-shaped kernels of this plan between MAUA_IMPL_TC and MAUA_IMPL_REF (tests only). */
+/* Copy the output of stack entry `entry` (conv entries: the post-ReLU activation, models.py:129-130; pool entries: the
+ * pooled map) from the last forward, NHWC [*h][*w][*c]; dst NULL queries the shape.  These are the tensors the backward
+ * pass derives its ReLU masks and max-pool arg-max decisions from (tests: decision-level comparison with the oracle). */
+MAUA_API int maua_plan_entry_output(maua_plan_t* plan, int entry, float* dst, int* h, int* w, int* c, int* is_pool,
+                                    maua_stream_t stream);
+/* Switch the GEMM-shaped kernels of this plan between MAUA_IMPL_TC (default), MAUA_IMPL_REF / _1CTA / _2CTA (tests) and
+ * MAUA_IMPL_FP32 (exact arithmetic; allocates un-rounded GEMM-layout weight copies on first use). */
 MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
 /* Fused pooling: when enabled, MaxPool2d / AvgPool2d(2,2) (models.py:119-122) is computed in the epilogue of the
  * convolution that produces its input instead of a separate pass over the activation (same arithmetic, bit for bit).

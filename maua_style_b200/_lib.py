@@ -18,6 +18,7 @@ MAUA_IMPL_TC = 0
 MAUA_IMPL_REF = 1
 MAUA_IMPL_TC_1CTA = 2
 MAUA_IMPL_TC_2CTA = 3
+MAUA_IMPL_FP32 = 4  # exact arithmetic (csrc/conv_fp32.cu): parity checks and MAUA_PRECISION=fp32
 MAUA_MAX_LAYERS = 32
 MAUA_MAX_TAPS = 16
 MODE_NONE, MODE_CAPTURE, MODE_LOSS = 0, 1, 2

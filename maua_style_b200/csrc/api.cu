@@ -80,6 +80,12 @@ MAUA_API int maua_prep_conv_weights(const float* w, float* out, int cout, int ci
     MAUA_REQUIRE(w && out && cout > 0 && cin > 0, "maua_prep_conv_weights: bad arguments");
     return prep_weights_launch(w, out, cout, cin, dgrad, 1, (cudaStream_t)stream);
 }
+MAUA_API int maua_prep_conv_weights_ex(const float* w, float* out, int cout, int cin, int dgrad, int round_tf32,
+                                       maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(w && out && cout > 0 && cin > 0, "maua_prep_conv_weights_ex: bad arguments");
+    return prep_weights_launch(w, out, cout, cin, dgrad, round_tf32, (cudaStream_t)stream);
+}
 MAUA_API int maua_nchw_to_nhwc(const float* src, float* dst, int b, int c, int h, int w, int round_tf32,
                                maua_stream_t stream) {
     MAUA_ENTRY_GUARD();
@@ -99,9 +105,8 @@ MAUA_API int maua_conv3x3_fwd(const float* x, const float* wg, const float* bias
     ConvArgs a;
     a.B = b; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ntaps = 9;
     a.in = x; a.wg = wg;
-    a.ep.out = y; a.ep.bias = bias; a.ep.relu = relu; a.ep.round = 1;
-    a.force_cg = impl == MAUA_IMPL_TC_1CTA ? 1 : (impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
-    return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
+    a.ep.out = y; a.ep.bias = bias; a.ep.relu = relu; a.ep.round = impl == MAUA_IMPL_FP32 ? 0 : 1;
+    return conv_dispatch(a, impl, (cudaStream_t)stream);
 }
 
 MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int b, int h, int w, int cout, int cin,
@@ -123,11 +128,10 @@ MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int
     a.ep.out = gx; a.ep.bias = aux_bias; a.ep.mask_src = mask_src;
     a.ep.cont_f = cont_f; a.ep.cont_t = cont_t; a.ep.cont_coef = cont_coef;
     a.ep.relu = 0; a.ep.round = round_tf32;
-    a.force_cg = impl == MAUA_IMPL_TC_1CTA ? 1 : (impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
     if (!gy && !aux_f) {
         MAUA_REQUIRE(false, "maua_conv3x3_dgrad: nothing to compute (no gy and no aux term)");
     }
-    return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
+    return conv_dispatch(a, impl, (cudaStream_t)stream);
 }
 
 MAUA_API int maua_relu_mask_bits(const float* x, uint32_t* bits, long npix, int c, maua_stream_t stream) {
@@ -152,8 +156,7 @@ MAUA_API int maua_conv3x3_dgrad_bits(const float* gy, const float* wd, float* gx
     if (aux_f) { a.K2 = cin; a.in2 = aux_f; a.w2 = aux_d; }
     a.ep.out = gx; a.ep.bias = aux_bias; a.ep.mask_bits = mask_bits;
     a.ep.relu = 0; a.ep.round = round_tf32;
-    a.force_cg = impl == MAUA_IMPL_TC_1CTA ? 1 : (impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
-    return impl == MAUA_IMPL_REF ? conv_ref_launch(a, (cudaStream_t)stream) : conv_tc_launch(a, (cudaStream_t)stream);
+    return conv_dispatch(a, impl, (cudaStream_t)stream);
 }
 
 MAUA_API int maua_conv_first_fwd(const float* img, const float* w_oihw, const float* bias, float* y, int b, int h,
@@ -175,7 +178,7 @@ MAUA_API int maua_conv_first_dgrad(const float* gy, const float* w_oihw, float* 
     t.temp_coef = temp_target ? temp_coef : nullptr;
     float* T = reinterpret_cast<float*>(workspace);
     float* wt = T + (((size_t)b * h * w * 32 + 63) & ~size_t(63));
-    int rc = conv_first_dgrad_prep_weights(w_oihw, wt, cout, (cudaStream_t)stream);
+    int rc = conv_first_dgrad_prep_weights(w_oihw, wt, cout, 1, (cudaStream_t)stream);
     if (rc) return rc;
     return conv_first_dgrad_launch(gy, wt, gimg, b, h, w, cout, t, T, MAUA_IMPL_TC, (cudaStream_t)stream);
 }
@@ -187,7 +190,7 @@ MAUA_API size_t maua_conv_first_dgrad_workspace_bytes(int b, int h, int w) {
 MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream) {
     MAUA_ENTRY_GUARD();
     MAUA_REQUIRE(x && y, "maua_pool2x2_fwd: null pointer");
-    return pool_fwd_launch(x, y, b, h, w, c, avg, (cudaStream_t)stream);
+    return pool_fwd_launch(x, y, b, h, w, c, avg, 1, (cudaStream_t)stream);
 }
 MAUA_API int maua_pool2x2_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w,
                               int c, int avg, int round_tf32, maua_stream_t stream) {

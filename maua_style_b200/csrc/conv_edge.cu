@@ -121,7 +121,7 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
 // Same kernel with the 27 x 64 multiply-adds issued as packed FFMA2 (fma.rn.f32x2, sm_100): two independent
 // round-to-nearest FMAs per instruction, i.e. the same results bit for bit at half the fma-pipe issue slots (the plain
 // kernel is bound by them: 1728 FFMA per thread and tile, 62 % of the scalar-FFMA peak in the round-1 ncu capture).
-// Opt-in (MAUA_CONV1_FFMA2=1) until it has been verified on hardware.
+// Default since round 2 (bit-identity verified on B200, tests/test_zz_arch_gpu.py); MAUA_CONV1_FFMA2=0 selects the scalar kernel.
 __global__ void __launch_bounds__(256)
 conv_first_fwd_f2_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ out, uint16_t* __restrict__ mask16, int B, int H, int W, int do_round) {
@@ -214,14 +214,15 @@ conv_first_fwd_f2_kernel(const float* __restrict__ img, const float* __restrict_
 // backward
 // ------------------------------------------------------------------------------------------------
 // wt[n][co], n = (ky*3 + kx)*3 + ci (27 rows, padded with zeros to 32): B operand of the per-pixel contraction
-__global__ void first_dgrad_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout) {
+__global__ void first_dgrad_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int do_round) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32 * Cout) return;
     const int n = i / Cout, co = i % Cout;
     float v = 0.f;
     if (n < 27) {
         const int tap = n / 3, ci = n % 3;
-        v = round_tf32(w[((long)co * 3 + ci) * 9 + tap]);
+        v = w[((long)co * 3 + ci) * 9 + tap];
+        if (do_round) v = round_tf32(v);
     }
     wt[i] = v;
 }
@@ -300,8 +301,8 @@ int conv_first_fwd_launch(const float* img, const float* w, const float* bias, f
     MAUA_REQUIRE(Cout == 64, "conv_first_fwd: the image layer must have 64 output channels (got %d)", Cout);
     const long ntiles = (long)B * ((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H);
     long blocks = ntiles > 148L * 8 ? 148L * 8 : ntiles;
-    const char* f2 = getenv("MAUA_CONV1_FFMA2");
-    if (f2 && atoi(f2) != 0)
+    const char* f2 = getenv("MAUA_CONV1_FFMA2");  // packed FFMA2 by default (bit-identical, verified on B200); 0: scalar FFMA
+    if (!f2 || atoi(f2) != 0)
         conv_first_fwd_f2_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
     else
         conv_first_fwd_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
@@ -313,9 +314,9 @@ size_t conv_first_dgrad_workspace_bytes(int B, int H, int W) {
     return ((size_t)B * H * W * 32 + 32 * 64) * sizeof(float) + 256;
 }
 
-int conv_first_dgrad_prep_weights(const float* w, float* wt, int Cout, cudaStream_t st) {
+int conv_first_dgrad_prep_weights(const float* w, float* wt, int Cout, int do_round, cudaStream_t st) {
     MAUA_REQUIRE(Cout == 64, "conv_first_dgrad: the image layer must have 64 output channels (got %d)", Cout);
-    first_dgrad_weights_kernel<<<(32 * Cout + 255) / 256, 256, 0, st>>>(w, wt, Cout);
+    first_dgrad_weights_kernel<<<(32 * Cout + 255) / 256, 256, 0, st>>>(w, wt, Cout, do_round);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
@@ -328,7 +329,7 @@ int conv_first_dgrad_launch(const float* gout, const float* wt, float* gimg, int
     a.B = B; a.H = H; a.W = W; a.Cin = Cout; a.Cout = 32; a.ntaps = 1;
     a.in = gout; a.wg = wt;
     a.ep.out = T; a.ep.round = 0;
-    int rc = impl == 1 ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
+    int rc = conv_dispatch(a, impl, st);
     if (rc) return rc;
     const long ntiles = (long)B * ((W + GT - 1) / GT) * ((H + GT - 1) / GT);
     long blocks = ntiles > 148L * 8 ? 148L * 8 : ntiles;

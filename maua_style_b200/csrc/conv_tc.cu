@@ -725,7 +725,7 @@ int conv_ref_launch(const ConvArgs& a, cudaStream_t st) {
         const int rc = relu_mask_bits_launch(a.ep.out, a.ep.mask_out, (long)a.B * a.H * a.W, a.Cout, st);
         if (rc) return rc;
     }
-    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, st);
+    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, a.ep.round, st);
     return MAUA_OK;
 }
 

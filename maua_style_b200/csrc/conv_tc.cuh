@@ -58,6 +58,15 @@ int relu_mask_bits_launch(const float* x, uint32_t* bits, long npix, int C, cuda
 
 int conv_tc_launch(const ConvArgs& a, cudaStream_t st);   // tcgen05 / TMEM / TMA path
 int conv_ref_launch(const ConvArgs& a, cudaStream_t st);  // naive SIMT cross-check (debug only)
+int conv_fp32_launch(const ConvArgs& a, cudaStream_t st); // exact arithmetic: FP32 operands, fp64 chunk sums (conv_fp32.cu)
+
+// impl: MAUA_IMPL_* of include/maua_b200.h (0 tcgen05, 1 naive SIMT, 2 / 3 tcgen05 with forced CTA grouping, 4 exact FP32)
+inline int conv_dispatch(ConvArgs a, int impl, cudaStream_t st) {
+    if (impl == 1) return conv_ref_launch(a, st);
+    if (impl == 4) return conv_fp32_launch(a, st);
+    a.force_cg = impl == 2 ? 1 : (impl == 3 ? 2 : 0);
+    return conv_tc_launch(a, st);
+}
 
 // conv1_1 forward: NCHW 3-channel image -> NHWC Cout, bias + ReLU, fp32 FFMA (K = 27).
 int conv_first_fwd_launch(const float* img, const float* w /*[Cout][3][3][3]*/, const float* bias, float* out,
@@ -75,7 +84,7 @@ struct ImageTail {
 };
 // wt: [32][Cout] from conv_first_dgrad_prep_weights; T: scratch of B*H*W*32 floats (the per-pixel tap contraction)
 size_t conv_first_dgrad_workspace_bytes(int B, int H, int W);
-int conv_first_dgrad_prep_weights(const float* w_oihw, float* wt, int Cout, cudaStream_t st);
+int conv_first_dgrad_prep_weights(const float* w_oihw, float* wt, int Cout, int do_round, cudaStream_t st);
 int conv_first_dgrad_launch(const float* gout, const float* wt, float* gimg, int B, int H, int W, int Cout,
                             const ImageTail& tail, float* T, int impl, cudaStream_t st);
 

@@ -47,7 +47,7 @@ struct GramCfg {
     static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 + 256;
 };
 
-// NACC > 1 (opt-in, MAUA_GRAM_NACC=4): pipeline stage ks accumulates into TMEM accumulator ks % NACC and the epilogue adds
+// NACC > 1 (default 4): pipeline stage ks accumulates into TMEM accumulator ks % NACC and the epilogue adds
 // the NACC accumulators.  The tensor core's fp32 accumulate truncates, so the error of a sum grows linearly with the
 // length of the accumulation chain (measured: 2.6e-5 relative at relu1_1 / 1024^2, ~890 dependent MMAs per CTA);
 // NACC interleaved chains are NACC times shorter.  This matters for the covariance, where sum(xy) - P mu mu^T cancels.
@@ -192,6 +192,40 @@ __global__ void gram_ref_kernel(const float* __restrict__ f, long P, int C, floa
     if (c < C && d < C) out[(size_t)c * C + d] = acc;
 }
 
+// Exact-arithmetic Gram / covariance (MAUA_IMPL_FP32): operands are the stored fp32 features, centred on load like the
+// reference does (loss.py:87-89: x - x.mean) when `mean` is given; products of 16 pixels are summed with FFMA in fp32 and
+// those chunk sums are added in fp64.  Pixels are split over blockIdx.z; the fp64 partials are added in a fixed order.
+__global__ void gram_exact_kernel(const float* __restrict__ f, long P, int C, const float* __restrict__ mean,
+                                  double* __restrict__ dpartial) {
+    __shared__ float sa[16][17], sb[16][17];
+    const int c = blockIdx.y * 16 + threadIdx.y, d = blockIdx.x * 16 + threadIdx.x;
+    const int ca = blockIdx.y * 16 + threadIdx.x;  // channel this thread loads for the A tile ([p][c], coalesced over c)
+    const float mu_a = (mean && ca < C) ? mean[ca] : 0.f;
+    const float mu_b = (mean && d < C) ? mean[d] : 0.f;
+    const long p_begin = P * blockIdx.z / gridDim.z, p_end = P * (blockIdx.z + 1) / gridDim.z;
+    double acc = 0.0;
+    for (long p0 = p_begin; p0 < p_end; p0 += 16) {
+        const long pp = p0 + threadIdx.y;
+        const bool live = pp < p_end;
+        sa[threadIdx.y][threadIdx.x] = (live && ca < C) ? f[pp * C + ca] - mu_a : 0.f;  // [p][c]
+        sb[threadIdx.y][threadIdx.x] = (live && d < C) ? f[pp * C + d] - mu_b : 0.f;    // [p][d]
+        __syncthreads();
+        float part = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) part = fmaf(sa[k][threadIdx.y], sb[k][threadIdx.x], part);
+        acc += (double)part;
+        __syncthreads();
+    }
+    if (c < C && d < C) dpartial[((size_t)blockIdx.z * C + c) * C + d] = acc;
+}
+__global__ void gram_exact_sum_kernel(const double* __restrict__ dpartial, int S, long total, float* __restrict__ out) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < S; ++k) s += dpartial[(size_t)k * total + i];
+        out[i] = (float)s;
+    }
+}
+
 // Sums the split-K partials in a fixed order (deterministic), mirrors the upper-triangular tiles into the lower ones,
 // applies the covariance correction and the 1/(C P) normalisation.  Block = (256 / G) consecutive outputs x G interleaved
 // groups of partials (G grows with the split count so that short and long reductions both keep the loads coalesced and
@@ -306,9 +340,11 @@ int launch_gram_nacc(const CUtensorMap& tm, const GramParams& p, int ntiles, cud
 
 template <int BN, bool OFFDIAG>
 int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, int ntiles, cudaStream_t st) {
-    const char* f = getenv("MAUA_GRAM_NACC");  // opt-in: interleaved accumulation chains (see gram_tc_kernel)
-    if (f && atoi(f) == 4) return launch_gram_nacc<BN, OFFDIAG, 4>(tm, p, ntiles, st);
-    return launch_gram_nacc<BN, OFFDIAG, 1>(tm, p, ntiles, st);
+    // four interleaved accumulation chains by default (see gram_tc_kernel; verified on B200 in round 2: covariance error
+    // vs fp64 1.0e-3 -> 2.2e-4 at 1024^2, same run time); MAUA_GRAM_NACC=1 selects the single chain
+    const char* f = getenv("MAUA_GRAM_NACC");
+    if (f && atoi(f) == 1) return launch_gram_nacc<BN, OFFDIAG, 1>(tm, p, ntiles, st);
+    return launch_gram_nacc<BN, OFFDIAG, 4>(tm, p, ntiles, st);
 }
 
 }  // namespace
@@ -340,7 +376,26 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
         if (rc) return rc;
     }
     int full = 0;
-    if (impl == 1) {
+    bool centred = false;
+    if (impl == 4) {
+        // workspace: fp64 partials in the first float slots, the fp32 sums in the last float slot of the partial area
+        const int slots = kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1;
+        MAUA_REQUIRE(slots >= 3, "gram (exact mode): channel count %d leaves no room for fp64 partials", C);
+        int S = (slots - 1) / 2;
+        if ((long)S > (P + 255) / 256) S = (int)((P + 255) / 256);
+        double* dpartial = reinterpret_cast<double*>(workspace);
+        const long cc = (long)C * C;
+        float* sums = partial + (size_t)(slots - 1) * cc;
+        gram_exact_kernel<<<dim3((C + 15) / 16, (C + 15) / 16, S), dim3(16, 16), 0, st>>>(f, P, C, use_cov ? mean_out : nullptr,
+                                                                                         dpartial);
+        MAUA_CUDA_CHECK(cudaGetLastError());
+        gram_exact_sum_kernel<<<(int)((cc + 255) / 256 > 592 ? 592 : (cc + 255) / 256), 256, 0, st>>>(dpartial, S, cc, sums);
+        MAUA_CUDA_CHECK(cudaGetLastError());
+        partial = sums;
+        nsplit = 1;
+        full = 1;
+        centred = true;
+    } else if (impl == 1) {
         nsplit = 1;
         full = 1;
         gram_ref_kernel<<<dim3((C + 15) / 16, (C + 15) / 16), dim3(16, 16), 0, st>>>(f, P, C, partial);
@@ -367,7 +422,7 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
         tgt = fuse->target; dif = fuse->diff; lout = fuse->loss_out; sc = fuse->value_scale;
         rp = fuse->rs.partials; cnt = fuse->rs.counter;
     }
-    const float* mu = use_cov ? mean_out : nullptr;
+    const float* mu = (use_cov && !centred) ? mean_out : nullptr;
 #define MAUA_FINALIZE(GG) gram_finalize_kernel<GG><<<fgrid, kReduceThreads, 0, st>>>(partial, nsplit, C, P, full, mu, gram, tgt, dif, sc, lout, rp, cnt)
     if (G == 8) MAUA_FINALIZE(8); else if (G == 4) MAUA_FINALIZE(4); else if (G == 2) MAUA_FINALIZE(2); else MAUA_FINALIZE(1);
 #undef MAUA_FINALIZE

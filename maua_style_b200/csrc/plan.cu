@@ -40,6 +40,7 @@ struct Entry {
     float* wd = nullptr;       // dgrad GEMM weights    [cin][9*cout]
     float* bias = nullptr;
     float* wt1 = nullptr;      // first conv only: [32][cout] tap-column weights of the dgrad contraction
+    float *wg32 = nullptr, *wd32 = nullptr, *wt1_32 = nullptr;  // un-rounded copies, MAUA_IMPL_FP32 only (made on demand)
     // per forward
     int H = 0, W = 0, C = 0;   // output extent
     float* out = nullptr;      // arena pointer
@@ -71,6 +72,7 @@ struct BwdPrep {
     int C[MAUA_MAX_TAPS];
     float inv_c3p[MAUA_MAX_TAPS];  // 4 / (C^3 P)
     int slot[MAUA_MAX_TAPS];
+    int do_round;
 };
 __global__ void bwd_prep_kernel(const float* __restrict__ coefs, float* __restrict__ coef2, const BwdPrep bp) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < bp.n_slots)
@@ -82,7 +84,7 @@ __global__ void bwd_prep_kernel(const float* __restrict__ coefs, float* __restri
     const float* __restrict__ diff = bp.diff[j];
     float* __restrict__ aux = bp.aux_d[j];
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
-        aux[i] = round_tf32(k * diff[i]);
+        aux[i] = bp.do_round ? round_tf32(k * diff[i]) : k * diff[i];
 }
 
 struct CoefParams {
@@ -126,7 +128,7 @@ struct maua_plan {
     std::vector<Entry> entries;
     std::vector<Tap> taps;
     int avg_pool = 0;
-    bool fuse_pool = false;       // pool inside the producing conv's epilogue (opt-in: MAUA_FUSE_POOL=1 at plan creation)
+    bool fuse_pool = true;        // pool inside the producing conv's epilogue (MAUA_FUSE_POOL=0 at plan creation: separate pass)
     size_t weight_bytes = 0;
     // workspaces
     float* arena = nullptr;
@@ -320,7 +322,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
             if (e == cudaSuccess) e = cudaMemcpy(en.bias, d->biases[i], (size_t)en.cout * sizeof(float), cudaMemcpyDefault);
             if (i == 0) {
                 alloc((void**)&en.wt1, (size_t)32 * en.cout * sizeof(float));
-                if (e == cudaSuccess && conv_first_dgrad_prep_weights(en.w_raw, en.wt1, en.cout, 0)) ok = false;
+                if (e == cudaSuccess && conv_first_dgrad_prep_weights(en.w_raw, en.wt1, en.cout, 1, 0)) ok = false;
             }
             if (e == cudaSuccess && i > 0) {
                 if (prep_weights_launch(en.w_raw, en.wg, en.cout, en.cin, 0, 1, 0) ||
@@ -411,6 +413,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     DeviceGuard guard(p->device);
     for (auto& e : p->entries) {
         cudaFree(e.w_raw); cudaFree(e.wg); cudaFree(e.wd); cudaFree(e.bias); cudaFree(e.wt1);
+        cudaFree(e.wg32); cudaFree(e.wd32); cudaFree(e.wt1_32);
     }
     for (auto& t : p->taps) {
         cudaFree(t.gram); cudaFree(t.diff); cudaFree(t.aux_d); cudaFree(t.mean); cudaFree(t.aux_bias); cudaFree(t.gram_ws);
@@ -429,7 +432,30 @@ MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* p) {
 }
 
 MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
-    MAUA_REQUIRE(p && impl >= MAUA_IMPL_TC && impl <= MAUA_IMPL_TC_2CTA, "maua_plan_set_impl: bad arguments");
+    MAUA_REQUIRE(p && impl >= MAUA_IMPL_TC && impl <= MAUA_IMPL_FP32, "maua_plan_set_impl: bad arguments");
+    if (impl == MAUA_IMPL_FP32) {
+        // un-rounded GEMM-layout weights for the exact-arithmetic kernels, made once
+        DeviceGuard guard(p->device);
+        for (auto& e : p->entries) {
+            if (e.pool) continue;
+            const size_t wn = (size_t)e.cout * e.cin * 9;
+            if (e.image_layer) {
+                if (e.wt1_32) continue;
+                MAUA_CUDA_CHECK(cudaMalloc(&e.wt1_32, (size_t)32 * e.cout * sizeof(float)));
+                int rc = conv_first_dgrad_prep_weights(e.w_raw, e.wt1_32, e.cout, 0, 0);
+                if (rc) return rc;
+            } else {
+                if (e.wg32) continue;
+                MAUA_CUDA_CHECK(cudaMalloc(&e.wg32, wn * sizeof(float)));
+                MAUA_CUDA_CHECK(cudaMalloc(&e.wd32, wn * sizeof(float)));
+                p->weight_bytes += 2 * wn * sizeof(float);
+                int rc = prep_weights_launch(e.w_raw, e.wg32, e.cout, e.cin, 0, 0, 0);
+                if (!rc) rc = prep_weights_launch(e.w_raw, e.wd32, e.cout, e.cin, 1, 0, 0);
+                if (rc) return rc;
+            }
+        }
+        MAUA_CUDA_CHECK(cudaDeviceSynchronize());
+    }
     p->impl = impl;
     return MAUA_OK;
 }
@@ -502,6 +528,8 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     memset(p->factors, 0, sizeof(p->factors));
     if (iio) p->img_io = *iio; else memset(&p->img_io, 0, sizeof(p->img_io));
     const long img_elems = 3L * H * W;
+    const bool exact = p->impl == MAUA_IMPL_FP32;  // nothing is rounded to TF32 in the exact-arithmetic mode
+    const int rnd = exact ? 0 : 1;
     p->prof.clear();
     p->ev_used = 0;
     prof_mark(p, st, "begin_fwd", -1, 0, 0);
@@ -556,7 +584,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
         Entry& e = p->entries[i];
         float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
         if (e.image_layer) {
-            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, 1, st))) return rc;
+            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, rnd, st))) return rc;
             if (hand_off)
                 MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
         } else if (e.pool) {
@@ -567,22 +595,20 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             }
             // a pooled map is not needed again by this stage (the backward pass reads the pre-pool activation), so at a
             // stage boundary it is written straight into the next stage's memory
-            if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, st))) return rc;
+            if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
         } else {
             ConvArgs a;
             a.B = 1; a.H = e.H; a.W = e.W; a.Cin = e.cin; a.Cout = e.cout; a.ntaps = 9;
-            a.in = cur; a.wg = e.wg;
-            a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = 1;
+            a.in = cur; a.wg = exact ? e.wg32 : e.wg;
+            a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = rnd;
             a.ep.mask_out = e.bits;
-            a.force_cg = p->impl == MAUA_IMPL_TC_1CTA ? 1 : (p->impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
                 a.ep.pool_avg = p->avg_pool;
                 pool_done = true;
             }
-            rc = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
-            if (rc) return rc;
+            if ((rc = conv_dispatch(a, p->impl, st))) return rc;
         }
         p->launches_fwd++;
         {
@@ -697,6 +723,8 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     const int H = p->H, W = p->W;
     p->launches_bwd = 0;
     int rc;
+    const bool exact = p->impl == MAUA_IMPL_FP32;
+    const int rnd = exact ? 0 : 1;
     prof_mark(p, st, "begin_bwd", -1, 0, 0);
 
     // scaled coefficients (content / temporal: 2/numel) and the style taps' scaled (G - A) matrices, one launch
@@ -704,6 +732,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         BwdPrep bp;
         memset(&bp, 0, sizeof(bp));
         bp.n_slots = nt + 2;
+        bp.do_round = rnd;
         for (int i = 0; i < nt + 2; ++i) bp.factors[i] = p->factors[i];
         for (int t = 0; t < nt; ++t) {
             Tap& tp = p->taps[t];
@@ -746,8 +775,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     };
     auto run_conv = [&](ConvArgs& a) -> int {
         p->launches_bwd++;
-        a.force_cg = p->impl == MAUA_IMPL_TC_1CTA ? 1 : (p->impl == MAUA_IMPL_TC_2CTA ? 2 : 0);
-        const int r = p->impl == MAUA_IMPL_REF ? conv_ref_launch(a, st) : conv_tc_launch(a, st);
+        const int r = conv_dispatch(a, p->impl, st);
         const double px = (double)a.H * a.W;
         // algorithmic work: dgrad GEMM + StyleLoss backward GEMM; bytes: gradient in + out, mask / feature read
         prof_mark(p, st, a.ntaps ? "conv_dgrad" : "tap_grad", a.Cout, 2.0 * (a.ntaps * (double)a.Cin + a.K2) * a.Cout * px,
@@ -787,7 +815,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             addend = t.ep.out;
         }
         float* outb = take_buf();
-        if ((rc = pool_bwd_launch(ep_.out, grad_top, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, 1, st))) return rc;
+        if ((rc = pool_bwd_launch(ep_.out, grad_top, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st))) return rc;
         p->launches_bwd++;
         prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
         gm = outb;
@@ -801,7 +829,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             ConvArgs a;
             a.B = 1; a.H = e.H; a.W = e.W; a.Cin = 32; a.Cout = e.C; a.ntaps = 0; a.K2 = 0;
             add_taps(a, e, style, content, ci);
-            a.ep.out = take_buf(); a.ep.mask_bits = e.bits; a.ep.round = 1; a.ep.addend = grad_top;
+            a.ep.out = take_buf(); a.ep.mask_bits = e.bits; a.ep.round = rnd; a.ep.addend = grad_top;
             if (style) {
                 if ((rc = run_conv(a))) return rc;
             } else {
@@ -828,10 +856,10 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         ConvArgs a;
         a.B = 1; a.H = ec.H; a.W = ec.W;
         a.Cin = ec.cout; a.Cout = ec.cin; a.ntaps = 9;
-        a.in = gm; a.wg = ec.wd;
+        a.in = gm; a.wg = exact ? ec.wd32 : ec.wd;
         if (!through_pool) {
             add_taps(a, ep_, style, content, ci);
-            a.ep.out = take_buf(); a.ep.mask_bits = ep_.bits; a.ep.round = 1;
+            a.ep.out = take_buf(); a.ep.mask_bits = ep_.bits; a.ep.round = rnd;
             if ((rc = run_conv(a))) return rc;
             gm = a.ep.out;
         } else {
@@ -851,7 +879,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             }
             float* outb = take_buf();
             if (outb == gpool || outb == addend) outb = take_buf();
-            if ((rc = pool_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, 1, st))) return rc;
+            if ((rc = pool_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st))) return rc;
             p->launches_bwd++;
             prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
             gm = outb;
@@ -867,7 +895,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         if (gm && gm_entry == 0) {
             ConvArgs a;
             a.B = 1; a.H = e0.H; a.W = e0.W; a.Cin = e0.cout; a.Cout = e0.cin; a.ntaps = 9;
-            a.in = gm; a.wg = e0.wd;
+            a.in = gm; a.wg = exact ? e0.wd32 : e0.wd;
             a.ep.out = grad_image; a.ep.round = 0;
             if ((rc = run_conv(a))) return rc;
         } else {
@@ -891,13 +919,15 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     if (gm && gm_entry == 0) {
         float* T = take_buf();
         if (T == gm) T = take_buf();
-        if ((rc = conv_first_dgrad_launch(gm, e0.wt1, grad_image, 1, H, W, e0.cout, tail, T, p->impl, st))) return rc;
+        if ((rc = conv_first_dgrad_launch(gm, exact ? e0.wt1_32 : e0.wt1, grad_image, 1, H, W, e0.cout, tail, T, p->impl, st)))
+            return rc;
         p->launches_bwd += 2;
         prof_mark(p, st, "conv_first_dgrad", 0, 2.0 * 27 * e0.cout * H * W, 4.0 * (e0.cout + 6) * H * W);
     } else {
         // no feature-space loss is active: only TV / temporal terms (or nothing at all)
         MAUA_CUDA_CHECK(cudaMemsetAsync(p->gbuf[0], 0, (size_t)H * W * e0.cout * sizeof(float), st));
-        if ((rc = conv_first_dgrad_launch(p->gbuf[0], e0.wt1, grad_image, 1, H, W, e0.cout, tail, p->gbuf[1], p->impl, st)))
+        if ((rc = conv_first_dgrad_launch(p->gbuf[0], exact ? e0.wt1_32 : e0.wt1, grad_image, 1, H, W, e0.cout, tail, p->gbuf[1],
+                                          p->impl, st)))
             return rc;
         p->launches_bwd += 2;
     }
@@ -968,6 +998,21 @@ MAUA_API int maua_plan_tap_gram(maua_plan_t* p, int tap, float* dst, int* c, mau
         MAUA_CUDA_CHECK(cudaMemcpyAsync(dst, tp.gram, (size_t)tp.C * tp.C * sizeof(float), cudaMemcpyDeviceToDevice,
                                         (cudaStream_t)stream));
     }
+    return MAUA_OK;
+}
+
+MAUA_API int maua_plan_entry_output(maua_plan_t* p, int entry, float* dst, int* h, int* w, int* c, int* is_pool,
+                                    maua_stream_t stream) {
+    MAUA_REQUIRE(p && entry >= 0 && entry < (int)p->entries.size(), "maua_plan_entry_output: bad entry index");
+    const Entry& e = p->entries[entry];
+    MAUA_REQUIRE(entry <= p->last_entry, "maua_plan_entry_output: entry was not reached by the last forward");
+    if (h) *h = e.H;
+    if (w) *w = e.W;
+    if (c) *c = e.C;
+    if (is_pool) *is_pool = e.pool ? 1 : 0;
+    if (dst)
+        MAUA_CUDA_CHECK(cudaMemcpyAsync(dst, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        (cudaStream_t)stream));
     return MAUA_OK;
 }
 

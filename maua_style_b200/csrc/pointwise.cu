@@ -121,7 +121,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
 // 2x2 stride-2 pooling on NHWC (models.py:119-122); floor semantics drop an odd last row/col.
 // --------------------------------------------------------------------------------------------
 __global__ void pool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H, int W, int C4,
-                                int avg) {
+                                int avg, int do_round) {
     const int PH = H / 2, PW = W / 2;
     const long total = (long)B * PH * PW * C4;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -137,7 +137,7 @@ __global__ void pool_fwd_kernel(const float4* __restrict__ x, float4* __restrict
         if (avg) {
             o.x = 0.25f * (a0.x + a1.x + a2.x + a3.x); o.y = 0.25f * (a0.y + a1.y + a2.y + a3.y);
             o.z = 0.25f * (a0.z + a1.z + a2.z + a3.z); o.w = 0.25f * (a0.w + a1.w + a2.w + a3.w);
-            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            if (do_round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         } else {
             o.x = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x)); o.y = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
             o.z = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z)); o.w = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
@@ -370,12 +370,12 @@ int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
-int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, cudaStream_t st) {
+int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, int do_round, cudaStream_t st) {
     MAUA_REQUIRE(C % 4 == 0, "pool: C %% 4 != 0");
     if (H / 2 == 0 || W / 2 == 0) return MAUA_OK;
     const long total = (long)B * (H / 2) * (W / 2) * (C / 4);
     pool_fwd_kernel<<<grid_for(total, 16), kThreads, 0, st>>>(reinterpret_cast<const float4*>(x),
-                                                              reinterpret_cast<float4*>(y), B, H, W, C / 4, avg);
+                                                              reinterpret_cast<float4*>(y), B, H, W, C / 4, avg, do_round);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

@@ -55,6 +55,18 @@ vgg19_dict = _layer_names(channel_list["VGG-19"])
 _MODES = {"none": _lib.MODE_NONE, "capture": _lib.MODE_CAPTURE, "loss": _lib.MODE_LOSS}
 
 
+def default_impl() -> int:
+    """MAUA_PRECISION=tf32 (default): tcgen05 kernels, TF32 operands / FP32 accumulate -- the arithmetic the reference's own
+    GPU path uses (cuDNN allows TF32 by default).  MAUA_PRECISION=fp32: the exact-arithmetic kernels (csrc/conv_fp32.cu),
+    which reproduce the reference's CPU / fp32 results to ~1e-6 at ~1/30 of the speed."""
+    prec = os.environ.get("MAUA_PRECISION", "tf32").lower()
+    if prec in ("tf32", ""):
+        return _lib.MAUA_IMPL_TC
+    if prec in ("fp32", "exact"):
+        return _lib.MAUA_IMPL_FP32
+    raise ValueError(f"MAUA_PRECISION={prec!r}: expected tf32 or fp32")
+
+
 def _match_architecture(name: str):
     if "prun" in name:  # models.py:249-258: channel list "VGG-16p" (24, 22, 41, 51, 108, ...)
         return "VGG-16p"
@@ -227,9 +239,9 @@ class B200Net(nn.Module):
         self._stages = core.stages
         for st in self._stages:  # a re-used core starts from the library defaults
             st["loss_vec"].zero_()
-            _lib.check(self._lib.maua_plan_set_impl(st["plan"], _lib.MAUA_IMPL_TC), "maua_plan_set_impl")
+            _lib.check(self._lib.maua_plan_set_impl(st["plan"], default_impl()), "maua_plan_set_impl")
             _lib.check(self._lib.maua_plan_set_profile(st["plan"], 0), "maua_plan_set_profile")
-            _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(os.environ.get("MAUA_FUSE_POOL", "0") == "1")),
+            _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(os.environ.get("MAUA_FUSE_POOL", "1") != "0")),
                        "maua_plan_set_fuse_pool")
         self._plan = self._stages[0]["plan"]
         self._loss_vec = torch.zeros(self._n_slots, device=device)
@@ -247,7 +259,10 @@ class B200Net(nn.Module):
 
     def __del__(self):
         # the plans belong to the core (shared with the model cache); dropping the last reference destroys them
-        self._stages, self._plan, self._core = [], None, None
+        try:
+            self.__dict__.update(_stages=[], _plan=None, _core=None)
+        except Exception:  # interpreter shutdown
+            pass
 
     @property
     def n_stages(self) -> int:
@@ -262,7 +277,7 @@ class B200Net(nn.Module):
             _lib.check(self._lib.maua_plan_set_impl(st["plan"], impl), "maua_plan_set_impl")
 
     def set_fuse_pool(self, enable: bool):
-        """Pool inside the producing conv's epilogue instead of a separate pass (csrc/conv_tc.cu; off by default)."""
+        """Pool inside the producing conv's epilogue (csrc/conv_tc.cu, the default) or as a separate pass."""
         for st in self._stages:
             _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(enable)), "maua_plan_set_fuse_pool")
 
@@ -524,6 +539,19 @@ class B200Net(nn.Module):
             out = torch.empty(1, h.value, w.value, c.value, device=st["device"])
             _lib.check(self._lib.maua_plan_tap_feature(st["plan"], t, _lib.ptr(out), C.byref(h), C.byref(w), C.byref(c),
                                                        _lib.stream_ptr()))
+        return out.permute(0, 3, 1, 2).contiguous()
+
+    def entry_output(self, i: int) -> torch.Tensor:
+        """Output of stack entry i (conv: post-ReLU activation, pool: pooled map) from the last forward, NCHW (copy)."""
+        k = next(k for k, st in enumerate(self._stages) if st["begin"] <= i < st["end"])
+        st = self._stages[k]
+        h, w, c, ip = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        with torch.cuda.device(st["device"]):
+            _lib.check(self._lib.maua_plan_entry_output(st["plan"], i - st["begin"], C.c_void_p(0), C.byref(h), C.byref(w),
+                                                        C.byref(c), C.byref(ip), _lib.stream_ptr()))
+            out = torch.empty(1, h.value, w.value, c.value, device=st["device"])
+            _lib.check(self._lib.maua_plan_entry_output(st["plan"], i - st["begin"], _lib.ptr(out), C.byref(h), C.byref(w),
+                                                        C.byref(c), C.byref(ip), _lib.stream_ptr()))
         return out.permute(0, 3, 1, 2).contiguous()
 
     def tap_gram(self, t: int) -> torch.Tensor:

@@ -125,6 +125,79 @@ def test_full_size_feval_vs_fp32_torch_on_device(case, ckpt):
     assert gerr < (3e-3 if pooling == "avg" else 5e-2)
 
 
+@pytest.mark.parametrize("case", ["gram_1style_max", "cov_2styles_max"])
+def test_full_size_exact_mode_vs_fp64_torch_on_device(case, ckpt):
+    """The exact-arithmetic plan (MAUA_IMPL_FP32) at 1024^2 with MAX pooling against the oracle's arithmetic run by torch
+    on the device in fp64: features / targets / losses to ~1e-6 and the image gradient within north_star's 1e-3.  The
+    same oracle in fp32 (cuDNN, TF32 off) is measured against fp64 too: any two fp32 implementations differ by a few
+    arg-max flips among the 25 M pooling windows of this size, which is the floor for this quantity."""
+    from maua_style_b200 import _lib, optim
+
+    cov = case.startswith("cov")
+    style_hws = [(896, 1152), (1152, 896)] if cov else [(S, S)]
+    over = dict(use_covariance=cov, pooling="max")
+    if cov:
+        over["style_blend_weights"] = "3,1"
+    content, styles, init = inputs(style_hws)
+    args, net, losses = ours(ckpt, **over)
+    net.set_impl(_lib.MAUA_IMPL_FP32)
+    optim.set_content_targets(net, content, args)
+    optim.set_style_targets(net, styles, args)
+    for m in losses:
+        m.mode = "loss"
+    x = init.clone().requires_grad_(True)
+    net(x)
+    vals = module_values(losses)
+    total = sum(m.loss for m in losses if not isinstance(m.loss, int))
+    total.backward()
+    for m in losses:
+        m.loss = 0
+    feats = {O.VGG19_RELU_NAMES[ridx]: net.tap_feature(t) for t, (ridx, _) in enumerate(net.taps)}
+    targets = [m.target.clone() for m in net.style_losses]
+    grad = x.grad.clone()
+    del net, losses
+    torch.cuda.empty_cache()
+
+    cfg = O.StyleConfig(content_weight=5.0, temporal_weight=0.0, use_covariance=cov, pooling="max",
+                        style_blend_weights=[3.0, 1.0] if cov else None)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        params = [(w.cuda().to(dt), b.cuda().to(dt)) for w, b in ckpt[2]]
+        onet = O.OracleNet(params, cfg)
+        O.set_content_targets(onet, content.to(dt))
+        O.set_style_targets(onet, [s.to(dt) for s in styles], cfg.blend(len(styles)))
+        for m in onet.losses:
+            m.mode = "loss"
+        taps = {}
+        if dt == torch.float64:
+            with torch.no_grad():
+                onet(init.to(dt), taps=taps)
+            for m in onet.losses:
+                m.loss = 0
+            for nm, f in feats.items():
+                err = rel(f, taps[nm])
+                print(f"exact {case} {S}^2 feature {nm} rel {err:.2e}")
+                assert err < 1e-5, (nm, err)
+            del taps
+            for i, (tg, om) in enumerate(zip(targets, onet.style_losses)):
+                err = rel(tg, om.target)
+                print(f"exact {case} {S}^2 style_target[{i}] rel {err:.2e}")
+                assert err < 1e-5
+        _, ovals, ograd = O.feval(onet, init.to(dt))
+        res[dt] = (ovals, ograd.double())
+        del onet, params
+        torch.cuda.empty_cache()
+    ovals, ograd = res[torch.float64]
+    for v, o in zip(vals, ovals):
+        if o != 0.0:
+            print(f"exact {case} {S}^2 loss: ours {v:.6e} fp64 {o:.6e} rel {abs(v / o - 1):.2e}")
+            assert abs(v / o - 1) < 1e-4
+    gerr = rel(grad, ograd)
+    ferr = rel(res[torch.float32][1], ograd)
+    print(f"exact {case} {S}^2 image-gradient (max pooling) rel vs fp64: ours {gerr:.2e} | torch fp32 (cuDNN, TF32 off) {ferr:.2e}")
+    assert gerr < 1e-3
+
+
 def test_self_target_losses_and_gradient_vanish(ckpt):
     from maua_style_b200 import optim
 

@@ -11,8 +11,6 @@ the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
   vgg19_taps_lbfgs_80x64 ..... style taps relu1_2 / relu3_3 and content tap relu2_2: loss modules directly in front of a
                                pool (their gradient joins the un-pooled gradient) and truncation after relu3_3
 
-(The file sorts last on purpose: it was written after the round's GPU budget was spent, so under `pytest -x` a surprise
-here cannot hide the results of the suites that were verified on the B200.)
 """
 import pytest
 import torch
@@ -141,16 +139,12 @@ def test_variant_optimize_matches_reference_golden(name, tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Opt-in code paths that have not run on a B200 yet (written after the round's GPU budget was spent).  They are off by
-# default in the product and their tests only run with MAUA_TEST_EXPERIMENTAL=1.
+# Round-1 opt-in paths, verified on a B200 at the start of round 2 (gpurun_out r02a: 23 passed) and now the defaults:
+# pooling in the conv epilogue, four interleaved Gram accumulation chains, packed-FFMA2 conv1_1.  Each test pins the new
+# default against the kernel it replaced (still selectable: set_fuse_pool(False), MAUA_GRAM_NACC=1, MAUA_CONV1_FFMA2=0).
 # ---------------------------------------------------------------------------------------------------------------------
-import os  # noqa: E402
-
-experimental = pytest.mark.skipif(os.environ.get("MAUA_TEST_EXPERIMENTAL", "0") != "1",
-                                  reason="opt-in paths not yet verified on hardware: set MAUA_TEST_EXPERIMENTAL=1")
 
 
-@experimental
 @pytest.mark.parametrize("pooling", ["max", "avg"])
 @pytest.mark.parametrize("hw", [(90, 122), (64, 64), (257, 131)])
 def test_fused_pool_epilogue_is_bit_identical_to_the_pool_kernel(pooling, hw, tmp_path):
@@ -185,7 +179,6 @@ def test_fused_pool_epilogue_is_bit_identical_to_the_pool_kernel(pooling, hw, tm
     assert torch.equal(res[0][1], res[1][1])
 
 
-@experimental
 @pytest.mark.parametrize("cov", [False, True])
 def test_interleaved_gram_accumulators_reduce_the_accumulation_error(cov, tmp_path, monkeypatch):
     """MAUA_GRAM_NACC=4 (gram_tc_kernel<.., NACC = 4>): four interleaved TMEM accumulation chains instead of one.  Against
@@ -219,7 +212,6 @@ def test_interleaved_gram_accumulators_reduce_the_accumulation_error(cov, tmp_pa
     assert max(errs["4"]) < (1e-3 if cov else 1e-4)
 
 
-@experimental
 @pytest.mark.parametrize("h,w", [(32, 32), (37, 53), (5, 3), (1024, 1024)])
 def test_conv1_1_ffma2_kernel_is_bit_identical(h, w, monkeypatch):
     """MAUA_CONV1_FFMA2=1 (conv_first_fwd_f2_kernel): the same 27 x 64 round-to-nearest FMAs per pixel, issued as packed
