@@ -15,10 +15,16 @@ The L-BFGS history is filled to 100 pairs during set-up so that the timed steps 
            and reads the updated pastiche + total loss back device->host
   roofline conv3x3 implicit-GEMM kernels (forward + dgrad, the dominant kernel family): algorithmic FLOPs
             / CUDA-event time of those launches, against the measured tensor peak
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on the host cores, bounded sample
+  cpu_baseline  the reference's own CPU path on the host cores, bounded sample
 
-`--impl reference` times the reference's CPU implementation of the same step (the oracle port: the reference is a
-Python package that cannot travel to the GPU box) on all host threads.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref: loss.py / models.py / optim.py as installed by
+__graft_entry__.build()) driving `optim.optimize` with torch.optim.LBFGS / Adam on all host threads; only when that
+directory is absent does it fall back to the oracle port (`kind: "port"`).
+
+Extra legs of the default N = 1 line (each bounded to a few seconds): `sizes` (512^2 and 2048^2), `adam_1024`,
+`covariance_2styles_1024` (BASELINE.json configs[2]), `multires_e2e` (configs[1] as a whole job), `multidevice_2048`
+(configs[3], only when two GPUs are visible) and, at every N, `batch_job` (configs[4]: 8 images per GPU through
+shard.stylize_images, wall clock incl. per-image set-up and D2H).
 """
 from __future__ import annotations
 
@@ -53,6 +59,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch profile JSON here")
     ap.add_argument("--no-multires", action="store_true", help="skip the 256->512->1024 multi-resolution job (configs[1] whole)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (sizes / adam / covariance / batch job / multidevice)")
+    ap.add_argument("--covariance", action="store_true", help="main workload = configs[2]: covariance loss, 2 blended styles")
+    ap.add_argument("--multidevice", default=None, help="run ONLY the layer-wise split leg on these devices, e.g. 0,1 (configs[3])")
+    ap.add_argument("--batch-images", type=int, default=8, help="images per GPU of the batch_job leg")
+    ap.add_argument("--batch-iters", type=int, default=100, help="L-BFGS iterations per image of the batch_job leg")
     ap.add_argument("--streams", type=int, default=1,
                     help="experimental: S independent images per GPU on S streams (batch jobs, BASELINE.json configs[4]); "
                          "prints its own JSON line, the default line is unchanged")
@@ -66,6 +77,35 @@ def peaks():
         return dict(hbm=float(d["hbm_gbs"]), bf16=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
                     bf16_burst=float(d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 matmul 8192^3 on this GPU, in this run: best single call (burst) and a 0.5 s back-to-back loop (sustained)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(int(500.0 / best), 10)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); e1.synchronize()
+        flop = 2.0 * n ** 3
+        return {"burst": flop / (best * 1e-3) / 1e12, "sustained": flop * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
 
 
 def conv_traffic_per_launch(size):
@@ -90,68 +130,116 @@ def workload_config(size, optimizer):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on the host cores
+# reference arm / CPU baseline: the UNMODIFIED reference (baseline/_ref) on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_step_fn(size, optimizer):
+def _reference_rate(size, optimizer, steps, warmup, budget_s):
+    """it/s of the reference's own `optim.optimize` (optim.py:111-255: torch.optim.LBFGS / Adam, its own modules, CPU) on a
+    bounded sample: K timed iterations after W warm-up iterations inside ONE optimize() call, timestamps taken by a
+    forward pre-hook on the reference's network (one closure evaluation = one iteration, optim.py:201-238).  When a full-
+    size iteration does not fit the budget the same job runs on a half / quarter-size image and the rate is scaled by the
+    pixel ratio (convolution cost is linear in pixels)."""
+    from baseline import ref_loader
+    from maua_style_b200 import synthetic as S  # seeded inputs / checkpoint only
+
+    if ref_loader.ref_dir() is None:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_flush_denormal(True)
+    ref = ref_loader.import_reference("stock")
+    tmp = Path(tempfile.mkdtemp(prefix="maua_refarm_"))
+    ckpt = tmp / "vgg19-random.pth"
+    S.save_random_checkpoint(ckpt)
+    rargs = ref_loader.reference_args(ref, tmp, ckpt, gpu="c", optimizer=optimizer)
+    net, losses = ref.models.load_model(rargs)
+
+    def job(sz, n_iters, stamps):
+        content = S.synthetic_image(sz, sz, seed=1, smooth=True)
+        style = S.synthetic_image(sz, sz, seed=2)
+        init = S.synthetic_image(sz, sz, seed=4) * 0.25
+        h = net.register_forward_pre_hook(lambda m, inp: stamps.append(time.perf_counter()))
+        try:
+            ref.optim.optimize(content, [style], init.clone(), n_iters, rargs, net, losses)
+        finally:
+            h.remove()
+
+    # probe: 1 iteration at full size (2 capture forwards + 1 or 2 closure evaluations)
+    stamps = []
+    t0 = time.perf_counter()
+    job(size, 1, stamps)
+    probe = (time.perf_counter() - t0) / 3.0
+    sub, scale = size, 1.0
+    while probe * scale * (steps + warmup + 3) > budget_s and sub >= 256:
+        sub //= 2
+        scale = (sub * sub) / float(size * size)
+    n_iters = steps + warmup + (1 if optimizer == "lbfgs" else 0)  # lbfgs: n evaluations, adam: n + 1 (optim.py:240)
+    stamps = []
+    job(sub, n_iters, stamps)
+    stamps = stamps[2:]  # the two capture forwards (content, 1 style) come first
+    dt = stamps[warmup + steps] - stamps[warmup]
+    sample = f"{steps} iterations of the unmodified reference optim.optimize ({optimizer}, torch.optim) at {sub}x{sub} after {warmup} warm-up"
+    if sub != size:
+        sample += f", scaled by {scale:.4f} to {size}x{size}-equivalent (full-size probe {probe:.2f} s/iteration)"
+    ref_loader.unload()
+    return {"value": steps / dt * scale, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference", "sample": sample,
+            "ms_per_step": dt / steps * 1e3 / scale}
+
+
+def _port_rate(size, optimizer, steps, warmup, budget_s):
+    """Fallback when baseline/_ref is absent: the oracle port's feval + its restated optimizer."""
     from oracle import maua_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
     torch.set_flush_denormal(True)
     params = O.he_init_vgg19(0)
     cfg = O.StyleConfig(content_weight=5.0, optimizer=optimizer)
-    net = O.OracleNet(params, cfg)
-    content = O.synthetic_image(size, size, seed=1, smooth=True)
-    style = O.synthetic_image(size, size, seed=2)
-    O.set_content_targets(net, content)
-    O.set_style_targets(net, [style], [1.0])
-    for m in net.losses:
-        m.mode = "loss"
-    state = {"p": O.synthetic_image(size, size, seed=4) * 0.25, "m": None, "v": None, "t": 0}
 
-    def step():  # feval + a plain Adam-style pixel update (the optimizer is <1% of a CPU iteration)
-        _, _, g = O.feval(net, state["p"])
-        state["t"] += 1
-        if state["m"] is None:
-            state["m"], state["v"] = torch.zeros_like(g), torch.zeros_like(g)
-        state["m"].lerp_(g, 0.1)
-        state["v"].mul_(0.999).addcmul_(g, g, value=0.001)
-        state["p"] = state["p"] - state["m"] / (state["v"].sqrt() + 1e-8)
+    def run(sz, n):
+        content = O.synthetic_image(sz, sz, seed=1, smooth=True)
+        style = O.synthetic_image(sz, sz, seed=2)
+        init = O.synthetic_image(sz, sz, seed=4) * 0.25
+        t0 = time.perf_counter()
+        O.optimize(content, [style], init, n, cfg, params)
+        return time.perf_counter() - t0
 
-    return step
+    probe = run(size, 1) / 3.0
+    sub, scale = size, 1.0
+    while probe * scale * (steps + warmup + 3) > budget_s and sub >= 256:
+        sub //= 2
+        scale = (sub * sub) / float(size * size)
+    t_small = run(sub, max(warmup, 1))
+    t_big = run(sub, max(warmup, 1) + steps)
+    dt = t_big - t_small
+    sample = f"{steps} iterations of the oracle port ({optimizer}) at {sub}x{sub}"
+    if sub != size:
+        sample += f", scaled by {scale:.4f} to {size}x{size}-equivalent"
+    return {"value": steps / dt * scale, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
+            "ms_per_step": dt / steps * 1e3 / scale}
+
+
+def cpu_rate(size, optimizer, steps, warmup, budget_s):
+    import contextlib
+
+    r = None
+    try:
+        # the reference's progress bar writes to sys.stdout (optim.py:19); stdout carries the JSON line only
+        with contextlib.redirect_stdout(sys.stderr):
+            r = _reference_rate(size, optimizer, steps, warmup, budget_s)
+    except Exception as e:  # noqa: BLE001  (a broken reference install must not cost the line)
+        sys.stderr.write(f"reference arm: unmodified reference failed ({type(e).__name__}: {e}); using the oracle port\n")
+    return r if r is not None else _port_rate(size, optimizer, steps, warmup, budget_s)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = args.size
-    step = cpu_step_fn(size, args.optimizer)
-    t0 = time.perf_counter()
-    step()
-    probe = time.perf_counter() - t0
-    scale, sample = 1.0, f"full {size}x{size} iterations"
-    budget = 150.0
-    if probe * (args.steps + args.warmup) > budget and size > 256:
-        # bounded sample: same step on a centre crop with 1/4 (or 1/16) of the pixels; CPU conv cost is linear in
-        # pixels, so throughput is scaled back by the pixel ratio
-        sub = size // 2 if probe * (args.steps + args.warmup) / 4 <= budget else size // 4
-        scale = (sub * sub) / float(size * size)
-        step = cpu_step_fn(sub, args.optimizer)
-        sample = f"{sub}x{sub} iterations scaled by {scale:.4f} to {size}x{size}-equivalent (probe {probe:.1f} s/iter at full size)"
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    value = args.steps / dt * scale
-    cores = os.cpu_count() or 1
+    r = cpu_rate(args.size, args.optimizer, args.steps, args.warmup, budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 / scale, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(size, args.optimizer),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.size, args.optimizer),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -159,24 +247,8 @@ def run_reference(args):
 
 def cpu_baseline(size, optimizer):
     """Bounded sample (about 10-30 s of CPU work) of the same step on the host cores."""
-    sub = size
-    step = cpu_step_fn(sub, optimizer)
-    t0 = time.perf_counter()
-    step()
-    probe = time.perf_counter() - t0
-    scale = 1.0
-    sample = f"2 iterations at {size}x{size} after 1 warm-up"
-    if probe > 12.0 and size >= 512:
-        sub = size // 2
-        scale = 0.25
-        step = cpu_step_fn(sub, optimizer)
-        step()
-        sample = f"2 iterations at {sub}x{sub} scaled by 0.25 to {size}x{size}-equivalent (full-size probe {probe:.1f} s)"
-    t0 = time.perf_counter()
-    for _ in range(2):
-        step()
-    dt = time.perf_counter() - t0
-    return {"value": 2 / dt * scale, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+    r = cpu_rate(size, optimizer, steps=3, warmup=1, budget_s=25.0)
+    return {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -237,14 +309,171 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def lbfgs_launches(calls, hist):
-    return 4  # multi-dot pass, partial reduce, scalar recurrences, direction + update (maua_style_b200/csrc/lbfgs.cu)
+LBFGS_LAUNCHES = 4  # multi-dot pass, partial reduce, scalar recurrences, direction + update (maua_style_b200/csrc/lbfgs.cu)
+
+
+class Job:
+    """One image being optimised exactly as optim.optimize drives it (2 eager rounds, then CUDA-graph replays)."""
+
+    def __init__(self, size, optimizer, dev, local_rank, rank=0, covariance=False, history_prefill=100, multidevice=None):
+        from maua_style_b200 import models, optim, synthetic as O
+
+        self.tmp = tempfile.mkdtemp(prefix=f"maua_bench_{rank}_")
+        ckpt = Path(self.tmp) / "vgg19-random.pth"
+        O.save_random_checkpoint(ckpt)
+        over = dict(optimizer=optimizer, gpu=str(local_rank))
+        if covariance:  # BASELINE.json configs[2]: covariance loss, 2 blended styles of different aspect (area-matched)
+            over.update(use_covariance=True, style_blend_weights="3,1")
+        if multidevice:
+            over.update(gpu=multidevice, multidevice=True, multidevice_strategy="5")
+        self.args = a = O.reference_args(ckpt, self.tmp, **over)
+        self.net, self.losses = models.load_model(a)
+        content = O.synthetic_image(size, size, seed=1 + 10 * rank, smooth=True)
+        if covariance:
+            h2 = int(size * 0.875) // 2 * 2
+            w2 = (size * size // h2) // 2 * 2
+            styles = [O.synthetic_image(h2, w2, seed=2), O.synthetic_image(w2, h2, seed=3, smooth=True)]
+        else:
+            styles = [O.synthetic_image(size, size, seed=2)]
+        init = O.synthetic_image(size, size, seed=4 + 10 * rank) * 0.25
+        optim.set_content_targets(self.net, content.to(dev), a)
+        optim.set_style_targets(self.net, [s.to(dev) for s in styles], a)
+        for m in self.losses:
+            m.mode = "loss"
+        self.pastiche = init.to(dev).contiguous()
+        self.opt = optim.PixelOptimizer(self.pastiche, optimizer, lr=1.0, history=100)
+        self.up = torch.zeros(self.net._n_slots, device=dev)
+        self.up[self.net._live_slots()] = 1.0
+        self.step = optim.GraphedIteration(self.net, self.pastiche, self.opt, self.up)
+        self.optimizer = optimizer
+        # set-up: fill the L-BFGS history so the timed steps run at full history (not part of warm-up or timing)
+        for _ in range(history_prefill if optimizer == "lbfgs" else 3):
+            self.step()
+        torch.cuda.synchronize(dev)
+
+    def launches_per_step(self):
+        f, b = self.net.last_launches()
+        return f + b + (LBFGS_LAUNCHES if self.optimizer == "lbfgs" else 2)  # adam: step counter + update
+
+    def timed(self, K, W, barrier=None):
+        """ms for K steps, CUDA events on the launching stream, synchronised on both sides."""
+        for _ in range(W):
+            self.step()
+        (barrier or torch.cuda.synchronize)()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            self.step()
+        e1.record()
+        (barrier or torch.cuda.synchronize)()
+        return e0.elapsed_time(e1)
+
+    def conv_profile(self, reps=3):
+        """Per-launch CUDA-event records of one feval (plan profile mode), last of `reps` evaluations."""
+        self.net.set_profile(True)
+        prof = None
+        for _ in range(reps):
+            self.net._forward_plan(self.pastiche, keep=True)
+            self.net._backward_plan(self.up)
+            prof = self.net.profile()
+        self.net.set_profile(False)
+        return prof
+
+    def close(self):
+        self.opt.close()
+
+
+def conv_summary(prof):
+    conv = [r for r in prof if r["name"] in ("conv_fwd", "conv_dgrad")]
+    ms = sum(r["ms"] for r in conv)
+    flops = sum(r["flops"] for r in conv)
+    return conv, ms, flops, sum(r["ms"] for r in prof)
+
+
+def side_leg(size, optimizer, dev, K, W, pk, covariance=False, prefill=100):
+    """A bounded extra measurement of another configuration: it/s (device-resident, CUDA events) + its conv roofline."""
+    job = Job(size, optimizer, dev, dev.index, covariance=covariance, history_prefill=prefill)
+    ms = job.timed(K, W)
+    conv, conv_ms, conv_flops, feval_ms = conv_summary(job.conv_profile())
+    tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    out = {"size": size, "optimizer": optimizer, "value": K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
+           "warmup": W, "conv_tflops": tf, "conv_frac_of_tf32_burst": tf / (pk["bf16_burst"] / 2.0),
+           "feval_ms": feval_ms, "gpu_launches_per_step": job.launches_per_step(), "cuda_graph": job.step.graph is not None}
+    if covariance:
+        out["styles"] = 2
+        out["loss"] = "covariance (--use_covariance), blend 3:1"
+    job.close()
+    del job
+    torch.cuda.empty_cache()
+    return out
+
+
+def batch_job(dev, info, images_per_gpu, iters, size=1024):
+    """BASELINE.json configs[4] per GPU: `images_per_gpu` independent content images at 1024^2 through the public sharded
+    runner (shard.stylize_images: one network per rank, style targets captured once, per-image content capture +
+    optimisation + device->host copy of the result).  Wall clock around the whole call; with N ranks the job is
+    N * images_per_gpu images (8 x 8 = the 64-image job at N = 8)."""
+    from maua_style_b200 import shard, synthetic as O
+
+    tmp = tempfile.mkdtemp(prefix=f"maua_batch_{info.rank}_")
+    ckpt = Path(tmp) / "vgg19-random.pth"
+    O.save_random_checkpoint(ckpt)
+    a = O.reference_args(ckpt, tmp, optimizer="lbfgs", gpu=str(info.local_rank))
+    n = images_per_gpu * info.world
+    style = O.synthetic_image(size, size, seed=2)
+    mine = set(shard.partition_round_robin(n, info.world, info.rank))
+    # every rank only materialises its own images (pinned host memory: what a decoded batch looks like)
+    contents = [O.synthetic_image(size, size, seed=100 + i, smooth=True).pin_memory() if i in mine else None for i in range(n)]
+    inits = contents
+    first = contents[min(mine)]
+    shard.stylize_images([first], [style], [first], 2, a, info=shard.RankInfo(0, 1, info.local_rank))  # warm-up: plan core, arena
+    shard.barrier()
+    t0 = time.perf_counter()
+    out = shard.stylize_images(contents, [style], inits, iters, a, info=info)
+    dt = shard.max_over_ranks(time.perf_counter() - t0)
+    assert len(out) == len(mine) and all(v.device.type == "cpu" for v in out.values())
+    return {"workload": f"{n} independent {size}x{size} content images ({images_per_gpu} per GPU), {iters} L-BFGS iterations each, "
+                        "shard.stylize_images (per-image content capture, optimisation, D2H of the result)",
+            "images": n, "iterations_per_image": iters, "seconds": dt, "images_per_min": 60.0 * n / dt,
+            "value": n * iters / dt, "unit": UNIT, "timing": "wall clock, max over ranks, barrier on both sides"}
+
+
+def multidevice_leg(devices, size, K, W):
+    """BASELINE.json configs[3]: one image, the reference's layer-wise split (models.py:503-566) over `devices`, Adam (the
+    reference switches to Adam above 1456 px, config/scaling-img.json).  The hand-over tensors are stored into the
+    consuming GPU's memory by the producing kernels over NVLink.  Reported next to the same image on one GPU."""
+    dev0 = torch.device("cuda", int(devices.split(",")[0]))
+    out = {"devices": devices, "size": size, "optimizer": "adam"}
+    for tag, md in (("single_gpu", None), ("split", devices)):
+        job = Job(size, "adam", dev0, dev0.index, multidevice=md)
+        for _ in range(W):
+            job.step()
+        for d in range(torch.cuda.device_count()):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            job.step()
+        for d in range(torch.cuda.device_count()):
+            torch.cuda.synchronize(d)
+        dt = time.perf_counter() - t0
+        rec = {"value": K / dt, "unit": UNIT, "ms_per_step": dt / K * 1e3, "steps": K}
+        if md:
+            stages = job.net._stages
+            rec["stages"] = [{"device": str(st["device"]), "entries": [st["begin"], st["end"]]} for st in stages]
+            rec["handoff_bytes_per_step"] = int(sum(2 * st["x_in"].numel() * 4 for st in stages if st["x_in"] is not None))
+            rec["handoff"] = "forward activation + backward gradient of the stage boundary, peer stores over NVLink"
+        out[tag] = rec
+        job.close()
+        del job
+        torch.cuda.empty_cache()
+    out["timing"] = "wall clock around K eager iterations (several devices: no single-stream events), all devices synchronised"
+    return out
 
 
 def run_ours(args):
     import torch.distributed as dist
 
-    from maua_style_b200 import _lib, models, optim, synthetic as O  # the product path never touches oracle/
+    from maua_style_b200 import _lib, optim, shard  # the product path never touches oracle/
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -254,36 +483,18 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.require_gpu()
+    info = shard.RankInfo(rank, world, local_rank)
+
+    if args.multidevice:
+        print(json.dumps({"metric": METRIC, "leg": "multidevice", **multidevice_leg(args.multidevice, args.size, args.steps, args.warmup)}),
+              flush=True)
+        return
 
     size, K, W = args.size, args.steps, args.warmup
-    tmp = tempfile.mkdtemp(prefix=f"maua_bench_{rank}_")
-    ckpt = Path(tmp) / "vgg19-random.pth"
-    O.save_random_checkpoint(ckpt)
-    a = O.reference_args(ckpt, tmp, optimizer=args.optimizer, gpu=str(local_rank))
-    net, losses = models.load_model(a)
-    content = O.synthetic_image(size, size, seed=1 + 10 * rank, smooth=True)
-    style = O.synthetic_image(size, size, seed=2)
-    init = O.synthetic_image(size, size, seed=4 + 10 * rank) * 0.25
-    optim.set_content_targets(net, content.to(dev), a)
-    optim.set_style_targets(net, [style.to(dev)], a)
-    for m in losses:
-        m.mode = "loss"
-    pastiche = init.to(dev).contiguous()
-    hist = 100
-    opt = optim.PixelOptimizer(pastiche, args.optimizer, lr=1.0, history=hist)
-    up = torch.zeros(net._n_slots, device=dev)
-    live = net._live_slots()
-    up[live] = 1.0
-    # the iteration exactly as optim.optimize drives it: 2 eager rounds, then one CUDA-graph replay per iteration
-    step = optim.GraphedIteration(net, pastiche, opt, up)
-
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # set-up: fill the L-BFGS history so the timed steps run at full history (not part of warm-up or timing)
-    if args.optimizer == "lbfgs":
-        for _ in range(args.history_prefill):
-            step()
-    torch.cuda.synchronize()
+    job = Job(size, args.optimizer, dev, local_rank, rank=rank, covariance=args.covariance, history_prefill=args.history_prefill)
+    net, pastiche, step = job.net, job.pastiche, job.step
 
     def barrier():
         if world > 1:
@@ -291,91 +502,87 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
-    for _ in range(W):
-        step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    calls0 = opt.step_count
     t_begin = time.time()
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    barrier()
+    ms_local = job.timed(K, W, barrier)
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end)
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms = torch.tensor([ms_local], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * K / (ms_total / 1e3)
-    fwd_l, bwd_l = net.last_launches()
-    opt_l = K * (lbfgs_launches(calls0, hist) if args.optimizer == "lbfgs" else 2)  # adam: step counter + update
-    gpu_launches = K * (fwd_l + bwd_l) + opt_l  # kernels executed (as nodes of the replayed graph when graphs are on)
+    gpu_launches = K * job.launches_per_step()  # kernels executed (as nodes of the replayed graph when graphs are on)
 
-    # ---- end to end with host buffers (pinned), every step H2D pastiche + D2H result ----
-    host = [pastiche.detach().cpu().pin_memory(), torch.empty_like(pastiche, device="cpu").pin_memory()]
-    host_loss = torch.empty(1).pin_memory()
-    total_dev = torch.zeros(1, device=dev)
-
-    def step_e2e():
-        host_in, host_out = host
-        pastiche.copy_(host_in, non_blocking=True)       # H2D: this step's input image from pinned host memory
-        step()
-        torch.sum(net._loss_vec, dim=0, keepdim=True, out=total_dev)
-        host_out.copy_(pastiche, non_blocking=True)      # D2H: the updated image ...
-        host_loss.copy_(total_dev, non_blocking=True)    # ... and the total loss
-        torch.cuda.current_stream().synchronize()        # the caller holds the result on the host
-        host[0], host[1] = host_out, host_in             # next step's input is this step's result (host side)
-
-    for _ in range(min(W, 3)):
-        step_e2e()
+    # ---- end to end with host buffers: every step's input image comes from pinned host memory (H2D) and its result
+    # (updated image + total loss) goes back to pinned host memory (D2H); copies are double-buffered on their own streams
+    # (optim.HostPipelinedIteration) so they overlap the neighbouring steps' kernels ----
+    pipe = optim.HostPipelinedIteration(step)
+    host_in = [pastiche.detach().cpu().pin_memory(), (pastiche.detach().cpu() * 0.5).pin_memory()]
+    for i in range(min(W, 3)):
+        pipe.submit(host_in[i % 2])
+    pipe.drain()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        step_e2e()
+    got = 0
+    for i in range(K):
+        r = pipe.submit(host_in[i % 2])
+        got += r is not None
+    r = pipe.drain()
+    got += r is not None
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    assert got == K and torch.isfinite(r[1]).all()
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * K / float(dt.item())
-    nbytes = pastiche.numel() * 4
 
+    cfg = workload_config(size, args.optimizer)
+    if args.covariance:
+        cfg["workload"] = (f"VGG-19 covariance style transfer {size}x{size} (--use_covariance), 2 blended styles 3:1, content relu4_2 + "
+                           f"style relu1_1..relu5_1 + TV, {args.optimizer} (BASELINE.json configs[2])")
+        cfg["styles"] = 2
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32", "dtype_detail": "TF32 tensor-core operands, fp32 accumulate, fp32 storage", "data": "synthetic",
-        "config": workload_config(size, args.optimizer), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 4},
+        "config": cfg, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.bytes_in, "d2h_bytes_per_step": pipe.bytes_out,
+                "how": "optim.HostPipelinedIteration: per step H2D of the input image from pinned memory, one iteration, D2H of the "
+                       "updated image + loss; copies double-buffered on separate streams; wall clock, max over ranks"},
         "gpu_launches": gpu_launches,
-        "images_per_min_at_1000_iters": value * 60.0 / 1000.0,
         "cuda_graph": bool(step.graph is not None),
     }
+
+    # ---- configs[4] at this N: images_per_gpu x N images through the sharded runner (all ranks take part) ----
+    if not args.no_extras and size == 1024 and not args.covariance:
+        try:
+            bj = batch_job(dev, info, args.batch_images, args.batch_iters)
+        except Exception as e:  # noqa: BLE001
+            bj = {"error": f"{type(e).__name__}: {e}"[:300]}
+        line["batch_job"] = bj
 
     if rank == 0:
         # ---- roofline of the dominant kernel family, measured live with per-launch CUDA events ----
         pk = peaks()
-        net.set_profile(True)
-        recs = []
-        for _ in range(3):
-            net._forward_plan(pastiche, keep=True)
-            net._backward_plan(up)
-            recs.append(net.profile())
-        net.set_profile(False)
-        prof = recs[-1]
-        conv = [r for r in prof if r["name"] in ("conv_fwd", "conv_dgrad")]
-        conv_ms = sum(r["ms"] for r in conv)
-        conv_flops = sum(r["flops"] for r in conv)
-        iter_ms = sum(r["ms"] for r in prof)
-        tf32_peak = pk["bf16"] / 2.0
+        prof = job.conv_profile()
+        conv, conv_ms, conv_flops, iter_ms = conv_summary(prof)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        tf32_burst, tf32_sustained = pk["bf16_burst"] / 2.0, pk["bf16"] / 2.0
+        try:
+            cublas = measure_tf32_peak(dev)
+        except Exception as e:  # noqa: BLE001
+            cublas = {"error": f"{type(e).__name__}: {e}"[:200]}
         line["roofline"] = {
-            "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv3x3, forward + dgrad, 25 launches/iteration)",
-            "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-            "peak_source": f"{pk['source']}: bf16_tflops_sustained {pk['bf16']:.1f} / 2 -- TF32 MMA issues at half the bf16 rate",
-            "frac_of_bf16_peak": achieved / pk["bf16"],
+            "kernel": f"conv_tc_kernel (tcgen05 implicit-GEMM conv3x3, forward + dgrad, {len(conv)} launches/iteration)",
+            "bound": "tensor", "achieved": achieved, "peak": tf32_burst, "unit": "TFLOP/s", "frac": achieved / tf32_burst,
+            "peak_source": f"{pk['source']}: bf16_tflops (burst) {pk['bf16_burst']:.1f} / 2 -- TF32 MMAs issue at half the bf16 rate; "
+                           "burst because the launches are timed one by one with CUDA events",
+            "frac_vs_sustained_peak": achieved / tf32_sustained, "sustained_peak": tf32_sustained,
+            "cublas_tf32_8192_measured_in_this_run": cublas,
+            "frac_of_bf16_peak": achieved / pk["bf16_burst"],
             "traffic": conv_traffic_per_launch(size),
-            "traffic_source": "profiles/conv_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch, ncu --set full)",
+            "traffic_source": "profiles/conv_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch, ncu --set full "
+                              "capture of this command, committed; not measurable inside an un-profiled run)",
             "achieved_per_launch_flops": conv_flops / max(len(conv), 1), "launches_per_iteration": len(conv),
             "share_of_feval": conv_ms / iter_ms if iter_ms > 0 else None,
             "algorithmic_flops_per_iteration": conv_flops,
@@ -390,19 +597,35 @@ def run_ours(args):
         line["hbm_peak_gbs"] = pk["hbm"]
         if args.profile_out:
             Path(args.profile_out).write_text(json.dumps({"per_launch": prof, "summary": by}, indent=1))
+        a = job.args
+        job.close()
+        del job, pipe, step, net
+        torch.cuda.empty_cache()
         # the extras must never cost the line itself: a failure is reported inside the line
-        if world == 1 and not args.no_multires and size == 1024:
-            try:
-                line["multires_e2e"] = multires_job(a, dev)
-            except Exception as e:  # noqa: BLE001
-                line["multires_e2e"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1 and size == 1024 and not args.covariance:
+            def guarded(fn, *fa, **kw):
+                try:
+                    return fn(*fa, **kw)
+                except Exception as e:  # noqa: BLE001
+                    return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+            if not args.no_multires:
+                line["multires_e2e"] = guarded(multires_job, a, dev)
+            if not args.no_extras:
+                line["sizes"] = {"512": guarded(side_leg, 512, args.optimizer, dev, 40, 5, pk),
+                                 "2048": guarded(side_leg, 2048, args.optimizer, dev, 10, 3, pk)}
+                line["adam_1024"] = guarded(side_leg, 1024, "adam", dev, 30, 5, pk)
+                line["covariance_2styles_1024"] = guarded(side_leg, 1024, args.optimizer, dev, 30, 5, pk, covariance=True)
+                if torch.cuda.device_count() >= 2:
+                    line["multidevice_2048"] = guarded(multidevice_leg, "0,1", 2048, 10, 3)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(size, args.optimizer)
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
-    opt.close()
+    else:
+        job.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -98,10 +98,37 @@ def _architecture(model_file: str, pooling: str):
     return channels, layer_list
 
 
+# models.py:246-347: a --model_file that is not an existing path is a model NAME; the reference maps it to its model zoo
+# (and downloads the file when it is missing -- there is no network on a B200 box, so that part is an error message)
+_MODELZOO = [("prun", "vgg16-prune.pth"), ("nyud", "nyud-fcn32s-color-heavy.pth"), ("fcn32s", "fcn32s-heavy-pascal.pth"),
+             ("sod", "vgg16-sod.pth"), ("vgg19", "vgg19.pth"), ("vgg16", "vgg16.pth"), ("nin", "nin.pth")]
+
+
+def resolve_model_file(model_file: str) -> str:
+    """The checkpoint path `select_model` would load (models.py:246-347): `model_file` itself when it exists, otherwise
+    `modelzoo/<name>.pth` for the model the name selects (relative to the working directory, like the reference; a
+    directory can be given with $MAUA_MODELZOO).  The stock config/scaling-img.json names models this way ("vgg19",
+    "prune", "nin") and optim.set_model_args overwrites args.model_file with those names for every scale."""
+    mf = str(model_file)
+    if os.path.exists(mf):
+        return mf
+    low = mf.lower()
+    for key, fname in _MODELZOO:
+        if key in low:
+            zoo = os.path.join(os.environ.get("MAUA_MODELZOO", "modelzoo"), fname)
+            if os.path.exists(zoo):
+                return zoo
+            raise FileNotFoundError(
+                f"model_file {mf!r} is not a file and the model-zoo checkpoint {zoo!r} does not exist either; the reference "
+                f"would download it here (models.py:246-347), which is not possible offline: place the checkpoint there, set "
+                f"$MAUA_MODELZOO, or pass --model_file with a real path (and name it in the --scaling_args JSON)")
+    raise ValueError("Model architecture not recognized.")  # models.py:338
+
+
 def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bool):
     """Returns (channels, layer names, state dict) -- the checkpoint is read with torch.load like models.py:343."""
     channels, layer_list = _architecture(model_file, pooling)
-    sd = torch.load(model_file, map_location="cpu")
+    sd = torch.load(resolve_model_file(model_file), map_location="cpu")
     return channels, layer_list, sd
 
 
@@ -572,7 +599,8 @@ def _device_from_args(args) -> torch.device:
     return torch.device("cuda", int(gpu.split(",")[0]))
 
 
-def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stage_bounds=None, devices=None) -> "B200Net":
+def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stage_bounds=None, devices=None,
+              model_path=None) -> "B200Net":
     """A B200Net on a cached plan core when one exists for (checkpoint file, layer layout, taps, pooling, devices) and no
     live network is using it; otherwise on a new core built from `params_fn()` (which reads the checkpoint)."""
     bounds = list(stage_bounds) if stage_bounds else [0, len(entries)]
@@ -582,10 +610,11 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
     key = None
     if os.environ.get("MAUA_NO_MODEL_CACHE", "0") != "1":
         try:
-            st = os.stat(str(args.model_file))
-            key = (os.path.realpath(str(args.model_file)), st.st_mtime_ns, st.st_size, avg, tuple(entries), tap_sig,
+            model_path = model_path or resolve_model_file(str(args.model_file))
+            st = os.stat(model_path)
+            key = (os.path.realpath(model_path), st.st_mtime_ns, st.st_size, avg, tuple(entries), tap_sig,
                    tuple(bounds), tuple(str(d) for d in devs))
-        except OSError:
+        except (OSError, ValueError):
             key = None
     core = _CORE_CACHE.get(key) if key is not None else None
     if core is not None and core.in_use():
@@ -608,6 +637,7 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
 def load_model(args):
     """models.py:351-453."""
     channels, layer_list = _architecture(str(args.model_file), args.pooling)
+    model_path = resolve_model_file(str(args.model_file))
     device = _device_from_args(args)
     content_layers = args.content_layers.split(",")
     style_layers = args.style_layers.split(",")
@@ -670,7 +700,7 @@ def load_model(args):
 
     def params():
         """The checkpoint's conv weights up to the last tapped layer -- only read when no cached core exists."""
-        sd = torch.load(str(args.model_file), map_location="cpu")  # models.py:343
+        sd = torch.load(model_path, map_location="cpu")  # models.py:343
         return _conv_params(sd, channels, getattr(args, "disable_check", False))[:n_convs]
 
     if getattr(args, "multidevice", False):
@@ -679,7 +709,7 @@ def load_model(args):
         return setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses,
                                   tv_losses, temporal_losses)
 
-    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device)
+    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device, model_path=model_path)
     net.content_losses = content_losses
     net.style_losses = style_losses
     net.tv_losses = tv_losses

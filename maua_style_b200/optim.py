@@ -185,8 +185,13 @@ class GraphedIteration:
             try:
                 with torch.cuda.graph(g):
                     self._eager()
-            except Exception:
-                # capture unsupported in this environment: stay eager (the capture launched nothing)
+            except Exception as e:  # noqa: BLE001
+                # capture unsupported in this environment: stay eager (the capture launched nothing) -- and say so,
+                # because eager launches are several times slower at <= 512^2
+                import warnings
+
+                warnings.warn(f"maua_style_b200: CUDA-graph capture of the iteration failed ({type(e).__name__}: {e}); "
+                              "falling back to eager kernel launches", RuntimeWarning)
                 self.enabled = False
                 self.opt.step_count = count
                 torch.cuda.synchronize(dev)
@@ -196,6 +201,69 @@ class GraphedIteration:
             self.graph = g
         self.graph.replay()
         self.opt.step_count += 1
+
+
+class HostPipelinedIteration:
+    """An iteration driven from HOST buffers without stalling the GPU: every `submit(host_image)` copies that step's input
+    image host->device from pinned memory, runs one fused iteration on it and copies the updated image + total loss back
+    to pinned host memory -- with the copies on their own streams, double-buffered, so that step i's device->host read
+    and step i+1's host->device copy run under step i+1's / step i's kernels.  `submit` returns the result of the
+    PREVIOUS step (already on the host); `drain()` returns the last one.  Used by bench.py's end-to-end number and by
+    callers that stream frames through one network."""
+
+    def __init__(self, iteration: "GraphedIteration"):
+        self.it = iteration
+        p = iteration.pastiche
+        dev = p.device
+        self.dev = dev
+        self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.dev_in = [torch.empty_like(p) for _ in range(2)]
+        self.dev_out = [torch.empty_like(p) for _ in range(2)]
+        self.dev_loss = [torch.zeros(1, device=dev) for _ in range(2)]
+        self.host_out = [torch.empty_like(p, device="cpu").pin_memory() for _ in range(2)]
+        self.host_loss = [torch.empty(1).pin_memory() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_consumed = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.n = 0
+        self.pending = None
+        self.bytes_in = p.numel() * 4
+        self.bytes_out = p.numel() * 4 + 4
+
+    def submit(self, host_image: torch.Tensor):
+        b = self.n % 2
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_in):
+            if self.n >= 2:
+                self.copy_in.wait_event(self.ev_consumed[b])      # the step two back has read this staging buffer
+            self.dev_in[b].copy_(host_image, non_blocking=True)    # H2D of THIS step's input
+            self.ev_in[b].record(self.copy_in)
+        main.wait_event(self.ev_in[b])
+        self.it.pastiche.copy_(self.dev_in[b])
+        self.ev_consumed[b].record(main)
+        self.it()
+        self.dev_out[b].copy_(self.it.pastiche)
+        torch.sum(self.it.net._loss_vec, dim=0, keepdim=True, out=self.dev_loss[b])
+        self.ev_done[b].record(main)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.ev_done[b])
+            self.host_out[b].copy_(self.dev_out[b], non_blocking=True)   # D2H of this step's result
+            self.host_loss[b].copy_(self.dev_loss[b], non_blocking=True)
+            self.ev_out[b].record(self.copy_out)
+        prev, self.pending = self.pending, b
+        self.n += 1
+        if prev is None:
+            return None
+        self.ev_out[prev].synchronize()                            # the previous step's result is on the host now
+        return self.host_out[prev], self.host_loss[prev]
+
+    def drain(self):
+        if self.pending is None:
+            return None
+        b, self.pending = self.pending, None
+        self.ev_out[b].synchronize()
+        return self.host_out[b], self.host_loss[b]
 
 
 def feval(net, pastiche: torch.Tensor, ones: Optional[torch.Tensor] = None):
@@ -239,6 +307,11 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
             i.strength = i.strength / max(i.target.size())
 
     if args.optimizer == "lbfgs":
+        # optim.py:180-186 passes tolerance_grad = -1 (never stops on the gradient norm); the device L-BFGS has no such
+        # test, so a value that could fire is refused instead of silently ignored
+        if float(getattr(args, "lbfgs_tolerance_grad", -1)) >= 0:
+            raise NotImplementedError("maua_style_b200: lbfgs_tolerance_grad >= 0 is not supported (the reference always "
+                                      "passes -1, optim.py:184); use the default")
         hist = getattr(args, "lbfgs_num_correction", 100)
         opt = PixelOptimizer(pastiche, "lbfgs", history=hist, tolerance_change=float(getattr(args, "lbfgs_tolerance_change", -1)))
         evals = num_iters  # one step() = num_iters closure evaluations and updates

@@ -163,7 +163,14 @@ def stylize_images(contents: Sequence, styles: Sequence, inits: Sequence, num_it
         net, losses = models.load_model(a)
     mine = partition_round_robin(len(contents), info.world, info.rank)
     out = {}
+    # One network serves all of this rank's images, but every image is an independent img_img job: the reference builds a
+    # fresh network per optimize() call (optim.py:127-129), so `--normalize_weights` (optim.py:176-178, which divides the
+    # module strengths in place) applies exactly once per image.  Restore the strengths between images.
+    mods = net.content_losses + net.style_losses + net.temporal_losses
+    base = [m.strength for m in mods]
     for i in mine:
         out[i] = optim.optimize(contents[i], styles, inits[i], num_iters, a, net, losses)
+        for m, s0 in zip(mods, base):
+            m.strength = s0
     torch.cuda.synchronize()
     return out

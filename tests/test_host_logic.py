@@ -75,7 +75,8 @@ def test_scale_schedule_matches_the_reference_arithmetic():
 
 
 def test_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores): one JSON line with the contract's keys."""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref on the host cores, else the oracle port): one
+    JSON line with the contract's keys."""
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--size", "64", "--steps", "1",
                           "--warmup", "0", "--optimizer", "adam"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -84,7 +85,8 @@ def test_reference_arm_prints_the_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["vs_baseline"] is None
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    installed = (ROOT / "baseline" / "_ref" / "optim.py").exists()
+    assert line["cpu_baseline"]["kind"] == ("reference" if installed else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 
@@ -96,3 +98,58 @@ def test_reference_arm_other_ranks_exit_without_work():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "64",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bare_model_names_resolve_like_select_model(tmp_path, monkeypatch):
+    """models.py:246-347: a --model_file that is not a file is a model NAME resolved inside modelzoo/; the stock
+    config/scaling-img.json uses such names ("vgg19") and optim.set_model_args writes them into args for every scale."""
+    import argparse
+
+    real = tmp_path / "my-vgg19-weights.pth"
+    real.write_bytes(b"x")
+    assert models.resolve_model_file(str(real)) == str(real)              # an existing path is used as is
+    zoo = tmp_path / "zoo"
+    zoo.mkdir()
+    monkeypatch.setenv("MAUA_MODELZOO", str(zoo))
+    with pytest.raises(FileNotFoundError, match="vgg19.pth"):                # nothing to download from on a GPU box
+        models.resolve_model_file("vgg19")
+    (zoo / "vgg19.pth").write_bytes(b"x")
+    (zoo / "vgg16-sod.pth").write_bytes(b"x")
+    assert models.resolve_model_file("vgg19") == str(zoo / "vgg19.pth")
+    assert models.resolve_model_file("sod") == str(zoo / "vgg16-sod.pth")
+    with pytest.raises(ValueError):
+        models.resolve_model_file("resnet50")
+    # the reference's own scaling presets, where they are installed (build() copies them into baseline/_ref)
+    stock = ROOT / "baseline" / "_ref" / "config" / "scaling-img.json"
+    if not stock.exists():
+        pytest.skip("reference presets not installed (baseline/_ref is created by __graft_entry__.build() where /root/reference is mounted)")
+    a = argparse.Namespace(scaling_args=str(stock), gpu="0", model_file=str(real), optimizer="adam")
+    optim.set_model_args(a, 1024)
+    assert a.model_file == "vgg19" and a.optimizer == "lbfgs"               # the user's path is overwritten by the preset
+    assert models._architecture(a.model_file, "max")[0] == models.channel_list["VGG-19"]
+    assert models.resolve_model_file(a.model_file) == str(zoo / "vgg19.pth")
+
+
+def test_sharded_batch_normalises_the_weights_once_per_image(monkeypatch):
+    """optim.py:176-178 divides the module strengths in place; the reference builds a fresh network per image (img_img), so
+    shard.stylize_images -- which re-uses one network -- must hand every image the un-normalised strengths."""
+    import types
+
+    from maua_style_b200 import shard
+
+    mods = [types.SimpleNamespace(strength=5.0), types.SimpleNamespace(strength=100.0)]
+    net = types.SimpleNamespace(content_losses=mods[:1], style_losses=mods[1:], temporal_losses=[])
+    seen = []
+
+    def fake_optimize(content, styles, init, num_iters, args, net_, losses):
+        seen.append([m.strength for m in mods])
+        for m in mods:  # what --normalize_weights does inside optimize
+            m.strength = m.strength / 512
+        return content
+
+    monkeypatch.setattr(optim, "optimize", fake_optimize)
+    monkeypatch.setattr("torch.cuda.synchronize", lambda *a, **k: None)
+    args = types.SimpleNamespace(gpu="0", normalize_weights=True)
+    out = shard.stylize_images([1, 2, 3], [], [None] * 3, 1, args, info=shard.RankInfo(0, 1, 0), net=net, losses=mods)
+    assert sorted(out) == [0, 1, 2]
+    assert seen == [[5.0, 100.0]] * 3 and [m.strength for m in mods] == [5.0, 100.0]
