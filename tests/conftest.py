@@ -11,6 +11,7 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (sm_100a); run with -m gpu on the GPU box")
+    config.addinivalue_line("markers", "multigpu: needs two B200s on one box (gpurun --gpus 2 -- pytest -m multigpu); not part of -m gpu")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -25,5 +26,5 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container (GPU tests run under gpurun)")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords or "multigpu" in item.keywords:
             item.add_marker(skip)

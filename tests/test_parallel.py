@@ -101,3 +101,49 @@ def test_staged_optimize_runs(tmp_path):
     p = O.psnr(outs[0], outs[1])
     print(f"staged vs single optimize, 5 Adam iterations: PSNR {p:.1f} dB")
     assert p > 50.0
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("strategy", ["5", "13"])
+def test_split_over_two_physical_gpus(tmp_path, strategy):
+    """BASELINE.json configs[3] on real hardware (run with `gpurun --gpus 2 -- python -m pytest tests/test_parallel.py -m
+    multigpu`): stage 0 on cuda:0, stage 1 on cuda:1, so the forward hand-over (dual TMA store from the conv / pool epilogue
+    into the peer's memory), the backward hand-over (dgrad epilogue storing into cuda:0's g_top), cudaDeviceEnablePeerAccess,
+    the cross-device events and the loss-vector gather all cross NVLink.  Against the single-GPU plan at 384 x 512."""
+    from helpers import O, make_args, rel, save_checkpoint
+    from maua_style_b200 import models, optim
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    h, w = 384, 512
+    content = O.synthetic_image(h, w, seed=1, smooth=True)
+    styles = [O.synthetic_image(h, w, seed=2)]
+    init = O.synthetic_image(h, w, seed=4) * 0.25
+    a1 = make_args(ckpt, tmp_path, pooling="avg")
+    net1, losses1 = models.load_model(a1)
+    vec1, g1 = _feval(net1, losses1, a1, content, styles, init)
+    a2 = make_args(ckpt, tmp_path, pooling="avg", multidevice=True, gpu="0,1", multidevice_strategy=strategy)
+    net2, losses2 = models.load_model(a2)
+    devs = [str(st["device"]) for st in net2._stages]
+    assert devs == ["cuda:0", "cuda:1"]
+    vec2, g2 = _feval(net2, losses2, a2, content, styles, init)
+    assert str(net2._stages[1]["x_in"].device) == "cuda:1" and str(net2._stages[0]["g_top"].device) == "cuda:0"
+    assert torch.allclose(vec1, vec2, rtol=1e-5, atol=0), (vec1, vec2)
+    err = rel(g2, g1)
+    print(f"two physical GPUs, strategy {strategy}: gradient vs single-GPU plan rel {err:.2e}, "
+          f"hand-over tensor {tuple(net2._stages[1]['x_in'].shape)} = {net2._stages[1]['x_in'].numel() * 4 / 1e6:.1f} MB each way")
+    assert err < 1e-4
+    # determinism across the link: a second evaluation is bit-identical
+    vec3, g3 = _feval(net2, losses2, a2, content, styles, init)
+    assert torch.equal(g2, g3) and torch.equal(vec2, vec3)
+    # a whole optimisation (Adam, 6 iterations) over the two GPUs equals the single-GPU run
+    outs = []
+    for multi in (False, True):
+        a = make_args(ckpt, tmp_path, pooling="avg", multidevice=multi, gpu="0,1" if multi else "0", multidevice_strategy=strategy)
+        net, losses = models.load_model(a)
+        outs.append(optim.optimize(content, styles, init.clone(), 6, a, net, losses))
+    p = O.psnr(outs[0], outs[1])
+    print(f"two physical GPUs, strategy {strategy}: 6 Adam iterations vs single GPU PSNR {p:.1f} dB")
+    assert p > 60.0
