@@ -77,6 +77,10 @@ MAUA_API int maua_prep_conv_weights(const float* w_oihw, float* out, int cout, i
 /* Same layouts with the TF32 rounding optional (round_tf32 = 0: the operands of MAUA_IMPL_FP32). */
 MAUA_API int maua_prep_conv_weights_ex(const float* w_oihw, float* out, int cout, int cin, int dgrad, int round_tf32,
                                        maua_stream_t stream);
+/* Host-side launch plan of a conv3x3 / pointwise / aux-GEMM launch on a device with `sms` SMs (no GPU needed): plan6 =
+ * {BN, MT, CTA-group size, whole tiles, K-split tiles, split factor}.  The persistent kernel computes the last, partial wave
+ * of tiles as `split` K-ranges on different CTAs (pairs) whose partial sums meet in a workspace (deterministic order). */
+MAUA_API int maua_conv_tile_plan(int h, int w, int cin, int cout, int ntaps, int k2, int sms, int allow_split, int* plan6);
 MAUA_API int maua_nchw_to_nhwc(const float* src, float* dst, int b, int c, int h, int w, int round_tf32,
                                maua_stream_t stream);
 MAUA_API int maua_nhwc_to_nchw(const float* src, float* dst, int b, int c, int h, int w, maua_stream_t stream);
@@ -332,6 +336,10 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
  * convolution that produces its input instead of a separate pass over the activation (same arithmetic, bit for bit).
  * Off by default in this release (also switched on by MAUA_FUSE_POOL=1 in the environment at plan creation). */
 MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* plan, int enable);
+/* K-split of the last partial wave of conv tiles (see maua_conv_tile_plan).  Off by default: on B200 the hand-over of
+ * the partial accumulators costs more than the idle SMs it recovers (profiles/r02_splitk_ab.txt); results agree with the
+ * unsplit plan to fp32 summation order. */
+MAUA_API int maua_plan_set_splitk(maua_plan_t* plan, int enable);
 /* Per-launch timing for roofline reports: when enabled, a CUDA event is recorded on the caller's stream after every
  * launch of forward / backward.  maua_plan_profile_json synchronises the stream and writes a JSON array
  * [{"name","layer","ms","flops","bytes"}...] (algorithmic FLOPs / bytes per launch) for the last forward + backward

@@ -76,6 +76,12 @@ MAUA_DEVINL float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
+MAUA_DEVINL unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 MAUA_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -4,8 +4,9 @@
 // (backward) the 64-channel full-resolution map.  The image itself stays NCHW [B,3,H,W] (the layout of the reference's
 // pastiche, optim.py:173), which is not TMA-friendly for W % 4 != 0.
 //
-// forward : direct fp32 FFMA kernel, thread = 4 pixels x 16 output channels, image halo staged in shared memory,
-//           weights broadcast from shared memory, NHWC output written as float4 (bias + ReLU + TF32 rounding fused).
+// forward : direct fp32 FFMA2 kernel, thread = 8 pixels x 16 output channels, image halo staged in shared memory,
+//           weights broadcast from shared memory, NHWC output written as float4 (bias + ReLU + TF32 rounding fused),
+//           TVLoss value folded in (the tile already holds every pixel's neighbours).
 // backward: two steps.  (1) a pointwise tensor-core GEMM (conv_tc.cu, ntaps = 1, Cin = 64, Cout = 32) contracts the
 //           64 channels of the masked gradient with the 27 (tap, ci) weight columns per pixel:
 //               T[p][tap*3 + ci] = sum_co gout[p][co] * W[co][ci][ky][kx]
@@ -16,6 +17,7 @@
 #include <cstdlib>
 
 #include "conv_tc.cuh"
+#include "reduce.cuh"
 
 namespace maua {
 
@@ -25,29 +27,41 @@ namespace {
 // forward
 // ------------------------------------------------------------------------------------------------
 constexpr int FG_STRIDE = 20;  // 16 channels + 4 pad floats per group: conflict-free float4 broadcast reads
-constexpr int FT_W = 64;       // tile: 64 x 4 pixels, 256 threads = 16 quads x 4 rows x 4 channel groups
+constexpr int FT_W = 64;       // tile: 64 x 4 pixels, 128 threads = 8 pixel octets x 4 rows x 4 channel groups
 constexpr int FT_H = 4;
 constexpr int FI_W = 68;       // staged image row: 64 + 2 halo, padded to a float4 multiple
+constexpr int FT_THREADS = 128;
 
-__global__ void __launch_bounds__(256)
+// Thread = 8 consecutive pixels of one tile row x 16 output channels (channel c4*16 + g*4 + i for c4, i in 0..3, so that
+// the four threads of a pixel write 64 contiguous bytes per store).  Per (ci, ky) a thread reads 10 image values and per
+// tap 16 weights (four broadcast LDS.128) for 128 multiply-adds: twice the arithmetic per shared-memory byte of the
+// round-1 kernel (4 pixels x 16 channels), which was bound by the weight reads, not by the FMA pipe.  PACKED issues the
+// multiply-adds as FFMA2 (fma.rn.f32x2, sm_100): two round-to-nearest FMAs per instruction, bit-identical results.
+// The TVLoss value (loss.py:229-233) is folded in when tv_out is given: the staged tile already holds every pixel's upper
+// and left neighbour, so the image is read once per forward instead of twice.
+template <bool PACKED>
+__global__ void __launch_bounds__(FT_THREADS, 3)
 conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
-                      float* __restrict__ out, uint16_t* __restrict__ mask16, int B, int H, int W, int do_round) {
+                      float* __restrict__ out, uint16_t* __restrict__ mask16, int B, int H, int W, int do_round,
+                      float tv_strength, float* __restrict__ tv_out, double* tv_partials, unsigned int* tv_counter) {
     constexpr int Cout = 64, G = 4;
     __shared__ __align__(16) float ws[27 * G * FG_STRIDE];
     __shared__ float bs[Cout];
     __shared__ __align__(16) float inp[3][FT_H + 2][FI_W];
     for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
         const int co = i / 27, k = i % 27;
-        ws[(k * G + co / 16) * FG_STRIDE + (co % 16)] = w[i];
+        const int c4 = co >> 4, g = (co >> 2) & 3, e = co & 3;
+        ws[(k * G + g) * FG_STRIDE + c4 * 4 + e] = w[i];
     }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
 
     const int g = threadIdx.x & 3;
-    const int quad = (threadIdx.x >> 2) & 15;
-    const int row = threadIdx.x >> 6;
+    const int oct = (threadIdx.x >> 2) & 7;
+    const int row = threadIdx.x >> 5;
     const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
     const long ntiles = (long)B * tiles_w * tiles_h;
     const long HW = (long)H * W;
+    float tv_local = 0.f;
 
     for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int tw = t % tiles_w;
@@ -64,19 +78,38 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
         }
         __syncthreads();
 
-        float acc[4][16];
+        const int h = h0 + row;
+        if (tv_out && g < 3 && h < H) {  // TVLoss: channel ci = g of this thread's 8 pixels (row / column 0 have no neighbour)
+            const float* cur = &inp[g][row + 1][8 * oct];
+            const float* up = &inp[g][row][8 * oct];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j) {
+                const int x = w0 + 8 * oct + j;
+                if (x < W) {
+                    const float v = cur[j + 1];
+                    if (h > 0) tv_local += fabsf(v - up[j + 1]);
+                    if (x > 0) tv_local += fabsf(v - cur[j]);
+                }
+            }
+        }
+
+        float2 acc[8][8];  // [pixel][channel pair]: channels c4*16 + g*4 + {0,1} and {2,3}
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[j][c] = bs[g * 16 + c];
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                acc[j][2 * c4] = make_float2(bs[c4 * 16 + g * 4], bs[c4 * 16 + g * 4 + 1]);
+                acc[j][2 * c4 + 1] = make_float2(bs[c4 * 16 + g * 4 + 2], bs[c4 * 16 + g * 4 + 3]);
+            }
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-                const float* ip = &inp[ci][row + ky][4 * quad];
+                const float* ip = &inp[ci][row + ky][8 * oct];
                 const float4 x0 = *reinterpret_cast<const float4*>(ip);
-                const float2 x1 = *reinterpret_cast<const float2*>(ip + 4);
-                const float xin[6] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y};
+                const float4 x1 = *reinterpret_cast<const float4*>(ip + 4);
+                const float2 x2 = *reinterpret_cast<const float2*>(ip + 8);
+                const float xin[10] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y};
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 9 + ky * 3 + kx) * G + g) * FG_STRIDE);
@@ -84,129 +117,51 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const float4 wv = wp[c4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            acc[j][4 * c4 + 0] = fmaf(xin[j + kx], wv.x, acc[j][4 * c4 + 0]);
-                            acc[j][4 * c4 + 1] = fmaf(xin[j + kx], wv.y, acc[j][4 * c4 + 1]);
-                            acc[j][4 * c4 + 2] = fmaf(xin[j + kx], wv.z, acc[j][4 * c4 + 2]);
-                            acc[j][4 * c4 + 3] = fmaf(xin[j + kx], wv.w, acc[j][4 * c4 + 3]);
+                        for (int j = 0; j < 8; ++j) {
+                            const float xv = xin[j + kx];
+                            if (PACKED) {
+                                acc[j][2 * c4] = __ffma2_rn(make_float2(xv, xv), make_float2(wv.x, wv.y), acc[j][2 * c4]);
+                                acc[j][2 * c4 + 1] = __ffma2_rn(make_float2(xv, xv), make_float2(wv.z, wv.w), acc[j][2 * c4 + 1]);
+                            } else {
+                                acc[j][2 * c4].x = fmaf(xv, wv.x, acc[j][2 * c4].x);
+                                acc[j][2 * c4].y = fmaf(xv, wv.y, acc[j][2 * c4].y);
+                                acc[j][2 * c4 + 1].x = fmaf(xv, wv.z, acc[j][2 * c4 + 1].x);
+                                acc[j][2 * c4 + 1].y = fmaf(xv, wv.w, acc[j][2 * c4 + 1].y);
+                            }
                         }
                     }
                 }
             }
-        const int h = h0 + row;
-        if (h < H) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = w0 + 4 * quad + j;
-                if (x >= W) continue;
-                const long pix = ((long)b * H + h) * W + x;
-                float4* op = reinterpret_cast<float4*>(out + pix * Cout + g * 16);
-                uint32_t bits = 0;
+        for (int j = 0; j < 8; ++j) {
+            const int x = w0 + 8 * oct + j;
+            const bool valid = (h < H) && (x < W);
+            const long pix = ((long)b * H + (valid ? h : 0)) * W + (valid ? x : 0);
+            float* op = out + pix * Cout + g * 4;
+            uint32_t mine = 0;  // nibble c4 = sign bits of this thread's channels c4*16 + g*4 + 0..3
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float4 o;
-                    o.x = fmaxf(acc[j][4 * c4 + 0], 0.f); o.y = fmaxf(acc[j][4 * c4 + 1], 0.f);
-                    o.z = fmaxf(acc[j][4 * c4 + 2], 0.f); o.w = fmaxf(acc[j][4 * c4 + 3], 0.f);
-                    if (do_round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                    op[c4] = o;
-                    bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << (4 * c4);
-                }
-                // sign bitmap of the output (16 channels of this thread = one half-word): the ReLU mask dgrad reads
-                if (mask16) mask16[pix * (Cout / 16) + g] = (uint16_t)bits;
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float4 o;
+                o.x = fmaxf(acc[j][2 * c4].x, 0.f); o.y = fmaxf(acc[j][2 * c4].y, 0.f);
+                o.z = fmaxf(acc[j][2 * c4 + 1].x, 0.f); o.w = fmaxf(acc[j][2 * c4 + 1].y, 0.f);
+                if (do_round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                if (valid) *reinterpret_cast<float4*>(op + c4 * 16) = o;
+                mine |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << (4 * c4);
             }
+            // sign bitmap (the ReLU mask dgrad reads): half-word c4 of a pixel = channels c4*16 .. c4*16+15 = the nibbles c4
+            // of the pixel's four threads; thread g assembles half-word g
+            uint32_t hw = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const uint32_t other = __shfl_sync(0xffffffffu, mine, (threadIdx.x & 28) | s);
+                hw |= ((other >> (4 * g)) & 0xFu) << (4 * s);
+            }
+            if (mask16 && valid) mask16[pix * (Cout / 16) + g] = (uint16_t)hw;
         }
     }
-}
-
-// Same kernel with the 27 x 64 multiply-adds issued as packed FFMA2 (fma.rn.f32x2, sm_100): two independent
-// round-to-nearest FMAs per instruction, i.e. the same results bit for bit at half the fma-pipe issue slots (the plain
-// kernel is bound by them: 1728 FFMA per thread and tile, 62 % of the scalar-FFMA peak in the round-1 ncu capture).
-// Default since round 2 (bit-identity verified on B200, tests/test_zz_arch_gpu.py); MAUA_CONV1_FFMA2=0 selects the scalar kernel.
-__global__ void __launch_bounds__(256)
-conv_first_fwd_f2_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
-                      float* __restrict__ out, uint16_t* __restrict__ mask16, int B, int H, int W, int do_round) {
-    constexpr int Cout = 64, G = 4;
-    __shared__ __align__(16) float ws[27 * G * FG_STRIDE];
-    __shared__ float bs[Cout];
-    __shared__ __align__(16) float inp[3][FT_H + 2][FI_W];
-    for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
-        const int co = i / 27, k = i % 27;
-        ws[(k * G + co / 16) * FG_STRIDE + (co % 16)] = w[i];
-    }
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
-
-    const int g = threadIdx.x & 3;
-    const int quad = (threadIdx.x >> 2) & 15;
-    const int row = threadIdx.x >> 6;
-    const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
-    const long ntiles = (long)B * tiles_w * tiles_h;
-    const long HW = (long)H * W;
-
-    for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int tw = t % tiles_w;
-        const int th = (t / tiles_w) % tiles_h;
-        const int b = t / ((long)tiles_w * tiles_h);
-        const int h0 = th * FT_H, w0 = tw * FT_W;
-        __syncthreads();  // previous tile consumed (and, first time, weights staged)
-        for (int i = threadIdx.x; i < 3 * (FT_H + 2) * (FT_W + 2); i += blockDim.x) {
-            const int x = i % (FT_W + 2);
-            const int r = (i / (FT_W + 2)) % (FT_H + 2);
-            const int ci = i / ((FT_W + 2) * (FT_H + 2));
-            const int hh = h0 + r - 1, ww = w0 + x - 1;
-            inp[ci][r][x] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + ((long)b * 3 + ci) * HW + (long)hh * W + ww) : 0.f;
-        }
-        __syncthreads();
-
-        float2 acc[4][8];  // [pixel][channel pair]: FFMA2 operands are 64-bit register pairs
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(bs[g * 16 + 2 * c], bs[g * 16 + 2 * c + 1]);
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const float* ip = &inp[ci][row + ky][4 * quad];
-                const float4 x0 = *reinterpret_cast<const float4*>(ip);
-                const float2 x1 = *reinterpret_cast<const float2*>(ip + 4);
-                const float2 xin[6] = {make_float2(x0.x, x0.x), make_float2(x0.y, x0.y), make_float2(x0.z, x0.z),
-                                       make_float2(x0.w, x0.w), make_float2(x1.x, x1.x), make_float2(x1.y, x1.y)};
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * 9 + ky * 3 + kx) * G + g) * FG_STRIDE);
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 wv = wp[c4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            acc[j][2 * c4 + 0] = __ffma2_rn(xin[j + kx], make_float2(wv.x, wv.y), acc[j][2 * c4 + 0]);
-                            acc[j][2 * c4 + 1] = __ffma2_rn(xin[j + kx], make_float2(wv.z, wv.w), acc[j][2 * c4 + 1]);
-                        }
-                    }
-                }
-            }
-        const int h = h0 + row;
-        if (h < H) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = w0 + 4 * quad + j;
-                if (x >= W) continue;
-                const long pix = ((long)b * H + h) * W + x;
-                float4* op = reinterpret_cast<float4*>(out + pix * Cout + g * 16);
-                uint32_t bits = 0;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float4 o;
-                    o.x = fmaxf(acc[j][2 * c4].x, 0.f); o.y = fmaxf(acc[j][2 * c4].y, 0.f);
-                    o.z = fmaxf(acc[j][2 * c4 + 1].x, 0.f); o.w = fmaxf(acc[j][2 * c4 + 1].y, 0.f);
-                    if (do_round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                    op[c4] = o;
-                    bits |= ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << (4 * c4);
-                }
-                // sign bitmap of the output (16 channels of this thread = one half-word): the ReLU mask dgrad reads
-                if (mask16) mask16[pix * (Cout / 16) + g] = (uint16_t)bits;
-            }
-        }
+    if (tv_out) {
+        double v[1] = {(double)tv_local}, tot[1];
+        if (grid_sum<1, FT_THREADS>(v, tv_partials, tv_counter, tot)) *tv_out = tv_strength * (float)tot[0];
     }
 }
 
@@ -297,15 +252,21 @@ conv_first_gather_kernel(const float* __restrict__ T /*NHWC [B][H][W][32]*/, flo
 }  // namespace
 
 int conv_first_fwd_launch(const float* img, const float* w, const float* bias, float* out, uint32_t* mask_out, int B,
-                          int H, int W, int Cout, int round, cudaStream_t st) {
+                          int H, int W, int Cout, int round, cudaStream_t st, const ConvFirstTV* tv) {
     MAUA_REQUIRE(Cout == 64, "conv_first_fwd: the image layer must have 64 output channels (got %d)", Cout);
     const long ntiles = (long)B * ((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H);
-    long blocks = ntiles > 148L * 8 ? 148L * 8 : ntiles;
-    const char* f2 = getenv("MAUA_CONV1_FFMA2");  // packed FFMA2 by default (bit-identical, verified on B200); 0: scalar FFMA
+    long blocks = ntiles > 148L * 6 ? 148L * 6 : ntiles;
+    MAUA_REQUIRE(!tv || (tv->out && tv->partials && tv->counter && blocks <= tv->max_blocks), "conv_first_fwd: bad TVLoss arguments");
+    const char* f2 = getenv("MAUA_CONV1_FFMA2");  // packed FFMA2 by default (bit-identical to scalar FFMA, verified on B200)
+    uint16_t* m16 = reinterpret_cast<uint16_t*>(mask_out);
+    const float tvs = tv ? tv->strength : 0.f;
+    float* tvo = tv ? tv->out : nullptr;
+    double* tvp = tv ? tv->partials : nullptr;
+    unsigned int* tvc = tv ? tv->counter : nullptr;
     if (!f2 || atoi(f2) != 0)
-        conv_first_fwd_f2_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
+        conv_first_fwd_kernel<true><<<(int)blocks, FT_THREADS, 0, st>>>(img, w, bias, out, m16, B, H, W, round, tvs, tvo, tvp, tvc);
     else
-        conv_first_fwd_kernel<<<(int)blocks, 256, 0, st>>>(img, w, bias, out, reinterpret_cast<uint16_t*>(mask_out), B, H, W, round);
+        conv_first_fwd_kernel<false><<<(int)blocks, FT_THREADS, 0, st>>>(img, w, bias, out, m16, B, H, W, round, tvs, tvo, tvp, tvc);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

@@ -45,6 +45,13 @@ constexpr int ROW_BYTES = TILE_W * 128;     // one image row of the tile: 16 pix
 struct ConvKParams {
     int B, H, W, Cin, Cout, ntaps, K2;
     int tiles_w, tiles_h, n_tiles, total_tiles;
+    // Work items: tiles [0, full_tiles) are computed whole; each of the remaining total_tiles - full_tiles tiles (the last,
+    // partial wave of the persistent grid) is split along K into `split` parts that run on different CTAs (pairs) at the
+    // same time.  Parts 0 .. split-2 dump their raw accumulators into splitk_ws; the last part adds them (fixed order:
+    // deterministic) and runs the fused epilogue.
+    int full_tiles, split, total_items;
+    float* splitk_ws;
+    unsigned int* splitk_flags;
     int direct;  // 1: register -> global epilogue (needed for the content / addend / fp32-mask terms), 0: TMA-store epilogue
     ConvEpilogue ep;
 };
@@ -119,6 +126,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ng2 = p.K2 / KCHUNK;                          // aux groups
     const int ng = ng1 + ng2;
 
+    struct Item { int tile, g0, g1, part, nparts, slot; };
+    auto get_item = [&](int it) {
+        Item o;
+        if (it < p.full_tiles) {
+            o.tile = it; o.g0 = 0; o.g1 = ng; o.part = 0; o.nparts = 1; o.slot = 0;
+        } else {
+            const int r = it - p.full_tiles;
+            o.slot = r / p.split;
+            o.part = r - o.slot * p.split;
+            o.nparts = p.split;
+            o.tile = p.full_tiles + o.slot;
+            o.g0 = ng * o.part / p.split;
+            o.g1 = ng * (o.part + 1) / p.split;
+        }
+        return o;
+    };
+
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -175,10 +199,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (CG == 2) tma_load_2d_2sm(dst, m, bar, c0, c1); else tma_load_2d(dst, m, bar, c0, c1);
         };
         uint32_t ia = 0, ib = 0;  // ring counters across tiles
-        for (int tile = cta_tile0; tile < p.total_tiles; tile += cta_tile_step) {
+        for (int it = cta_tile0; it < p.total_items; it += cta_tile_step) {
+            const Item item = get_item(it);
             int b, h0, w0, n0;
-            decode(tile, b, h0, w0, n0);
-            for (int g = 0; g < ng; ++g) {
+            decode(item.tile, b, h0, w0, n0);
+            for (int g = item.g0; g < item.g1; ++g) {
                 const int sa = ia % NA;
                 mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
                 ++ia;
@@ -225,13 +250,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         auto commit = [&](uint64_t* bar) { if (CG == 2) umma_commit_2sm(bar); else umma_commit(bar); };
         uint32_t ia = 0, ib = 0, lt = 0;
-        for (int tile = cta_tile0; tile < p.total_tiles; tile += cta_tile_step, ++lt) {
+        for (int it = cta_tile0; it < p.total_items; it += cta_tile_step, ++lt) {
+            const Item item = get_item(it);
             const int acc = lt % NACC;
             mbar_wait(&tmem_empty_bar[acc], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
             uint32_t started = 0;  // 0 until the first MMA of this tile has been issued (per sub-tile: same flag)
-            for (int g = 0; g < ng; ++g) {
+            for (int g = item.g0; g < item.g1; ++g) {
                 const int sa = ia % NA;
                 mbar_wait(&a_full[sa], (ia / NA) & 1);
                 ++ia;
@@ -258,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         commit(&b_empty[sb]);  // frees the weight slot (in both CTAs) once these MMAs have read it
                         if (j == nsteps - 1) commit(&a_empty[sa]);  // ... and the activation box after its last tap
-                        if (j == nsteps - 1 && g == ng - 1) commit(&tmem_full_bar[acc]);  // accumulator complete
+                        if (j == nsteps - 1 && g == item.g1 - 1) commit(&tmem_full_bar[acc]);  // accumulator complete
                     }
                     __syncwarp();
                     started = 1;
@@ -276,13 +302,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int words = p.Cout >> 5;  // 32-channel words of the sign bitmaps per pixel
         const bool issuer = (threadIdx.x == 128);
         uint32_t lt = 0, box = 0;
-        for (int tile = cta_tile0; tile < p.total_tiles; tile += cta_tile_step, ++lt) {
+        for (int it = cta_tile0; it < p.total_items; it += cta_tile_step, ++lt) {
+            const Item item = get_item(it);
             int b, h0, w0, n0;
-            decode(tile, b, h0, w0, n0);
+            decode(item.tile, b, h0, w0, n0);
             const int acc = lt % NACC;
             mbar_wait(&tmem_full_bar[acc], (lt / NACC) & 1);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            // split-K: workspace of this tile's partial accumulators, [part][rank][m][row][BN]; flags [slot][rank][quadrant]
+            constexpr size_t kPartElems = static_cast<size_t>(MT) * 128 * BN;
+            float* ws_tile = p.splitk_ws + static_cast<size_t>(item.slot) * (p.split - 1) * CG * kPartElems;
+            unsigned int* flag = p.splitk_flags + (static_cast<size_t>(item.slot) * CG + rank) * 4 + q;
+            if (item.part < item.nparts - 1) {
+                // not the last part of a split tile: hand the raw partial sums to the CTA (pair) that holds the last part
+                float* dst = ws_tile + (static_cast<size_t>(item.part) * CG + rank) * kPartElems;
+#pragma unroll 1
+                for (int m = 0; m < MT; ++m)
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 32) {
+                        float v[32];
+                        tmem_ld_x32(t_base + m * BN + c, v);
+                        float4* d4 = reinterpret_cast<float4*>(dst + (static_cast<size_t>(m) * 128 + row) * BN + c);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) __stcg(d4 + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+                    }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(flag, 1u);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+                continue;
+            }
+            const int nprev = item.nparts - 1;  // partial sums to add before the epilogue (0 for an unsplit tile)
+            if (nprev > 0) {
+                if (lane == 0) {
+                    while (ld_acquire_gpu(flag) < static_cast<unsigned int>(nprev)) __nanosleep(64);
+                }
+                __syncwarp();
+            }
+            auto add_partials = [&](float* v, int n, int m, int c) {
+                for (int pp = 0; pp < nprev; ++pp) {
+                    const float4* s4 = reinterpret_cast<const float4*>(
+                        ws_tile + (static_cast<size_t>(pp) * CG + rank) * kPartElems + (static_cast<size_t>(m) * 128 + row) * BN + c);
+                    for (int k = 0; k < n / 4; ++k) {
+                        const float4 u = __ldcg(s4 + k);
+                        v[4 * k] += u.x; v[4 * k + 1] += u.y; v[4 * k + 2] += u.z; v[4 * k + 3] += u.w;
+                    }
+                }
+            };
             if (!p.direct) {
                 // TMEM -> registers -> fused epilogue -> swizzled staging box in shared memory -> TMA store.  A warp-wide
                 // 16-byte store straight to global would touch 32 different lines (the lanes are 32 different pixels): the
@@ -298,6 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int c = 0; c < BN; c += 32, ++box) {
                         float v[32];
                         tmem_ld_x32(t_base + m * BN + c, v);
+                        if (nprev > 0) add_partials(v, 32, m, c);
                         if (ep.bias) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
@@ -384,6 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int c = 0; c < BN; c += 16) {
                     float v[16];
                     tmem_ld_x16(t_base + m * BN + c, v);
+                    if (nprev > 0) add_partials(v, 16, m, c);
                     if (valid) {
                         if (ep.bias) {
 #pragma unroll
@@ -450,7 +521,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // all TMEM reads of this warp are complete (the loads wait): hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+            if (lane == 0) {
+                if (nprev > 0) *flag = 0u;  // re-arm for the next launch (this warp was the flag's only reader)
+                if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]);
+            }
         }
         if (issuer && !p.direct) bulk_wait_group<0>();  // outstanding output stores must land before the CTA retires
     }
@@ -549,6 +623,86 @@ int num_sms() {
     return n;
 }
 
+constexpr int kMaxSplit = 8;
+constexpr int kMinGroupsPerPart = 4;
+
+// Split-K plan of a launch: the tiles of the last partial wave (all tiles when there are fewer tiles than CTA units) are
+// split into `split` K-ranges each, as long as every range keeps >= kMinGroupsPerPart k-groups.
+struct SplitPlan { int full_tiles, split, items; };
+SplitPlan plan_split(long tiles, int units, int ngroups, bool allowed) {
+    SplitPlan sp{(int)tiles, 1, (int)tiles};
+    const int rem = (int)(tiles % units);
+    if (!allowed || rem == 0) return sp;
+    int s = units / rem;
+    if (s > kMaxSplit) s = kMaxSplit;
+    if (s > ngroups / kMinGroupsPerPart) s = ngroups / kMinGroupsPerPart;
+    if (s < 2) return sp;
+    sp.full_tiles = (int)tiles - rem;
+    sp.split = s;
+    sp.items = sp.full_tiles + rem * s;
+    return sp;
+}
+int conv_groups(const ConvArgs& a) {
+    return (a.ntaps == 9 ? 3 * (a.Cin / KCHUNK) : (a.ntaps == 1 ? a.Cin / KCHUNK : 0)) + a.K2 / KCHUNK;
+}
+bool splitk_enabled() { return true; }  // the caller opts in by passing a workspace (maua_plan_set_splitk / MAUA_SPLITK=1)
+
+// Tile selection: relative MAC rates of the tile shapes measured on B200 (tools/sweep_conv.sh, profiles/ round 1) times
+// the occupancy of the waves.  What the sweep shows: with both operands in shared memory an MMA is paced by the
+// operand read (4 KB of activations + 32 B per weight row the CTA holds), so wide tiles and CTA pairs (cta_group::2,
+// each CTA holds half of the weight rows) win, and a tile needs its accumulator double-buffered in TMEM (MT * BN <= 256)
+// to keep the epilogue off the critical path.  With split-K (plan_split) the last partial wave costs 1 / split of a tile
+// time instead of a whole one, which is what decides the shape at <= 512^2 where every layer is a partial wave.
+SplitPlan choose_tile(const ConvArgs& a, int sms, bool allow_split, int& bn_out, int& mt_out, int& cg_out) {
+    auto shape_rate = [](int bn, int mt, int cg) -> double {
+        if (cg == 2) {
+            if (bn == 256) return mt == 1 ? 1.00 : 0.88;
+            if (bn == 128) return mt == 2 ? 1.00 : 0.80;
+            if (bn == 64) return mt == 2 ? 0.75 : 0.47;
+            return mt == 2 ? 0.36 : 0.30;
+        }
+        if (bn == 256) return mt == 1 ? 0.90 : 0.85;
+        if (bn == 128) return mt == 2 ? 0.73 : 0.66;
+        if (bn == 64) return mt == 2 ? 0.52 : 0.40;
+        return mt == 2 ? 0.30 : 0.25;
+    };
+    int best_bn = 32, best_mt = 1, best_cg = 1;
+    double best = -1.0;
+    SplitPlan best_sp{0, 1, 0};
+    const int ngroups = conv_groups(a);
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+        if (a.Cout % bn) continue;
+        for (int mt = 2; mt >= 1; --mt)
+            for (int cg = 2; cg >= 1; --cg) {
+                if (a.force_cg && cg != a.force_cg) continue;
+                const int units = sms / cg;
+                const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) *
+                                   ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
+                // time in units of one tile: full waves + the split last wave (1 / split, plus the hand-over of partials)
+                const SplitPlan sp = plan_split(tiles, units, ngroups, allow_split);
+                const double waves = sp.split > 1 ? (double)(sp.full_tiles / units) + 1.0 / sp.split + 0.03
+                                                  : (double)((tiles + units - 1) / units);
+                const double eff = (double)tiles / (waves * units);
+                // rows of the (pair) tile that exist: ragged bottoms waste MMA work
+                const double rows = (double)a.H / (double)(((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * cg * mt * TILE_H);
+                const double score = eff * rows * shape_rate(bn, mt, cg);
+                if (score > best) { best = score; best_bn = bn; best_mt = mt; best_cg = cg; best_sp = sp; }
+            }
+    }
+    int bn = best_bn, mt = best_mt, cg = best_cg;
+    if (const char* f = getenv("MAUA_CONV_FORCE")) {  // developer override for tile-shape experiments: "bn,mt,cg"
+        int fb = 0, fm = 0, fc = 0;
+        if (sscanf(f, "%d,%d,%d", &fb, &fm, &fc) == 3 && a.Cout % fb == 0 && (fm == 1 || fm == 2) && (fc == 1 || fc == 2) &&
+            (fb == 32 || fb == 64 || fb == 128 || fb == 256)) {
+            bn = fb; mt = fm; cg = fc;
+            const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
+            best_sp = plan_split(tiles, sms / cg, ngroups, allow_split);
+        }
+    }
+    bn_out = bn; mt_out = mt; cg_out = cg;
+    return best_sp;
+}
+
 template <int BN, int MT, int CG, bool POOL>
 int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = ConvCfg<BN, MT, CG>;
@@ -595,7 +749,10 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     p.ep = a.ep;
     p.direct = direct ? 1 : 0;
     const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
-    const int grid = CG * (p.total_tiles < units ? p.total_tiles : units);
+    const SplitPlan sp = plan_split(p.total_tiles, units, conv_groups(a), a.splitk_ws && a.splitk_flags && splitk_enabled());
+    p.full_tiles = sp.full_tiles; p.split = sp.split; p.total_items = sp.items;
+    p.splitk_ws = a.splitk_ws; p.splitk_flags = a.splitk_flags;
+    const int grid = CG * (p.total_items < units ? p.total_items : units);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -619,6 +776,18 @@ int launch_cg(const ConvArgs& a, int cg, cudaStream_t st) {
 
 }  // namespace
 
+size_t conv_splitk_ws_bytes() { return (size_t)148 * 128 * 512 * sizeof(float); }  // < 148 split parts x (MT * 128 x BN <= 512 cols)
+size_t conv_splitk_flag_words() { return 148 * 4 * 2; }
+
+// host-logic view of the launch plan (no GPU needed): tile shape + split-K plan for a layer on a device with `sms` SMs
+void conv_tile_plan(const ConvArgs& a, int sms, bool allow_split, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles, int* split) {
+    int b, m, c;
+    const SplitPlan sp = choose_tile(a, sms, allow_split && splitk_enabled(), b, m, c);
+    *bn = b; *mt = m; *cg = c;
+    *full_tiles = sp.full_tiles; *split = sp.split;
+    *split_tiles = sp.split > 1 ? (sp.items - sp.full_tiles) / sp.split : 0;
+}
+
 int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     MAUA_REQUIRE(a.ntaps == 9 || a.ntaps == 1 || a.ntaps == 0, "ntaps must be 9, 1 or 0 (got %d)", a.ntaps);
     MAUA_REQUIRE(a.ntaps > 0 || a.K2 > 0, "conv has neither a main nor an aux term");
@@ -630,47 +799,12 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     MAUA_REQUIRE(a.B >= 1 && a.H >= 1 && a.W >= 1, "bad extent B=%d H=%d W=%d", a.B, a.H, a.W);
     MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
 
-    // Tile selection: relative MAC rates of the tile shapes measured on B200 (tools/sweep_conv.sh, profiles/ round 1) times
-    // the occupancy of the last wave.  What the sweep shows: with both operands in shared memory an MMA is paced by the
-    // operand read (4 KB of activations + 32 B per weight row the CTA holds), so wide tiles and CTA pairs (cta_group::2,
-    // each CTA holds half of the weight rows) win, and a tile needs its accumulator double-buffered in TMEM (MT * BN <= 256)
-    // to keep the epilogue off the critical path.
-    auto shape_rate = [](int bn, int mt, int cg) -> double {
-        if (cg == 2) {
-            if (bn == 256) return mt == 1 ? 1.00 : 0.88;
-            if (bn == 128) return mt == 2 ? 1.00 : 0.80;
-            if (bn == 64) return mt == 2 ? 0.75 : 0.47;
-            return mt == 2 ? 0.36 : 0.30;
-        }
-        if (bn == 256) return mt == 1 ? 0.90 : 0.85;
-        if (bn == 128) return mt == 2 ? 0.73 : 0.66;
-        if (bn == 64) return mt == 2 ? 0.52 : 0.40;
-        return mt == 2 ? 0.30 : 0.25;
-    };
-    const int sms = num_sms();
-    int best_bn = 32, best_mt = 1, best_cg = 1;
-    double best = -1.0;
-    for (int bn = 256; bn >= 32; bn >>= 1) {
-        if (a.Cout % bn) continue;
-        for (int mt = 2; mt >= 1; --mt)
-            for (int cg = 2; cg >= 1; --cg) {
-                if (a.force_cg && cg != a.force_cg) continue;
-                const int units = sms / cg;
-                const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) *
-                                   ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
-                const long waves = (tiles + units - 1) / units;
-                const double eff = (double)tiles / (double)(waves * units);
-                // rows of the (pair) tile that exist: ragged bottoms waste MMA work
-                const double rows = (double)a.H / (double)(((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * cg * mt * TILE_H);
-                const double score = eff * rows * shape_rate(bn, mt, cg);
-                if (score > best) { best = score; best_bn = bn; best_mt = mt; best_cg = cg; }
-            }
-    }
-    int bn = best_bn, mt = best_mt, cg = best_cg;
-    if (const char* f = getenv("MAUA_CONV_FORCE")) {  // developer override for tile-shape experiments: "bn,mt,cg"
-        int fb = 0, fm = 0, fc = 0;
-        if (sscanf(f, "%d,%d,%d", &fb, &fm, &fc) == 3 && a.Cout % fb == 0 && (fm == 1 || fm == 2) && (fc == 1 || fc == 2) &&
-            (fb == 32 || fb == 64 || fb == 128 || fb == 256)) { bn = fb; mt = fm; cg = fc; }
+    int bn, mt, cg;
+    const SplitPlan spc = choose_tile(a, num_sms(), a.splitk_ws && a.splitk_flags && splitk_enabled(), bn, mt, cg);
+    if (getenv("MAUA_CONV_DEBUG")) {  // one line per launch: the tile shape and split-K plan that was chosen
+        fprintf(stderr, "conv_tc %dx%d Cin %d Cout %d taps %d K2 %d: BN %d MT %d CG %d, %d whole tiles + %d split x%d on %d units\n",
+                a.H, a.W, a.Cin, a.Cout, a.ntaps, a.K2, bn, mt, cg, spc.full_tiles, spc.split > 1 ? (spc.items - spc.full_tiles) / spc.split : 0,
+                spc.split, num_sms() / cg);
     }
     if (bn == 256) return mt == 2 ? launch_cg<256, 2>(a, cg, st) : launch_cg<256, 1>(a, cg, st);
     if (bn == 128) return mt == 2 ? launch_cg<128, 2>(a, cg, st) : launch_cg<128, 1>(a, cg, st);

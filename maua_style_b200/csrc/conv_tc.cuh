@@ -51,7 +51,16 @@ struct ConvArgs {
     const float* in2 = nullptr;  // NHWC [B][H][W][K2]
     const float* w2 = nullptr;   // [Cout][K2]
     ConvEpilogue ep;
+    // Split-K of the last (partial) wave of tiles (tcgen05 path): partial accumulators travel through this workspace.
+    // Optional: without it every tile is computed by one CTA (pair).  Sizes: conv_splitk_ws_bytes() / conv_splitk_flag_words();
+    // the flag words must be zero before the first launch and are left zero by every launch.
+    float* splitk_ws = nullptr;
+    unsigned int* splitk_flags = nullptr;
 };
+void conv_tile_plan(const ConvArgs& a, int sms, bool allow_split, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles,
+                    int* split);
+size_t conv_splitk_ws_bytes();
+size_t conv_splitk_flag_words();
 
 // sign bitmap of an NHWC activation: bits[pixel * (C/32) + c/32] bit (c % 32) = x[pixel][c] > 0   (C % 32 == 0)
 int relu_mask_bits_launch(const float* x, uint32_t* bits, long npix, int C, cudaStream_t st);
@@ -68,10 +77,18 @@ inline int conv_dispatch(ConvArgs a, int impl, cudaStream_t st) {
     return conv_tc_launch(a, st);
 }
 
-// conv1_1 forward: NCHW 3-channel image -> NHWC Cout, bias + ReLU, fp32 FFMA (K = 27).
+// conv1_1 forward: NCHW 3-channel image -> NHWC Cout, bias + ReLU, fp32 FFMA (K = 27).  Optionally also the TVLoss value
+// of the image (loss.py:229-233): *out = strength * (sum |x[h]-x[h-1]| + sum |x[w]-x[w-1]|), deterministic grid sum.
+struct ConvFirstTV {
+    float strength = 0.f;
+    float* out = nullptr;
+    double* partials = nullptr;      // ReduceScratch of the caller
+    unsigned int* counter = nullptr;
+    int max_blocks = 0;
+};
 int conv_first_fwd_launch(const float* img, const float* w /*[Cout][3][3][3]*/, const float* bias, float* out,
                           uint32_t* mask_out /*optional sign bitmap*/, int B, int H, int W, int Cout, int round,
-                          cudaStream_t st);
+                          cudaStream_t st, const ConvFirstTV* tv = nullptr);
 
 // conv1_1 dgrad (+ fused image-side tail): NHWC Cout gradient -> NCHW 3-channel image gradient,
 // plus TV gradient and temporal ContentLoss gradient.

@@ -128,6 +128,10 @@ struct maua_plan {
     std::vector<Entry> entries;
     std::vector<Tap> taps;
     int avg_pool = 0;
+    // K-split of the last partial wave of conv tiles (conv_tc.cu).  Measured on B200 in round 2 (profiles/r02_splitk_ab.txt):
+    // the hand-over of partial accumulators through L2 costs ~20 us per split wave, more than the idle SMs it recovers at
+    // every size from 256^2 to 2048^2, so it is OFF by default (MAUA_SPLITK=1 / maua_plan_set_splitk turn it on).
+    bool splitk = false;
     bool fuse_pool = true;        // pool inside the producing conv's epilogue (MAUA_FUSE_POOL=0 at plan creation: separate pass)
     size_t weight_bytes = 0;
     // workspaces
@@ -139,6 +143,8 @@ struct maua_plan {
     size_t gbuf_elems = 0;
     void* reduce_ws = nullptr;
     float* coef2 = nullptr;       // [n_taps + 2] scaled coefficients
+    float* splitk_ws = nullptr;   // partial accumulators of K-split conv tiles (conv_tc.cu)
+    unsigned int* splitk_flags = nullptr;
     size_t tap_bytes = 0;
     // last forward
     int H = 0, W = 0;
@@ -265,6 +271,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     p->device = device;
     p->avg_pool = d->avg_pool;
     if (const char* f = getenv("MAUA_FUSE_POOL")) p->fuse_pool = atoi(f) != 0;
+    if (const char* f = getenv("MAUA_SPLITK")) p->splitk = atoi(f) != 0;
     p->begin = begin;
     p->last_stage = (end == d->n_entries);
     memset(&p->img_io, 0, sizeof(p->img_io));
@@ -382,6 +389,9 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     }
     alloc(&p->reduce_ws, maua_reduce_workspace_bytes());
     alloc((void**)&p->coef2, (MAUA_MAX_TAPS + 2) * sizeof(float));
+    alloc((void**)&p->splitk_ws, conv_splitk_ws_bytes());
+    alloc((void**)&p->splitk_flags, conv_splitk_flag_words() * sizeof(unsigned int));
+    if (e == cudaSuccess && ok) e = cudaMemset(p->splitk_flags, 0, conv_splitk_flag_words() * sizeof(unsigned int));
     if (e == cudaSuccess && ok) e = cudaMemset(p->reduce_ws, 0, maua_reduce_workspace_bytes());
     if (e == cudaSuccess && ok) e = cudaDeviceSynchronize();
     if (e != cudaSuccess || !ok) {
@@ -422,6 +432,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     cudaFree(p->bits_arena);
     for (int i = 0; i < 3; ++i) cudaFree(p->gbuf[i]);
     cudaFree(p->reduce_ws); cudaFree(p->coef2);
+    cudaFree(p->splitk_ws); cudaFree(p->splitk_flags);
     delete p;
 }
 
@@ -463,6 +474,12 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
 MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* p, int enable) {
     MAUA_REQUIRE(p, "maua_plan_set_fuse_pool: null plan");
     p->fuse_pool = enable != 0;
+    return MAUA_OK;
+}
+
+MAUA_API int maua_plan_set_splitk(maua_plan_t* p, int enable) {
+    MAUA_REQUIRE(p, "maua_plan_set_splitk: null plan");
+    p->splitk = enable != 0;
     return MAUA_OK;
 }
 
@@ -535,11 +552,10 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     prof_mark(p, st, "begin_fwd", -1, 0, 0);
 
     // ---- image-side modules: TVLoss, temporal ContentLoss ----
+    bool tv_pending = false;  // TVLoss value: folded into conv1_1's forward (which reads the image anyway) when that runs
     if (p->img_io.tv_mode == MAUA_MODE_LOSS) {
         MAUA_REQUIRE(losses_out, "losses_out is required in loss mode");
-        if ((rc = tv_value_launch(image, 3, H, W, p->img_io.tv_strength, losses_out + nt, rs, st))) return rc;
-        p->launches_fwd++;
-        prof_mark(p, st, "tv_value", -1, 0, 4.0 * img_elems);
+        tv_pending = true;
         p->factors[nt] = 1.f;
     }
     bool temporal_active = false;
@@ -575,6 +591,12 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     const int n_ent = (int)p->entries.size();
     if (boundary_out) last_needed = n_ent - 1;  // the next stage consumes this stage's last activation
     p->last_entry = last_needed;
+    if (tv_pending && !(last_needed >= 0 && p->entries[0].image_layer)) {
+        if ((rc = tv_value_launch(image, 3, H, W, p->img_io.tv_strength, losses_out + nt, rs, st))) return rc;
+        p->launches_fwd++;
+        prof_mark(p, st, "tv_value", -1, 0, 4.0 * img_elems);
+        tv_pending = false;
+    }
 
     // ---- feature stack ----
     const float* cur = p->stage_input;
@@ -584,7 +606,13 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
         Entry& e = p->entries[i];
         float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
         if (e.image_layer) {
-            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, rnd, st))) return rc;
+            ConvFirstTV tv;
+            if (tv_pending) {
+                tv.strength = p->img_io.tv_strength; tv.out = losses_out + nt;
+                tv.partials = rs.partials; tv.counter = rs.counter; tv.max_blocks = rs.max_blocks;
+            }
+            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, rnd, st, tv_pending ? &tv : nullptr)))
+                return rc;
             if (hand_off)
                 MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
         } else if (e.pool) {
@@ -602,6 +630,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.in = cur; a.wg = exact ? e.wg32 : e.wg;
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = rnd;
             a.ep.mask_out = e.bits;
+            if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
@@ -775,6 +804,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     };
     auto run_conv = [&](ConvArgs& a) -> int {
         p->launches_bwd++;
+        if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
         const int r = conv_dispatch(a, p->impl, st);
         const double px = (double)a.H * a.W;
         // algorithmic work: dgrad GEMM + StyleLoss backward GEMM; bytes: gradient in + out, mask / feature read

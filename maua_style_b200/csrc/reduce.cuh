@@ -12,9 +12,10 @@ constexpr int kReduceThreads = 256;
 
 // Call from all threads of every block (blockDim.x == kReduceThreads).  Returns true in thread 0 of the last block
 // only, with tot[] holding the grid totals.
-template <int NV>
+template <int NV, int NT = kReduceThreads>
 __device__ __forceinline__ bool grid_sum(const double (&v)[NV], double* __restrict__ partials, unsigned int* counter,
                                          double (&tot)[NV]) {
+    constexpr int kReduceThreads = NT;  // blockDim.x of the calling kernel
     __shared__ double sh[NV][kReduceThreads / 32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -268,6 +268,7 @@ class B200Net(nn.Module):
             st["loss_vec"].zero_()
             _lib.check(self._lib.maua_plan_set_impl(st["plan"], default_impl()), "maua_plan_set_impl")
             _lib.check(self._lib.maua_plan_set_profile(st["plan"], 0), "maua_plan_set_profile")
+            _lib.check(self._lib.maua_plan_set_splitk(st["plan"], int(os.environ.get("MAUA_SPLITK", "0") == "1")), "maua_plan_set_splitk")
             _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(os.environ.get("MAUA_FUSE_POOL", "1") != "0")),
                        "maua_plan_set_fuse_pool")
         self._plan = self._stages[0]["plan"]
@@ -307,6 +308,11 @@ class B200Net(nn.Module):
         """Pool inside the producing conv's epilogue (csrc/conv_tc.cu, the default) or as a separate pass."""
         for st in self._stages:
             _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(enable)), "maua_plan_set_fuse_pool")
+
+    def set_splitk(self, enable: bool):
+        """K-split of the last partial wave of conv tiles (csrc/conv_tc.cu; off by default)."""
+        for st in self._stages:
+            _lib.check(self._lib.maua_plan_set_splitk(st["plan"], int(enable)), "maua_plan_set_splitk")
 
     def device_bytes(self) -> int:
         return sum(int(self._lib.maua_plan_device_bytes(st["plan"])) for st in self._stages)

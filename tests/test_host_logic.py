@@ -153,3 +153,31 @@ def test_sharded_batch_normalises_the_weights_once_per_image(monkeypatch):
     out = shard.stylize_images([1, 2, 3], [], [None] * 3, 1, args, info=shard.RankInfo(0, 1, 0), net=net, losses=mods)
     assert sorted(out) == [0, 1, 2]
     assert seen == [[5.0, 100.0]] * 3 and [m.strength for m in mods] == [5.0, 100.0]
+
+
+def test_conv_tile_plan_host_logic():
+    """maua_conv_tile_plan (csrc/conv_tc.cu choose_tile / plan_split), no GPU: shapes and K-split plans for VGG layers on 148
+    SMs.  Without split the 256-channel layers at 256 x 256 pixels take 256 pair tiles (3.46 waves of 74 pairs); with split
+    the last 34 tiles are halved along K; a split never leaves fewer than 4 k-groups per part."""
+    import ctypes as C
+
+    from maua_style_b200 import _lib
+
+    lib = _lib.load()
+
+    def plan(h, w, cin, cout, taps=9, k2=0, split=0, sms=148):
+        p = (C.c_int * 6)()
+        assert lib.maua_conv_tile_plan(h, w, cin, cout, taps, k2, sms, split, p) == 0
+        return list(p)
+
+    assert plan(256, 256, 256, 256) == [256, 1, 2, 256, 0, 1]
+    assert plan(256, 256, 256, 256, split=1) == [256, 1, 2, 222, 34, 2]
+    assert plan(1024, 1024, 64, 64) == [64, 2, 2, 2048, 0, 1]
+    bn, mt, cg, whole, split_tiles, s = plan(16, 16, 512, 512, split=1)
+    assert whole == 0 and 2 <= s <= 8 and split_tiles * s <= 148 // cg
+    bn, mt, cg, whole, split_tiles, s = plan(16, 16, 64, 64, split=1)   # 6 k-groups: too short to split
+    assert s == 1 and split_tiles == 0
+    for hw in (5, 37, 724, 1448):                                        # every extent gets a plan that covers it
+        bn, mt, cg, whole, split_tiles, s = plan(hw, hw, 128, 128)
+        tiles = -(-hw // 16) * -(-hw // (8 * mt * cg)) * (128 // bn)
+        assert whole + split_tiles == tiles

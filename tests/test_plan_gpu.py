@@ -242,6 +242,37 @@ def test_cta_pair_and_single_cta_plans_agree(ckpt):
     assert torch.allclose(vecs[0], vecs[1], rtol=1e-4)
 
 
+@pytest.mark.parametrize("hw", [(90, 122), (256, 256)])
+def test_split_k_plan_agrees_with_the_unsplit_plan(ckpt, hw):
+    """K-split conv tiles (opt-in, maua_plan_set_splitk): partial accumulators of the last wave's tiles are summed in a fixed
+    order by the CTA that holds the last K-range, so the plan stays deterministic and equals the unsplit plan up to fp32
+    summation order (average pooling: no arg-max flips in the comparison)."""
+    from maua_style_b200 import optim
+
+    z, meta = load_golden("adam_gram_90x122")
+    meta = dict(meta)
+    meta["over"] = dict(meta["over"], pooling="avg")
+    meta["h"], meta["w"] = hw
+    meta["style_hw"] = [list(hw)]
+    content, styles, init = golden_inputs(meta)
+    res = []
+    for split in (False, True, True):
+        args, net, losses, _ = build(ckpt, meta)
+        net.set_splitk(split)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, styles, args)
+        for m in losses:
+            m.mode = "loss"
+        v, g = optim.feval(net, init.clone().cuda())
+        res.append((v.clone(), g.clone()))
+        del net, losses
+    err = rel(res[1][1], res[0][1])
+    report(f"split-K vs unsplit plan gradient {hw} (avg pool) rel {err:.2e}")
+    assert err < 5e-4
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-4)
+    assert torch.equal(res[1][1], res[2][1]) and torch.equal(res[1][0], res[2][0])  # deterministic
+
+
 def test_temporal_loss_and_autograd_interface(ckpt):
     """vid_img path: set_temporal_targets + weighted temporal ContentLoss (loss.py:46-54) through net(x).backward()."""
     from maua_style_b200 import optim
