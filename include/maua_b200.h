@@ -215,6 +215,10 @@ MAUA_API void maua_lbfgs_destroy(maua_lbfgs_t* s);
 /* One L-BFGS iteration given the gradient at the current parameters: updates history, computes the two-loop
  * direction and applies param += t * d.  Fully asynchronous (all scalars stay on the device). */
 MAUA_API int maua_lbfgs_step(maua_lbfgs_t* s, float* param, const float* grad, maua_stream_t stream);
+/* Back to the state right after maua_lbfgs_create (empty history, first-step rule armed) without re-allocating the
+ * history rings: what a caller that optimises many images of one size with the same state object does between images
+ * (the reference constructs a new torch.optim.LBFGS per optimize() call, optim.py:180-191). */
+MAUA_API int maua_lbfgs_reset(maua_lbfgs_t* s, maua_stream_t stream);
 /* Debug / test read-back (synchronises): n_iter, history length, halted flag. */
 MAUA_API int maua_lbfgs_query(maua_lbfgs_t* s, int* n_iter, int* hist_len, int* halted, maua_stream_t stream);
 

@@ -2,6 +2,7 @@
 // The plan-level entry points live in plan.cu.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "conv_tc.cuh"
@@ -49,6 +50,12 @@ static int current_device_ok() {
     int rc = check_device_arch(dev);
     if (rc == MAUA_OK) checked_dev = dev;
     return rc;
+}
+
+bool pdl_enabled(int kind) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAUA_PDL"); v = e ? atoi(e) : (PDL_CONV | PDL_GRAM | PDL_EDGE); }
+    return (v & kind) != 0;
 }
 
 ReduceScratch scratch_from_workspace(void* ws) {

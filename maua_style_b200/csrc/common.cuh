@@ -4,6 +4,7 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld) and
 // the UMMA shared-memory / instruction descriptors.  No CUTLASS dependency.
 #pragma once
+#include <cstring>
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -58,6 +59,41 @@ inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, unsigned long long* 
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) *done_mask |= bit;
     return e;
+}
+
+// --------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The iteration is a chain of ~45 dependent kernels; at <= 512^2 most of them run
+// for a few microseconds, so launch latency + prologue (barrier init, TMEM allocation, descriptor prefetch, weight
+// staging) is a large share of the step.  Kernels launched through launch_pdl() may start while their predecessor in the
+// stream is still draining: everything before pdl_wait() (which must not touch memory another kernel writes or reads)
+// overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible.
+// pdl_trigger() lets the successor begin its own launch as early as possible.  Both are no-ops in a kernel that was
+// launched normally, and stream capture records the edge as a programmatic dependency of the CUDA graph.
+// MAUA_PDL is a bit mask of kernel families (PdlKind) that carry the launch attribute; 0 = plain stream order.  Default:
+// convolutions + Gram + image-edge kernels.  Measured on B200 (profiles/r02_pdl_ab.txt): -3.5 % per iteration at 256^2,
+// -2.7 % at 512^2, neutral at 1024^2; with the L-BFGS streaming kernels included the step gets SLOWER at >= 1024^2
+// (+0.2 ms at 1024^2, +0.9 ms at 2048^2: their balanced-span grids assume they own the SMs), so they launch normally.
+// --------------------------------------------------------------------------------------------
+MAUA_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MAUA_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// kernel families (bits of MAUA_PDL, default: all): which launches carry the programmatic-serialization attribute
+enum PdlKind { PDL_CONV = 1, PDL_LBFGS = 2, PDL_POINTWISE = 4, PDL_GRAM = 8, PDL_EDGE = 16 };
+bool pdl_enabled(int kind);  // api.cu
+
+template <int KIND = PDL_POINTWISE, class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled(KIND) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -54,6 +54,8 @@ conv_first_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w
         ws[(k * G + g) * FG_STRIDE + c4 * 4 + e] = w[i];
     }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+    pdl_wait();  // the (frozen) weights were staged while the optimizer kernel that writes the image was still draining
+    pdl_trigger();
 
     const int g = threadIdx.x & 3;
     const int oct = (threadIdx.x >> 2) & 7;
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(256)
 conv_first_gather_kernel(const float* __restrict__ T /*NHWC [B][H][W][32]*/, float* __restrict__ gimg, int B, int H,
                          int W, ImageTail tail) {
     __shared__ float tile[GH * GH * GPS];
+    pdl_wait();
+    pdl_trigger();
     const int tiles_w = (W + GT - 1) / GT, tiles_h = (H + GT - 1) / GT;
     const long ntiles = (long)B * tiles_w * tiles_h;
     const long HW = (long)H * W;
@@ -264,10 +268,11 @@ int conv_first_fwd_launch(const float* img, const float* w, const float* bias, f
     double* tvp = tv ? tv->partials : nullptr;
     unsigned int* tvc = tv ? tv->counter : nullptr;
     if (!f2 || atoi(f2) != 0)
-        conv_first_fwd_kernel<true><<<(int)blocks, FT_THREADS, 0, st>>>(img, w, bias, out, m16, B, H, W, round, tvs, tvo, tvp, tvc);
+        MAUA_CUDA_CHECK(launch_pdl<PDL_EDGE>(conv_first_fwd_kernel<true>, dim3((unsigned)blocks), dim3(FT_THREADS), 0, st, img, w, bias, out, m16, B, H,
+                                   W, round, tvs, tvo, tvp, tvc));
     else
-        conv_first_fwd_kernel<false><<<(int)blocks, FT_THREADS, 0, st>>>(img, w, bias, out, m16, B, H, W, round, tvs, tvo, tvp, tvc);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+        MAUA_CUDA_CHECK(launch_pdl<PDL_EDGE>(conv_first_fwd_kernel<false>, dim3((unsigned)blocks), dim3(FT_THREADS), 0, st, img, w, bias, out, m16, B, H,
+                                   W, round, tvs, tvo, tvp, tvc));
     return MAUA_OK;
 }
 
@@ -294,8 +299,7 @@ int conv_first_dgrad_launch(const float* gout, const float* wt, float* gimg, int
     if (rc) return rc;
     const long ntiles = (long)B * ((W + GT - 1) / GT) * ((H + GT - 1) / GT);
     long blocks = ntiles > 148L * 8 ? 148L * 8 : ntiles;
-    conv_first_gather_kernel<<<(int)blocks, 256, 0, st>>>(T, gimg, B, H, W, tail);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl<PDL_EDGE>(conv_first_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, st, T, gimg, B, H, W, tail));
     return MAUA_OK;
 }
 

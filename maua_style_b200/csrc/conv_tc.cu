@@ -170,6 +170,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();     // everything above (descriptor prefetch, barrier init, TMEM allocation) overlapped the previous kernel's tail
+    pdl_trigger();
 
     auto decode = [&](int tile, int& b, int& h0, int& w0, int& n0) {
         const int nt = tile % p.n_tiles;
@@ -759,11 +761,20 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled(PDL_CONV)) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CG > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     MAUA_CUDA_CHECK((cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG, POOL>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p)));
     return MAUA_OK;
 }

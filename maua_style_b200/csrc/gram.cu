@@ -97,6 +97,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
+    pdl_trigger();
 
     // producer / MMA roles run warp-converged; one lane chosen by elect.sync issues (see conv_tc.cu)
     if (warp == 0) {
@@ -238,6 +240,8 @@ gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long 
                      float* __restrict__ loss_out, double* red_partials, unsigned int* counter) {
     constexpr int NO = kReduceThreads / G;  // outputs per block round
     __shared__ float sh[G][NO + 1];
+    pdl_wait();
+    pdl_trigger();
     const int tx = threadIdx.x % NO, ty = threadIdx.x / NO;
     const long total = (long)C * C;
     double acc = 0.0;
@@ -333,8 +337,7 @@ int launch_gram_nacc(const CUtensorMap& tm, const GramParams& p, int ntiles, cud
     using Cfg = GramCfg<BN, OFFDIAG>;
     static unsigned long long attr_done = 0;
     MAUA_CUDA_CHECK((ensure_dynamic_smem(gram_tc_kernel<BN, OFFDIAG, NACC>, Cfg::SMEM_BYTES, &attr_done)));
-    gram_tc_kernel<BN, OFFDIAG, NACC><<<dim3(ntiles, p.nsplit), 256, Cfg::SMEM_BYTES, st>>>(tm, p);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl<PDL_GRAM>(gram_tc_kernel<BN, OFFDIAG, NACC>, dim3(ntiles, p.nsplit), dim3(256), Cfg::SMEM_BYTES, st, tm, p));
     return MAUA_OK;
 }
 
@@ -423,10 +426,11 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
         rp = fuse->rs.partials; cnt = fuse->rs.counter;
     }
     const float* mu = (use_cov && !centred) ? mean_out : nullptr;
-#define MAUA_FINALIZE(GG) gram_finalize_kernel<GG><<<fgrid, kReduceThreads, 0, st>>>(partial, nsplit, C, P, full, mu, gram, tgt, dif, sc, lout, rp, cnt)
+#define MAUA_FINALIZE(GG)                                                                                                          \
+    MAUA_CUDA_CHECK(launch_pdl<PDL_GRAM>(gram_finalize_kernel<GG>, dim3(fgrid), dim3(kReduceThreads), 0, st, (const float*)partial, nsplit, C, P, \
+                               full, mu, gram, tgt, dif, sc, lout, rp, cnt))
     if (G == 8) MAUA_FINALIZE(8); else if (G == 4) MAUA_FINALIZE(4); else if (G == 2) MAUA_FINALIZE(2); else MAUA_FINALIZE(1);
 #undef MAUA_FINALIZE
-    MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
 

@@ -78,6 +78,8 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a
 //    [G0 + {0: y_new.s_new, 1: y_new.y_new, 2: g.g, 3: |g|_1, 4: s_new.g, 5: y_new.g}].
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(const Args a) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float acc[];  // [nacc]
     __shared__ float red[kThreads / 32][2 * kNV];
     const LbfgsState* st = a.st;
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(const Args a) {
 // 2. deterministic reduction of the per-CTA partials: one warp per dot product, fixed lane / shuffle order
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lbfgs_reduce_kernel(const Args a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.st->halted) return;
     const int nacc = kNV * (a.K + 1) + kNG;
     const int idx = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -229,6 +233,8 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 constexpr int kPerLane = (kMaxHist + 31) / 32;  // history entries owned by one lane of the solver warp
 
 __global__ void __launch_bounds__(kThreads) lbfgs_scalar_kernel(const Args a) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double mats[];  // optional cache of SY (and YY): [ring][ring] each
     __shared__ double sh[kThreads / 32];
     __shared__ double SG[kRing], YG[kRing], SYn[kRing], YYn[kRing], YSn[kRing], al[kRing], be[kRing], ro[kRing], wv[kRing];
@@ -389,6 +395,8 @@ __global__ void __launch_bounds__(kThreads) lbfgs_scalar_kernel(const Args a) {
 // 4. direction + parameter update:  d = cg g + sum cy_j y_j + sum cs_j s_j ;  x += t d
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(const Args a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float cy[kRing], cs[kRing];
     __shared__ int slots[kRing];
     const LbfgsState* st = a.st;
@@ -446,6 +454,7 @@ struct maua_lbfgs {
     float *prev_g = nullptr, *d = nullptr, *S = nullptr, *Y = nullptr, *partials = nullptr;
     double *SY = nullptr, *YY = nullptr, *reduced = nullptr;
     LbfgsState* st = nullptr;
+    LbfgsState* st_init = nullptr;  // pristine copy of the device state (maua_lbfgs_reset)
 };
 
 extern "C" {
@@ -501,6 +510,8 @@ MAUA_API int maua_lbfgs_create(long n, int history, float lr, float tolerance_ch
     memset(&h, 0, sizeof(h));
     h.lr = lr; h.tol_change = tolerance_change; h.H_diag = 1.f; h.t = lr; h.cand = -1;
     MAUA_CUDA_CHECK(cudaMemcpy(s->st, &h, sizeof(h), cudaMemcpyHostToDevice));
+    MAUA_CUDA_CHECK(cudaMalloc((void**)&s->st_init, sizeof(LbfgsState)));
+    MAUA_CUDA_CHECK(cudaMemcpy(s->st_init, &h, sizeof(h), cudaMemcpyHostToDevice));
     *out = s;
     return MAUA_OK;
 }
@@ -508,7 +519,7 @@ MAUA_API int maua_lbfgs_create(long n, int history, float lr, float tolerance_ch
 MAUA_API void maua_lbfgs_destroy(maua_lbfgs_t* s) {
     if (!s) return;
     cudaFree(s->prev_g); cudaFree(s->d); cudaFree(s->S); cudaFree(s->Y); cudaFree(s->partials); cudaFree(s->reduced);
-    cudaFree(s->SY); cudaFree(s->YY); cudaFree(s->st);
+    cudaFree(s->SY); cudaFree(s->YY); cudaFree(s->st); cudaFree(s->st_init);
     delete s;
 }
 
@@ -522,15 +533,28 @@ MAUA_API int maua_lbfgs_step(maua_lbfgs_t* s, float* param, const float* grad, m
     a.K = s->K; a.first = s->calls == 0; a.n = s->n; a.ld = s->ld; a.grid = s->grid_dots; a.mats_in_smem = s->mats_in_smem;
     a.param = param; a.g = grad; a.prev_g = s->prev_g; a.d = s->d; a.S = s->S; a.Y = s->Y;
     a.st = s->st; a.partials = s->partials; a.reduced = s->reduced; a.SY = s->SY; a.YY = s->YY;
-    lbfgs_dots_kernel<<<s->grid_dots, kThreads, nacc * sizeof(float), st>>>(a);
-    MAUA_CUDA_CHECK(cudaGetLastError());
-    lbfgs_reduce_kernel<<<(nacc + kThreads / 32 - 1) / (kThreads / 32), kThreads, 0, st>>>(a);
-    MAUA_CUDA_CHECK(cudaGetLastError());
-    lbfgs_scalar_kernel<<<1, kThreads, s->scalar_smem, st>>>(a);
-    MAUA_CUDA_CHECK(cudaGetLastError());
-    lbfgs_update_kernel<<<s->grid_update, kThreads, 0, st>>>(a);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl<PDL_LBFGS>(lbfgs_dots_kernel, dim3(s->grid_dots), dim3(kThreads), nacc * sizeof(float), st, a));
+    MAUA_CUDA_CHECK(launch_pdl<PDL_LBFGS>(lbfgs_reduce_kernel, dim3((nacc + kThreads / 32 - 1) / (kThreads / 32)), dim3(kThreads), 0, st, a));
+    MAUA_CUDA_CHECK(launch_pdl<PDL_LBFGS>(lbfgs_scalar_kernel, dim3(1), dim3(kThreads), s->scalar_smem, st, a));
+    MAUA_CUDA_CHECK(launch_pdl<PDL_LBFGS>(lbfgs_update_kernel, dim3(s->grid_update), dim3(kThreads), 0, st, a));
     s->calls += 1;
+    return MAUA_OK;
+}
+
+MAUA_API int maua_lbfgs_reset(maua_lbfgs_t* s, maua_stream_t stream) {
+    MAUA_REQUIRE(s, "maua_lbfgs_reset: null state");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ring = s->K + 1;
+    const size_t mat = (size_t)ring * ring * sizeof(double);
+    // history slots are only read up to hist_len and every vector's zero padding is preserved by the kernels, so the
+    // (large) S / Y rings need no clearing: a reset costs a few hundred KB of memsets instead of re-allocating 2.5 GB
+    MAUA_CUDA_CHECK(cudaMemsetAsync(s->prev_g, 0, (size_t)s->ld * sizeof(float), st));
+    MAUA_CUDA_CHECK(cudaMemsetAsync(s->d, 0, (size_t)s->ld * sizeof(float), st));
+    MAUA_CUDA_CHECK(cudaMemsetAsync(s->SY, 0, mat, st));
+    MAUA_CUDA_CHECK(cudaMemsetAsync(s->YY, 0, mat, st));
+    MAUA_CUDA_CHECK(cudaMemsetAsync(s->reduced, 0, (size_t)(kNV * ring + kNG) * sizeof(double), st));
+    MAUA_CUDA_CHECK(cudaMemcpyAsync(s->st, s->st_init, sizeof(LbfgsState), cudaMemcpyDeviceToDevice, st));
+    s->calls = 0;
     return MAUA_OK;
 }
 

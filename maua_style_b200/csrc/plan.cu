@@ -75,6 +75,8 @@ struct BwdPrep {
     int do_round;
 };
 __global__ void bwd_prep_kernel(const float* __restrict__ coefs, float* __restrict__ coef2, const BwdPrep bp) {
+    pdl_wait();
+    pdl_trigger();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < bp.n_slots)
         coef2[threadIdx.x] = coefs[threadIdx.x] * bp.factors[threadIdx.x];
     if ((int)blockIdx.y >= bp.n_style) return;
@@ -97,6 +99,8 @@ struct CoefParams {
 __device__ __forceinline__ float sg(float x) { return x / (fabsf(x) + 1e-8f); }
 // ScaleGradients (loss.py:10-20) applied to the scalar loss: grad / (|grad| + 1e-8) * strength^2
 __global__ void loss_grad_coefs_kernel(const float* __restrict__ up, float* __restrict__ coefs, CoefParams p) {
+    pdl_wait();
+    pdl_trigger();
     const int i = threadIdx.x;
     if (i >= p.n) return;
     const float u = up[i], s = p.strength[i], v = p.vsf[i];
@@ -729,8 +733,7 @@ MAUA_API int maua_loss_grad_coefs(const float* upstream, float* coefs, int n, co
     for (int i = 0; i < n; ++i) {
         cp.strength[i] = strength[i]; cp.vsf[i] = vsf[i]; cp.normalize[i] = normalize[i]; cp.kind[i] = kind[i];
     }
-    loss_grad_coefs_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(upstream, coefs, cp);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(loss_grad_coefs_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, upstream, coefs, cp));
     return MAUA_OK;
 }
 
@@ -771,8 +774,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             bp.diff[j] = tp.diff; bp.aux_d[j] = tp.aux_d; bp.C[j] = tp.C; bp.slot[j] = t;
             bp.inv_c3p[j] = 4.f / ((float)tp.C * (float)tp.C * (float)tp.C * (float)((long)e.H * e.W));
         }
-        bwd_prep_kernel<<<dim3(128, bp.n_style > 0 ? bp.n_style : 1), 256, 0, st>>>(grad_coefs, p->coef2, bp);
-        MAUA_CUDA_CHECK(cudaGetLastError());
+        MAUA_CUDA_CHECK(launch_pdl(bwd_prep_kernel, dim3(128, bp.n_style > 0 ? bp.n_style : 1), dim3(256), 0, st, grad_coefs, p->coef2, bp));
         p->launches_bwd++;
         for (int t = 0; t < nt; ++t) {  // covariance: aux_bias = -aux_d @ mean (loss.py:87-89)
             Tap& tp = p->taps[t];

@@ -122,6 +122,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
 // --------------------------------------------------------------------------------------------
 __global__ void pool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H, int W, int C4,
                                 int avg, int do_round) {
+    pdl_wait();
+    pdl_trigger();
     const int PH = H / 2, PW = W / 2;
     const long total = (long)B * PH * PW * C4;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -162,6 +164,8 @@ __device__ __forceinline__ int first_argmax(float a0, float a1, float a2, float 
 __global__ void pool_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy,
                                 const float4* __restrict__ addend, float4* __restrict__ gx, int B, int H, int W,
                                 int C4, int avg, int do_round) {
+    pdl_wait();
+    pdl_trigger();
     const int PH = H / 2, PW = W / 2;
     const int WH = (H + 1) / 2, WW = (W + 1) / 2;  // windows incl. partial ones
     const long total = (long)B * WH * WW * C4;
@@ -225,6 +229,8 @@ __global__ void pool_bwd_kernel(const float4* __restrict__ x, const float4* __re
 // --------------------------------------------------------------------------------------------
 __global__ void tv_value_kernel(const float* __restrict__ x, int planes, int H, int W, float strength,
                                 float* __restrict__ loss_out, double* partials, unsigned int* counter) {
+    pdl_wait();
+    pdl_trigger();
     const long total = (long)planes * H * W;
     double acc[1] = {0.0};
     float local = 0.f;
@@ -246,6 +252,8 @@ __global__ void tv_value_kernel(const float* __restrict__ x, int planes, int H, 
 // --------------------------------------------------------------------------------------------
 __global__ void mse_value_kernel(const float4* __restrict__ x, const float4* __restrict__ t, long n4, float scale,
                                  float* __restrict__ loss_out, double* partials, unsigned int* counter) {
+    pdl_wait();
+    pdl_trigger();
     double acc[1] = {0.0};
     float local = 0.f;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -261,6 +269,8 @@ __global__ void mse_value_kernel(const float4* __restrict__ x, const float4* __r
 __global__ void wmse_value_kernel(const float* __restrict__ x, const float* __restrict__ wts,
                                   const float* __restrict__ t, long n, long plane, float scale,
                                   float* __restrict__ loss_out, double* partials, unsigned int* counter) {
+    pdl_wait();
+    pdl_trigger();
     double acc[1] = {0.0};
     float local = 0.f;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -307,6 +317,8 @@ __global__ void channel_sum_final_kernel(const double* __restrict__ partial, int
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt, const int* __restrict__ step_dev) {
+    pdl_wait();
+    pdl_trigger();
     const long n4 = n / 4;
     if (step_dev) {
         const int t = *step_dev;
@@ -374,27 +386,25 @@ int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int av
     MAUA_REQUIRE(C % 4 == 0, "pool: C %% 4 != 0");
     if (H / 2 == 0 || W / 2 == 0) return MAUA_OK;
     const long total = (long)B * (H / 2) * (W / 2) * (C / 4);
-    pool_fwd_kernel<<<grid_for(total, 16), kThreads, 0, st>>>(reinterpret_cast<const float4*>(x),
-                                                              reinterpret_cast<float4*>(y), B, H, W, C / 4, avg, do_round);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(pool_fwd_kernel, dim3(grid_for(total, 16)), dim3(kThreads), 0, st, reinterpret_cast<const float4*>(x),
+                               reinterpret_cast<float4*>(y), B, H, W, C / 4, avg, do_round));
     return MAUA_OK;
 }
 int pool_bwd_launch(const float* x, const float* gy, const float* addend, float* gx, int B, int H, int W, int C,
                     int avg, int do_round, cudaStream_t st) {
     MAUA_REQUIRE(C % 4 == 0, "pool: C %% 4 != 0");
     const long total = (long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    pool_bwd_kernel<<<grid_for(total, 16), kThreads, 0, st>>>(
-        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gy),
-        reinterpret_cast<const float4*>(addend), reinterpret_cast<float4*>(gx), B, H, W, C / 4, avg, do_round);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(pool_bwd_kernel, dim3(grid_for(total, 16)), dim3(kThreads), 0, st, reinterpret_cast<const float4*>(x),
+                               reinterpret_cast<const float4*>(gy), reinterpret_cast<const float4*>(addend),
+                               reinterpret_cast<float4*>(gx), B, H, W, C / 4, avg, do_round));
     return MAUA_OK;
 }
 int tv_value_launch(const float* x, int planes, int H, int W, float strength, float* loss_out, ReduceScratch rs,
                     cudaStream_t st) {
     const int grid = grid_for((long)planes * H * W, 4);
     MAUA_REQUIRE(grid <= rs.max_blocks, "reduce scratch too small");
-    tv_value_kernel<<<grid, kThreads, 0, st>>>(x, planes, H, W, strength, loss_out, rs.partials, rs.counter);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(tv_value_kernel, dim3(grid), dim3(kThreads), 0, st, x, planes, H, W, strength, loss_out, rs.partials,
+                               rs.counter));
     return MAUA_OK;
 }
 int mse_value_launch(const float* x, const float* t, long n, float scale, float* loss_out, ReduceScratch rs,
@@ -402,17 +412,16 @@ int mse_value_launch(const float* x, const float* t, long n, float scale, float*
     MAUA_REQUIRE(n % 4 == 0, "mse: n %% 4 != 0");
     const int grid = grid_for(n / 4, 4);
     MAUA_REQUIRE(grid <= rs.max_blocks, "reduce scratch too small");
-    mse_value_kernel<<<grid, kThreads, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(t),
-                                                n / 4, scale, loss_out, rs.partials, rs.counter);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(mse_value_kernel, dim3(grid), dim3(kThreads), 0, st, reinterpret_cast<const float4*>(x),
+                               reinterpret_cast<const float4*>(t), n / 4, scale, loss_out, rs.partials, rs.counter));
     return MAUA_OK;
 }
 int wmse_value_launch(const float* x, const float* wts, const float* t, long n, long plane, float scale,
                       float* loss_out, ReduceScratch rs, cudaStream_t st) {
     const int grid = grid_for(n, 4);
     MAUA_REQUIRE(grid <= rs.max_blocks, "reduce scratch too small");
-    wmse_value_kernel<<<grid, kThreads, 0, st>>>(x, wts, t, n, plane, scale, loss_out, rs.partials, rs.counter);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(wmse_value_kernel, dim3(grid), dim3(kThreads), 0, st, x, wts, t, n, plane, scale, loss_out, rs.partials,
+                               rs.counter));
     return MAUA_OK;
 }
 int channel_mean_launch(const float* x, long P, int C, float* mean_out, double* scratch, int scratch_blocks,
@@ -434,9 +443,8 @@ int adam_launch(float* p, const float* g, float* m, float* v, long n, float lr, 
                    reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam: pointers must be 16-byte aligned");
     const double bc1 = 1.0 - pow((double)b1, step);
     const double bc2 = 1.0 - pow((double)b2, step);
-    adam_kernel<<<grid_for(n / 4 + 1, 8), kThreads, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, (float)bc1,
-                                                             (float)sqrt(bc2), step_dev);
-    MAUA_CUDA_CHECK(cudaGetLastError());
+    MAUA_CUDA_CHECK(launch_pdl(adam_kernel, dim3(grid_for(n / 4 + 1, 8)), dim3(kThreads), 0, st, p, g, m, v, n, lr, b1, b2, eps,
+                               (float)bc1, (float)sqrt(bc2), step_dev));
     return MAUA_OK;
 }
 

@@ -197,6 +197,7 @@ class _PlanCore:
             desc.tap_kind[t] = kind
         n_slots = len(tap_sig) + 2
         self.stages = []
+        self.loop_states = collections.OrderedDict()  # optim.optimize_device: optimizer state + captured graph per image size
         self.owner = None  # weakref to the network currently using this core
         torch.cuda.synchronize(device)  # the weight uploads above are consumed by plan creation on other devices
         for k, dv in enumerate(devs):
@@ -275,6 +276,7 @@ class B200Net(nn.Module):
         self._loss_vec = torch.zeros(self._n_slots, device=device)
         self._coefs = self._stages[0]["coefs"]
         self._fwd_token = 0
+        self.reuse_target_buffers = False  # set by optimisation loops that keep a captured graph across images
         self._tap_channels = []
         self._tap_stage = []
         ch = [c for c in entries if c > 0]
@@ -354,14 +356,9 @@ class B200Net(nn.Module):
                     return h, w
         raise AssertionError
 
-    def _forward_plan(self, x: torch.Tensor, keep: bool) -> int:
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError(f"expected a [1,3,H,W] image, got {tuple(x.shape)}")
-        if x.shape[0] != 1:
-            raise NotImplementedError("maua_style_b200 supports batch size 1 only (img_vid windows are out of scope)")
-        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
-            raise ValueError("internal: image must be a contiguous fp32 CUDA tensor")
-        H, W = int(x.shape[2]), int(x.shape[3])
+    def _build_io(self, H: int, W: int):
+        """The per-forward description of every loss module for the plan (maua_tap_io / maua_image_io): modes, strengths,
+        target buffers.  Capture-mode modules get their target buffers here (loss.py:61-62, :146-151)."""
         tio = (_lib.TapIO * max(len(self.taps), 1))()
         for t, (ridx, mod) in enumerate(self.taps):
             io = tio[t]
@@ -389,8 +386,13 @@ class B200Net(nn.Module):
                 io.value_scale = float(mod.strength)
                 h, w = self._tap_hw(H, W, ridx)
                 if mod.mode == "capture":
-                    # NCHW-shaped view over NHWC memory (channels_last): .size() matches the reference's target
-                    mod.target = torch.empty(1, h, w, C_, device=tdev).permute(0, 3, 1, 2)
+                    # NCHW-shaped view over NHWC memory (channels_last): .size() matches the reference's target.  With
+                    # reuse_target_buffers (optimisation loops over many images of one size) an existing buffer of the right
+                    # shape is overwritten in place, so that a captured CUDA graph of the iteration stays valid.
+                    tgt = mod.target
+                    if not (self.reuse_target_buffers and tgt.nelement() != 0 and tuple(tgt.shape) == (1, C_, h, w)
+                            and tgt.device == tdev and tgt.permute(0, 2, 3, 1).is_contiguous()):
+                        mod.target = torch.empty(1, h, w, C_, device=tdev).permute(0, 3, 1, 2)
                 if mod.mode != "none" and mod.target.nelement() != 0:
                     tgt = mod.target
                     if tuple(tgt.shape[1:]) == (C_, h, w):
@@ -409,7 +411,9 @@ class B200Net(nn.Module):
             iio.temporal_mode = _MODES[tm.mode]
             iio.temporal_strength = float(tm.strength)
             if tm.mode == "capture":
-                tm.target = torch.empty(1, 3, H, W, device=self.device)
+                if not (self.reuse_target_buffers and tm.target.nelement() != 0 and tuple(tm.target.shape) == (1, 3, H, W)
+                        and tm.target.is_cuda and tm.target.is_contiguous()):
+                    tm.target = torch.empty(1, 3, H, W, device=self.device)
             if tm.target.nelement() != 0 and tuple(tm.target.shape[1:]) == (3, H, W):
                 if not (tm.target.is_cuda and tm.target.is_contiguous()):
                     tm.target = tm.target.to(self.device, torch.float32).contiguous()
@@ -423,6 +427,23 @@ class B200Net(nn.Module):
                         wts = wts.to(self.device, torch.float32).contiguous()
                         tm.weights = wts
                     iio.temporal_weights = wts.data_ptr()
+        return tio, iio
+
+    def io_signature(self, H: int, W: int) -> bytes:
+        """Everything a captured iteration bakes into its kernel arguments besides the pastiche: extents, module modes,
+        strengths and target addresses.  Two iterations with equal signatures launch identical kernels."""
+        tio, iio = self._build_io(H, W)
+        return bytes(memoryview(tio)) + bytes(memoryview(iio)) + f"{H}x{W}".encode()
+
+    def _forward_plan(self, x: torch.Tensor, keep: bool) -> int:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected a [1,3,H,W] image, got {tuple(x.shape)}")
+        if x.shape[0] != 1:
+            raise NotImplementedError("maua_style_b200 supports batch size 1 only (img_vid windows are out of scope)")
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("internal: image must be a contiguous fp32 CUDA tensor")
+        H, W = int(x.shape[2]), int(x.shape[3])
+        tio, iio = self._build_io(H, W)
         self._keepalive = (x, tio, iio)
         if len(self._stages) == 1:
             with torch.cuda.device(self.device):

@@ -138,6 +138,18 @@ class PixelOptimizer:
                 _lib.check(self.lib.maua_lbfgs_step(self._state, _lib.ptr(self.p), _lib.ptr(grad), _lib.stream_ptr()),
                            "maua_lbfgs_step")
 
+    def reset(self) -> None:
+        """Back to the freshly constructed optimizer (the reference builds a new torch.optim object per optimize() call,
+        optim.py:180-196) without re-allocating the state: Adam moments / step counter zeroed, L-BFGS history emptied."""
+        self.step_count = 0
+        with torch.cuda.device(self.p.device):
+            if self.kind == "adam":
+                self.m.zero_()
+                self.v.zero_()
+                self.step_dev.zero_()
+            else:
+                _lib.check(self.lib.maua_lbfgs_reset(self._state, _lib.stream_ptr()), "maua_lbfgs_reset")
+
     def close(self):
         if self._state:
             self.lib.maua_lbfgs_destroy(self._state)
@@ -163,9 +175,20 @@ class GraphedIteration:
 
         self.net, self.pastiche, self.opt, self.up = net, pastiche, opt, up
         self.graph = None
+        self.signature = None
         self.eager_calls = 0
         self.enabled = net.n_stages == 1 and os.environ.get("MAUA_NO_GRAPH", "0") != "1"
         self.warmup = warmup  # eager iterations first: workspaces get sized, the L-BFGS "first call" path is taken eagerly
+
+    def rearm(self, net, signature) -> None:
+        """Start another optimisation with the same buffers: the warm-up iterations run eagerly again (the L-BFGS first-step
+        path is host-selected), and the captured graph is kept only if it would launch exactly the same kernels."""
+        self.net = net
+        self.eager_calls = 0
+        if signature != self.signature:
+            self.graph = None
+        self.signature = signature
+        self.enabled = net.n_stages == 1 and __import__("os").environ.get("MAUA_NO_GRAPH", "0") != "1"
 
     def _eager(self):
         self.net._forward_plan(self.pastiche, keep=True)
@@ -293,13 +316,16 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
         net, losses = models.load_model(args)
     device = net.device
 
+    import os
+
+    if os.environ.get("MAUA_NO_LOOP_CACHE", "0") != "1":
+        # content / temporal targets of the same shape are re-captured into their existing buffers, so that the iteration
+        # captured for the previous image of this size can be replayed for this one (see _LoopState)
+        net.reuse_target_buffers = True
     set_content_targets(net, content.to(device, torch.float32), args)
     set_style_targets(net, styles, args)  # (the network moves host tensors itself; identity is kept for the target cache)
     for mod in losses:
         mod.mode = "loss"
-
-    # optim.py:173: the pastiche lives on the device for the whole optimisation
-    pastiche = init.detach().to(device, torch.float32).contiguous().clone()
 
     # optim.py:176-178 (only once, strengths are not reset)
     if getattr(args, "normalize_weights", False):
@@ -312,21 +338,18 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
         if float(getattr(args, "lbfgs_tolerance_grad", -1)) >= 0:
             raise NotImplementedError("maua_style_b200: lbfgs_tolerance_grad >= 0 is not supported (the reference always "
                                       "passes -1, optim.py:184); use the default")
-        hist = getattr(args, "lbfgs_num_correction", 100)
-        opt = PixelOptimizer(pastiche, "lbfgs", history=hist, tolerance_change=float(getattr(args, "lbfgs_tolerance_change", -1)))
         evals = num_iters  # one step() = num_iters closure evaluations and updates
     elif args.optimizer == "adam":
-        opt = PixelOptimizer(pastiche, "adam", lr=args.learning_rate)
         evals = num_iters + 1  # optim.py:240 `while i[0] <= iters`
     else:
         raise ValueError(f"unknown optimizer {args.optimizer!r}")
 
+    live = net._live_slots()  # modules in loss mode with a target (a shape mismatch just contributes 0, loss.py:44)
+    state = _loop_state(net, init, args, live)
+    pastiche, opt, iteration = state.pastiche, state.opt, state.iteration
+
     print_iter = int(getattr(args, "print_iter", 0) or 0)
     save_iter = int(getattr(args, "save_iter", 0) or 0)
-    live = net._live_slots()  # modules in loss mode with a target (a shape mismatch just contributes 0, loss.py:44)
-    up = torch.zeros(net._n_slots, device=device)
-    up[live] = 1.0
-    iteration = GraphedIteration(net, pastiche, opt, up)
     for it in range(1, evals + 1):
         want_print = print_iter > 0 and it % print_iter == 0 and getattr(args, "verbose", False)
         want_save = save_iter > 0 and (it % save_iter == 0 or it == num_iters)
@@ -339,8 +362,65 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
             print(f"Iteration {it} / {args.num_iters}, Loss: {total}")
     for mod in losses:
         mod.loss = 0
+    if state.cached:
+        iteration.net = None     # the cached state must not keep the network (and through it the plan core's owner) alive
+        return pastiche.clone()  # the buffer belongs to the cached loop state and is overwritten by the next call
     opt.close()
     return pastiche
+
+
+class _LoopState:
+    """What one optimisation loop needs besides the network: the device-resident pastiche, the optimizer state and the
+    captured iteration.  Kept on the plan core per (image size, optimizer settings) so that the next image / frame /
+    call of the same size re-uses the buffers (an L-BFGS history at 1024^2 is 2.5 GB of cudaMalloc + cudaFree per call
+    otherwise) and -- when the kernel arguments are identical -- the captured CUDA graph."""
+
+    def __init__(self, key, pastiche, opt, iteration, cached):
+        self.key, self.pastiche, self.opt, self.iteration, self.cached = key, pastiche, opt, iteration, cached
+
+
+_LOOP_STATES_MAX = 4
+
+
+def _loop_state(net, init, args, live) -> _LoopState:
+    import os
+
+    device = net.device
+    kind = args.optimizer
+    hist = int(getattr(args, "lbfgs_num_correction", 100))
+    tol = float(getattr(args, "lbfgs_tolerance_change", -1))
+    lr = float(getattr(args, "learning_rate", 1.0)) if kind == "adam" else 1.0
+    key = (tuple(init.shape), kind, hist, tol, lr)
+    cache = getattr(getattr(net, "_core", None), "loop_states", None)
+    use_cache = cache is not None and os.environ.get("MAUA_NO_LOOP_CACHE", "0") != "1"
+    H, W = int(init.shape[2]), int(init.shape[3])
+    signature = (net.io_signature(H, W), tuple(live))
+    state = cache.get(key) if use_cache else None
+    if state is not None:
+        cache.move_to_end(key)
+        state.pastiche.copy_(init.detach().to(device, torch.float32))  # optim.py:173
+        state.opt.reset()
+        state.iteration.up.zero_()
+        state.iteration.up[live] = 1.0
+        state.iteration.rearm(net, signature)
+        return state
+    # optim.py:173: the pastiche lives on the device for the whole optimisation
+    pastiche = init.detach().to(device, torch.float32).contiguous().clone()
+    if kind == "lbfgs":
+        opt = PixelOptimizer(pastiche, "lbfgs", history=hist, tolerance_change=tol)
+    else:
+        opt = PixelOptimizer(pastiche, "adam", lr=lr)
+    up = torch.zeros(net._n_slots, device=device)
+    up[live] = 1.0
+    iteration = GraphedIteration(net, pastiche, opt, up)
+    iteration.signature = signature
+    state = _LoopState(key, pastiche, opt, iteration, use_cache)
+    if use_cache:
+        cache[key] = state
+        while len(cache) > _LOOP_STATES_MAX:
+            _, old = cache.popitem(last=False)
+            old.opt.close()
+    return state
 
 
 def _save_intermediate(pastiche, args, it, num_iters):

@@ -303,3 +303,37 @@ def test_img_img_driver_with_histogram_matching(tmp_path):
         mo = image_ops.image_moments(o).cpu().numpy()
         assert np.allclose(mo[1:4] / mo[0], ms[1:4] / ms[0], atol=1e-2)
         assert np.allclose(mo[[4, 7, 9]] / mo[0] - (mo[1:4] / mo[0]) ** 2, ms[[4, 7, 9]] / ms[0] - (ms[1:4] / ms[0]) ** 2, rtol=5e-3)
+
+
+def test_loop_state_cache_reuses_buffers_and_graph_without_changing_results(tmp_path, monkeypatch):
+    """optim.optimize_device keeps the optimizer state, the pastiche buffer and the captured CUDA graph per image size on the
+    plan core (_LoopState): a batch of images of one size (shard.stylize_images, vid_img frames) must give exactly the
+    results of fresh optimisations, L-BFGS and Adam, and the second image must replay the first image's graph."""
+    from maua_style_b200 import models, optim
+
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    style = [O.synthetic_image(64, 64, seed=2)]
+    images = [O.synthetic_image(64, 80, seed=10 + i, smooth=True) for i in range(3)]
+    for kind in ("lbfgs", "adam"):
+        fresh = []
+        monkeypatch.setenv("MAUA_NO_LOOP_CACHE", "1")
+        for img in images:
+            models.clear_model_cache()
+            a = make_args(ckpt, tmp_path, optimizer=kind)
+            net, losses = models.load_model(a)
+            fresh.append(optim.optimize(img, style, img.clone(), 8, a, net, losses))
+            del net, losses
+        monkeypatch.setenv("MAUA_NO_LOOP_CACHE", "0")
+        models.clear_model_cache()
+        a = make_args(ckpt, tmp_path, optimizer=kind)
+        net, losses = models.load_model(a)
+        graphs = []
+        for img, want in zip(images, fresh):
+            got = optim.optimize(img, style, img.clone(), 8, a, net, losses)
+            assert torch.equal(got, want), kind
+            state = next(iter(net._core.loop_states.values()))
+            graphs.append(state.iteration.graph)
+        assert len(net._core.loop_states) == 1
+        assert graphs[0] is not None and graphs[1] is graphs[0] and graphs[2] is graphs[0]  # captured once, replayed for all
+        del net, losses

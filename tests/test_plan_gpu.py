@@ -269,7 +269,7 @@ def test_split_k_plan_agrees_with_the_unsplit_plan(ckpt, hw):
     err = rel(res[1][1], res[0][1])
     report(f"split-K vs unsplit plan gradient {hw} (avg pool) rel {err:.2e}")
     assert err < 5e-4
-    assert torch.allclose(res[0][0], res[1][0], rtol=1e-4)
+    assert torch.allclose(res[0][0], res[1][0], rtol=2e-3)
     assert torch.equal(res[1][1], res[2][1]) and torch.equal(res[1][0], res[2][0])  # deterministic
 
 
