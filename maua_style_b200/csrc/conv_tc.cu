@@ -396,36 +396,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
                             ep.mask_out[pix * words + ((n0 + c) >> 5)] = bits;
                         }
-                        if (POOL) {
-                            // (compiled into the POOL = true instantiations only: the default kernels are unchanged)
-                            // 2x2 window = lanes {l, l^1, l^16, l^17}: w and w+1 are neighbouring lanes, h and h+1 are the
-                            // two half-warps (this warp holds tile rows 2q and 2q+1).  Every lane takes part in the
-                            // shuffles; the lane of the window's top-left pixel stores the pooled pixel (32 channels =
-                            // one 128-byte line).  Windows that hang over the image edge are dropped (floor semantics).
-                            const bool writer = (lane & 17) == 0;
-                            const int PH = p.H >> 1, PW = p.W >> 1;
-                            const int ph = h >> 1, pw = w >> 1;
-                            const bool pvalid = writer && ph < PH && pw < PW;
-                            float* pdst = ep.pool_out + ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + n0 + c;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float o[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float a0 = v[i + j];
-                                    if (ep.pool_avg) {
-                                        const float a1 = __shfl_xor_sync(0xffffffffu, a0, 1);
-                                        const float a2 = __shfl_xor_sync(0xffffffffu, a0, 16);
-                                        const float a3 = __shfl_xor_sync(0xffffffffu, a0, 17);
-                                        o[j] = round_tf32(0.25f * (a0 + a1 + a2 + a3));
-                                    } else {
-                                        const float m = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, 1));
-                                        o[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                                    }
-                                }
-                                if (pvalid) *reinterpret_cast<float4*>(pdst + i) = make_float4(o[0], o[1], o[2], o[3]);
-                            }
-                        }
                         uint8_t* sbox = stage_box + (box & 1) * STAGE_BOX_BYTES;
                         // the store that last read this staging box (two boxes ago) must have drained it
                         if (issuer) bulk_wait_group_read<1>();
@@ -441,6 +411,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_store_4d(&tmOut, sbox, n0 + c, w0, h0 + m * TILE_H, b);
                             if (ep.out2) tma_store_4d(&tmOut2, sbox, n0 + c, w0, h0 + m * TILE_H, b);
                             bulk_commit_group();
+                        }
+                        if (POOL) {
+                            // 2x2 / stride-2 pooling of the finished box (models.py:119-122) straight from the staging copy:
+                            // the box holds 16 x 8 pixels x 32 channels, i.e. 8 x 4 pooled pixels x eight 16-byte channel chunks
+                            // = 256 items, two per epilogue thread.  An item reads its window's four chunks (de-swizzled),
+                            // reduces them and writes one 16-byte piece of the pooled NHWC map; eight consecutive threads cover
+                            // one pooled pixel's 128-byte line.  Same arithmetic as pool_fwd_kernel, bit for bit.  The box is
+                            // not rewritten before every thread has passed the next-but-one box's first barrier.
+                            const int PH = p.H >> 1, PW = p.W >> 1;
+                            const int tid = threadIdx.x - 128;
+#pragma unroll
+                            for (int it2 = 0; it2 < 2; ++it2) {
+                                const int item = tid + 128 * it2;
+                                const int k = item & 7;          // 16-byte channel chunk
+                                const int pp = item >> 3;        // pooled pixel of the box: 8 wide x 4 high
+                                const int pwl = pp & 7, phl = pp >> 3;
+                                const int ph = ((h0 + m * TILE_H) >> 1) + phl, pw = (w0 >> 1) + pwl;
+                                float4 a[4];
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) {
+                                    const int rr = (2 * phl + (qd >> 1)) * TILE_W + 2 * pwl + (qd & 1);
+                                    a[qd] = *reinterpret_cast<const float4*>(sbox + rr * 128 + ((k ^ (rr & 7)) << 4));
+                                }
+                                float4 o;
+                                if (ep.pool_avg) {
+                                    o.x = 0.25f * (a[0].x + a[1].x + a[2].x + a[3].x); o.y = 0.25f * (a[0].y + a[1].y + a[2].y + a[3].y);
+                                    o.z = 0.25f * (a[0].z + a[1].z + a[2].z + a[3].z); o.w = 0.25f * (a[0].w + a[1].w + a[2].w + a[3].w);
+                                    if (ep.round) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                                } else {
+                                    o.x = fmaxf(fmaxf(a[0].x, a[1].x), fmaxf(a[2].x, a[3].x)); o.y = fmaxf(fmaxf(a[0].y, a[1].y), fmaxf(a[2].y, a[3].y));
+                                    o.z = fmaxf(fmaxf(a[0].z, a[1].z), fmaxf(a[2].z, a[3].z)); o.w = fmaxf(fmaxf(a[0].w, a[1].w), fmaxf(a[2].w, a[3].w));
+                                }
+                                if (ph < PH && pw < PW)
+                                    *reinterpret_cast<float4*>(ep.pool_out + ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + n0 + c + 4 * k) = o;
+                            }
                         }
                     }
                 }

@@ -88,7 +88,8 @@ struct ConvFirstTV {
 };
 int conv_first_fwd_launch(const float* img, const float* w /*[Cout][3][3][3]*/, const float* bias, float* out,
                           uint32_t* mask_out /*optional sign bitmap*/, int B, int H, int W, int Cout, int round,
-                          cudaStream_t st, const ConvFirstTV* tv = nullptr);
+                          cudaStream_t st, const ConvFirstTV* tv = nullptr, int exact = 0);
+int make_tmap_nhwc(CUtensorMap* m, const float* ptr, int B, int H, int W, int C, int box_w, int box_h);
 
 // conv1_1 dgrad (+ fused image-side tail): NHWC Cout gradient -> NCHW 3-channel image gradient,
 // plus TV gradient and temporal ContentLoss gradient.

@@ -615,7 +615,9 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 tv.strength = p->img_io.tv_strength; tv.out = losses_out + nt;
                 tv.partials = rs.partials; tv.counter = rs.counter; tv.max_blocks = rs.max_blocks;
             }
-            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, rnd, st, tv_pending ? &tv : nullptr)))
+            // tcgen05 kernel (3xTF32) on the product path; the FFMA kernel in exact mode and for the SIMT cross-check plan
+            if ((rc = conv_first_fwd_launch(image, e.w_raw, e.bias, e.out, e.bits, 1, H, W, e.cout, rnd, st, tv_pending ? &tv : nullptr,
+                                            exact || p->impl == MAUA_IMPL_REF)))
                 return rc;
             if (hand_off)
                 MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));

@@ -180,7 +180,9 @@ def test_conv_first_fwd_and_dgrad(lib, h, w):
     _lib.check(lib.maua_conv_first_fwd(_lib.ptr(imgd), _lib.ptr(wtd), _lib.ptr(bd), _lib.ptr(y), 1, h, w,
                                        64, _lib.stream_ptr()))
     torch.cuda.synchronize()
-    assert rel(nchw(y), tf32_round(ref)) < 2e-5  # rare 1-ulp tf32 rounding flips
+    # tcgen05 kernel with 3xTF32 operand splitting: ~1e-6 before the output is rounded to TF32, so a fraction of a percent of
+    # the outputs lands on the other side of a TF32 rounding boundary (one such flip = 2^-11 of that element)
+    assert rel(nchw(y), tf32_round(ref)) < 1e-4
 
     # dgrad + TV + temporal tail
     gy = tf32_round(torch.randn(1, 64, h, w, generator=g))  # the plan hands over a TF32-rounded masked gradient

@@ -224,6 +224,7 @@ def test_conv1_1_ffma2_kernel_is_bit_identical(h, w, monkeypatch):
     wt = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).cuda()
     b = torch.randn(64, generator=g).cuda()
     outs = []
+    monkeypatch.setenv("MAUA_CONV1_TC", "0")  # the FFMA kernels (exact-arithmetic path); the product path is the tcgen05 kernel
     for flag in ("0", "1"):
         monkeypatch.setenv("MAUA_CONV1_FFMA2", flag)
         y = torch.empty(1, h, w, 64, device="cuda")
@@ -231,6 +232,31 @@ def test_conv1_1_ffma2_kernel_is_bit_identical(h, w, monkeypatch):
         torch.cuda.synchronize()
         outs.append(y)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("h,w", [(64, 64), (37, 53), (5, 3), (90, 122), (512, 384)])
+def test_conv1_1_tensor_core_kernel_matches_the_fp32_kernel(h, w, monkeypatch):
+    """conv_first_tc_kernel (K = 27 -> 32 tcgen05 GEMM, 3xTF32 operand split) against the FFMA kernel: the same sums to ~1e-6
+    before TF32 output rounding, identical ReLU sign bitmaps except where a pre-activation is within that noise of zero,
+    identical TVLoss value (to fp32 summation order)."""
+    from maua_style_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(h * 7 + w)
+    img = (torch.rand(1, 3, h, w, generator=g) * 255 - 110).cuda()
+    wt = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MAUA_CONV1_TC", flag)
+        y = torch.full((1, h, w, 64), 7.0, device="cuda")
+        _lib.check(lib.maua_conv_first_fwd(_lib.ptr(img), _lib.ptr(wt), _lib.ptr(b), _lib.ptr(y), 1, h, w, 64, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append(y)
+    err = rel(outs[1], outs[0])
+    print(f"conv1_1 tcgen05 vs FFMA kernel {h}x{w}: rel {err:.2e}")
+    assert err < 1e-4
+    assert float(((outs[0] > 0) != (outs[1] > 0)).float().mean()) < 1e-4
 
 
 def test_config0_256_adam_100_iterations_reaches_the_reference_loss(tmp_path):
