@@ -337,3 +337,50 @@ def test_loop_state_cache_reuses_buffers_and_graph_without_changing_results(tmp_
         assert len(net._core.loop_states) == 1
         assert graphs[0] is not None and graphs[1] is graphs[0] and graphs[2] is graphs[0]  # captured once, replayed for all
         del net, losses
+
+
+def test_host_pipelined_iteration_equals_sequential_steps(tmp_path):
+    """optim.HostPipelinedIteration (bench.py's end-to-end path): every submit copies that step's host image to the device,
+    runs one iteration on it and returns the PREVIOUS step's result from pinned host memory; with the copies on their own
+    streams the results must be exactly those of doing the same steps one after the other."""
+    from maua_style_b200 import models, optim
+
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    a = make_args(ckpt, tmp_path, optimizer="adam")
+    content = O.synthetic_image(64, 96, seed=1, smooth=True)
+    style = [O.synthetic_image(64, 64, seed=2)]
+    frames = [(O.synthetic_image(64, 96, seed=20 + i) * 0.25).pin_memory() for i in range(5)]
+
+    def setup():
+        net, losses = models.load_model(a)
+        optim.set_content_targets(net, content, a)
+        optim.set_style_targets(net, style, a)
+        for m in losses:
+            m.mode = "loss"
+        p = frames[0].cuda().contiguous()
+        opt = optim.PixelOptimizer(p, "adam", lr=1.0)
+        up = torch.zeros(net._n_slots, device="cuda")
+        up[net._live_slots()] = 1.0
+        return net, losses, p, optim.GraphedIteration(net, p, opt, up)
+
+    net, losses, p, it = setup()
+    want = []
+    for f in frames:
+        p.copy_(f)
+        it()
+        want.append((p.detach().cpu().clone(), float(net._loss_vec.sum())))
+    del net, losses, it
+    net, losses, p, it = setup()
+    pipe = optim.HostPipelinedIteration(it)
+    got = []
+    for f in frames:
+        r = pipe.submit(f)
+        if r is not None:
+            got.append((r[0].clone(), float(r[1])))
+    r = pipe.drain()
+    got.append((r[0].clone(), float(r[1])))
+    assert pipe.drain() is None and len(got) == len(frames)
+    for (gi, gl), (wi, wl) in zip(got, want):
+        assert torch.equal(gi, wi)
+        assert abs(gl / wl - 1) < 1e-6
