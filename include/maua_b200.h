@@ -78,9 +78,10 @@ MAUA_API int maua_prep_conv_weights(const float* w_oihw, float* out, int cout, i
 MAUA_API int maua_prep_conv_weights_ex(const float* w_oihw, float* out, int cout, int cin, int dgrad, int round_tf32,
                                        maua_stream_t stream);
 /* Host-side launch plan of a conv3x3 / pointwise / aux-GEMM launch on a device with `sms` SMs (no GPU needed): plan6 =
- * {BN, MT, CTA-group size, whole tiles, K-split tiles, split factor}.  The persistent kernel computes the last, partial wave
- * of tiles as `split` K-ranges on different CTAs (pairs) whose partial sums meet in a workspace (deterministic order). */
-MAUA_API int maua_conv_tile_plan(int h, int w, int cin, int cout, int ntaps, int k2, int sms, int allow_split, int* plan6);
+ * {BN, MT, CTA-group size, whole tiles, tail tiles, items per tail tile}.  tail_mode selects how the last, partial wave of the
+ * persistent grid is computed: 0 whole tiles, 1 K-split (parts meet in a workspace, deterministic order), 2 two half-N items
+ * per tile (the default of a plan: independent items, no hand-over). */
+MAUA_API int maua_conv_tile_plan(int h, int w, int cin, int cout, int ntaps, int k2, int sms, int tail_mode, int* plan6);
 MAUA_API int maua_nchw_to_nhwc(const float* src, float* dst, int b, int c, int h, int w, int round_tf32,
                                maua_stream_t stream);
 MAUA_API int maua_nhwc_to_nchw(const float* src, float* dst, int b, int c, int h, int w, maua_stream_t stream);
@@ -344,6 +345,9 @@ MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* plan, int enable);
  * the partial accumulators costs more than the idle SMs it recovers (profiles/r02_splitk_ab.txt); results agree with the
  * unsplit plan to fp32 summation order. */
 MAUA_API int maua_plan_set_splitk(maua_plan_t* plan, int enable);
+/* Tail handling of the persistent conv kernels: 0 whole tiles, 1 K-split, 2 half-N items (default; MAUA_CONV_TAIL in the
+ * environment at plan creation).  Half-N items compute exactly the sums of the whole tile, so results do not change. */
+MAUA_API int maua_plan_set_conv_tail(maua_plan_t* plan, int mode);
 /* Per-launch timing for roofline reports: when enabled, a CUDA event is recorded on the caller's stream after every
  * launch of forward / backward.  maua_plan_profile_json synchronises the stream and writes a JSON array
  * [{"name","layer","ms","flops","bytes"}...] (algorithmic FLOPs / bytes per launch) for the last forward + backward

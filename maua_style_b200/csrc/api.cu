@@ -141,11 +141,15 @@ MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int
     return conv_dispatch(a, impl, (cudaStream_t)stream);
 }
 
-MAUA_API int maua_conv_tile_plan(int h, int w, int cin, int cout, int ntaps, int k2, int sms, int allow_split, int* plan6) {
+MAUA_API int maua_conv_tile_plan(int h, int w, int cin, int cout, int ntaps, int k2, int sms, int tail_mode, int* plan6) {
     MAUA_REQUIRE(plan6 && h > 0 && w > 0 && cout > 0 && sms > 0, "maua_conv_tile_plan: bad arguments");
     ConvArgs a;
     a.B = 1; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ntaps = ntaps; a.K2 = k2;
-    conv_tile_plan(a, sms, allow_split != 0, plan6, plan6 + 1, plan6 + 2, plan6 + 3, plan6 + 4, plan6 + 5);
+    // K-split plans assume the workspace exists (the plan owns one)
+    static float dummy_ws; static unsigned int dummy_flag;
+    if (tail_mode == 1) { a.splitk_ws = &dummy_ws; a.splitk_flags = &dummy_flag; }
+    a.tail_mode = tail_mode;
+    conv_tile_plan(a, sms, tail_mode == 1 ? 1 : (tail_mode == 2 ? 2 : 0), plan6, plan6 + 1, plan6 + 2, plan6 + 3, plan6 + 4, plan6 + 5);
     return MAUA_OK;
 }
 

@@ -50,6 +50,7 @@ struct ConvKParams {
     // same time.  Parts 0 .. split-2 dump their raw accumulators into splitk_ws; the last part adds them (fixed order:
     // deterministic) and runs the fused epilogue.
     int full_tiles, split, total_items;
+    int tail_halves;  // 1: the tail tiles are computed as two half-N items each (no hand-over) instead of K-split parts
     float* splitk_ws;
     unsigned int* splitk_flags;
     int direct;  // 1: register -> global epilogue (needed for the content / addend / fp32-mask terms), 0: TMA-store epilogue
@@ -126,11 +127,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ng2 = p.K2 / KCHUNK;                          // aux groups
     const int ng = ng1 + ng2;
 
-    struct Item { int tile, g0, g1, part, nparts, slot; };
+    struct Item { int tile, g0, g1, part, nparts, slot, nh; };
     auto get_item = [&](int it) {
         Item o;
+        o.nh = -1;
         if (it < p.full_tiles) {
             o.tile = it; o.g0 = 0; o.g1 = ng; o.part = 0; o.nparts = 1; o.slot = 0;
+        } else if (p.tail_halves) {
+            // tail tile r / 2, output-channel half r % 2: the whole K range, half of the tile's channels -- two independent
+            // items on two CTA units, nothing to hand over
+            const int r = it - p.full_tiles;
+            o.tile = p.full_tiles + (r >> 1);
+            o.nh = r & 1;
+            o.g0 = 0; o.g1 = ng; o.part = 0; o.nparts = 1; o.slot = 0;
         } else {
             const int r = it - p.full_tiles;
             o.slot = r / p.split;
@@ -141,6 +150,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o.g1 = ng * (o.part + 1) / p.split;
         }
         return o;
+    };
+
+    // Output channel (relative to the tile's first channel) of accumulator column c.  A half-N item of a CTA pair uses the first
+    // or second quarter of EACH CTA's weight rows (the pair's MMA takes N/2 rows from either CTA), i.e. two channel runs.
+    auto chan = [&](int c, int nh) -> int {
+        if (nh < 0) return c;
+        if (CG == 2) return (c < BN / 4 ? c : c - BN / 4 + BN / 2) + nh * (BN / 4);
+        return c + nh * (BN / 2);
     };
 
     if (warp == 0 && lane == 0) {
@@ -246,8 +263,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (the even CTA issues for the pair) =====================
-        constexpr uint32_t idesc = make_idesc_tf32(128 * CG, BN, 0, 0);
-        auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accumulate) {
+        constexpr uint32_t idesc_full = make_idesc_tf32(128 * CG, BN, 0, 0);
+        constexpr uint32_t idesc_half = make_idesc_tf32(128 * CG, BN >= 32 ? BN / 2 : BN, 0, 0);
+        auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accumulate) {
             if (CG == 2) umma_tf32_2sm(d, ad, bd, idesc, accumulate); else umma_tf32(d, ad, bd, idesc, accumulate);
         };
         auto commit = [&](uint64_t* bar) { if (CG == 2) umma_commit_2sm(bar); else umma_commit(bar); };
@@ -258,6 +276,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_empty_bar[acc], ((lt / NACC) & 1) ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
+            const uint32_t idesc = item.nh < 0 ? idesc_full : idesc_half;
+            // half-N item: this CTA's quarter (pair) / half (single CTA) of the weight rows it holds
+            const uint32_t b_off = item.nh < 0 ? 0u : static_cast<uint32_t>(item.nh) * ((CG == 2 ? BN / 4 : BN / 2) * 128);
             uint32_t started = 0;  // 0 until the first MMA of this tile has been issued (per sub-tile: same flag)
             for (int g = item.g0; g < item.g1; ++g) {
                 const int sa = ia % NA;
@@ -272,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ++ib;
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + sb * Cfg::B_STAGE), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smemB + sb * Cfg::B_STAGE) + b_off, 16, 1024);
 #pragma unroll
                         for (int m = 0; m < MT; ++m) {
                             // halo box: sub-tile m, vertical tap j starts (m*8 + j) image rows into the box
@@ -281,7 +302,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int kk = 0; kk < KCHUNK / 8; ++kk) {
                                 // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr >> 4) field
-                                mma(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, (started | kk) ? 1u : 0u);
+                                mma(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (started | kk) ? 1u : 0u);
                             }
                         }
                         commit(&b_empty[sb]);  // frees the weight slot (in both CTAs) once these MMAs have read it
@@ -354,6 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             };
+            const int ncols = item.nh < 0 ? BN : BN / 2;
             if (!p.direct) {
                 // TMEM -> registers -> fused epilogue -> swizzled staging box in shared memory -> TMA store.  A warp-wide
                 // 16-byte store straight to global would touch 32 different lines (the lanes are 32 different pixels): the
@@ -366,14 +388,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const bool valid = (h < p.H) && (w < p.W);
                     const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
 #pragma unroll 1
-                    for (int c = 0; c < BN; c += 32, ++box) {
+                    for (int c = 0; c < ncols; c += 32, ++box) {
+                        const int cn = n0 + chan(c, item.nh);  // first output channel of this 32-column chunk
                         float v[32];
                         tmem_ld_x32(t_base + m * BN + c, v);
                         if (nprev > 0) add_partials(v, 32, m, c);
                         if (ep.bias) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c + i));
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + cn + i));
                                 v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
                             }
                         }
@@ -382,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
                         if (ep.mask_bits) {
-                            const uint32_t mk = valid ? __ldg(ep.mask_bits + pix * words + ((n0 + c) >> 5)) : 0u;
+                            const uint32_t mk = valid ? __ldg(ep.mask_bits + pix * words + (cn >> 5)) : 0u;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
                         }
@@ -394,7 +417,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             uint32_t bits = 0;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-                            ep.mask_out[pix * words + ((n0 + c) >> 5)] = bits;
+                            ep.mask_out[pix * words + (cn >> 5)] = bits;
                         }
                         uint8_t* sbox = stage_box + (box & 1) * STAGE_BOX_BYTES;
                         // the store that last read this staging box (two boxes ago) must have drained it
@@ -408,8 +431,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         fence_proxy_async_smem();
                         named_bar_sync(2, 128);
                         if (issuer) {
-                            tma_store_4d(&tmOut, sbox, n0 + c, w0, h0 + m * TILE_H, b);
-                            if (ep.out2) tma_store_4d(&tmOut2, sbox, n0 + c, w0, h0 + m * TILE_H, b);
+                            tma_store_4d(&tmOut, sbox, cn, w0, h0 + m * TILE_H, b);
+                            if (ep.out2) tma_store_4d(&tmOut2, sbox, cn, w0, h0 + m * TILE_H, b);
                             bulk_commit_group();
                         }
                         if (POOL) {
@@ -444,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     o.z = fmaxf(fmaxf(a[0].z, a[1].z), fmaxf(a[2].z, a[3].z)); o.w = fmaxf(fmaxf(a[0].w, a[1].w), fmaxf(a[2].w, a[3].w));
                                 }
                                 if (ph < PH && pw < PW)
-                                    *reinterpret_cast<float4*>(ep.pool_out + ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + n0 + c + 4 * k) = o;
+                                    *reinterpret_cast<float4*>(ep.pool_out + ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + cn + 4 * k) = o;
                             }
                         }
                     }
@@ -456,17 +479,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int w = w0 + wl;
                 const bool valid = (h < p.H) && (w < p.W);
                 const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
-                const size_t off = pix * p.Cout + n0;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 16) {
+                for (int c0 = 0; c0 < ncols; c0 += 16) {
+                    const int cn = n0 + chan(c0, item.nh);
+                    const size_t off = pix * p.Cout + cn;  // element offset of this 16-channel chunk
+                    constexpr int c = 0;                   // (the chunk-relative offsets below were written as off + c + i)
                     float v[16];
-                    tmem_ld_x16(t_base + m * BN + c, v);
-                    if (nprev > 0) add_partials(v, 16, m, c);
+                    tmem_ld_x16(t_base + m * BN + c0, v);
+                    if (nprev > 0) add_partials(v, 16, m, c0);
                     if (valid) {
                         if (ep.bias) {
 #pragma unroll
                             for (int i = 0; i < 16; i += 4) {
-                                const float4 bv = *reinterpret_cast<const float4*>(ep.bias + n0 + c + i);
+                                const float4 bv = *reinterpret_cast<const float4*>(ep.bias + cn + i);
                                 v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
                             }
                         }
@@ -499,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                         if (ep.mask_bits) {
-                            const uint32_t mk = ep.mask_bits[pix * words + ((n0 + c) >> 5)] >> ((n0 + c) & 31);
+                            const uint32_t mk = ep.mask_bits[pix * words + (cn >> 5)] >> (cn & 31);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
                         }
@@ -511,7 +536,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             uint32_t bits = 0;
 #pragma unroll
                             for (int i = 0; i < 16; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-                            reinterpret_cast<uint16_t*>(ep.mask_out)[pix * (2 * words) + ((n0 + c) >> 4)] = (uint16_t)bits;
+                            reinterpret_cast<uint16_t*>(ep.mask_out)[pix * (2 * words) + (cn >> 4)] = (uint16_t)bits;
                         }
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
@@ -635,11 +660,20 @@ constexpr int kMinGroupsPerPart = 4;
 
 // Split-K plan of a launch: the tiles of the last partial wave (all tiles when there are fewer tiles than CTA units) are
 // split into `split` K-ranges each, as long as every range keeps >= kMinGroupsPerPart k-groups.
-struct SplitPlan { int full_tiles, split, items; };
-SplitPlan plan_split(long tiles, int units, int ngroups, bool allowed) {
-    SplitPlan sp{(int)tiles, 1, (int)tiles};
+struct SplitPlan { int full_tiles, split, items, halves; };
+// mode 0: every tile whole; 1: K-split tail (needs the workspace); 2: half-N tail -- the R tiles of the last partial wave become
+// 2 R independent half-channel items when they fit the CTA units (2 R <= units) and the halves stay MMA / epilogue friendly.
+SplitPlan plan_split(long tiles, int units, int ngroups, int mode, int bn = 0, int cg = 1) {
+    SplitPlan sp{(int)tiles, 1, (int)tiles, 0};
     const int rem = (int)(tiles % units);
-    if (!allowed || rem == 0) return sp;
+    if (mode == 0 || rem == 0) return sp;
+    if (mode == 2) {
+        if (2 * rem > units || bn < (cg == 2 ? 128 : 64)) return sp;
+        sp.full_tiles = (int)tiles - rem;
+        sp.halves = 1;
+        sp.items = sp.full_tiles + 2 * rem;
+        return sp;
+    }
     int s = units / rem;
     if (s > kMaxSplit) s = kMaxSplit;
     if (s > ngroups / kMinGroupsPerPart) s = ngroups / kMinGroupsPerPart;
@@ -652,7 +686,11 @@ SplitPlan plan_split(long tiles, int units, int ngroups, bool allowed) {
 int conv_groups(const ConvArgs& a) {
     return (a.ntaps == 9 ? 3 * (a.Cin / KCHUNK) : (a.ntaps == 1 ? a.Cin / KCHUNK : 0)) + a.K2 / KCHUNK;
 }
-bool splitk_enabled() { return true; }  // the caller opts in by passing a workspace (maua_plan_set_splitk / MAUA_SPLITK=1)
+// tail handling requested by the caller: ConvArgs::tail_mode (K-split additionally needs the workspace)
+int effective_tail_mode(const ConvArgs& a) {
+    if (a.tail_mode == 1) return (a.splitk_ws && a.splitk_flags) ? 1 : 0;
+    return a.tail_mode == 2 ? 2 : 0;
+}
 
 // Tile selection: relative MAC rates of the tile shapes measured on B200 (tools/sweep_conv.sh, profiles/ round 1) times
 // the occupancy of the waves.  What the sweep shows: with both operands in shared memory an MMA is paced by the
@@ -660,7 +698,7 @@ bool splitk_enabled() { return true; }  // the caller opts in by passing a works
 // each CTA holds half of the weight rows) win, and a tile needs its accumulator double-buffered in TMEM (MT * BN <= 256)
 // to keep the epilogue off the critical path.  With split-K (plan_split) the last partial wave costs 1 / split of a tile
 // time instead of a whole one, which is what decides the shape at <= 512^2 where every layer is a partial wave.
-SplitPlan choose_tile(const ConvArgs& a, int sms, bool allow_split, int& bn_out, int& mt_out, int& cg_out) {
+SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, int& mt_out, int& cg_out) {
     auto shape_rate = [](int bn, int mt, int cg) -> double {
         if (cg == 2) {
             if (bn == 256) return mt == 1 ? 1.00 : 0.88;
@@ -686,9 +724,11 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, bool allow_split, int& bn_out,
                 const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) *
                                    ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
                 // time in units of one tile: full waves + the split last wave (1 / split, plus the hand-over of partials)
-                const SplitPlan sp = plan_split(tiles, units, ngroups, allow_split);
-                const double waves = sp.split > 1 ? (double)(sp.full_tiles / units) + 1.0 / sp.split + 0.03
-                                                  : (double)((tiles + units - 1) / units);
+                const SplitPlan sp = plan_split(tiles, units, ngroups, tail_mode, bn, cg);
+                // a half-N item does half the MMA work at the (lower) rate of the half-width shape
+                const double waves = sp.halves ? (double)(sp.full_tiles / units) + 0.5 * shape_rate(bn, mt, cg) / shape_rate(bn / 2, mt, cg)
+                                     : sp.split > 1 ? (double)(sp.full_tiles / units) + 1.0 / sp.split + 0.03
+                                                    : (double)((tiles + units - 1) / units);
                 const double eff = (double)tiles / (waves * units);
                 // rows of the (pair) tile that exist: ragged bottoms waste MMA work
                 const double rows = (double)a.H / (double)(((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * cg * mt * TILE_H);
@@ -703,7 +743,7 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, bool allow_split, int& bn_out,
             (fb == 32 || fb == 64 || fb == 128 || fb == 256)) {
             bn = fb; mt = fm; cg = fc;
             const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
-            best_sp = plan_split(tiles, sms / cg, ngroups, allow_split);
+            best_sp = plan_split(tiles, sms / cg, ngroups, tail_mode, bn, cg);
         }
     }
     bn_out = bn; mt_out = mt; cg_out = cg;
@@ -756,8 +796,8 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     p.ep = a.ep;
     p.direct = direct ? 1 : 0;
     const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
-    const SplitPlan sp = plan_split(p.total_tiles, units, conv_groups(a), a.splitk_ws && a.splitk_flags && splitk_enabled());
-    p.full_tiles = sp.full_tiles; p.split = sp.split; p.total_items = sp.items;
+    const SplitPlan sp = plan_split(p.total_tiles, units, conv_groups(a), effective_tail_mode(a), BN, CG);
+    p.full_tiles = sp.full_tiles; p.split = sp.split; p.total_items = sp.items; p.tail_halves = sp.halves;
     p.splitk_ws = a.splitk_ws; p.splitk_flags = a.splitk_flags;
     const int grid = CG * (p.total_items < units ? p.total_items : units);
     cudaLaunchConfig_t cfg;
@@ -796,12 +836,13 @@ size_t conv_splitk_ws_bytes() { return (size_t)148 * 128 * 512 * sizeof(float); 
 size_t conv_splitk_flag_words() { return 148 * 4 * 2; }
 
 // host-logic view of the launch plan (no GPU needed): tile shape + split-K plan for a layer on a device with `sms` SMs
-void conv_tile_plan(const ConvArgs& a, int sms, bool allow_split, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles, int* split) {
+void conv_tile_plan(const ConvArgs& a, int sms, int tail_mode, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles, int* split) {
     int b, m, c;
-    const SplitPlan sp = choose_tile(a, sms, allow_split && splitk_enabled(), b, m, c);
+    const SplitPlan sp = choose_tile(a, sms, tail_mode, b, m, c);
     *bn = b; *mt = m; *cg = c;
-    *full_tiles = sp.full_tiles; *split = sp.split;
-    *split_tiles = sp.split > 1 ? (sp.items - sp.full_tiles) / sp.split : 0;
+    *full_tiles = sp.full_tiles;
+    *split = sp.halves ? 2 : sp.split;
+    *split_tiles = sp.halves ? (sp.items - sp.full_tiles) / 2 : (sp.split > 1 ? (sp.items - sp.full_tiles) / sp.split : 0);
 }
 
 int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
@@ -816,11 +857,12 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
     MAUA_REQUIRE(a.ep.out != nullptr, "null output pointer");
 
     int bn, mt, cg;
-    const SplitPlan spc = choose_tile(a, num_sms(), a.splitk_ws && a.splitk_flags && splitk_enabled(), bn, mt, cg);
+    const SplitPlan spc = choose_tile(a, num_sms(), effective_tail_mode(a), bn, mt, cg);
     if (getenv("MAUA_CONV_DEBUG")) {  // one line per launch: the tile shape and split-K plan that was chosen
-        fprintf(stderr, "conv_tc %dx%d Cin %d Cout %d taps %d K2 %d: BN %d MT %d CG %d, %d whole tiles + %d split x%d on %d units\n",
-                a.H, a.W, a.Cin, a.Cout, a.ntaps, a.K2, bn, mt, cg, spc.full_tiles, spc.split > 1 ? (spc.items - spc.full_tiles) / spc.split : 0,
-                spc.split, num_sms() / cg);
+        fprintf(stderr, "conv_tc %dx%d Cin %d Cout %d taps %d K2 %d: BN %d MT %d CG %d, %d whole tiles + %d tail tiles (%s x%d) on %d units\n",
+                a.H, a.W, a.Cin, a.Cout, a.ntaps, a.K2, bn, mt, cg, spc.full_tiles,
+                spc.halves ? (spc.items - spc.full_tiles) / 2 : (spc.split > 1 ? (spc.items - spc.full_tiles) / spc.split : 0),
+                spc.halves ? "half-N" : "K-split", spc.halves ? 2 : spc.split, num_sms() / cg);
     }
     if (bn == 256) return mt == 2 ? launch_cg<256, 2>(a, cg, st) : launch_cg<256, 1>(a, cg, st);
     if (bn == 128) return mt == 2 ? launch_cg<128, 2>(a, cg, st) : launch_cg<128, 1>(a, cg, st);

@@ -56,8 +56,11 @@ struct ConvArgs {
     // the flag words must be zero before the first launch and are left zero by every launch.
     float* splitk_ws = nullptr;
     unsigned int* splitk_flags = nullptr;
+    // How the last partial wave of tiles is computed: 0 = whole tiles, 1 = K-split (needs the workspace above), 2 = as two
+    // half-N items per tile (independent, no hand-over).
+    int tail_mode = 0;
 };
-void conv_tile_plan(const ConvArgs& a, int sms, bool allow_split, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles,
+void conv_tile_plan(const ConvArgs& a, int sms, int tail_mode, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles,
                     int* split);
 size_t conv_splitk_ws_bytes();
 size_t conv_splitk_flag_words();

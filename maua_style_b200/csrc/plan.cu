@@ -136,6 +136,7 @@ struct maua_plan {
     // the hand-over of partial accumulators through L2 costs ~20 us per split wave, more than the idle SMs it recovers at
     // every size from 256^2 to 2048^2, so it is OFF by default (MAUA_SPLITK=1 / maua_plan_set_splitk turn it on).
     bool splitk = false;
+    int conv_tail = 2;            // half-N items for the last partial wave (0: whole tiles; K-split: `splitk`)
     bool fuse_pool = true;        // pool inside the producing conv's epilogue (MAUA_FUSE_POOL=0 at plan creation: separate pass)
     size_t weight_bytes = 0;
     // workspaces
@@ -276,6 +277,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     p->avg_pool = d->avg_pool;
     if (const char* f = getenv("MAUA_FUSE_POOL")) p->fuse_pool = atoi(f) != 0;
     if (const char* f = getenv("MAUA_SPLITK")) p->splitk = atoi(f) != 0;
+    if (const char* f = getenv("MAUA_CONV_TAIL")) p->conv_tail = atoi(f);
     p->begin = begin;
     p->last_stage = (end == d->n_entries);
     memset(&p->img_io, 0, sizeof(p->img_io));
@@ -487,6 +489,13 @@ MAUA_API int maua_plan_set_splitk(maua_plan_t* p, int enable) {
     return MAUA_OK;
 }
 
+MAUA_API int maua_plan_set_conv_tail(maua_plan_t* p, int mode) {
+    MAUA_REQUIRE(p && mode >= 0 && mode <= 2, "maua_plan_set_conv_tail: bad arguments");
+    p->splitk = mode == 1;
+    p->conv_tail = mode == 1 ? 0 : mode;
+    return MAUA_OK;
+}
+
 MAUA_API int maua_plan_set_profile(maua_plan_t* p, int enable) {
     MAUA_REQUIRE(p, "maua_plan_set_profile: null plan");
     p->profile = enable != 0;
@@ -637,6 +646,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = rnd;
             a.ep.mask_out = e.bits;
             if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
+            a.tail_mode = p->splitk ? 1 : p->conv_tail;
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
@@ -809,6 +819,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     auto run_conv = [&](ConvArgs& a) -> int {
         p->launches_bwd++;
         if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
+        a.tail_mode = p->splitk ? 1 : p->conv_tail;
         const int r = conv_dispatch(a, p->impl, st);
         const double px = (double)a.H * a.W;
         // algorithmic work: dgrad GEMM + StyleLoss backward GEMM; bytes: gradient in + out, mask / feature read

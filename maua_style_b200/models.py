@@ -269,7 +269,8 @@ class B200Net(nn.Module):
             st["loss_vec"].zero_()
             _lib.check(self._lib.maua_plan_set_impl(st["plan"], default_impl()), "maua_plan_set_impl")
             _lib.check(self._lib.maua_plan_set_profile(st["plan"], 0), "maua_plan_set_profile")
-            _lib.check(self._lib.maua_plan_set_splitk(st["plan"], int(os.environ.get("MAUA_SPLITK", "0") == "1")), "maua_plan_set_splitk")
+            _lib.check(self._lib.maua_plan_set_conv_tail(st["plan"], 1 if os.environ.get("MAUA_SPLITK", "0") == "1"
+                                                         else int(os.environ.get("MAUA_CONV_TAIL", "2"))), "maua_plan_set_conv_tail")
             _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(os.environ.get("MAUA_FUSE_POOL", "1") != "0")),
                        "maua_plan_set_fuse_pool")
         self._plan = self._stages[0]["plan"]
@@ -315,6 +316,11 @@ class B200Net(nn.Module):
         """K-split of the last partial wave of conv tiles (csrc/conv_tc.cu; off by default)."""
         for st in self._stages:
             _lib.check(self._lib.maua_plan_set_splitk(st["plan"], int(enable)), "maua_plan_set_splitk")
+
+    def set_conv_tail(self, mode: int):
+        """Last partial wave of the persistent conv kernels: 0 whole tiles, 1 K-split, 2 half-N items (default)."""
+        for st in self._stages:
+            _lib.check(self._lib.maua_plan_set_conv_tail(st["plan"], int(mode)), "maua_plan_set_conv_tail")
 
     def device_bytes(self) -> int:
         return sum(int(self._lib.maua_plan_device_bytes(st["plan"])) for st in self._stages)

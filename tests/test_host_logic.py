@@ -172,6 +172,8 @@ def test_conv_tile_plan_host_logic():
 
     assert plan(256, 256, 256, 256) == [256, 1, 2, 256, 0, 1]
     assert plan(256, 256, 256, 256, split=1) == [256, 1, 2, 222, 34, 2]
+    assert plan(256, 256, 256, 256, split=2) == [256, 1, 2, 222, 34, 2]   # half-N tail: 34 tiles -> 68 independent items
+    assert plan(128, 128, 512, 512, split=2)[5] == 1                      # 128 tiles on 74 pairs: 2 x 54 > 74, stays whole
     assert plan(1024, 1024, 64, 64) == [64, 2, 2, 2048, 0, 1]
     bn, mt, cg, whole, split_tiles, s = plan(16, 16, 512, 512, split=1)
     assert whole == 0 and 2 <= s <= 8 and split_tiles * s <= 148 // cg

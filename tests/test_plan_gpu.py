@@ -273,6 +273,35 @@ def test_split_k_plan_agrees_with_the_unsplit_plan(ckpt, hw):
     assert torch.equal(res[1][1], res[2][1]) and torch.equal(res[1][0], res[2][0])  # deterministic
 
 
+@pytest.mark.parametrize("hw", [(256, 256), (200, 328), (90, 122)])
+def test_half_n_tail_items_are_bit_identical_to_whole_tiles(ckpt, hw):
+    """The last partial wave of a persistent conv launch is computed as two half-channel items per tile (default): each
+    output element is the same K-ordered sum in the same accumulator, so features, losses and the image gradient must be
+    bit-identical to whole-tile execution -- max pooling, fused pool epilogue, folded StyleLoss backward and content taps
+    included."""
+    from maua_style_b200 import optim
+
+    z, meta = load_golden("adam_gram_90x122")
+    meta = dict(meta)
+    meta["h"], meta["w"] = hw
+    meta["style_hw"] = [list(hw)]
+    content, styles, init = golden_inputs(meta)
+    res = []
+    for mode in (0, 2):
+        args, net, losses, _ = build(ckpt, meta)
+        net.set_conv_tail(mode)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, styles, args)
+        for m in losses:
+            m.mode = "loss"
+        v, g = optim.feval(net, init.clone().cuda())
+        res.append((v.clone(), g.clone(), [net.tap_feature(t) for t in range(len(net.taps))]))
+        del net, losses
+    for a, b in zip(res[0][2], res[1][2]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 def test_temporal_loss_and_autograd_interface(ckpt):
     """vid_img path: set_temporal_targets + weighted temporal ContentLoss (loss.py:46-54) through net(x).backward()."""
     from maua_style_b200 import optim
