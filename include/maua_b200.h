@@ -233,7 +233,11 @@ typedef struct maua_plan maua_plan_t;
 #define MAUA_MAX_TAPS 16
 
 typedef enum maua_tap_kind { MAUA_TAP_STYLE = 0, MAUA_TAP_CONTENT = 1 } maua_tap_kind;
-typedef enum maua_tap_mode { MAUA_MODE_NONE = 0, MAUA_MODE_CAPTURE = 1, MAUA_MODE_LOSS = 2 } maua_tap_mode;
+/* MAUA_MODE_EXTERNAL (style taps only): the forward pass keeps the tap's feature map but computes nothing for it; the
+ * caller forms the loss from the features of SEVERAL plans (the frames of an img_vid window, loss.py:141-181 with B > 1:
+ * per-frame static Grams and the [B*C, B*C] dynamic Gram) and hands this frame's backward GEMM term back with
+ * maua_plan_set_tap_fold before maua_plan_backward. */
+typedef enum maua_tap_mode { MAUA_MODE_NONE = 0, MAUA_MODE_CAPTURE = 1, MAUA_MODE_LOSS = 2, MAUA_MODE_EXTERNAL = 3 } maua_tap_mode;
 
 /* Network description: models.py:135-139 channel_list entry truncated after the last tapped ReLU
  * (models.py:382).  channels[i] > 0: conv3x3(channels[i]) + ReLU;  channels[i] == 0: 2x2 pool. */
@@ -247,6 +251,11 @@ typedef struct maua_net_desc {
     int tap_relu_index[MAUA_MAX_TAPS];  /* 0-based index of the ReLU (= conv count - 1) the loss module follows */
     int tap_kind[MAUA_MAX_TAPS];        /* maua_tap_kind; taps must be ordered by relu index (content before style
                                            at the same index, as models.py:411-431 inserts them) */
+    /* Channel-pruned VGG-16 (models.py:136 "VGG-16p": 24, 22, 41, 51, 108, 89, 111, 184, 276, 228, 512...): the caller
+     * zero-pads every conv's weights / bias to a channel count the tcgen05 kernels tile (multiples of 64; 64 or a
+     * multiple of 128 under a style tap) and names the REAL count here; the Gram 1/(C*H*W), the nn.MSELoss means and the
+     * gradient scales use it, so padded and unpadded networks give the same losses and gradients.  0 = channels[i]. */
+    int norm_channels[MAUA_MAX_LAYERS];
 } maua_net_desc;
 
 /* Per-call, per-tap state: targets are caller-owned tensors so the Python loss modules can expose them
@@ -329,6 +338,18 @@ MAUA_API int maua_plan_tap_gram(maua_plan_t* plan, int tap, float* dst, int* c, 
 /* Copy the feature map of tap `tap` from the last forward (NHWC [H_l][W_l][C]) into dst (NULL: query the shape). */
 MAUA_API int maua_plan_tap_feature(maua_plan_t* plan, int tap, float* dst, int* h, int* w, int* c,
                                    maua_stream_t stream);
+/* The same copy into a wider matrix: pixel p of the tap goes to dst + p * dst_pixel_stride (channels contiguous).  With
+ * dst = X + b*C and stride B*C the B frames of an img_vid window are laid side by side as the [H_l*W_l][B*C] matrix whose
+ * Gram is the reference's dynamic [B*C, B*C] Gram (loss.py:164-168) and whose diagonal blocks are the per-frame static
+ * Grams (loss.py:143-144).  Asynchronous on `stream`, graph-capturable. */
+MAUA_API int maua_plan_tap_feature_strided(maua_plan_t* plan, int tap, float* dst, long dst_pixel_stride,
+                                           maua_stream_t stream);
+/* Backward term of a style tap in MAUA_MODE_EXTERNAL: the gradient w.r.t. the tapped feature map gets
+ * + sum_k in2[pixel][k] * w2[c][k] (+ bias[c]), folded into the dgrad GEMM of the layer above as k2/32 extra k-steps.
+ * in2: NHWC [H_l][W_l][k2] (TF32-rounded values), w2: [C][k2] (TF32-rounded), bias: [C] or NULL; k2 % 32 == 0.  Replaces
+ * the four backward torch.mm of loss.py:141-181 for B > 1.  Must be called after every forward that used the mode. */
+MAUA_API int maua_plan_set_tap_fold(maua_plan_t* plan, int tap, const float* in2, int k2, const float* w2,
+                                    const float* bias);
 /* Copy the output of stack entry `entry` (conv entries: the post-ReLU activation, models.py:129-130; pool entries: the
  * pooled map) from the last forward, NHWC [*h][*w][*c]; dst NULL queries the shape.  These are the tensors the backward
  * pass derives its ReLU masks and max-pool arg-max decisions from (tests: decision-level comparison with the oracle). */

@@ -37,6 +37,7 @@ class NetDesc(C.Structure):
         ("n_taps", C.c_int),
         ("tap_relu_index", C.c_int * MAUA_MAX_TAPS),
         ("tap_kind", C.c_int * MAUA_MAX_TAPS),
+        ("norm_channels", C.c_int * MAUA_MAX_LAYERS),
     ]
 
 

@@ -235,7 +235,7 @@ __global__ void gram_exact_sum_kernel(const double* __restrict__ dpartial, int S
 // *loss_out = scale * mean(diff^2).
 template <int G>
 __global__ void __launch_bounds__(kReduceThreads)
-gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long P, int full, const float* __restrict__ mean,
+gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, int Cn, long P, int full, const float* __restrict__ mean,
                      float* __restrict__ gram, const float* __restrict__ target, float* __restrict__ diff, float scale,
                      float* __restrict__ loss_out, double* red_partials, unsigned int* counter) {
     constexpr int NO = kReduceThreads / G;  // outputs per block round
@@ -265,7 +265,7 @@ gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long 
                 for (int y = 0; y < G; ++y) t += sh[y][tx];
             }
             if (mean) t -= (float)P * mean[c] * mean[d];
-            const float g = t / ((float)C * (float)P);
+            const float g = t / ((float)Cn * (float)P);  // Cn < C: zero-padded channels (pruned VGG-16), normalised as the real count
             const bool mirror = !full && ((c >> 7) != (d >> 7));
             const long im = (long)d * C + c;
             gram[i] = g;
@@ -285,7 +285,7 @@ gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long 
     }
     if (target) {
         double v[1] = {acc}, tot[1];
-        if (grid_sum<1>(v, red_partials, counter, tot)) *loss_out = scale * (float)(tot[0] / (double)total);
+        if (grid_sum<1>(v, red_partials, counter, tot)) *loss_out = scale * (float)(tot[0] / ((double)Cn * (double)Cn));
     }
 }
 
@@ -361,9 +361,11 @@ size_t gram_workspace_bytes(int C) {
 }
 
 int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* mean_out, void* workspace, int impl,
-                cudaStream_t st, const GramLossFuse* fuse) {
-    MAUA_REQUIRE(C >= 64 && (C == 64 || C % 128 == 0) && C <= 1024,
-                 "gram: channel count %d unsupported (need 64 or a multiple of 128, <= 1024)", C);
+                cudaStream_t st, const GramLossFuse* fuse, int Cn) {
+    if (Cn <= 0) Cn = C;
+    // (the [B*C, B*C] dynamic Gram of an img_vid window, loss.py:164-168, is this kernel on the B*C-channel matrix)
+    MAUA_REQUIRE(C >= 64 && (C == 64 || C % 128 == 0) && C <= 16384,
+                 "gram: channel count %d unsupported (need 64 or a multiple of 128, <= 16384)", C);
     MAUA_REQUIRE(P >= 1 && P < (1L << 31), "gram: bad pixel count %ld", P);
     const int T = (C + 127) / 128;
     const int ntiles = T * (T + 1) / 2;
@@ -427,7 +429,7 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
     }
     const float* mu = (use_cov && !centred) ? mean_out : nullptr;
 #define MAUA_FINALIZE(GG)                                                                                                          \
-    MAUA_CUDA_CHECK(launch_pdl<PDL_GRAM>(gram_finalize_kernel<GG>, dim3(fgrid), dim3(kReduceThreads), 0, st, (const float*)partial, nsplit, C, P, \
+    MAUA_CUDA_CHECK(launch_pdl<PDL_GRAM>(gram_finalize_kernel<GG>, dim3(fgrid), dim3(kReduceThreads), 0, st, (const float*)partial, nsplit, C, Cn, P, \
                                full, mu, gram, tgt, dif, sc, lout, rp, cnt))
     if (G == 8) MAUA_FINALIZE(8); else if (G == 4) MAUA_FINALIZE(4); else if (G == 2) MAUA_FINALIZE(2); else MAUA_FINALIZE(1);
 #undef MAUA_FINALIZE

@@ -6,7 +6,8 @@
 namespace maua {
 
 size_t gram_workspace_bytes(int C);
-// gram[c][d] = (sum_p f[p][c] f[p][d] - [cov] P mu_c mu_d) / (C * P);   f is NHWC-flattened [P][C].
+// gram[c][d] = (sum_p f[p][c] f[p][d] - [cov] P mu_c mu_d) / (Cn * P);   f is NHWC-flattened [P][C].
+// Cn (0 = C) is the channel count the normalisations use: the real count of a layer whose channels are zero-padded to C.
 // Optional fusion of the StyleLoss value into the finalize kernel: diff = gram - target, *loss_out = scale * mse.
 struct GramLossFuse {
     const float* target = nullptr;
@@ -16,7 +17,7 @@ struct GramLossFuse {
     ReduceScratch rs;
 };
 int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* mean_out, void* workspace, int impl,
-                cudaStream_t st, const GramLossFuse* fuse = nullptr);
+                cudaStream_t st, const GramLossFuse* fuse = nullptr, int Cn = 0);
 int style_loss_fwd_launch(const float* gram, const float* target, int C, float value_scale, float* loss_out,
                           float* diff, ReduceScratch rs, cudaStream_t st);
 int style_loss_bwd_prep_launch(const float* diff, const float* mean, int C, long P, const float* coef, float* aux_d,

@@ -43,6 +43,7 @@ struct Entry {
     float *wg32 = nullptr, *wd32 = nullptr, *wt1_32 = nullptr;  // un-rounded copies, MAUA_IMPL_FP32 only (made on demand)
     // per forward
     int H = 0, W = 0, C = 0;   // output extent
+    int Cn = 0;                // conv only: channel count the loss normalisations use (< C when the layer is zero-padded)
     float* out = nullptr;      // arena pointer
     uint32_t* bits = nullptr;  // conv only: sign bitmap of `out` (1 bit / element), the ReLU mask of the backward pass
 };
@@ -52,6 +53,7 @@ struct Tap {
     int relu_index = 0;
     int entry = -1;
     int C = 0;
+    int Cn = 0;  // normalisation channel count (maua_net_desc::norm_channels)
     float *gram = nullptr, *diff = nullptr, *mean = nullptr, *aux_d = nullptr, *aux_bias = nullptr;
     void* gram_ws = nullptr;
     // state of the last forward
@@ -59,6 +61,12 @@ struct Tap {
     bool active = false;  // contributes to the backward pass
     int use_cov = 0;
     float* target = nullptr;
+    // MAUA_MODE_EXTERNAL (img_vid windows, loss.py:141-181 with B > 1): the caller computes the style loss from the
+    // tap features of all frames and hands the backward GEMM term of THIS frame back through maua_plan_set_tap_fold
+    const float* ext_in2 = nullptr;   // NHWC [H][W][ext_K2]
+    int ext_K2 = 0;
+    const float* ext_w2 = nullptr;    // [C][ext_K2]
+    const float* ext_bias = nullptr;  // [C] or null
 };
 
 // Backward prologue in ONE launch: coef2[i] = coefs[i] * factor[i] for every module slot (block (0,0)), and for every live
@@ -305,6 +313,8 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
             en.cin = cin;
             en.cout = d->channels[i];
             en.C = en.cout;
+            en.Cn = d->norm_channels[i] > 0 ? d->norm_channels[i] : en.cout;
+            MAUA_REQUIRE(en.Cn <= en.cout, "conv entry %d: norm_channels %d exceeds channels %d", i, en.Cn, en.cout);
             en.conv_index = convs++;
             en.image_layer = (i == 0);
             if (i > 0 && !(en.cin % 32 == 0 && en.cout % 64 == 0)) {
@@ -376,6 +386,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
             }
         if (tp.entry >= 0) {
             tp.C = p->entries[tp.entry].cout;
+            tp.Cn = p->entries[tp.entry].Cn;
             if (tp.kind == MAUA_TAP_STYLE) {
                 if (!(tp.C == 64 || tp.C % 128 == 0)) {
                     set_last_error("style tap on %d channels unsupported", tp.C);
@@ -670,7 +681,13 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             if (tp.entry != i || tp.mode == MAUA_MODE_NONE) continue;
             const long P = (long)e.H * e.W;
             const long numel = P * e.C;
-            if (tp.kind == MAUA_TAP_STYLE) {
+            const float numel_n = (float)(P * e.Cn);  // nn.MSELoss mean over the REAL elements (padded channels are zero)
+            if (tp.kind == MAUA_TAP_STYLE && tp.mode == MAUA_MODE_EXTERNAL) {
+                // the feature map stays in the arena; loss value and backward term come from the caller
+                tp.active = true;
+                tp.ext_in2 = nullptr; tp.ext_K2 = 0; tp.ext_w2 = nullptr; tp.ext_bias = nullptr;
+                p->factors[t] = 1.f;
+            } else if (tp.kind == MAUA_TAP_STYLE) {
                 MAUA_REQUIRE(tp.target && tio[t].target_elems == (long)tp.C * tp.C,
                              "style tap %d: target must be a [%d,%d] device tensor", t, tp.C, tp.C);
                 GramLossFuse fuse;
@@ -682,7 +699,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 }
                 // one SYRK + one finalize kernel (which also produces G - A and the loss value in loss mode)
                 if ((rc = gram_launch(e.out, P, tp.C, tp.use_cov, tp.gram, tp.mean, tp.gram_ws, p->impl, st,
-                                      loss_mode ? &fuse : nullptr)))
+                                      loss_mode ? &fuse : nullptr, tp.Cn)))
                     return rc;
                 p->launches_fwd += 2 + (tp.use_cov ? 2 : 0);
                 prof_mark(p, st, "gram_syrk", i, (double)tp.C * (tp.C + 1) * P, 4.0 * P * tp.C);
@@ -704,13 +721,13 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                     MAUA_CUDA_CHECK(cudaMemcpyAsync(tp.target, e.out, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
                 } else if (tp.target && tio[t].target_elems == numel) {  // loss.py:44: silently skipped on shape mismatch
                     MAUA_REQUIRE(losses_out, "losses_out is required in loss mode");
-                    if ((rc = mse_value_launch(e.out, tp.target, numel, tio[t].value_scale / (float)numel, losses_out + t,
+                    if ((rc = mse_value_launch(e.out, tp.target, numel, tio[t].value_scale / numel_n, losses_out + t,
                                                rs, st)))
                         return rc;
                     p->launches_fwd++;
                     prof_mark(p, st, "content_loss", i, 0, 8.0 * numel);
                     tp.active = true;
-                    p->factors[t] = 2.f / (float)numel;
+                    p->factors[t] = 2.f / numel_n;
                 }
             }
         }
@@ -781,16 +798,21 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         for (int t = 0; t < nt; ++t) {
             Tap& tp = p->taps[t];
             if (!tp.active || tp.kind != MAUA_TAP_STYLE) continue;
+            if (tp.mode == MAUA_MODE_EXTERNAL) {
+                MAUA_REQUIRE(tp.ext_in2 && tp.ext_w2 && tp.ext_K2 > 0,
+                             "style tap %d is in external mode but maua_plan_set_tap_fold was not called after the forward pass", t);
+                continue;
+            }
             const Entry& e = p->entries[tp.entry];
             const int j = bp.n_style++;
             bp.diff[j] = tp.diff; bp.aux_d[j] = tp.aux_d; bp.C[j] = tp.C; bp.slot[j] = t;
-            bp.inv_c3p[j] = 4.f / ((float)tp.C * (float)tp.C * (float)tp.C * (float)((long)e.H * e.W));
+            bp.inv_c3p[j] = 4.f / ((float)tp.Cn * (float)tp.Cn * (float)tp.Cn * (float)((long)e.H * e.W));
         }
         MAUA_CUDA_CHECK(launch_pdl(bwd_prep_kernel, dim3(128, bp.n_style > 0 ? bp.n_style : 1), dim3(256), 0, st, grad_coefs, p->coef2, bp));
         p->launches_bwd++;
         for (int t = 0; t < nt; ++t) {  // covariance: aux_bias = -aux_d @ mean (loss.py:87-89)
             Tap& tp = p->taps[t];
-            if (!tp.active || tp.kind != MAUA_TAP_STYLE || !tp.use_cov) continue;
+            if (!tp.active || tp.kind != MAUA_TAP_STYLE || !tp.use_cov || tp.mode == MAUA_MODE_EXTERNAL) continue;
             if ((rc = style_loss_bwd_bias_launch(tp.aux_d, tp.mean, tp.C, tp.aux_bias, st))) return rc;
             p->launches_bwd++;
         }
@@ -808,7 +830,10 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         }
     };
     auto add_taps = [&](ConvArgs& a, const Entry& e, Tap* style, Tap* content, int content_idx) {
-        if (style) {
+        if (style && style->mode == MAUA_MODE_EXTERNAL) {
+            a.K2 = style->ext_K2; a.in2 = style->ext_in2; a.w2 = style->ext_w2;
+            a.ep.bias = style->ext_bias;
+        } else if (style) {
             a.K2 = e.C; a.in2 = e.out; a.w2 = style->aux_d;
             a.ep.bias = style->use_cov ? style->aux_bias : nullptr;
         }
@@ -1058,6 +1083,29 @@ MAUA_API int maua_plan_entry_output(maua_plan_t* p, int entry, float* dst, int* 
     if (dst)
         MAUA_CUDA_CHECK(cudaMemcpyAsync(dst, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDeviceToDevice,
                                         (cudaStream_t)stream));
+    return MAUA_OK;
+}
+
+MAUA_API int maua_plan_set_tap_fold(maua_plan_t* p, int tap, const float* in2, int k2, const float* w2, const float* bias) {
+    MAUA_REQUIRE(p && tap >= 0 && tap < (int)p->taps.size() && p->taps[tap].kind == MAUA_TAP_STYLE && p->taps[tap].entry >= 0,
+                 "maua_plan_set_tap_fold: bad tap index");
+    MAUA_REQUIRE(in2 && w2 && k2 > 0 && k2 % 32 == 0, "maua_plan_set_tap_fold: need in2, w2 and k2 %% 32 == 0 (got %d)", k2);
+    Tap& tp = p->taps[tap];
+    MAUA_REQUIRE(tp.mode == MAUA_MODE_EXTERNAL && tp.active, "maua_plan_set_tap_fold: tap %d was not in external mode in the last forward", tap);
+    tp.ext_in2 = in2; tp.ext_K2 = k2; tp.ext_w2 = w2; tp.ext_bias = bias;
+    return MAUA_OK;
+}
+
+MAUA_API int maua_plan_tap_feature_strided(maua_plan_t* p, int tap, float* dst, long dst_pixel_stride, maua_stream_t stream) {
+    MAUA_REQUIRE(p && dst && tap >= 0 && tap < (int)p->taps.size() && p->taps[tap].entry >= 0,
+                 "maua_plan_tap_feature_strided: bad arguments");
+    const Entry& e = p->entries[p->taps[tap].entry];
+    MAUA_REQUIRE(p->taps[tap].entry <= p->last_entry, "maua_plan_tap_feature_strided: tap was not reached by the last forward");
+    MAUA_REQUIRE(dst_pixel_stride >= e.C, "maua_plan_tap_feature_strided: stride %ld < %d channels", dst_pixel_stride, e.C);
+    DeviceGuard guard(p->device);
+    MAUA_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pixel_stride * sizeof(float), e.out, (size_t)e.C * sizeof(float),
+                                      (size_t)e.C * sizeof(float), (size_t)e.H * e.W, cudaMemcpyDeviceToDevice,
+                                      (cudaStream_t)stream));
     return MAUA_OK;
 }
 

@@ -29,6 +29,7 @@ from .loss import ContentLoss, ScaleGradients, StyleLoss, TVLoss  # noqa: F401  
 
 # models.py:135-139
 channel_list = {
+    "VGG-16p": [24, 22, "P", 41, 51, "P", 108, 89, 111, "P", 184, 276, 228, "P", 512, 512, 512, "P"],
     "VGG-16": [64, 64, "P", 128, 128, "P", 256, 256, 256, "P", 512, 512, 512, "P", 512, 512, 512, "P"],
     "VGG-19": [64, 64, "P", 128, 128, "P", 256, 256, 256, 256, "P", 512, 512, 512, 512, "P", 512, 512, 512, 512, "P"],
 }
@@ -84,10 +85,6 @@ def _architecture(model_file: str, pooling: str):
     e.g. "episode" does not select the SOD model)."""
     full = str(model_file).lower()
     arch = _match_architecture(os.path.basename(full)) or _match_architecture(full)
-    if arch == "VGG-16p":
-        raise ValueError(
-            f"maua_style_b200: the channel-pruned VGG-16 ({model_file!r}) has channel counts that are not multiples of 32, "
-            "which the tcgen05 conv kernels require; use the reference's torch modules for it")
     if arch is None:
         raise ValueError(
             f"maua_style_b200 accelerates the VGG-19 / VGG-16 feature stacks only (model_file={model_file!r}); "
@@ -130,6 +127,33 @@ def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bo
     channels, layer_list = _architecture(model_file, pooling)
     sd = torch.load(resolve_model_file(model_file), map_location="cpu")
     return channels, layer_list, sd
+
+
+def padded_channels(c: int, style_tap: bool) -> int:
+    """Channel count a conv layer of `c` real channels runs with: the tcgen05 kernels tile output channels in multiples of
+    64 and the Gram SYRK takes 64 or a multiple of 128 (csrc/plan.cu).  The channel-pruned VGG-16 (models.py:136: 24, 22,
+    41, 51, 108, 89, 111, 184, 276, 228, ...) is run with zero weights / bias in the padded channels -- they stay exactly
+    zero through ReLU, pooling, Gram and every gradient -- and the plan normalises with the real count
+    (maua_net_desc::norm_channels)."""
+    cp = -(-c // 64) * 64
+    if style_tap and cp > 64 and cp % 128:
+        cp += 64
+    return cp
+
+
+def _pad_params(params, real, padded):
+    """Zero-pad [(w [c, cin, 3, 3], b [c])] to the padded channel counts (both the output and the input side)."""
+    out, cin_p = [], 3
+    for (w, b), c, cp in zip(params, real, padded):
+        if (cp, cin_p) != (w.shape[0], w.shape[1]):
+            wp = torch.zeros(cp, cin_p, *w.shape[2:], dtype=w.dtype)
+            wp[: w.shape[0], : w.shape[1]] = w
+            bp = torch.zeros(cp, dtype=b.dtype)
+            bp[: b.shape[0]] = b
+            w, b = wp, bp
+        out.append((w, b))
+        cin_p = cp
+    return out
 
 
 def _conv_params(sd, channels, disable_check):
@@ -175,7 +199,7 @@ class _PlanCore:
     SURVEY.md section 8f rank 1 asks for this to be cached.  A core is keyed by everything the plan depends on and is
     only handed to one live network at a time."""
 
-    def __init__(self, entries, params, avg_pool, tap_sig, device, bounds, devs):
+    def __init__(self, entries, params, avg_pool, tap_sig, device, bounds, devs, norm_channels=None):
         lib = _lib.load()
         self._lib = lib
         self.device = device
@@ -186,6 +210,8 @@ class _PlanCore:
         ci = 0
         for i, c in enumerate(entries):
             desc.channels[i] = c
+            if norm_channels is not None:
+                desc.norm_channels[i] = norm_channels[i]
             if c > 0:
                 desc.weights[i] = self.weights[ci].data_ptr()
                 desc.biases[i] = self.biases[ci].data_ptr()
@@ -242,7 +268,7 @@ class B200Net(nn.Module):
 
     def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device,
                  stage_bounds: Optional[List[int]] = None, devices: Optional[List[torch.device]] = None,
-                 core: Optional[_PlanCore] = None):
+                 core: Optional[_PlanCore] = None, norm_channels: Optional[List[int]] = None):
         super().__init__()
         _lib.require_gpu()
         self._lib = _lib.load()
@@ -259,7 +285,7 @@ class B200Net(nn.Module):
             raise ValueError(f"bad stage layout: bounds {bounds} for {len(devs)} device(s) and {len(entries)} entries")
         if core is None:
             tap_sig = [(ridx, _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT) for ridx, mod in taps]
-            core = _PlanCore(entries, params, avg_pool, tap_sig, device, bounds, devs)
+            core = _PlanCore(entries, params, avg_pool, tap_sig, device, bounds, devs, norm_channels)
         core.owner = weakref.ref(self)
         self._core = core
         # parameters are kept (frozen) so that net.parameters() / state inspection behave like the reference's net
@@ -278,12 +304,16 @@ class B200Net(nn.Module):
         self._coefs = self._stages[0]["coefs"]
         self._fwd_token = 0
         self.reuse_target_buffers = False  # set by optimisation loops that keep a captured graph across images
-        self._tap_channels = []
+        self._tap_channels = []   # real channel count of each tapped layer (what .target exposes)
+        self._tap_cpad = []       # channel count the plan runs it with (>= real: zero-padded, see padded_channels)
         self._tap_stage = []
         ch = [c for c in entries if c > 0]
+        real = [c for c in (norm_channels or entries) if c > 0]
+        self.real_channels = real
         conv_entry = [i for i, c in enumerate(entries) if c > 0]
         for ridx, _ in taps:
-            self._tap_channels.append(ch[ridx])
+            self._tap_channels.append(real[ridx])
+            self._tap_cpad.append(ch[ridx])
             e = conv_entry[ridx]
             self._tap_stage.append(next(k for k, st in enumerate(self._stages) if st["begin"] <= e < st["end"]))
         self.content_losses, self.style_losses, self.tv_losses, self.temporal_losses = [], [], [], []
@@ -370,6 +400,7 @@ class B200Net(nn.Module):
             io = tio[t]
             io.mode = _MODES[mod.mode]
             C_ = self._tap_channels[t]
+            Cp = self._tap_cpad[t]
             tdev = self._tap_device(t)
             if isinstance(mod, StyleLoss):
                 io.use_covariance = int(bool(mod.use_covariance))
@@ -377,17 +408,29 @@ class B200Net(nn.Module):
                 io.value_scale = float(mod.strength) * (1.0 + (vsf if vsf > 0 else 0.0))
                 if mod.mode == "capture":
                     fresh = mod.target.nelement() == 0
-                    if fresh:
+                    if fresh and Cp == C_:
                         mod.target = torch.zeros(C_, C_, device=tdev)
-                    mod.video_target = mod.target  # identical for B = 1 (loss.py:164-175)
-                    mod.loss = 0
                     io.capture_weight = float(mod.blend_weight)
                     io.capture_accumulate = 0 if fresh else 1
-                if mod.mode != "none":
+                if mod.mode != "none" and Cp != C_:
+                    buf = self._padded_style_target(mod, C_, Cp, tdev)  # mod.target is its [:C, :C] view
+                    io.target = buf.data_ptr()
+                    io.target_elems = buf.numel()
+                elif mod.mode != "none":
                     if not (mod.target.device == tdev and mod.target.dtype == torch.float32 and mod.target.is_contiguous()):
                         mod.target = mod.target.to(tdev, torch.float32).contiguous()
                     io.target = mod.target.data_ptr()
                     io.target_elems = mod.target.numel()
+                if mod.mode == "capture":
+                    mod.video_target = mod.target  # identical for B = 1 (loss.py:164-175)
+                    mod.loss = 0
+            elif Cp != C_:
+                io.value_scale = float(mod.strength)
+                h, w = self._tap_hw(H, W, ridx)
+                buf = self._padded_content_target(mod, C_, Cp, h, w, tdev, capture=mod.mode == "capture")
+                if mod.mode != "none" and buf is not None:
+                    io.target = buf.data_ptr()
+                    io.target_elems = buf.numel()
             else:
                 io.value_scale = float(mod.strength)
                 h, w = self._tap_hw(H, W, ridx)
@@ -434,6 +477,39 @@ class B200Net(nn.Module):
                         tm.weights = wts
                     iio.temporal_weights = wts.data_ptr()
         return tio, iio
+
+    # -- zero-padded layers (channel-pruned VGG-16): the plan's targets are padded buffers, `.target` is the real-size view --
+    @staticmethod
+    def _padded_style_target(mod, C_, Cp, tdev):
+        buf = getattr(mod, "_b200_target_pad", None)
+        tgt = mod.target
+        aliased = (buf is not None and tuple(buf.shape) == (Cp, Cp) and buf.device == tdev and tgt.nelement() != 0
+                   and tgt.data_ptr() == buf.data_ptr() and tuple(tgt.shape) == (C_, C_) and tgt.stride() == (Cp, 1))
+        if not aliased:
+            buf = torch.zeros(Cp, Cp, device=tdev)
+            if tgt.nelement() != 0:  # a target set from outside (or moved): adopt its values
+                buf[:C_, :C_] = tgt.to(tdev, torch.float32)
+            mod._b200_target_pad = buf
+            mod.target = buf[:C_, :C_]
+        return buf
+
+    def _padded_content_target(self, mod, C_, Cp, h, w, tdev, capture):
+        buf = getattr(mod, "_b200_target_pad", None)
+        tgt = mod.target
+        aliased = (buf is not None and tuple(buf.shape) == (1, h, w, Cp) and buf.device == tdev and tgt.nelement() != 0
+                   and tgt.data_ptr() == buf.data_ptr() and tuple(tgt.shape) == (1, C_, h, w))
+        if aliased and (not capture or self.reuse_target_buffers):
+            return buf
+        if capture:
+            buf = torch.zeros(1, h, w, Cp, device=tdev)
+        elif tgt.nelement() != 0 and tuple(tgt.shape[1:]) == (C_, h, w):
+            buf = torch.zeros(1, h, w, Cp, device=tdev)
+            buf[..., :C_] = tgt.to(tdev, torch.float32).permute(0, 2, 3, 1)
+        else:
+            return None  # no target yet, or a shape mismatch: the module is skipped (loss.py:44)
+        mod._b200_target_pad = buf
+        mod.target = buf.permute(0, 3, 1, 2)[:, :C_]
+        return buf
 
     def io_signature(self, H: int, W: int) -> bytes:
         """Everything a captured iteration bakes into its kernel arguments besides the pastiche: extents, module modes,
@@ -599,7 +675,7 @@ class B200Net(nn.Module):
             out = torch.empty(1, h.value, w.value, c.value, device=st["device"])
             _lib.check(self._lib.maua_plan_tap_feature(st["plan"], t, _lib.ptr(out), C.byref(h), C.byref(w), C.byref(c),
                                                        _lib.stream_ptr()))
-        return out.permute(0, 3, 1, 2).contiguous()
+        return out.permute(0, 3, 1, 2)[:, : self._tap_channels[t]].contiguous()
 
     def entry_output(self, i: int) -> torch.Tensor:
         """Output of stack entry i (conv: post-ReLU activation, pool: pooled map) from the last forward, NCHW (copy)."""
@@ -622,7 +698,7 @@ class B200Net(nn.Module):
             _lib.check(self._lib.maua_plan_tap_gram(st["plan"], t, C.c_void_p(0), C.byref(c), _lib.stream_ptr()))
             out = torch.empty(c.value, c.value, device=st["device"])
             _lib.check(self._lib.maua_plan_tap_gram(st["plan"], t, _lib.ptr(out), C.byref(c), _lib.stream_ptr()))
-        return out
+        return out[: self._tap_channels[t], : self._tap_channels[t]].contiguous()
 
 
 def _device_from_args(args) -> torch.device:
@@ -633,7 +709,7 @@ def _device_from_args(args) -> torch.device:
 
 
 def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stage_bounds=None, devices=None,
-              model_path=None) -> "B200Net":
+              model_path=None, norm_channels=None) -> "B200Net":
     """A B200Net on a cached plan core when one exists for (checkpoint file, layer layout, taps, pooling, devices) and no
     live network is using it; otherwise on a new core built from `params_fn()` (which reads the checkpoint)."""
     bounds = list(stage_bounds) if stage_bounds else [0, len(entries)]
@@ -645,8 +721,8 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
         try:
             model_path = model_path or resolve_model_file(str(args.model_file))
             st = os.stat(model_path)
-            key = (os.path.realpath(model_path), st.st_mtime_ns, st.st_size, avg, tuple(entries), tap_sig,
-                   tuple(bounds), tuple(str(d) for d in devs))
+            key = (os.path.realpath(model_path), st.st_mtime_ns, st.st_size, avg, tuple(entries), tuple(norm_channels or ()),
+                   tap_sig, tuple(bounds), tuple(str(d) for d in devs))
         except (OSError, ValueError):
             key = None
     core = _CORE_CACHE.get(key) if key is not None else None
@@ -656,7 +732,7 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
     if core is None:
         cache_stats["misses"] += 1
         _lib.require_gpu()
-        core = _PlanCore(entries, params_fn(), avg, list(tap_sig), device, bounds, devs)
+        core = _PlanCore(entries, params_fn(), avg, list(tap_sig), device, bounds, devs, norm_channels)
         if key is not None:
             _CORE_CACHE[key] = core
             while len(_CORE_CACHE) > _CORE_CACHE_MAX:
@@ -664,7 +740,8 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
     else:
         cache_stats["hits"] += 1
         _CORE_CACHE.move_to_end(key)
-    return B200Net(entries, None, avg, taps, tv_mod, temporal_mod, device, stage_bounds=bounds, devices=devs, core=core)
+    return B200Net(entries, None, avg, taps, tv_mod, temporal_mod, device, stage_bounds=bounds, devices=devs, core=core,
+                   norm_channels=norm_channels)
 
 
 def load_model(args):
@@ -730,19 +807,31 @@ def load_model(args):
         entries.pop()  # a trailing pool feeds nothing
 
     n_convs = conv_i
+    # layers whose channel counts the tcgen05 kernels do not tile (channel-pruned VGG-16) run zero-padded
+    style_relu = {ridx for ridx, mod in taps if isinstance(mod, StyleLoss)}
+    real, padded, k = [c for c in entries if c > 0], [], 0
+    for c in real:
+        padded.append(padded_channels(c, k in style_relu))
+        k += 1
+    norm_channels = None
+    if padded != real:
+        it = iter(padded)
+        norm_channels = list(entries)
+        entries = [next(it) if c > 0 else 0 for c in entries]
 
     def params():
         """The checkpoint's conv weights up to the last tapped layer -- only read when no cached core exists."""
         sd = torch.load(model_path, map_location="cpu")  # models.py:343
-        return _conv_params(sd, channels, getattr(args, "disable_check", False))[:n_convs]
+        raw = _conv_params(sd, channels, getattr(args, "disable_check", False))[:n_convs]
+        return _pad_params(raw, real, padded) if norm_channels is not None else raw
 
     if getattr(args, "multidevice", False):
         from .parallel import setup_multi_device  # layer-wise split over NVLink peers (models.py:537-566)
 
         return setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses,
-                                  tv_losses, temporal_losses)
+                                  tv_losses, temporal_losses, norm_channels=norm_channels)
 
-    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device, model_path=model_path)
+    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device, model_path=model_path, norm_channels=norm_channels)
     net.content_losses = content_losses
     net.style_losses = style_losses
     net.tv_losses = tv_losses

@@ -64,7 +64,7 @@ def stage_bounds(entries: List[int], strategy: str, n_devices: int, taps, has_tv
 
 
 def setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses, tv_losses,
-                       temporal_losses):
+                       temporal_losses, norm_channels=None):
     """models.py:537-566 + :440-441: returns (net, losses) with `net` spanning the devices of `--gpu`."""
     from .models import build_net
 
@@ -81,7 +81,8 @@ def setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, conten
     if getattr(args, "verbose", False):
         for k, d in enumerate(devices):
             print(f"device {d}: entries [{bounds[k]}, {bounds[k + 1]})")
-    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, devices[0], stage_bounds=bounds, devices=devices)
+    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, devices[0], stage_bounds=bounds, devices=devices,
+                    norm_channels=norm_channels)
     net.content_losses = content_losses
     net.style_losses = style_losses
     net.tv_losses = tv_losses

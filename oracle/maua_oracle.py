@@ -43,6 +43,8 @@ VGG19_RELU_NAMES = ["relu1_1", "relu1_2", "relu2_1", "relu2_2", "relu3_1", "relu
                     "relu4_1", "relu4_2", "relu4_3", "relu4_4", "relu5_1", "relu5_2", "relu5_3", "relu5_4"]
 # models.py:137 and :140-203 (VGG-16: three convs in blocks 3-5)
 VGG16_CHANNELS = [64, 64, "P", 128, 128, "P", 256, 256, 256, "P", 512, 512, 512, "P", 512, 512, 512, "P"]
+# models.py:136 (channel-pruned VGG-16, `--model_file *prun*`, models.py:249-258; layer names = vgg16_dict)
+VGG16P_CHANNELS = [24, 22, "P", 41, 51, "P", 108, 89, 111, "P", 184, 276, 228, "P", 512, 512, 512, "P"]
 
 
 def relu_names(channels) -> List[str]:

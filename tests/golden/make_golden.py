@@ -64,7 +64,7 @@ def reference_args(rconfig, workdir: Path, ckpt: Path, **over):
 
 
 def save_checkpoint(rmodels, path: Path, seed: int = 0, arch: str = "VGG-19"):
-    channels = O.VGG19_CHANNELS if arch == "VGG-19" else O.VGG16_CHANNELS
+    channels = {"VGG-19": O.VGG19_CHANNELS, "VGG-16": O.VGG16_CHANNELS, "VGG-16p": O.VGG16P_CHANNELS}[arch]
     params = O.he_init_vgg19(seed, channels)
     seq = rmodels.build_sequential(rmodels.channel_list[arch], "max")
     sd = seq.state_dict()

@@ -11,6 +11,9 @@ CPU (same recipe as make_golden.py, whose helpers this script re-uses):
                                  layer past relu5_1, average pooling, 3 Adam iterations
   vgg19_same_layer_taps_64x64 .. ContentLoss and StyleLoss on the same ReLU (relu4_2; models.py:411-431 inserts the content
                                  module first)
+  vgg16p_adam_gram_72x88 ....... `--model_file *prun*` (models.py:249-258: the channel-pruned VGG-16, channel list "VGG-16p" =
+                                 24, 22, 41, 51, 108, 89, 111, 184, 276, 228, 512...), default layers, 3 Adam iterations
+  vgg16p_cov_lbfgs_64x80 ....... the same stack with the covariance loss, 2 blended styles, 4 L-BFGS iterations
   vgg19_taps_lbfgs_80x64 ....... VGG-19 with `--style_layers relu1_2,relu3_3 --content_layers relu2_2`: taps that sit
                                  directly before a pool, truncation after relu3_3 (models.py:382), 4 L-BFGS iterations
 """
@@ -29,10 +32,23 @@ O = mg.O
 
 
 def main():
+    only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     rconfig, rloss, rmodels, roptim = mg.import_reference()
+    run = mg.run_case
+    if only:
+        mg.run_case = lambda name, **kw: run(name, **kw) if name in only else None
     with tempfile.TemporaryDirectory() as td:
         workdir = Path(td)
         os.chdir(workdir)
+        ckpt16p = workdir / "vgg16-prune-random.pth"
+        mg.save_checkpoint(rmodels, ckpt16p, arch="VGG-16p")
+        names16 = O.relu_names(O.VGG16P_CHANNELS)
+        pre = dict(rconfig=rconfig, rmodels=rmodels, roptim=roptim, workdir=workdir)
+        mg.run_case("vgg16p_adam_gram_72x88", ckpt=ckpt16p, h=72, w=88, style_hw=[(64, 96)], iters=3, relu_names=names16,
+                    meta_extra={"arch": "VGG-16p"}, **pre)
+        mg.run_case("vgg16p_cov_lbfgs_64x80", ckpt=ckpt16p, h=64, w=80, style_hw=[(72, 72), (56, 96)], iters=4,
+                    optimizer="lbfgs", use_covariance=True, style_blend_weights="3,1", relu_names=names16,
+                    meta_extra={"arch": "VGG-16p"}, **pre)
         ckpt16 = workdir / "vgg16-random.pth"
         mg.save_checkpoint(rmodels, ckpt16, arch="VGG-16")
         common = dict(rconfig=rconfig, rmodels=rmodels, roptim=roptim, workdir=workdir)

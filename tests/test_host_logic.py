@@ -12,15 +12,25 @@ from maua_style_b200 import models, optim
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def test_vgg16_family_names_and_pruned_model_is_rejected():
-    """models.py:246-347: fcn32s / sod / nyud checkpoints are VGG-16 stacks; the channel-pruned VGG-16 has channel counts
-    that are not multiples of 32 and is refused loudly instead of silently computing something else."""
+def test_vgg16_family_names_and_pruned_model():
+    """models.py:246-347: fcn32s / sod / nyud checkpoints are VGG-16 stacks; "prun" selects the channel-pruned VGG-16
+    (channel list "VGG-16p", vgg16_dict names), which runs zero-padded to channel counts the kernels tile."""
     for nm in ("vgg16-sod.pth", "fcn32s-heavy-pascal.pth", "modelzoo/nyud-fcn32s-color-heavy.pth", "vgg16-00b39a1b.pth"):
         ch, names = models._architecture(nm, "max")
         assert ch == models.channel_list["VGG-16"] and names["R"][7] == "relu4_1"
     assert models._architecture("modelzoo/vgg19-d01eb7cb.pth", "avg")[0] == models.channel_list["VGG-19"]
     assert models._architecture("/tmp/episode-3/vgg19-random.pth", "max")[0] == models.channel_list["VGG-19"]
-    for bad in ("modelzoo/vgg16-prune.pth", "modelzoo/nin.pth", "resnet50.pth"):
+    ch, names = models._architecture("modelzoo/vgg16-prune.pth", "max")
+    assert ch == models.channel_list["VGG-16p"] and ch[:2] == [24, 22] and names is models.vgg16_dict
+    # padded counts: multiples of 64; 64 or a multiple of 128 under a style tap
+    assert [models.padded_channels(c, False) for c in (24, 41, 108, 184, 276, 228, 512)] == [64, 64, 128, 192, 320, 256, 512]
+    assert [models.padded_channels(c, True) for c in (24, 41, 108, 184, 276)] == [64, 64, 128, 256, 384]
+    import torch
+    raw = [(torch.ones(24, 3, 3, 3), torch.ones(24)), (torch.ones(22, 24, 3, 3), torch.ones(22))]
+    (w0, b0), (w1, b1) = models._pad_params(raw, [24, 22], [64, 64])
+    assert w0.shape == (64, 3, 3, 3) and w1.shape == (64, 64, 3, 3) and float(w1.sum()) == 22 * 24 * 9 and float(b1[22:].abs().sum()) == 0
+    assert float(w1[:, 24:].abs().sum()) == 0 and float(w0[24:].abs().sum()) == 0
+    for bad in ("modelzoo/nin.pth", "resnet50.pth"):
         with pytest.raises(ValueError):
             models._architecture(bad, "max")
     with pytest.raises(ValueError):

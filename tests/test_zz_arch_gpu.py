@@ -2,6 +2,10 @@
 the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
 
   vgg16_adam_gram_72x88 ...... `--model_file *vgg16*`: the VGG-16 channel list and layer names (models.py:137, :140-203)
+  vgg16p_adam_gram_72x88 ..... `--model_file *prun*`: the channel-pruned VGG-16 (models.py:136, :249-258; 24, 22, 41, 51, 108,
+                               89, 111, 184, 276, 228, 512 channels), run zero-padded to tileable channel counts with the
+                               loss normalisations on the real counts (models.padded_channels, maua_net_desc::norm_channels)
+  vgg16p_cov_lbfgs_64x80 ..... the same stack with the covariance loss, two blended styles, L-BFGS
   vid_frame_temporal_64x80 ... one vid_img frame (style.py:276-294): optim.set_temporal_targets with a flow-reliability map,
                                then optimize(content, styles, init, n, args, net, losses) -- the weighted temporal
                                ContentLoss on the image (loss.py:46-54) pinned to the reference's own numbers
@@ -19,7 +23,7 @@ from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoi
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96",
+CASES = ["vgg16_adam_gram_72x88", "vgg16p_adam_gram_72x88", "vgg16p_cov_lbfgs_64x80", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96",
          "vgg19_same_layer_taps_64x64"]
 
 
@@ -29,6 +33,8 @@ CASES = ["vgg16_adam_gram_72x88", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_
 # (DESIGN.md section 2), so the step lengths of iterations 2-4 differ visibly between any two arithmetics.
 BOUNDS = {
     "vgg16_adam_gram_72x88": (5e-2, 40.0),        # 3.0e-2, 56.0 dB
+    "vgg16p_adam_gram_72x88": (5e-2, 40.0),       # measured on B200: see profiles/r02_f4_parity.txt
+    "vgg16p_cov_lbfgs_64x80": (5e-2, 20.0),       # 4 L-BFGS iterations: same sensitivity as vgg19_taps_lbfgs_80x64
     "vid_frame_temporal_64x80": (4e-2, 40.0),     # 2.2e-2, 56.1 dB
     "vgg19_taps_lbfgs_80x64": (4e-2, 20.0),       # 2.5e-2, 34.7 dB (fp32 leaps by 7.5 grey levels rms in iteration 3, the
                                                   # TF32 arithmetic crawls by 3.1: the two can differ by at most ~24 dB)
@@ -50,9 +56,9 @@ def setup_case(name, tmp_path):
     from maua_style_b200 import models
 
     z, meta = load_golden(name)
-    vgg16 = meta.get("arch") == "VGG-16"
-    channels = O.VGG16_CHANNELS if vgg16 else O.VGG19_CHANNELS
-    path = tmp_path / ("vgg16-random.pth" if vgg16 else "vgg19-random.pth")
+    arch = meta.get("arch", "VGG-19")
+    channels = {"VGG-19": O.VGG19_CHANNELS, "VGG-16": O.VGG16_CHANNELS, "VGG-16p": O.VGG16P_CHANNELS}[arch]
+    path = tmp_path / {"VGG-19": "vgg19-random.pth", "VGG-16": "vgg16-random.pth", "VGG-16p": "vgg16-prune-random.pth"}[arch]
     params = save_checkpoint(path, channels=channels)
     over = dict(meta["over"])
     args = make_args(path, tmp_path, **over)
@@ -60,6 +66,8 @@ def setup_case(name, tmp_path):
     cfg = O.StyleConfig(content_weight=5.0)
     cfg.optimizer = over.pop("optimizer", "adam")
     for k, v in over.items():
+        if k == "style_blend_weights" and isinstance(v, str):
+            v = [float(x) for x in v.split(",")]  # config.py:146-164 parses the CLI string
         setattr(cfg, k, v)
     return z, meta, args, net, losses, params, cfg, channels
 
