@@ -252,8 +252,8 @@ typedef struct maua_net_desc {
     int tap_kind[MAUA_MAX_TAPS];        /* maua_tap_kind; taps must be ordered by relu index (content before style
                                            at the same index, as models.py:411-431 inserts them) */
     /* Channel-pruned VGG-16 (models.py:136 "VGG-16p": 24, 22, 41, 51, 108, 89, 111, 184, 276, 228, 512...): the caller
-     * zero-pads every conv's weights / bias to a channel count the tcgen05 kernels tile (multiples of 64; 64 or a
-     * multiple of 128 under a style tap) and names the REAL count here; the Gram 1/(C*H*W), the nn.MSELoss means and the
+     * zero-pads every conv's weights / bias to a channel count the tcgen05 kernels tile (multiples of 64) and names the
+     * REAL count here; the Gram 1/(C*H*W), the nn.MSELoss means and the
      * gradient scales use it, so padded and unpadded networks give the same losses and gradients.  0 = channels[i]. */
     int norm_channels[MAUA_MAX_LAYERS];
 } maua_net_desc;

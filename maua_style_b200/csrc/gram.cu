@@ -79,7 +79,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
     const bool diag = (ti == tj);
     const int m0 = ti * 128, n0 = tj * 128;
     const int boxesA = min(4, (p.C - m0) / 32);
-    const int boxesB = diag ? 0 : BN / 32;
+    const int boxesB = diag ? 0 : min(BN / 32, (p.C - n0) / 32);
 
     const long total_st = (p.P + GK - 1) / GK;
     const long st0 = total_st * blockIdx.y / p.nsplit;
@@ -161,14 +161,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmF, const GramParams p) {
                         for (int i = 0; i < 16; ++i) v[i] += u[i];
                     }
                 }
-                if (c < p.C) {
+                if (c < p.C && n0 + col < p.C) {  // (C % 128 == 64: the last tile row / column is half a tile)
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         *reinterpret_cast<float4*>(dst + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }
             }
         } else if (c < p.C) {
-            for (int col = 0; col < BN; col += 4) *reinterpret_cast<float4*>(dst + col) = make_float4(0, 0, 0, 0);
+            for (int col = 0; col < BN && n0 + col < p.C; col += 4) *reinterpret_cast<float4*>(dst + col) = make_float4(0, 0, 0, 0);
         }
     }
     tc_fence_before();
@@ -352,20 +352,26 @@ int launch_gram_tc(const CUtensorMap& tm, const GramParams& p, int ntiles, cudaS
 
 }  // namespace
 
-size_t gram_workspace_bytes(int C) {
-    // [kMaxSplit-bounded partials][C][C] floats + channel-mean scratch (doubles)
+// [C][C] float slots of the partial area: the split-K partials of the tensor-core path (kMaxSplit / ntiles of them), and at
+// least 3 so that the exact-arithmetic path always has room for one fp64 partial (2 slots) + the fp32 sums (1 slot)
+static int gram_slots(int C) {
     const int T = (C + 127) / 128;
     const int ntiles = T * (T + 1) / 2;
-    const int nsplit = kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1;
-    return (size_t)nsplit * C * C * sizeof(float) + (size_t)kMaxSplit * 4 * C * sizeof(double) + 1024;
+    const int s = kMaxSplit / ntiles;
+    return s > 3 ? s : 3;
+}
+
+size_t gram_workspace_bytes(int C) {
+    // [slots][C][C] floats + channel-mean scratch (doubles)
+    return (((size_t)gram_slots(C) * C * C * sizeof(float) + 255) & ~size_t(255)) + (size_t)kMaxSplit * 4 * C * sizeof(double) + 1024;
 }
 
 int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* mean_out, void* workspace, int impl,
                 cudaStream_t st, const GramLossFuse* fuse, int Cn) {
     if (Cn <= 0) Cn = C;
     // (the [B*C, B*C] dynamic Gram of an img_vid window, loss.py:164-168, is this kernel on the B*C-channel matrix)
-    MAUA_REQUIRE(C >= 64 && (C == 64 || C % 128 == 0) && C <= 16384,
-                 "gram: channel count %d unsupported (need 64 or a multiple of 128, <= 16384)", C);
+    MAUA_REQUIRE(C >= 64 && C % 64 == 0 && C <= 16384,
+                 "gram: channel count %d unsupported (need a multiple of 64, <= 16384)", C);
     MAUA_REQUIRE(P >= 1 && P < (1L << 31), "gram: bad pixel count %ld", P);
     const int T = (C + 127) / 128;
     const int ntiles = T * (T + 1) / 2;
@@ -374,8 +380,7 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
     if (nsplit > total_st) nsplit = (int)total_st;
     float* partial = reinterpret_cast<float*>(workspace);
     double* mean_scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
-                                                     (((size_t)(kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1) * C * C *
-                                                       sizeof(float) + 255) & ~size_t(255)));
+                                                     (((size_t)gram_slots(C) * C * C * sizeof(float) + 255) & ~size_t(255)));
     if (use_cov) {
         int rc = channel_mean_launch(f, P, C, mean_out, mean_scratch, kMaxSplit * 4, st);
         if (rc) return rc;
@@ -384,8 +389,7 @@ int gram_launch(const float* f, long P, int C, int use_cov, float* gram, float* 
     bool centred = false;
     if (impl == 4) {
         // workspace: fp64 partials in the first float slots, the fp32 sums in the last float slot of the partial area
-        const int slots = kMaxSplit / ntiles > 0 ? kMaxSplit / ntiles : 1;
-        MAUA_REQUIRE(slots >= 3, "gram (exact mode): channel count %d leaves no room for fp64 partials", C);
+        const int slots = gram_slots(C);
         int S = (slots - 1) / 2;
         if ((long)S > (P + 255) / 256) S = (int)((P + 255) / 256);
         double* dpartial = reinterpret_cast<double*>(workspace);

@@ -388,7 +388,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
             tp.C = p->entries[tp.entry].cout;
             tp.Cn = p->entries[tp.entry].Cn;
             if (tp.kind == MAUA_TAP_STYLE) {
-                if (!(tp.C == 64 || tp.C % 128 == 0)) {
+                if (tp.C % 64 != 0) {
                     set_last_error("style tap on %d channels unsupported", tp.C);
                     ok = false;
                     break;

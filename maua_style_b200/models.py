@@ -130,15 +130,12 @@ def select_model(model_file: str, pooling: str, verbose: bool, disable_check: bo
 
 
 def padded_channels(c: int, style_tap: bool) -> int:
-    """Channel count a conv layer of `c` real channels runs with: the tcgen05 kernels tile output channels in multiples of
-    64 and the Gram SYRK takes 64 or a multiple of 128 (csrc/plan.cu).  The channel-pruned VGG-16 (models.py:136: 24, 22,
+    """Channel count a conv layer of `c` real channels runs with: the tcgen05 conv and Gram kernels tile channels in
+    multiples of 64 (csrc/plan.cu).  The channel-pruned VGG-16 (models.py:136: 24, 22,
     41, 51, 108, 89, 111, 184, 276, 228, ...) is run with zero weights / bias in the padded channels -- they stay exactly
     zero through ReLU, pooling, Gram and every gradient -- and the plan normalises with the real count
     (maua_net_desc::norm_channels)."""
-    cp = -(-c // 64) * 64
-    if style_tap and cp > 64 and cp % 128:
-        cp += 64
-    return cp
+    return -(-c // 64) * 64
 
 
 def _pad_params(params, real, padded):
@@ -203,6 +200,9 @@ class _PlanCore:
         lib = _lib.load()
         self._lib = lib
         self.device = device
+        # kept so that sibling cores can be built for the frames of an img_vid window (window.py)
+        self.entries, self.avg_pool, self.tap_sig, self.bounds, self.devs = list(entries), avg_pool, list(tap_sig), list(bounds), list(devs)
+        self.norm_channels = list(norm_channels) if norm_channels is not None else None
         self.weights = nn.ParameterList([nn.Parameter(w.to(device).contiguous(), requires_grad=False) for w, _ in params])
         self.biases = nn.ParameterList([nn.Parameter(b.to(device).contiguous(), requires_grad=False) for _, b in params])
         desc = _lib.NetDesc()
@@ -300,6 +300,9 @@ class B200Net(nn.Module):
             _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(os.environ.get("MAUA_FUSE_POOL", "1") != "0")),
                        "maua_plan_set_fuse_pool")
         self._plan = self._stages[0]["plan"]
+        self._impl = default_impl()
+        self._window = None       # FrameWindow (window.py): evaluation of [B > 1, 3, H, W] inputs (img_vid)
+        self._window_live = False
         self._loss_vec = torch.zeros(self._n_slots, device=device)
         self._coefs = self._stages[0]["coefs"]
         self._fwd_token = 0
@@ -334,6 +337,7 @@ class B200Net(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     def set_impl(self, impl: int):
+        self._impl = impl
         for st in self._stages:
             _lib.check(self._lib.maua_plan_set_impl(st["plan"], impl), "maua_plan_set_impl")
 
@@ -392,7 +396,7 @@ class B200Net(nn.Module):
                     return h, w
         raise AssertionError
 
-    def _build_io(self, H: int, W: int):
+    def _build_io(self, H: int, W: int, window: bool = False):
         """The per-forward description of every loss module for the plan (maua_tap_io / maua_image_io): modes, strengths,
         target buffers.  Capture-mode modules get their target buffers here (loss.py:61-62, :146-151)."""
         tio = (_lib.TapIO * max(len(self.taps), 1))()
@@ -404,9 +408,9 @@ class B200Net(nn.Module):
             tdev = self._tap_device(t)
             if isinstance(mod, StyleLoss):
                 io.use_covariance = int(bool(mod.use_covariance))
-                vsf = float(mod.video_style_factor)
-                io.value_scale = float(mod.strength) * (1.0 + (vsf if vsf > 0 else 0.0))
-                if mod.mode == "capture":
+                vsf = self._effective_vsf(mod, C_)
+                io.value_scale = float(mod.strength) * (1.0 + vsf)
+                if mod.mode == "capture" and not window:  # (a window of B > 1 frames manages its captures itself)
                     fresh = mod.target.nelement() == 0
                     if fresh and Cp == C_:
                         mod.target = torch.zeros(C_, C_, device=tdev)
@@ -421,8 +425,9 @@ class B200Net(nn.Module):
                         mod.target = mod.target.to(tdev, torch.float32).contiguous()
                     io.target = mod.target.data_ptr()
                     io.target_elems = mod.target.numel()
-                if mod.mode == "capture":
-                    mod.video_target = mod.target  # identical for B = 1 (loss.py:164-175)
+                if mod.mode == "capture" and not window:
+                    if not self._dynamic_skipped(mod, C_):
+                        mod.video_target = mod.target  # identical for B = 1 (loss.py:164-175)
                     mod.loss = 0
             elif Cp != C_:
                 io.value_scale = float(mod.strength)
@@ -511,6 +516,17 @@ class B200Net(nn.Module):
         mod.target = buf.permute(0, 3, 1, 2)[:, :C_]
         return buf
 
+    @staticmethod
+    def _dynamic_skipped(mod, C_) -> bool:
+        """loss.py:165-166: a video target captured from windows of B > 1 frames is [B*C, B*C]; a single image then has no
+        dynamic term (neither captured nor evaluated)."""
+        vt = mod.video_target
+        return vt.nelement() != 0 and vt.shape[0] != C_
+
+    def _effective_vsf(self, mod, C_) -> float:
+        vsf = float(mod.video_style_factor)
+        return vsf if vsf > 0 and not self._dynamic_skipped(mod, C_) else 0.0
+
     def io_signature(self, H: int, W: int) -> bytes:
         """Everything a captured iteration bakes into its kernel arguments besides the pastiche: extents, module modes,
         strengths and target addresses.  Two iterations with equal signatures launch identical kernels."""
@@ -519,11 +535,20 @@ class B200Net(nn.Module):
 
     def _forward_plan(self, x: torch.Tensor, keep: bool) -> int:
         if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError(f"expected a [1,3,H,W] image, got {tuple(x.shape)}")
-        if x.shape[0] != 1:
-            raise NotImplementedError("maua_style_b200 supports batch size 1 only (img_vid windows are out of scope)")
+            raise ValueError(f"expected a [B,3,H,W] image batch, got {tuple(x.shape)}")
         if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
             raise ValueError("internal: image must be a contiguous fp32 CUDA tensor")
+        self._window_live = x.shape[0] != 1
+        if self._window_live:
+            # a window of B > 1 frames (img_vid: loss.py:141-181 batch semantics): one plan per frame + one SYRK over all
+            if self._window is None:
+                from .window import FrameWindow
+
+                self._window = FrameWindow(self)
+            self._keepalive = (x, None, None)
+            self._window.forward(x, keep)
+            self._fwd_token += 1
+            return self._fwd_token
         H, W = int(x.shape[2]), int(x.shape[3])
         tio, iio = self._build_io(H, W)
         self._keepalive = (x, tio, iio)
@@ -578,6 +603,8 @@ class B200Net(nn.Module):
 
     def _backward_plan(self, grad_losses: torch.Tensor) -> torch.Tensor:
         x = self._keepalive[0]
+        if self._window_live:
+            return self._window.backward(grad_losses, x)
         n = self._n_slots
         strength = (C.c_float * n)()
         vsf = (C.c_float * n)()
@@ -588,7 +615,7 @@ class B200Net(nn.Module):
                 continue
             strength[i] = float(mod.strength)
             if isinstance(mod, StyleLoss):
-                kind[i], vsf[i], normalize[i] = 0, float(mod.video_style_factor), int(bool(mod.normalize))
+                kind[i], vsf[i], normalize[i] = 0, self._effective_vsf(mod, self._tap_channels[i]), int(bool(mod.normalize))
             elif isinstance(mod, ContentLoss):
                 kind[i], normalize[i] = 1, int(bool(mod.normalize))
             else:

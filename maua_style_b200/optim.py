@@ -82,6 +82,38 @@ def set_style_targets(net, style_images, args):
     net._style_cache = (sig, list(style_images))
 
 
+def set_style_video_targets(net, style_videos, args):
+    """optim.py:69-90 (img_vid): every style video is averaged over all of its windows of `gram_frame_window` frames; a
+    forward over a window of B frames captures the per-frame static Grams and the [B*C, B*C] dynamic Gram (window.py)."""
+    gfw = int(args.gram_frame_window)
+    for j in net.style_losses:
+        j.reset_targets()
+        j.mode = "capture"
+    for i, video in enumerate(style_videos):
+        n_win = max(len(video) - gfw + 1, 1)
+        for j in net.style_losses:
+            j.blend_weight = args.style_blend_weights[i] / n_win
+        for window_start in range(n_win):
+            net(video[window_start:window_start + gfw])
+    for j in net.style_losses:
+        j.mode = "none"
+    net._style_cache = None  # (the image-style target cache of set_style_targets does not describe these targets)
+
+
+def wrapping_slice(tensor, start, length, return_indices=False):
+    """utils.py:76-85: `length` consecutive frames from `start`, wrapping around the end; a 1-frame tensor gives frame 0."""
+    n = tensor.shape[0]
+    if start + length <= n:
+        indices = torch.arange(start, start + length)
+    else:
+        indices = torch.cat((torch.arange(start, n), torch.arange(0, (start + length) % n)))
+    if n == 1:
+        indices = torch.zeros(1, dtype=torch.int64)
+    if return_indices:
+        return indices
+    return tensor[indices.to(tensor.device)]
+
+
 def set_model_args(args, current_size):
     """optim.py:93-108."""
     with open(args.scaling_args, "r") as f:
@@ -99,6 +131,14 @@ def set_model_args(args, current_size):
         print("Warning: no model configuration found for this size, out of memory error is likely...")
     for key, param in params.items():
         args.__dict__[key] = param
+
+
+def lbfgs_updates(num_iters: int) -> int:
+    """Parameter updates of ONE torch.optim.LBFGS.step() with max_iter = num_iters as optim.py:180-191 constructs it: the
+    loop also stops after max_eval = max_iter * 5 // 4 closure evaluations (torch's default, not overridden by the
+    reference) -- one evaluation before the loop and one per update -- so 2 / 3 iterations give 1 / 2 updates and every
+    other count gives num_iters."""
+    return min(num_iters, max(num_iters * 5 // 4 - 1, 1))
 
 
 class PixelOptimizer:
@@ -177,6 +217,7 @@ class GraphedIteration:
         self.graph = None
         self.signature = None
         self.eager_calls = 0
+        self.zero_frames = None
         self.enabled = net.n_stages == 1 and os.environ.get("MAUA_NO_GRAPH", "0") != "1"
         self.warmup = warmup  # eager iterations first: workspaces get sized, the L-BFGS "first call" path is taken eagerly
 
@@ -193,6 +234,12 @@ class GraphedIteration:
     def _eager(self):
         self.net._forward_plan(self.pastiche, keep=True)
         grad = self.net._backward_plan(self.up)
+        if self.zero_frames is not None:
+            # optim.py:216-219 (img_vid): frames already styled by the previous window get no gradient
+            front, end = self.zero_frames
+            grad[:front] = 0
+            if end > 0:
+                grad[-end:] = 0
         self.opt.step(grad)
 
     def __call__(self):
@@ -309,8 +356,7 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
     """`optimize` without the final device->host copy: the result stays in HBM for the next scale / frame
     (maua_style_b200/style.py keeps the whole multi-resolution schedule on the device)."""
     if "_vid" in getattr(args, "transfer_type", "img_img"):
-        raise NotImplementedError("img_vid (windowed video-style) optimisation is out of scope for the B200 backend "
-                                  "(SURVEY.md section 8f rank 4); use the reference's torch path")
+        return _optimize_windows(content, styles, init, num_iters, args, net, losses)
     if net is None or losses is None:
         set_model_args(args, max(*init.shape))
         net, losses = models.load_model(args)
@@ -338,7 +384,7 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
         if float(getattr(args, "lbfgs_tolerance_grad", -1)) >= 0:
             raise NotImplementedError("maua_style_b200: lbfgs_tolerance_grad >= 0 is not supported (the reference always "
                                       "passes -1, optim.py:184); use the default")
-        evals = num_iters  # one step() = num_iters closure evaluations and updates
+        evals = lbfgs_updates(num_iters)  # one step() = num_iters closure evaluations and updates
     elif args.optimizer == "adam":
         evals = num_iters + 1  # optim.py:240 `while i[0] <= iters`
     else:
@@ -367,6 +413,72 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
         return pastiche.clone()  # the buffer belongs to the cached loop state and is overwritten by the next call
     opt.close()
     return pastiche
+
+
+def _optimize_windows(content, styles, init, num_iters, args, net=None, losses=None):
+    """optim.py:113-125, :149-170, :216-219, :242-247 -- transfer type img_vid: the pastiche is a video [T, 3, H, W] optimised
+    in overlapping windows of `gram_frame_window` frames (a batch of B frames through the network, window.py); window
+    starts are spread evenly over the pastiche and over every style video; frames a previous window already styled get
+    no gradient; every window starts a fresh optimizer."""
+    gfw = int(args.gram_frame_window)
+    afw = int(getattr(args, "avg_frame_window", -1))
+    clips = [init] + list(styles)
+    num_windows = math.ceil(init.shape[0] / gfw)
+    framestep = [(c.shape[0] - gfw / 2) / num_windows for c in clips]
+    windows = [[math.ceil(framestep[idx] * n) for n in range(num_windows + 1)] if clips[idx].shape[0] != 1
+               else [0] * (num_windows + 1) for idx in range(len(clips))]
+    if net is None or losses is None:
+        set_model_args(args, max(*init.shape))
+        net, losses = models.load_model(args)
+    device = net.device
+    if args.optimizer == "lbfgs":
+        if float(getattr(args, "lbfgs_tolerance_grad", -1)) >= 0:
+            raise NotImplementedError("maua_style_b200: lbfgs_tolerance_grad >= 0 is not supported")
+        evals = lbfgs_updates(num_iters)
+    elif args.optimizer == "adam":
+        evals = num_iters + 1
+    else:
+        raise ValueError(f"unknown optimizer {args.optimizer!r}")
+
+    set_content_targets(net, content.to(device, torch.float32), args)
+    styles_dev = [s.to(device, torch.float32) for s in styles]
+    if afw == -1:
+        set_style_video_targets(net, styles_dev, args)
+        for mod in losses:
+            mod.mode = "loss"
+    output = init.detach().to(device, torch.float32).clone()
+    T = output.shape[0]
+    for w, window_start in enumerate(windows[0]):
+        front_overlap = windows[0][w - 1] + gfw - window_start
+        end_overlap = (window_start + gfw) % T if window_start + gfw >= T else 0
+        indices = wrapping_slice(output, window_start, gfw, return_indices=True).to(device)
+        if afw != -1:
+            current_styles = [wrapping_slice(style, windows[num + 1][w], afw) for num, style in enumerate(styles_dev)]
+            set_style_video_targets(net, current_styles, args)
+            for mod in losses:
+                mod.mode = "loss"
+        pastiche = output[indices].contiguous()
+        if w == 0 and getattr(args, "normalize_weights", False):  # optim.py:176-178
+            for i in net.content_losses + net.style_losses + net.temporal_losses:
+                i.strength = i.strength / max(i.target.size())
+        if args.optimizer == "lbfgs":
+            opt = PixelOptimizer(pastiche, "lbfgs", history=int(getattr(args, "lbfgs_num_correction", 100)),
+                                 tolerance_change=float(getattr(args, "lbfgs_tolerance_change", -1)))
+        else:
+            opt = PixelOptimizer(pastiche, "adam", lr=float(getattr(args, "learning_rate", 1.0)))
+        live = net._live_slots()
+        up = torch.zeros(net._n_slots, device=device)
+        up[live] = 1.0
+        iteration = GraphedIteration(net, pastiche, opt, up)
+        if w != 0:
+            iteration.zero_frames = (front_overlap, end_overlap)
+        for _ in range(evals):
+            iteration()
+        output[indices] = pastiche  # optim.py:244
+        opt.close()
+    for mod in losses:
+        mod.loss = 0
+    return output
 
 
 class _LoopState:

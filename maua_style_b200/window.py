@@ -73,8 +73,10 @@ class FrameWindow:
                                         core.norm_channels))
         plans = [net._plan] + [c.stages[0]["plan"] for c in self.cores[:B - 1]]
         impl = net._impl
-        for p in plans[1:]:
-            _lib.check(self.lib.maua_plan_set_impl(p, impl), "maua_plan_set_impl")
+        for c in self.cores[:B - 1]:
+            if getattr(c, "_impl_set", None) != impl:  # (not on every pass: the call synchronises, which a graph capture forbids)
+                _lib.check(self.lib.maua_plan_set_impl(c.stages[0]["plan"], impl), "maua_plan_set_impl")
+                c._impl_set = impl
         while len(self.loss_vecs) < B:
             self.loss_vecs.append(torch.zeros(net._n_slots, device=net.device))
             self.coefs.append(torch.zeros(net._n_slots, device=net.device))
@@ -141,6 +143,7 @@ class FrameWindow:
                 else:
                     io.value_scale = float(mod.strength) / B              # loss.py:59
             xb = x[b]
+            self.loss_vecs[b].zero_()  # slots this pass does not write must not carry values of an earlier pass
             self._keep += [tio, base_iio]
             with torch.cuda.device(net.device):
                 _lib.check(lib.maua_plan_forward(plans[b], _lib.ptr(xb), H, W, tio, C.byref(base_iio), _lib.ptr(self.loss_vecs[b]),
@@ -176,10 +179,10 @@ class FrameWindow:
             if mod.mode == "capture":
                 bw = float(mod.blend_weight)
                 mod.target += bw * stat.sum(0) / B                                    # loss.py:148-151
-                if mod.video_target.nelement() == 0 or mod.video_target.data_ptr() == mod.target.data_ptr():
-                    mod.video_target = bw * gram.clone() if fresh[t] or mod.video_target.shape[0] != BC else mod.video_target + bw * gram
+                if mod.video_target.nelement() == 0:                                  # loss.py:172-175
+                    mod.video_target = bw * gram
                 else:
-                    mod.video_target = mod.video_target + bw * gram                   # loss.py:172-175
+                    mod.video_target = mod.video_target + bw * gram
             else:
                 s, vsf = float(mod.strength), float(mod.video_style_factor)
                 ds = stat - mod.target.to(dev)                                       # [B, C, C]

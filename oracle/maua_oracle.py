@@ -349,6 +349,9 @@ def lbfgs_optimize(p: torch.Tensor, closure: Callable, max_iter: int, lr: float 
                    tolerance_change: float = -1.0):
     """torch.optim.LBFGS.step without line search, tolerance_grad = -1 (never satisfied); one call = max_iter
     closure evaluations and max_iter parameter updates (optim.py:180-191, :240)."""
+    # torch.optim.LBFGS also stops on max_eval = max_iter * 5 // 4 closure evaluations (its default; optim.py:180-191 does not
+    # pass it): one evaluation before the loop + one per iteration, so max_iter = 2 / 3 give only 1 / 2 updates
+    max_iter = min(max_iter, max(max_iter * 5 // 4 - 1, 1))
     p = p.clone()
     flat = p.view(-1)
     g = closure(p).reshape(-1)
@@ -379,7 +382,8 @@ def lbfgs_optimize(p: torch.Tensor, closure: Callable, max_iter: int, lr: float 
                 be = float(old_dirs[i].dot(r)) * ro[i]
                 r.add_(old_stps[i], alpha=al[i] - be)
         prev_g = g.clone()
-        t = min(1.0, 1.0 / float(g.abs().sum())) * lr if n_iter == 1 else lr
+        g1 = float(g.abs().sum())  # (torch divides tensors: 1 / 0 = inf and min(1, inf) = 1 -- an all-masked img_vid window)
+        t = min(1.0, 1.0 / g1 if g1 > 0 else float("inf")) * lr if n_iter == 1 else lr
         gtd = float(g.dot(d))
         if gtd > -tolerance_change:
             break
@@ -410,6 +414,83 @@ def optimize(content, styles, init, num_iters, cfg: StyleConfig, params, tempora
     if cfg.optimizer == "adam":
         return adam_optimize(p0, closure, num_iters + 1, lr=cfg.learning_rate)
     return lbfgs_optimize(p0, closure, num_iters, lr=1.0, history=cfg.lbfgs_num_correction)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# transfer type img_vid: windows of B > 1 frames (optim.py:69-90, :113-125, :149-170, :216-219, :242-247)
+# ------------------------------------------------------------------------------------------------------------
+def set_style_video_targets(net: OracleNet, videos: Sequence[torch.Tensor], blend: Sequence[float], gfw: int):
+    """optim.py:69-90: every style clip is averaged over all of its windows of `gfw` frames."""
+    for m in net.style_losses:
+        m.reset_targets()
+        m.mode = "capture"
+    for i, video in enumerate(videos):
+        n_win = max(len(video) - gfw + 1, 1)
+        for m in net.style_losses:
+            m.blend_weight = blend[i] / n_win
+        for start in range(n_win):
+            net(video[start:start + gfw])
+    for m in net.style_losses:
+        m.mode = "none"
+
+
+def wrapping_indices(n: int, start: int, length: int) -> torch.Tensor:
+    """utils.py:76-85."""
+    if start + length <= n:
+        idx = torch.arange(start, start + length)
+    else:
+        idx = torch.cat((torch.arange(start, n), torch.arange(0, (start + length) % n)))
+    if n == 1:
+        idx = torch.zeros(1, dtype=torch.int64)
+    return idx
+
+
+def optimize_windows(content, styles, init, num_iters, cfg: StyleConfig, params, gfw: int, afw: int = -1,
+                     channels=VGG19_CHANNELS):
+    """optim.py:111-255 with "_vid" in transfer_type: the pastiche video is optimised window by window; frames the previous
+    window styled get zero gradient (:216-219); a fresh optimizer per window."""
+    clips = [init] + list(styles)
+    num_windows = math.ceil(init.shape[0] / gfw)
+    framestep = [(c.shape[0] - gfw / 2) / num_windows for c in clips]
+    windows = [[math.ceil(framestep[i] * n) for n in range(num_windows + 1)] if clips[i].shape[0] != 1
+               else [0] * (num_windows + 1) for i in range(len(clips))]
+    net = OracleNet(params, cfg, channels)
+    blend = cfg.blend(len(styles))
+    set_content_targets(net, content)
+    if afw == -1:
+        set_style_video_targets(net, styles, blend, gfw)
+        for m in net.losses:
+            m.mode = "loss"
+    output = init.clone().float()
+    T = output.shape[0]
+    for w, start in enumerate(windows[0]):
+        front = windows[0][w - 1] + gfw - start
+        end = (start + gfw) % T if start + gfw >= T else 0
+        idx = wrapping_indices(T, start, gfw)
+        if afw != -1:
+            cur = [s[wrapping_indices(s.shape[0], windows[k + 1][w], afw)] for k, s in enumerate(styles)]
+            set_style_video_targets(net, cur, blend, gfw)
+            for m in net.losses:
+                m.mode = "loss"
+        if w == 0 and cfg.normalize_weights:
+            for m in net.content_losses + net.style_losses + net.temporal_losses:
+                m.strength = m.strength / max(m.target.size())
+
+        def closure(p, w=w, front=front, end=end):
+            g = feval(net, p)[2]
+            if w != 0:
+                g[:front] = 0
+                if end > 0:
+                    g[-end:] = 0
+            return g
+
+        p0 = output[idx].clone()
+        if cfg.optimizer == "adam":
+            res = adam_optimize(p0, closure, num_iters + 1, lr=cfg.learning_rate)
+        else:
+            res = lbfgs_optimize(p0, closure, num_iters, lr=1.0, history=cfg.lbfgs_num_correction)
+        output[idx] = res
+    return output
 
 
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 255.0) -> float:

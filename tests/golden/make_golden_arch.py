@@ -31,6 +31,65 @@ import make_golden as mg  # noqa: E402
 O = mg.O
 
 
+def video_inputs(T, h, w, style_shapes):
+    """Seeded stand-ins for an img_vid job: content image, style clips [(frames, h, w)], pastiche video of T frames."""
+    import torch
+
+    content = O.synthetic_image(h, w, seed=1, smooth=True)
+    styles = [torch.cat([O.synthetic_image(sh, sw, seed=20 + 10 * i + f, smooth=(f % 2 == 0)) for f in range(n)])
+              for i, (n, sh, sw) in enumerate(style_shapes)]
+    init = torch.cat([O.synthetic_image(h, w, seed=40 + f) * 0.25 for f in range(T)])
+    return content, styles, init
+
+
+def run_video_case(name, rconfig, rmodels, roptim, workdir, ckpt, T, h, w, style_shapes, gfw, afw, iters, **over):
+    """transfer_type img_vid (optim.py:113-125, :149-170, :216-219): one feval on the first window of `gfw` frames (per-module
+    losses, the static / dynamic style targets, the gradient of every frame) and the whole windowed optimisation."""
+    import json
+
+    import numpy as np
+    import torch
+
+    torch.manual_seed(0)
+    torch.set_flush_denormal(True)
+    args = mg.reference_args(rconfig, workdir, ckpt, n_styles=len(style_shapes), **over)
+    args.transfer_type, args.gram_frame_window, args.avg_frame_window = "img_vid", gfw, afw
+    content, styles, init = video_inputs(T, h, w, style_shapes)
+    out = {"meta": json.dumps(dict(name=name, T=T, h=h, w=w, style_shapes=style_shapes, gfw=gfw, afw=afw, iters=iters, over=over,
+                                   blend=[float(x) for x in args.style_blend_weights], arch="VGG-19"))}
+    net, losses = rmodels.load_model(args)
+    roptim.set_content_targets(net, content, args)
+    first = styles if afw == -1 else [s[:afw] if s.shape[0] > 1 else s for s in styles]
+    roptim.set_style_video_targets(net, first, args)
+    for m in losses:
+        m.mode = "loss"
+    x = init[:gfw].clone().requires_grad_(True)
+    net(x)
+    total = 0
+    for i, m in enumerate(losses):
+        if isinstance(m.loss, int):
+            out[f"loss_{i}_{m.name.split()[0]}"] = np.float32(0)
+            continue
+        out[f"loss_{i}_{m.name.split()[0]}"] = np.float32(m.loss.item())
+        total = total + m.loss
+    total.backward()
+    out["grad"] = x.grad.numpy().astype(np.float32)
+    out["total"] = np.float32(total.item())
+    for i, m in enumerate(net.style_losses):
+        out[f"style_target_{i}_stats"] = np.array([m.target.sum().item(), m.target.norm().item()], dtype=np.float64)
+        out[f"style_target_{i}_block"] = m.target[:16, :16].numpy().astype(np.float32)
+        vt = m.video_target
+        out[f"video_target_{i}_shape"] = np.array(vt.shape, dtype=np.int64)
+        out[f"video_target_{i}_stats"] = np.array([vt.sum().item(), vt.norm().item()], dtype=np.float64)
+        out[f"video_target_{i}_sample"] = mg.sample(vt)
+    for m in losses:
+        m.loss = 0
+    res = roptim.optimize(content, styles, init.clone(), iters, args)
+    out["optimized"] = res.detach().numpy().astype(np.float32)
+    np.savez_compressed(mg.HERE / f"{name}.npz", **out)
+    print(f"wrote {name}.npz ({(mg.HERE / (name + '.npz')).stat().st_size / 1024:.0f} KiB)")
+
+
 def main():
     only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     rconfig, rloss, rmodels, roptim = mg.import_reference()
@@ -49,6 +108,17 @@ def main():
         mg.run_case("vgg16p_cov_lbfgs_64x80", ckpt=ckpt16p, h=64, w=80, style_hw=[(72, 72), (56, 96)], iters=4,
                     optimizer="lbfgs", use_covariance=True, style_blend_weights="3,1", relu_names=names16,
                     meta_extra={"arch": "VGG-16p"}, **pre)
+        ckpt19v = workdir / "vgg19-random.pth"
+        mg.save_checkpoint(rmodels, ckpt19v)
+        if not only or "img_vid_windows_adam_48x64" in only:
+            # a style video (4 frames) and a style image, all targets captured once (avg_frame_window -1), 3 windows of 3 frames
+            run_video_case("img_vid_windows_adam_48x64", ckpt=ckpt19v, T=5, h=48, w=64, style_shapes=[(4, 56, 56), (1, 48, 48)],
+                           gfw=3, afw=-1, iters=2, style_blend_weights="3,1", **pre)
+        if not only or "img_vid_avgwin_lbfgs_48x48" in only:
+            # style targets re-captured per window from 2-frame style windows: the dynamic target is [2C, 2C] and the dynamic
+            # term of the 3-frame pastiche windows is skipped (loss.py:165-166); covariance loss; L-BFGS
+            run_video_case("img_vid_avgwin_lbfgs_48x48", ckpt=ckpt19v, T=4, h=48, w=48, style_shapes=[(3, 48, 64)],
+                           gfw=3, afw=2, iters=3, optimizer="lbfgs", use_covariance=True, **pre)
         ckpt16 = workdir / "vgg16-random.pth"
         mg.save_checkpoint(rmodels, ckpt16, arch="VGG-16")
         common = dict(rconfig=rconfig, rmodels=rmodels, roptim=roptim, workdir=workdir)

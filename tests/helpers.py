@@ -74,3 +74,24 @@ def golden_inputs(meta):
 def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def video_inputs(meta):
+    """make_golden_arch.video_inputs: content image, style clips, pastiche video of an img_vid golden."""
+    content = O.synthetic_image(meta["h"], meta["w"], seed=1, smooth=True)
+    styles = [torch.cat([O.synthetic_image(sh, sw, seed=20 + 10 * i + f, smooth=(f % 2 == 0)) for f in range(n)])
+              for i, (n, sh, sw) in enumerate(meta["style_shapes"])]
+    init = torch.cat([O.synthetic_image(meta["h"], meta["w"], seed=40 + f) * 0.25 for f in range(meta["T"])])
+    return content, styles, init
+
+
+def video_cfg(meta):
+    over = dict(meta["over"])
+    cfg = O.StyleConfig(content_weight=5.0)
+    cfg.optimizer = over.pop("optimizer", "adam")
+    if "style_blend_weights" in over:
+        cfg.style_blend_weights = [float(x) for x in over.pop("style_blend_weights").split(",")]
+    for k, v in over.items():
+        assert hasattr(cfg, k), k
+        setattr(cfg, k, v)
+    return cfg

@@ -22,9 +22,8 @@ def test_vgg16_family_names_and_pruned_model():
     assert models._architecture("/tmp/episode-3/vgg19-random.pth", "max")[0] == models.channel_list["VGG-19"]
     ch, names = models._architecture("modelzoo/vgg16-prune.pth", "max")
     assert ch == models.channel_list["VGG-16p"] and ch[:2] == [24, 22] and names is models.vgg16_dict
-    # padded counts: multiples of 64; 64 or a multiple of 128 under a style tap
+    # padded counts: multiples of 64
     assert [models.padded_channels(c, False) for c in (24, 41, 108, 184, 276, 228, 512)] == [64, 64, 128, 192, 320, 256, 512]
-    assert [models.padded_channels(c, True) for c in (24, 41, 108, 184, 276)] == [64, 64, 128, 256, 384]
     import torch
     raw = [(torch.ones(24, 3, 3, 3), torch.ones(24)), (torch.ones(22, 24, 3, 3), torch.ones(22))]
     (w0, b0), (w1, b1) = models._pad_params(raw, [24, 22], [64, 64])
@@ -193,3 +192,26 @@ def test_conv_tile_plan_host_logic():
         bn, mt, cg, whole, split_tiles, s = plan(hw, hw, 128, 128)
         tiles = -(-hw // 16) * -(-hw // (8 * mt * cg)) * (128 // bn)
         assert whole + split_tiles == tiles
+
+
+def test_lbfgs_update_count_matches_torch_max_eval():
+    """torch.optim.LBFGS(max_iter=n) as optim.py:180-191 builds it stops after max_eval = n*5//4 closure evaluations: count
+    the parameter updates torch really makes and compare with optim.lbfgs_updates / the oracle's restated loop."""
+    import torch
+
+    for n in (1, 2, 3, 4, 5, 8):
+        p = torch.nn.Parameter(torch.tensor([3.0, -2.0, 1.0]))
+        opt = torch.optim.LBFGS([p], max_iter=n, tolerance_change=-1, tolerance_grad=-1)
+        seen = []
+
+        def closure():
+            opt.zero_grad()
+            loss = (p ** 4).sum() + (p ** 2).sum()
+            loss.backward()
+            seen.append(p.detach().clone())
+            return loss
+
+        opt.step(closure)
+        pts = seen + [p.detach().clone()]
+        updates = sum(1 for a, b in zip(pts[:-1], pts[1:]) if not torch.equal(a, b))
+        assert updates == optim.lbfgs_updates(n), (n, updates)

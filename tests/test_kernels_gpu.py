@@ -233,7 +233,8 @@ def test_pool_fwd_bwd(lib, avg, h, w):
 
 @IMPLS
 @pytest.mark.parametrize("cov", [0, 1])
-@pytest.mark.parametrize("c,h,w", [(64, 40, 56), (128, 33, 21), (256, 16, 16), (512, 9, 13), (64, 3, 5)])
+@pytest.mark.parametrize("c,h,w", [(64, 40, 56), (128, 33, 21), (256, 16, 16), (512, 9, 13), (64, 3, 5),
+                                   (192, 24, 20), (320, 12, 17), (1536, 8, 9)])  # B*C of img_vid windows; pruned VGG-16 (192, 320)
 def test_gram(lib, impl, cov, c, h, w):
     g = torch.Generator().manual_seed(c + h)
     f = tf32_round(F.relu(torch.randn(1, c, h, w, generator=g) + 0.3))

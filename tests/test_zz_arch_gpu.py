@@ -34,13 +34,20 @@ CASES = ["vgg16_adam_gram_72x88", "vgg16p_adam_gram_72x88", "vgg16p_cov_lbfgs_64
 BOUNDS = {
     "vgg16_adam_gram_72x88": (5e-2, 40.0),        # 3.0e-2, 56.0 dB
     "vgg16p_adam_gram_72x88": (5e-2, 40.0),       # measured on B200: see profiles/r02_f4_parity.txt
-    "vgg16p_cov_lbfgs_64x80": (5e-2, 20.0),       # 4 L-BFGS iterations: same sensitivity as vgg19_taps_lbfgs_80x64
+    "vgg16p_cov_lbfgs_64x80": (5e-2, 45.0),       # optimisation in exact-arithmetic mode, see EXACT_OPTIMIZE
     "vid_frame_temporal_64x80": (4e-2, 40.0),     # 2.2e-2, 56.1 dB
     "vgg19_taps_lbfgs_80x64": (4e-2, 20.0),       # 2.5e-2, 34.7 dB (fp32 leaps by 7.5 grey levels rms in iteration 3, the
                                                   # TF32 arithmetic crawls by 3.1: the two can differ by at most ~24 dB)
     "vgg19_deep_taps_avg_64x96": (1.5e-2, 40.0),  # 6.9e-3, 62.0 dB (ReLU-sign flips remain with average pooling, 18 layers deep)
     "vgg19_same_layer_taps_64x64": (7e-2, 40.0),  # 4.3e-2, 55.5 dB
 }
+
+
+# L-BFGS without line search takes its second step from a curvature pair that is rounding noise under TF32 operands (DESIGN.md
+# section 2): depending on the sign the noise gives y.s, the pair is dropped and the step is the raw gradient.  On this case the
+# B200 realisation drops it (11 dB; the CPU emulation of the same roundings keeps it: 50 dB), so the optimisation is pinned in
+# the exact-arithmetic mode, where it has to follow the reference closely.
+EXACT_OPTIMIZE = {"vgg16p_cov_lbfgs_64x80"}
 
 
 def temporal_inputs(meta):
@@ -140,6 +147,10 @@ def test_variant_optimize_matches_reference_golden(name, tmp_path):
     temporal = temporal_inputs(meta)
     if temporal:
         optim.set_temporal_targets(net, temporal[0], temporal[1], args)
+    if name in EXACT_OPTIMIZE:
+        from maua_style_b200 import _lib
+
+        net.set_impl(_lib.MAUA_IMPL_FP32)
     out = optim.optimize(content, styles, init.clone(), meta["iters"], args, net, losses)
     p = O.psnr(out, torch.from_numpy(z["optimized"]))
     print(f"{name} optimize {meta['iters']} iters PSNR {p:.1f} dB")
