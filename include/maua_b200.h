@@ -133,6 +133,25 @@ MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int
 MAUA_API int maua_pool2x2_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w,
                               int c, int avg, int round_tf32, maua_stream_t stream);
 
+/* NIN backbone (models.py:74-113): the layer shapes that are not 3x3 / pad 1 or 1x1 GEMMs, as direct fp32 convolutions.
+ * out NHWC [b][oh][ow][cout] = act(conv(in, w OIHW [cout][cin][ks][ks], stride, pad) + bias), oh = (h + 2 pad - ks) / stride + 1;
+ * `in` is NHWC [b][h][w][cin], or the NCHW image when in_nchw (conv1: 11x11 / stride 4, models.py:83; conv2: 5x5 / pad 2, :90). */
+MAUA_API int maua_conv_direct_fwd(const float* in, int in_nchw, const float* w, const float* bias, float* out, int b, int h,
+                                  int wd, int cin, int cout, int ks, int stride, int pad, int relu, int round_tf32,
+                                  maua_stream_t stream);
+/* [cout][cin][ks][ks] -> [cin][cout][ks][ks] rotated by 180 degrees: with these weights and pad' = ks - 1 - pad the input gradient
+ * of a stride-1 convolution is maua_conv_direct_fwd of the output gradient (autograd's conv backward-data, models.py:90). */
+MAUA_API int maua_conv_direct_flip_weights(const float* w, float* out, int cout, int cin, int ks, maua_stream_t stream);
+/* Input gradient of the strided, unpadded image layer: gout NHWC [b][oh][ow][cout] -> gimg NCHW [b][3][h][w] (models.py:83). */
+MAUA_API int maua_conv_direct_dgrad_image(const float* gout, const float* w, float* gimg, int b, int h, int wd, int cout, int ks,
+                                          int stride, maua_stream_t stream);
+/* MaxPool2d / AvgPool2d((3,3), (2,2), (0,0), ceil_mode=True) on NHWC (models.py:77-80): output (h < 2 ? 0 : (h - 2) / 2 + 1), the
+ * last window clipped at the border (the average divides by the clipped size); backward like maua_pool2x2_bwd, gather form over
+ * the <= 4 windows that contain a pixel, first maximum in row-major window order. */
+MAUA_API int maua_pool3x3_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream);
+MAUA_API int maua_pool3x3_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w, int c,
+                              int avg, int round_tf32, maua_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Loss kernels -- loss.py
  * ---------------------------------------------------------------------------------------------- */
@@ -256,6 +275,11 @@ typedef struct maua_net_desc {
      * REAL count here; the Gram 1/(C*H*W), the nn.MSELoss means and the
      * gradient scales use it, so padded and unpadded networks give the same losses and gradients.  0 = channels[i]. */
     int norm_channels[MAUA_MAX_LAYERS];
+    /* NIN (models.py:74-113, nin_dict :140-172): per conv entry 0 = 3x3 / pad 1 (VGG), 1 = 1x1 ("cccp" layers), 5 = 5x5 / pad 2
+     * (conv2), 11 = 11x11 / stride 4 / no padding (conv1, image layer only).  pool_kind 0 = 2x2 / stride 2 (floor),
+     * 1 = 3x3 / stride 2 / ceil_mode (models.py:77-80). */
+    int conv_kind[MAUA_MAX_LAYERS];
+    int pool_kind;
 } maua_net_desc;
 
 /* Per-call, per-tap state: targets are caller-owned tensors so the Python loss modules can expose them

@@ -38,6 +38,8 @@ class NetDesc(C.Structure):
         ("tap_relu_index", C.c_int * MAUA_MAX_TAPS),
         ("tap_kind", C.c_int * MAUA_MAX_TAPS),
         ("norm_channels", C.c_int * MAUA_MAX_LAYERS),
+        ("conv_kind", C.c_int * MAUA_MAX_LAYERS),
+        ("pool_kind", C.c_int),
     ]
 
 

@@ -218,6 +218,36 @@ MAUA_API int maua_pool2x2_bwd(const float* x, const float* gy, const float* adde
     return pool_bwd_launch(x, gy, addend, gx, b, h, w, c, avg, round_tf32, (cudaStream_t)stream);
 }
 
+MAUA_API int maua_conv_direct_fwd(const float* in, int in_nchw, const float* w, const float* bias, float* out, int b, int h,
+                                  int wd, int cin, int cout, int ks, int stride, int pad, int relu, int round_tf32,
+                                  maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    return conv_gen_fwd_launch(in, in_nchw, w, bias, out, nullptr, b, h, wd, cin, cout, ks, stride, pad, relu, round_tf32,
+                               (cudaStream_t)stream);
+}
+MAUA_API int maua_conv_direct_flip_weights(const float* w, float* out, int cout, int cin, int ks, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(w && out, "maua_conv_direct_flip_weights: null pointer");
+    return conv_gen_flip_weights_launch(w, out, cout, cin, ks, (cudaStream_t)stream);
+}
+MAUA_API int maua_conv_direct_dgrad_image(const float* gout, const float* w, float* gimg, int b, int h, int wd, int cout, int ks,
+                                          int stride, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    ImageTail tail;
+    return conv_gen_dgrad_img_launch(gout, w, gimg, b, h, wd, cout, ks, stride, tail, (cudaStream_t)stream);
+}
+MAUA_API int maua_pool3x3_fwd(const float* x, float* y, int b, int h, int w, int c, int avg, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && y, "maua_pool3x3_fwd: null pointer");
+    return pool3_fwd_launch(x, y, b, h, w, c, avg, 0, (cudaStream_t)stream);
+}
+MAUA_API int maua_pool3x3_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w, int c,
+                              int avg, int round_tf32, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && gy && gx, "maua_pool3x3_bwd: null pointer");
+    return pool3_bwd_launch(x, gy, addend, gx, b, h, w, c, avg, round_tf32, (cudaStream_t)stream);
+}
+
 MAUA_API size_t maua_reduce_workspace_bytes(void) { return 256 + sizeof(double) * 148 * 8 * 4; }
 
 MAUA_API size_t maua_gram_workspace_bytes(int c) { return gram_workspace_bytes(c); }

@@ -109,4 +109,18 @@ int conv_first_dgrad_prep_weights(const float* w_oihw, float* wt, int Cout, int 
 int conv_first_dgrad_launch(const float* gout, const float* wt, float* gimg, int B, int H, int W, int Cout,
                             const ImageTail& tail, float* T, int impl, cudaStream_t st);
 
+// conv_gen.cu: direct fp32 convolutions and the 3x3 / 2 ceil_mode pooling of the NIN backbone (models.py:74-113)
+// out NHWC [B][OH][OW][Cout] = act(conv(in, w [Cout][Cin][ks][ks]) + bias); `in` is NHWC, or the NCHW image when in_nchw
+int conv_gen_fwd_launch(const float* in, int in_nchw, const float* w, const float* bias, float* out, uint32_t* mask_out, int B,
+                        int H, int W, int Cin, int Cout, int ks, int stride, int pad, int relu, int round, cudaStream_t st);
+// [Cout][Cin][ks][ks] -> [Cin][Cout][ks][ks] rotated by 180 degrees (weights of the stride-1 input-gradient convolution)
+int conv_gen_flip_weights_launch(const float* w, float* out, int Cout, int Cin, int ks, cudaStream_t st);
+// image-layer backward for a strided convolution without padding (+ TVLoss / temporal gradients); gout may be null
+int conv_gen_dgrad_img_launch(const float* gout, const float* w, float* gimg, int B, int H, int W, int Cout, int ks, int stride,
+                              const ImageTail& tail, cudaStream_t st);
+void pool3_out_extent(int H, int W, int* PH, int* PW);
+int pool3_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, int do_round, cudaStream_t st);
+int pool3_bwd_launch(const float* x, const float* gy, const float* addend, float* gx, int B, int H, int W, int C, int avg,
+                     int do_round, cudaStream_t st);
+
 }  // namespace maua

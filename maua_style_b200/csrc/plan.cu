@@ -33,6 +33,9 @@ namespace {
 struct Entry {
     bool pool = false;
     int cin = 0, cout = 0;     // conv only
+    int ks = 3, stride = 1, pad = 1;  // conv geometry: 3x3 / 1 / 1 (VGG), 1x1, 5x5 / 1 / 2, 11x11 / 4 / 0 (NIN, models.py:82-111)
+    bool pool3 = false;        // pool only: 3x3 / stride 2 / ceil_mode (NIN, models.py:77-80) instead of 2x2 / stride 2
+    float* w_flip = nullptr;   // 5x5 only: [cin][cout][5][5] rotated copy = the weights of the input-gradient convolution
     int conv_index = -1;       // = relu index (global, counted from conv1_1)
     bool image_layer = false;  // conv1_1: consumes the NCHW image (conv_edge.cu)
     float* w_raw = nullptr;    // OIHW copy (first conv only needs it, kept for all: 52 MB total)
@@ -201,15 +204,24 @@ struct DeviceGuard {
     }
 };
 
+// output extent of one entry given its input extent
+void entry_extent(const Entry& e, int& h, int& w) {
+    if (e.pool) {
+        if (e.pool3) pool3_out_extent(h, w, &h, &w);
+        else { h /= 2; w /= 2; }
+    } else {
+        h = h + 2 * e.pad >= e.ks ? (h + 2 * e.pad - e.ks) / e.stride + 1 : 0;
+        w = w + 2 * e.pad >= e.ks ? (w + 2 * e.pad - e.ks) / e.stride + 1 : 0;
+    }
+}
+
 int ensure_workspaces(maua_plan* p, int H, int W) {
     // extents per entry
     size_t need = 0, max_act = 0, need_bits = 0;
     int h = H, w = W;
     for (auto& e : p->entries) {
-        if (e.pool) {
-            h /= 2; w /= 2;
-            MAUA_REQUIRE(h >= 1 && w >= 1, "image %dx%d is too small for this network (pooled to nothing)", H, W);
-        }
+        entry_extent(e, h, w);
+        MAUA_REQUIRE(h >= 1 && w >= 1, "image %dx%d is too small for this network (an activation would be empty)", H, W);
         e.H = h; e.W = w;
         const size_t n = (size_t)h * w * e.C;
         need += (n + 63) & ~size_t(63);
@@ -307,6 +319,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
         Entry en;
         if (d->channels[i] == 0) {
             en.pool = true;
+            en.pool3 = d->pool_kind == 1;
             en.C = cin;
             MAUA_REQUIRE(cin % 4 == 0, "pool over %d channels unsupported", cin);
         } else {
@@ -317,13 +330,34 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
             MAUA_REQUIRE(en.Cn <= en.cout, "conv entry %d: norm_channels %d exceeds channels %d", i, en.Cn, en.cout);
             en.conv_index = convs++;
             en.image_layer = (i == 0);
+            {
+                const int kind = d->conv_kind[i];
+                if (kind == 1) { en.ks = 1; en.pad = 0; }
+                else if (kind == 5) { en.ks = 5; en.pad = 2; }
+                else if (kind == 11) { en.ks = 11; en.stride = 4; en.pad = 0; }
+                else if (kind != 0) {
+                    set_last_error("conv entry %d: unknown conv_kind %d (0: 3x3, 1: 1x1, 5: 5x5 pad 2, 11: 11x11 stride 4)", i, kind);
+                    ok = false;
+                    break;
+                }
+                if ((kind == 11) != (i == 0 && kind != 0)) {
+                    set_last_error("conv entry %d: the 11x11 / 4 layer is the image layer and only that", i);
+                    ok = false;
+                    break;
+                }
+                if (i == 0 && kind != 0 && kind != 11) {
+                    set_last_error("the image layer must be a 3x3 or the 11x11 / 4 convolution");
+                    ok = false;
+                    break;
+                }
+            }
             if (i > 0 && !(en.cin % 32 == 0 && en.cout % 64 == 0)) {
                 set_last_error("conv %d: %d -> %d channels unsupported by the tcgen05 path (need Cin %% 32 == 0, Cout %% 64 == 0); "
                                "only VGG-16/19-shaped stacks are supported", en.conv_index, en.cin, en.cout);
                 ok = false;
                 break;
             }
-            if (i == 0 && !(en.cout % 16 == 0 && en.cout <= 128 && 256 % (en.cout / 16) == 0 && en.cout % 64 == 0)) {
+            if (i == 0 && en.ks == 3 && !(en.cout % 16 == 0 && en.cout <= 128 && 256 % (en.cout / 16) == 0 && en.cout % 64 == 0)) {
                 set_last_error("first conv: 3 -> %d channels unsupported", en.cout);
                 ok = false;
                 break;
@@ -333,25 +367,28 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
                 ok = false;
                 break;
             }
-            const size_t wn = (size_t)en.cout * en.cin * 9;
+            const size_t wn = (size_t)en.cout * en.cin * en.ks * en.ks;
+            const bool gemm_layer = i > 0 && en.ks <= 3;  // 3x3 and 1x1: tcgen05 implicit GEMM on rounded GEMM-layout copies
             alloc((void**)&en.w_raw, wn * sizeof(float));
             alloc((void**)&en.bias, (size_t)en.cout * sizeof(float));
-            if (i > 0) {
+            if (gemm_layer) {
                 alloc((void**)&en.wg, wn * sizeof(float));
                 alloc((void**)&en.wd, wn * sizeof(float));
             }
+            if (en.ks == 5) alloc((void**)&en.w_flip, wn * sizeof(float));
             // the checkpoint tensors may live on another device (the first stage's): peer-capable default copy
             if (e == cudaSuccess) e = cudaMemcpy(en.w_raw, d->weights[i], wn * sizeof(float), cudaMemcpyDefault);
             if (e == cudaSuccess) e = cudaMemcpy(en.bias, d->biases[i], (size_t)en.cout * sizeof(float), cudaMemcpyDefault);
-            if (i == 0) {
+            if (i == 0 && en.ks == 3) {
                 alloc((void**)&en.wt1, (size_t)32 * en.cout * sizeof(float));
                 if (e == cudaSuccess && conv_first_dgrad_prep_weights(en.w_raw, en.wt1, en.cout, 1, 0)) ok = false;
             }
-            if (e == cudaSuccess && i > 0) {
-                if (prep_weights_launch(en.w_raw, en.wg, en.cout, en.cin, 0, 1, 0) ||
-                    prep_weights_launch(en.w_raw, en.wd, en.cout, en.cin, 1, 1, 0))
+            if (e == cudaSuccess && gemm_layer) {
+                if (prep_weights_launch(en.w_raw, en.wg, en.cout, en.cin, 0, 1, 0, en.ks * en.ks) ||
+                    prep_weights_launch(en.w_raw, en.wd, en.cout, en.cin, 1, 1, 0, en.ks * en.ks))
                     ok = false;
             }
+            if (e == cudaSuccess && en.ks == 5 && conv_gen_flip_weights_launch(en.w_raw, en.w_flip, en.cout, en.cin, 5, 0)) ok = false;
             cin = en.cout;
         }
         p->entries.push_back(en);
@@ -440,7 +477,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     DeviceGuard guard(p->device);
     for (auto& e : p->entries) {
         cudaFree(e.w_raw); cudaFree(e.wg); cudaFree(e.wd); cudaFree(e.bias); cudaFree(e.wt1);
-        cudaFree(e.wg32); cudaFree(e.wd32); cudaFree(e.wt1_32);
+        cudaFree(e.wg32); cudaFree(e.wd32); cudaFree(e.wt1_32); cudaFree(e.w_flip);
     }
     for (auto& t : p->taps) {
         cudaFree(t.gram); cudaFree(t.diff); cudaFree(t.aux_d); cudaFree(t.mean); cudaFree(t.aux_bias); cudaFree(t.gram_ws);
@@ -466,7 +503,8 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
         DeviceGuard guard(p->device);
         for (auto& e : p->entries) {
             if (e.pool) continue;
-            const size_t wn = (size_t)e.cout * e.cin * 9;
+            const size_t wn = (size_t)e.cout * e.cin * e.ks * e.ks;
+            if (e.ks > 3) continue;  // direct fp32 convolutions (conv_gen.cu) read the raw weights in every mode
             if (e.image_layer) {
                 if (e.wt1_32) continue;
                 MAUA_CUDA_CHECK(cudaMalloc(&e.wt1_32, (size_t)32 * e.cout * sizeof(float)));
@@ -477,8 +515,8 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
                 MAUA_CUDA_CHECK(cudaMalloc(&e.wg32, wn * sizeof(float)));
                 MAUA_CUDA_CHECK(cudaMalloc(&e.wd32, wn * sizeof(float)));
                 p->weight_bytes += 2 * wn * sizeof(float);
-                int rc = prep_weights_launch(e.w_raw, e.wg32, e.cout, e.cin, 0, 0, 0);
-                if (!rc) rc = prep_weights_launch(e.w_raw, e.wd32, e.cout, e.cin, 1, 0, 0);
+                int rc = prep_weights_launch(e.w_raw, e.wg32, e.cout, e.cin, 0, 0, 0, e.ks * e.ks);
+                if (!rc) rc = prep_weights_launch(e.w_raw, e.wd32, e.cout, e.cin, 1, 0, 0, e.ks * e.ks);
                 if (rc) return rc;
             }
         }
@@ -615,7 +653,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     const int n_ent = (int)p->entries.size();
     if (boundary_out) last_needed = n_ent - 1;  // the next stage consumes this stage's last activation
     p->last_entry = last_needed;
-    if (tv_pending && !(last_needed >= 0 && p->entries[0].image_layer)) {
+    if (tv_pending && !(last_needed >= 0 && p->entries[0].image_layer && p->entries[0].ks == 3)) {
         if ((rc = tv_value_launch(image, 3, H, W, p->img_io.tv_strength, losses_out + nt, rs, st))) return rc;
         p->launches_fwd++;
         prof_mark(p, st, "tv_value", -1, 0, 4.0 * img_elems);
@@ -629,7 +667,13 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     for (int i = 0; i <= last_needed; ++i) {
         Entry& e = p->entries[i];
         float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
-        if (e.image_layer) {
+        if (e.image_layer && e.ks != 3) {
+            // NIN conv1 (models.py:83): 11x11 / stride 4 straight from the NCHW image
+            if ((rc = conv_gen_fwd_launch(image, 1, e.w_raw, e.bias, e.out, e.bits, 1, H, W, 3, e.cout, e.ks, e.stride, e.pad, 1, rnd, st)))
+                return rc;
+            if (hand_off)
+                MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
+        } else if (e.image_layer) {
             ConvFirstTV tv;
             if (tv_pending) {
                 tv.strength = p->img_io.tv_strength; tv.out = losses_out + nt;
@@ -649,17 +693,26 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             }
             // a pooled map is not needed again by this stage (the backward pass reads the pre-pool activation), so at a
             // stage boundary it is written straight into the next stage's memory
-            if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
+            if (e.pool3) {
+                if ((rc = pool3_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
+            } else if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
+        } else if (e.ks == 5) {
+            // NIN conv2 (models.py:90): 5x5 / pad 2, direct fp32 convolution
+            if ((rc = conv_gen_fwd_launch(cur, 0, e.w_raw, e.bias, e.out, e.bits, 1, curH, curW, e.cin, e.cout, 5, 1, 2, 1, rnd, st)))
+                return rc;
+            if (hand_off)
+                MAUA_CUDA_CHECK(cudaMemcpyAsync(hand_off, e.out, (size_t)e.H * e.W * e.C * sizeof(float), cudaMemcpyDefault, st));
         } else {
             ConvArgs a;
-            a.B = 1; a.H = e.H; a.W = e.W; a.Cin = e.cin; a.Cout = e.cout; a.ntaps = 9;
+            a.B = 1; a.H = e.H; a.W = e.W; a.Cin = e.cin; a.Cout = e.cout; a.ntaps = e.ks * e.ks;
             a.in = cur; a.wg = exact ? e.wg32 : e.wg;
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = rnd;
             a.ep.mask_out = e.bits;
             if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
             a.tail_mode = p->splitk ? 1 : p->conv_tail;
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
-            if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && e.H >= 2 && e.W >= 2) {
+            if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && !p->entries[i + 1].pool3 &&
+                e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
                 a.ep.pool_avg = p->avg_pool;
                 pool_done = true;
@@ -671,7 +724,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             const double px = (double)e.H * e.W;
             if (e.image_layer) prof_mark(p, st, "conv_first_fwd", i, 2.0 * 27 * e.cout * px, 4.0 * (3 + e.cout) * px);
             else if (e.pool) prof_mark(p, st, "pool_fwd", i, 0, 4.0 * 5 * e.C * px);
-            else prof_mark(p, st, "conv_fwd", i, 2.0 * 9 * e.cin * e.cout * px, 4.0 * (e.cin + e.cout) * px);
+            else prof_mark(p, st, "conv_fwd", i, 2.0 * e.ks * e.ks * e.cin * e.cout * px, 4.0 * (e.cin + e.cout) * px);
         }
         cur = e.out; curH = e.H; curW = e.W;
         if (e.pool) continue;
@@ -853,6 +906,15 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         return r;
     };
 
+    // un-pool + ReLU mask (+ tap gradients of the pre-pool layer) through the pool entry that follows conv entry `prod`
+    auto unpool = [&](const Entry& ep_, const Entry& epool, const float* gpool, const float* addend, float* outb) -> int {
+        p->launches_bwd++;
+        const int r = epool.pool3 ? pool3_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st)
+                                  : pool_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st);
+        prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
+        return r;
+    };
+
     // Walk down from the last executed conv.  `gm` = Gm of the conv entry above the current position.
     float* gm = nullptr;       // masked gradient w.r.t. the output of entry `gm_entry`
     int gm_entry = -1;
@@ -885,9 +947,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             addend = t.ep.out;
         }
         float* outb = take_buf();
-        if ((rc = pool_bwd_launch(ep_.out, grad_top, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st))) return rc;
-        p->launches_bwd++;
-        prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
+        if ((rc = unpool(ep_, p->entries[e_idx], grad_top, addend, outb))) return rc;
         gm = outb;
         gm_entry = prod;
     } else if (e_idx >= 0) {
@@ -925,9 +985,41 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         taps_at(prod, style, content, ci);
         ConvArgs a;
         a.B = 1; a.H = ec.H; a.W = ec.W;
-        a.Cin = ec.cout; a.Cout = ec.cin; a.ntaps = 9;
+        a.Cin = ec.cout; a.Cout = ec.cin; a.ntaps = ec.ks * ec.ks;
         a.in = gm; a.wg = exact ? ec.wd32 : ec.wd;
-        if (!through_pool) {
+        if (ec.ks == 5) {
+            // NIN conv2 (5x5 / pad 2): the input gradient is the direct convolution of Gm with the rotated, transposed weights
+            // (conv_gen.cu, fp32); the ReLU mask, tap gradients and rounding follow in the un-pool kernel or an epilogue-only launch
+            float* raw = take_buf();
+            if ((rc = conv_gen_fwd_launch(gm, 0, ec.w_flip, nullptr, raw, nullptr, 1, ec.H, ec.W, ec.cout, ec.cin, 5, 1, 2, 0, 0, st)))
+                return rc;
+            p->launches_bwd++;
+            prof_mark(p, st, "conv_dgrad", ec.cin, 2.0 * 25 * ec.cin * ec.cout * ec.H * ec.W, 4.0 * (ec.cin + ec.cout) * ec.H * ec.W);
+            if (!through_pool) {
+                ConvArgs t;
+                t.B = 1; t.H = ep_.H; t.W = ep_.W; t.Cin = 32; t.Cout = ep_.C; t.ntaps = 0;
+                add_taps(t, ep_, style, content, ci);
+                t.ep.out = take_buf(); t.ep.mask_bits = ep_.bits; t.ep.round = rnd; t.ep.addend = raw;
+                if (style) { if ((rc = run_conv(t))) return rc; }
+                else { if ((rc = conv_ref_launch(t, st))) return rc; p->launches_bwd++; }
+                gm = t.ep.out;
+            } else {
+                float* addend = nullptr;
+                if (style || content) {
+                    ConvArgs t;
+                    t.B = 1; t.H = ep_.H; t.W = ep_.W; t.Cin = 32; t.Cout = ep_.C; t.ntaps = 0;
+                    add_taps(t, ep_, style, content, ci);
+                    t.ep.out = take_buf(); t.ep.round = 0;
+                    if (style) { if ((rc = run_conv(t))) return rc; }
+                    else { if ((rc = conv_ref_launch(t, st))) return rc; p->launches_bwd++; }
+                    addend = t.ep.out;
+                }
+                float* outb = take_buf();
+                if (outb == raw || outb == addend) outb = take_buf();
+                if ((rc = unpool(ep_, p->entries[below], raw, addend, outb))) return rc;
+                gm = outb;
+            }
+        } else if (!through_pool) {
             add_taps(a, ep_, style, content, ci);
             a.ep.out = take_buf(); a.ep.mask_bits = ep_.bits; a.ep.round = rnd;
             if ((rc = run_conv(a))) return rc;
@@ -949,9 +1041,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             }
             float* outb = take_buf();
             if (outb == gpool || outb == addend) outb = take_buf();
-            if ((rc = pool_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st))) return rc;
-            p->launches_bwd++;
-            prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
+            if ((rc = unpool(ep_, p->entries[below], gpool, addend, outb))) return rc;
             gm = outb;
         }
         c = prod;
@@ -964,10 +1054,14 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         const size_t in_elems = (size_t)e0.H * e0.W * e0.cin;
         if (gm && gm_entry == 0) {
             ConvArgs a;
-            a.B = 1; a.H = e0.H; a.W = e0.W; a.Cin = e0.cout; a.Cout = e0.cin; a.ntaps = 9;
+            a.B = 1; a.H = e0.H; a.W = e0.W; a.Cin = e0.cout; a.Cout = e0.cin; a.ntaps = e0.ks * e0.ks;
             a.in = gm; a.wg = exact ? e0.wd32 : e0.wd;
             a.ep.out = grad_image; a.ep.round = 0;
-            if ((rc = run_conv(a))) return rc;
+            if (e0.ks == 5) {
+                if ((rc = conv_gen_fwd_launch(gm, 0, e0.w_flip, nullptr, grad_image, nullptr, 1, e0.H, e0.W, e0.cout, e0.cin, 5, 1, 2, 0, 0, st)))
+                    return rc;
+                p->launches_bwd++;
+            } else if ((rc = run_conv(a))) return rc;
         } else {
             MAUA_CUDA_CHECK(cudaMemsetAsync(grad_image, 0, in_elems * sizeof(float), st));
         }
@@ -986,7 +1080,14 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         tail.temp_coef = p->coef2 + nt + 1;
     }
     Entry& e0 = p->entries[0];
-    if (gm && gm_entry == 0) {
+    if (e0.ks != 3) {
+        // NIN conv1 (11x11 / 4): gather-form input gradient + the image-side terms in one kernel (conv_gen.cu)
+        if ((rc = conv_gen_dgrad_img_launch((gm && gm_entry == 0) ? gm : nullptr, e0.w_raw, grad_image, 1, H, W, e0.cout, e0.ks, e0.stride,
+                                            tail, st)))
+            return rc;
+        p->launches_bwd++;
+        prof_mark(p, st, "conv_first_dgrad", 0, 2.0 * 3 * e0.ks * e0.ks * e0.cout * e0.H * e0.W, 4.0 * (e0.cout * (double)e0.H * e0.W + 6.0 * H * W));
+    } else if (gm && gm_entry == 0) {
         float* T = take_buf();
         if (T == gm) T = take_buf();
         if ((rc = conv_first_dgrad_launch(gm, exact ? e0.wt1_32 : e0.wt1, grad_image, 1, H, W, e0.cout, tail, T, p->impl, st)))
@@ -1048,7 +1149,7 @@ MAUA_API int maua_plan_stage_output_shape(const maua_plan_t* p, int h, int w, in
     MAUA_REQUIRE(p && h >= 1 && w >= 1, "maua_plan_stage_output_shape: bad arguments");
     int c = p->in_C;
     for (const auto& e : p->entries) {
-        if (e.pool) { h /= 2; w /= 2; }
+        entry_extent(e, h, w);
         c = e.C;
     }
     MAUA_REQUIRE(h >= 1 && w >= 1, "image too small for this stage");

@@ -98,20 +98,20 @@ __global__ void relu_mask_bits_kernel(const float* __restrict__ x, uint32_t* __r
 // fwd : wg[co][tap*Cin + ci]  = tf32(w[co][ci][ky][kx]),           tap = ky*3 + kx
 // dgrad: wd[ci][tap*Cout + co] = tf32(w[co][ci][2-ky][2-kx])        (180-degree rotation, transposed)
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin,
-                                    int dgrad, int do_round) {
-    const long total = (long)Cout * Cin * 9;
+                                    int dgrad, int do_round, int T /* taps: 9 (3x3) or 1 (1x1) */) {
+    const long total = (long)Cout * Cin * T;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         float v;
         if (!dgrad) {
             const int ci = i % Cin;
-            const int tap = (i / Cin) % 9;
-            const int co = i / (9L * Cin);
-            v = w[((long)co * Cin + ci) * 9 + tap];
+            const int tap = (i / Cin) % T;
+            const int co = i / ((long)T * Cin);
+            v = w[((long)co * Cin + ci) * T + tap];
         } else {
             const int co = i % Cout;
-            const int tap = (i / Cout) % 9;
-            const int ci = i / (9L * Cout);
-            v = w[((long)co * Cin + ci) * 9 + (8 - tap)];
+            const int tap = (i / Cout) % T;
+            const int ci = i / ((long)T * Cout);
+            v = w[((long)co * Cin + ci) * T + (T - 1 - tap)];
         }
         out[i] = do_round ? round_tf32(v) : v;
     }
@@ -377,8 +377,8 @@ int relu_mask_bits_launch(const float* x, uint32_t* bits, long npix, int C, cuda
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }
-int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad, int do_round, cudaStream_t st) {
-    prep_weights_kernel<<<grid_for((long)Cout * Cin * 9), kThreads, 0, st>>>(w, out, Cout, Cin, dgrad, do_round);
+int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad, int do_round, cudaStream_t st, int taps) {
+    prep_weights_kernel<<<grid_for((long)Cout * Cin * taps), kThreads, 0, st>>>(w, out, Cout, Cin, dgrad, do_round, taps);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

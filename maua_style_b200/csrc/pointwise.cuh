@@ -13,7 +13,7 @@ struct ReduceScratch {
 
 int nchw_to_nhwc_launch(const float* src, float* dst, int B, int C, int H, int W, int do_round, cudaStream_t st);
 int nhwc_to_nchw_launch(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
-int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad, int do_round, cudaStream_t st);
+int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad, int do_round, cudaStream_t st, int taps = 9);
 // do_round: TF32-round the averaged values (operands of the next tensor-core conv); max pooling never needs it
 int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, int do_round, cudaStream_t st);
 int pool_bwd_launch(const float* x, const float* gy, const float* addend, float* gx, int B, int H, int W, int C,

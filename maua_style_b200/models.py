@@ -35,6 +35,24 @@ channel_list = {
 }
 
 
+# models.py:74-113 (class NIN): (output channels, kernel) per conv; conv1 is 11x11 / stride 4 / no padding, conv2 5x5 / pad 2,
+# conv3 / conv4 3x3 / pad 1, the "cccp" layers 1x1; pools are 3x3 / stride 2 / ceil_mode.  The Dropout in front of conv4 and
+# the classifier tail (6x6 average pool, Softmax) are never part of the style network: load_model only keeps Conv2d / ReLU /
+# pool modules up to the last tapped layer (models.py:381-436).
+NIN_LAYERS = [(96, 11), (96, 1), (96, 1), "P", (256, 5), (256, 1), (256, 1), "P", (384, 3), (384, 1), (384, 1), "P",
+              (1024, 3), (1024, 1), (1000, 1)]
+# index of every conv inside NIN.features (ReLU after each conv, pools at 6 / 13 / 20, Dropout at 21)
+NIN_FEATURE_INDEX = [0, 2, 4, 7, 9, 11, 14, 16, 18, 22, 24, 26]
+# models.py:140-172
+nin_dict = {
+    "C": ["conv1", "cccp1", "cccp2", "conv2", "cccp3", "cccp4", "conv3", "cccp5", "cccp6", "conv4-1024", "cccp7-1024", "cccp8-1024"],
+    "R": [f"relu{i}" for i in range(1, 13)],
+    "P": ["pool1", "pool2", "pool3", "pool4"],
+    "D": ["drop"],
+}
+_CONV_KIND = {3: 0, 1: 1, 5: 5, 11: 11}  # kernel size -> maua_net_desc::conv_kind
+
+
 def _layer_names(channels):
     """models.py:140-243 (vgg16_dict / vgg19_dict): conv{b}_{i}, relu{b}_{i}, pool{b}."""
     names = {"C": [], "R": [], "P": []}
@@ -76,6 +94,8 @@ def _match_architecture(name: str):
     # models.py:259-288, :334-347: the fcn32s / nyud / sod checkpoints are VGG-16 feature stacks with other heads
     if any(k in name for k in ("vgg16", "vgg-16", "fcn32s", "nyud", "sod")):
         return "VGG-16"
+    if "vgg" not in name and "nin" in name:  # models.py:327-339
+        return "NIN"
     return None
 
 
@@ -86,12 +106,12 @@ def _architecture(model_file: str, pooling: str):
     full = str(model_file).lower()
     arch = _match_architecture(os.path.basename(full)) or _match_architecture(full)
     if arch is None:
-        raise ValueError(
-            f"maua_style_b200 accelerates the VGG-19 / VGG-16 feature stacks only (model_file={model_file!r}); "
-            "use the reference's torch modules for other model families")
-    channels, layer_list = channel_list[arch], (vgg19_dict if arch == "VGG-19" else vgg16_dict)
+        raise ValueError("Model architecture not recognized.")  # models.py:341 (VGG-16 / -19 / pruned / NIN are what it knows)
     if pooling not in ("max", "avg"):
         raise ValueError("Unrecognized pooling argseter")  # models.py:124
+    if arch == "NIN":
+        return NIN_LAYERS, nin_dict
+    channels, layer_list = channel_list[arch], (vgg19_dict if arch == "VGG-19" else vgg16_dict)
     return channels, layer_list
 
 
@@ -155,20 +175,25 @@ def _pad_params(params, real, padded):
 
 def _conv_params(sd, channels, disable_check):
     """(weight, bias) per conv, from torchvision-style keys features.{k}.weight (k counts conv/relu/pool slots)."""
-    params, k, cin = [], 0, 3
+    params, k, cin, conv_i = [], 0, 3, 0
+    nin = channels is NIN_LAYERS
     for c in channels:
         if c == "P":
             k += 1
             continue
+        c, ks = c if isinstance(c, tuple) else (c, 3)
+        if nin:
+            k = NIN_FEATURE_INDEX[conv_i]
         wk, bk = f"features.{k}.weight", f"features.{k}.bias"
         if wk not in sd or bk not in sd:
             raise KeyError(f"checkpoint is missing {wk} / {bk}")
         w, b = sd[wk].float(), sd[bk].float()
-        if tuple(w.shape) != (c, cin, 3, 3):
-            raise ValueError(f"{wk} has shape {tuple(w.shape)}, expected {(c, cin, 3, 3)}")
+        if tuple(w.shape) != (c, cin, ks, ks):
+            raise ValueError(f"{wk} has shape {tuple(w.shape)}, expected {(c, cin, ks, ks)}")
         params.append((w, b))
         cin = c
         k += 2
+        conv_i += 1
     return params
 
 
@@ -196,13 +221,15 @@ class _PlanCore:
     SURVEY.md section 8f rank 1 asks for this to be cached.  A core is keyed by everything the plan depends on and is
     only handed to one live network at a time."""
 
-    def __init__(self, entries, params, avg_pool, tap_sig, device, bounds, devs, norm_channels=None):
+    def __init__(self, entries, params, avg_pool, tap_sig, device, bounds, devs, norm_channels=None, conv_kinds=None,
+                 pool_kind=0):
         lib = _lib.load()
         self._lib = lib
         self.device = device
         # kept so that sibling cores can be built for the frames of an img_vid window (window.py)
         self.entries, self.avg_pool, self.tap_sig, self.bounds, self.devs = list(entries), avg_pool, list(tap_sig), list(bounds), list(devs)
         self.norm_channels = list(norm_channels) if norm_channels is not None else None
+        self.conv_kinds, self.pool_kind = (list(conv_kinds) if conv_kinds is not None else None), int(pool_kind)
         self.weights = nn.ParameterList([nn.Parameter(w.to(device).contiguous(), requires_grad=False) for w, _ in params])
         self.biases = nn.ParameterList([nn.Parameter(b.to(device).contiguous(), requires_grad=False) for _, b in params])
         desc = _lib.NetDesc()
@@ -212,11 +239,14 @@ class _PlanCore:
             desc.channels[i] = c
             if norm_channels is not None:
                 desc.norm_channels[i] = norm_channels[i]
+            if conv_kinds is not None:
+                desc.conv_kind[i] = conv_kinds[i]
             if c > 0:
                 desc.weights[i] = self.weights[ci].data_ptr()
                 desc.biases[i] = self.biases[ci].data_ptr()
                 ci += 1
         desc.avg_pool = int(avg_pool)
+        desc.pool_kind = int(pool_kind)
         desc.n_taps = len(tap_sig)
         for t, (ridx, kind) in enumerate(tap_sig):
             desc.tap_relu_index[t] = ridx
@@ -268,12 +298,15 @@ class B200Net(nn.Module):
 
     def __init__(self, entries: List[int], params, avg_pool: bool, taps, tv_mod, temporal_mod, device: torch.device,
                  stage_bounds: Optional[List[int]] = None, devices: Optional[List[torch.device]] = None,
-                 core: Optional[_PlanCore] = None, norm_channels: Optional[List[int]] = None):
+                 core: Optional[_PlanCore] = None, norm_channels: Optional[List[int]] = None,
+                 conv_kinds: Optional[List[int]] = None, pool_kind: int = 0):
         super().__init__()
         _lib.require_gpu()
         self._lib = _lib.load()
         self.device = device  # device of the image side (stage 0); losses and the image gradient are delivered there
         self.entries = entries
+        self.conv_kinds = list(conv_kinds) if conv_kinds is not None else [0] * len(entries)
+        self.pool_kind = int(pool_kind)
         self.taps = taps  # [(relu_index, module)] ordered by relu index
         self.tv_mod = tv_mod
         self.temporal_mod = temporal_mod
@@ -285,7 +318,7 @@ class B200Net(nn.Module):
             raise ValueError(f"bad stage layout: bounds {bounds} for {len(devs)} device(s) and {len(entries)} entries")
         if core is None:
             tap_sig = [(ridx, _lib.TAP_STYLE if isinstance(mod, StyleLoss) else _lib.TAP_CONTENT) for ridx, mod in taps]
-            core = _PlanCore(entries, params, avg_pool, tap_sig, device, bounds, devs, norm_channels)
+            core = _PlanCore(entries, params, avg_pool, tap_sig, device, bounds, devs, norm_channels, conv_kinds, pool_kind)
         core.owner = weakref.ref(self)
         self._core = core
         # parameters are kept (frozen) so that net.parameters() / state inspection behave like the reference's net
@@ -387,10 +420,15 @@ class B200Net(nn.Module):
 
     def _tap_hw(self, H, W, ridx):
         h, w, conv = H, W, -1
-        for c in self.entries:
+        for c, kind in zip(self.entries, self.conv_kinds):
             if c == 0:
-                h, w = h // 2, w // 2
+                if self.pool_kind == 1:  # 3x3 / stride 2 / ceil_mode (models.py:77-80)
+                    h, w = (0 if h < 2 else (h - 2) // 2 + 1), (0 if w < 2 else (w - 2) // 2 + 1)
+                else:
+                    h, w = h // 2, w // 2
             else:
+                if kind == 11:   # 11x11 / stride 4 / no padding (models.py:83)
+                    h, w = (h - 11) // 4 + 1, (w - 11) // 4 + 1
                 conv += 1
                 if conv == ridx:
                     return h, w
@@ -736,7 +774,7 @@ def _device_from_args(args) -> torch.device:
 
 
 def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stage_bounds=None, devices=None,
-              model_path=None, norm_channels=None) -> "B200Net":
+              model_path=None, norm_channels=None, conv_kinds=None, pool_kind=0) -> "B200Net":
     """A B200Net on a cached plan core when one exists for (checkpoint file, layer layout, taps, pooling, devices) and no
     live network is using it; otherwise on a new core built from `params_fn()` (which reads the checkpoint)."""
     bounds = list(stage_bounds) if stage_bounds else [0, len(entries)]
@@ -749,7 +787,7 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
             model_path = model_path or resolve_model_file(str(args.model_file))
             st = os.stat(model_path)
             key = (os.path.realpath(model_path), st.st_mtime_ns, st.st_size, avg, tuple(entries), tuple(norm_channels or ()),
-                   tap_sig, tuple(bounds), tuple(str(d) for d in devs))
+                   tuple(conv_kinds or ()), pool_kind, tap_sig, tuple(bounds), tuple(str(d) for d in devs))
         except (OSError, ValueError):
             key = None
     core = _CORE_CACHE.get(key) if key is not None else None
@@ -759,7 +797,7 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
     if core is None:
         cache_stats["misses"] += 1
         _lib.require_gpu()
-        core = _PlanCore(entries, params_fn(), avg, list(tap_sig), device, bounds, devs, norm_channels)
+        core = _PlanCore(entries, params_fn(), avg, list(tap_sig), device, bounds, devs, norm_channels, conv_kinds, pool_kind)
         if key is not None:
             _CORE_CACHE[key] = core
             while len(_CORE_CACHE) > _CORE_CACHE_MAX:
@@ -768,7 +806,7 @@ def build_net(args, entries, params_fn, taps, tv_mod, temporal_mod, device, stag
         cache_stats["hits"] += 1
         _CORE_CACHE.move_to_end(key)
     return B200Net(entries, None, avg, taps, tv_mod, temporal_mod, device, stage_bounds=bounds, devices=devs, core=core,
-                   norm_channels=norm_channels)
+                   norm_channels=norm_channels, conv_kinds=conv_kinds, pool_kind=pool_kind)
 
 
 def load_model(args):
@@ -797,16 +835,20 @@ def load_model(args):
         n_modules += 1
         temporal_losses.append(temporal_mod)
 
-    entries, taps = [], []
+    entries, taps, conv_kinds = [], [], []
+    pool_kind = 1 if channels is NIN_LAYERS else 0
     next_content_idx, next_style_idx, r, conv_i = 1, 1, 0, 0
     for c in channels:
         if not (next_content_idx <= len(content_layers) or next_style_idx <= len(style_layers)):
             break  # models.py:382: nothing below the last requested tap is built
         if c == "P":
             entries.append(0)
+            conv_kinds.append(0)
             n_modules += 1
             continue
+        c, ks = c if isinstance(c, tuple) else (c, 3)
         entries.append(c)
+        conv_kinds.append(_CONV_KIND[ks])
         conv_i += 1
         n_modules += 2  # conv + relu
         name = layer_list["R"][r]
@@ -832,6 +874,7 @@ def load_model(args):
         r += 1
     while entries and entries[-1] == 0:
         entries.pop()  # a trailing pool feeds nothing
+        conv_kinds.pop()
 
     n_convs = conv_i
     # layers whose channel counts the tcgen05 kernels do not tile (channel-pruned VGG-16) run zero-padded
@@ -856,9 +899,10 @@ def load_model(args):
         from .parallel import setup_multi_device  # layer-wise split over NVLink peers (models.py:537-566)
 
         return setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses,
-                                  tv_losses, temporal_losses, norm_channels=norm_channels)
+                                  tv_losses, temporal_losses, norm_channels=norm_channels, conv_kinds=conv_kinds, pool_kind=pool_kind)
 
-    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device, model_path=model_path, norm_channels=norm_channels)
+    net = build_net(args, entries, params, taps, tv_mod, temporal_mod, device, model_path=model_path, norm_channels=norm_channels,
+                    conv_kinds=conv_kinds, pool_kind=pool_kind)
     net.content_losses = content_losses
     net.style_losses = style_losses
     net.tv_losses = tv_losses

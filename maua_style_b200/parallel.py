@@ -64,7 +64,7 @@ def stage_bounds(entries: List[int], strategy: str, n_devices: int, taps, has_tv
 
 
 def setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, content_losses, style_losses, tv_losses,
-                       temporal_losses, norm_channels=None):
+                       temporal_losses, norm_channels=None, conv_kinds=None, pool_kind=0):
     """models.py:537-566 + :440-441: returns (net, losses) with `net` spanning the devices of `--gpu`."""
     from .models import build_net
 
@@ -82,7 +82,7 @@ def setup_multi_device(entries, params, args, taps, tv_mod, temporal_mod, conten
         for k, d in enumerate(devices):
             print(f"device {d}: entries [{bounds[k]}, {bounds[k + 1]})")
     net = build_net(args, entries, params, taps, tv_mod, temporal_mod, devices[0], stage_bounds=bounds, devices=devices,
-                    norm_channels=norm_channels)
+                    norm_channels=norm_channels, conv_kinds=conv_kinds, pool_kind=pool_kind)
     net.content_losses = content_losses
     net.style_losses = style_losses
     net.tv_losses = tv_losses

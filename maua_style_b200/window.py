@@ -58,6 +58,7 @@ class FrameWindow:
         self.gram = {}           # tap -> (gram [BC, BC], mean [BC], workspace)
         self.state = {}          # tap -> tensors kept for the backward pass
         self._keep = []
+        self._scale = None       # per-slot upstream scale (1/B for the per-frame means, 1 for TVLoss) on the device
 
     # ------------------------------------------------------------------------------------------------------------
     def _plans(self, B: int):
@@ -70,7 +71,7 @@ class FrameWindow:
         while len(self.cores) < B - 1:
             params = [(w.data, b.data) for w, b in zip(core.weights, core.biases)]
             self.cores.append(_PlanCore(core.entries, params, core.avg_pool, core.tap_sig, net.device, core.bounds, core.devs,
-                                        core.norm_channels))
+                                        core.norm_channels, core.conv_kinds, core.pool_kind))
         plans = [net._plan] + [c.stages[0]["plan"] for c in self.cores[:B - 1]]
         impl = net._impl
         for c in self.cores[:B - 1]:
@@ -202,7 +203,7 @@ class FrameWindow:
         vsf0 = (C.c_float * n)()
         normalize = (C.c_int * n)()
         kind = (C.c_int * n)()
-        scale = torch.ones(n, device=net.device)
+        scale = [1.0] * n
         for i, mod in enumerate(net.slot_modules()):
             if mod is None:
                 continue
@@ -215,8 +216,11 @@ class FrameWindow:
                 scale[i] = 1.0 / B
             else:
                 kind[i] = 2  # TVLoss: a sum over the batch, never normalised
+        if self._scale is None or self._scale[0] != scale:
+            # (made once, in the eager warm-up iterations: a host -> device copy cannot be captured into a CUDA graph)
+            self._scale = (scale, torch.tensor(scale, device=net.device))
         up = up.detach().to(net.device, torch.float32)
-        up_f = (up * scale).contiguous()
+        up_f = (up * self._scale[1]).contiguous()
         exact = net._impl == _lib.MAUA_IMPL_FP32
         keep = []
         for t, (ds, dd, mean, P, C_, BC) in self.state.items():

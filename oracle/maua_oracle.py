@@ -47,8 +47,22 @@ VGG16_CHANNELS = [64, 64, "P", 128, 128, "P", 256, 256, 256, "P", 512, 512, 512,
 VGG16P_CHANNELS = [24, 22, "P", 41, 51, "P", 108, 89, 111, "P", 184, 276, 228, "P", 512, 512, 512, "P"]
 
 
+# models.py:74-113 (class NIN): (output channels, kernel size) per conv -- conv1 11x11 / stride 4 / no padding, conv2 5x5 / pad 2,
+# conv3 / conv4 3x3 / pad 1, "cccp" layers 1x1; pools MaxPool2d / AvgPool2d((3,3), (2,2), (0,0), ceil_mode=True).  load_model keeps
+# only Conv2d / ReLU / pool modules (models.py:381-436): the Dropout in front of conv4 is never part of the style network.
+NIN_LAYERS = [(96, 11), (96, 1), (96, 1), "P", (256, 5), (256, 1), (256, 1), "P", (384, 3), (384, 1), (384, 1), "P",
+              (1024, 3), (1024, 1), (1000, 1)]
+_CONV_GEOMETRY = {3: (1, 1), 1: (1, 0), 5: (1, 2), 11: (4, 0)}  # kernel -> (stride, padding)
+
+
+def is_nin(channels) -> bool:
+    return any(isinstance(c, tuple) for c in channels)
+
+
 def relu_names(channels) -> List[str]:
-    """models.py:140-243 (vgg16_dict / vgg19_dict "R" lists): relu{block}_{index} in network order."""
+    """models.py:140-243 (vgg16_dict / vgg19_dict "R" lists): relu{block}_{index} in network order; nin_dict (:140-172): relu1.."""
+    if is_nin(channels):
+        return [f"relu{i + 1}" for i in range(sum(1 for c in channels if c != "P"))]
     names, block, idx = [], 1, 1
     for c in channels:
         if c == "P":
@@ -96,7 +110,8 @@ def he_init_vgg19(seed: int = 0, channels=VGG19_CHANNELS) -> List[Tuple[torch.Te
     for c in channels:
         if c == "P":
             continue
-        w = torch.randn(c, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))
+        c, ks = c if isinstance(c, tuple) else (c, 3)
+        w = torch.randn(c, cin, ks, ks, generator=g) * math.sqrt(2.0 / (cin * ks * ks))
         b = torch.randn(c, generator=g) * 0.1
         params.append((w, b))
         cin = c
@@ -233,6 +248,7 @@ class OracleNet:
         self.cfg = cfg
         self.params = params
         self.channels = channels
+        self.nin = is_nin(channels)
         self.relu_names = relu_names(channels)
         content_layers = cfg.content_layers.split(",")
         style_layers = cfg.style_layers.split(",")
@@ -268,12 +284,16 @@ class OracleNet:
         for kind, payload in self.seq:
             if kind == "conv":
                 w, b = self.params[payload]
-                x = F.conv2d(x, w, b, padding=1)
+                stride, pad = _CONV_GEOMETRY[w.shape[-1]]
+                x = F.conv2d(x, w, b, stride=stride, padding=pad)
             elif kind == "relu":
                 x = F.relu(x)
                 if taps is not None:
                     taps[self.relu_names[relu_i]] = x
                 relu_i += 1
+            elif kind == "pool" and self.nin:  # models.py:77-80
+                x = (F.max_pool2d(x, 3, 2, 0, ceil_mode=True) if self.cfg.pooling == "max"
+                     else F.avg_pool2d(x, 3, 2, 0, ceil_mode=True))
             elif kind == "pool":
                 x = F.max_pool2d(x, 2, 2) if self.cfg.pooling == "max" else F.avg_pool2d(x, 2, 2)
             else:

@@ -90,6 +90,23 @@ def run_video_case(name, rconfig, rmodels, roptim, workdir, ckpt, T, h, w, style
     print(f"wrote {name}.npz ({(mg.HERE / (name + '.npz')).stat().st_size / 1024:.0f} KiB)")
 
 
+def save_nin_checkpoint(rmodels, path, seed=0):
+    """State dict of the reference's NIN module (models.py:74-113) with the oracle's seeded He-normal weights in its 12 convs."""
+    import torch
+
+    params = O.he_init_vgg19(seed, O.NIN_LAYERS)
+    net = rmodels.NIN("max")
+    sd = net.state_dict()
+    keys = [k for k in sd if k.endswith(".weight")]
+    assert len(keys) == len(params) == 12
+    for (w, b), k in zip(params, keys):
+        assert sd[k].shape == w.shape, (k, sd[k].shape, w.shape)
+        sd[k] = w.clone()
+        sd[k.replace(".weight", ".bias")] = b.clone()
+    torch.save(sd, path)
+    return params
+
+
 def main():
     only = set(sys.argv[1:])  # optional: names of the cases to (re)generate
     rconfig, rloss, rmodels, roptim = mg.import_reference()
@@ -119,6 +136,16 @@ def main():
             # term of the 3-frame pastiche windows is skipped (loss.py:165-166); covariance loss; L-BFGS
             run_video_case("img_vid_avgwin_lbfgs_48x48", ckpt=ckpt19v, T=4, h=48, w=48, style_shapes=[(3, 48, 64)],
                            gfw=3, afw=2, iters=3, optimizer="lbfgs", use_covariance=True, **pre)
+        ckptnin = workdir / "nin-random.pth"
+        save_nin_checkpoint(rmodels, ckptnin)
+        nin_names = O.relu_names(O.NIN_LAYERS)
+        # the layer lists the stock config/scaling-img.json uses for NIN (:32-47)
+        mg.run_case("nin_adam_gram_131x150", ckpt=ckptnin, h=131, w=150, style_hw=[(140, 128)], iters=3, relu_names=nin_names,
+                    style_layers="relu1,relu3,relu5,relu7,relu9,relu11", content_layers="relu8", meta_extra={"arch": "NIN"}, **pre)
+        # taps in front of the pools, the 1000-channel cccp8 layer as content tap, average pooling, covariance loss, L-BFGS
+        mg.run_case("nin_avg_cov_lbfgs_128x144", ckpt=ckptnin, h=128, w=144, style_hw=[(120, 150), (136, 130)], iters=4,
+                    optimizer="lbfgs", pooling="avg", use_covariance=True, style_blend_weights="3,1", relu_names=nin_names,
+                    style_layers="relu3,relu6,relu10", content_layers="relu12", meta_extra={"arch": "NIN"}, **pre)
         ckpt16 = workdir / "vgg16-random.pth"
         mg.save_checkpoint(rmodels, ckpt16, arch="VGG-16")
         common = dict(rconfig=rconfig, rmodels=rmodels, roptim=roptim, workdir=workdir)

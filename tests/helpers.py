@@ -46,10 +46,13 @@ def save_checkpoint(path, seed=0, channels=O.VGG19_CHANNELS):
     """torchvision-style state dict (features.N.weight / bias) with the seeded He-normal VGG-19 (or VGG-16) weights."""
     params = O.he_init_vgg19(seed, channels)
     sd, k, ci = {}, 0, 0
+    nin_index = [0, 2, 4, 7, 9, 11, 14, 16, 18, 22, 24, 26]  # convs inside the reference's NIN.features (models.py:82-111)
     for c in channels:
         if c == "P":
             k += 1
             continue
+        if O.is_nin(channels):
+            k = nin_index[ci]
         w, b = params[ci]
         sd[f"features.{k}.weight"] = w.clone()
         sd[f"features.{k}.bias"] = b.clone()

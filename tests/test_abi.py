@@ -46,4 +46,4 @@ def test_fails_loudly_without_a_gpu():
         model_file = "nin"
         pooling = "max"
     with pytest.raises(ValueError):
-        models.select_model("nin_imagenet.pth", "max", False, False)
+        models.select_model("resnet50.pth", "max", False, False)

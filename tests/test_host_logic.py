@@ -29,7 +29,9 @@ def test_vgg16_family_names_and_pruned_model():
     (w0, b0), (w1, b1) = models._pad_params(raw, [24, 22], [64, 64])
     assert w0.shape == (64, 3, 3, 3) and w1.shape == (64, 64, 3, 3) and float(w1.sum()) == 22 * 24 * 9 and float(b1[22:].abs().sum()) == 0
     assert float(w1[:, 24:].abs().sum()) == 0 and float(w0[24:].abs().sum()) == 0
-    for bad in ("modelzoo/nin.pth", "resnet50.pth"):
+    ch, names = models._architecture("modelzoo/nin.pth", "avg")  # models.py:327-339
+    assert ch is models.NIN_LAYERS and names["R"][-1] == "relu12" and names["C"][3] == "conv2" and len(names["C"]) == 12
+    for bad in ("resnet50.pth",):
         with pytest.raises(ValueError):
             models._architecture(bad, "max")
     with pytest.raises(ValueError):

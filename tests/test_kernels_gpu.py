@@ -360,3 +360,68 @@ def test_lbfgs_matches_torch(lib, n, history, iters):
     assert n_iter.value == iters and halted.value == 0 and hist.value == torch_hist, (n_iter.value, hist.value, torch_hist)
     assert f(xd.cpu()).item() <= f(x0).item()
     assert rel(xd, p.detach()) < 1e-4, f"lbfgs rel err {rel(xd, p.detach())}"
+
+
+# ---- NIN layer shapes (models.py:74-113): direct convolutions and the 3x3 / 2 ceil_mode pools (csrc/conv_gen.cu) ----------------
+@pytest.mark.parametrize("cin,cout,ks,stride,pad,h,w,img", [(3, 96, 11, 4, 0, 67, 90, True), (3, 128, 11, 4, 0, 131, 150, True),
+                                                            (96, 256, 5, 1, 2, 15, 18, False), (128, 256, 5, 1, 2, 33, 9, False)])
+def test_direct_conv_forward_and_input_gradient(lib, cin, cout, ks, stride, pad, h, w, img):
+    g = torch.Generator().manual_seed(cin + h)
+    x = torch.randn(1, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, ks, ks, generator=g) * (2.0 / (cin * ks * ks)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    xr = x.double().requires_grad_(True)
+    ref = F.relu(F.conv2d(xr, wt.double(), b.double(), stride=stride, padding=pad))
+    oh, ow = ref.shape[2], ref.shape[3]
+    out = torch.empty(1, oh, ow, cout, device="cuda")
+    xin = x.cuda().contiguous() if img else nhwc(x).cuda()
+    _lib.check(lib.maua_conv_direct_fwd(_lib.ptr(xin), int(img), _lib.ptr(wt.cuda()), _lib.ptr(b.cuda()), _lib.ptr(out), 1, h, w, cin,
+                                        cout, ks, stride, pad, 1, 0, _lib.stream_ptr()), "conv_direct_fwd")
+    torch.cuda.synchronize()
+    assert rel(nchw(out), ref.float()) < 2e-6
+    # input gradient for a random output gradient
+    go = torch.randn(1, cout, oh, ow, generator=g)
+    pre = F.conv2d(xr, wt.double(), b.double(), stride=stride, padding=pad)
+    (gref,) = torch.autograd.grad(pre, xr, go.double())
+    god = nhwc(go).cuda()
+    if img:
+        gx = torch.empty(1, cin, h, w, device="cuda")
+        _lib.check(lib.maua_conv_direct_dgrad_image(_lib.ptr(god), _lib.ptr(wt.cuda()), _lib.ptr(gx), 1, h, w, cout, ks, stride,
+                                                    _lib.stream_ptr()), "conv_direct_dgrad_image")
+        torch.cuda.synchronize()
+        assert rel(gx, gref.float()) < 2e-6
+    else:
+        wf = torch.empty(cin, cout, ks, ks, device="cuda")
+        _lib.check(lib.maua_conv_direct_flip_weights(_lib.ptr(wt.cuda()), _lib.ptr(wf), cout, cin, ks, _lib.stream_ptr()))
+        gx = torch.empty(1, h, w, cin, device="cuda")
+        _lib.check(lib.maua_conv_direct_fwd(_lib.ptr(god), 0, _lib.ptr(wf), C.c_void_p(0), _lib.ptr(gx), 1, oh, ow, cout, cin, ks, 1,
+                                            ks - 1 - pad, 0, 0, _lib.stream_ptr()), "conv_direct dgrad")
+        torch.cuda.synchronize()
+        assert rel(nchw(gx), gref.float()) < 2e-6
+
+
+@pytest.mark.parametrize("avg", [0, 1])
+@pytest.mark.parametrize("c,h,w", [(96, 30, 37), (128, 15, 15), (256, 7, 8), (64, 2, 5), (32, 3, 4)])
+def test_pool3x3_ceil_forward_backward(lib, avg, c, h, w):
+    """MaxPool2d / AvgPool2d((3,3),(2,2),(0,0), ceil_mode=True) and their backward with the ReLU mask of the producer folded in
+    (models.py:77-80); ties: quantised inputs make equal maxima frequent, torch's CPU kernel is the arbiter."""
+    g = torch.Generator().manual_seed(c * 7 + h)
+    x = F.relu(torch.round(torch.randn(1, c, h, w, generator=g) * 2) / 2)
+    xr = x.clone().requires_grad_(True)
+    pool = (F.avg_pool2d if avg else F.max_pool2d)
+    y = pool(F.relu(xr), 3, 2, 0, ceil_mode=True)
+    ph, pw = y.shape[2], y.shape[3]
+    yd = torch.empty(1, ph, pw, c, device="cuda")
+    xd = nhwc(x).cuda()
+    _lib.check(lib.maua_pool3x3_fwd(_lib.ptr(xd), _lib.ptr(yd), 1, h, w, c, avg, _lib.stream_ptr()), "pool3 fwd")
+    torch.cuda.synchronize()
+    assert rel(nchw(yd), y.detach()) < 1e-6
+    gy = torch.randn(1, c, ph, pw, generator=g)
+    add = torch.randn(1, c, h, w, generator=g)
+    (gref,) = torch.autograd.grad(y, xr, gy)
+    gref = gref + add * (x > 0)
+    gx = torch.empty(1, h, w, c, device="cuda")
+    _lib.check(lib.maua_pool3x3_bwd(_lib.ptr(xd), _lib.ptr(nhwc(gy).cuda()), _lib.ptr(nhwc(add).cuda()), _lib.ptr(gx), 1, h, w, c, avg,
+                                    0, _lib.stream_ptr()), "pool3 bwd")
+    torch.cuda.synchronize()
+    assert rel(nchw(gx), gref) < 1e-6

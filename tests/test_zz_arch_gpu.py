@@ -6,6 +6,11 @@ the UNMODIFIED reference (tests/golden/make_golden_arch.py) and the CPU oracle:
                                89, 111, 184, 276, 228, 512 channels), run zero-padded to tileable channel counts with the
                                loss normalisations on the real counts (models.padded_channels, maua_net_desc::norm_channels)
   vgg16p_cov_lbfgs_64x80 ..... the same stack with the covariance loss, two blended styles, L-BFGS
+  nin_adam_gram_131x150 ...... `--model_file *nin*` (models.py:74-113, :327-339): 11x11 / 4 image layer and 5x5 layer as direct
+                               fp32 convolutions (csrc/conv_gen.cu), 1x1 and 3x3 layers on the tensor core, 3x3 / 2 ceil_mode
+                               pools, the style / content layers of the stock config/scaling-img.json
+  nin_avg_cov_lbfgs_128x144 .. NIN with average pooling, covariance loss, two styles, taps in front of the pools, the 1000-channel
+                               cccp8 layer (padded to 1024) as content tap
   vid_frame_temporal_64x80 ... one vid_img frame (style.py:276-294): optim.set_temporal_targets with a flow-reliability map,
                                then optimize(content, styles, init, n, args, net, losses) -- the weighted temporal
                                ContentLoss on the image (loss.py:46-54) pinned to the reference's own numbers
@@ -23,7 +28,8 @@ from helpers import O, golden_inputs, load_golden, make_args, rel, save_checkpoi
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["vgg16_adam_gram_72x88", "vgg16p_adam_gram_72x88", "vgg16p_cov_lbfgs_64x80", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96",
+CASES = ["vgg16_adam_gram_72x88", "vgg16p_adam_gram_72x88", "vgg16p_cov_lbfgs_64x80", "nin_adam_gram_131x150",
+         "nin_avg_cov_lbfgs_128x144", "vid_frame_temporal_64x80", "vgg19_taps_lbfgs_80x64", "vgg19_deep_taps_avg_64x96",
          "vgg19_same_layer_taps_64x64"]
 
 
@@ -34,6 +40,8 @@ CASES = ["vgg16_adam_gram_72x88", "vgg16p_adam_gram_72x88", "vgg16p_cov_lbfgs_64
 BOUNDS = {
     "vgg16_adam_gram_72x88": (5e-2, 40.0),        # 3.0e-2, 56.0 dB
     "vgg16p_adam_gram_72x88": (5e-2, 40.0),       # measured on B200: see profiles/r02_f4_parity.txt
+    "nin_adam_gram_131x150": (5e-2, 40.0),
+    "nin_avg_cov_lbfgs_128x144": (2e-2, 45.0),    # average pooling: no arg-max flips; optimisation in exact mode (EXACT_OPTIMIZE)
     "vgg16p_cov_lbfgs_64x80": (5e-2, 45.0),       # optimisation in exact-arithmetic mode, see EXACT_OPTIMIZE
     "vid_frame_temporal_64x80": (4e-2, 40.0),     # 2.2e-2, 56.1 dB
     "vgg19_taps_lbfgs_80x64": (4e-2, 20.0),       # 2.5e-2, 34.7 dB (fp32 leaps by 7.5 grey levels rms in iteration 3, the
@@ -47,7 +55,7 @@ BOUNDS = {
 # section 2): depending on the sign the noise gives y.s, the pair is dropped and the step is the raw gradient.  On this case the
 # B200 realisation drops it (11 dB; the CPU emulation of the same roundings keeps it: 50 dB), so the optimisation is pinned in
 # the exact-arithmetic mode, where it has to follow the reference closely.
-EXACT_OPTIMIZE = {"vgg16p_cov_lbfgs_64x80"}
+EXACT_OPTIMIZE = {"vgg16p_cov_lbfgs_64x80", "nin_avg_cov_lbfgs_128x144"}
 
 
 def temporal_inputs(meta):
@@ -64,8 +72,9 @@ def setup_case(name, tmp_path):
 
     z, meta = load_golden(name)
     arch = meta.get("arch", "VGG-19")
-    channels = {"VGG-19": O.VGG19_CHANNELS, "VGG-16": O.VGG16_CHANNELS, "VGG-16p": O.VGG16P_CHANNELS}[arch]
-    path = tmp_path / {"VGG-19": "vgg19-random.pth", "VGG-16": "vgg16-random.pth", "VGG-16p": "vgg16-prune-random.pth"}[arch]
+    channels = {"VGG-19": O.VGG19_CHANNELS, "VGG-16": O.VGG16_CHANNELS, "VGG-16p": O.VGG16P_CHANNELS, "NIN": O.NIN_LAYERS}[arch]
+    path = tmp_path / {"VGG-19": "vgg19-random.pth", "VGG-16": "vgg16-random.pth", "VGG-16p": "vgg16-prune-random.pth",
+                       "NIN": "nin-random.pth"}[arch]
     params = save_checkpoint(path, channels=channels)
     over = dict(meta["over"])
     args = make_args(path, tmp_path, **over)
