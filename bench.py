@@ -315,13 +315,22 @@ LBFGS_LAUNCHES = 4  # multi-dot pass, partial reduce, scalar recurrences, direct
 class Job:
     """One image being optimised exactly as optim.optimize drives it (2 eager rounds, then CUDA-graph replays)."""
 
-    def __init__(self, size, optimizer, dev, local_rank, rank=0, covariance=False, history_prefill=100, multidevice=None):
+    def __init__(self, size, optimizer, dev, local_rank, rank=0, covariance=False, history_prefill=100, multidevice=None,
+                 arch="vgg19"):
         from maua_style_b200 import models, optim, synthetic as O
 
         self.tmp = tempfile.mkdtemp(prefix=f"maua_bench_{rank}_")
-        ckpt = Path(self.tmp) / "vgg19-random.pth"
-        O.save_random_checkpoint(ckpt)
         over = dict(optimizer=optimizer, gpu=str(local_rank))
+        if arch == "prune":  # models.py:136, :249-258: the channel-pruned VGG-16 (stock schedule above 2656 px)
+            ckpt = Path(self.tmp) / "vgg16-prune-random.pth"
+            O.save_random_checkpoint(ckpt, channels=models.channel_list["VGG-16p"])
+        elif arch == "nin":  # models.py:74-113; layer lists of config/scaling-img.json:32-47 (stock schedule above 4096 px)
+            ckpt = Path(self.tmp) / "nin-random.pth"
+            O.save_random_checkpoint(ckpt, channels=models.NIN_LAYERS)
+            over.update(style_layers="relu1,relu3,relu5,relu7,relu9,relu11", content_layers="relu8")
+        else:
+            ckpt = Path(self.tmp) / "vgg19-random.pth"
+            O.save_random_checkpoint(ckpt)
         if covariance:  # BASELINE.json configs[2]: covariance loss, 2 blended styles of different aspect (area-matched)
             over.update(use_covariance=True, style_blend_weights="3,1")
         if multidevice:
@@ -390,9 +399,9 @@ def conv_summary(prof):
     return conv, ms, flops, sum(r["ms"] for r in prof)
 
 
-def side_leg(size, optimizer, dev, K, W, pk, covariance=False, prefill=100):
+def side_leg(size, optimizer, dev, K, W, pk, covariance=False, prefill=100, arch="vgg19"):
     """A bounded extra measurement of another configuration: it/s (device-resident, CUDA events) + its conv roofline."""
-    job = Job(size, optimizer, dev, dev.index, covariance=covariance, history_prefill=prefill)
+    job = Job(size, optimizer, dev, dev.index, covariance=covariance, history_prefill=prefill, arch=arch)
     ms = job.timed(K, W)
     conv, conv_ms, conv_flops, feval_ms = conv_summary(job.conv_profile())
     tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -402,10 +411,56 @@ def side_leg(size, optimizer, dev, K, W, pk, covariance=False, prefill=100):
     if covariance:
         out["styles"] = 2
         out["loss"] = "covariance (--use_covariance), blend 3:1"
+    if arch != "vgg19":
+        out["model"] = {"prune": "channel-pruned VGG-16 (zero-padded to tileable channel counts)",
+                        "nin": "NIN (11x11/4 and 5x5 layers as direct fp32 convolutions, 1x1 / 3x3 layers on the tensor core)"}[arch]
+        out["kernel_breakdown_ms"] = {}
+        for r in job.conv_profile():
+            out["kernel_breakdown_ms"][r["name"]] = round(out["kernel_breakdown_ms"].get(r["name"], 0.0) + r["ms"], 4)
     job.close()
     del job
     torch.cuda.empty_cache()
     return out
+
+
+def video_window_leg(dev, size, frames, K, W):
+    """One img_vid window (optim.py:113-170): `frames` pastiche frames as ONE batch through the network -- per-frame static
+    Grams, the [frames*C, frames*C] dynamic Gram (one SYRK over the side-by-side features), Adam.  it/s counts window
+    iterations (each is `frames` forward + backward passes)."""
+    from maua_style_b200 import models, optim, synthetic as O
+
+    tmp = tempfile.mkdtemp(prefix="maua_bench_vid_")
+    ckpt = Path(tmp) / "vgg19-random.pth"
+    O.save_random_checkpoint(ckpt)
+    a = O.reference_args(ckpt, tmp, optimizer="adam", gpu=str(dev.index), transfer_type="img_vid", gram_frame_window=frames,
+                         avg_frame_window=-1)
+    net, losses = models.load_model(a)
+    content = O.synthetic_image(size, size, seed=1, smooth=True).to(dev)
+    video = torch.cat([O.synthetic_image(size, size, seed=20 + f, smooth=(f % 2 == 0)) for f in range(frames + 1)]).to(dev)
+    optim.set_content_targets(net, content, a)
+    optim.set_style_video_targets(net, [video], a)
+    for m in losses:
+        m.mode = "loss"
+    pastiche = torch.cat([O.synthetic_image(size, size, seed=40 + f) * 0.25 for f in range(frames)]).to(dev).contiguous()
+    opt = optim.PixelOptimizer(pastiche, "adam", lr=1.0)
+    up = torch.zeros(net._n_slots, device=dev)
+    up[net._live_slots()] = 1.0
+    step = optim.GraphedIteration(net, pastiche, opt, up)
+    for _ in range(W + 3):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    opt.close()
+    return {"workload": f"one img_vid window: {frames} frames of {size}x{size}, style video of {frames + 1} frames, static + dynamic "
+                        f"([{frames}*C]^2) Gram losses, Adam", "value": K / (ms * 1e-3), "unit": "window it/s",
+            "frame_evals_per_sec": frames * K / (ms * 1e-3), "ms_per_step": ms / K, "steps": K, "warmup": W,
+            "cuda_graph": step.graph is not None}
 
 
 def batch_job(dev, info, images_per_gpu, iters, size=1024):
@@ -616,6 +671,10 @@ def run_ours(args):
                                  "2048": guarded(side_leg, 2048, args.optimizer, dev, 10, 3, pk)}
                 line["adam_1024"] = guarded(side_leg, 1024, "adam", dev, 30, 5, pk)
                 line["covariance_2styles_1024"] = guarded(side_leg, 1024, args.optimizer, dev, 30, 5, pk, covariance=True)
+                # the other backbones of the stock schedule (config/scaling-img.json: "prune" above 2656 px, "nin" above 4096 px)
+                line["pruned_vgg16_2048_adam"] = guarded(side_leg, 2048, "adam", dev, 10, 3, pk, arch="prune")
+                line["nin_4096_adam"] = guarded(side_leg, 4096, "adam", dev, 5, 2, pk, arch="nin")
+                line["img_vid_window"] = guarded(video_window_leg, dev, 512, 4, 10, 3)
                 if torch.cuda.device_count() >= 2:
                     line["multidevice_2048"] = guarded(multidevice_leg, "0,1", 2048, 10, 3)
         if world == 1 and not args.no_cpu_baseline:

@@ -8,8 +8,8 @@ Same class names, constructor arguments, attributes (`mode`, `loss`, `target`, `
 Inside a `models.B200Net` the modules are descriptors: the network reads their mode / strength / target and runs
 the fused plan (one SYRK per style layer, loss gradients folded into the dgrad kernels).  Called on their own
 (`module(feature_map)`) they run the same kernels one at a time through the per-kernel C ABI, so they remain
-usable as drop-in nn.Modules.  Only batch size 1 is supported (the reference's B > 1 video-style semantics are
-out of scope).
+usable as drop-in nn.Modules (batch size 1; the B > 1 window semantics of img_vid live in the network path,
+maua_style_b200/window.py).
 """
 from __future__ import annotations
 

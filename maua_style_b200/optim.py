@@ -26,6 +26,28 @@ import torch.nn as nn
 from . import _lib, models
 
 
+class _Trace:
+    """MAUA_TRACE=1: wall-clock phases of an optimize() call (device synchronised at every mark) on stderr -- where the time of
+    a whole multi-resolution job goes besides the iterations themselves."""
+
+    def __init__(self, what: str):
+        import os
+        import time
+
+        self.on = os.environ.get("MAUA_TRACE", "0") == "1"
+        self.what, self.t, self.time = what, 0.0, time
+        if self.on:
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def mark(self, label: str) -> None:
+        if self.on:
+            torch.cuda.synchronize()
+            now = self.time.perf_counter()
+            print(f"[maua trace] {self.what}: {label} {1e3 * (now - self.t):.2f} ms", file=sys.stderr, flush=True)
+            self.t = now
+
+
 def set_content_targets(net, content_image, args=None):
     """optim.py:22-32."""
     for i in net.content_losses:
@@ -357,10 +379,12 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
     (maua_style_b200/style.py keeps the whole multi-resolution schedule on the device)."""
     if "_vid" in getattr(args, "transfer_type", "img_img"):
         return _optimize_windows(content, styles, init, num_iters, args, net, losses)
+    tr = _Trace(f"optimize {tuple(init.shape[2:])}")
     if net is None or losses is None:
         set_model_args(args, max(*init.shape))
         net, losses = models.load_model(args)
     device = net.device
+    tr.mark("load_model")
 
     import os
 
@@ -372,6 +396,7 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
     set_style_targets(net, styles, args)  # (the network moves host tensors itself; identity is kept for the target cache)
     for mod in losses:
         mod.mode = "loss"
+    tr.mark("target capture")
 
     # optim.py:176-178 (only once, strengths are not reset)
     if getattr(args, "normalize_weights", False):
@@ -393,6 +418,7 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
     live = net._live_slots()  # modules in loss mode with a target (a shape mismatch just contributes 0, loss.py:44)
     state = _loop_state(net, init, args, live)
     pastiche, opt, iteration = state.pastiche, state.opt, state.iteration
+    tr.mark("loop state")
 
     print_iter = int(getattr(args, "print_iter", 0) or 0)
     save_iter = int(getattr(args, "save_iter", 0) or 0)
@@ -406,6 +432,7 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
         if want_print:
             total = float(net._loss_vec[live].sum())  # the losses of the image before the update, like optim.py:228-229
             print(f"Iteration {it} / {args.num_iters}, Loss: {total}")
+    tr.mark(f"{evals} iterations")
     for mod in losses:
         mod.loss = 0
     if state.cached:

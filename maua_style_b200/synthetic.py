@@ -16,7 +16,7 @@ from pathlib import Path
 import torch
 import torch.nn.functional as F
 
-from .models import channel_list
+from .models import NIN_FEATURE_INDEX, NIN_LAYERS, channel_list
 
 BGR_MEAN = (103.939, 116.779, 123.68)  # load.py:30
 
@@ -39,7 +39,8 @@ def he_init(seed: int = 0, channels=None):
     for c in channels:
         if c == "P":
             continue
-        w = torch.randn(c, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))
+        c, ks = c if isinstance(c, tuple) else (c, 3)  # NIN_LAYERS entries are (channels, kernel size)
+        w = torch.randn(c, cin, ks, ks, generator=g) * math.sqrt(2.0 / (cin * ks * ks))
         b = torch.randn(c, generator=g) * 0.1
         params.append((w, b))
         cin = c
@@ -55,6 +56,8 @@ def save_random_checkpoint(path, seed: int = 0, channels=None):
         if c == "P":
             k += 1
             continue
+        if channels is NIN_LAYERS:
+            k = NIN_FEATURE_INDEX[ci]  # position of the conv inside the reference's NIN.features (models.py:82-111)
         w, b = params[ci]
         sd[f"features.{k}.weight"] = w.clone()
         sd[f"features.{k}.bias"] = b.clone()

@@ -375,7 +375,8 @@ def test_direct_conv_forward_and_input_gradient(lib, cin, cout, ks, stride, pad,
     oh, ow = ref.shape[2], ref.shape[3]
     out = torch.empty(1, oh, ow, cout, device="cuda")
     xin = x.cuda().contiguous() if img else nhwc(x).cuda()
-    _lib.check(lib.maua_conv_direct_fwd(_lib.ptr(xin), int(img), _lib.ptr(wt.cuda()), _lib.ptr(b.cuda()), _lib.ptr(out), 1, h, w, cin,
+    wd, bd = wt.cuda(), b.cuda()  # (named: a temporary's block would be handed to the next temporary while the kernel is pending)
+    _lib.check(lib.maua_conv_direct_fwd(_lib.ptr(xin), int(img), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(out), 1, h, w, cin,
                                         cout, ks, stride, pad, 1, 0, _lib.stream_ptr()), "conv_direct_fwd")
     torch.cuda.synchronize()
     assert rel(nchw(out), ref.float()) < 2e-6
@@ -386,13 +387,13 @@ def test_direct_conv_forward_and_input_gradient(lib, cin, cout, ks, stride, pad,
     god = nhwc(go).cuda()
     if img:
         gx = torch.empty(1, cin, h, w, device="cuda")
-        _lib.check(lib.maua_conv_direct_dgrad_image(_lib.ptr(god), _lib.ptr(wt.cuda()), _lib.ptr(gx), 1, h, w, cout, ks, stride,
+        _lib.check(lib.maua_conv_direct_dgrad_image(_lib.ptr(god), _lib.ptr(wd), _lib.ptr(gx), 1, h, w, cout, ks, stride,
                                                     _lib.stream_ptr()), "conv_direct_dgrad_image")
         torch.cuda.synchronize()
         assert rel(gx, gref.float()) < 2e-6
     else:
         wf = torch.empty(cin, cout, ks, ks, device="cuda")
-        _lib.check(lib.maua_conv_direct_flip_weights(_lib.ptr(wt.cuda()), _lib.ptr(wf), cout, cin, ks, _lib.stream_ptr()))
+        _lib.check(lib.maua_conv_direct_flip_weights(_lib.ptr(wd), _lib.ptr(wf), cout, cin, ks, _lib.stream_ptr()))
         gx = torch.empty(1, h, w, cin, device="cuda")
         _lib.check(lib.maua_conv_direct_fwd(_lib.ptr(god), 0, _lib.ptr(wf), C.c_void_p(0), _lib.ptr(gx), 1, oh, ow, cout, cin, ks, 1,
                                             ks - 1 - pad, 0, 0, _lib.stream_ptr()), "conv_direct dgrad")
@@ -421,7 +422,8 @@ def test_pool3x3_ceil_forward_backward(lib, avg, c, h, w):
     (gref,) = torch.autograd.grad(y, xr, gy)
     gref = gref + add * (x > 0)
     gx = torch.empty(1, h, w, c, device="cuda")
-    _lib.check(lib.maua_pool3x3_bwd(_lib.ptr(xd), _lib.ptr(nhwc(gy).cuda()), _lib.ptr(nhwc(add).cuda()), _lib.ptr(gx), 1, h, w, c, avg,
+    gyd, addd = nhwc(gy).cuda(), nhwc(add).cuda()
+    _lib.check(lib.maua_pool3x3_bwd(_lib.ptr(xd), _lib.ptr(gyd), _lib.ptr(addd), _lib.ptr(gx), 1, h, w, c, avg,
                                     0, _lib.stream_ptr()), "pool3 bwd")
     torch.cuda.synchronize()
     assert rel(nchw(gx), gref) < 1e-6
