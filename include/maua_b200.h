@@ -133,6 +133,15 @@ MAUA_API int maua_pool2x2_fwd(const float* x, float* y, int b, int h, int w, int
 MAUA_API int maua_pool2x2_bwd(const float* x, const float* gy, const float* addend, float* gx, int b, int h, int w,
                               int c, int avg, int round_tf32, maua_stream_t stream);
 
+/* k x k / stride 1 / pad k/2 convolution for k = 1, 3, 5 through the same tcgen05 implicit-GEMM kernel (k = 1: NIN's "cccp"
+ * layers, models.py:85-110; k = 5: NIN conv2, models.py:90 -- a halo of 2 pixels, 5 box loads per channel chunk, 5 vertical taps
+ * per box).  wg from maua_prep_conv_weights_k: forward [cout][k*k*cin] (tap-major), dgrad = rotated + transposed, optionally
+ * TF32-rounded.  With the dgrad weights and cin / cout swapped the same call is the input gradient. */
+MAUA_API int maua_prep_conv_weights_k(const float* w, float* out, int cout, int cin, int ks, int dgrad, int round_tf32,
+                                      maua_stream_t stream);
+MAUA_API int maua_conv_kxk_fwd(const float* x, const float* wg, const float* bias, float* y, int b, int h, int w, int cin,
+                               int cout, int ks, int relu, int impl, maua_stream_t stream);
+
 /* NIN backbone (models.py:74-113): the layer shapes that are not 3x3 / pad 1 or 1x1 GEMMs, as direct fp32 convolutions.
  * out NHWC [b][oh][ow][cout] = act(conv(in, w OIHW [cout][cin][ks][ks], stride, pad) + bias), oh = (h + 2 pad - ks) / stride + 1;
  * `in` is NHWC [b][h][w][cin], or the NCHW image when in_nchw (conv1: 11x11 / stride 4, models.py:83; conv2: 5x5 / pad 2, :90). */

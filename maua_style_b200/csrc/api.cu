@@ -116,6 +116,24 @@ MAUA_API int maua_conv3x3_fwd(const float* x, const float* wg, const float* bias
     return conv_dispatch(a, impl, (cudaStream_t)stream);
 }
 
+MAUA_API int maua_prep_conv_weights_k(const float* w, float* out, int cout, int cin, int ks, int dgrad, int round_tf32,
+                                      maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(w && out && cout > 0 && cin > 0 && (ks == 1 || ks == 3 || ks == 5), "maua_prep_conv_weights_k: bad arguments");
+    return prep_weights_launch(w, out, cout, cin, dgrad, round_tf32, (cudaStream_t)stream, ks * ks);
+}
+MAUA_API int maua_conv_kxk_fwd(const float* x, const float* wg, const float* bias, float* y, int b, int h, int w, int cin,
+                               int cout, int ks, int relu, int impl, maua_stream_t stream) {
+    MAUA_ENTRY_GUARD();
+    MAUA_REQUIRE(x && wg && y && (ks == 1 || ks == 3 || ks == 5), "maua_conv_kxk_fwd: bad arguments");
+    MAUA_REQUIRE(impl != MAUA_IMPL_FP32 || ks != 5, "maua_conv_kxk_fwd: the exact-arithmetic 5x5 convolution is maua_conv_direct_fwd");
+    ConvArgs a;
+    a.B = b; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ntaps = ks * ks;
+    a.in = x; a.wg = wg;
+    a.ep.out = y; a.ep.bias = bias; a.ep.relu = relu; a.ep.round = impl == MAUA_IMPL_FP32 ? 0 : 1;
+    return conv_dispatch(a, impl, (cudaStream_t)stream);
+}
+
 MAUA_API int maua_conv3x3_dgrad(const float* gy, const float* wd, float* gx, int b, int h, int w, int cout, int cin,
                                 const float* mask_src, const float* aux_f, const float* aux_d,
                                 const float* aux_bias, const float* cont_f, const float* cont_t,

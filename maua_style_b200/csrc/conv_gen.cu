@@ -186,6 +186,80 @@ conv_gen_dgrad_img_kernel(const float* __restrict__ gout /*NHWC [B][OH][OW][Cout
     }
 }
 
+// ---- the image layer as a GEMM (product path): im2col of the NCHW image, pointwise tcgen05 GEMM, and col2im for its gradient ----
+// A[p][k], p = output position, k = c * ks^2 + ky * ks + kx (the OIHW order of a weight row), zero-padded to KP columns
+__global__ void im2col_img_kernel(const float* __restrict__ img, float* __restrict__ A, int H, int W, int ks, int stride, int OH,
+                                  int OW, int K, int KP, int do_round) {
+    const long total = (long)OH * OW * KP;
+    const int kk = ks * ks;
+    const long HW = (long)H * W;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = i % KP;
+        const long p = i / KP;
+        float v = 0.f;
+        if (k < K) {
+            const int ox = p % OW, oy = p / OW;
+            const int c = k / kk, r = k - c * kk;
+            const int ky = r / ks, kx = r - ky * ks;
+            v = __ldg(img + c * HW + (long)(oy * stride + ky) * W + ox * stride + kx);
+            if (do_round) v = round_tf32(v);
+        }
+        A[i] = v;
+    }
+}
+
+// gimg[c][y][x] = sum over the output positions whose window covers (y, x) of T[position][c * ks^2 + ky * ks + kx], + image tail
+__global__ void __launch_bounds__(256)
+col2im_img_kernel(const float* __restrict__ T, float* __restrict__ gimg, int H, int W, int ks, int stride, int OH, int OW, int KP,
+                  ImageTail tail) {
+    const long HW = (long)H * W;
+    const int kk = ks * ks;
+    const float tvc = tail.tv_coef ? *tail.tv_coef : 0.f;
+    const float tpc = tail.temp_coef ? *tail.temp_coef : 0.f;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < HW; p += (long)gridDim.x * blockDim.x) {
+        const int x = p % W, y = p / W;
+        float acc[3] = {0.f, 0.f, 0.f};
+        if (T) {
+            const int oy_lo = y - ks + 1 > 0 ? (y - ks + 1 + stride - 1) / stride : 0;
+            const int ox_lo = x - ks + 1 > 0 ? (x - ks + 1 + stride - 1) / stride : 0;
+            for (int oy = oy_lo; oy < OH && oy * stride <= y; ++oy)
+                for (int ox = ox_lo; ox < OW && ox * stride <= x; ++ox) {
+                    const float* t = T + ((long)oy * OW + ox) * KP + (y - oy * stride) * ks + (x - ox * stride);
+                    acc[0] += __ldg(t); acc[1] += __ldg(t + kk); acc[2] += __ldg(t + 2 * kk);
+                }
+        }
+        const float wt = (tail.temp_coef && tail.temp_weights) ? tail.temp_weights[p] : 1.f;
+        for (int ci = 0; ci < 3; ++ci) {
+            const long idx = ci * HW + p;
+            float v = acc[ci];
+            if (tail.tv_coef) {
+                const float c0 = tail.img[idx];
+                float s = 0.f;
+                if (y > 0) s += (float)((c0 - tail.img[idx - W] > 0.f) - (c0 - tail.img[idx - W] < 0.f));
+                if (y + 1 < H) s -= (float)((tail.img[idx + W] - c0 > 0.f) - (tail.img[idx + W] - c0 < 0.f));
+                if (x > 0) s += (float)((c0 - tail.img[idx - 1] > 0.f) - (c0 - tail.img[idx - 1] < 0.f));
+                if (x + 1 < W) s -= (float)((tail.img[idx + 1] - c0 > 0.f) - (tail.img[idx + 1] - c0 < 0.f));
+                v += tvc * s;
+            }
+            if (tail.temp_coef) v += tpc * wt * (tail.img[idx] * wt - tail.temp_target[idx]);
+            gimg[idx] = v;
+        }
+    }
+}
+
+// GEMM weights of the image layer: wg[co][k] = w[co][k] (k < K, else 0) and its transpose wt[k][co], TF32-rounded
+__global__ void im2col_weights_kernel(const float* __restrict__ w, float* __restrict__ wg, float* __restrict__ wt, int Cout, int K,
+                                      int KP) {
+    const long total = (long)Cout * KP;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = i % KP;
+        const int co = i / KP;
+        const float v = k < K ? round_tf32(w[(long)co * K + k]) : 0.f;
+        wg[i] = v;
+        wt[(long)k * Cout + co] = v;
+    }
+}
+
 // [Cout][Cin][ks][ks] -> [Cin][Cout][ks][ks] rotated by 180 degrees: the weights with which the stride-1 input gradient is again a
 // direct convolution (pad' = ks - 1 - pad)
 __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int ks) {
@@ -230,44 +304,57 @@ __global__ void pool3_fwd_kernel(const float4* __restrict__ x, float4* __restric
 }
 
 // gx[h][w][c] = (sum over the <= 2 x 2 windows that contain (h, w) of: gy[window] if (h, w) is the window's arg-max [max] or
-// gy[window] / window size [avg]) * (x > 0) [+ addend * (x > 0)].  Gather form: no atomics, deterministic.
-__global__ void pool3_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ addend,
-                                 float* __restrict__ gx, int B, int H, int W, int C, int PH, int PW, int avg, int do_round) {
-    const long total = (long)B * H * W * C;
+// gy[window] / window size [avg]) * (x > 0) [+ addend * (x > 0)].  Gather form: no atomics, deterministic.  Four channels per thread.
+__global__ void pool3_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, const float4* __restrict__ addend,
+                                 float4* __restrict__ gx, int B, int H, int W, int C4, int PH, int PW, int avg, int do_round) {
+    const long total = (long)B * H * W * C4;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = i % C;
-        long r = i / C;
+        const int c = i % C4;
+        long r = i / C4;
         const int w = r % W;
         r /= W;
         const int h = r % H;
         const int b = r / H;
-        const float xv = x[i];
-        float g = 0.f;
-        if (xv > 0.f) {
+        const float4 xv = x[i];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xv.x > 0.f || xv.y > 0.f || xv.z > 0.f || xv.w > 0.f) {
             for (int ph = max((h - 1) / 2, 0); ph < PH && 2 * ph <= h; ++ph) {
                 if (h >= 2 * ph + 3) continue;
                 for (int pw = max((w - 1) / 2, 0); pw < PW && 2 * pw <= w; ++pw) {
                     if (w >= 2 * pw + 3) continue;
-                    const float gv = gy[(((long)b * PH + ph) * PW + pw) * C + c];
+                    const float4 gv = gy[(((long)b * PH + ph) * PW + pw) * C4 + c];
                     const int h1 = min(2 * ph + 3, H), w1 = min(2 * pw + 3, W);
                     if (avg) {
-                        g += gv / (float)((h1 - 2 * ph) * (w1 - 2 * pw));
+                        const float inv = 1.f / (float)((h1 - 2 * ph) * (w1 - 2 * pw));
+                        g.x += gv.x * inv; g.y += gv.y * inv; g.z += gv.z * inv; g.w += gv.w * inv;
                     } else {
-                        // is (h, w) the first maximum of this window?
-                        bool win = true;
-                        for (int hh = 2 * ph; hh < h1 && win; ++hh)
+                        // is (h, w) the first maximum of this window? (per channel)
+                        bool wx = true, wy = true, wz = true, ww_ = true;
+                        for (int hh = 2 * ph; hh < h1; ++hh)
                             for (int ww = 2 * pw; ww < w1; ++ww) {
-                                const float v = x[(((long)b * H + hh) * W + ww) * C + c];
-                                const bool before = hh < h || (hh == h && ww < w);
-                                if (before ? v >= xv : v > xv) { win = false; break; }
+                                if (hh == h && ww == w) continue;
+                                const float4 v = x[(((long)b * H + hh) * W + ww) * C4 + c];
+                                if (hh < h || (hh == h && ww < w)) {
+                                    wx = wx && !(v.x >= xv.x); wy = wy && !(v.y >= xv.y); wz = wz && !(v.z >= xv.z); ww_ = ww_ && !(v.w >= xv.w);
+                                } else {
+                                    wx = wx && !(v.x > xv.x); wy = wy && !(v.y > xv.y); wz = wz && !(v.z > xv.z); ww_ = ww_ && !(v.w > xv.w);
+                                }
                             }
-                        if (win) g += gv;
+                        if (wx) g.x += gv.x;
+                        if (wy) g.y += gv.y;
+                        if (wz) g.z += gv.z;
+                        if (ww_) g.w += gv.w;
                     }
                 }
             }
-            if (addend) g += addend[i];
+            if (addend) {
+                const float4 a = addend[i];
+                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            }
         }
-        gx[i] = do_round ? round_tf32(g) : g;
+        g.x = xv.x > 0.f ? g.x : 0.f; g.y = xv.y > 0.f ? g.y : 0.f; g.z = xv.z > 0.f ? g.z : 0.f; g.w = xv.w > 0.f ? g.w : 0.f;
+        if (do_round) { g.x = round_tf32(g.x); g.y = round_tf32(g.y); g.z = round_tf32(g.z); g.w = round_tf32(g.w); }
+        gx[i] = g;
     }
 }
 
@@ -314,6 +401,33 @@ int conv_gen_dgrad_img_launch(const float* gout, const float* w, float* gimg, in
     return MAUA_OK;
 }
 
+int im2col_img_launch(const float* img, float* A, int H, int W, int ks, int stride, int KP, int do_round, cudaStream_t st) {
+    MAUA_REQUIRE(img && A && H >= ks && W >= ks && KP >= 3 * ks * ks, "im2col: bad arguments");
+    const int OH = (H - ks) / stride + 1, OW = (W - ks) / stride + 1;
+    const long total = (long)OH * OW * KP;
+    im2col_img_kernel<<<(int)((total + 255) / 256 > 148L * 64 ? 148L * 64 : (total + 255) / 256), 256, 0, st>>>(
+        img, A, H, W, ks, stride, OH, OW, 3 * ks * ks, KP, do_round);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+int col2im_img_launch(const float* T, float* gimg, int H, int W, int ks, int stride, int KP, const ImageTail& tail, cudaStream_t st) {
+    MAUA_REQUIRE(gimg, "col2im: null output");
+    const int OH = (H - ks) / stride + 1, OW = (W - ks) / stride + 1;
+    const long total = (long)H * W;
+    col2im_img_kernel<<<(int)((total + 255) / 256 > 148L * 32 ? 148L * 32 : (total + 255) / 256), 256, 0, st>>>(
+        T, gimg, H, W, ks, stride, OH, OW, KP, tail);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
+int im2col_weights_launch(const float* w, float* wg, float* wt, int Cout, int K, int KP, cudaStream_t st) {
+    const long total = (long)Cout * KP;
+    im2col_weights_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(w, wg, wt, Cout, K, KP);
+    MAUA_CUDA_CHECK(cudaGetLastError());
+    return MAUA_OK;
+}
+
 void pool3_out_extent(int H, int W, int* PH, int* PW) {
     // ATen pooling_output_shape with ceil_mode, pad 0: floor((H - 3 + 1) / 2) + 1
     // (n = 2 is one clipped window; n = 1 gives 0: ATen refuses it as "output size is too small"; with kernel 3 / stride 2 the
@@ -337,9 +451,11 @@ int pool3_bwd_launch(const float* x, const float* gy, const float* addend, float
                      int do_round, cudaStream_t st) {
     int PH, PW;
     pool3_out_extent(H, W, &PH, &PW);
-    const long total = (long)B * H * W * C;
+    MAUA_REQUIRE(C % 4 == 0, "pool: C %% 4 != 0");
+    const long total = (long)B * H * W * (C / 4);
     pool3_bwd_kernel<<<(int)((total + 255) / 256 > 148L * 32 ? 148L * 32 : (total + 255) / 256), 256, 0, st>>>(
-        x, gy, addend, gx, B, H, W, C, PH, PW, avg, do_round);
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gy), reinterpret_cast<const float4*>(addend),
+        reinterpret_cast<float4*>(gx), B, H, W, C / 4, PH, PW, avg, do_round);
     MAUA_CUDA_CHECK(cudaGetLastError());
     return MAUA_OK;
 }

@@ -60,10 +60,12 @@ struct ConvKParams {
 constexpr int STAGE_BOX_BYTES = 128 * 128;  // epilogue staging: one {32 ch, 16 w, 8 h} output box
 constexpr int N_STAGE_BOX = 2;
 
-template <int BN, int MT, int CG>
+// KS: kernel size of the halo main term -- 3 (VGG, NIN conv3 / conv4) or 5 (NIN conv2, models.py:90: 5x5 / pad 2): the same
+// pipeline with a halo of KS / 2 pixels, KS horizontal box loads per channel chunk and KS vertical taps per box.
+template <int BN, int MT, int CG, int KS = 3>
 struct ConvCfg {
     static constexpr int BNL = BN / CG;                            // weight rows this CTA keeps (half the tile in a pair)
-    static constexpr int A_ROWS = MT * TILE_H + 2;                 // image rows incl. the vertical halo
+    static constexpr int A_ROWS = MT * TILE_H + KS - 1;            // image rows incl. the vertical halo
     static constexpr int A_STAGE = A_ROWS * ROW_BYTES;             // 36864 (MT=2) / 20480 (MT=1): multiples of 1024
     static constexpr int B_STAGE = BNL * 128;
     static constexpr int BUDGET = 192 * 1024;                      // operand rings; 32 KB more go to the epilogue staging
@@ -94,13 +96,13 @@ struct ConvCfg {
 // (this CTA the ones at rows h0 + rank*MT*8 ...), every MMA is M = 256 across both CTAs, and each CTA loads its own
 // activation boxes but only HALF of every weight tile.  All TMA loads complete on the even CTA's barriers (its producer
 // arms them for both CTAs' bytes), the even CTA's MMA warp issues for the pair and its commits arrive in both CTAs.
-template <int BN, int MT, int CG, bool POOL = false>
+template <int BN, int MT, int CG, bool POOL = false, int KS = 3>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                const ConvKParams p) {
-    using Cfg = ConvCfg<BN, MT, CG>;
+    using Cfg = ConvCfg<BN, MT, CG, KS>;
     constexpr int NA = Cfg::NA, NB = Cfg::NB, NACC = Cfg::NACC;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 leads
     const int cta_tile0 = blockIdx.x / CG, cta_tile_step = gridDim.x / CG;
@@ -122,8 +124,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
 
     const int cpt = p.Cin / KCHUNK;                         // channel chunks of the main term
-    const bool halo = (p.ntaps == 9);
-    const int ng1 = halo ? 3 * cpt : (p.ntaps == 1 ? cpt : 0);  // main groups
+    const bool halo = (p.ntaps == KS * KS);
+    const int ng1 = halo ? KS * cpt : (p.ntaps == 1 ? cpt : 0);  // main groups
     const int ng2 = p.K2 / KCHUNK;                          // aux groups
     const int ng = ng1 + ng2;
 
@@ -228,20 +230,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ++ia;
                 uint8_t* sA = smemA + sa * Cfg::A_STAGE;
                 if (g < ng1 && halo) {
-                    const int dxi = g / cpt;                  // 0..2  <->  dx = -1, 0, +1
+                    const int dxi = g / cpt;                  // 0..KS-1  <->  dx = -KS/2 .. +KS/2
                     const int c0 = (g - dxi * cpt) * KCHUNK;
                     if (elect_one()) {
                         arm(&a_full[sa], Cfg::A_STAGE);
-                        load_a(sA, &tmA, &a_full[sa], c0, w0 + dxi - 1, h0 - 1, b);
+                        load_a(sA, &tmA, &a_full[sa], c0, w0 + dxi - KS / 2, h0 - KS / 2, b);
                     }
                     __syncwarp();
-                    for (int dyi = 0; dyi < 3; ++dyi) {
+                    for (int dyi = 0; dyi < KS; ++dyi) {
                         const int sb = ib % NB;
                         mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
                         ++ib;
                         if (elect_one()) {
                             arm(&b_full[sb], Cfg::B_STAGE);
-                            load_b(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * 3 + dxi) * p.Cin + c0, n0 + nb0);
+                            load_b(smemB + sb * Cfg::B_STAGE, &tmB, &b_full[sb], (dyi * KS + dxi) * p.Cin + c0, n0 + nb0);
                         }
                         __syncwarp();
                     }
@@ -286,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ++ia;
                 const uint32_t sA = smem_u32(smemA + sa * Cfg::A_STAGE);
                 const bool is_halo = (g < ng1) && halo;
-                const int nsteps = is_halo ? 3 : 1;
+                const int nsteps = is_halo ? KS : 1;
                 for (int j = 0; j < nsteps; ++j) {
                     const int sb = ib % NB;
                     mbar_wait(&b_full[sb], (ib / NB) & 1);
@@ -684,7 +686,8 @@ SplitPlan plan_split(long tiles, int units, int ngroups, int mode, int bn = 0, i
     return sp;
 }
 int conv_groups(const ConvArgs& a) {
-    return (a.ntaps == 9 ? 3 * (a.Cin / KCHUNK) : (a.ntaps == 1 ? a.Cin / KCHUNK : 0)) + a.K2 / KCHUNK;
+    return (a.ntaps == 9 ? 3 * (a.Cin / KCHUNK) : a.ntaps == 25 ? 5 * (a.Cin / KCHUNK) : (a.ntaps == 1 ? a.Cin / KCHUNK : 0)) +
+           a.K2 / KCHUNK;
 }
 // tail handling requested by the caller: ConvArgs::tail_mode (K-split additionally needs the workspace)
 int effective_tail_mode(const ConvArgs& a) {
@@ -698,6 +701,12 @@ int effective_tail_mode(const ConvArgs& a) {
 // each CTA holds half of the weight rows) win, and a tile needs its accumulator double-buffered in TMEM (MT * BN <= 256)
 // to keep the epilogue off the critical path.  With split-K (plan_split) the last partial wave costs 1 / split of a tile
 // time instead of a whole one, which is what decides the shape at <= 512^2 where every layer is a partial wave.
+// tile shapes the 5x5 kernel is instantiated for (conv_tc_launch)
+bool ks5_shape(int bn, int mt, int cg) {
+    return (bn == 256 && mt == 1 && cg == 2) || (bn == 128 && mt == 2 && cg == 2) || (bn == 128 && mt == 1 && cg == 1) ||
+           (bn == 64 && mt == 2 && cg == 2) || (bn == 64 && mt == 1 && cg == 1);
+}
+
 SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, int& mt_out, int& cg_out) {
     auto shape_rate = [](int bn, int mt, int cg) -> double {
         if (cg == 2) {
@@ -720,6 +729,7 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, in
         for (int mt = 2; mt >= 1; --mt)
             for (int cg = 2; cg >= 1; --cg) {
                 if (a.force_cg && cg != a.force_cg) continue;
+                if (a.ntaps == 25 && !ks5_shape(bn, mt, cg)) continue;
                 const int units = sms / cg;
                 const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) *
                                    ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
@@ -740,7 +750,7 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, in
     if (const char* f = getenv("MAUA_CONV_FORCE")) {  // developer override for tile-shape experiments: "bn,mt,cg"
         int fb = 0, fm = 0, fc = 0;
         if (sscanf(f, "%d,%d,%d", &fb, &fm, &fc) == 3 && a.Cout % fb == 0 && (fm == 1 || fm == 2) && (fc == 1 || fc == 2) &&
-            (fb == 32 || fb == 64 || fb == 128 || fb == 256)) {
+            (fb == 32 || fb == 64 || fb == 128 || fb == 256) && (a.ntaps != 25 || ks5_shape(fb, fm, fc))) {
             bn = fb; mt = fm; cg = fc;
             const long tiles = (long)((a.W + TILE_W - 1) / TILE_W) * ((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * a.B * (a.Cout / bn);
             best_sp = plan_split(tiles, sms / cg, ngroups, tail_mode, bn, cg);
@@ -750,18 +760,18 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, in
     return best_sp;
 }
 
-template <int BN, int MT, int CG, bool POOL>
+template <int BN, int MT, int CG, bool POOL, int KS = 3>
 int launch_cfg(const ConvArgs& a, cudaStream_t st) {
-    using Cfg = ConvCfg<BN, MT, CG>;
-    static unsigned long long attr_done = 0;  // per (BN, MT, CG, POOL) instantiation; benign race (idempotent call)
-    MAUA_CUDA_CHECK((ensure_dynamic_smem(conv_tc_kernel<BN, MT, CG, POOL>, Cfg::SMEM_BYTES, &attr_done)));
+    using Cfg = ConvCfg<BN, MT, CG, KS>;
+    static unsigned long long attr_done = 0;  // per (BN, MT, CG, POOL, KS) instantiation; benign race (idempotent call)
+    MAUA_CUDA_CHECK((ensure_dynamic_smem(conv_tc_kernel<BN, MT, CG, POOL, KS>, Cfg::SMEM_BYTES, &attr_done)));
     CUtensorMap tmA, tmB, tmA2, tmB2;
     int rc;
     const bool has_main = a.ntaps > 0;
     const bool has_aux = a.K2 > 0;
     if (has_main) {
         // 3x3: halo box (MT*8 + 2 image rows) shared by the three vertical taps; pointwise: plain box
-        if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, a.ntaps == 9 ? Cfg::A_ROWS : MT * TILE_H))) return rc;
+        if ((rc = make_tmap_nhwc(&tmA, a.in, a.B, a.H, a.W, a.Cin, TILE_W, a.ntaps == KS * KS ? Cfg::A_ROWS : MT * TILE_H))) return rc;
         if ((rc = make_tmap_2d(&tmB, a.wg, a.Cout, (long)a.ntaps * a.Cin, Cfg::BNL, 0))) return rc;
     }
     if (has_aux) {
@@ -820,7 +830,7 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    MAUA_CUDA_CHECK((cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG, POOL>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p)));
+    MAUA_CUDA_CHECK((cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG, POOL, KS>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p)));
     return MAUA_OK;
 }
 
@@ -846,7 +856,7 @@ void conv_tile_plan(const ConvArgs& a, int sms, int tail_mode, int* bn, int* mt,
 }
 
 int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
-    MAUA_REQUIRE(a.ntaps == 9 || a.ntaps == 1 || a.ntaps == 0, "ntaps must be 9, 1 or 0 (got %d)", a.ntaps);
+    MAUA_REQUIRE(a.ntaps == 25 || a.ntaps == 9 || a.ntaps == 1 || a.ntaps == 0, "ntaps must be 25, 9, 1 or 0 (got %d)", a.ntaps);
     MAUA_REQUIRE(a.ntaps > 0 || a.K2 > 0, "conv has neither a main nor an aux term");
     MAUA_REQUIRE(a.ntaps == 0 || (a.Cin % KCHUNK == 0 && a.Cin >= KCHUNK),
                  "tcgen05 conv needs Cin %% 32 == 0 (got %d); the 3-channel image layer uses conv_first_*", a.Cin);
@@ -863,6 +873,16 @@ int conv_tc_launch(const ConvArgs& a, cudaStream_t st) {
                 a.H, a.W, a.Cin, a.Cout, a.ntaps, a.K2, bn, mt, cg, spc.full_tiles,
                 spc.halves ? (spc.items - spc.full_tiles) / 2 : (spc.split > 1 ? (spc.items - spc.full_tiles) / spc.split : 0),
                 spc.halves ? "half-N" : "K-split", spc.halves ? 2 : spc.split, num_sms() / cg);
+    }
+    if (a.ntaps == 25) {
+        // 5x5: the shapes ks5_shape() lets the chooser pick (each is one more instantiation of the kernel)
+        MAUA_REQUIRE(!a.ep.pool_out, "the 5x5 convolution has no fused pooling");
+        if (bn == 256 && mt == 1 && cg == 2) return launch_cfg<256, 1, 2, false, 5>(a, st);
+        if (bn == 128 && mt == 2 && cg == 2) return launch_cfg<128, 2, 2, false, 5>(a, st);
+        if (bn == 128 && mt == 1 && cg == 1) return launch_cfg<128, 1, 1, false, 5>(a, st);
+        if (bn == 64 && mt == 2 && cg == 2) return launch_cfg<64, 2, 2, false, 5>(a, st);
+        if (bn == 64 && mt == 1 && cg == 1) return launch_cfg<64, 1, 1, false, 5>(a, st);
+        MAUA_REQUIRE(false, "5x5 convolution: no kernel for tile shape BN %d MT %d CG %d (Cout %d must be a multiple of 64)", bn, mt, cg, a.Cout);
     }
     if (bn == 256) return mt == 2 ? launch_cg<256, 2>(a, cg, st) : launch_cg<256, 1>(a, cg, st);
     if (bn == 128) return mt == 2 ? launch_cg<128, 2>(a, cg, st) : launch_cg<128, 1>(a, cg, st);
@@ -884,7 +904,8 @@ __global__ void conv_ref_kernel(ConvArgs a) {
         const int b = pix / ((long)a.W * a.H);
         float acc = 0.f;
         for (int tap = 0; tap < a.ntaps; ++tap) {
-            const int dy = a.ntaps == 9 ? tap / 3 - 1 : 0, dx = a.ntaps == 9 ? tap % 3 - 1 : 0;
+            const int ks = a.ntaps == 25 ? 5 : (a.ntaps == 9 ? 3 : 1);
+            const int dy = tap / ks - ks / 2, dx = tap % ks - ks / 2;
             const int hh = h + dy, ww = w + dx;
             if (hh < 0 || hh >= a.H || ww < 0 || ww >= a.W) continue;
             const float* ip = a.in + (((long)b * a.H + hh) * a.W + ww) * a.Cin;

@@ -118,6 +118,11 @@ int conv_gen_flip_weights_launch(const float* w, float* out, int Cout, int Cin, 
 // image-layer backward for a strided convolution without padding (+ TVLoss / temporal gradients); gout may be null
 int conv_gen_dgrad_img_launch(const float* gout, const float* w, float* gimg, int B, int H, int W, int Cout, int ks, int stride,
                               const ImageTail& tail, cudaStream_t st);
+// the image layer as a GEMM (product path): A [OH*OW][KP] = im2col(NCHW image), k = c*ks^2 + ky*ks + kx zero-padded to KP;
+// GEMM weights wg [Cout][KP] and wt [KP][Cout] (TF32-rounded); col2im of T [OH*OW][KP] back to the NCHW image gradient + tail
+int im2col_img_launch(const float* img, float* A, int H, int W, int ks, int stride, int KP, int do_round, cudaStream_t st);
+int col2im_img_launch(const float* T, float* gimg, int H, int W, int ks, int stride, int KP, const ImageTail& tail, cudaStream_t st);
+int im2col_weights_launch(const float* w, float* wg, float* wt, int Cout, int K, int KP, cudaStream_t st);
 void pool3_out_extent(int H, int W, int* PH, int* PW);
 int pool3_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, int do_round, cudaStream_t st);
 int pool3_bwd_launch(const float* x, const float* gy, const float* addend, float* gx, int B, int H, int W, int C, int avg,

@@ -35,6 +35,7 @@ struct Entry {
     int cin = 0, cout = 0;     // conv only
     int ks = 3, stride = 1, pad = 1;  // conv geometry: 3x3 / 1 / 1 (VGG), 1x1, 5x5 / 1 / 2, 11x11 / 4 / 0 (NIN, models.py:82-111)
     bool pool3 = false;        // pool only: 3x3 / stride 2 / ceil_mode (NIN, models.py:77-80) instead of 2x2 / stride 2
+    float *w1g = nullptr, *w1t = nullptr;  // 11x11 / 4 image layer only: GEMM weights [cout][KP] and [KP][cout] of the im2col form
     float* w_flip = nullptr;   // 5x5 only: [cin][cout][5][5] rotated copy = the weights of the input-gradient convolution
     int conv_index = -1;       // = relu index (global, counted from conv1_1)
     bool image_layer = false;  // conv1_1: consumes the NCHW image (conv_edge.cu)
@@ -159,6 +160,8 @@ struct maua_plan {
     size_t gbuf_elems = 0;
     void* reduce_ws = nullptr;
     float* coef2 = nullptr;       // [n_taps + 2] scaled coefficients
+    float* im2col_ws = nullptr;   // NIN image layer (11x11 / 4): im2col matrix / its gradient [OH*OW][kIm2colK]
+    size_t im2col_elems = 0;
     float* splitk_ws = nullptr;   // partial accumulators of K-split conv tiles (conv_tc.cu)
     unsigned int* splitk_flags = nullptr;
     size_t tap_bytes = 0;
@@ -191,6 +194,8 @@ static void prof_mark(maua_plan* p, cudaStream_t st, const char* name, int layer
 }
 
 namespace {
+
+constexpr int kIm2colK = 384;  // 3 * 11 * 11 = 363 columns of the NIN image layer's im2col matrix, padded to a multiple of 128
 
 struct DeviceGuard {
     int prev = -1;
@@ -264,6 +269,20 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
             }
         }
         p->gbuf_elems = max_act;
+    }
+    if (!p->entries.empty() && p->entries[0].image_layer && p->entries[0].ks == 11) {
+        const size_t need_i = (size_t)p->entries[0].H * p->entries[0].W * kIm2colK;
+        if (need_i > p->im2col_elems) {
+            if (p->im2col_ws) cudaFree(p->im2col_ws);
+            p->im2col_ws = nullptr;
+            p->im2col_elems = 0;
+            if (cudaMalloc(&p->im2col_ws, need_i * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                set_last_error("out of device memory allocating the im2col workspace (%.2f GB) for %dx%d", need_i * 4e-9, H, W);
+                return MAUA_ERR_OOM;
+            }
+            p->im2col_elems = need_i;
+        }
     }
     size_t off = 0, boff = 0;
     for (auto& e : p->entries) {
@@ -368,7 +387,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
                 break;
             }
             const size_t wn = (size_t)en.cout * en.cin * en.ks * en.ks;
-            const bool gemm_layer = i > 0 && en.ks <= 3;  // 3x3 and 1x1: tcgen05 implicit GEMM on rounded GEMM-layout copies
+            const bool gemm_layer = i > 0 && en.ks <= 5;  // 5x5, 3x3, 1x1: tcgen05 implicit GEMM on rounded GEMM-layout copies
             alloc((void**)&en.w_raw, wn * sizeof(float));
             alloc((void**)&en.bias, (size_t)en.cout * sizeof(float));
             if (gemm_layer) {
@@ -389,6 +408,11 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
                     ok = false;
             }
             if (e == cudaSuccess && en.ks == 5 && conv_gen_flip_weights_launch(en.w_raw, en.w_flip, en.cout, en.cin, 5, 0)) ok = false;
+            if (i == 0 && en.ks == 11) {
+                alloc((void**)&en.w1g, (size_t)en.cout * kIm2colK * sizeof(float));
+                alloc((void**)&en.w1t, (size_t)en.cout * kIm2colK * sizeof(float));
+                if (e == cudaSuccess && im2col_weights_launch(en.w_raw, en.w1g, en.w1t, en.cout, 3 * 11 * 11, kIm2colK, 0)) ok = false;
+            }
             cin = en.cout;
         }
         p->entries.push_back(en);
@@ -477,12 +501,13 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     DeviceGuard guard(p->device);
     for (auto& e : p->entries) {
         cudaFree(e.w_raw); cudaFree(e.wg); cudaFree(e.wd); cudaFree(e.bias); cudaFree(e.wt1);
-        cudaFree(e.wg32); cudaFree(e.wd32); cudaFree(e.wt1_32); cudaFree(e.w_flip);
+        cudaFree(e.wg32); cudaFree(e.wd32); cudaFree(e.wt1_32); cudaFree(e.w_flip); cudaFree(e.w1g); cudaFree(e.w1t);
     }
     for (auto& t : p->taps) {
         cudaFree(t.gram); cudaFree(t.diff); cudaFree(t.aux_d); cudaFree(t.mean); cudaFree(t.aux_bias); cudaFree(t.gram_ws);
     }
     cudaFree(p->arena);
+    cudaFree(p->im2col_ws);
     cudaFree(p->bits_arena);
     for (int i = 0; i < 3; ++i) cudaFree(p->gbuf[i]);
     cudaFree(p->reduce_ws); cudaFree(p->coef2);
@@ -492,7 +517,7 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
 
 MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* p) {
     if (!p) return 0;
-    return p->weight_bytes + p->arena_elems * sizeof(float) + p->bits_words * sizeof(uint32_t) +
+    return p->weight_bytes + (p->arena_elems + p->im2col_elems) * sizeof(float) + p->bits_words * sizeof(uint32_t) +
            3 * p->gbuf_elems * sizeof(float);
 }
 
@@ -667,8 +692,19 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     for (int i = 0; i <= last_needed; ++i) {
         Entry& e = p->entries[i];
         float* hand_off = (boundary_out && i == n_ent - 1) ? boundary_out : nullptr;
-        if (e.image_layer && e.ks != 3) {
-            // NIN conv1 (models.py:83): 11x11 / stride 4 straight from the NCHW image
+        if (e.image_layer && e.ks != 3 && !exact) {
+            // NIN conv1 (models.py:83: 11x11 / stride 4 on the NCHW image) on the product path: im2col (363 -> 384 columns, TF32-
+            // rounded) + the pointwise tcgen05 GEMM with the fused bias / ReLU / sign-bitmap epilogue
+            if ((rc = im2col_img_launch(image, p->im2col_ws, H, W, e.ks, e.stride, kIm2colK, 1, st))) return rc;
+            p->launches_fwd++;
+            ConvArgs a;
+            a.B = 1; a.H = e.H; a.W = e.W; a.Cin = kIm2colK; a.Cout = e.cout; a.ntaps = 1;
+            a.in = p->im2col_ws; a.wg = e.w1g;
+            a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = rnd; a.ep.mask_out = e.bits; a.ep.out2 = hand_off;
+            a.tail_mode = p->conv_tail;
+            if ((rc = conv_dispatch(a, p->impl, st))) return rc;
+        } else if (e.image_layer && e.ks != 3) {
+            // ... and in the exact-arithmetic mode: direct fp32 convolution
             if ((rc = conv_gen_fwd_launch(image, 1, e.w_raw, e.bias, e.out, e.bits, 1, H, W, 3, e.cout, e.ks, e.stride, e.pad, 1, rnd, st)))
                 return rc;
             if (hand_off)
@@ -696,8 +732,9 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             if (e.pool3) {
                 if ((rc = pool3_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
             } else if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
-        } else if (e.ks == 5) {
-            // NIN conv2 (models.py:90): 5x5 / pad 2, direct fp32 convolution
+        } else if (e.ks == 5 && exact) {
+            // NIN conv2 (models.py:90) in the exact-arithmetic mode: 5x5 / pad 2 as a direct fp32 convolution (conv_gen.cu); the
+            // product path runs it through conv_tc_kernel<.., KS = 5> below
             if ((rc = conv_gen_fwd_launch(cur, 0, e.w_raw, e.bias, e.out, e.bits, 1, curH, curW, e.cin, e.cout, 5, 1, 2, 1, rnd, st)))
                 return rc;
             if (hand_off)
@@ -712,7 +749,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.tail_mode = p->splitk ? 1 : p->conv_tail;
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
             if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && !p->entries[i + 1].pool3 &&
-                e.H >= 2 && e.W >= 2) {
+                e.ks == 3 && e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
                 a.ep.pool_avg = p->avg_pool;
                 pool_done = true;
@@ -722,7 +759,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
         p->launches_fwd++;
         {
             const double px = (double)e.H * e.W;
-            if (e.image_layer) prof_mark(p, st, "conv_first_fwd", i, 2.0 * 27 * e.cout * px, 4.0 * (3 + e.cout) * px);
+            if (e.image_layer) prof_mark(p, st, "conv_first_fwd", i, 2.0 * 3 * e.ks * e.ks * e.cout * px, 4.0 * (3.0 * H * W + e.cout * px));
             else if (e.pool) prof_mark(p, st, "pool_fwd", i, 0, 4.0 * 5 * e.C * px);
             else prof_mark(p, st, "conv_fwd", i, 2.0 * e.ks * e.ks * e.cin * e.cout * px, 4.0 * (e.cin + e.cout) * px);
         }
@@ -987,8 +1024,8 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         a.B = 1; a.H = ec.H; a.W = ec.W;
         a.Cin = ec.cout; a.Cout = ec.cin; a.ntaps = ec.ks * ec.ks;
         a.in = gm; a.wg = exact ? ec.wd32 : ec.wd;
-        if (ec.ks == 5) {
-            // NIN conv2 (5x5 / pad 2): the input gradient is the direct convolution of Gm with the rotated, transposed weights
+        if (ec.ks == 5 && exact) {
+            // NIN conv2 (5x5 / pad 2), exact mode: the input gradient is the direct convolution of Gm with the rotated, transposed weights
             // (conv_gen.cu, fp32); the ReLU mask, tap gradients and rounding follow in the un-pool kernel or an epilogue-only launch
             float* raw = take_buf();
             if ((rc = conv_gen_fwd_launch(gm, 0, ec.w_flip, nullptr, raw, nullptr, 1, ec.H, ec.W, ec.cout, ec.cin, 5, 1, 2, 0, 0, st)))
@@ -1057,7 +1094,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
             a.B = 1; a.H = e0.H; a.W = e0.W; a.Cin = e0.cout; a.Cout = e0.cin; a.ntaps = e0.ks * e0.ks;
             a.in = gm; a.wg = exact ? e0.wd32 : e0.wd;
             a.ep.out = grad_image; a.ep.round = 0;
-            if (e0.ks == 5) {
+            if (e0.ks == 5 && exact) {
                 if ((rc = conv_gen_fwd_launch(gm, 0, e0.w_flip, nullptr, grad_image, nullptr, 1, e0.H, e0.W, e0.cout, e0.cin, 5, 1, 2, 0, 0, st)))
                     return rc;
                 p->launches_bwd++;
@@ -1080,8 +1117,22 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         tail.temp_coef = p->coef2 + nt + 1;
     }
     Entry& e0 = p->entries[0];
-    if (e0.ks != 3) {
-        // NIN conv1 (11x11 / 4): gather-form input gradient + the image-side terms in one kernel (conv_gen.cu)
+    if (e0.ks != 3 && !exact) {
+        // NIN conv1 (11x11 / 4) on the product path: T = Gm . W^T as a pointwise tcgen05 GEMM (128 -> 384 tap columns), then col2im
+        // (<= 3 x 3 positions per pixel) fused with the image-side terms -- the scheme of conv1_1's dgrad (conv_edge.cu)
+        const bool have = gm && gm_entry == 0;
+        if (have) {
+            ConvArgs a;
+            a.B = 1; a.H = e0.H; a.W = e0.W; a.Cin = e0.cout; a.Cout = kIm2colK; a.ntaps = 1;
+            a.in = gm; a.wg = e0.w1t;
+            a.ep.out = p->im2col_ws; a.ep.round = 0;
+            if ((rc = run_conv(a))) return rc;
+        }
+        if ((rc = col2im_img_launch(have ? p->im2col_ws : nullptr, grad_image, H, W, e0.ks, e0.stride, kIm2colK, tail, st))) return rc;
+        p->launches_bwd++;
+        prof_mark(p, st, "conv_first_dgrad", 0, 2.0 * 3 * e0.ks * e0.ks * e0.cout * e0.H * e0.W, 4.0 * ((e0.cout + 2.0 * kIm2colK) * e0.H * e0.W + 6.0 * H * W));
+    } else if (e0.ks != 3) {
+        // ... exact mode: gather-form input gradient + the image-side terms in one kernel (conv_gen.cu)
         if ((rc = conv_gen_dgrad_img_launch((gm && gm_entry == 0) ? gm : nullptr, e0.w_raw, grad_image, 1, H, W, e0.cout, e0.ks, e0.stride,
                                             tail, st)))
             return rc;

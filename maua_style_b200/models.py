@@ -451,7 +451,16 @@ class B200Net(nn.Module):
                 if mod.mode == "capture" and not window:  # (a window of B > 1 frames manages its captures itself)
                     fresh = mod.target.nelement() == 0
                     if fresh and Cp == C_:
-                        mod.target = torch.zeros(C_, C_, device=tdev)
+                        if self.reuse_target_buffers:
+                            # optimisation loops (optim.optimize_device) build a new network per call on the SAME plan core: the
+                            # style targets go into the core's buffers again, so that the iteration captured for the previous
+                            # call launches identical kernel arguments and its CUDA graph is replayed instead of re-captured
+                            bufs = self._core.__dict__.setdefault("style_target_bufs", {})
+                            if (t, C_) not in bufs:
+                                bufs[(t, C_)] = torch.zeros(C_, C_, device=tdev)
+                            mod.target = bufs[(t, C_)]
+                        else:
+                            mod.target = torch.zeros(C_, C_, device=tdev)
                     io.capture_weight = float(mod.blend_weight)
                     io.capture_accumulate = 0 if fresh else 1
                 if mod.mode != "none" and Cp != C_:

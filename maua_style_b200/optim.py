@@ -34,7 +34,8 @@ class _Trace:
         import os
         import time
 
-        self.on = os.environ.get("MAUA_TRACE", "0") == "1"
+        self.on = os.environ.get("MAUA_TRACE", "0") in ("1", "2")
+        self.fine = os.environ.get("MAUA_TRACE", "0") == "2"  # also every 100 iterations of the loop
         self.what, self.t, self.time = what, 0.0, time
         if self.on:
             torch.cuda.synchronize()
@@ -224,6 +225,16 @@ class PixelOptimizer:
             pass
 
 
+_CAPTURE_STREAMS = {}
+
+
+def _capture_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(dev)
+    return _CAPTURE_STREAMS[key]
+
+
 class GraphedIteration:
     """One whole reference iteration -- feval (optim.py:201-221) + pixel update (optim.py:240) -- captured once into a CUDA
     graph and replayed: ~65 kernel launches become one graph launch, which removes the host launch cost and the gaps
@@ -271,12 +282,21 @@ class GraphedIteration:
             return
         if self.graph is None:
             dev = self.pastiche.device
-            torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             count = self.opt.step_count
             try:
-                with torch.cuda.graph(g):
-                    self._eager()
+                # capture_begin / capture_end on a side stream instead of the torch.cuda.graph() context manager: that one
+                # also runs gc.collect() and torch.cuda.empty_cache() on entry, which costs 20-260 ms per capture (measured:
+                # tools/dbg_small_scale.py) -- more than 200 iterations at 256^2 -- every time a scale starts
+                side = _capture_stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    g.capture_begin()
+                    try:
+                        self._eager()
+                    finally:
+                        g.capture_end()
+                torch.cuda.current_stream(dev).wait_stream(side)
             except Exception as e:  # noqa: BLE001
                 # capture unsupported in this environment: stay eager (the capture launched nothing) -- and say so,
                 # because eager launches are several times slower at <= 512^2
@@ -429,6 +449,8 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
             # optim.py:230-236 saves the image the closure was evaluated on, i.e. before this iteration's update
             _save_intermediate(pastiche, args, it, num_iters)
         iteration()
+        if tr.fine and it % 100 == 0:
+            tr.mark(f"iterations {it - 99}..{it}")
         if want_print:
             total = float(net._loss_vec[live].sum())  # the losses of the image before the update, like optim.py:228-229
             print(f"Iteration {it} / {args.num_iters}, Loss: {total}")

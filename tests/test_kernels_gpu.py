@@ -427,3 +427,38 @@ def test_pool3x3_ceil_forward_backward(lib, avg, c, h, w):
                                     0, _lib.stream_ptr()), "pool3 bwd")
     torch.cuda.synchronize()
     assert rel(nchw(gx), gref) < 1e-6
+
+
+@pytest.mark.parametrize("impl", [pytest.param(_lib.MAUA_IMPL_REF, id="ref"), pytest.param(_lib.MAUA_IMPL_TC, id="tc"),
+                                  pytest.param(_lib.MAUA_IMPL_TC_1CTA, id="tc1cta"), pytest.param(_lib.MAUA_IMPL_TC_2CTA, id="tc2cta")])
+@pytest.mark.parametrize("cin,cout,ks,h,w", [(128, 256, 5, 40, 56), (96 + 32, 64, 5, 17, 33), (256, 128, 5, 64, 64), (64, 128, 5, 9, 5),
+                                              (96 + 32, 128, 1, 31, 45), (384, 384, 1, 12, 20)])
+def test_conv_kxk_tensor_core(lib, impl, cin, cout, ks, h, w):
+    """NIN's 5x5 / pad 2 and 1x1 layers through conv_tc_kernel (KS = 5 halo pipeline / pointwise), forward and -- with the
+    rotated, transposed weights -- input gradient, against fp32 torch on TF32-rounded operands."""
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = tf32_round(torch.randn(1, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, ks, ks, generator=g) * (2.0 / (cin * ks * ks)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    xr = x.double().requires_grad_(True)
+    pre = F.conv2d(xr, tf32_round(wt).double(), b.double(), padding=ks // 2)
+    ref = F.relu(pre).float()
+    wd_, bd, xd = wt.cuda(), b.cuda(), nhwc(x).cuda()
+    wg = torch.empty(cout, ks * ks * cin, device="cuda")
+    _lib.check(lib.maua_prep_conv_weights_k(_lib.ptr(wd_), _lib.ptr(wg), cout, cin, ks, 0, 1, _lib.stream_ptr()))
+    y = torch.empty(1, h, w, cout, device="cuda")
+    _lib.check(lib.maua_conv_kxk_fwd(_lib.ptr(xd), _lib.ptr(wg), _lib.ptr(bd), _lib.ptr(y), 1, h, w, cin, cout, ks, 1, impl,
+                                     _lib.stream_ptr()), "conv_kxk_fwd")
+    torch.cuda.synchronize()
+    assert rel(nchw(y), ref) < 1.5e-3
+    # input gradient: the same kernel on the rotated / transposed weights
+    go = tf32_round(torch.randn(1, cout, h, w, generator=g))
+    (gref,) = torch.autograd.grad(pre, xr, go.double())
+    wdg = torch.empty(cin, ks * ks * cout, device="cuda")
+    _lib.check(lib.maua_prep_conv_weights_k(_lib.ptr(wd_), _lib.ptr(wdg), cout, cin, ks, 1, 1, _lib.stream_ptr()))
+    god = nhwc(go).cuda()
+    gx = torch.empty(1, h, w, cin, device="cuda")
+    _lib.check(lib.maua_conv_kxk_fwd(_lib.ptr(god), _lib.ptr(wdg), C.c_void_p(0), _lib.ptr(gx), 1, h, w, cout, cin, ks, 0, impl,
+                                     _lib.stream_ptr()), "conv_kxk dgrad")
+    torch.cuda.synchronize()
+    assert rel(nchw(gx), gref.float()) < 1.5e-3

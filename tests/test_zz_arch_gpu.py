@@ -41,7 +41,8 @@ BOUNDS = {
     "vgg16_adam_gram_72x88": (5e-2, 40.0),        # 3.0e-2, 56.0 dB
     "vgg16p_adam_gram_72x88": (5e-2, 40.0),       # measured on B200: see profiles/r02_f4_parity.txt
     "nin_adam_gram_131x150": (5e-2, 40.0),
-    "nin_avg_cov_lbfgs_128x144": (2e-2, 45.0),    # average pooling: no arg-max flips; optimisation in exact mode (EXACT_OPTIMIZE)
+    "nin_avg_cov_lbfgs_128x144": (3.5e-2, 45.0),  # measured 2.0e-2 (average pooling: ReLU-sign flips only, but the 11x11 image
+                                                  # layer now reads TF32-rounded pixels); optimisation in exact mode (EXACT_OPTIMIZE)
     "vgg16p_cov_lbfgs_64x80": (5e-2, 45.0),       # optimisation in exact-arithmetic mode, see EXACT_OPTIMIZE
     "vid_frame_temporal_64x80": (4e-2, 40.0),     # 2.2e-2, 56.1 dB
     "vgg19_taps_lbfgs_80x64": (4e-2, 20.0),       # 2.5e-2, 34.7 dB (fp32 leaps by 7.5 grey levels rms in iteration 3, the
