@@ -323,6 +323,10 @@ MAUA_API int maua_plan_create_stage(int device, const maua_net_desc* desc, int e
                                     maua_plan_t** out);
 MAUA_API void maua_plan_destroy(maua_plan_t* plan);
 /* Bytes of device memory the plan currently owns (weights + workspaces), for capacity planning. */
+/* Number of times the plan (re)allocated one of its workspaces (activation arena, sign bitmaps, gradient buffers): they grow
+ * with the image size and keep their size afterwards.  A CUDA graph captured from maua_plan_forward / _backward bakes their
+ * addresses in; a caller that replays captured iterations (optim.GraphedIteration) re-captures when this number changed. */
+MAUA_API int maua_plan_workspace_generation(const maua_plan_t* plan);
 MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* plan);
 
 /* net(image): forward to the last tap.  image NCHW [1,3,H,W].  For taps in CAPTURE mode updates `target`;

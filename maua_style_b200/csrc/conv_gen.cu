@@ -190,21 +190,27 @@ conv_gen_dgrad_img_kernel(const float* __restrict__ gout /*NHWC [B][OH][OW][Cout
 // A[p][k], p = output position, k = c * ks^2 + ky * ks + kx (the OIHW order of a weight row), zero-padded to KP columns
 __global__ void im2col_img_kernel(const float* __restrict__ img, float* __restrict__ A, int H, int W, int ks, int stride, int OH,
                                   int OW, int K, int KP, int do_round) {
-    const long total = (long)OH * OW * KP;
-    const int kk = ks * ks;
+    // one thread per (position, image row of the window): ks contiguous pixels of the image -> ks contiguous columns of A;
+    // the thread with row index 3 * ks writes the zero padding K .. KP - 1
+    const int rows = 3 * ks + 1;
+    const long total = (long)OH * OW * rows;
     const long HW = (long)H * W;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int k = i % KP;
-        const long p = i / KP;
-        float v = 0.f;
-        if (k < K) {
-            const int ox = p % OW, oy = p / OW;
-            const int c = k / kk, r = k - c * kk;
-            const int ky = r / ks, kx = r - ky * ks;
-            v = __ldg(img + c * HW + (long)(oy * stride + ky) * W + ox * stride + kx);
-            if (do_round) v = round_tf32(v);
+        const int r = i % rows;
+        const long p = i / rows;
+        float* dst = A + p * KP;
+        if (r == 3 * ks) {
+            for (int k = K; k < KP; ++k) dst[k] = 0.f;
+            continue;
         }
-        A[i] = v;
+        const int ox = p % OW, oy = p / OW;
+        const int c = r / ks, ky = r - c * ks;
+        const float* src = img + c * HW + (long)(oy * stride + ky) * W + ox * stride;
+        dst += r * ks;
+        for (int kx = 0; kx < ks; ++kx) {
+            const float v = __ldg(src + kx);
+            dst[kx] = do_round ? round_tf32(v) : v;
+        }
     }
 }
 
@@ -404,7 +410,7 @@ int conv_gen_dgrad_img_launch(const float* gout, const float* w, float* gimg, in
 int im2col_img_launch(const float* img, float* A, int H, int W, int ks, int stride, int KP, int do_round, cudaStream_t st) {
     MAUA_REQUIRE(img && A && H >= ks && W >= ks && KP >= 3 * ks * ks, "im2col: bad arguments");
     const int OH = (H - ks) / stride + 1, OW = (W - ks) / stride + 1;
-    const long total = (long)OH * OW * KP;
+    const long total = (long)OH * OW * (3 * ks + 1);
     im2col_img_kernel<<<(int)((total + 255) / 256 > 148L * 64 ? 148L * 64 : (total + 255) / 256), 256, 0, st>>>(
         img, A, H, W, ks, stride, OH, OW, 3 * ks * ks, KP, do_round);
     MAUA_CUDA_CHECK(cudaGetLastError());

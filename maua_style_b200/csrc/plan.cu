@@ -154,6 +154,7 @@ struct maua_plan {
     // workspaces
     float* arena = nullptr;
     size_t arena_elems = 0;
+    int ws_generation = 0;        // bumped whenever a workspace is (re)allocated: a CUDA graph captured before is stale
     uint32_t* bits_arena = nullptr;
     size_t bits_words = 0;
     float* gbuf[3] = {nullptr, nullptr, nullptr};
@@ -234,6 +235,7 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         if (n > max_act) max_act = n;
     }
     if (need_bits > p->bits_words) {
+        p->ws_generation++;
         if (p->bits_arena) cudaFree(p->bits_arena);
         p->bits_arena = nullptr;
         p->bits_words = 0;
@@ -245,6 +247,7 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         p->bits_words = need_bits;
     }
     if (need > p->arena_elems) {
+        p->ws_generation++;
         if (p->arena) cudaFree(p->arena);
         p->arena = nullptr;
         p->arena_elems = 0;
@@ -256,6 +259,7 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         p->arena_elems = need;
     }
     if (max_act > p->gbuf_elems) {
+        p->ws_generation++;
         for (int i = 0; i < 3; ++i) {
             if (p->gbuf[i]) cudaFree(p->gbuf[i]);
             p->gbuf[i] = nullptr;
@@ -273,6 +277,7 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
     if (!p->entries.empty() && p->entries[0].image_layer && p->entries[0].ks == 11) {
         const size_t need_i = (size_t)p->entries[0].H * p->entries[0].W * kIm2colK;
         if (need_i > p->im2col_elems) {
+            p->ws_generation++;
             if (p->im2col_ws) cudaFree(p->im2col_ws);
             p->im2col_ws = nullptr;
             p->im2col_elems = 0;
@@ -520,6 +525,8 @@ MAUA_API size_t maua_plan_device_bytes(const maua_plan_t* p) {
     return p->weight_bytes + (p->arena_elems + p->im2col_elems) * sizeof(float) + p->bits_words * sizeof(uint32_t) +
            3 * p->gbuf_elems * sizeof(float);
 }
+
+MAUA_API int maua_plan_workspace_generation(const maua_plan_t* p) { return p ? p->ws_generation : -1; }
 
 MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
     MAUA_REQUIRE(p && impl >= MAUA_IMPL_TC && impl <= MAUA_IMPL_FP32, "maua_plan_set_impl: bad arguments");

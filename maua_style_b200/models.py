@@ -578,7 +578,9 @@ class B200Net(nn.Module):
         """Everything a captured iteration bakes into its kernel arguments besides the pastiche: extents, module modes,
         strengths and target addresses.  Two iterations with equal signatures launch identical kernels."""
         tio, iio = self._build_io(H, W)
-        return bytes(memoryview(tio)) + bytes(memoryview(iio)) + f"{H}x{W}".encode()
+        # (the plan's workspaces are part of the captured kernel arguments too: they are re-allocated when a larger image comes)
+        gen = ",".join(str(int(self._lib.maua_plan_workspace_generation(st["plan"]))) for st in self._stages)
+        return bytes(memoryview(tio)) + bytes(memoryview(iio)) + f"{H}x{W} ws {gen} impl {self._impl}".encode()
 
     def _forward_plan(self, x: torch.Tensor, keep: bool) -> int:
         if x.dim() != 4 or x.shape[1] != 3:

@@ -404,7 +404,7 @@ def optimize_device(content, styles, init, num_iters, args, net=None, losses=Non
         set_model_args(args, max(*init.shape))
         net, losses = models.load_model(args)
     device = net.device
-    tr.mark("load_model")
+    tr.mark(f"load_model (plan-core cache: {models.cache_stats['hits']} hits / {models.cache_stats['misses']} misses so far)")
 
     import os
 

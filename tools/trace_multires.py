@@ -11,6 +11,21 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from maua_style_b200 import image_ops, style, synthetic as O  # noqa: E402
 
+import gc
+
+_gc_t = {}
+
+
+def _gc_cb(phase, info):  # how long does the cyclic collector stop the host thread, and when?
+    if phase == "start":
+        _gc_t["t"] = time.perf_counter()
+    else:
+        dt = 1e3 * (time.perf_counter() - _gc_t.get("t", time.perf_counter()))
+        if dt > 2.0:
+            print(f"[trace] gc generation {info['generation']}: {dt:.1f} ms, {info['collected']} collected", file=sys.stderr, flush=True)
+
+
+gc.callbacks.append(_gc_cb)
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 tmp = tempfile.mkdtemp(prefix="maua_trace_")
