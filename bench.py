@@ -413,7 +413,7 @@ def side_leg(size, optimizer, dev, K, W, pk, covariance=False, prefill=100, arch
         out["loss"] = "covariance (--use_covariance), blend 3:1"
     if arch != "vgg19":
         out["model"] = {"prune": "channel-pruned VGG-16 (zero-padded to tileable channel counts)",
-                        "nin": "NIN (11x11/4 and 5x5 layers as direct fp32 convolutions, 1x1 / 3x3 layers on the tensor core)"}[arch]
+                        "nin": "NIN (1x1 / 3x3 / 5x5 layers: conv_tc_kernel; 11x11/4 image layer: im2col + pointwise tcgen05 GEMM; 3x3/2 ceil pools)"}[arch]
         out["kernel_breakdown_ms"] = {}
         for r in job.conv_profile():
             out["kernel_breakdown_ms"][r["name"]] = round(out["kernel_breakdown_ms"].get(r["name"], 0.0) + r["ms"], 4)

@@ -403,7 +403,9 @@ MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* plan, int enable);
  * the partial accumulators costs more than the idle SMs it recovers (profiles/r02_splitk_ab.txt); results agree with the
  * unsplit plan to fp32 summation order. */
 MAUA_API int maua_plan_set_splitk(maua_plan_t* plan, int enable);
-/* Tail handling of the persistent conv kernels: 0 whole tiles, 1 K-split, 2 half-N items (default; MAUA_CONV_TAIL in the
+/* Tail handling of the persistent conv kernels: 0 whole tiles, 1 K-split (parts meet in the last part's CTA through flags), 2
+ * half-N items, 3 = 2 plus: a launch with FEWER tiles than SMs (the deep layers at <= 512^2) is K-split over all SMs, every part
+ * dumps its raw accumulators and a small reduce kernel behind it sums them and runs the fused epilogue (MAUA_CONV_TAIL in the
  * environment at plan creation).  Half-N items compute exactly the sums of the whole tile, so results do not change. */
 MAUA_API int maua_plan_set_conv_tail(maua_plan_t* plan, int mode);
 /* Per-launch timing for roofline reports: when enabled, a CUDA event is recorded on the caller's stream after every

@@ -165,9 +165,9 @@ MAUA_API int maua_conv_tile_plan(int h, int w, int cin, int cout, int ntaps, int
     a.B = 1; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ntaps = ntaps; a.K2 = k2;
     // K-split plans assume the workspace exists (the plan owns one)
     static float dummy_ws; static unsigned int dummy_flag;
-    if (tail_mode == 1) { a.splitk_ws = &dummy_ws; a.splitk_flags = &dummy_flag; }
+    if (tail_mode == 1 || tail_mode == 3) { a.splitk_ws = &dummy_ws; a.splitk_flags = &dummy_flag; }
     a.tail_mode = tail_mode;
-    conv_tile_plan(a, sms, tail_mode == 1 ? 1 : (tail_mode == 2 ? 2 : 0), plan6, plan6 + 1, plan6 + 2, plan6 + 3, plan6 + 4, plan6 + 5);
+    conv_tile_plan(a, sms, tail_mode >= 1 && tail_mode <= 3 ? tail_mode : 0, plan6, plan6 + 1, plan6 + 2, plan6 + 3, plan6 + 4, plan6 + 5);
     return MAUA_OK;
 }
 

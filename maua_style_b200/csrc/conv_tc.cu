@@ -51,6 +51,8 @@ struct ConvKParams {
     // deterministic) and runs the fused epilogue.
     int full_tiles, split, total_items;
     int tail_halves;  // 1: the tail tiles are computed as two half-N items each (no hand-over) instead of K-split parts
+    int split_nowait; // 1 (tail mode 3, only when EVERY tile is split): all parts dump their raw accumulators and return; the
+                      // sums and the fused epilogue are done by conv_splitk_reduce_kernel launched right behind (no flags, no wait)
     float* splitk_ws;
     unsigned int* splitk_flags;
     int direct;  // 1: register -> global epilogue (needed for the content / addend / fp32-mask terms), 0: TMA-store epilogue
@@ -337,9 +339,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             // split-K: workspace of this tile's partial accumulators, [part][rank][m][row][BN]; flags [slot][rank][quadrant]
             constexpr size_t kPartElems = static_cast<size_t>(MT) * 128 * BN;
-            float* ws_tile = p.splitk_ws + static_cast<size_t>(item.slot) * (p.split - 1) * CG * kPartElems;
+            float* ws_tile = p.splitk_ws + static_cast<size_t>(item.slot) * (p.split - (p.split_nowait ? 0 : 1)) * CG * kPartElems;
             unsigned int* flag = p.splitk_flags + (static_cast<size_t>(item.slot) * CG + rank) * 4 + q;
-            if (item.part < item.nparts - 1) {
+            if (item.part < item.nparts - 1 || (p.split_nowait && item.nparts > 1)) {
                 // not the last part of a split tile: hand the raw partial sums to the CTA (pair) that holds the last part
                 float* dst = ws_tile + (static_cast<size_t>(item.part) * CG + rank) * kPartElems;
 #pragma unroll 1
@@ -354,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(flag, 1u);
+                if (lane == 0 && !p.split_nowait) atomicAdd(flag, 1u);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
@@ -669,6 +671,7 @@ SplitPlan plan_split(long tiles, int units, int ngroups, int mode, int bn = 0, i
     SplitPlan sp{(int)tiles, 1, (int)tiles, 0};
     const int rem = (int)(tiles % units);
     if (mode == 0 || rem == 0) return sp;
+    if (mode == 3 && tiles >= units) mode = 2;  // K-split + reduce kernel only when the whole launch is one partial wave
     if (mode == 2) {
         if (2 * rem > units || bn < (cg == 2 ? 128 : 64)) return sp;
         sp.full_tiles = (int)tiles - rem;
@@ -692,6 +695,7 @@ int conv_groups(const ConvArgs& a) {
 // tail handling requested by the caller: ConvArgs::tail_mode (K-split additionally needs the workspace)
 int effective_tail_mode(const ConvArgs& a) {
     if (a.tail_mode == 1) return (a.splitk_ws && a.splitk_flags) ? 1 : 0;
+    if (a.tail_mode == 3) return (a.splitk_ws && !a.ep.pool_out) ? 3 : 2;
     return a.tail_mode == 2 ? 2 : 0;
 }
 
@@ -760,6 +764,89 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, in
     return best_sp;
 }
 
+// Tail mode 3: sum of the K-split parts of every tile + the fused epilogue of ConvEpilogue (same order of operations as the
+// in-kernel epilogue; fixed summation order: deterministic).  Workspace layout: [tile][part][rank][m][row][BN] raw accumulators.
+struct SplitReduce {
+    const float* ws;
+    int split, ntiles, BN, MT, CG;
+    int B, H, W, Cout, tiles_w, tiles_h, n_tiles;
+    ConvEpilogue ep;
+};
+__global__ void __launch_bounds__(256)
+conv_splitk_reduce_kernel(const SplitReduce r) {
+    pdl_wait();
+    pdl_trigger();
+    const int c4n = r.BN / 4;
+    const long total = (long)r.ntiles * r.CG * r.MT * 128 * c4n;
+    const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;  // (total is a multiple of 32: whole warps are live or dead together)
+    if (idx >= total) return;
+    const int c = (int)(idx % c4n) * 4;
+    long t = idx / c4n;
+    const int row = (int)(t % 128);
+    t /= 128;
+    const int m = (int)(t % r.MT);
+    t /= r.MT;
+    const int rank = (int)(t % r.CG);
+    const int tile = (int)(t / r.CG);
+    const size_t part_elems = (size_t)r.MT * 128 * r.BN;
+    const float* src = r.ws + ((size_t)tile * r.split * r.CG + rank) * part_elems + ((size_t)m * 128 + row) * r.BN + c;
+    float4 acc = __ldcg(reinterpret_cast<const float4*>(src));
+    for (int pp = 1; pp < r.split; ++pp) {
+        const float4 u = __ldcg(reinterpret_cast<const float4*>(src + (size_t)pp * r.CG * part_elems));
+        acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+    }
+    const int nt = tile % r.n_tiles;
+    int pt = tile / r.n_tiles;
+    const int tw = pt % r.tiles_w;
+    pt /= r.tiles_w;
+    const int th = pt % r.tiles_h;
+    const int b = pt / r.tiles_h;
+    const int h = th * (TILE_H * r.MT * r.CG) + rank * (TILE_H * r.MT) + m * TILE_H + row / TILE_W;
+    const int w = tw * TILE_W + row % TILE_W;
+    const int n = nt * r.BN + c;
+    const bool valid = h < r.H && w < r.W;
+    const ConvEpilogue& ep = r.ep;
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    const size_t pix = ((size_t)b * r.H + h) * r.W + w;
+    const size_t off = pix * r.Cout + n;
+    if (valid) {
+        if (ep.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n)); v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w; }
+        if (ep.cont_f) {
+            const float cc = *ep.cont_coef;
+            const float4 f = *reinterpret_cast<const float4*>(ep.cont_f + off), tg = *reinterpret_cast<const float4*>(ep.cont_t + off);
+            v[0] += cc * (f.x - tg.x); v[1] += cc * (f.y - tg.y); v[2] += cc * (f.z - tg.z); v[3] += cc * (f.w - tg.w);
+        }
+        if (ep.addend) { const float4 a4 = *reinterpret_cast<const float4*>(ep.addend + off); v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w; }
+        if (ep.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+        if (ep.mask_src) {
+            const float4 mk = *reinterpret_cast<const float4*>(ep.mask_src + off);
+            v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f; v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
+        }
+        if (ep.mask_bits) {
+            const uint32_t mk = ep.mask_bits[pix * (r.Cout >> 5) + (n >> 5)] >> (n & 31);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ((mk >> i) & 1u) ? v[i] : 0.f;
+        }
+        if (ep.round) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = round_tf32(v[i]);
+        }
+        const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(ep.out + off) = o;
+        if (ep.out2) *reinterpret_cast<float4*>(ep.out2 + off) = o;
+    }
+    if (ep.mask_out) {
+        // sign bitmap: the 8 threads that hold the 32 channels of one word are 8 consecutive lanes
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << ((n & 31) + i);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+        if (valid && (n & 31) == 0) ep.mask_out[pix * (r.Cout >> 5) + (n >> 5)] = bits;
+    }
+}
+
 template <int BN, int MT, int CG, bool POOL, int KS = 3>
 int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = ConvCfg<BN, MT, CG, KS>;
@@ -809,6 +896,7 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     const SplitPlan sp = plan_split(p.total_tiles, units, conv_groups(a), effective_tail_mode(a), BN, CG);
     p.full_tiles = sp.full_tiles; p.split = sp.split; p.total_items = sp.items; p.tail_halves = sp.halves;
     p.splitk_ws = a.splitk_ws; p.splitk_flags = a.splitk_flags;
+    p.split_nowait = (effective_tail_mode(a) == 3 && sp.split > 1 && !sp.halves && sp.full_tiles == 0) ? 1 : 0;
     const int grid = CG * (p.total_items < units ? p.total_items : units);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -831,6 +919,15 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     MAUA_CUDA_CHECK((cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MT, CG, POOL, KS>, tmA, tmB, tmA2, tmB2, tmOut, tmOut2, p)));
+    if (p.split_nowait) {
+        // sums of the K-split parts + the fused epilogue, one float4 per thread
+        SplitReduce r;
+        r.ws = p.splitk_ws; r.split = p.split; r.ntiles = p.total_tiles; r.BN = BN; r.MT = MT; r.CG = CG;
+        r.B = p.B; r.H = p.H; r.W = p.W; r.Cout = p.Cout; r.tiles_w = p.tiles_w; r.tiles_h = p.tiles_h; r.n_tiles = p.n_tiles;
+        r.ep = a.ep;
+        const long total = (long)p.total_tiles * CG * MT * 128 * (BN / 4);
+        MAUA_CUDA_CHECK(launch_pdl<PDL_CONV>(conv_splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, r));
+    }
     return MAUA_OK;
 }
 

@@ -571,7 +571,7 @@ MAUA_API int maua_plan_set_splitk(maua_plan_t* p, int enable) {
 }
 
 MAUA_API int maua_plan_set_conv_tail(maua_plan_t* p, int mode) {
-    MAUA_REQUIRE(p && mode >= 0 && mode <= 2, "maua_plan_set_conv_tail: bad arguments");
+    MAUA_REQUIRE(p && mode >= 0 && mode <= 3, "maua_plan_set_conv_tail: bad arguments");
     p->splitk = mode == 1;
     p->conv_tail = mode == 1 ? 0 : mode;
     return MAUA_OK;
@@ -752,10 +752,16 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             a.in = cur; a.wg = exact ? e.wg32 : e.wg;
             a.ep.out = e.out; a.ep.bias = e.bias; a.ep.relu = 1; a.ep.round = rnd;
             a.ep.mask_out = e.bits;
-            if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
+            if (p->splitk || p->conv_tail == 3) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
             a.tail_mode = p->splitk ? 1 : p->conv_tail;
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
-            if (p->fuse_pool && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && !p->entries[i + 1].pool3 &&
+            bool split_layer = false;  // tail mode 3: a launch of fewer tiles than SMs is K-split + reduced; its pool stays separate
+            if (a.tail_mode == 3 && p->impl != MAUA_IMPL_REF && !exact) {
+                int bn, mt, cg, full, st_, sp_;
+                conv_tile_plan(a, 148, 3, &bn, &mt, &cg, &full, &st_, &sp_);
+                split_layer = full == 0 && sp_ > 1 && st_ > 0;
+            }
+            if (p->fuse_pool && !split_layer && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && !p->entries[i + 1].pool3 &&
                 e.ks == 3 && e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
                 a.ep.pool_avg = p->avg_pool;
@@ -940,7 +946,7 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     };
     auto run_conv = [&](ConvArgs& a) -> int {
         p->launches_bwd++;
-        if (p->splitk) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
+        if (p->splitk || p->conv_tail == 3) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
         a.tail_mode = p->splitk ? 1 : p->conv_tail;
         const int r = conv_dispatch(a, p->impl, st);
         const double px = (double)a.H * a.W;

@@ -190,6 +190,11 @@ def test_conv_tile_plan_host_logic():
     assert whole == 0 and 2 <= s <= 8 and split_tiles * s <= 148 // cg
     bn, mt, cg, whole, split_tiles, s = plan(16, 16, 64, 64, split=1)   # 6 k-groups: too short to split
     assert s == 1 and split_tiles == 0
+    # tail mode 3: a launch with fewer tiles than CTA units is K-split as a whole (parts reduced by a second kernel); a launch
+    # with at least one full wave falls back to the half-N tail
+    bn, mt, cg, whole, split_tiles, s3 = plan(32, 32, 512, 512, split=3)
+    assert whole == 0 and s3 >= 2 and split_tiles * s3 <= 148 // cg
+    assert plan(256, 256, 256, 256, split=3) == plan(256, 256, 256, 256, split=2)
     for hw in (5, 37, 724, 1448):                                        # every extent gets a plan that covers it
         bn, mt, cg, whole, split_tiles, s = plan(hw, hw, 128, 128)
         tiles = -(-hw // 16) * -(-hw // (8 * mt * cg)) * (128 // bn)
