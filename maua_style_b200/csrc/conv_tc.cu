@@ -741,7 +741,8 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, in
                 const SplitPlan sp = plan_split(tiles, units, ngroups, tail_mode, bn, cg);
                 // a half-N item does half the MMA work at the (lower) rate of the half-width shape
                 const double waves = sp.halves ? (double)(sp.full_tiles / units) + 0.5 * shape_rate(bn, mt, cg) / shape_rate(bn / 2, mt, cg)
-                                     : sp.split > 1 ? (double)(sp.full_tiles / units) + 1.0 / sp.split + 0.03
+                                     // (tail mode 3 hands the parts over through a second kernel: ~ a third of a short wave, measured)
+                                     : sp.split > 1 ? (double)(sp.full_tiles / units) + 1.0 / sp.split + (tail_mode == 3 ? 0.35 : 0.03)
                                                     : (double)((tiles + units - 1) / units);
                 const double eff = (double)tiles / (waves * units);
                 // rows of the (pair) tile that exist: ragged bottoms waste MMA work

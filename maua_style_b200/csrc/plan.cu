@@ -760,6 +760,8 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 int bn, mt, cg, full, st_, sp_;
                 conv_tile_plan(a, 148, 3, &bn, &mt, &cg, &full, &st_, &sp_);
                 split_layer = full == 0 && sp_ > 1 && st_ > 0;
+                // a layer that feeds a pool keeps the pooling fused unless the split is deep enough to pay for a separate pool pass
+                if (split_layer && sp_ < 8 && i + 1 <= last_needed && p->entries[i + 1].pool) { split_layer = false; a.tail_mode = 2; }
             }
             if (p->fuse_pool && !split_layer && !boundary_out && i + 1 <= last_needed && p->entries[i + 1].pool && !p->entries[i + 1].pool3 &&
                 e.ks == 3 && e.H >= 2 && e.W >= 2) {

@@ -302,6 +302,54 @@ def test_half_n_tail_items_are_bit_identical_to_whole_tiles(ckpt, hw):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize("hw,pooling", [((64, 64), "avg"), ((90, 122), "avg"), ((256, 256), "avg"), ((200, 328), "avg"), ((64, 64), "max")])
+def test_reduce_kernel_tail_agrees_with_the_default_plan(ckpt, hw, pooling):
+    """Conv tail mode 3: launches with fewer tiles than SMs (the deep layers at small sizes) are K-split over all SMs and a
+    second kernel sums the parts and runs the fused epilogue (bias / content / addend / ReLU / sign-bitmap mask / rounding /
+    bitmap output).  Same operands, fp32 sums in another order: features, losses and the image gradient agree with the
+    default plan to summation-order level (average pooling: no arg-max flips in the comparison; the max-pooling case is
+    bounded like two TF32 realisations), and the mode is deterministic."""
+    from maua_style_b200 import optim
+
+    z, meta = load_golden("adam_gram_90x122")
+    meta = dict(meta)
+    meta["over"] = dict(meta["over"], pooling=pooling)
+    meta["h"], meta["w"] = hw
+    meta["style_hw"] = [list(hw)]
+    content, styles, init = golden_inputs(meta)
+    res = []
+    for mode in (2, 3, 3):
+        args, net, losses, _ = build(ckpt, meta)
+        net.set_conv_tail(mode)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, styles, args)
+        for m in losses:
+            m.mode = "loss"
+        v, g = optim.feval(net, init.clone().cuda())
+        res.append((v.clone(), g.clone(), [net.tap_feature(t) for t in range(len(net.taps))]))
+        net_taps = list(net.taps)
+        del net, losses
+    ferr = max(rel(a, b) for a, b in zip(res[1][2], res[0][2]))
+    gerr = rel(res[1][1], res[0][1])
+    report(f"tail mode 3 vs 2 {hw} {pooling}: features rel {ferr:.2e}, gradient rel {gerr:.2e}")
+    if hw == (64, 64):
+        # which of the two is closer to the fp32 oracle?  The tensor core's fp32 accumulate truncates, so the error of a sum grows
+        # with the length of its MMA chain (576 MMAs for K = 4608): the K-split parts have 1/8 of the chain
+        cfg = oracle_cfg(meta)
+        onet = O.OracleNet(O.he_init_vgg19(0), cfg)
+        taps = {}
+        onet(init.clone(), taps=taps)
+        names = O.relu_names(O.VGG19_CHANNELS)
+        for mode, r in ((2, res[0]), (3, res[1])):
+            errs = [rel(f, taps[names[ridx]]) for f, (ridx, _) in zip(r[2], net_taps)]
+            report(f"   tail mode {mode} features vs the fp32 oracle: " + " ".join(f"{e:.2e}" for e in errs))
+    # (two TF32 realisations: the differences are of the size of the TF32 operand rounding itself)
+    assert ferr < 2e-3
+    assert gerr < (1e-2 if pooling == "avg" else 5e-2)
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-2)
+    assert torch.equal(res[1][1], res[2][1]) and torch.equal(res[1][0], res[2][0])  # deterministic
+
+
 def test_temporal_loss_and_autograd_interface(ckpt):
     """vid_img path: set_temporal_targets + weighted temporal ContentLoss (loss.py:46-54) through net(x).backward()."""
     from maua_style_b200 import optim

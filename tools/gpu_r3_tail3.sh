@@ -2,7 +2,7 @@
 # A/B of conv tail mode 3 (K-split + reduce kernel for launches with fewer tiles than SMs) against the default mode 2
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 OUT=gpurun_out/${1:-r03t}; mkdir -p $OUT
-MAUA_CONV_TAIL=3 timeout 600 python -m pytest tests/test_plan_gpu.py tests/test_zz_arch_gpu.py tests/test_exact_gpu.py tests/test_fullsize_gpu.py -q -x 2>&1 | tail -3
+MAUA_CONV_TAIL=3 timeout 600 python -m pytest tests/test_plan_gpu.py tests/test_zz_arch_gpu.py tests/test_exact_gpu.py tests/test_fullsize_gpu.py tests/test_video_gpu.py tests/test_image_gpu.py -q -s 2>&1 | grep -E "PSNR|passed|failed|FAILED|assert" | tail -40
 for S in 256 512 1024; do
   for M in 2 3 2 3; do
     MAUA_CONV_TAIL=$M timeout 150 python bench.py --size $S --steps 40 --warmup 5 --no-cpu-baseline --no-multires --no-extras --profile-out $OUT/prof_${S}_$M.json > $OUT/b_${S}_$M.json 2> $OUT/b_${S}_$M.err
