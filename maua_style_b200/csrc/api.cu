@@ -22,18 +22,24 @@ void set_last_error(const char* fmt, ...) {
 }
 
 int check_device_arch(int device) {
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    // two attribute queries, cached per device: cudaGetDeviceProperties costs 60-270 ms per call on a busy B200 (measured:
+    // profiles/r03_multires_trace.txt, "load_model" of a warm job) and this check runs for every network that is built
+    static int ok_major[64] = {0};
+    if (device >= 0 && device < 64 && ok_major[device] == 10) return MAUA_OK;
+    int major = 0, minor = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
     if (e != cudaSuccess) {
-        set_last_error("cudaGetDeviceProperties(%d) failed: %s (no CUDA device? this library has no CPU fallback)",
+        cudaGetLastError();
+        set_last_error("cudaDeviceGetAttribute(%d) failed: %s (no CUDA device? this library has no CPU fallback)",
                        device, cudaGetErrorString(e));
         return MAUA_ERR_CUDA;
     }
-    if (prop.major != 10) {
-        set_last_error("device %d is sm_%d%d; libmaua_b200 is built for sm_100a (B200) only", device, prop.major,
-                       prop.minor);
+    if (major != 10) {
+        set_last_error("device %d is sm_%d%d; libmaua_b200 is built for sm_100a (B200) only", device, major, minor);
         return MAUA_ERR_ARCH;
     }
+    if (device >= 0 && device < 64) ok_major[device] = major;
     return MAUA_OK;
 }
 

@@ -30,7 +30,7 @@ from typing import List
 import torch
 
 from . import _lib
-from .loss import ContentLoss, StyleLoss, TVLoss
+from .loss import ContentLoss, StyleLoss
 
 MODE_EXTERNAL = 3
 
