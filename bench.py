@@ -124,7 +124,8 @@ def workload_config(size, optimizer):
         "workload": f"VGG-19 Gram style transfer {size}x{size}, content relu4_2 + style relu1_1..relu5_1 + TV, "
                     f"{optimizer} (BASELINE.json configs[1] final scale)",
         "image": [size, size], "styles": 1, "optimizer": optimizer, "lbfgs_history": 100,
-        "weights": "He-normal random init (seed 0)", "timing": "inputs larger than L2: 1.2 GB of activations per step",
+        "weights": "He-normal random init (seed 0)", "init": "content image (--init content / the up-sampled previous scale)",
+        "timing": "inputs larger than L2: 1.2 GB of activations per step",
         "sharding": "one independent image per GPU, no collective",
     }
 
@@ -155,7 +156,7 @@ def _reference_rate(size, optimizer, steps, warmup, budget_s):
     def job(sz, n_iters, stamps):
         content = S.synthetic_image(sz, sz, seed=1, smooth=True)
         style = S.synthetic_image(sz, sz, seed=2)
-        init = S.synthetic_image(sz, sz, seed=4) * 0.25
+        init = content.clone()  # same starting point as the GPU arm (Job): the content image
         h = net.register_forward_pre_hook(lambda m, inp: stamps.append(time.perf_counter()))
         try:
             ref.optim.optimize(content, [style], init.clone(), n_iters, rargs, net, losses)
@@ -344,7 +345,11 @@ class Job:
             styles = [O.synthetic_image(h2, w2, seed=2), O.synthetic_image(w2, h2, seed=3, smooth=True)]
         else:
             styles = [O.synthetic_image(size, size, seed=2)]
-        init = O.synthetic_image(size, size, seed=4 + 10 * rank) * 0.25
+        # the pastiche starts from the content image (style.py:56-57 `--init content`; at the later scales of a multi-resolution job
+        # it is the up-sampled previous result, style.py:64-66): an image-like starting point.  A random starting point makes the
+        # line-search-free L-BFGS of the reference reject every curvature pair at <= 512^2 with random-init weights (y.s <= 1e-10,
+        # torch's gate), which would time the loop at history 1 instead of 100 -- the history length reached is reported
+        init = content.clone()
         optim.set_content_targets(self.net, content.to(dev), a)
         optim.set_style_targets(self.net, [s.to(dev) for s in styles], a)
         for m in self.losses:
@@ -359,6 +364,19 @@ class Job:
         for _ in range(history_prefill if optimizer == "lbfgs" else 3):
             self.step()
         torch.cuda.synchronize(dev)
+
+    def lbfgs_state(self):
+        """(iterations, history length, halted flag) of the device L-BFGS, or None for Adam."""
+        import ctypes as C
+
+        from maua_style_b200 import _lib
+
+        if self.optimizer != "lbfgs":
+            return None
+        n, h, halted = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.load().maua_lbfgs_query(self.opt._state, C.byref(n), C.byref(h), C.byref(halted), _lib.stream_ptr()))
+        return {"iterations": n.value, "history_len": h.value, "halted": bool(halted.value),
+                "pastiche_finite": bool(torch.isfinite(self.pastiche).all())}
 
     def launches_per_step(self):
         f, b = self.net.last_launches()
@@ -408,6 +426,8 @@ def side_leg(size, optimizer, dev, K, W, pk, covariance=False, prefill=100, arch
     out = {"size": size, "optimizer": optimizer, "value": K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
            "warmup": W, "conv_tflops": tf, "conv_frac_of_tf32_burst": tf / (pk["bf16_burst"] / 2.0),
            "feval_ms": feval_ms, "gpu_launches_per_step": job.launches_per_step(), "cuda_graph": job.step.graph is not None}
+    if optimizer == "lbfgs":
+        out["lbfgs_state"] = job.lbfgs_state()
     if covariance:
         out["styles"] = 2
         out["loss"] = "covariance (--use_covariance), blend 3:1"
@@ -606,6 +626,7 @@ def run_ours(args):
                        "updated image + loss; copies double-buffered on separate streams; wall clock, max over ranks"},
         "gpu_launches": gpu_launches,
         "cuda_graph": bool(step.graph is not None),
+        "lbfgs_state": job.lbfgs_state(),
     }
 
     # ---- configs[4] at this N: images_per_gpu x N images through the sharded runner (all ranks take part) ----
