@@ -71,16 +71,28 @@ struct ConvCfg {
     static constexpr int A_STAGE = A_ROWS * ROW_BYTES;             // 36864 (MT=2) / 20480 (MT=1): multiples of 1024
     static constexpr int B_STAGE = BNL * 128;
     static constexpr int BUDGET = 192 * 1024;                      // operand rings; 32 KB more go to the epilogue staging
-    static constexpr int NA = (3 * A_STAGE + 4 * B_STAGE <= BUDGET) ? 3 : 2;
+    // Pipeline shape.  Every barrier hand-over costs the issuing threads a few hundred cycles (try_wait + elect + tcgen05.commit:
+    // measured with the loads and the MMAs switched off, tools/exp_conv_chain.py: ~440 cycles per weight step), which a
+    // weight step of a narrow tile (4 * MT MMAs of N <= 128: 64..512 tensor cycles) does not cover -- the 64-channel layers
+    // ran at <= 50 % tensor-pipe-active and every launch of the small scales was a chain of 3 * 48 such steps.  Narrow shapes
+    // therefore use MERGED stages: one activation box + its KS weight tiles behind ONE full / ONE empty barrier (one wait and
+    // one commit per k-group instead of KS waits and KS + 1 commits), as many stages as fit (>= 3, <= 8).  Wide shapes, whose
+    // weight tiles are too big for three such stages and whose steps are long enough, keep separate activation / weight rings.
+    static constexpr int STAGE = A_STAGE + KS * B_STAGE;
+    static constexpr int NS_RAW = BUDGET / STAGE;
+    static constexpr bool MERGED = NS_RAW >= 3;
+    static constexpr int NA = MERGED ? (NS_RAW > 8 ? 8 : NS_RAW) : ((3 * A_STAGE + 4 * B_STAGE <= BUDGET) ? 3 : 2);
     static constexpr int NB_RAW = (BUDGET - NA * A_STAGE) / B_STAGE;
-    static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
+    static constexpr int NB = MERGED ? 0 : (NB_RAW > 8 ? 8 : NB_RAW);
+    static constexpr int A_PITCH = MERGED ? STAGE : A_STAGE;      // distance between the activation boxes of two stages
     static constexpr int ACC_COLS = MT * BN;                       // one accumulator set: 32..512 columns
     static constexpr int NACC = ACC_COLS <= 256 ? 2 : 1;           // double-buffered when TMEM has room
     static constexpr int TMEM_COLS_RAW = NACC * ACC_COLS;
     static constexpr int TMEM_COLS = TMEM_COLS_RAW < 32 ? 32 : TMEM_COLS_RAW;  // power of two, 32..512
-    static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ +
-                                      N_STAGE_BOX * STAGE_BOX_BYTES;
-    static_assert(NB >= 3, "weight ring too shallow");
+    static constexpr int RING_BYTES = NA * A_PITCH + NB * B_STAGE;
+    static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + N_STAGE_BOX * STAGE_BOX_BYTES;
+    static_assert(MERGED || NB >= 3, "weight ring too shallow");
+    static_assert(A_PITCH % 1024 == 0 && B_STAGE % 1024 == 0, "operand tiles must stay 1024-byte aligned (128B swizzle atoms)");
     static_assert(CG == 1 || CG == 2, "CTA group size");
     static_assert(BNL % 16 == 0 && BNL >= 16, "per-CTA weight rows");
 };
@@ -112,15 +124,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smemA = smem;
-    uint8_t* smemB = smem + NA * Cfg::A_STAGE;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smemB + NB * Cfg::B_STAGE);
+    uint8_t* smemB = smem + NA * Cfg::A_PITCH;  // (separate weight ring; merged stages keep their weight tiles behind the box)
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
     uint64_t* a_empty = a_full + NA;
     uint64_t* b_full = a_empty + NA;
     uint64_t* b_empty = b_full + NB;
     uint64_t* tmem_full_bar = b_empty + NB;        // [NACC]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [NACC]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    uint8_t* stage_box = smemB + NB * Cfg::B_STAGE + 1024;  // 1024-byte aligned (ring sizes are multiples of 1024)
+    uint8_t* stage_box = smem + Cfg::RING_BYTES + 1024;  // 1024-byte aligned (ring sizes are multiples of 1024)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -230,10 +242,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int sa = ia % NA;
                 mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
                 ++ia;
-                uint8_t* sA = smemA + sa * Cfg::A_STAGE;
-                if (g < ng1 && halo) {
-                    const int dxi = g / cpt;                  // 0..KS-1  <->  dx = -KS/2 .. +KS/2
-                    const int c0 = (g - dxi * cpt) * KCHUNK;
+                uint8_t* sA = smemA + sa * Cfg::A_PITCH;
+                const bool is_halo = g < ng1 && halo;
+                const bool aux = g >= ng1;
+                const int dxi = is_halo ? g / cpt : 0;        // 0..KS-1  <->  dx = -KS/2 .. +KS/2
+                const int c0 = (is_halo ? g - dxi * cpt : (aux ? g - ng1 : g)) * KCHUNK;
+                if constexpr (Cfg::MERGED) {
+                    // one stage = the activation box + its weight tiles, all against one barrier
+                    if (elect_one()) {
+                        uint8_t* sB = sA + Cfg::A_STAGE;
+                        if (is_halo) {
+                            arm(&a_full[sa], Cfg::A_STAGE + KS * Cfg::B_STAGE);
+                            load_a(sA, &tmA, &a_full[sa], c0, w0 + dxi - KS / 2, h0 - KS / 2, b);
+#pragma unroll
+                            for (int dyi = 0; dyi < KS; ++dyi)
+                                load_b(sB + dyi * Cfg::B_STAGE, &tmB, &a_full[sa], (dyi * KS + dxi) * p.Cin + c0, n0 + nb0);
+                        } else {
+                            arm(&a_full[sa], MT * A_BYTES + Cfg::B_STAGE);
+                            load_a(sA, aux ? &tmA2 : &tmA, &a_full[sa], c0, w0, h0, b);
+                            load_b(sB, aux ? &tmB2 : &tmB, &a_full[sa], c0, n0 + nb0);
+                        }
+                    }
+                    __syncwarp();
+                } else if (is_halo) {
                     if (elect_one()) {
                         arm(&a_full[sa], Cfg::A_STAGE);
                         load_a(sA, &tmA, &a_full[sa], c0, w0 + dxi - KS / 2, h0 - KS / 2, b);
@@ -250,8 +281,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __syncwarp();
                     }
                 } else {
-                    const bool aux = g >= ng1;
-                    const int c0 = (aux ? g - ng1 : g) * KCHUNK;
                     const int sb = ib % NB;
                     mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
                     ++ib;
@@ -288,9 +317,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int sa = ia % NA;
                 mbar_wait(&a_full[sa], (ia / NA) & 1);
                 ++ia;
-                const uint32_t sA = smem_u32(smemA + sa * Cfg::A_STAGE);
+                const uint32_t sA = smem_u32(smemA + sa * Cfg::A_PITCH);
                 const bool is_halo = (g < ng1) && halo;
                 const int nsteps = is_halo ? KS : 1;
+                if constexpr (Cfg::MERGED) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        for (int j = 0; j < nsteps; ++j) {
+                            const uint64_t bdesc = make_smem_desc_sw128(sA + Cfg::A_STAGE + j * Cfg::B_STAGE + b_off, 16, 1024);
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) {
+                                const uint32_t a_off = is_halo ? (m * TILE_H + j) * ROW_BYTES : m * A_BYTES;
+                                const uint64_t adesc = make_smem_desc_sw128(sA + a_off, 16, 1024);
+#pragma unroll
+                                for (int kk = 0; kk < KCHUNK / 8; ++kk)
+                                    mma(d_base + m * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (started | j | kk) ? 1u : 0u);
+                            }
+                        }
+                        commit(&a_empty[sa]);  // frees the stage (in both CTAs) once these MMAs have read it
+                        if (g == item.g1 - 1) commit(&tmem_full_bar[acc]);  // accumulator complete
+                    }
+                    __syncwarp();
+                    started = 1;
+                } else {
                 for (int j = 0; j < nsteps; ++j) {
                     const int sb = ib % NB;
                     mbar_wait(&b_full[sb], (ib / NB) & 1);
@@ -315,6 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     __syncwarp();
                     started = 1;
+                }
                 }
             }
         }
@@ -712,17 +762,18 @@ bool ks5_shape(int bn, int mt, int cg) {
 }
 
 SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, int& mt_out, int& cg_out) {
+    // (re-fitted after the merged pipeline stages: tools/sweep_conv_small.py with SWEEP_BIG=1, full-wave layers, round 2)
     auto shape_rate = [](int bn, int mt, int cg) -> double {
         if (cg == 2) {
-            if (bn == 256) return mt == 1 ? 1.00 : 0.88;
-            if (bn == 128) return mt == 2 ? 1.00 : 0.80;
-            if (bn == 64) return mt == 2 ? 0.75 : 0.47;
-            return mt == 2 ? 0.36 : 0.30;
+            if (bn == 256) return mt == 1 ? 0.96 : 0.90;
+            if (bn == 128) return mt == 1 ? 1.00 : 0.98;
+            if (bn == 64) return mt == 2 ? 0.83 : 0.78;
+            return mt == 2 ? 0.51 : 0.43;
         }
-        if (bn == 256) return mt == 1 ? 0.90 : 0.85;
-        if (bn == 128) return mt == 2 ? 0.73 : 0.66;
-        if (bn == 64) return mt == 2 ? 0.52 : 0.40;
-        return mt == 2 ? 0.30 : 0.25;
+        if (bn == 256) return mt == 1 ? 0.87 : 0.88;
+        if (bn == 128) return mt == 2 ? 0.76 : 0.63;
+        if (bn == 64) return mt == 2 ? 0.64 : 0.56;
+        return mt == 2 ? 0.385 : 0.32;
     };
     int best_bn = 32, best_mt = 1, best_cg = 1;
     double best = -1.0;

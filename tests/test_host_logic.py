@@ -168,8 +168,8 @@ def test_sharded_batch_normalises_the_weights_once_per_image(monkeypatch):
 
 def test_conv_tile_plan_host_logic():
     """maua_conv_tile_plan (csrc/conv_tc.cu choose_tile / plan_split), no GPU: shapes and K-split plans for VGG layers on 148
-    SMs.  Without split the 256-channel layers at 256 x 256 pixels take 256 pair tiles (3.46 waves of 74 pairs); with split
-    the last 34 tiles are halved along K; a split never leaves fewer than 4 k-groups per part."""
+    SMs.  Without split the 512-channel layers at 128 x 128 pixels take 256 pair tiles (3.46 waves of 74 pairs); with split
+    the last 34 tiles are halved along K (mode 1) or N (mode 2); a split never leaves fewer than 4 k-groups per part."""
     import ctypes as C
 
     from maua_style_b200 import _lib
@@ -181,10 +181,10 @@ def test_conv_tile_plan_host_logic():
         assert lib.maua_conv_tile_plan(h, w, cin, cout, taps, k2, sms, split, p) == 0
         return list(p)
 
-    assert plan(256, 256, 256, 256) == [256, 1, 2, 256, 0, 1]
-    assert plan(256, 256, 256, 256, split=1) == [256, 1, 2, 222, 34, 2]
-    assert plan(256, 256, 256, 256, split=2) == [256, 1, 2, 222, 34, 2]   # half-N tail: 34 tiles -> 68 independent items
-    assert plan(128, 128, 512, 512, split=2)[5] == 1                      # 128 tiles on 74 pairs: 2 x 54 > 74, stays whole
+    assert plan(128, 128, 512, 512) == [128, 1, 2, 256, 0, 1]
+    assert plan(128, 128, 512, 512, split=1) == [128, 1, 2, 222, 34, 2]
+    assert plan(128, 128, 512, 512, split=2) == [128, 1, 2, 222, 34, 2]   # half-N tail: 34 tiles -> 68 independent items
+    assert plan(256, 256, 256, 256, split=2) == [128, 1, 2, 512, 0, 1]    # 512 tiles on 74 pairs: 2 x 68 > 74, stays whole
     assert plan(1024, 1024, 64, 64) == [64, 2, 2, 2048, 0, 1]
     bn, mt, cg, whole, split_tiles, s = plan(16, 16, 512, 512, split=1)
     assert whole == 0 and 2 <= s <= 8 and split_tiles * s <= 148 // cg

@@ -1,0 +1,24 @@
+#!/bin/bash
+# round 2, third session: full -m gpu suite, conv sweeps (small + full-wave shapes), the 256^2 / 512^2 / 1024^2 legs
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+OUT=gpurun_out/${1:-r04c}; mkdir -p $OUT
+WHAT=${2:-tsb}
+if [[ $WHAT == *t* ]]; then
+  timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee $OUT/gpu_tests.txt
+fi
+if [[ $WHAT == *s* ]]; then
+  timeout 60 python tools/exp_conv_chain.py 2>/dev/null | tee $OUT/chain.txt
+  timeout 120 python tools/sweep_conv_small.py 9 2>&1 | tee $OUT/sweep.txt
+  SWEEP_BIG=1 timeout 120 python tools/sweep_conv_small.py 7 2>&1 | tee $OUT/sweep_big.txt
+fi
+if [[ $WHAT == *b* ]]; then
+for S in 256 512 1024; do
+  timeout 150 python bench.py --size $S --steps 40 --warmup 5 --no-cpu-baseline --no-multires --no-extras --profile-out $OUT/prof_${S}.json > $OUT/b_${S}.json 2> $OUT/b_${S}.err
+  python - $OUT/b_${S}.json $S <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+k = d['kernel_breakdown_ms']
+print(f"size {sys.argv[2]}: {d['ms_per_step']:.3f} ms  {d['value']:.1f} it/s  conv fwd {k['conv_fwd']:.4f} dgrad {k['conv_dgrad']:.4f} clk {d['clocks']['sm_mhz']} roofline {d['roofline']['achieved']:.0f} TF/s lbfgs {d.get('lbfgs_state')}")
+PY
+done
+fi
