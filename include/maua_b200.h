@@ -399,6 +399,13 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* plan, int impl);
  * convolution that produces its input instead of a separate pass over the activation (same arithmetic, bit for bit).
  * Off by default in this release (also switched on by MAUA_FUSE_POOL=1 in the environment at plan creation). */
 MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* plan, int enable);
+/* Loss modules of the forward pass on a side stream: the GramMatrix / StyleLoss (loss.py:67-91, 141-157) and ContentLoss MSE
+ * (loss.py:42-64) kernels of a tap only read that tap's feature map, so they can run next to the following convolutions
+ * (models.py:403-431 splices them between the layers; autograd orders them the same way).  mode -1 = automatic (on up to
+ * 640 x 640 pixels, where conv launches leave SMs idle), 0 = off, 1 = on; MAUA_SIDE_STREAM in the environment at plan creation.
+ * Forked with an event after the producing conv and joined once at the end of maua_plan_forward: works eagerly and inside
+ * stream capture; results are bit-identical (same kernels, same order per tap). */
+MAUA_API int maua_plan_set_side_stream(maua_plan_t* plan, int mode);
 /* K-split of the last partial wave of conv tiles (see maua_conv_tile_plan).  Off by default: on B200 the hand-over of
  * the partial accumulators costs more than the idle SMs it recovers (profiles/r02_splitk_ab.txt); results agree with the
  * unsplit plan to fp32 summation order. */

@@ -150,6 +150,14 @@ struct maua_plan {
     bool splitk = false;
     int conv_tail = 2;            // half-N items for the last partial wave (0: whole tiles; K-split: `splitk`)
     bool fuse_pool = true;        // pool inside the producing conv's epilogue (MAUA_FUSE_POOL=0 at plan creation: separate pass)
+    // Loss modules on a side stream (forward pass): the Gram SYRK + finalize of a style tap and the MSE of a content tap only
+    // read the tap's feature map, so they run on `side` next to the following convolutions (fork: event after the producing
+    // conv; join: once, at the end of the forward pass).  -1 = automatic: on while the image has at most kSideAutoPixels
+    // pixels -- there the conv launches leave SMs idle and every launch is latency; at 1024^2 the persistent conv CTAs hold
+    // every SM and the side work only delays them.  0 / 1 force it (MAUA_SIDE_STREAM, maua_plan_set_side_stream).
+    int side_mode = -1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t weight_bytes = 0;
     // workspaces
     float* arena = nullptr;
@@ -320,6 +328,11 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     p->device = device;
     p->avg_pool = d->avg_pool;
     if (const char* f = getenv("MAUA_FUSE_POOL")) p->fuse_pool = atoi(f) != 0;
+    if (const char* f = getenv("MAUA_SIDE_STREAM")) p->side_mode = atoi(f) < 0 ? -1 : (atoi(f) != 0);
+    // (created here, not at first use: a first forward pass may already run inside a stream capture)
+    MAUA_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    MAUA_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    MAUA_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     if (const char* f = getenv("MAUA_SPLITK")) p->splitk = atoi(f) != 0;
     if (const char* f = getenv("MAUA_CONV_TAIL")) p->conv_tail = atoi(f);
     p->begin = begin;
@@ -517,6 +530,10 @@ MAUA_API void maua_plan_destroy(maua_plan_t* p) {
     for (int i = 0; i < 3; ++i) cudaFree(p->gbuf[i]);
     cudaFree(p->reduce_ws); cudaFree(p->coef2);
     cudaFree(p->splitk_ws); cudaFree(p->splitk_flags);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->side) cudaStreamDestroy(p->side);
+    for (cudaEvent_t ev : p->ev_pool) cudaEventDestroy(ev);
     delete p;
 }
 
@@ -561,6 +578,12 @@ MAUA_API int maua_plan_set_impl(maua_plan_t* p, int impl) {
 MAUA_API int maua_plan_set_fuse_pool(maua_plan_t* p, int enable) {
     MAUA_REQUIRE(p, "maua_plan_set_fuse_pool: null plan");
     p->fuse_pool = enable != 0;
+    return MAUA_OK;
+}
+
+MAUA_API int maua_plan_set_side_stream(maua_plan_t* p, int mode) {
+    MAUA_REQUIRE(p && mode >= -1 && mode <= 1, "maua_plan_set_side_stream: mode must be -1 (automatic), 0 or 1");
+    p->side_mode = mode;
     return MAUA_OK;
 }
 
@@ -692,6 +715,19 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
         tv_pending = false;
     }
 
+    // ---- side stream for the loss modules (see maua_plan::side_mode) ----
+    constexpr long kSideAutoPixels = 640L * 640L;
+    const bool use_side = !p->profile && (p->side_mode == 1 || (p->side_mode < 0 && (long)H * W <= kSideAutoPixels));
+    bool forked = false;
+    // stream the loss modules of the tap that has just been produced on `st` are launched on
+    auto loss_stream = [&]() -> cudaStream_t {
+        if (!use_side) return st;
+        cudaEventRecord(p->ev_fork, st);
+        cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+        forked = true;
+        return p->side;
+    };
+
     // ---- feature stack ----
     const float* cur = p->stage_input;
     int curH = H, curW = W;
@@ -787,6 +823,9 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             const long P = (long)e.H * e.W;
             const long numel = P * e.C;
             const float numel_n = (float)(P * e.Cn);  // nn.MSELoss mean over the REAL elements (padded channels are zero)
+            const bool has_work = tp.kind == MAUA_TAP_STYLE ? tp.mode != MAUA_MODE_EXTERNAL
+                                                            : (tp.mode != MAUA_MODE_CAPTURE && tp.target && tio[t].target_elems == numel);
+            cudaStream_t ls = has_work ? loss_stream() : st;
             if (tp.kind == MAUA_TAP_STYLE && tp.mode == MAUA_MODE_EXTERNAL) {
                 // the feature map stays in the arena; loss value and backward term come from the caller
                 tp.active = true;
@@ -803,7 +842,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                     fuse.value_scale = tio[t].value_scale; fuse.rs = rs;
                 }
                 // one SYRK + one finalize kernel (which also produces G - A and the loss value in loss mode)
-                if ((rc = gram_launch(e.out, P, tp.C, tp.use_cov, tp.gram, tp.mean, tp.gram_ws, p->impl, st,
+                if ((rc = gram_launch(e.out, P, tp.C, tp.use_cov, tp.gram, tp.mean, tp.gram_ws, p->impl, ls,
                                       loss_mode ? &fuse : nullptr, tp.Cn)))
                     return rc;
                 p->launches_fwd += 2 + (tp.use_cov ? 2 : 0);
@@ -811,7 +850,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 if (!loss_mode) {
                     // loss.py:146-151: target (+)= blend_weight * gram   (B = 1)
                     if ((rc = axpby_launch(tp.gram, tp.target, (long)tp.C * tp.C, tio[t].capture_weight,
-                                           tio[t].capture_accumulate, st)))
+                                           tio[t].capture_accumulate, ls)))
                         return rc;
                     p->launches_fwd++;
                 } else {
@@ -827,7 +866,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 } else if (tp.target && tio[t].target_elems == numel) {  // loss.py:44: silently skipped on shape mismatch
                     MAUA_REQUIRE(losses_out, "losses_out is required in loss mode");
                     if ((rc = mse_value_launch(e.out, tp.target, numel, tio[t].value_scale / numel_n, losses_out + t,
-                                               rs, st)))
+                                               rs, ls)))
                         return rc;
                     p->launches_fwd++;
                     prof_mark(p, st, "content_loss", i, 0, 8.0 * numel);
@@ -836,6 +875,10 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 }
             }
         }
+    }
+    if (forked) {  // everything behind the forward pass on `st` (loss read-back, backward pass) sees the loss modules' results
+        MAUA_CUDA_CHECK(cudaEventRecord(p->ev_join, p->side));
+        MAUA_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_join, 0));
     }
     p->can_backward = keep_for_backward != 0;
     return MAUA_OK;

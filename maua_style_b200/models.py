@@ -379,6 +379,12 @@ class B200Net(nn.Module):
         for st in self._stages:
             _lib.check(self._lib.maua_plan_set_fuse_pool(st["plan"], int(enable)), "maua_plan_set_fuse_pool")
 
+    def set_side_stream(self, mode: int):
+        """Loss modules of the forward pass (Gram + StyleLoss, ContentLoss MSE) on a side stream next to the following
+        convolutions: -1 automatic (on up to 640 x 640 pixels), 0 off, 1 on.  Same kernels, bit-identical results."""
+        for st in self._stages:
+            _lib.check(self._lib.maua_plan_set_side_stream(st["plan"], int(mode)), "maua_plan_set_side_stream")
+
     def set_splitk(self, enable: bool):
         """K-split of the last partial wave of conv tiles (csrc/conv_tc.cu; off by default)."""
         for st in self._stages:

@@ -209,6 +209,42 @@ def test_fused_pool_epilogue_is_bit_identical_to_the_pool_kernel(pooling, hw, tm
 
 
 @pytest.mark.parametrize("cov", [False, True])
+def test_loss_modules_on_the_side_stream_are_bit_identical(cov, tmp_path):
+    """maua_plan_set_side_stream: the Gram / StyleLoss and ContentLoss kernels of the forward pass forked onto a side stream
+    (next to the following convolutions) and joined at the end of the forward pass -- same kernels, so losses and the image
+    gradient must be bit-identical to the single-stream plan, repeatedly (a missing join would show up as a stale loss), and a
+    whole captured optimisation must produce the same image."""
+    from maua_style_b200 import models, optim
+
+    path = tmp_path / "vgg19-random.pth"
+    save_checkpoint(path)
+    h, w = 200, 328
+    content = O.synthetic_image(h, w, seed=1, smooth=True)
+    style = O.synthetic_image(h, w, seed=2)
+    init = (O.synthetic_image(h, w, seed=4) * 0.25).cuda()
+    res = []
+    for mode in (0, 1):
+        args = make_args(path, tmp_path, use_covariance=cov, temporal_weight=0.0, optimizer="adam")
+        net, losses = models.load_model(args)
+        net.set_side_stream(mode)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, [style], args)
+        for m in losses:
+            m.mode = "loss"
+        fe = []
+        for k in range(3):
+            vec, g = optim.feval(net, init.clone() * (1.0 + 0.1 * k))
+            fe.append((vec.clone(), g.clone()))
+        out = optim.optimize(content.clone(), [style], init.clone().cpu(), 12, args, net=net, losses=losses)
+        res.append((fe, out.clone()))
+        del net, losses
+    for (v0, g0), (v1, g1) in zip(res[0][0], res[1][0]):
+        assert torch.equal(v0, v1)
+        assert torch.equal(g0, g1)
+    assert torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("cov", [False, True])
 def test_interleaved_gram_accumulators_reduce_the_accumulation_error(cov, tmp_path, monkeypatch):
     """MAUA_GRAM_NACC=4 (gram_tc_kernel<.., NACC = 4>): four interleaved TMEM accumulation chains instead of one.  Against
     the fp64 product of the stored 1024^2 tap features the error must not grow, and for the covariance (where the one-pass

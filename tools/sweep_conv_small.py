@@ -21,13 +21,13 @@ SHAPES = [(512, 512, 16, 16), (512, 512, 32, 32), (256, 512, 32, 32), (512, 512,
 if os.environ.get("SWEEP_BIG"):  # the layer shapes of the 1024^2 scale (full waves: what the chooser's shape_rate table is fitted to)
     SHAPES = [(64, 64, 1024, 1024), (64, 128, 512, 512), (128, 128, 512, 512), (128, 256, 256, 256), (256, 256, 256, 256),
               (256, 512, 128, 128), (512, 512, 128, 128), (512, 512, 64, 64)]
-CFGS = [(bn, mt, cg) for bn in (256, 128, 64, 32) for mt in (2, 1) for cg in (2, 1)]
+CFGS = [(bn, mt, cg) for bn in (256, 128, 64, 32) for mt in (2, 1) for cg in (2, 1)] + [(64, 1, 2, 1)]  # last: nine-tap geometry
 flush = torch.empty(64 << 20, device="cuda")  # 256 MB: evict L2 between timed launches
 
 
 def time_cfg(x, wg, b, y, cin, cout, h, w, force):
     if force:
-        os.environ["MAUA_CONV_FORCE"] = "%d,%d,%d" % force
+        os.environ["MAUA_CONV_FORCE"] = ",".join(str(v) for v in force)
     else:
         os.environ.pop("MAUA_CONV_FORCE", None)
     ts = []
@@ -58,5 +58,5 @@ for cin, cout, h, w in SHAPES:
     res.sort()
     fl = 2.0 * 9 * cin * cout * h * w
     print(f"conv {cin}->{cout} {h}x{w} ({fl / 1e9:.2f} GFLOP): chooser {base:.1f} us | " +
-          "  ".join(f"{c[0]},{c[1]},{c[2]}: {t:.1f}" for t, c in res[:int(os.environ.get("SWEEP_TOP", "6"))]), flush=True)
+          "  ".join(f"{','.join(str(v) for v in c)}: {t:.1f}" for t, c in res[:int(os.environ.get("SWEEP_TOP", "6"))]), flush=True)
 os.environ.pop("MAUA_CONV_FORCE", None)
