@@ -177,6 +177,10 @@ MAUA_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 MAUA_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// ask L2 to fetch [ptr, ptr + bytes) (16-byte aligned, bytes a multiple of 16); no completion tracking
+MAUA_DEVINL void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(ptr)), "r"(bytes) : "memory");
+}
 MAUA_DEVINL void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -55,6 +55,8 @@ struct ConvKParams {
                       // sums and the fused epilogue are done by conv_splitk_reduce_kernel launched right behind (no flags, no wait)
     float* splitk_ws;
     unsigned int* splitk_flags;
+    const uint8_t* prefetch;        // next layer's weights: L2 prefetch by the spare warp (ConvArgs::prefetch)
+    unsigned long long prefetch_bytes;
     int direct;  // 1: register -> global epilogue (needed for the content / addend / fp32-mask terms), 0: TMA-store epilogue
     ConvEpilogue ep;
 };
@@ -203,6 +205,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp == 3 && p.prefetch_bytes) {
+        // frozen weights of the next launch -> L2, in 16 KB pieces spread over the grid (independent of the previous kernel: no wait)
+        constexpr unsigned long long kPiece = 16384;
+        const unsigned long long npieces = (p.prefetch_bytes + kPiece - 1) / kPiece;
+        for (unsigned long long i = blockIdx.x * 32ull + lane; i < npieces; i += gridDim.x * 32ull) {
+            const unsigned long long off = i * kPiece;
+            const unsigned long long left = p.prefetch_bytes - off;
+            l2_prefetch_bulk(p.prefetch + off, static_cast<uint32_t>(left < kPiece ? left : kPiece));
+        }
+    }
     pdl_wait();     // everything above (descriptor prefetch, barrier init, TMEM allocation) overlapped the previous kernel's tail
     pdl_trigger();
 
@@ -944,6 +956,8 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     p.total_tiles = p.tiles_w * p.tiles_h * a.B * p.n_tiles;
     p.ep = a.ep;
     p.direct = direct ? 1 : 0;
+    p.prefetch = static_cast<const uint8_t*>(a.prefetch);
+    p.prefetch_bytes = (a.prefetch && (reinterpret_cast<uintptr_t>(a.prefetch) & 15) == 0) ? (a.prefetch_bytes & ~size_t(15)) : 0;
     const int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
     const SplitPlan sp = plan_split(p.total_tiles, units, conv_groups(a), effective_tail_mode(a), BN, CG);
     p.full_tiles = sp.full_tiles; p.split = sp.split; p.total_items = sp.items; p.tail_halves = sp.halves;

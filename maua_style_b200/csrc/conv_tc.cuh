@@ -59,6 +59,11 @@ struct ConvArgs {
     // How the last partial wave of tiles is computed: 0 = whole tiles, 1 = K-split (needs the workspace above), 2 = as two
     // half-N items per tile (independent, no hand-over).
     int tail_mode = 0;
+    // Optional: weights of the NEXT convolution of the iteration (frozen data).  The tcgen05 kernel's spare warp asks L2 to fetch
+    // them (cp.async.bulk.prefetch.L2) while this launch runs, so that the next launch's first weight tiles -- which sit at the
+    // head of its k-loop chain -- do not come from HBM (the optimizer's history sweep flushes L2 once per iteration).
+    const void* prefetch = nullptr;
+    size_t prefetch_bytes = 0;  // multiple of 16
 };
 void conv_tile_plan(const ConvArgs& a, int sms, int tail_mode, int* bn, int* mt, int* cg, int* full_tiles, int* split_tiles,
                     int* split);

@@ -155,6 +155,7 @@ struct maua_plan {
     // conv; join: once, at the end of the forward pass).  -1 = automatic: on while the image has at most kSideAutoPixels
     // pixels -- there the conv launches leave SMs idle and every launch is latency; at 1024^2 the persistent conv CTAs hold
     // every SM and the side work only delays them.  0 / 1 force it (MAUA_SIDE_STREAM, maua_plan_set_side_stream).
+    bool prefetch_weights = true;  // L2 prefetch of the next conv's weights by the running conv kernel (MAUA_PREFETCH_W=0: off)
     int side_mode = -1;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -329,6 +330,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     p->avg_pool = d->avg_pool;
     if (const char* f = getenv("MAUA_FUSE_POOL")) p->fuse_pool = atoi(f) != 0;
     if (const char* f = getenv("MAUA_SIDE_STREAM")) p->side_mode = atoi(f) < 0 ? -1 : (atoi(f) != 0);
+    if (const char* f = getenv("MAUA_PREFETCH_W")) p->prefetch_weights = atoi(f) != 0;
     // (created here, not at first use: a first forward pass may already run inside a stream capture)
     MAUA_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
     MAUA_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -791,6 +793,17 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             if (p->splitk || p->conv_tail == 3) { a.splitk_ws = p->splitk_ws; a.splitk_flags = p->splitk_flags; }
             a.tail_mode = p->splitk ? 1 : p->conv_tail;
             a.ep.out2 = hand_off;  // dual store: tile by tile into the peer's memory while the GEMM runs
+            if (p->prefetch_weights && !exact) {
+                // weights of the next launch of the iteration: the next conv of the stack, or -- from the last layer -- its own
+                // rotated copy, which the backward pass starts with
+                int j = i + 1;
+                while (j <= last_needed && p->entries[j].pool) ++j;
+                const Entry* nx = j <= last_needed ? &p->entries[j] : (keep_for_backward ? &e : nullptr);
+                if (nx && !nx->image_layer && nx->ks == 3) {
+                    a.prefetch = j <= last_needed ? nx->wg : nx->wd;
+                    a.prefetch_bytes = (size_t)nx->cout * nx->cin * 9 * sizeof(float);
+                }
+            }
             bool split_layer = false;  // tail mode 3: a launch of fewer tiles than SMs is K-split + reduced; its pool stays separate
             if (a.tail_mode == 3 && p->impl != MAUA_IMPL_REF && !exact) {
                 int bn, mt, cg, full, st_, sp_;
@@ -1082,6 +1095,10 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
         a.B = 1; a.H = ec.H; a.W = ec.W;
         a.Cin = ec.cout; a.Cout = ec.cin; a.ntaps = ec.ks * ec.ks;
         a.in = gm; a.wg = exact ? ec.wd32 : ec.wd;
+        if (p->prefetch_weights && !exact && prod > 0 && !ep_.image_layer && ep_.ks == 3) {
+            a.prefetch = ep_.wd;  // the next dgrad's weights (see ConvArgs::prefetch)
+            a.prefetch_bytes = (size_t)ep_.cout * ep_.cin * 9 * sizeof(float);
+        }
         if (ec.ks == 5 && exact) {
             // NIN conv2 (5x5 / pad 2), exact mode: the input gradient is the direct convolution of Gm with the rotated, transposed weights
             // (conv_gen.cu, fp32); the ReLU mask, tap gradients and rounding follow in the un-pool kernel or an epilogue-only launch
