@@ -22,8 +22,9 @@
 // same TMEM tile as extra k-steps: this is the StyleLoss backward 4(G-A)F/(C^3 N) (loss.py:141-157)
 // folded into the dgrad of the following layer.
 //
-// Warp roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> fused epilogue -> global).
+// Warp roles (384 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warp 3 = L2 prefetch of the next layer's weights, warps 4-7 and 8-11 = two epilogue groups (TMEM ->
+// registers -> fused epilogue -> global) that take alternate 32-column boxes of a tile.
 #include "conv_tc.cuh"
 #include "pointwise.cuh"
 
@@ -61,7 +62,12 @@ struct ConvKParams {
     ConvEpilogue ep;
 };
 
-constexpr int STAGE_BOX_BYTES = 128 * 128;  // epilogue staging: one {32 ch, 16 w, 8 h} output box
+// Threads: 4 role warps + TWO groups of 4 epilogue warps.  One epilogue warp per scheduler issues ~340 dependent instructions per
+// 32-column box at ~6 cycles each (~2200 cycles per box, measured with the stores switched off): for the short-K layers
+// (Cin = 64: 6 k-groups per tile) that was longer than the tile's MMAs and sat on the critical path (conv2_1 forward 72.7 us, of
+// which 42.7 without the epilogue).  Two warps per scheduler, working on alternate boxes, hide each other's latencies.
+constexpr int kConvThreads = 384;
+constexpr int STAGE_BOX_BYTES = 128 * 128;  // epilogue staging: one {32 ch, 16 w, 8 h} output box per epilogue group
 constexpr int N_STAGE_BOX = 2;
 
 // KS: kernel size of the halo main term -- 3 (VGG, NIN conv3 / conv4) or 5 (NIN conv2, models.py:90: 5x5 / pad 2): the same
@@ -113,7 +119,7 @@ struct ConvCfg {
 // activation boxes but only HALF of every weight tile.  All TMA loads complete on the even CTA's barriers (its producer
 // arms them for both CTAs' bytes), the even CTA's MMA warp issues for the pair and its commits arrive in both CTAs.
 template <int BN, int MT, int CG, bool POOL = false, int KS = 3>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -192,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 4 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
+            mbar_init(&tmem_empty_bar[i], 8 * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
         }
         fence_barrier_init();
     }
@@ -389,8 +395,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const ConvEpilogue& ep = p.ep;
         const float ccoef = ep.cont_f ? *ep.cont_coef : 0.f;
         const int words = p.Cout >> 5;  // 32-channel words of the sign bitmaps per pixel
-        const bool issuer = (threadIdx.x == 128);
-        uint32_t lt = 0, box = 0;
+        const int grp = (warp - 4) >> 2;                 // epilogue group 0 / 1
+        const int gtid = threadIdx.x - 128 - grp * 128;  // thread of the group
+        const bool issuer = (gtid == 0);
+        uint8_t* sbox = stage_box + grp * STAGE_BOX_BYTES;  // this group's staging box
+        const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;  // this group's named barriers
+        uint32_t lt = 0;
         for (int it = cta_tile0; it < p.total_items; it += cta_tile_step, ++lt) {
             const Item item = get_item(it);
             int b, h0, w0, n0;
@@ -399,6 +409,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_full_bar[acc], (lt / NACC) & 1);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            // K-split parts are handled by group 0 alone (the hand-over flags count one warp per lane quadrant)
+            const bool solo = item.nparts > 1;
+            if (solo && grp == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+                continue;
+            }
             // split-K: workspace of this tile's partial accumulators, [part][rank][m][row][BN]; flags [slot][rank][quadrant]
             constexpr size_t kPartElems = static_cast<size_t>(MT) * 128 * BN;
             float* ws_tile = p.splitk_ws + static_cast<size_t>(item.slot) * (p.split - (p.split_nowait ? 0 : 1)) * CG * kPartElems;
@@ -454,7 +472,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const bool valid = (h < p.H) && (w < p.W);
                     const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
 #pragma unroll 1
-                    for (int c = 0; c < ncols; c += 32, ++box) {
+                    for (int c = 0; c < ncols; c += 32) {
+                        // the two epilogue groups take alternate boxes (the parity flips from tile to tile: single-box tiles)
+                        if (!solo && (((m * (ncols >> 5) + (c >> 5) + static_cast<int>(lt)) & 1) != grp)) continue;
                         const int cn = n0 + chan(c, item.nh);  // first output channel of this 32-column chunk
                         float v[32];
                         tmem_ld_x32(t_base + m * BN + c, v);
@@ -485,17 +505,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
                             ep.mask_out[pix * words + (cn >> 5)] = bits;
                         }
-                        uint8_t* sbox = stage_box + (box & 1) * STAGE_BOX_BYTES;
-                        // the store that last read this staging box (two boxes ago) must have drained it
-                        if (issuer) bulk_wait_group_read<1>();
-                        named_bar_sync(1, 128);
+                        // the store that last read this group's staging box must have drained it (it was issued a whole box of
+                        // arithmetic ago)
+                        if (issuer) bulk_wait_group_read<0>();
+                        named_bar_sync(bar_a, 128);
                         uint8_t* srow = sbox + row * 128;
 #pragma unroll
                         for (int k = 0; k < 8; ++k)  // 128B swizzle: 16-byte chunk k of row r lives at chunk k ^ (r % 8)
                             *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
                                 make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                         fence_proxy_async_smem();
-                        named_bar_sync(2, 128);
+                        named_bar_sync(bar_b, 128);
                         if (issuer) {
                             tma_store_4d(&tmOut, sbox, cn, w0, h0 + m * TILE_H, b);
                             if (ep.out2) tma_store_4d(&tmOut2, sbox, cn, w0, h0 + m * TILE_H, b);
@@ -509,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // one pooled pixel's 128-byte line.  Same arithmetic as pool_fwd_kernel, bit for bit.  The box is
                             // not rewritten before every thread has passed the next-but-one box's first barrier.
                             const int PH = p.H >> 1, PW = p.W >> 1;
-                            const int tid = threadIdx.x - 128;
+                            const int tid = gtid;
 #pragma unroll
                             for (int it2 = 0; it2 < 2; ++it2) {
                                 const int item = tid + 128 * it2;
@@ -547,6 +567,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const size_t pix = (static_cast<size_t>(b) * p.H + h) * p.W + w;
 #pragma unroll 1
                 for (int c0 = 0; c0 < ncols; c0 += 16) {
+                    if (!solo && (((m * (ncols >> 4) + (c0 >> 4) + static_cast<int>(lt)) & 1) != grp)) continue;
                     const int cn = n0 + chan(c0, item.nh);
                     const size_t off = pix * p.Cout + cn;  // element offset of this 16-channel chunk
                     constexpr int c = 0;                   // (the chunk-relative offsets below were written as off + c + i)
@@ -969,7 +990,7 @@ int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];

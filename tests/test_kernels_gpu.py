@@ -320,7 +320,8 @@ def test_content_tv_adam(lib):
     assert rel(pd, p.detach()) < 1e-6
 
 
-@pytest.mark.parametrize("n,history,iters", [(4096, 5, 30), (1003 * 4, 100, 40), (1003 * 4, 70, 85)])
+@pytest.mark.parametrize("n,history,iters", [(4096, 5, 30), (1003 * 4, 100, 40), (1003 * 4, 70, 85), (3 * 37 * 5, 7, 25),
+                                             (3 * 101 * 67 + 1, 12, 16)])
 def test_lbfgs_matches_torch(lib, n, history, iters):
     """Device-resident L-BFGS vs torch.optim.LBFGS driven the way optim.py:180-191 drives it."""
     g = torch.Generator().manual_seed(n)

@@ -14,7 +14,7 @@ from maua_style_b200 import _lib
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 lib = _lib.load()
 _lib.require_gpu()
-SHAPES = [(512, 512, 16, 16), (512, 512, 32, 32), (256, 512, 32, 32), (256, 256, 64, 64), (128, 128, 128, 128), (64, 64, 256, 256),
+SHAPES = [tuple(int(v) for v in sh.split(",")) for sh in os.environ["EXP_SHAPES"].split(";")] if os.environ.get("EXP_SHAPES") else [(512, 512, 16, 16), (512, 512, 32, 32), (256, 512, 32, 32), (256, 256, 64, 64), (128, 128, 128, 128), (64, 64, 256, 256),
           (512, 512, 64, 64)]
 MODES = [int(m) for m in os.environ.get("EXP_MODES", "0").split(",")]  # non-zero modes need a build with the MAUA_CONV_DBG knob (see git history)
 for cin, cout, h, w in SHAPES:
