@@ -831,8 +831,9 @@ SplitPlan choose_tile(const ConvArgs& a, int sms, int tail_mode, int& bn_out, in
                 const double eff = (double)tiles / (waves * units);
                 // rows of the (pair) tile that exist: ragged bottoms waste MMA work
                 const double rows = (double)a.H / (double)(((a.H + cg * mt * TILE_H - 1) / (cg * mt * TILE_H)) * cg * mt * TILE_H);
-                // fused pooling: the 128-wide pair tile pools faster from two stacked sub-tiles (conv2_2 at 512^2 x 128: 112 vs 121 us)
-                const double pool_f = (a.ep.pool_out && bn == 128 && cg == 2 && mt == 1) ? 0.92 : 1.0;
+                // fused pooling and short-K layers (Cin = 64: the epilogue weighs more): the 128-wide pair tile does better with two
+                // stacked sub-tiles (conv2_2 + pool at 512^2 x 128: 112 vs 121 us; conv2_1 at 512^2: 60.4 vs 64.5 us)
+                const double pool_f = ((a.ep.pool_out || (a.ntaps == 9 && a.Cin <= 64)) && bn == 128 && cg == 2 && mt == 1) ? 0.92 : 1.0;
                 const double score = eff * rows * shape_rate(bn, mt, cg) * pool_f;
                 if (score > best) { best = score; best_bn = bn; best_mt = mt; best_cg = cg; best_sp = sp; }
             }

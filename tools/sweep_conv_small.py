@@ -21,7 +21,7 @@ SHAPES = [(512, 512, 16, 16), (512, 512, 32, 32), (256, 512, 32, 32), (512, 512,
 if os.environ.get("SWEEP_BIG"):  # the layer shapes of the 1024^2 scale (full waves: what the chooser's shape_rate table is fitted to)
     SHAPES = [(64, 64, 1024, 1024), (64, 128, 512, 512), (128, 128, 512, 512), (128, 256, 256, 256), (256, 256, 256, 256),
               (256, 512, 128, 128), (512, 512, 128, 128), (512, 512, 64, 64)]
-CFGS = [(bn, mt, cg) for bn in (256, 128, 64, 32) for mt in (2, 1) for cg in (2, 1)] + [(64, 1, 2, 1)]  # last: nine-tap geometry
+CFGS = [(bn, mt, cg) for bn in (256, 128, 64, 32) for mt in (2, 1) for cg in (2, 1)]
 flush = torch.empty(64 << 20, device="cuda")  # 256 MB: evict L2 between timed launches
 
 
