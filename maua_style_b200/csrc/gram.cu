@@ -233,8 +233,10 @@ __global__ void gram_exact_sum_kernel(const double* __restrict__ dpartial, int S
 // groups of partials (G grows with the split count so that short and long reductions both keep the loads coalesced and
 // the threads busy).  Optionally fused with the StyleLoss value (loss.py:153-157): diff = gram - target,
 // *loss_out = scale * mean(diff^2).
+// (min 4 blocks per SM: without the bound ptxas unrolls the partial-sum loop into 128 registers -- 2 blocks per SM, 24 % occupancy --
+// and the kernel, which is all load latency, took 26 us for a 512-channel layer)
 template <int G>
-__global__ void __launch_bounds__(kReduceThreads)
+__global__ void __launch_bounds__(kReduceThreads, 4)
 gram_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, int Cn, long P, int full, const float* __restrict__ mean,
                      float* __restrict__ gram, const float* __restrict__ target, float* __restrict__ diff, float scale,
                      float* __restrict__ loss_out, double* red_partials, unsigned int* counter) {
