@@ -332,9 +332,13 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     if (const char* f = getenv("MAUA_SIDE_STREAM")) p->side_mode = atoi(f) < 0 ? -1 : (atoi(f) != 0);
     if (const char* f = getenv("MAUA_PREFETCH_W")) p->prefetch_weights = atoi(f) != 0;
     // (created here, not at first use: a first forward pass may already run inside a stream capture)
-    MAUA_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-    MAUA_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    MAUA_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        set_last_error("maua_plan_create: cannot create the side stream / its events: %s", cudaGetErrorString(cudaGetLastError()));
+        maua_plan_destroy(p);
+        return MAUA_ERR_CUDA;
+    }
     if (const char* f = getenv("MAUA_SPLITK")) p->splitk = atoi(f) != 0;
     if (const char* f = getenv("MAUA_CONV_TAIL")) p->conv_tail = atoi(f);
     p->begin = begin;
@@ -722,10 +726,12 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
     const bool use_side = !p->profile && (p->side_mode == 1 || (p->side_mode < 0 && (long)H * W <= kSideAutoPixels));
     bool forked = false;
     // stream the loss modules of the tap that has just been produced on `st` are launched on
+    cudaError_t fork_err = cudaSuccess;
     auto loss_stream = [&]() -> cudaStream_t {
         if (!use_side) return st;
-        cudaEventRecord(p->ev_fork, st);
-        cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+        cudaError_t e1 = cudaEventRecord(p->ev_fork, st);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+        if (e1 != cudaSuccess) { fork_err = e1; return st; }  // (reported below; the work then simply stays on the caller's stream)
         forked = true;
         return p->side;
     };
@@ -893,6 +899,7 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
         MAUA_CUDA_CHECK(cudaEventRecord(p->ev_join, p->side));
         MAUA_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_join, 0));
     }
+    MAUA_CUDA_CHECK(fork_err);
     p->can_backward = keep_for_backward != 0;
     return MAUA_OK;
 }
