@@ -71,10 +71,11 @@ def set_temporal_targets(net, warp_image, warp_weights=None, args=None):
 
 def _style_signature(net, style_images, args):
     """Everything the captured style targets depend on: the image tensors themselves (identity, storage, in-place version,
-    shape) and the capture settings."""
+    shape), the capture settings and the arithmetic mode of the plan (`set_impl`)."""
     imgs = tuple((id(t), t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in style_images)
     mods = tuple((bool(j.use_covariance), id(j)) for j in net.style_losses)
-    return imgs, tuple(float(w) for w in args.style_blend_weights[:len(style_images)]), mods
+    # (the arithmetic mode is part of it: targets captured by the TF32 kernels differ from the exact-mode ones by ~1e-4)
+    return imgs, tuple(float(w) for w in args.style_blend_weights[:len(style_images)]), mods, getattr(net, "_impl", None)
 
 
 def set_style_targets(net, style_images, args):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, O, make_args, save_checkpoint
+from helpers import GOLDEN, O, make_args, rel, save_checkpoint
 from oracle import image_oracle as I
 
 pytestmark = pytest.mark.gpu
@@ -185,6 +185,34 @@ def test_model_and_target_caches_do_not_change_results(tmp_path, monkeypatch):
     styles[0].mul_(0.5)
     optim.optimize(content, styles, init.clone(), 1, a, net, losses)
     assert getattr(net, "style_cache_hits", 0) == 0 and not torch.equal(t0, net.style_losses[0].target)
+
+
+def test_style_target_cache_follows_the_arithmetic_mode(tmp_path):
+    """Targets captured by the TF32 kernels must not be re-used after net.set_impl() switched the plan to the exact-arithmetic
+    kernels (and back): the cache signature carries the mode.  (__graft_entry__.smoke() switches modes on one net; with stale
+    targets its exact-mode losses were 8e-4 away from the oracle.)"""
+    from maua_style_b200 import _lib, models, optim
+
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    style = [O.synthetic_image(64, 64, seed=2)]
+    a = make_args(ckpt, tmp_path)
+    net, losses = models.load_model(a)
+    optim.set_style_targets(net, style, a)
+    t_tf32 = [m.target.clone() for m in net.style_losses]
+    optim.set_style_targets(net, style, a)
+    assert getattr(net, "style_cache_hits", 0) == 1
+    net.set_impl(_lib.MAUA_IMPL_FP32)
+    optim.set_style_targets(net, style, a)
+    assert net.style_cache_hits == 1                       # re-captured, not a cache hit
+    t_exact = [m.target.clone() for m in net.style_losses]
+    errs = [rel(x, y) for x, y in zip(t_tf32, t_exact)]
+    assert any(e > 0 for e in errs) and max(errs) < 5e-3, errs
+    net.set_impl(_lib.MAUA_IMPL_TC)
+    optim.set_style_targets(net, style, a)
+    assert net.style_cache_hits == 1
+    for x, y in zip(t_tf32, (m.target for m in net.style_losses)):
+        assert torch.equal(x, y)                           # deterministic kernels: the TF32 capture is reproduced bit for bit
 
 
 def test_stylize_frame_matches_oracle(tmp_path):
