@@ -178,7 +178,7 @@ int conv_fp32_launch(const ConvArgs& a, cudaStream_t st) {
         const int rc = relu_mask_bits_launch(a.ep.out, a.ep.mask_out, (long)a.B * a.H * a.W, a.Cout, st);
         if (rc) return rc;
     }
-    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, a.ep.round, st);
+    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, a.ep.round, st, a.ep.pool_codes);
     return MAUA_OK;
 }
 

@@ -552,8 +552,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     o.x = fmaxf(fmaxf(a[0].x, a[1].x), fmaxf(a[2].x, a[3].x)); o.y = fmaxf(fmaxf(a[0].y, a[1].y), fmaxf(a[2].y, a[3].y));
                                     o.z = fmaxf(fmaxf(a[0].z, a[1].z), fmaxf(a[2].z, a[3].z)); o.w = fmaxf(fmaxf(a[0].w, a[1].w), fmaxf(a[2].w, a[3].w));
                                 }
-                                if (ph < PH && pw < PW)
-                                    *reinterpret_cast<float4*>(ep.pool_out + ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + cn + 4 * k) = o;
+                                if (ph < PH && pw < PW) {
+                                    const size_t po = ((static_cast<size_t>(b) * PH + ph) * PW + pw) * p.Cout + cn + 4 * k;
+                                    *reinterpret_cast<float4*>(ep.pool_out + po) = o;
+                                    if (ep.pool_codes && !ep.pool_avg)  // arg-max codes for the backward pass (ConvEpilogue::pool_codes)
+                                        ep.pool_codes[po >> 2] = static_cast<uint8_t>(
+                                            first_argmax(a[0].x, a[1].x, a[2].x, a[3].x) | (first_argmax(a[0].y, a[1].y, a[2].y, a[3].y) << 2) |
+                                            (first_argmax(a[0].z, a[1].z, a[2].z, a[3].z) << 4) | (first_argmax(a[0].w, a[1].w, a[2].w, a[3].w) << 6));
+                                }
                             }
                         }
                     }
@@ -1125,7 +1131,7 @@ int conv_ref_launch(const ConvArgs& a, cudaStream_t st) {
         const int rc = relu_mask_bits_launch(a.ep.out, a.ep.mask_out, (long)a.B * a.H * a.W, a.Cout, st);
         if (rc) return rc;
     }
-    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, a.ep.round, st);
+    if (a.ep.pool_out) return pool_fwd_launch(a.ep.out, a.ep.pool_out, a.B, a.H, a.W, a.Cout, a.ep.pool_avg, a.ep.round, st, a.ep.pool_codes);
     return MAUA_OK;
 }
 

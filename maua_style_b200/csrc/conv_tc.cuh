@@ -36,6 +36,10 @@ struct ConvEpilogue {
     // l^16, l^17 of one epilogue warp).  Same arithmetic as pool_fwd_kernel, bit for bit.
     float* pool_out = nullptr;
     int pool_avg = 0;
+    // Optional, max pooling: arg-max codes of the pooled map, one byte per 4 channels ([B][H/2][W/2][Cout/4], two bits per
+    // channel, first maximum in row-major window order like pool_bwd_kernel recomputes it) -- lets the backward pass un-pool
+    // from the codes and the sign bitmap instead of re-reading the pre-pool activation (pool_bwd_codes_kernel).
+    uint8_t* pool_codes = nullptr;
 };
 
 // out[b][h][w][n] = epilogue( sum_{tap,c} in[b][h+dy][w+dx][c] * wg[n][tap*Cin + c]

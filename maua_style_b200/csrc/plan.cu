@@ -50,6 +50,8 @@ struct Entry {
     int Cn = 0;                // conv only: channel count the loss normalisations use (< C when the layer is zero-padded)
     float* out = nullptr;      // arena pointer
     uint32_t* bits = nullptr;  // conv only: sign bitmap of `out` (1 bit / element), the ReLU mask of the backward pass
+    uint8_t* codes = nullptr;  // 2x2 pool only: arg-max codes of `out` (1 byte / 4 channels), written by the forward pass
+    bool codes_ok = false;     // ... by the last forward pass (max pooling, product path)
 };
 
 struct Tap {
@@ -155,6 +157,7 @@ struct maua_plan {
     // conv; join: once, at the end of the forward pass).  -1 = automatic: on while the image has at most kSideAutoPixels
     // pixels -- there the conv launches leave SMs idle and every launch is latency; at 1024^2 the persistent conv CTAs hold
     // every SM and the side work only delays them.  0 / 1 force it (MAUA_SIDE_STREAM, maua_plan_set_side_stream).
+    bool pool_codes = true;        // un-pool from arg-max codes + sign bitmaps (pool_bwd_codes_kernel; MAUA_POOL_CODES=0: re-read the activation)
     bool prefetch_weights = true;  // L2 prefetch of the next conv's weights by the running conv kernel (MAUA_PREFETCH_W=0: off)
     int side_mode = -1;
     cudaStream_t side = nullptr;
@@ -241,6 +244,7 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         const size_t n = (size_t)h * w * e.C;
         need += (n + 63) & ~size_t(63);
         if (!e.pool) need_bits += (n / 32 + 63) & ~size_t(63);
+        else if (!e.pool3) need_bits += (n / 16 + 63) & ~size_t(63);  // arg-max codes: one byte per 4 channels
         if (n > max_act) max_act = n;
     }
     if (need_bits > p->bits_words) {
@@ -303,9 +307,13 @@ int ensure_workspaces(maua_plan* p, int H, int W) {
         e.out = p->arena + off;
         off += ((size_t)e.H * e.W * e.C + 63) & ~size_t(63);
         e.bits = nullptr;
+        e.codes = nullptr;
         if (!e.pool) {
             e.bits = p->bits_arena + boff;
             boff += ((size_t)e.H * e.W * e.C / 32 + 63) & ~size_t(63);
+        } else if (!e.pool3) {
+            e.codes = reinterpret_cast<uint8_t*>(p->bits_arena + boff);
+            boff += ((size_t)e.H * e.W * e.C / 16 + 63) & ~size_t(63);
         }
     }
     return MAUA_OK;
@@ -331,6 +339,7 @@ static int plan_create_impl(int device, const maua_net_desc* d, int begin, int e
     if (const char* f = getenv("MAUA_FUSE_POOL")) p->fuse_pool = atoi(f) != 0;
     if (const char* f = getenv("MAUA_SIDE_STREAM")) p->side_mode = atoi(f) < 0 ? -1 : (atoi(f) != 0);
     if (const char* f = getenv("MAUA_PREFETCH_W")) p->prefetch_weights = atoi(f) != 0;
+    if (const char* f = getenv("MAUA_POOL_CODES")) p->pool_codes = atoi(f) != 0;
     // (created here, not at first use: a first forward pass may already run inside a stream capture)
     if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -782,7 +791,12 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
             // stage boundary it is written straight into the next stage's memory
             if (e.pool3) {
                 if ((rc = pool3_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
-            } else if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st))) return rc;
+            } else {
+                e.codes_ok = p->pool_codes && !p->avg_pool && !exact && p->impl != MAUA_IMPL_REF && e.codes && e.C % 32 == 0;
+                if ((rc = pool_fwd_launch(cur, hand_off ? hand_off : e.out, 1, curH, curW, e.C, p->avg_pool, rnd, st,
+                                          e.codes_ok ? e.codes : nullptr)))
+                    return rc;
+            }
         } else if (e.ks == 5 && exact) {
             // NIN conv2 (models.py:90) in the exact-arithmetic mode: 5x5 / pad 2 as a direct fp32 convolution (conv_gen.cu); the
             // product path runs it through conv_tc_kernel<.., KS = 5> below
@@ -822,6 +836,9 @@ static int plan_forward_impl(maua_plan_t* p, const float* image, int H, int W, c
                 e.ks == 3 && e.H >= 2 && e.W >= 2) {
                 a.ep.pool_out = p->entries[i + 1].out;  // models.py:119-122 pooled from the accumulator registers
                 a.ep.pool_avg = p->avg_pool;
+                Entry& pe = p->entries[i + 1];
+                pe.codes_ok = p->pool_codes && !p->avg_pool && !exact && p->impl != MAUA_IMPL_REF && pe.codes && e.C % 32 == 0;
+                a.ep.pool_codes = pe.codes_ok ? pe.codes : nullptr;
                 pool_done = true;
             }
             if ((rc = conv_dispatch(a, p->impl, st))) return rc;
@@ -1024,7 +1041,12 @@ static int plan_backward_impl(maua_plan_t* p, const float* grad_coefs, const flo
     // un-pool + ReLU mask (+ tap gradients of the pre-pool layer) through the pool entry that follows conv entry `prod`
     auto unpool = [&](const Entry& ep_, const Entry& epool, const float* gpool, const float* addend, float* outb) -> int {
         p->launches_bwd++;
+        // 2x2 pools of the product path un-pool from the forward pass's arg-max codes (max) and the sign bitmap of the pre-pool
+        // activation instead of the activation itself: same decisions, bit-identical gradient, 42 % less traffic
+        const bool compact = !epool.pool3 && p->pool_codes && !exact && p->impl != MAUA_IMPL_REF && ep_.bits && ep_.C % 32 == 0 &&
+                             (p->avg_pool || epool.codes_ok);
         const int r = epool.pool3 ? pool3_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st)
+                      : compact   ? pool_bwd_codes_launch(ep_.bits, epool.codes, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st)
                                   : pool_bwd_launch(ep_.out, gpool, addend, outb, 1, ep_.H, ep_.W, ep_.C, p->avg_pool, rnd, st);
         prof_mark(p, st, "pool_bwd", ep_.C, 0, 4.0 * 2.25 * ep_.C * ep_.H * ep_.W);
         return r;

@@ -15,9 +15,25 @@ int nchw_to_nhwc_launch(const float* src, float* dst, int B, int C, int H, int W
 int nhwc_to_nchw_launch(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t st);
 int prep_weights_launch(const float* w, float* out, int Cout, int Cin, int dgrad, int do_round, cudaStream_t st, int taps = 9);
 // do_round: TF32-round the averaged values (operands of the next tensor-core conv); max pooling never needs it
-int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, int do_round, cudaStream_t st);
+// codes (optional, max pooling): arg-max codes of the pooled map, see ConvEpilogue::pool_codes
+int pool_fwd_launch(const float* x, float* y, int B, int H, int W, int C, int avg, int do_round, cudaStream_t st,
+                    uint8_t* codes = nullptr);
 int pool_bwd_launch(const float* x, const float* gy, const float* addend, float* gx, int B, int H, int W, int C,
                     int avg, int do_round, cudaStream_t st);
+// the same un-pooling from the forward pass's arg-max codes and the sign bitmap of the pre-pool activation
+// (bits[pixel * (C/32) + c/32] bit c%32 = x > 0) instead of the activation itself: 5.2 instead of 9 bytes per element
+int pool_bwd_codes_launch(const uint32_t* bits, const uint8_t* codes, const float* gy, const float* addend, float* gx, int B,
+                          int H, int W, int C, int avg, int do_round, cudaStream_t st);
+
+// argmax with "first maximum in row-major window order wins" (ATen max_pool2d behaviour)
+__device__ __forceinline__ int first_argmax(float a0, float a1, float a2, float a3) {
+    int k = 0;
+    float m = a0;
+    if (a1 > m) { m = a1; k = 1; }
+    if (a2 > m) { m = a2; k = 2; }
+    if (a3 > m) { m = a3; k = 3; }
+    return k;
+}
 int tv_value_launch(const float* x, int planes, int H, int W, float strength, float* loss_out, ReduceScratch rs,
                     cudaStream_t st);
 int mse_value_launch(const float* x, const float* t, long n, float scale, float* loss_out, ReduceScratch rs,

@@ -208,6 +208,41 @@ def test_fused_pool_epilogue_is_bit_identical_to_the_pool_kernel(pooling, hw, tm
     assert torch.equal(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize("pooling", ["max", "avg"])
+@pytest.mark.parametrize("hw", [(90, 122), (64, 64), (257, 131)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_unpooling_from_argmax_codes_is_bit_identical(pooling, hw, fuse, tmp_path, monkeypatch):
+    """pool_bwd_codes_kernel (the backward pass un-pools from the arg-max codes the forward pass wrote + the sign bitmap of the
+    pre-pool activation) against pool_bwd_kernel (re-reads the activation and recomputes the winner): same decisions, so losses
+    and the image gradient must be bit-identical -- odd extents (dropped last row / column), both pooling modes, codes written
+    by the conv epilogue (fused pooling) and by pool_fwd_kernel."""
+    from maua_style_b200 import models, optim
+
+    path = tmp_path / "vgg19-random.pth"
+    save_checkpoint(path)
+    h, w = hw
+    content = O.synthetic_image(h, w, seed=1, smooth=True)
+    style = O.synthetic_image(h, w, seed=2)
+    init = (O.synthetic_image(h, w, seed=4) * 0.25).cuda()
+    res = []
+    for codes in ("0", "1"):
+        monkeypatch.setenv("MAUA_POOL_CODES", codes)
+        monkeypatch.setenv("MAUA_NO_MODEL_CACHE", "1")  # the switch is read when the plan is created
+        args = make_args(path, tmp_path, pooling=pooling, temporal_weight=0.0)
+        net, losses = models.load_model(args)
+        net.set_fuse_pool(fuse)
+        optim.set_content_targets(net, content, args)
+        optim.set_style_targets(net, [style], args)
+        for m in losses:
+            m.mode = "loss"
+        vec, g = optim.feval(net, init.clone())
+        res.append((vec.clone(), g.clone()))
+        del net, losses
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    assert float(res[0][1].abs().sum()) > 0
+
+
 @pytest.mark.parametrize("cov", [False, True])
 def test_loss_modules_on_the_side_stream_are_bit_identical(cov, tmp_path):
     """maua_plan_set_side_stream: the Gram / StyleLoss and ContentLoss kernels of the forward pass forked onto a side stream
