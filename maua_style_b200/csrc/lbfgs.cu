@@ -247,12 +247,10 @@ __global__ void __launch_bounds__(kThreads) lbfgs_dots_small_kernel(const Args a
         // this thread's elements of the sub-chunk: 2 float4 of g, y_new, s_new stay in registers
         float4 g4[2], y4[2], s4[2];
         bool ok[2];
-        long off[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const long i4 = c0 + u * kThreads + threadIdx.x;
             const long e = i4 * 4;
-            off[u] = e;
             ok[u] = i4 < b1;
             g4[u] = y4[u] = s4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!ok[u]) continue;
@@ -369,7 +367,6 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 
 inline size_t dots_smem_bytes(int nacc) { return (size_t)((nacc + 3) & ~3) * sizeof(float) + 3 * (size_t)kSub4 * sizeof(float4); }
 
-constexpr int kPerLane = (kMaxHist + 31) / 32;  // history entries owned by one lane of the solver warp
 
 __global__ void __launch_bounds__(kThreads) lbfgs_scalar_kernel(const Args a) {
     pdl_wait();
