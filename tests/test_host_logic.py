@@ -201,6 +201,26 @@ def test_conv_tile_plan_host_logic():
         assert whole + split_tiles == tiles
 
 
+def test_style_target_cache_signature_carries_the_arithmetic_mode():
+    """optim._style_signature: same images / weights / modules but another plan arithmetic (net.set_impl) is another signature,
+    so cached style targets of the TF32 kernels are not re-used by the exact-arithmetic mode (and vice versa)."""
+    import types
+
+    import torch
+
+    imgs = [torch.zeros(1, 3, 8, 8)]
+    mods = [types.SimpleNamespace(use_covariance=False), types.SimpleNamespace(use_covariance=True)]
+    args = types.SimpleNamespace(style_blend_weights=[1.0])
+    net = types.SimpleNamespace(style_losses=mods, _impl=0)
+    a = optim._style_signature(net, imgs, args)
+    assert a == optim._style_signature(net, imgs, args)
+    net._impl = 4
+    assert a != optim._style_signature(net, imgs, args)
+    net._impl = 0
+    imgs[0].add_(1.0)                      # an in-place edit of a style image is another signature too
+    assert a != optim._style_signature(net, imgs, args)
+
+
 def test_lbfgs_update_count_matches_torch_max_eval():
     """torch.optim.LBFGS(max_iter=n) as optim.py:180-191 builds it stops after max_eval = n*5//4 closure evaluations: count
     the parameter updates torch really makes and compare with optim.lbfgs_updates / the oracle's restated loop."""
