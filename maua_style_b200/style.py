@@ -12,7 +12,7 @@ module is what it looks like when the steps *around* `optim.optimize` stop bounc
   pastiche.cpu() -> match_histogram -> next scale             pastiche stays in HBM (optim.optimize_device)
   load.save_tensor_to_file: fp32 D2H, deprocess on the CPU    deprocess on the device, 3 B/pixel D2H (image_ops.deprocess)
 
-`img_img_tensors` / `stylize_frame` work on tensors (what benchmarks and the sharded runner call); `img_img(args)` is
+`img_img_tensors` / `vid_img_tensors` / `stylize_frame` work on tensors (what benchmarks and the sharded runner call); `img_img(args)` is
 the file-level entry with the reference's argument names.  Histogram matching (utils.match_histogram, style.py:24, :67,
 :71) runs on the device when `args.match_histograms` is set (image_ops.match_histogram: the style images' colour
 moments are taken once, each call is two passes over the pastiche).  Note that on torch >= 2 the reference's own call
@@ -130,6 +130,135 @@ def stylize_frame(net, losses, content_frame: torch.Tensor, style_images: Sequen
                     blend_image = image_ops.interpolate(blend_image, size=tuple(pastiche.shape[2:]))  # style.py:253-255
                 pastiche = image_ops.blend(blend_image, pastiche, 1.0 - tb, tb)
         return optim.optimize_device(content_frame, style_images, pastiche, num_iters, args, net, losses)
+
+
+def vid_img_pairs(order: Sequence[int], loop: bool = False):
+    """style.py:195-197: the (previous frame, this frame) pairs of one pass over the frame list `order`.  Without --loop every
+    frame is `this frame` once and the first frame comes last (it follows the last one); with --loop the first frames are
+    styled a second time so that the end of the clip meets its start."""
+    order = list(order)
+    return list(zip(order + order[: 11 if loop else 1], order[1:] + order[: 10 if loop else 1]))
+
+
+def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.Tensor], args,
+                    flows: Callable[[str, int, int], tuple],
+                    on_frame: Optional[Callable[[int, int, int, torch.Tensor], None]] = None) -> dict:
+    """style.py:145-300 on tensors: every scale x `args.passes_per_scale` passes (forward, then backward over the reversed
+    frame list, :299-300) x every frame, with everything between the decoded frames and the encoded results on the device.
+
+    frames ...... the decoded clip, [1,3,H,W] preprocessed images (load.preprocess layout; host or device)
+    styles_big .. the style images, same layout
+    flows ....... `flows(direction, prev_index, this_index) -> (flow, reliable)`: what the reference reads from
+                  `<work_dir>/flow/<direction>_<prev>_<this>.flo` / `.png` (:222, :274, :278) -- the flow field [h,w,2] after
+                  the host-side normalisation + blur of load.py:201-206 (`read_flo`), and the flow-reliability map [1,1,h,w]
+                  in [0,1] (load.py:217-218).  Estimating the flow is not part of this path: the fields are inputs.
+    on_frame .... called as on_frame(size, pass (1-based), frame index, uint8 [H,W,3] RGB device tensor) for every result,
+                  e.g. to encode `<size>/<pass>_<frame>.png` (:185, :295-297)
+
+    The reference hands results from one pass / scale to the next through those PNG files (:229-271); here they are the
+    returned dict {(size, pass, frame index): uint8 image in HBM} and never leave the device, but they keep the 8-bit
+    quantisation the files impose, so the frames equal the reference's.  Within a pass the previous frame's fp32 result is
+    carried over directly (:294).  Reads args.image_sizes, num_iters, passes_per_scale, init ("random" | "prev_warp" | else
+    the content frame), temporal_blend, loop, style_scale, match_histograms and everything `optim.optimize` reads; calls
+    `optim.set_model_args(args, size)` per scale like the reference does (:176), i.e. it updates `args` in place."""
+    import random
+
+    dev = _device(args)
+    n = len(frames)
+    if n < 2:
+        raise ValueError("vid_img needs at least two frames")
+    passes = int(getattr(args, "passes_per_scale", 1))
+    tb = float(getattr(args, "temporal_blend", 0.5))
+    loop = bool(getattr(args, "loop", False))
+    hist = getattr(args, "match_histograms", False)
+    init = getattr(args, "init", "prev_warp")
+    store = {}
+    with torch.cuda.device(dev):
+        frames = [f.to(dev, torch.float32).contiguous() for f in frames]
+        styles_big = [s.to(dev, torch.float32).contiguous() for s in styles_big]
+        H, W = (int(v) for v in frames[0].shape[-2:])
+        moments = torch.stack([image_ops.image_moments(styles_big[0])]) if hist else None  # :209, :294: the first style image
+
+        def matched(img):
+            return image_ops.match_histogram(img, None, mode=hist, source_moments=moments) if hist else img
+
+        def stored(key):  # load.preprocess(<png>) of a frame an earlier pass / scale wrote
+            return image_ops.preprocess(store[key], dev)
+
+        order = list(range(n))
+        prev_size = None
+        for size_n, (current_size, num_iters) in enumerate(zip(args.image_sizes, args.num_iters)):
+            content_scale = current_size / max(H, W)
+            # scale style images (:165-172; the area comes from the un-rounded scale factor, unlike img_img)
+            content_area = content_scale ** 2 * H * W
+            style_images = []
+            for img in styles_big:
+                style_scale = math.sqrt(content_area / (img.size(3) * img.size(2))) * getattr(args, "style_scale", 1.0)
+                style_images.append(image_ops.interpolate(img, scale_factor=style_scale))
+            optim.set_model_args(args, current_size)  # :176-177: one network per scale, every frame re-uses it
+            net, losses = models.load_model(args)
+            for pass_n in range(passes):
+                pastiche = None
+                if loop:  # :181-183
+                    start = random.randrange(0, n - 1)
+                    order = order[start:] + order[:start]
+                direction = "forward" if pass_n % 2 == 0 else "backward"  # :213
+                for k, (prev_f, this_f) in enumerate(vid_img_pairs(order, loop)):
+                    content_frame = matched(image_ops.interpolate(frames[this_f], scale_factor=content_scale))
+                    if size_n == 0 and pass_n == 0:  # :215-226
+                        if init == "random":
+                            pastiche = torch.randn(content_frame.size()).mul(0.001).to(dev)
+                        elif init == "prev_warp":
+                            if pastiche is None:
+                                pastiche = matched(image_ops.interpolate(frames[prev_f], scale_factor=content_scale))
+                            flow, _ = flows(direction, prev_f, this_f)
+                            pastiche = image_ops.grid_sample(pastiche, image_ops.flow_warp_grid(flow, tuple(pastiche.shape[2:])))
+                        else:
+                            pastiche = content_frame.clone()
+                    else:  # :227-290
+                        if pass_n == 0:  # the last pass of the previous scale (:229-255) ...
+                            src = (prev_size, passes) if k <= n else (current_size, pass_n + 1)
+                        else:            # ... or the previous pass of this scale (:256-271)
+                            src = (current_size, pass_n) if k <= n else (current_size, pass_n + 1)
+                        hw = tuple(content_frame.shape[2:])
+                        if pastiche is None:
+                            pastiche = stored(src + (prev_f,))
+                            if tuple(pastiche.shape[2:]) != hw:
+                                pastiche = image_ops.interpolate(pastiche, size=hw)
+                        blend_image = stored(src + (this_f,))
+                        if tuple(blend_image.shape[2:]) != hw:
+                            blend_image = image_ops.interpolate(blend_image, size=hw)
+                        flow, reliable = flows(direction, prev_f, this_f)
+                        warp_image = image_ops.grid_sample(pastiche, image_ops.flow_warp_grid(flow, hw))  # :273-276
+                        reliable = image_ops.interpolate(reliable.to(dev, torch.float32), size=hw)        # :278-282
+                        optim.set_temporal_targets(net, warp_image, warp_weights=reliable, args=args)     # :284
+                        pastiche = image_ops.blend(blend_image, pastiche, 1.0 - tb, tb)                    # :286
+                    out = optim.optimize_device(content_frame, style_images, pastiche, num_iters // passes, args, net, losses)
+                    pastiche = matched(out)  # :294
+                    u8 = image_ops.deprocess_u8(pastiche)
+                    store[(current_size, pass_n + 1, this_f)] = u8
+                    if on_frame is not None:
+                        on_frame(current_size, pass_n + 1, this_f, u8)
+                order = list(reversed(order))  # :299-300
+            prev_size = current_size
+    return store
+
+
+def read_flo(path: str) -> torch.Tensor:
+    """The host-side half of load.flow_warp_map (load.py:191-206): a Middlebury .flo file -> the field normalised by its own
+    extent and blurred (sigma 5), [h,w,2] float32 -- the `flow` input of `vid_img_tensors` / `image_ops.flow_warp_grid`."""
+    import numpy as np
+    import scipy.ndimage
+
+    with open(path, "rb") as f:
+        if np.fromfile(f, np.float32, count=1)[0] != np.float32(202021.25):
+            raise ValueError(f"{path}: not a .flo file (bad magic number)")
+        w = int(np.fromfile(f, np.int32, count=1)[0])
+        h = int(np.fromfile(f, np.int32, count=1)[0])
+        flow = np.fromfile(f, np.float32, count=2 * w * h).reshape(h, w, 2).copy()
+    flow[:, :, 0] /= w
+    flow[:, :, 1] /= h
+    return torch.from_numpy(scipy.ndimage.gaussian_filter(flow, [5, 5, 0]))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

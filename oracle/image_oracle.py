@@ -14,6 +14,8 @@ reference repo root, JCBrouwer/maua-style @ 316c552):
     blend ................ (1 - temporal_blend) * blend_image + temporal_blend * p   style.py:290
     match_histogram ...... utils.match_histogram (colour-statistics transfer)       utils.py:88-151
     img_img .............. the multi-resolution driver                               style.py:22-73
+    flow_warp_map ........ .flo field -> sampling grid                               load.py:191-214
+    vid_img .............. the per-frame video driver (scales x passes x frames)     style.py:145-300
 
 The arithmetic of interpolate / grid_sample lives in the third-party dependency PyTorch (pinned torch==1.8.1,
 requirements.txt:1; ATen UpSampleBilinear2d / GridSampler, not in the reference tree); the published algorithm is
@@ -26,7 +28,8 @@ matching torch 2.11's outputs bit for bit; with it the restatement is bit-exact 
 Pinning: tests/golden/make_golden_image.py runs torch's own F.interpolate / F.grid_sample (the ops the reference
 calls), the UNMODIFIED reference load.preprocess / load.deprocess and the UNMODIFIED reference style.img_img on
 seeded inputs and commits the outputs (tests/golden/image_ops.npz, img_img_64_96.npz); tests/test_image_oracle.py
-checks this file against them.
+checks this file against them.  The video driver is pinned the same way: tests/golden/make_golden_video.py runs the
+UNMODIFIED reference style.vid_img on seeded frames / .flo files (tests/golden/vid_img_3f_48_80.npz).
 """
 from __future__ import annotations
 
@@ -222,3 +225,90 @@ def img_img(content_big: np.ndarray, styles_big: List[np.ndarray], image_sizes: 
         pastiche = np.asarray(optimize_fn(content, styles, pastiche, iters), dtype=np.float32)
         outs.append(pastiche)
     return outs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# style.py:145-300 vid_img on arrays.  The PNG files the reference writes after every frame and reads back at the start
+# of the next pass / scale are a dict of uint8 images here (the 8-bit quantisation between passes is part of the result).
+# ---------------------------------------------------------------------------------------------------------------
+def flow_warp_map(flow_raw: np.ndarray, size: Tuple[int, int]) -> np.ndarray:
+    """load.flow_warp_map (load.py:191-214) from the [h, w, 2] field of a .flo file: normalise by the field's own extent,
+    Gaussian blur (sigma 5 along h and w), add the identity grid linspace(-1, 1), resize to `size`.  Returns [H, W, 2]."""
+    import scipy.ndimage
+
+    h, w = flow_raw.shape[:2]
+    flow = np.array(flow_raw, dtype=np.float32)
+    flow[:, :, 0] /= w
+    flow[:, :, 1] /= h
+    flow = scipy.ndimage.gaussian_filter(flow, [5, 5, 0])
+    neutral = np.rollaxis(np.array(np.meshgrid(np.linspace(-1, 1, w), np.linspace(-1, 1, h))), 0, 3)
+    warp = (neutral + flow).astype(np.float32)  # th.FloatTensor(float64 array): one rounding to fp32
+    return resize_bilinear(warp.transpose(2, 0, 1)[None], size=tuple(size))[0].transpose(1, 2, 0)
+
+
+def vid_img_schedule(n_frames: int, loop: bool = False):
+    """style.py:195-197: the (previous frame, this frame) pairs of one pass over `order` (a list of frame indices).
+    Without --loop every frame is `this frame` exactly once, the first one last (it follows the last frame)."""
+    def pairs(order):
+        return list(zip(order + order[: 11 if loop else 1], order[1:] + order[: 10 if loop else 1]))
+    return pairs
+
+
+def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image_sizes: Sequence[int], num_iters: Sequence[int],
+            passes_per_scale: int, optimize_fn, flows, init: str = "prev_warp", temporal_blend: float = 0.5,
+            style_scale: float = 1.0):
+    """Drives `optimize_fn(content, styles, pastiche, num_iters, temporal) -> pastiche` like style.vid_img does
+    (`temporal` = None or (warped previous result, resized flow-reliability map), i.e. what optim.set_temporal_targets got).
+
+    frames_u8: the decoded frames, uint8 [H,W,3] RGB; styles_big: preprocessed [1,3,h,w] arrays;
+    flows(direction, prev_index, this_index) -> (raw .flo field [h,w,2], reliability PNG bytes uint8 [h,w]).
+    Returns {(size, pass (1-based), frame index): uint8 [h,w,3]} -- the PNGs `<size>/<pass>_<frame>.png` (style.py:185).
+    --loop (random rotation, style.py:181-183) and random init (unseeded, style.py:217) are not restated."""
+    assert init in ("prev_warp", "content"), init
+    n = len(frames_u8)
+    order = list(range(n))
+    pairs = vid_img_schedule(n)
+    big = [preprocess_u8(f) for f in frames_u8]
+    H, W = big[0].shape[-2:]
+    store = {}
+    prev_size = None
+    for size_n, (size, iters) in enumerate(zip(image_sizes, num_iters)):
+        cs = size / max(H, W)
+        area = cs ** 2 * H * W  # style.py:166: from the un-rounded scale, not from the resized frame
+        styles = [resize_bilinear(s, scale_factor=math.sqrt(area / (s.shape[3] * s.shape[2])) * style_scale) for s in styles_big]
+        for pass_n in range(passes_per_scale):
+            pastiche = None
+            direction = "forward" if pass_n % 2 == 0 else "backward"
+            for prev_f, this_f in pairs(order):
+                content = [resize_bilinear(big[prev_f], scale_factor=cs), resize_bilinear(big[this_f], scale_factor=cs)]
+                temporal = None
+                if size_n == 0 and pass_n == 0:  # style.py:215-226
+                    if init == "prev_warp":
+                        if pastiche is None:
+                            pastiche = content[0]
+                        raw, _ = flows(direction, prev_f, this_f)
+                        grid = flow_warp_map(raw, pastiche.shape[2:])
+                        pastiche = grid_sample_border(pastiche[0], grid)[None]
+                    else:
+                        pastiche = content[1].copy()
+                else:  # style.py:227-290
+                    src = (prev_size, passes_per_scale) if pass_n == 0 else (size, pass_n)
+                    if pastiche is None:
+                        pastiche = preprocess_u8(store[src + (prev_f,)])
+                        if pass_n == 0:
+                            pastiche = resize_bilinear(pastiche, size=content[0].shape[2:])
+                    blend_image = preprocess_u8(store[src + (this_f,)])
+                    if pass_n == 0:
+                        blend_image = resize_bilinear(blend_image, size=content[0].shape[2:])
+                    raw, rel_u8 = flows(direction, prev_f, this_f)
+                    grid = flow_warp_map(raw, pastiche.shape[2:])
+                    warp_image = grid_sample_border(pastiche[0], grid)[None]
+                    rel = (rel_u8.astype(np.float32) / f32(255))[None, None]  # T.ToTensor (load.py:217-218)
+                    rel = resize_bilinear(rel, size=pastiche.shape[2:])
+                    temporal = (warp_image, rel)
+                    pastiche = blend(blend_image, pastiche, 1 - temporal_blend, temporal_blend)  # the UN-warped previous result
+                pastiche = np.asarray(optimize_fn(content[1], styles, pastiche, iters // passes_per_scale, temporal), dtype=np.float32)
+                store[(size, pass_n + 1, this_f)] = deprocess_u8(pastiche)
+            order = list(reversed(order))  # style.py:299-300
+        prev_size = size
+    return store

@@ -242,3 +242,98 @@ def test_lbfgs_update_count_matches_torch_max_eval():
         pts = seen + [p.detach().clone()]
         updates = sum(1 for a, b in zip(pts[:-1], pts[1:]) if not torch.equal(a, b))
         assert updates == optim.lbfgs_updates(n), (n, updates)
+
+
+def test_vid_img_driver_host_logic_reproduces_the_reference_pngs(tmp_path, monkeypatch):
+    """style.vid_img_tensors without a GPU: its device calls (image_ops.*, the per-frame optimisation, the network) are replaced
+    by the CPU oracle's, so what runs here is the driver's own control flow -- frame order, pass reversal, which stored frame
+    initialises / blends which frame, when temporal targets exist -- against the PNGs of the unmodified reference
+    (tests/golden/vid_img_3f_48_80.npz).  The GPU version of this test is tests/test_vid_driver_gpu.py."""
+    import contextlib
+    import types
+
+    import numpy as np
+    import torch
+
+    from helpers import GOLDEN, O, make_args
+    from maua_style_b200 import image_ops, style
+    from oracle import image_oracle as I
+
+    z = np.load(GOLDEN / "vid_img_3f_48_80.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        temporal_weight=meta["temporal_weight"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    n_ = lambda x: x.detach().numpy()
+    net = types.SimpleNamespace(temporal=None, loads=0)
+
+    def load_model(args):
+        net.temporal, net.loads = None, net.loads + 1  # a fresh network has no temporal target (loss.py:46-47 skips it)
+        return net, []
+
+    def set_temporal_targets(nt, warp, warp_weights=None, args=None):
+        nt.temporal = (warp.clone(), warp_weights.clone())
+
+    def optimize_device(content, styles, init, iters, args, nt, losses):
+        return O.optimize(content, list(styles), init, iters, cfg, params, temporal=nt.temporal).detach()
+
+    def interpolate(x, size=None, scale_factor=None):
+        return t(I.resize_bilinear(n_(x), size=None if size is None else tuple(size), scale_factor=scale_factor))
+
+    def flow_warp_grid(flow, size):  # `flow` is already normalised + blurred (style.read_flo)
+        h, w = flow.shape[:2]
+        neutral = np.rollaxis(np.array(np.meshgrid(np.linspace(-1, 1, w), np.linspace(-1, 1, h))), 0, 3)
+        warp = (neutral + n_(flow)).astype(np.float32)
+        return t(I.resize_bilinear(warp.transpose(2, 0, 1)[None], size=tuple(size))[0].transpose(1, 2, 0))[None]
+
+    monkeypatch.setattr(style, "_device", lambda args: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(style.models, "load_model", load_model)
+    monkeypatch.setattr(style.optim, "set_temporal_targets", set_temporal_targets)
+    monkeypatch.setattr(style.optim, "optimize_device", optimize_device)
+    monkeypatch.setattr(image_ops, "interpolate", interpolate)
+    monkeypatch.setattr(image_ops, "flow_warp_grid", flow_warp_grid)
+    monkeypatch.setattr(image_ops, "grid_sample", lambda x, g: t(I.grid_sample_border(n_(x)[0], n_(g)[0]))[None])
+    monkeypatch.setattr(image_ops, "blend", lambda x, y, a, b: t(I.blend(n_(x), n_(y), a, b)))
+    monkeypatch.setattr(image_ops, "deprocess_u8", lambda x: t(I.deprocess_u8(n_(x))))
+    monkeypatch.setattr(image_ops, "preprocess", lambda img, device=None: t(I.preprocess_u8(n_(img))))
+
+    ckpt = tmp_path / "unused.pth"
+    a = make_args(ckpt, tmp_path, transfer_type="vid_img", optimizer=meta["optimizer"], image_sizes=list(meta["sizes"]),
+                  num_iters=list(meta["iters"]), passes_per_scale=meta["passes"], init=meta["init"],
+                  temporal_blend=meta["temporal_blend"], loop=False, style_scale=1.0, match_histograms=False)
+    flo_dir = tmp_path / "flow"
+    flo_dir.mkdir()
+
+    def flows(direction, i, j):
+        raw = z[f"flow_{direction}_{i}_{j}"]
+        path = flo_dir / f"{direction}_{i}_{j}.flo"
+        with open(path, "wb") as f:
+            np.array([202021.25], dtype=np.float32).tofile(f)
+            np.array([raw.shape[1]], dtype=np.int32).tofile(f)
+            np.array([raw.shape[0]], dtype=np.int32).tofile(f)
+            raw.astype(np.float32).tofile(f)
+        return style.read_flo(str(path)), t(z[f"rel_{direction}_{i}_{j}"].astype(np.float32) / np.float32(255))[None, None]
+
+    frames = [t(I.preprocess_u8(z[f"frame_{i}"])) for i in range(meta["n_frames"])]
+    seen = []
+    store = style.vid_img_tensors(frames, [t(I.preprocess_u8(z["style"]))], a, flows, on_frame=lambda s, p, f, u8: seen.append((p, f)))
+    assert net.loads == len(meta["sizes"])  # one network per scale (style.py:176-177)
+    assert seen[:6] == [(1, 1), (1, 2), (1, 0), (2, 1), (2, 0), (2, 2)]
+    assert len(store) == len(meta["sizes"]) * meta["passes"] * meta["n_frames"]
+    for (size, p, f), got in store.items():
+        ref = z[f"out_{size}_{p}_{f}"]
+        got = got.numpy()
+        assert got.shape == ref.shape
+        mse = float(((got.astype(np.float64) - ref.astype(np.float64)) ** 2).mean())
+        psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+        assert psnr > 45.0, (size, p, f, psnr)
+    # a bad .flo file is reported, not read as garbage
+    bad = tmp_path / "bad.flo"
+    bad.write_bytes(b"\x00" * 64)
+    with pytest.raises(ValueError):
+        style.read_flo(str(bad))
+    assert style.vid_img_pairs([0, 1, 2, 3]) == I.vid_img_schedule(4)([0, 1, 2, 3])
+    assert style.vid_img_pairs([0, 1, 2, 3], loop=True) == I.vid_img_schedule(4, loop=True)([0, 1, 2, 3])

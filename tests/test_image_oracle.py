@@ -90,6 +90,56 @@ def test_img_img_driver_matches_reference_pngs(tmp_path):
         assert psnr > 45.0, (size, psnr, int(diff.max()))
 
 
+def load_vid_golden():
+    z = np.load(GOLDEN / "vid_img_3f_48_80.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    frames = [z[f"frame_{i}"] for i in range(meta["n_frames"])]
+    flows = lambda d, a, b: (z[f"flow_{d}_{a}_{b}"], z[f"rel_{d}_{a}_{b}"])
+    return z, meta, frames, flows
+
+
+def psnr_u8(a, b):
+    mse = float(((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean())
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def test_vid_img_driver_matches_reference_pngs():
+    """style.py:145-300 end to end: frame order and pass reversal, which stored frame initialises / blends which frame,
+    the prev_warp start of the very first pass, warp + flow-reliability temporal targets, 8-bit quantisation between
+    passes -- every PNG the unmodified reference wrote (2 scales x 2 passes x 3 frames) must be reproduced."""
+    z, meta, frames, flows = load_vid_golden()
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        temporal_weight=meta["temporal_weight"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def optimize_fn(content, styles, pastiche, iters, temporal):
+        tmp = None if temporal is None else (t(temporal[0]), t(temporal[1]))
+        return O.optimize(t(content), [t(s) for s in styles], t(pastiche), iters, cfg, params, temporal=tmp).detach().numpy()
+
+    store = I.vid_img(frames, [I.preprocess_u8(z["style"])], meta["sizes"], meta["iters"], meta["passes"], optimize_fn, flows,
+                      init=meta["init"], temporal_blend=meta["temporal_blend"])
+    assert len(store) == len(meta["sizes"]) * meta["passes"] * meta["n_frames"]
+    worst = 99.0
+    for (size, p, f), got in store.items():
+        ref = z[f"out_{size}_{p}_{f}"]
+        assert got.shape == ref.shape, (size, p, f, got.shape, ref.shape)
+        worst = min(worst, psnr_u8(got, ref))
+        assert psnr_u8(got, ref) > 45.0, (size, p, f, psnr_u8(got, ref))
+    print(f"vid_img oracle vs reference PNGs: worst PSNR {worst:.1f} dB")
+
+
+def test_vid_img_schedule_visits_every_frame_once_per_pass():
+    pairs = I.vid_img_schedule(4)
+    assert pairs([0, 1, 2, 3]) == [(0, 1), (1, 2), (2, 3), (3, 0)]
+    assert pairs([3, 2, 1, 0]) == [(3, 2), (2, 1), (1, 0), (0, 3)]
+    # --loop styles the first frames a second time so that the end meets the start (zip stops at the shorter list)
+    looped = I.vid_img_schedule(4, loop=True)([0, 1, 2, 3])
+    assert looped == [(0, 1), (1, 2), (2, 3), (3, 0), (0, 1), (1, 2), (2, 3)]
+    assert len(I.vid_img_schedule(24, loop=True)(list(range(24)))) == 24 + 9  # frames[1:] + frames[:10]
+
+
 def hist_cases():
     g = np.load(GOLDEN / "hist_match.npz", allow_pickle=False)
     for name, thw, shws, mode, seed in json.loads(str(g["cases"])):
