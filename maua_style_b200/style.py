@@ -12,7 +12,7 @@ module is what it looks like when the steps *around* `optim.optimize` stop bounc
   pastiche.cpu() -> match_histogram -> next scale             pastiche stays in HBM (optim.optimize_device)
   load.save_tensor_to_file: fp32 D2H, deprocess on the CPU    deprocess on the device, 3 B/pixel D2H (image_ops.deprocess)
 
-`img_img_tensors` / `vid_img_tensors` / `stylize_frame` work on tensors (what benchmarks and the sharded runner call); `img_img(args)` is
+`img_img_tensors` / `vid_img_tensors` / `img_vid_tensors` / `stylize_frame` work on tensors (what benchmarks and the sharded runner call); `img_img(args)` is
 the file-level entry with the reference's argument names.  Histogram matching (utils.match_histogram, style.py:24, :67,
 :71) runs on the device when `args.match_histograms` is set (image_ops.match_histogram: the style images' colour
 moments are taken once, each call is two passes over the pastiche).  Note that on torch >= 2 the reference's own call
@@ -242,6 +242,91 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
                 order = list(reversed(order))  # :299-300
             prev_size = current_size
     return store
+
+
+def temporal_blur(video: torch.Tensor, sigma: float) -> torch.Tensor:
+    """`ndi.gaussian_filter(video, [sigma, 0, 0, 0], mode="wrap")` (style.py:137-138) without leaving the device: a normalised
+    Gaussian of radius int(4 sigma + 0.5) along the frame axis with periodic extension, accumulated in float64 like scipy."""
+    r = int(4.0 * float(sigma) + 0.5)
+    ks = list(range(-r, r + 1))
+    w = [math.exp(-0.5 / (sigma * sigma) * k * k) for k in ks]
+    total = sum(w)
+    v = video.to(torch.float64)
+    out = torch.zeros_like(v)
+    for k, wk in zip(ks, w):
+        out += (wk / total) * torch.roll(v, -k, dims=0)  # out[t] += w[k] * v[(t + k) mod T]
+    return out.to(torch.float32)
+
+
+def initial_video(content_big: torch.Tensor, video_length: int, init: str = "content") -> torch.Tensor:
+    """style.py:92-103: the initial pastiche video of img_vid for init "random" / "content" -- seeded noise (torch's global RNG,
+    like the reference) blurred over time and space with scipy on the host, once per job.  Returns a host tensor [T,3,H,W]."""
+    import scipy.ndimage as ndi
+
+    H, W = (int(v) for v in content_big.shape[-2:])
+    if init == "random":
+        pastiche = torch.randn((video_length, 3, H, W)) * 255
+        return torch.from_numpy(ndi.gaussian_filter(pastiche.numpy(), [video_length, 0, H / 32, W / 32], mode="wrap"))
+    if init != "content":
+        raise ValueError("init names a video: pass it as init_video")
+    pastiche = content_big.detach().to("cpu", torch.float32).clone().repeat([video_length, 1, 1, 1])
+    pastiche += torch.randn((video_length, 3, H, W)) * 255
+    return torch.from_numpy(ndi.gaussian_filter(pastiche.numpy(), [video_length, 0, 4, 4], mode="wrap"))
+
+
+def img_vid_tensors(content_big: torch.Tensor, style_videos_big: Sequence[torch.Tensor], args,
+                    init_video: Optional[torch.Tensor] = None,
+                    on_scale: Optional[Callable[[int, torch.Tensor], None]] = None) -> List[torch.Tensor]:
+    """style.py:76-142 on tensors: the pastiche is a video [T,3,H,W] that `optim.optimize` styles in overlapping frame windows
+    (one window = one batch of B frames through the network, window.py); between scales the pastiche and the style clips are
+    rolled by 7 frames (:134-135) so that the window seams fall elsewhere, and the pastiche is blurred over time (:137-138).
+    The video stays in HBM across scales.
+
+    content_big: [1,3,H,W]; style_videos_big: clips [T_i,3,h,w] (load.preprocess layout); `init_video`: the initial pastiche
+    (default: `initial_video(content_big, T, args.init)`, :92-103; a shorter clip is repeated like :101-102).  Reads
+    args.image_sizes, num_iters, gram_frame_window (one window length per scale: "18,9,7", a list, or one int), num_frames
+    (-1: the longest style clip), temporal_blend, style_scale and everything `optim.optimize` reads; like the reference it
+    sets `args.gram_frame_window` to the current scale's value.  Histogram matching against style *videos* (:82, :104, :139)
+    is refused: on torch >= 2 the reference's own call is a no-op and the device version
+    handles single images."""
+    if getattr(args, "match_histograms", False):
+        raise NotImplementedError("maua_style_b200: match_histograms with style videos is not supported (pass --no_hist_match)")
+    dev = _device(args)
+    nf = int(getattr(args, "num_frames", -1))
+    video_length = max(int(v.shape[0]) for v in style_videos_big) if nf == -1 else nf
+    gfw = getattr(args, "gram_frame_window")
+    delta_ts = [int(x) for x in gfw.split(",")] if isinstance(gfw, str) else ([int(x) for x in gfw] if isinstance(gfw, (list, tuple)) else [int(gfw)] * len(args.image_sizes))
+    if len(delta_ts) < len(args.image_sizes):
+        raise ValueError("gram_frame_window needs one window length per image size")
+    tb = float(getattr(args, "temporal_blend", 0.0))
+    if init_video is None:
+        init_video = initial_video(content_big, video_length, getattr(args, "init", "content"))
+    elif init_video.shape[0] != video_length:
+        init_video = init_video.repeat([video_length, 1, 1, 1])  # :101-102
+    with torch.cuda.device(dev):
+        content_big = content_big.to(dev, torch.float32).contiguous()
+        clips = [v.to(dev, torch.float32).contiguous() for v in style_videos_big]
+        pastiche = init_video.to(dev, torch.float32).contiguous()
+        H, W = (int(v) for v in content_big.shape[-2:])
+        outs = []
+        for i, (current_size, num_iters) in enumerate(zip(args.image_sizes, args.num_iters)):
+            args.gram_frame_window = delta_ts[i]  # :112
+            content_image = image_ops.interpolate(content_big, scale_factor=current_size / max(H, W))  # :115-117
+            content_area = content_image.shape[2] * content_image.shape[3]
+            style_videos = []
+            for vid in clips:  # :120-126
+                style_scale = math.sqrt(content_area / (vid.size(3) * vid.size(2))) * getattr(args, "style_scale", 1.0)
+                style_videos.append(image_ops.interpolate(vid, scale_factor=style_scale))
+            pastiche = image_ops.interpolate(pastiche, size=tuple(content_image.shape[2:]))  # :129-131
+            pastiche = optim.optimize_device(content_image, style_videos, pastiche, num_iters, args)  # :133
+            pastiche = torch.cat((pastiche[7:], pastiche[:7]))  # :135-136
+            clips = [torch.cat((c[7:], c[:7])) for c in clips]
+            if tb > 0:
+                pastiche = temporal_blur(pastiche, tb)
+            outs.append(pastiche)
+            if on_scale is not None:
+                on_scale(current_size, pastiche)
+        return outs
 
 
 def read_flo(path: str) -> torch.Tensor:

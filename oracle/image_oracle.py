@@ -16,6 +16,7 @@ reference repo root, JCBrouwer/maua-style @ 316c552):
     img_img .............. the multi-resolution driver                               style.py:22-73
     flow_warp_map ........ .flo field -> sampling grid                               load.py:191-214
     vid_img .............. the per-frame video driver (scales x passes x frames)     style.py:145-300
+    img_vid .............. the frame-window video driver (roll + temporal blur)      style.py:76-142
 
 The arithmetic of interpolate / grid_sample lives in the third-party dependency PyTorch (pinned torch==1.8.1,
 requirements.txt:1; ATen UpSampleBilinear2d / GridSampler, not in the reference tree); the published algorithm is
@@ -29,7 +30,8 @@ Pinning: tests/golden/make_golden_image.py runs torch's own F.interpolate / F.gr
 calls), the UNMODIFIED reference load.preprocess / load.deprocess and the UNMODIFIED reference style.img_img on
 seeded inputs and commits the outputs (tests/golden/image_ops.npz, img_img_64_96.npz); tests/test_image_oracle.py
 checks this file against them.  The video driver is pinned the same way: tests/golden/make_golden_video.py runs the
-UNMODIFIED reference style.vid_img on seeded frames / .flo files (tests/golden/vid_img_3f_48_80.npz).
+UNMODIFIED reference style.vid_img on seeded frames / .flo files (tests/golden/vid_img_3f_48_80.npz) and style.img_vid
+on a seeded style clip (tests/golden/img_vid_9f_32_48.npz).
 """
 from __future__ import annotations
 
@@ -312,3 +314,45 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
             order = list(reversed(order))  # style.py:299-300
         prev_size = size
     return store
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# style.py:76-142 img_vid on arrays (the pastiche is a video [T,3,H,W] optimised in frame windows by optim.optimize)
+# ---------------------------------------------------------------------------------------------------------------
+def temporal_blur_wrap(video: np.ndarray, sigma: float) -> np.ndarray:
+    """ndi.gaussian_filter(video, [sigma, 0, 0, 0], mode="wrap") (style.py:137-138) restated: a normalised Gaussian of radius
+    int(4 sigma + 0.5) along the frame axis with periodic extension, accumulated in float64, result in the input's fp32."""
+    r = int(4.0 * float(sigma) + 0.5)
+    x = np.arange(-r, r + 1)
+    w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    w = w / w.sum()
+    v = np.asarray(video, dtype=np.float64)
+    out = np.zeros_like(v)
+    for k, wk in zip(x, w):
+        out += wk * np.roll(v, -int(k), axis=0)  # out[t] += w[k] * v[(t + k) mod T]
+    return out.astype(np.float32)
+
+
+def img_vid(content_big: np.ndarray, style_clips_big: List[np.ndarray], init_video: np.ndarray, image_sizes: Sequence[int],
+            num_iters: Sequence[int], frame_windows: Sequence[int], optimize_fn, temporal_blend: float = 0.5,
+            style_scale: float = 1.0, roll: int = 7):
+    """Drives `optimize_fn(content, style_clips, pastiche_video, num_iters, gram_frame_window) -> pastiche_video` over the
+    scales like style.img_vid: resize content / style clips / pastiche (:114-130), optimise (:132), roll pastiche and style
+    clips by 7 frames (:134-135), blur over time (:137-138).  `init_video` is the initial pastiche of :92-103 (its noise is
+    drawn from the global RNG and blurred on the host; the golden stores it).  Returns the per-scale videos [T,3,h,w]."""
+    H, W = content_big.shape[-2:]
+    pastiche = np.asarray(init_video, dtype=np.float32)
+    clips = [np.asarray(c, dtype=np.float32) for c in style_clips_big]
+    outs = []
+    for size, iters, gfw in zip(image_sizes, num_iters, frame_windows):
+        content = resize_bilinear(content_big, scale_factor=size / max(H, W))
+        area = content.shape[2] * content.shape[3]
+        styles = [resize_bilinear(c, scale_factor=math.sqrt(area / (c.shape[3] * c.shape[2])) * style_scale) for c in clips]
+        pastiche = resize_bilinear(pastiche, size=content.shape[2:])
+        pastiche = np.asarray(optimize_fn(content, styles, pastiche, iters, int(gfw)), dtype=np.float32)
+        pastiche = np.concatenate((pastiche[roll:], pastiche[:roll]))
+        clips = [np.concatenate((c[roll:], c[:roll])) for c in clips]
+        if temporal_blend > 0:
+            pastiche = temporal_blur_wrap(pastiche, temporal_blend)
+        outs.append(pastiche)
+    return outs

@@ -15,6 +15,15 @@ CuPy networks) -- the frames, `.flo` fields and reliability maps they would have
 synthetic data -- and the ffmpeg encode of each finished scale into an .mp4 (style.py:302-304), which is a no-op here.  Everything else (frame ordering, pass reversal, which PNG initialises / blends which frame, warp,
 temporal targets, per-frame `optim.optimize`, PNG quantisation between passes) is the reference's own code.
 
+  img_vid_9f_32_48.npz ... the UNMODIFIED reference `style.img_vid` (style.py:76-142): one 40x48 content image, one style
+                           clip of 9 frames, two scales (32 px, 48 px) with frame windows of 3 and 2 frames, init=content
+                           (content + seeded noise, blurred over time and space on the host), the 7-frame roll of pastiche
+                           and style clips between scales (:134-135) and the temporal blur (:137-138), Adam.  Stored: the
+                           content PNG bytes, the style clip, the initial pastiche video the driver built (its noise comes
+                           from torch's global RNG) and the video tensor it handed to `load.save_tensor_to_file` after
+                           every scale.  Replaced by stubs: `load.process_style_videos` (ffmpeg decode of the style clips)
+                           and `load.save_tensor_to_file` (skvideo encode).
+
 Adam, not L-BFGS, for the reason given in make_golden_image.py.
 """
 from __future__ import annotations
@@ -57,6 +66,64 @@ def write_flo(path, flow):
         flow.astype(np.float32).tofile(f)
 
 
+def make_img_vid(rconfig, rmodels, rload, rstyle):
+    from PIL import Image
+
+    import scipy.ndimage as ndi
+
+    T, (H, W) = 9, (40, 48)
+    sizes, iters, windows = [32, 48], [3, 2], "3,2"
+    with tempfile.TemporaryDirectory(prefix="maua_golden_imgvid_") as tmp:
+        workdir = Path(tmp)
+        ckpt = workdir / "vgg19-random.pth"
+        save_checkpoint(rmodels, ckpt)
+        content_rgb = smooth_rgb(H, W, 1)
+        Image.fromarray(content_rgb, mode="RGB").save(workdir / "content.png")
+        mean = torch.tensor([103.939, 116.779, 123.68])[:, None, None]
+
+        def pre(rgb):  # load.preprocess layout (load.py:21-32): BGR, 0-255, mean-subtracted
+            return (torch.from_numpy(rgb.astype(np.float32)).permute(2, 0, 1)[[2, 1, 0]] - mean)[None]
+
+        clip = torch.cat([pre(smooth_rgb(44, 52, 30, drift=1.0 * f)) for f in range(T)])
+        args = reference_args(rconfig, workdir, ckpt, optimizer="adam", image_sizes=",".join(map(str, sizes)),
+                              num_iters=",".join(map(str, iters)), init="content", transfer_type="img_vid",
+                              gram_frame_window=windows, avg_frame_window=-1, num_frames=-1, temporal_blend=0.5, fps=24)
+        args.content = str(workdir / "content.png")
+        args.output = str(workdir / "out")
+        args.match_histograms = False
+        saved, inits = [], []
+        rload.process_style_videos = lambda a: [clip.clone()]                          # ffmpeg decode: out of scope
+        rload.save_tensor_to_file = lambda t, a, filename=None, **k: saved.append((filename, t.clone()))  # skvideo encode
+        real_filter = ndi.gaussian_filter
+
+        def spy(x, sigma, **k):  # the first call builds the initial pastiche video (style.py:99); record it
+            y = real_filter(x, sigma, **k)
+            if not inits:
+                inits.append(np.array(y, dtype=np.float32))
+            return y
+
+        rstyle.ndi.gaussian_filter = spy
+        torch.manual_seed(0)
+        torch.set_flush_denormal(True)
+        cwd = os.getcwd()
+        os.chdir(workdir)
+        try:
+            rstyle.img_vid(args)
+        finally:
+            os.chdir(cwd)
+            rstyle.ndi.gaussian_filter = real_filter
+        out = {"content": content_rgb, "style_clip": clip.numpy().astype(np.float32), "init_video": inits[0]}
+        assert len(saved) == len(sizes) + 1  # one per scale + the final file (style.py:141, :143)
+        for s_, (fname, t) in zip(sizes, saved):
+            assert fname.endswith(f"_{s_}")
+            out[f"out_{s_}"] = t.numpy().astype(np.float32)
+        out["meta"] = json.dumps(dict(sizes=sizes, iters=iters, windows=windows, T=T, init="content", optimizer="adam", temporal_blend=0.5,
+                                      content_weight=args.content_weight, style_weight=args.style_weight, tv_weight=args.tv_weight,
+                                      video_style_factor=args.video_style_factor))
+        np.savez_compressed(HERE / "img_vid_9f_32_48.npz", **out)
+        print("img_vid_9f_32_48.npz:", {k: getattr(v, "shape", None) for k, v in out.items() if not isinstance(v, str)})
+
+
 def main():
     from PIL import Image
 
@@ -71,6 +138,10 @@ def main():
     import load as rload  # noqa
     import style as rstyle  # noqa
 
+    if "--only-vid-img" not in sys.argv:
+        make_img_vid(rconfig, rmodels, rload, rstyle)
+    if "--only-img-vid" in sys.argv:
+        return
     H, W = FRAME_HW
     with tempfile.TemporaryDirectory(prefix="maua_golden_vid_") as tmp:
         workdir = Path(tmp)

@@ -337,3 +337,52 @@ def test_vid_img_driver_host_logic_reproduces_the_reference_pngs(tmp_path, monke
         style.read_flo(str(bad))
     assert style.vid_img_pairs([0, 1, 2, 3]) == I.vid_img_schedule(4)([0, 1, 2, 3])
     assert style.vid_img_pairs([0, 1, 2, 3], loop=True) == I.vid_img_schedule(4, loop=True)([0, 1, 2, 3])
+
+
+def test_img_vid_driver_host_logic_reproduces_the_reference_videos(tmp_path, monkeypatch):
+    """style.img_vid_tensors without a GPU (resize and the windowed optimisation replaced by the CPU oracle's): per-scale
+    window lengths, the 7-frame roll of pastiche and style clips, the temporal blur, against the videos of the unmodified
+    reference (tests/golden/img_vid_9f_32_48.npz).  GPU version: tests/test_vid_driver_gpu.py."""
+    import contextlib
+
+    import numpy as np
+    import torch
+
+    from helpers import GOLDEN, O, make_args
+    from maua_style_b200 import image_ops, style
+    from oracle import image_oracle as I
+
+    z = np.load(GOLDEN / "img_vid_9f_32_48.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        video_style_factor=meta["video_style_factor"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    windows_seen = []
+
+    def optimize_device(content, styles, init, iters, args, net=None, losses=None):
+        windows_seen.append(args.gram_frame_window)
+        return O.optimize_windows(content, list(styles), init, iters, cfg, params, gfw=int(args.gram_frame_window)).detach()
+
+    monkeypatch.setattr(style, "_device", lambda args: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(style.optim, "optimize_device", optimize_device)
+    monkeypatch.setattr(image_ops, "interpolate", lambda x, size=None, scale_factor=None: t(I.resize_bilinear(
+        x.numpy(), size=None if size is None else tuple(size), scale_factor=scale_factor)))
+    a = make_args(tmp_path / "unused.pth", tmp_path, transfer_type="img_vid", optimizer=meta["optimizer"],
+                  image_sizes=list(meta["sizes"]), num_iters=list(meta["iters"]), gram_frame_window=meta["windows"],
+                  avg_frame_window=-1, num_frames=-1, temporal_blend=meta["temporal_blend"], init="content", style_scale=1.0,
+                  match_histograms=False)
+    outs = style.img_vid_tensors(t(I.preprocess_u8(z["content"])), [t(z["style_clip"])], a, init_video=t(z["init_video"]))
+    assert windows_seen == [3, 2]
+    for size, out in zip(meta["sizes"], outs):
+        ref = t(z[f"out_{size}"])
+        assert out.shape == ref.shape
+        assert O.psnr(out, ref) > 80.0, (size, O.psnr(out, ref))
+    # the initial pastiche video of style.py:92-103 from the same seed
+    torch.manual_seed(0)
+    assert torch.equal(style.initial_video(t(I.preprocess_u8(z["content"])), meta["T"], "content"), t(z["init_video"]))
+    a.match_histograms = "avg"
+    with pytest.raises(NotImplementedError):
+        style.img_vid_tensors(t(I.preprocess_u8(z["content"])), [t(z["style_clip"])], a, init_video=t(z["init_video"]))

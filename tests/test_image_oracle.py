@@ -140,6 +140,41 @@ def test_vid_img_schedule_visits_every_frame_once_per_pass():
     assert len(I.vid_img_schedule(24, loop=True)(list(range(24)))) == 24 + 9  # frames[1:] + frames[:10]
 
 
+def test_img_vid_driver_matches_reference_videos():
+    """style.py:76-142 end to end: per-scale frame windows, the 7-frame roll of pastiche and style clips, the temporal blur --
+    the video tensors the unmodified reference handed to load.save_tensor_to_file after each scale must be reproduced."""
+    z = np.load(GOLDEN / "img_vid_9f_32_48.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        video_style_factor=meta["video_style_factor"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def optimize_fn(content, styles, pastiche, iters, gfw):
+        return O.optimize_windows(t(content), [t(s) for s in styles], t(pastiche), iters, cfg, params, gfw=gfw).detach().numpy()
+
+    outs = I.img_vid(I.preprocess_u8(z["content"]), [z["style_clip"]], z["init_video"], meta["sizes"], meta["iters"],
+                     [int(w) for w in meta["windows"].split(",")], optimize_fn, temporal_blend=meta["temporal_blend"])
+    for size, out in zip(meta["sizes"], outs):
+        ref = z[f"out_{size}"]
+        assert out.shape == ref.shape, (size, out.shape, ref.shape)
+        p = O.psnr(t(out), t(ref))
+        print(f"img_vid oracle {size}px vs reference video: PSNR {p:.1f} dB")
+        assert p > 80.0, (size, p)  # measured 170.8 / 94.4 dB
+
+
+def test_temporal_blur_matches_scipy():
+    import scipy.ndimage as ndi
+
+    rs = np.random.RandomState(4)
+    for T, sigma in [(9, 0.5), (5, 1.0), (3, 2.0), (12, 0.3)]:  # incl. a radius longer than the clip (periodic extension)
+        v = (rs.randn(T, 3, 6, 7) * 50).astype(np.float32)
+        ref = ndi.gaussian_filter(v, [sigma, 0, 0, 0], mode="wrap")
+        got = I.temporal_blur_wrap(v, sigma)
+        assert float(np.abs(got - ref).max()) <= 4e-5, (T, sigma, float(np.abs(got - ref).max()))  # measured: bit-equal
+
+
 def hist_cases():
     g = np.load(GOLDEN / "hist_match.npz", allow_pickle=False)
     for name, thw, shws, mode, seed in json.loads(str(g["cases"])):

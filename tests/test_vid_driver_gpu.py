@@ -162,3 +162,86 @@ def test_unmodified_reference_vid_img_on_the_b200_modules(ref_b200, tmp_path, mo
     get = lambda s, p, f: np.asarray(Image.open(work / str(s) / f"{p}_{f + 1:04d}.png").convert("RGB"))
     worst = compare(z, meta, get, f"reference style.vid_img + b200 modules ({precision}) vs reference PNGs")
     assert worst > MIN_PSNR[precision], worst
+
+
+# ---- img_vid: the frame-window video driver (style.py:76-142) ----
+# Adam, 2 scales, 4 + 6 windows of 3 / 2 frames; measured on a B200 (profiles/r05_vid_driver.txt): exact mode 168.6 / 94.4 dB
+# (the CPU oracle's own restatement: 170.8 / 94.4 dB), TF32 operands 56.6 / 51.0 dB
+IMG_VID_MIN_PSNR = {"fp32": 80.0, "tf32": 44.0}
+
+
+def load_img_vid_golden():
+    z = np.load(GOLDEN / "img_vid_9f_32_48.npz", allow_pickle=False)
+    return z, json.loads(str(z["meta"]))
+
+
+def video_psnr(a, b):
+    mse = float(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).mean())
+    return 199.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_img_vid_tensors_matches_reference_videos(tmp_path, monkeypatch, precision):
+    from maua_style_b200 import image_ops, models, style
+
+    monkeypatch.setenv("MAUA_PRECISION", precision)
+    models.clear_model_cache()
+    z, meta = load_img_vid_golden()
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    a = make_args(ckpt, tmp_path, transfer_type="img_vid", optimizer=meta["optimizer"], content_weight=meta["content_weight"],
+                  style_weight=meta["style_weight"], tv_weight=meta["tv_weight"], video_style_factor=meta["video_style_factor"],
+                  image_sizes=list(meta["sizes"]), num_iters=list(meta["iters"]), gram_frame_window=meta["windows"],
+                  avg_frame_window=-1, num_frames=-1, temporal_blend=meta["temporal_blend"], init="content", style_scale=1.0,
+                  match_histograms=False)
+    content = image_ops.preprocess(torch.from_numpy(z["content"]))
+    outs = style.img_vid_tensors(content, [torch.from_numpy(z["style_clip"])], a, init_video=torch.from_numpy(z["init_video"]))
+    for size, out in zip(meta["sizes"], outs):
+        ref = z[f"out_{size}"]
+        assert out.is_cuda and tuple(out.shape) == ref.shape
+        p = video_psnr(out.cpu().numpy(), ref)
+        print(f"img_vid_tensors ({precision}) {size}px vs reference video: PSNR {p:.1f} dB")
+        assert p > IMG_VID_MIN_PSNR[precision], (size, p)
+    # the temporal blur on the device is scipy's (style.py:137-138)
+    import scipy.ndimage as ndi
+
+    v = torch.randn(9, 3, 20, 24, generator=torch.Generator().manual_seed(3)) * 60
+    got = style.temporal_blur(v.cuda(), 0.5).cpu().numpy()
+    assert float(np.abs(got - ndi.gaussian_filter(v.numpy(), [0.5, 0, 0, 0], mode="wrap")).max()) <= 4e-5
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_unmodified_reference_img_vid_on_the_b200_modules(ref_b200, tmp_path, monkeypatch, precision):
+    """The reference's own style.img_vid with loss / models / optim swapped; its video decode / encode (ffmpeg, skvideo) are
+    stubbed exactly like in tests/golden/make_golden_video.py."""
+    from PIL import Image
+
+    ref, ref_loader = ref_b200
+    monkeypatch.setenv("MAUA_PRECISION", precision)
+    z, meta = load_img_vid_golden()
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    Image.fromarray(z["content"], mode="RGB").save(tmp_path / "content.png")
+    args = ref_loader.reference_args(ref, tmp_path, ckpt, gpu="0", optimizer=meta["optimizer"],
+                                     image_sizes=",".join(map(str, meta["sizes"])), num_iters=",".join(map(str, meta["iters"])),
+                                     init="content", transfer_type="img_vid", gram_frame_window=meta["windows"],
+                                     avg_frame_window=-1, num_frames=-1, temporal_blend=meta["temporal_blend"], fps=24)
+    args.content = str(tmp_path / "content.png")
+    args.output = str(tmp_path / "out")
+    args.match_histograms = False
+    saved = []
+    clip = torch.from_numpy(z["style_clip"])
+    monkeypatch.setattr(ref.load, "process_style_videos", lambda a: [clip.clone()])
+    monkeypatch.setattr(ref.load, "save_tensor_to_file", lambda t, a, filename=None, **k: saved.append((filename, t.clone())))
+    torch.manual_seed(0)  # the driver draws the initial pastiche from the global RNG (style.py:95-99), as in the golden run
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        ref.style.img_vid(args)
+    finally:
+        os.chdir(cwd)
+    assert len(saved) == len(meta["sizes"]) + 1
+    for size, (fname, out) in zip(meta["sizes"], saved):
+        p = video_psnr(out.numpy(), z[f"out_{size}"])
+        print(f"reference style.img_vid + b200 modules ({precision}) {size}px vs reference video: PSNR {p:.1f} dB")
+        assert p > IMG_VID_MIN_PSNR[precision], (size, p)
