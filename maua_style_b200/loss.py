@@ -110,6 +110,79 @@ class _StyleLossFn(torch.autograd.Function):
         return gx.permute(0, 3, 1, 2), None, None
 
 
+def _reduce_scratch(device) -> torch.Tensor:
+    return torch.zeros(_lib.load().maua_reduce_workspace_bytes(), dtype=torch.uint8, device=device)
+
+
+class _WeightedMSEFn(torch.autograd.Function):
+    """mean((x * weights - target)^2) of one [1,C,H,W] frame (loss.py:53-57) through maua_content_loss_fwd; `weights` is None or a
+    [1,1,H,W] map broadcast over the channels (the flow-reliability weights of the temporal loss).  Backward:
+    2 weights (x weights - target) / numel."""
+
+    @staticmethod
+    def forward(ctx, x, weights, target):
+        _lib.require_gpu()
+        lib = _lib.load()
+        xd = x.detach().cuda().float().contiguous()
+        td = target.detach().to(xd.device).float().contiguous()
+        wd = None
+        plane = 0
+        if weights is not None:
+            plane = int(xd.shape[2] * xd.shape[3])
+            if weights.numel() != plane:
+                raise ValueError("weights must have H*W elements ([1,1,H,W])")
+            wd = weights.detach().to(xd.device).float().contiguous()
+        loss = torch.zeros(1, device=xd.device)
+        with torch.cuda.device(xd.device):
+            _lib.check(lib.maua_content_loss_fwd(_lib.ptr(xd), _lib.ptr(wd), _lib.ptr(td), C.c_long(xd.numel()), C.c_long(plane),
+                                                 C.c_float(1.0), _lib.ptr(loss), _lib.ptr(_reduce_scratch(xd.device)),
+                                                 _lib.stream_ptr()), "maua_content_loss_fwd")
+        ctx.save_for_backward(xd, td, wd if wd is not None else torch.empty(0, device=xd.device))
+        ctx.x_device = x.device
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        xd, td, wd = ctx.saved_tensors
+        if wd.numel():
+            w = wd.reshape(1, 1, xd.shape[2], xd.shape[3])
+            gx = (xd * w - td) * w
+        else:
+            gx = xd - td
+        return (gx * (g * (2.0 / xd.numel()))).to(ctx.x_device), None, None
+
+
+class _TVFn(torch.autograd.Function):
+    """strength * (sum |x[r+1] - x[r]| + sum |x[c+1] - x[c]|) (loss.py:229-233) through maua_tv_loss_fwd; backward: the signs
+    of the differences scattered to both pixels (sign(0) = 0, like torch.abs)."""
+
+    @staticmethod
+    def forward(ctx, x, strength):
+        _lib.require_gpu()
+        lib = _lib.load()
+        xd = x.detach().cuda().float().contiguous()
+        b, c, h, w = xd.shape
+        loss = torch.zeros(1, device=xd.device)
+        with torch.cuda.device(xd.device):
+            _lib.check(lib.maua_tv_loss_fwd(_lib.ptr(xd), int(b * c), int(h), int(w), C.c_float(strength), _lib.ptr(loss),
+                                            _lib.ptr(_reduce_scratch(xd.device)), _lib.stream_ptr()), "maua_tv_loss_fwd")
+        ctx.save_for_backward(xd)
+        ctx.strength, ctx.x_device = strength, x.device
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (xd,) = ctx.saved_tensors
+        gx = torch.zeros_like(xd)
+        sv = torch.sign(xd[:, :, 1:, :] - xd[:, :, :-1, :])
+        sh = torch.sign(xd[:, :, :, 1:] - xd[:, :, :, :-1])
+        gx[:, :, 1:, :] += sv
+        gx[:, :, :-1, :] -= sv
+        gx[:, :, :, 1:] += sh
+        gx[:, :, :, :-1] -= sh
+        return (gx * (g * ctx.strength)).to(ctx.x_device), None
+
+
 class ContentLoss(nn.Module):
     """loss.py:32-64."""
 
@@ -125,21 +198,26 @@ class ContentLoss(nn.Module):
         self.name = "cont"
 
     def forward(self, input):
-        # standalone use (outside a B200Net): plain tensor ops on the device, same control flow as loss.py:42-64
+        # standalone use (outside a B200Net, which reads the attributes and fuses the loss into the conv epilogue): the value
+        # comes from the library's reduction kernel, the mode protocol is loss.py:42-64
         if self.mode == "none" or (input.shape[1:] != self.target.shape[1:] and self.target.nelement() != 0):
             return input
         if "temporal" in self.name and self.target.shape[0] == 0 and self.mode == "loss":
             return input
-        self.loss = 0
-        for idx in range(input.shape[0]):
-            if self.mode == "loss":
-                xi = input[[idx]]
-                loss = self.crit(xi * self.weights, self.target) if self.weights is not None else self.crit(xi, self.target)
+        if self.mode == "capture":
+            self.loss = 0
+            self.target = input.detach()
+        elif self.mode == "loss":
+            if self.target.shape[0] != 1:
+                raise NotImplementedError("maua_style_b200: a standalone ContentLoss compares against a one-frame target")
+            frames = input.shape[0]
+            total = 0
+            for idx in range(frames):
+                mse = _WeightedMSEFn.apply(input[[idx]], self.weights, self.target)
                 if self.normalize:
-                    loss = ScaleGradients.apply(loss, self.strength)
-                self.loss = self.loss + loss * self.strength / input.shape[0]
-            if self.mode == "capture":
-                self.target = input.detach()
+                    mse = ScaleGradients.apply(mse, self.strength)
+                total = total + mse * (self.strength / frames)
+            self.loss = total
         return input
 
 
@@ -205,9 +283,8 @@ class TVLoss(nn.Module):
         self.name = "tv"
 
     def forward(self, input):
-        x_diff = input[:, :, 1:, :] - input[:, :, :-1, :]
-        y_diff = input[:, :, :, 1:] - input[:, :, :, :-1]
-        self.loss = self.strength * (torch.sum(torch.abs(x_diff)) + torch.sum(torch.abs(y_diff)))
+        # standalone use: value from the library's kernel; `.loss` is assigned on every call, also in capture passes (loss.py:233)
+        self.loss = _TVFn.apply(input, float(self.strength))
         return input
 
 
