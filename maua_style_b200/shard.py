@@ -9,8 +9,10 @@ the natural partition over an 8 x B200 box is
   * frames  : contiguous chunks (rank r owns frames [r*ceil(n/world), ...)); chunk heads take their init image from
               the previous pass / scale exactly like the reference's resume path does (style.py:232-271).
 
-Weights (52 MB) are replicated and the style targets (<= 2.4 MB) are recomputed per rank (1 forward), so nothing has
-to be exchanged.  torch.distributed is only used for the control plane: the rendezvous, a barrier around timed regions
+Weights (52 MB) are replicated and the style targets (<= 2.4 MB) are recomputed per rank (1 forward), so independent images
+exchange nothing.  A video in frame chunks (`stylize_video`) has one exchange step per pass: the 8-bit frames every rank
+produced are all-gathered (`exchange_frames`), because chunk heads start from their predecessor's previous-pass result.
+Otherwise torch.distributed is only used for the control plane: the rendezvous, a barrier around timed regions
 and the max-over-ranks of the elapsed time (bench.py).  Works with the `gloo` backend on CPU (tests) and `nccl` on GPUs.
 """
 from __future__ import annotations
@@ -174,3 +176,60 @@ def stylize_images(contents: Sequence, styles: Sequence, inits: Sequence, num_it
             m.strength = s0
     torch.cuda.synchronize()
     return out
+
+
+def exchange_frames(fresh: dict, info: Optional[RankInfo] = None) -> dict:
+    """The one exchange step of a sharded video job: after a pass every rank holds the 8-bit frames it styled,
+    {(size, pass, frame index): uint8 [H,W,3]}, and the next pass needs its neighbours' (the frame in front of a chunk head, and
+    for the file-level driver the whole pass).  One all_gather of the padded per-rank stacks (3 bytes per pixel and frame: 151 MB
+    for 48 frames of 1024^2 -- against minutes of optimisation per pass) + the keys as objects.  Returns all ranks' frames."""
+    import torch
+    import torch.distributed as dist
+
+    info = info or RankInfo.from_env()
+    if info.world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return dict(fresh)
+    keys = sorted(fresh)
+    shape = tuple(fresh[keys[0]].shape) if keys else None
+    metas = [None] * info.world
+    dist.all_gather_object(metas, (keys, shape))
+    shapes = {m[1] for m in metas if m[1] is not None}
+    if not shapes:
+        return {}
+    if len(shapes) != 1:
+        raise RuntimeError(f"ranks disagree on the frame size of this pass: {sorted(shapes)}")
+    shape = shapes.pop()
+    most = max(len(m[0]) for m in metas)
+    dev = fresh[keys[0]].device if keys else (torch.device("cuda", torch.cuda.current_device())
+                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
+    buf = torch.zeros((most,) + shape, dtype=torch.uint8, device=dev)
+    for i, k in enumerate(keys):
+        buf[i] = fresh[k]
+    parts = [torch.empty_like(buf) for _ in range(info.world)]
+    dist.all_gather(parts, buf)
+    merged = {}
+    for (ks, _), part in zip(metas, parts):
+        for i, k in enumerate(ks):
+            merged[tuple(k)] = part[i].clone()
+    return merged
+
+
+def stylize_video(frames: Sequence, styles: Sequence, args, flows: Callable, info: Optional[RankInfo] = None,
+                  on_frame: Optional[Callable] = None) -> dict:
+    """BASELINE.json config 5, video form: the frames of one clip in contiguous chunks, one chunk per GPU.
+    Every rank walks the same scales x passes schedule (style.vid_img_tensors) on its own chunk; after each pass the ranks
+    exchange the 8-bit frames they produced (`exchange_frames`), so chunk heads start from their predecessor's result of the
+    previous pass / scale -- what the reference's resume path does with the PNGs of an interrupted run (style.py:186-188,
+    :229-271).  Within a chunk results are carried from frame to frame as in the unsharded driver; only the first frame of a
+    chunk differs from a single-GPU run (it sees its predecessor one pass late).  Returns every frame of every pass on every
+    rank: {(size, pass, frame index): uint8 [H,W,3]}."""
+    import copy
+
+    from . import style
+
+    info = info or RankInfo.from_env()
+    a = copy.copy(args)
+    a.gpu = str(info.local_rank)
+    owned = partition_contiguous(len(frames), info.world, info.rank)
+    return style.vid_img_tensors(frames, styles, a, flows, on_frame=on_frame, owned=owned,
+                                 exchange=lambda fresh: exchange_frames(fresh, info))

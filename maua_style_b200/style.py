@@ -142,7 +142,9 @@ def vid_img_pairs(order: Sequence[int], loop: bool = False):
 
 def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.Tensor], args,
                     flows: Callable[[str, int, int], tuple],
-                    on_frame: Optional[Callable[[int, int, int, torch.Tensor], None]] = None) -> dict:
+                    on_frame: Optional[Callable[[int, int, int, torch.Tensor], None]] = None,
+                    owned: Optional[Sequence[int]] = None,
+                    exchange: Optional[Callable[[dict], dict]] = None) -> dict:
     """style.py:145-300 on tensors: every scale x `args.passes_per_scale` passes (forward, then backward over the reversed
     frame list, :299-300) x every frame, with everything between the decoded frames and the encoded results on the device.
 
@@ -160,7 +162,12 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
     quantisation the files impose, so the frames equal the reference's.  Within a pass the previous frame's fp32 result is
     carried over directly (:294).  Reads args.image_sizes, num_iters, passes_per_scale, init ("random" | "prev_warp" | else
     the content frame), temporal_blend, loop, style_scale, match_histograms and everything `optim.optimize` reads; calls
-    `optim.set_model_args(args, size)` per scale like the reference does (:176), i.e. it updates `args` in place."""
+    `optim.set_model_args(args, size)` per scale like the reference does (:176), i.e. it updates `args` in place.
+
+    Sharding over GPUs (shard.stylize_video): `owned` = the frame indices this process styles (default: all), `exchange` =
+    called after every pass with the frames this process produced in it, returns the frames of all processes.  A frame that
+    another process styles breaks the chain of carried-over results exactly like a frame whose PNG already exists does in the
+    reference's resume path (:186-188): the next owned frame starts from the stored result of its predecessor (:229-271)."""
     import random
 
     dev = _device(args)
@@ -173,6 +180,10 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
     hist = getattr(args, "match_histograms", False)
     init = getattr(args, "init", "prev_warp")
     store = {}
+    mine = None if owned is None else set(int(i) for i in owned)
+    if mine is not None and (loop or init == "random"):
+        raise NotImplementedError("maua_style_b200: sharded vid_img draws nothing at random (no --loop rotation, no random init): "
+                                  "every process must walk the same schedule")
     with torch.cuda.device(dev):
         frames = [f.to(dev, torch.float32).contiguous() for f in frames]
         styles_big = [s.to(dev, torch.float32).contiguous() for s in styles_big]
@@ -203,7 +214,11 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
                     start = random.randrange(0, n - 1)
                     order = order[start:] + order[:start]
                 direction = "forward" if pass_n % 2 == 0 else "backward"  # :213
+                fresh = {}
                 for k, (prev_f, this_f) in enumerate(vid_img_pairs(order, loop)):
+                    if mine is not None and this_f not in mine:
+                        pastiche = None  # someone else's frame: the chain of carried-over results ends here
+                        continue
                     content_frame = matched(image_ops.interpolate(frames[this_f], scale_factor=content_scale))
                     if size_n == 0 and pass_n == 0:  # :215-226
                         if init == "random":
@@ -236,9 +251,11 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
                     out = optim.optimize_device(content_frame, style_images, pastiche, num_iters // passes, args, net, losses)
                     pastiche = matched(out)  # :294
                     u8 = image_ops.deprocess_u8(pastiche)
-                    store[(current_size, pass_n + 1, this_f)] = u8
+                    store[(current_size, pass_n + 1, this_f)] = fresh[(current_size, pass_n + 1, this_f)] = u8
                     if on_frame is not None:
                         on_frame(current_size, pass_n + 1, this_f, u8)
+                if exchange is not None:
+                    store.update(exchange(fresh))  # the next pass / scale reads its neighbours' frames (:229-271)
                 order = list(reversed(order))  # :299-300
             prev_size = current_size
     return store

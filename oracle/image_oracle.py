@@ -258,14 +258,19 @@ def vid_img_schedule(n_frames: int, loop: bool = False):
 
 def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image_sizes: Sequence[int], num_iters: Sequence[int],
             passes_per_scale: int, optimize_fn, flows, init: str = "prev_warp", temporal_blend: float = 0.5,
-            style_scale: float = 1.0):
+            style_scale: float = 1.0, chunks: Optional[Sequence[Sequence[int]]] = None):
     """Drives `optimize_fn(content, styles, pastiche, num_iters, temporal) -> pastiche` like style.vid_img does
     (`temporal` = None or (warped previous result, resized flow-reliability map), i.e. what optim.set_temporal_targets got).
 
     frames_u8: the decoded frames, uint8 [H,W,3] RGB; styles_big: preprocessed [1,3,h,w] arrays;
     flows(direction, prev_index, this_index) -> (raw .flo field [h,w,2], reliability PNG bytes uint8 [h,w]).
     Returns {(size, pass (1-based), frame index): uint8 [h,w,3]} -- the PNGs `<size>/<pass>_<frame>.png` (style.py:185).
-    --loop (random rotation, style.py:181-183) and random init (unseeded, style.py:217) are not restated."""
+    --loop (random rotation, style.py:181-183) and random init (unseeded, style.py:217) are not restated.
+
+    `chunks` (lists of frame indices, one per GPU) restates what a job sharded over GPUs computes: whenever the owner of the
+    frame changes, the chain of carried-over results breaks and the frame starts from the stored result of its predecessor in
+    the previous pass / scale -- the reference's resume rule for frames whose PNG already exists (style.py:186-188, :229-271)."""
+    owner = {f: r for r, c in enumerate(chunks or []) for f in c}
     assert init in ("prev_warp", "content"), init
     n = len(frames_u8)
     order = list(range(n))
@@ -281,7 +286,10 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
         for pass_n in range(passes_per_scale):
             pastiche = None
             direction = "forward" if pass_n % 2 == 0 else "backward"
+            last_owner = None
             for prev_f, this_f in pairs(order):
+                if owner and owner[this_f] != last_owner:
+                    pastiche, last_owner = None, owner[this_f]
                 content = [resize_bilinear(big[prev_f], scale_factor=cs), resize_bilinear(big[this_f], scale_factor=cs)]
                 temporal = None
                 if size_n == 0 and pass_n == 0:  # style.py:215-226

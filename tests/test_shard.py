@@ -4,6 +4,8 @@ No GPU and no compute calls here: the jobs are stand-ins; the data path of the r
 """
 import os
 import socket
+import sys
+from pathlib import Path
 
 import pytest
 import torch
@@ -11,6 +13,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from maua_style_b200 import shard
+
+ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.parametrize("n,world", [(0, 1), (1, 1), (7, 2), (8, 8), (64, 8), (5, 8), (13, 4)])
@@ -85,3 +89,118 @@ def test_world_size_2_gloo_control_plane():
         assert [frames[i] for i in range(9)] == [0] * 5 + [1] * 4       # contiguous chunks in frame order
         assert slowest == 2.0                                           # max over ranks
         assert total == 7.0
+
+
+# ---- a video sharded in contiguous frame chunks (shard.stylize_video): schedule, chunk heads, the per-pass frame exchange ----
+VID = dict(n=5, hw=(32, 40), sizes=[24, 40], iters=[4, 2], passes=2)
+
+
+def _video_inputs():
+    import numpy as np
+
+    rs = np.random.RandomState(11)
+    n, (h, w) = VID["n"], VID["hw"]
+    frames = [rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8) for _ in range(n)]
+    style = rs.randint(0, 256, size=(36, 30, 3)).astype(np.uint8)
+    flows = {}
+    for i in range(n):
+        for d, j in (("forward", (i + 1) % n), ("backward", (i - 1) % n)):
+            flows[(d, i, j)] = ((rs.randn(h // 2, w // 2, 2) * 0.8).astype(np.float32), (rs.rand(h // 2, w // 2) * 255).astype(np.uint8))
+    return frames, style, flows
+
+
+def _stand_in_optimize(content, pastiche, temporal):
+    """A cheap deterministic stand-in for the per-frame optimisation (the arithmetic is tested elsewhere; this test is about which
+    frame starts from what): numpy fp32, the same function on both sides of the comparison."""
+    import numpy as np
+
+    out = np.float32(0.5) * np.asarray(pastiche, np.float32) + np.float32(0.5) * np.asarray(content, np.float32)
+    if temporal is not None:
+        out = out + np.float32(0.25) * (np.asarray(temporal[0], np.float32) * np.asarray(temporal[1], np.float32) - out)
+    return out.astype(np.float32)
+
+
+def _video_worker(rank, world, port, q, tmpdir):
+    import contextlib
+    import types
+
+    import numpy as np
+
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import make_args
+    from maua_style_b200 import image_ops, style
+    from oracle import image_oracle as I
+
+    info = shard.init_process_group("gloo")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    net = types.SimpleNamespace(temporal=None)
+    # the device calls of the driver, replaced by the CPU oracle's (as in tests/test_host_logic.py)
+    style._device = lambda args: torch.device("cpu")
+    torch.cuda.device = lambda dev: contextlib.nullcontext()
+
+    def load_model(args):
+        net.temporal = None
+        return net, []
+
+    style.models.load_model = load_model
+    style.optim.set_temporal_targets = lambda nt, warp, warp_weights=None, args=None: setattr(nt, "temporal", (warp.numpy(), warp_weights.numpy()))
+    style.optim.optimize_device = lambda content, styles, init, iters, args, nt, losses: t(_stand_in_optimize(content.numpy(), init.numpy(), nt.temporal))
+    image_ops.interpolate = lambda x, size=None, scale_factor=None: t(I.resize_bilinear(x.numpy(), size=None if size is None else tuple(size), scale_factor=scale_factor))
+    image_ops.flow_warp_grid = lambda flow, size: t(I.flow_warp_map(flow.numpy(), size))[None]
+    image_ops.grid_sample = lambda x, g: t(I.grid_sample_border(x.numpy()[0], g.numpy()[0]))[None]
+    image_ops.blend = lambda x, y, a, b: t(I.blend(x.numpy(), y.numpy(), a, b))
+    image_ops.deprocess_u8 = lambda x: t(I.deprocess_u8(x.numpy()))
+    image_ops.preprocess = lambda img, device=None: t(I.preprocess_u8(img.numpy()))
+
+    frames, style_rgb, flows = _video_inputs()
+    a = make_args(Path(tmpdir) / "unused.pth", Path(tmpdir) / f"r{rank}", transfer_type="vid_img", image_sizes=VID["sizes"],
+                  num_iters=VID["iters"], passes_per_scale=VID["passes"], init="prev_warp", temporal_blend=0.5, loop=False,
+                  style_scale=1.0, match_histograms=False)
+    # (the oracle's flow_warp_map takes the raw field and does normalisation + blur itself, so the raw field is passed through)
+    get = lambda d, i, j: (t(flows[(d, i, j)][0]), t(flows[(d, i, j)][1].astype(np.float32) / np.float32(255))[None, None])
+    seen = []
+    store = shard.stylize_video([t(I.preprocess_u8(f)) for f in frames], [t(I.preprocess_u8(style_rgb))], a, get, info,
+                                on_frame=lambda s, p, f, u8: seen.append(f))
+    q.put((rank, sorted(set(seen)), {k: v.numpy() for k, v in store.items()}))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_video(tmp_path):
+    """Two ranks, five frames in chunks [0,1,2] / [3,4]: every rank ends up with every frame of every pass, and the frames equal
+    what the oracle's driver computes when the chain of carried-over results breaks at every chunk boundary."""
+    import numpy as np
+
+    from oracle import image_oracle as I
+
+    world = 2
+    for r in range(world):
+        (tmp_path / f"r{r}").mkdir()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_video_worker, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][1] == [0, 1, 2] and results[1][1] == [3, 4]  # who styled what
+    frames, style_rgb, flows = _video_inputs()
+    chunks = [shard.partition_contiguous(VID["n"], world, r) for r in range(world)]
+    want = I.vid_img(frames, [I.preprocess_u8(style_rgb)], VID["sizes"], VID["iters"], VID["passes"],
+                     lambda content, styles, pastiche, iters, temporal: _stand_in_optimize(content, pastiche, temporal),
+                     lambda d, i, j: flows[(d, i, j)], init="prev_warp", temporal_blend=0.5, chunks=chunks)
+    plain = I.vid_img(frames, [I.preprocess_u8(style_rgb)], VID["sizes"], VID["iters"], VID["passes"],
+                      lambda content, styles, pastiche, iters, temporal: _stand_in_optimize(content, pastiche, temporal),
+                      lambda d, i, j: flows[(d, i, j)], init="prev_warp", temporal_blend=0.5)
+    assert len(want) == len(VID["sizes"]) * VID["passes"] * VID["n"]
+    for rank, _, store in results:
+        assert sorted(store) == sorted(want)  # after the last exchange every rank holds the whole job
+        for k in want:
+            assert np.array_equal(store[k], want[k]), (rank, k)
+    # sharding changes chunk heads only in how fresh their predecessor is: the job is not bit-identical to the unsharded one ...
+    assert any(not np.array_equal(want[k], plain[k]) for k in want)
+    # ... but a frame that never follows a chunk boundary in the first pass of the first scale is
+    assert np.array_equal(want[(VID["sizes"][0], 1, 1)], plain[(VID["sizes"][0], 1, 1)])
