@@ -90,6 +90,47 @@ def test_vid_img_tensors_matches_reference_pngs(tmp_path, monkeypatch, precision
     assert models.cache_stats["misses"] >= 1
 
 
+def test_sharded_video_with_one_rank_is_the_plain_driver(tmp_path, monkeypatch):
+    """shard.stylize_video on one GPU owns every frame and exchanges with nobody: bit-identical to style.vid_img_tensors.  (Two
+    ranks: tests/test_shard.py on gloo, against the oracle's chunked restatement.)"""
+    from maua_style_b200 import image_ops, models, shard, style
+
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    z, meta = load_golden()
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+
+    def args():
+        return make_args(ckpt, tmp_path, transfer_type="vid_img", optimizer=meta["optimizer"], content_weight=meta["content_weight"],
+                         style_weight=meta["style_weight"], tv_weight=meta["tv_weight"], temporal_weight=meta["temporal_weight"],
+                         image_sizes=list(meta["sizes"])[:1], num_iters=list(meta["iters"])[:1], passes_per_scale=meta["passes"],
+                         init=meta["init"], temporal_blend=meta["temporal_blend"], loop=False, style_scale=1.0, match_histograms=False)
+
+    frames = [image_ops.preprocess(torch.from_numpy(z[f"frame_{i}"])) for i in range(meta["n_frames"])]
+    styles = [image_ops.preprocess(torch.from_numpy(z["style"]))]
+
+    def flows(direction, i, j):
+        raw = z[f"flow_{direction}_{i}_{j}"].astype(np.float32).copy()
+        raw[:, :, 0] /= raw.shape[1]
+        raw[:, :, 1] /= raw.shape[0]
+        import scipy.ndimage
+
+        rel = torch.from_numpy(z[f"rel_{direction}_{i}_{j}"].astype(np.float32) / np.float32(255))[None, None]
+        return torch.from_numpy(scipy.ndimage.gaussian_filter(raw, [5, 5, 0])), rel
+
+    plain = style.vid_img_tensors(frames, styles, args(), flows)
+    sharded = shard.stylize_video(frames, styles, args(), flows, shard.RankInfo(0, 1, 0))
+    assert sorted(plain) == sorted(sharded) and len(plain) == meta["passes"] * meta["n_frames"]
+    for k in plain:
+        assert torch.equal(plain[k], sharded[k]), k
+    # a schedule that draws random numbers cannot be sharded: refused, not silently different per rank
+    a = args()
+    a.loop = True
+    with pytest.raises(NotImplementedError):
+        style.vid_img_tensors(frames, styles, a, flows, owned=[0, 1])
+
+
 @pytest.fixture
 def ref_b200():
     sys.path.insert(0, str(ROOT))
