@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--multidevice", default=None, help="run ONLY the layer-wise split leg on these devices, e.g. 0,1 (configs[3])")
     ap.add_argument("--batch-images", type=int, default=8, help="images per GPU of the batch_job leg")
     ap.add_argument("--batch-iters", type=int, default=100, help="L-BFGS iterations per image of the batch_job leg")
+    ap.add_argument("--video-leg", action="store_true", help="run ONLY the vid_img frame-driver leg and print its JSON")
     ap.add_argument("--streams", type=int, default=1,
                     help="experimental: S independent images per GPU on S streams (batch jobs, BASELINE.json configs[4]); "
                          "prints its own JSON line, the default line is unchanged")
@@ -483,6 +484,43 @@ def video_window_leg(dev, size, frames, K, W):
             "cuda_graph": step.graph is not None}
 
 
+def video_frames_leg(dev, size=1024, frames=8, iters=100, passes=2):
+    """BASELINE.json configs[4] in its frame-chunk form, per GPU: `frames` consecutive frames through the public video driver
+    (maua_style_b200.style.vid_img_tensors; style.py:145-300): one scale, `passes` passes of iters // passes L-BFGS iterations per
+    frame, the previous result warped along the flow as the temporal target from the second pass on, results handed on as
+    8-bit frames.  Flow fields / reliability maps are synthetic inputs (flow estimation is not part of the path).  Wall clock
+    around the whole call, device synchronised on both sides; second (warm) run reported."""
+    from maua_style_b200 import style, synthetic as O
+
+    tmp = tempfile.mkdtemp(prefix="maua_bench_frames_")
+    ckpt = Path(tmp) / "vgg19-random.pth"
+    O.save_random_checkpoint(ckpt)
+    clip = [O.synthetic_image(size, size, seed=100 + i, smooth=True).to(dev) for i in range(frames)]
+    styles = [O.synthetic_image(size, size, seed=2).to(dev)]
+    g = torch.Generator().manual_seed(5)
+    flow = torch.randn(size // 4, size // 4, 2, generator=g) * 0.002  # normalised + blurred field (style.read_flo's output)
+    rel = (torch.rand(1, 1, size // 4, size // 4, generator=g) > 0.1).float().to(dev)
+    flows = lambda d, i, j: (flow if d == "forward" else -flow, rel)
+
+    def job():
+        a = O.reference_args(ckpt, tmp, transfer_type="vid_img", optimizer="lbfgs", gpu=str(dev.index), image_sizes=[size],
+                             num_iters=[iters], passes_per_scale=passes, init="content", temporal_blend=0.5, loop=False,
+                             style_scale=1.0, match_histograms=False)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        store = style.vid_img_tensors(clip, styles, a, flows)
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, len(store)
+
+    job()
+    dt, n = job()
+    evals = frames * passes * (iters // passes)
+    return {"workload": f"vid_img driver: {frames} consecutive {size}x{size} frames, 1 scale, {passes} passes x {iters // passes} L-BFGS "
+                        "iterations per frame, warp + flow-weighted temporal loss from pass 2, synthetic frames / flows",
+            "frames": frames, "seconds": dt, "frames_per_min": 60.0 * frames / dt, "iterations": evals, "value": evals / dt,
+            "unit": UNIT, "results": n, "timing": "wall clock around style.vid_img_tensors, device synchronised on both sides"}
+
+
 def batch_job(dev, info, images_per_gpu, iters, size=1024):
     """BASELINE.json configs[4] per GPU: `images_per_gpu` independent content images at 1024^2 through the public sharded
     runner (shard.stylize_images: one network per rank, style targets captured once, per-image content capture +
@@ -563,6 +601,10 @@ def run_ours(args):
     if args.multidevice:
         print(json.dumps({"metric": METRIC, "leg": "multidevice", **multidevice_leg(args.multidevice, args.size, args.steps, args.warmup)}),
               flush=True)
+        return
+
+    if args.video_leg:
+        print(json.dumps({"metric": METRIC, "leg": "vid_img_frames", **video_frames_leg(dev, args.size)}), flush=True)
         return
 
     size, K, W = args.size, args.steps, args.warmup
@@ -696,6 +738,7 @@ def run_ours(args):
                 line["pruned_vgg16_2048_adam"] = guarded(side_leg, 2048, "adam", dev, 10, 3, pk, arch="prune")
                 line["nin_4096_adam"] = guarded(side_leg, 4096, "adam", dev, 5, 2, pk, arch="nin")
                 line["img_vid_window"] = guarded(video_window_leg, dev, 512, 4, 10, 3)
+                line["vid_img_frames"] = guarded(video_frames_leg, dev)
                 if torch.cuda.device_count() >= 2:
                     line["multidevice_2048"] = guarded(multidevice_leg, "0,1", 2048, 10, 3)
         if world == 1 and not args.no_cpu_baseline:
