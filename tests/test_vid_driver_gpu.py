@@ -131,6 +131,30 @@ def test_sharded_video_with_one_rank_is_the_plain_driver(tmp_path, monkeypatch):
         style.vid_img_tensors(frames, styles, a, flows, owned=[0, 1])
 
 
+def test_vid_img_tensors_with_histogram_matching(tmp_path):
+    """style.py:209 / :294 with match_histograms on: content frames and every result take the colour statistics of the first
+    style image (on torch >= 2 the reference's own call is a silent no-op; this is what it did under its pinned torch 1.8.1)."""
+    from helpers import O
+    from maua_style_b200 import image_ops, style
+
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    a = make_args(ckpt, tmp_path, transfer_type="vid_img", image_sizes=[48], num_iters=[4], passes_per_scale=2, init="content",
+                  temporal_blend=0.5, loop=False, style_scale=1.0, match_histograms=True)
+    frames = [O.synthetic_image(48, 64, seed=60 + i, smooth=True) for i in range(3)]
+    sty = (O.synthetic_image(56, 60, seed=2, smooth=True) * 0.5 + 20).cuda()
+    flow = torch.zeros(12, 16, 2)
+    rel = torch.ones(1, 1, 12, 16)
+    store = style.vid_img_tensors(frames, [sty], a, lambda d, i, j: (flow, rel))
+    ms = image_ops.image_moments(sty).cpu().numpy()
+    assert len(store) == 6
+    for key, u8 in store.items():
+        mo = image_ops.image_moments(image_ops.preprocess(u8)).cpu().numpy()
+        # 8-bit truncation shifts the mean by about half a grey level and adds 1/12 to the variance
+        assert np.allclose(mo[1:4] / mo[0], ms[1:4] / ms[0], atol=1.0), key
+        assert np.allclose(mo[[4, 7, 9]] / mo[0] - (mo[1:4] / mo[0]) ** 2, ms[[4, 7, 9]] / ms[0] - (ms[1:4] / ms[0]) ** 2, rtol=3e-2), key
+
+
 @pytest.fixture
 def ref_b200():
     sys.path.insert(0, str(ROOT))
