@@ -386,3 +386,28 @@ def test_img_vid_driver_host_logic_reproduces_the_reference_videos(tmp_path, mon
     a.match_histograms = "avg"
     with pytest.raises(NotImplementedError):
         style.img_vid_tensors(t(I.preprocess_u8(z["content"])), [t(z["style_clip"])], a, init_video=t(z["init_video"]))
+
+
+def test_read_flo_is_the_host_half_of_flow_warp_map(tmp_path):
+    """style.read_flo against tests/golden/image_ops.npz: the field that make_golden_image.py wrote as a .flo file for the unmodified
+    load.flow_warp_map (load.py:191-214) and smoothed the way load.py:201-206 does; the reference's grid is then the identity grid
+    plus this field, resized (checked bit for bit on the CPU by the oracle and on the device by tests/test_image_gpu.py)."""
+    import numpy as np
+
+    from helpers import GOLDEN
+    from maua_style_b200 import style
+    from oracle import image_oracle as I
+
+    gold = np.load(GOLDEN / "image_ops.npz", allow_pickle=False)
+    fh, fw = gold["flow_smooth"].shape[:2]
+    raw = (np.random.RandomState(9).randn(fh, fw, 2) * 3.0).astype(np.float32)  # make_golden_image.py's seeded field
+    path = tmp_path / "f.flo"
+    with open(path, "wb") as f:
+        np.array([202021.25], dtype=np.float32).tofile(f)
+        np.array([fw], dtype=np.int32).tofile(f)
+        np.array([fh], dtype=np.int32).tofile(f)
+        raw.tofile(f)
+    got = style.read_flo(str(path)).numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, gold["flow_smooth"])
+    # and the oracle's whole flow_warp_map reproduces the reference's grid from the raw field
+    assert np.array_equal(I.flow_warp_map(raw, gold["flow_grid"].shape[1:3]), gold["flow_grid"][0])
