@@ -411,3 +411,53 @@ def test_read_flo_is_the_host_half_of_flow_warp_map(tmp_path):
     assert got.dtype == np.float32 and np.array_equal(got, gold["flow_smooth"])
     # and the oracle's whole flow_warp_map reproduces the reference's grid from the raw field
     assert np.array_equal(I.flow_warp_map(raw, gold["flow_grid"].shape[1:3]), gold["flow_grid"][0])
+
+
+def test_vid_img_driver_loop_mode_walks_the_reference_schedule(tmp_path, monkeypatch):
+    """--loop (style.py:181-183, :195-197): the frame list is rotated at a random start every pass and the first frames are styled
+    a second time; those repeats read the frames this pass has just produced (`n > len(frames)` branches of :229-271).  Runs the
+    driver's control flow on the CPU with stand-ins for the device calls and checks the order in which frames are visited."""
+    import contextlib
+    import random
+    import types
+
+    import numpy as np
+    import torch
+
+    from helpers import make_args
+    from maua_style_b200 import image_ops, style
+
+    n, passes = 4, 2
+    visits = []
+    net = types.SimpleNamespace()
+    monkeypatch.setattr(style, "_device", lambda args: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(style.models, "load_model", lambda args: (net, []))
+    monkeypatch.setattr(style.optim, "set_temporal_targets", lambda *a, **k: None)
+    monkeypatch.setattr(style.optim, "optimize_device", lambda content, styles, init, iters, args, nt, losses: 0.5 * content + 0.5 * init)
+    monkeypatch.setattr(image_ops, "interpolate", lambda x, size=None, scale_factor=None: torch.nn.functional.interpolate(
+        x, size=size, scale_factor=scale_factor, mode="bilinear", align_corners=False))
+    monkeypatch.setattr(image_ops, "flow_warp_grid", lambda flow, size: torch.zeros(1, size[0], size[1], 2))
+    monkeypatch.setattr(image_ops, "grid_sample", lambda x, g: x.clone())
+    monkeypatch.setattr(image_ops, "blend", lambda x, y, a, b: a * x + b * y)
+    monkeypatch.setattr(image_ops, "deprocess_u8", lambda x: x[0].permute(1, 2, 0).clamp(0, 255).to(torch.uint8))
+    monkeypatch.setattr(image_ops, "preprocess", lambda img, device=None: img.permute(2, 0, 1)[None].float())
+    a = make_args(tmp_path / "unused.pth", tmp_path, transfer_type="vid_img", image_sizes=[16, 24], num_iters=[2, 2],
+                  passes_per_scale=passes, init="content", temporal_blend=0.5, loop=True, style_scale=1.0, match_histograms=False)
+    frames = [torch.full((1, 3, 24, 32), 10.0 * (i + 1)) for i in range(n)]
+    random.seed(3)
+    store = style.vid_img_tensors(frames, [torch.zeros(1, 3, 20, 20)], a, lambda d, i, j: (torch.zeros(4, 4, 2), torch.ones(1, 1, 4, 4)),
+                                  on_frame=lambda s, p, f, u8: visits.append((s, p, f)))
+    per_pass = len(style.vid_img_pairs(list(range(n)), loop=True))
+    assert per_pass == 2 * n - 1 == 7  # zip stops at frames[1:] + frames[:10]
+    assert len(visits) == 2 * passes * per_pass
+    assert sorted(store) == sorted({(s, p, f) for s in (16, 24) for p in (1, 2) for f in range(n)})  # repeats overwrite their frame
+    for s in (16, 24):
+        for p in (1, 2):
+            seq = [f for (s_, p_, f) in visits if (s_, p_) == (s, p)]
+            step = 1 if p == 1 else -1  # forward pass, then the reversed list (style.py:299-300)
+            assert all((b_ - a_) % n == step % n for a_, b_ in zip(seq, seq[1:])), (s, p, seq)
+            assert seq[:n - 1] == seq[n:2 * n - 1] or len(set(seq)) == n  # the repeats are the frames the pass started with
+    # sharded runs refuse the random rotation
+    with pytest.raises(NotImplementedError):
+        style.vid_img_tensors(frames, [torch.zeros(1, 3, 20, 20)], a, lambda d, i, j: None, owned=[0, 1])
