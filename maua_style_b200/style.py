@@ -409,3 +409,52 @@ def img_img(args) -> List[torch.Tensor]:
     if init_image is not None:
         a.init = "image"
     return img_img_tensors(content_big, styles_big, a, init_image=init_image, on_scale=on_scale)
+
+
+def _name(path: str) -> str:
+    """load.name (load.py:99-100)."""
+    return str(path).split("/")[-1].split(".")[0]
+
+
+def vid_img(args, frames: Optional[Sequence[str]] = None) -> dict:
+    """style.py:145-300 at file level, on the files the reference's own preparation stage leaves in
+    `<output_dir>/<content>_<styles>/` (load.process_content_video, load.py:141-188: ffmpeg frame extraction + optical flow, both
+    outside this path): `frames/*.png`, `flow/<direction>_<prev>_<this>.flo` and `.png`.  Decodes them, runs `vid_img_tensors` with
+    the clip resident in HBM and writes `<size>/<pass>_<frame>.png` like the reference (:185, :295-297).  `frames`: the frame files
+    in clip order (default: the sorted contents of `frames/`).  Not restated: skipping frames whose PNG already exists (resume),
+    `--original_colors`, the ffmpeg encode of each finished scale (:302-304)."""
+    import glob
+
+    from PIL import Image
+
+    _lib.require_gpu()
+    if getattr(args, "original_colors", 0) == 1:
+        raise NotImplementedError("maua_style_b200: --original_colors is host-side PIL work and not part of the device driver")
+    dev = _device(args)
+    work = str(args.output_dir) + "/" + _name(args.content) + "_" + "_".join(_name(p) for p in args.style)
+    files = list(frames) if frames is not None else sorted(glob.glob(f"{work}/frames/*.png"))
+    if len(files) < 2:
+        raise FileNotFoundError(f"no frames under {work}/frames (run the reference's frame / flow preparation first)")
+    names = [_name(f) for f in files]
+    style_files = []
+    for p in args.style:  # load.process_style_images (load.py:77-92): a directory stands for the images inside it
+        if os.path.isdir(p):
+            style_files += [f"{p}/{f}" for f in os.listdir(p) if os.path.splitext(f)[1].lower() in (".png", ".jpeg", ".jpg", ".tiff")]
+        else:
+            style_files.append(p)
+    clip = [load_image(f, dev) for f in files]
+    styles_big = [load_image(p, dev) for p in style_files]
+
+    def flows(direction, i, j):
+        stem = f"{work}/flow/{direction}_{names[i]}_{names[j]}"
+        import numpy as np
+
+        rel = np.asarray(Image.open(stem + ".png"), dtype=np.float32) / np.float32(255)  # T.ToTensor (load.py:217-218)
+        rel = torch.from_numpy(rel if rel.ndim == 2 else rel[..., 0].copy())[None, None]
+        return read_flo(stem + ".flo"), rel
+
+    def on_frame(size, pass_n, f, u8):
+        os.makedirs(f"{work}/{size}", exist_ok=True)
+        Image.fromarray(u8.cpu().numpy(), mode="RGB").save(f"{work}/{size}/{pass_n}_{names[f]}.png")
+
+    return vid_img_tensors(clip, styles_big, args, flows, on_frame=on_frame)

@@ -461,3 +461,92 @@ def test_vid_img_driver_loop_mode_walks_the_reference_schedule(tmp_path, monkeyp
     # sharded runs refuse the random rotation
     with pytest.raises(NotImplementedError):
         style.vid_img_tensors(frames, [torch.zeros(1, 3, 20, 20)], a, lambda d, i, j: None, owned=[0, 1])
+
+
+def test_vid_img_file_level_entry_reads_and_writes_the_reference_layout(tmp_path, monkeypatch):
+    """style.vid_img(args): frames, .flo fields and reliability PNGs where the reference's preparation stage leaves them, results
+    as `<size>/<pass>_<frame>.png` -- against the PNGs of the unmodified reference (device calls replaced by the CPU oracle's)."""
+    import contextlib
+    import types
+
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from helpers import GOLDEN, O, make_args
+    from maua_style_b200 import _lib, image_ops, style
+    from oracle import image_oracle as I
+
+    z = np.load(GOLDEN / "vid_img_3f_48_80.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        temporal_weight=meta["temporal_weight"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    n_ = lambda x: x.detach().numpy()
+    net = types.SimpleNamespace(temporal=None)
+
+    def load_model(args):
+        net.temporal = None
+        return net, []
+
+    def flow_warp_grid(flow, size):
+        h, w = flow.shape[:2]
+        neutral = np.rollaxis(np.array(np.meshgrid(np.linspace(-1, 1, w), np.linspace(-1, 1, h))), 0, 3)
+        return t(I.resize_bilinear((neutral + n_(flow)).astype(np.float32).transpose(2, 0, 1)[None], size=tuple(size))[0].transpose(1, 2, 0))[None]
+
+    monkeypatch.setattr(_lib, "require_gpu", lambda: None)
+    monkeypatch.setattr(style, "_device", lambda args: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(style, "load_image", lambda path, dev: t(I.preprocess_u8(np.asarray(Image.open(path).convert("RGB")))))
+    monkeypatch.setattr(style.models, "load_model", load_model)
+    monkeypatch.setattr(style.optim, "set_temporal_targets", lambda nt, warp, warp_weights=None, args=None: setattr(nt, "temporal", (warp.clone(), warp_weights.clone())))
+    monkeypatch.setattr(style.optim, "optimize_device", lambda content, styles, init, iters, args, nt, losses: O.optimize(
+        content, list(styles), init, iters, cfg, params, temporal=nt.temporal).detach())
+    monkeypatch.setattr(image_ops, "interpolate", lambda x, size=None, scale_factor=None: t(I.resize_bilinear(
+        n_(x), size=None if size is None else tuple(size), scale_factor=scale_factor)))
+    monkeypatch.setattr(image_ops, "flow_warp_grid", flow_warp_grid)
+    monkeypatch.setattr(image_ops, "grid_sample", lambda x, g: t(I.grid_sample_border(n_(x)[0], n_(g)[0]))[None])
+    monkeypatch.setattr(image_ops, "blend", lambda x, y, a, b: t(I.blend(n_(x), n_(y), a, b)))
+    monkeypatch.setattr(image_ops, "deprocess_u8", lambda x: t(I.deprocess_u8(n_(x))))
+    monkeypatch.setattr(image_ops, "preprocess", lambda img, device=None: t(I.preprocess_u8(n_(img))))
+
+    out_dir = tmp_path / "out"
+    work = out_dir / "clip_style"
+    (work / "frames").mkdir(parents=True)
+    (work / "flow").mkdir()
+    (tmp_path / "in").mkdir()
+    Image.fromarray(z["style"], mode="RGB").save(tmp_path / "in" / "style.png")
+    n = meta["n_frames"]
+    for i in range(n):
+        Image.fromarray(z[f"frame_{i}"], mode="RGB").save(work / "frames" / f"{i + 1:04d}.png")
+        for d, j in (("forward", (i + 1) % n), ("backward", (i - 1) % n)):
+            stem = work / "flow" / f"{d}_{i + 1:04d}_{j + 1:04d}"
+            raw = z[f"flow_{d}_{i}_{j}"]
+            with open(f"{stem}.flo", "wb") as f:
+                np.array([202021.25], dtype=np.float32).tofile(f)
+                np.array([raw.shape[1]], dtype=np.int32).tofile(f)
+                np.array([raw.shape[0]], dtype=np.int32).tofile(f)
+                raw.astype(np.float32).tofile(f)
+            Image.fromarray(z[f"rel_{d}_{i}_{j}"], mode="L").save(f"{stem}.png")
+    a = make_args(tmp_path / "unused.pth", tmp_path, transfer_type="vid_img", optimizer=meta["optimizer"], image_sizes=list(meta["sizes"]),
+                  num_iters=list(meta["iters"]), passes_per_scale=meta["passes"], init=meta["init"], temporal_blend=meta["temporal_blend"],
+                  loop=False, style_scale=1.0, match_histograms=False, output_dir=str(out_dir), content=str(tmp_path / "in" / "clip.mp4"),
+                  style=[str(tmp_path / "in" / "style.png")], original_colors=0)
+    store = style.vid_img(a)
+    assert len(store) == len(meta["sizes"]) * meta["passes"] * n
+    for size in meta["sizes"]:
+        for p in range(1, meta["passes"] + 1):
+            for f in range(n):
+                png = np.asarray(Image.open(work / str(size) / f"{p}_{f + 1:04d}.png").convert("RGB"))
+                assert np.array_equal(png, store[(size, p, f)].numpy())
+                ref = z[f"out_{size}_{p}_{f}"]
+                mse = float(((png.astype(np.float64) - ref.astype(np.float64)) ** 2).mean())
+                assert (99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)) > 45.0, (size, p, f)
+    a.original_colors = 1
+    with pytest.raises(NotImplementedError):
+        style.vid_img(a)
+    a.original_colors, a.content = 0, str(tmp_path / "in" / "other.mp4")
+    with pytest.raises(FileNotFoundError):
+        style.vid_img(a)

@@ -90,6 +90,43 @@ def test_vid_img_tensors_matches_reference_pngs(tmp_path, monkeypatch, precision
     assert models.cache_stats["misses"] >= 1
 
 
+def test_vid_img_file_level_entry(tmp_path):
+    """style.vid_img(args) on the device: frames / .flo / reliability PNGs in the reference's directory layout in, the reference's
+    `<size>/<pass>_<frame>.png` out, against the PNGs the unmodified reference wrote."""
+    from PIL import Image
+
+    from maua_style_b200 import style
+
+    z, meta = load_golden()
+    ckpt = tmp_path / "vgg19-random.pth"
+    save_checkpoint(ckpt)
+    work = tmp_path / "out" / "clip_style"
+    (work / "frames").mkdir(parents=True)
+    (work / "flow").mkdir()
+    Image.fromarray(z["style"], mode="RGB").save(tmp_path / "style.png")
+    n = meta["n_frames"]
+    for i in range(n):
+        Image.fromarray(z[f"frame_{i}"], mode="RGB").save(work / "frames" / f"{i + 1:04d}.png")
+        for d, j in (("forward", (i + 1) % n), ("backward", (i - 1) % n)):
+            stem = work / "flow" / f"{d}_{i + 1:04d}_{j + 1:04d}"
+            raw = z[f"flow_{d}_{i}_{j}"]
+            with open(f"{stem}.flo", "wb") as f:
+                np.array([202021.25], dtype=np.float32).tofile(f)
+                np.array([raw.shape[1]], dtype=np.int32).tofile(f)
+                np.array([raw.shape[0]], dtype=np.int32).tofile(f)
+                raw.astype(np.float32).tofile(f)
+            Image.fromarray(z[f"rel_{d}_{i}_{j}"], mode="L").save(f"{stem}.png")
+    a = make_args(ckpt, tmp_path, transfer_type="vid_img", optimizer=meta["optimizer"], content_weight=meta["content_weight"],
+                  style_weight=meta["style_weight"], tv_weight=meta["tv_weight"], temporal_weight=meta["temporal_weight"],
+                  image_sizes=list(meta["sizes"]), num_iters=list(meta["iters"]), passes_per_scale=meta["passes"], init=meta["init"],
+                  temporal_blend=meta["temporal_blend"], loop=False, style_scale=1.0, match_histograms=False, original_colors=0,
+                  output_dir=str(tmp_path / "out"), content=str(tmp_path / "clip.mp4"), style=[str(tmp_path / "style.png")])
+    store = style.vid_img(a)
+    get = lambda s, p, f: np.asarray(Image.open(work / str(s) / f"{p}_{f + 1:04d}.png").convert("RGB"))
+    assert all(np.array_equal(get(s, p, f), v.cpu().numpy()) for (s, p, f), v in store.items())
+    assert compare(z, meta, get, "style.vid_img (files) vs reference PNGs") > MIN_PSNR["tf32"]
+
+
 def test_sharded_video_with_one_rank_is_the_plain_driver(tmp_path, monkeypatch):
     """shard.stylize_video on one GPU owns every frame and exchanges with nobody: bit-identical to style.vid_img_tensors.  (Two
     ranks: tests/test_shard.py on gloo, against the oracle's chunked restatement.)"""
