@@ -62,6 +62,12 @@ def _worker(rank, world, port, q):
     local = shard.run_sharded(jobs, lambda i, j: (j, rank), info)
     merged = shard.run_sharded(jobs, lambda i, j: (j, rank), info, gather=True)
     frames = shard.run_sharded(list(range(9)), lambda i, j: rank, info, contiguous=True, gather=True)
+    # the per-pass frame exchange of a sharded video with ragged chunks: rank 0 produced three frames, rank 1 none
+    fresh = {(16, 1, f): torch.full((4, 5, 3), 10 * f + 1, dtype=torch.uint8) for f in ([0, 1, 2] if rank == 0 else [])}
+    merged_frames = shard.exchange_frames(fresh, info)
+    assert sorted(merged_frames) == [(16, 1, 0), (16, 1, 1), (16, 1, 2)]
+    assert all(int(v[0, 0, 0]) == 10 * k[2] + 1 and v.shape == (4, 5, 3) for k, v in merged_frames.items())
+    assert shard.exchange_frames({}, info) == {}  # a pass in which nobody produced anything
     shard.barrier()
     slowest = shard.max_over_ranks(1.0 + rank)
     total = shard.sum_over_ranks(len(local))
