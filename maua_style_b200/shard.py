@@ -10,7 +10,8 @@ the natural partition over an 8 x B200 box is
               the previous pass / scale exactly like the reference's resume path does (style.py:232-271).
 
 Weights (52 MB) are replicated and the style targets (<= 2.4 MB) are recomputed per rank (1 forward), so independent images
-exchange nothing.  A video in frame chunks (`stylize_video`) has one exchange step per pass: the 8-bit frames every rank
+exchange nothing, and neither do video-frame chunks styled as clips of their own (`stylize_video_chunks`).  A video whose chunk
+seams stay temporally coupled (`stylize_video`) has one exchange step per pass: the 8-bit frames every rank
 produced are all-gathered (`exchange_frames`), because chunk heads start from their predecessor's previous-pass result.
 Otherwise torch.distributed is only used for the control plane: the rendezvous, a barrier around timed regions
 and the max-over-ranks of the elapsed time (bench.py).  Works with the `gloo` backend on CPU (tests) and `nccl` on GPUs.
@@ -233,3 +234,27 @@ def stylize_video(frames: Sequence, styles: Sequence, args, flows: Callable, inf
     owned = partition_contiguous(len(frames), info.world, info.rank)
     return style.vid_img_tensors(frames, styles, a, flows, on_frame=on_frame, owned=owned,
                                  exchange=lambda fresh: exchange_frames(fresh, info))
+
+
+def stylize_video_chunks(frames: Sequence, styles: Sequence, args, flows: Callable, info: Optional[RankInfo] = None,
+                         on_frame: Optional[Callable] = None) -> dict:
+    """BASELINE.json config 5 as it is worded -- "video-frame chunks ... one per GPU, with no collective": the clip is cut into
+    contiguous chunks and every rank styles ITS chunk as a clip of its own (style.vid_img_tensors on the sub-list: the pair that
+    closes a pass goes from the chunk's last frame back to its first, style.py:195-197), so no frame ever crosses a GPU boundary
+    and nothing is exchanged.  `flows(direction, i, j)` is called with indices into `frames` and must also know the closing pair
+    of every chunk.  Returns this rank's frames only: {(size, pass, frame index in `frames`): uint8 [H,W,3]}.  Chunk seams are
+    not temporally coupled; `stylize_video` is the coupled variant (one all-gather of 8-bit frames per pass)."""
+    import copy
+
+    from . import style
+
+    info = info or RankInfo.from_env()
+    a = copy.copy(args)
+    a.gpu = str(info.local_rank)
+    idx = partition_contiguous(len(frames), info.world, info.rank)
+    if len(idx) < 2:
+        raise ValueError(f"rank {info.rank} would get {len(idx)} frame(s): a chunk needs at least two")
+    sub = [frames[i] for i in idx]
+    cb = None if on_frame is None else (lambda size, p, f, u8: on_frame(size, p, idx[f], u8))
+    store = style.vid_img_tensors(sub, styles, a, lambda d, i, j: flows(d, idx[i], idx[j]), on_frame=cb)
+    return {(size, p, idx[f]): v for (size, p, f), v in store.items()}

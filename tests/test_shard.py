@@ -168,7 +168,18 @@ def _video_worker(rank, world, port, q, tmpdir):
     seen = []
     store = shard.stylize_video([t(I.preprocess_u8(f)) for f in frames], [t(I.preprocess_u8(style_rgb))], a, get, info,
                                 on_frame=lambda s, p, f, u8: seen.append(f))
-    q.put((rank, sorted(set(seen)), {k: v.numpy() for k, v in store.items()}))
+    # the uncoupled variant (no collective): every rank styles its chunk as a clip of its own
+    chunk_flows = dict(flows)
+    for r in range(world):
+        idx = shard.partition_contiguous(VID["n"], world, r)
+        chunk_flows[("forward", idx[-1], idx[0])] = flows[("forward", idx[-1], (idx[-1] + 1) % VID["n"])]   # the pair that closes a pass
+        chunk_flows[("backward", idx[0], idx[-1])] = flows[("backward", idx[0], (idx[0] - 1) % VID["n"])]
+    get2 = lambda d, i, j: (t(chunk_flows[(d, i, j)][0]), t(chunk_flows[(d, i, j)][1].astype(np.float32) / np.float32(255))[None, None])
+    a2 = make_args(Path(tmpdir) / "unused.pth", Path(tmpdir) / f"r{rank}", transfer_type="vid_img", image_sizes=VID["sizes"],
+                   num_iters=VID["iters"], passes_per_scale=VID["passes"], init="prev_warp", temporal_blend=0.5, loop=False,
+                   style_scale=1.0, match_histograms=False)
+    own = shard.stylize_video_chunks([t(I.preprocess_u8(f)) for f in frames], [t(I.preprocess_u8(style_rgb))], a2, get2, info)
+    q.put((rank, sorted(set(seen)), {k: v.numpy() for k, v in store.items()}, {k: v.numpy() for k, v in own.items()}))
     dist.destroy_process_group()
 
 
@@ -202,7 +213,7 @@ def test_world_size_2_gloo_sharded_video(tmp_path):
                       lambda content, styles, pastiche, iters, temporal: _stand_in_optimize(content, pastiche, temporal),
                       lambda d, i, j: flows[(d, i, j)], init="prev_warp", temporal_blend=0.5)
     assert len(want) == len(VID["sizes"]) * VID["passes"] * VID["n"]
-    for rank, _, store in results:
+    for rank, _, store, _own in results:
         assert sorted(store) == sorted(want)  # after the last exchange every rank holds the whole job
         for k in want:
             assert np.array_equal(store[k], want[k]), (rank, k)
@@ -210,3 +221,13 @@ def test_world_size_2_gloo_sharded_video(tmp_path):
     assert any(not np.array_equal(want[k], plain[k]) for k in want)
     # ... but a frame that never follows a chunk boundary in the first pass of the first scale is
     assert np.array_equal(want[(VID["sizes"][0], 1, 1)], plain[(VID["sizes"][0], 1, 1)])
+    # stylize_video_chunks: every rank's result is the oracle's driver run on that chunk as a clip of its own
+    for rank, _, _store, own in results:
+        idx = chunks[rank]
+        chunk_flows = lambda d, i, j: flows[(d, idx[i], (idx[i] + (1 if d == "forward" else -1)) % VID["n"])]
+        alone = I.vid_img([frames[i] for i in idx], [I.preprocess_u8(style_rgb)], VID["sizes"], VID["iters"], VID["passes"],
+                          lambda content, styles, pastiche, iters, temporal: _stand_in_optimize(content, pastiche, temporal),
+                          chunk_flows, init="prev_warp", temporal_blend=0.5)
+        assert sorted(own) == sorted((s, p, idx[f]) for (s, p, f) in alone)
+        for (s, p, f), v in alone.items():
+            assert np.array_equal(own[(s, p, idx[f])], v), (rank, s, p, f)
