@@ -116,3 +116,46 @@ def test_adam_loss_trajectory_is_insensitive_to_tf32_rounding():
     for a, b in zip(*curves):
         assert abs(b / a - 1) < 1e-2
     assert curves[0][-1] < 0.7 * curves[0][0]
+
+
+def test_expected_deviation_of_the_video_driver():
+    """The vid_img driver chains 12 short optimisations (2 scales x 2 passes x 3 frames), every frame starting from earlier
+    results, so TF32 rounding accumulates along the chain.  With the CUDA path's operand roundings inserted on the CPU, the oracle's
+    driver lands where the B200 measured the device driver (46.3 dB worst frame, profiles/r05_vid_driver.txt): the bound of
+    tests/test_vid_driver_gpu.py (40 dB) is rounding, not a driver difference -- in exact arithmetic the same driver gives 52.7 dB."""
+    import json
+
+    import numpy as np
+
+    from helpers import GOLDEN
+    from oracle import image_oracle as I
+
+    z = np.load(GOLDEN / "vid_img_3f_48_80.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        temporal_weight=meta["temporal_weight"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+    def optimize_fn(content, styles, pastiche, iters, temporal):  # O.optimize with the emulated network
+        net = TF32Net(params, cfg)
+        O.set_content_targets(net, t(content))
+        if temporal is not None:
+            O.set_temporal_targets(net, t(temporal[0]), t(temporal[1]))
+        O.set_style_targets(net, [t(s) for s in styles], cfg.blend(len(styles)))
+        for m in net.losses:
+            m.mode = "loss"
+        return O.adam_optimize(t(pastiche).clone(), lambda p: O.feval(net, p)[2], iters + 1, lr=cfg.learning_rate).detach().numpy()
+
+    frames = [z[f"frame_{i}"] for i in range(meta["n_frames"])]
+    store = I.vid_img(frames, [I.preprocess_u8(z["style"])], meta["sizes"], meta["iters"], meta["passes"], optimize_fn,
+                      lambda d, a, b: (z[f"flow_{d}_{a}_{b}"], z[f"rel_{d}_{a}_{b}"]), init=meta["init"],
+                      temporal_blend=meta["temporal_blend"])
+    worst = 99.0
+    for (size, p, f), got in store.items():
+        ref = z[f"out_{size}_{p}_{f}"]
+        mse = float(((got.astype(np.float64) - ref.astype(np.float64)) ** 2).mean())
+        worst = min(worst, 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse))
+    print(f"vid_img driver under TF32 emulation: worst frame {worst:.1f} dB (B200: 46.3 dB)")
+    assert 43.0 < worst < 50.0, worst  # emulated: 46.1 dB
