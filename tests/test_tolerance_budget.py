@@ -159,3 +159,31 @@ def test_expected_deviation_of_the_video_driver():
         worst = min(worst, 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse))
     print(f"vid_img driver under TF32 emulation: worst frame {worst:.1f} dB (B200: 46.3 dB)")
     assert 43.0 < worst < 50.0, worst  # emulated: 46.1 dB
+
+
+def test_expected_deviation_of_the_frame_window_driver(monkeypatch):
+    """The img_vid driver (2 scales, 4 + 6 windows of 3 / 2 frames) with the CUDA path's operand roundings inserted on the CPU:
+    56.8 / 51.0 dB at 32 / 48 px -- the B200 measured 56.6 / 51.0 dB (profiles/r05_vid_driver.txt); exact arithmetic: 168.6 / 94.4 dB."""
+    import json
+
+    import numpy as np
+
+    from helpers import GOLDEN
+    from oracle import image_oracle as I
+
+    z = np.load(GOLDEN / "img_vid_9f_32_48.npz", allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    params = O.he_init_vgg19(0)
+    cfg = O.StyleConfig(content_weight=meta["content_weight"], style_weight=meta["style_weight"], tv_weight=meta["tv_weight"],
+                        video_style_factor=meta["video_style_factor"], optimizer=meta["optimizer"])
+    torch.set_flush_denormal(True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    monkeypatch.setattr(O, "OracleNet", TF32Net)  # optimize_windows builds its network through this name
+    outs = I.img_vid(I.preprocess_u8(z["content"]), [z["style_clip"]], z["init_video"], meta["sizes"], meta["iters"],
+                     [int(w) for w in meta["windows"].split(",")],
+                     lambda c, s, p, it, gfw: O.optimize_windows(t(c), [t(x) for x in s], t(p), it, cfg, params, gfw=gfw).detach().numpy(),
+                     temporal_blend=meta["temporal_blend"])
+    for (size, lo, hi), out in zip(((32, 52.0, 62.0), (48, 47.0, 56.0)), outs):
+        p = O.psnr(t(out), t(z[f"out_{size}"]))
+        print(f"img_vid driver under TF32 emulation, {size}px: {p:.1f} dB")
+        assert lo < p < hi, (size, p)
