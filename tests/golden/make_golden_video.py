@@ -15,6 +15,9 @@ CuPy networks) -- the frames, `.flo` fields and reliability maps they would have
 synthetic data -- and the ffmpeg encode of each finished scale into an .mp4 (style.py:302-304), which is a no-op here.  Everything else (frame ordering, pass reversal, which PNG initialises / blends which frame, warp,
 temporal targets, per-frame `optim.optimize`, PNG quantisation between passes) is the reference's own code.
 
+  vid_img_loop_3f_48_80.npz  the same clip with --loop (style.py:181-183, :195-197): the frame list is rotated at a random start
+                           every pass (python's global RNG, seeded with 7 here) and the first frames are styled a second
+                           time from the frames the pass has just written (the `n > len(frames)` branches of :229-271).
   img_vid_9f_32_48.npz ... the UNMODIFIED reference `style.img_vid` (style.py:76-142): one 40x48 content image, one style
                            clip of 9 frames, two scales (32 px, 48 px) with frame windows of 3 and 2 frames, init=content
                            (content + seeded noise, blurred over time and space on the host), the 7-frame roll of pastiche
@@ -142,6 +145,18 @@ def main():
         make_img_vid(rconfig, rmodels, rload, rstyle)
     if "--only-img-vid" in sys.argv:
         return
+    if "--only-loop" not in sys.argv:
+        make_vid_img(rconfig, rmodels, rload, rstyle, loop=False, fname="vid_img_3f_48_80.npz", iters=ITERS)
+    # --loop: random rotation of the frame list per pass (python's `random`, seeded here) + the first frames styled twice
+    make_vid_img(rconfig, rmodels, rload, rstyle, loop=True, fname="vid_img_loop_3f_48_80.npz", iters=[4, 4])
+
+
+def make_vid_img(rconfig, rmodels, rload, rstyle, loop, fname, iters):
+    import random
+
+    from PIL import Image
+
+    ITERS = iters
     H, W = FRAME_HW
     with tempfile.TemporaryDirectory(prefix="maua_golden_vid_") as tmp:
         workdir = Path(tmp)
@@ -152,7 +167,7 @@ def main():
         Image.fromarray(style_rgb, mode="RGB").save(workdir / "in" / "style.png")
         args = reference_args(rconfig, workdir, ckpt, optimizer="adam", image_sizes=",".join(map(str, SIZES)),
                               num_iters=",".join(map(str, ITERS)), init="prev_warp", transfer_type="vid_img",
-                              temporal_weight=50.0, passes_per_scale=PASSES, loop=False, temporal_blend=0.5)
+                              temporal_weight=50.0, passes_per_scale=PASSES, loop=loop, temporal_blend=0.5)
         args.content = str(workdir / "in" / "clip.mp4")
         args.style = [str(workdir / "in" / "style.png")]
         args.match_histograms = False
@@ -186,6 +201,7 @@ def main():
                 out[f"rel_{direction}_{i}_{j}"] = rel
         rload.process_content_video = lambda model, a: list(frames)  # ffmpeg + flow estimation: out of scope
         torch.manual_seed(0)
+        random.seed(7)  # style.py:182 draws the rotation of a --loop pass from python's global RNG
         torch.set_flush_denormal(True)
         cwd = os.getcwd()
         os.chdir(workdir)
@@ -199,10 +215,10 @@ def main():
                     f = work / str(s) / f"{p}_{i + 1:04d}.png"
                     out[f"out_{s}_{p}_{i}"] = np.asarray(Image.open(f).convert("RGB"))
         out["meta"] = json.dumps(dict(sizes=SIZES, iters=ITERS, passes=PASSES, n_frames=N_FRAMES, init="prev_warp", optimizer="adam",
-                                      temporal_blend=0.5, temporal_weight=50.0, content_weight=args.content_weight,
+                                      loop=loop, random_seed=7, temporal_blend=0.5, temporal_weight=50.0, content_weight=args.content_weight,
                                       style_weight=args.style_weight, tv_weight=args.tv_weight))
-        np.savez_compressed(HERE / "vid_img_3f_48_80.npz", **out)
-        print("vid_img_3f_48_80.npz:", {k: getattr(v, "shape", None) for k, v in out.items() if not isinstance(v, str)})
+        np.savez_compressed(HERE / fname, **out)
+        print(fname + ":", {k: getattr(v, "shape", None) for k, v in out.items() if not isinstance(v, str)})
 
 
 if __name__ == "__main__":
