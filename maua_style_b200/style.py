@@ -133,7 +133,7 @@ def stylize_frame(net, losses, content_frame: torch.Tensor, style_images: Sequen
 
 
 def vid_img_pairs(order: Sequence[int], loop: bool = False):
-    """style.py:195-197: the (previous frame, this frame) pairs of one pass over the frame list `order`.  Without --loop every
+    """style.py:192-194: the (previous frame, this frame) pairs of one pass over the frame list `order`.  Without --loop every
     frame is `this frame` once and the first frame comes last (it follows the last one); with --loop the first frames are
     styled a second time so that the end of the clip meets its start."""
     order = list(order)
@@ -146,28 +146,28 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
                     owned: Optional[Sequence[int]] = None,
                     exchange: Optional[Callable[[dict], dict]] = None) -> dict:
     """style.py:145-300 on tensors: every scale x `args.passes_per_scale` passes (forward, then backward over the reversed
-    frame list, :299-300) x every frame, with everything between the decoded frames and the encoded results on the device.
+    frame list, :300) x every frame, with everything between the decoded frames and the encoded results on the device.
 
     frames ...... the decoded clip, [1,3,H,W] preprocessed images (load.preprocess layout; host or device)
     styles_big .. the style images, same layout
     flows ....... `flows(direction, prev_index, this_index) -> (flow, reliable)`: what the reference reads from
-                  `<work_dir>/flow/<direction>_<prev>_<this>.flo` / `.png` (:222, :274, :278) -- the flow field [h,w,2] after
+                  `<work_dir>/flow/<direction>_<prev>_<this>.flo` / `.png` (:226-227, :273-274, :278-279) -- the flow field [h,w,2] after
                   the host-side normalisation + blur of load.py:201-206 (`read_flo`), and the flow-reliability map [1,1,h,w]
                   in [0,1] (load.py:217-218).  Estimating the flow is not part of this path: the fields are inputs.
     on_frame .... called as on_frame(size, pass (1-based), frame index, uint8 [H,W,3] RGB device tensor) for every result,
-                  e.g. to encode `<size>/<pass>_<frame>.png` (:185, :295-297)
+                  e.g. to encode `<size>/<pass>_<frame>.png` (:197, :294-297)
 
-    The reference hands results from one pass / scale to the next through those PNG files (:229-271); here they are the
+    The reference hands results from one pass / scale to the next through those PNG files (:232-271); here they are the
     returned dict {(size, pass, frame index): uint8 image in HBM} and never leave the device, but they keep the 8-bit
     quantisation the files impose, so the frames equal the reference's.  Within a pass the previous frame's fp32 result is
-    carried over directly (:294).  Reads args.image_sizes, num_iters, passes_per_scale, init ("random" | "prev_warp" | else
+    carried over directly (:292).  Reads args.image_sizes, num_iters, passes_per_scale, init ("random" | "prev_warp" | else
     the content frame), temporal_blend, loop, style_scale, match_histograms and everything `optim.optimize` reads; calls
     `optim.set_model_args(args, size)` per scale like the reference does (:176), i.e. it updates `args` in place.
 
     Sharding over GPUs (shard.stylize_video): `owned` = the frame indices this process styles (default: all), `exchange` =
     called after every pass with the frames this process produced in it, returns the frames of all processes.  A frame that
     another process styles breaks the chain of carried-over results exactly like a frame whose PNG already exists does in the
-    reference's resume path (:186-188): the next owned frame starts from the stored result of its predecessor (:229-271)."""
+    reference's resume path (:198-200): the next owned frame starts from the stored result of its predecessor (:232-271)."""
     import random
 
     dev = _device(args)
@@ -188,7 +188,7 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
         frames = [f.to(dev, torch.float32).contiguous() for f in frames]
         styles_big = [s.to(dev, torch.float32).contiguous() for s in styles_big]
         H, W = (int(v) for v in frames[0].shape[-2:])
-        moments = torch.stack([image_ops.image_moments(styles_big[0])]) if hist else None  # :209, :294: the first style image
+        moments = torch.stack([image_ops.image_moments(styles_big[0])]) if hist else None  # :212-214, :292: the first style image
 
         def matched(img):
             return image_ops.match_histogram(img, None, mode=hist, source_moments=moments) if hist else img
@@ -200,7 +200,7 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
         prev_size = None
         for size_n, (current_size, num_iters) in enumerate(zip(args.image_sizes, args.num_iters)):
             content_scale = current_size / max(H, W)
-            # scale style images (:165-172; the area comes from the un-rounded scale factor, unlike img_img)
+            # scale style images (:167-174; the area comes from the un-rounded scale factor, unlike img_img)
             content_area = content_scale ** 2 * H * W
             style_images = []
             for img in styles_big:
@@ -210,17 +210,17 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
             net, losses = models.load_model(args)
             for pass_n in range(passes):
                 pastiche = None
-                if loop:  # :181-183
+                if loop:  # :183-185
                     start = random.randrange(0, n - 1)
                     order = order[start:] + order[:start]
-                direction = "forward" if pass_n % 2 == 0 else "backward"  # :213
+                direction = "forward" if pass_n % 2 == 0 else "backward"  # :215
                 fresh = {}
                 for k, (prev_f, this_f) in enumerate(vid_img_pairs(order, loop)):
                     if mine is not None and this_f not in mine:
                         pastiche = None  # someone else's frame: the chain of carried-over results ends here
                         continue
                     content_frame = matched(image_ops.interpolate(frames[this_f], scale_factor=content_scale))
-                    if size_n == 0 and pass_n == 0:  # :215-226
+                    if size_n == 0 and pass_n == 0:  # :220-230
                         if init == "random":
                             pastiche = torch.randn(content_frame.size()).mul(0.001).to(dev)
                         elif init == "prev_warp":
@@ -230,10 +230,10 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
                             pastiche = image_ops.grid_sample(pastiche, image_ops.flow_warp_grid(flow, tuple(pastiche.shape[2:])))
                         else:
                             pastiche = content_frame.clone()
-                    else:  # :227-290
-                        if pass_n == 0:  # the last pass of the previous scale (:229-255) ...
+                    else:  # :231-286
+                        if pass_n == 0:  # the last pass of the previous scale (:232-254) ...
                             src = (prev_size, passes) if k <= n else (current_size, pass_n + 1)
-                        else:            # ... or the previous pass of this scale (:256-271)
+                        else:            # ... or the previous pass of this scale (:255-271)
                             src = (current_size, pass_n) if k <= n else (current_size, pass_n + 1)
                         hw = tuple(content_frame.shape[2:])
                         if pastiche is None:
@@ -249,14 +249,14 @@ def vid_img_tensors(frames: Sequence[torch.Tensor], styles_big: Sequence[torch.T
                         optim.set_temporal_targets(net, warp_image, warp_weights=reliable, args=args)     # :284
                         pastiche = image_ops.blend(blend_image, pastiche, 1.0 - tb, tb)                    # :286
                     out = optim.optimize_device(content_frame, style_images, pastiche, num_iters // passes, args, net, losses)
-                    pastiche = matched(out)  # :294
+                    pastiche = matched(out)  # :292
                     u8 = image_ops.deprocess_u8(pastiche)
                     store[(current_size, pass_n + 1, this_f)] = fresh[(current_size, pass_n + 1, this_f)] = u8
                     if on_frame is not None:
                         on_frame(current_size, pass_n + 1, this_f, u8)
                 if exchange is not None:
-                    store.update(exchange(fresh))  # the next pass / scale reads its neighbours' frames (:229-271)
-                order = list(reversed(order))  # :299-300
+                    store.update(exchange(fresh))  # the next pass / scale reads its neighbours' frames (:232-271)
+                order = list(reversed(order))  # :300
             prev_size = current_size
     return store
 
@@ -276,7 +276,7 @@ def temporal_blur(video: torch.Tensor, sigma: float) -> torch.Tensor:
 
 
 def initial_video(content_big: torch.Tensor, video_length: int, init: str = "content") -> torch.Tensor:
-    """style.py:92-103: the initial pastiche video of img_vid for init "random" / "content" -- seeded noise (torch's global RNG,
+    """style.py:93-103: the initial pastiche video of img_vid for init "random" / "content" -- seeded noise (torch's global RNG,
     like the reference) blurred over time and space with scipy on the host, once per job.  Returns a host tensor [T,3,H,W]."""
     import scipy.ndimage as ndi
 
@@ -300,10 +300,10 @@ def img_vid_tensors(content_big: torch.Tensor, style_videos_big: Sequence[torch.
     The video stays in HBM across scales.
 
     content_big: [1,3,H,W]; style_videos_big: clips [T_i,3,h,w] (load.preprocess layout); `init_video`: the initial pastiche
-    (default: `initial_video(content_big, T, args.init)`, :92-103; a shorter clip is repeated like :101-102).  Reads
+    (default: `initial_video(content_big, T, args.init)`, :93-103; a shorter clip is repeated like :102-103).  Reads
     args.image_sizes, num_iters, gram_frame_window (one window length per scale: "18,9,7", a list, or one int), num_frames
     (-1: the longest style clip), temporal_blend, style_scale and everything `optim.optimize` reads; like the reference it
-    sets `args.gram_frame_window` to the current scale's value.  Histogram matching against style *videos* (:82, :104, :139)
+    sets `args.gram_frame_window` to the current scale's value.  Histogram matching against style *videos* (:82, :104, :139, :142)
     is refused: on torch >= 2 the reference's own call is a no-op and the device version
     handles single images."""
     if getattr(args, "match_histograms", False):
@@ -319,7 +319,7 @@ def img_vid_tensors(content_big: torch.Tensor, style_videos_big: Sequence[torch.
     if init_video is None:
         init_video = initial_video(content_big, video_length, getattr(args, "init", "content"))
     elif init_video.shape[0] != video_length:
-        init_video = init_video.repeat([video_length, 1, 1, 1])  # :101-102
+        init_video = init_video.repeat([video_length, 1, 1, 1])  # :102-103
     with torch.cuda.device(dev):
         content_big = content_big.to(dev, torch.float32).contiguous()
         clips = [v.to(dev, torch.float32).contiguous() for v in style_videos_big]
@@ -327,16 +327,16 @@ def img_vid_tensors(content_big: torch.Tensor, style_videos_big: Sequence[torch.
         H, W = (int(v) for v in content_big.shape[-2:])
         outs = []
         for i, (current_size, num_iters) in enumerate(zip(args.image_sizes, args.num_iters)):
-            args.gram_frame_window = delta_ts[i]  # :112
-            content_image = image_ops.interpolate(content_big, scale_factor=current_size / max(H, W))  # :115-117
+            args.gram_frame_window = delta_ts[i]  # :111
+            content_image = image_ops.interpolate(content_big, scale_factor=current_size / max(H, W))  # :114-116
             content_area = content_image.shape[2] * content_image.shape[3]
             style_videos = []
-            for vid in clips:  # :120-126
+            for vid in clips:  # :119-125
                 style_scale = math.sqrt(content_area / (vid.size(3) * vid.size(2))) * getattr(args, "style_scale", 1.0)
                 style_videos.append(image_ops.interpolate(vid, scale_factor=style_scale))
-            pastiche = image_ops.interpolate(pastiche, size=tuple(content_image.shape[2:]))  # :129-131
-            pastiche = optim.optimize_device(content_image, style_videos, pastiche, num_iters, args)  # :133
-            pastiche = torch.cat((pastiche[7:], pastiche[:7]))  # :135-136
+            pastiche = image_ops.interpolate(pastiche, size=tuple(content_image.shape[2:]))  # :128-130
+            pastiche = optim.optimize_device(content_image, style_videos, pastiche, num_iters, args)  # :132
+            pastiche = torch.cat((pastiche[7:], pastiche[:7]))  # :134-135
             clips = [torch.cat((c[7:], c[:7])) for c in clips]
             if tb > 0:
                 pastiche = temporal_blur(pastiche, tb)
@@ -420,7 +420,7 @@ def vid_img(args, frames: Optional[Sequence[str]] = None) -> dict:
     """style.py:145-300 at file level, on the files the reference's own preparation stage leaves in
     `<output_dir>/<content>_<styles>/` (load.process_content_video, load.py:141-188: ffmpeg frame extraction + optical flow, both
     outside this path): `frames/*.png`, `flow/<direction>_<prev>_<this>.flo` and `.png`.  Decodes them, runs `vid_img_tensors` with
-    the clip resident in HBM and writes `<size>/<pass>_<frame>.png` like the reference (:185, :295-297).  `frames`: the frame files
+    the clip resident in HBM and writes `<size>/<pass>_<frame>.png` like the reference (:197, :294-297).  `frames`: the frame files
     in clip order (default: the sorted contents of `frames/`).  Not restated: skipping frames whose PNG already exists (resume),
     `--original_colors`, the ffmpeg encode of each finished scale (:302-304)."""
     import glob

@@ -8,10 +8,10 @@ reference repo root, JCBrouwer/maua-style @ 316c552):
 
     resize_bilinear ...... F.interpolate(x, scale_factor=s | size=hw, mode="bilinear", align_corners=False)
                            style.py:38-41, :47-49, :57-66, :205-212, :241-255, :284-286; load.py:211-213
-    grid_sample_border ... F.grid_sample(x, grid, padding_mode="border")            style.py:223, :279
+    grid_sample_border ... F.grid_sample(x, grid, padding_mode="border")            style.py:228, :276
     preprocess_u8 / _f32 . load.preprocess                                          load.py:21-32
     deprocess_u8 ......... load.deprocess + T.ToPILImage                             load.py:47-52
-    blend ................ (1 - temporal_blend) * blend_image + temporal_blend * p   style.py:290
+    blend ................ (1 - temporal_blend) * blend_image + temporal_blend * p   style.py:286
     match_histogram ...... utils.match_histogram (colour-statistics transfer)       utils.py:88-151
     img_img .............. the multi-resolution driver                               style.py:22-73
     flow_warp_map ........ .flo field -> sampling grid                               load.py:191-214
@@ -249,7 +249,7 @@ def flow_warp_map(flow_raw: np.ndarray, size: Tuple[int, int]) -> np.ndarray:
 
 
 def vid_img_schedule(n_frames: int, loop: bool = False):
-    """style.py:195-197: the (previous frame, this frame) pairs of one pass over `order` (a list of frame indices).
+    """style.py:192-194: the (previous frame, this frame) pairs of one pass over `order` (a list of frame indices).
     Without --loop every frame is `this frame` exactly once, the first one last (it follows the last frame)."""
     def pairs(order):
         return list(zip(order + order[: 11 if loop else 1], order[1:] + order[: 10 if loop else 1]))
@@ -264,12 +264,12 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
 
     frames_u8: the decoded frames, uint8 [H,W,3] RGB; styles_big: preprocessed [1,3,h,w] arrays;
     flows(direction, prev_index, this_index) -> (raw .flo field [h,w,2], reliability PNG bytes uint8 [h,w]).
-    Returns {(size, pass (1-based), frame index): uint8 [h,w,3]} -- the PNGs `<size>/<pass>_<frame>.png` (style.py:185).
-    --loop (random rotation, style.py:181-183) and random init (unseeded, style.py:217) are not restated.
+    Returns {(size, pass (1-based), frame index): uint8 [h,w,3]} -- the PNGs `<size>/<pass>_<frame>.png` (style.py:197).
+    --loop (random rotation, style.py:183-185) and random init (unseeded, style.py:221-222) are not restated.
 
     `chunks` (lists of frame indices, one per GPU) restates what a job sharded over GPUs computes: whenever the owner of the
     frame changes, the chain of carried-over results breaks and the frame starts from the stored result of its predecessor in
-    the previous pass / scale -- the reference's resume rule for frames whose PNG already exists (style.py:186-188, :229-271)."""
+    the previous pass / scale -- the reference's resume rule for frames whose PNG already exists (style.py:198-200, :232-271)."""
     owner = {f: r for r, c in enumerate(chunks or []) for f in c}
     assert init in ("prev_warp", "content"), init
     n = len(frames_u8)
@@ -281,7 +281,7 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
     prev_size = None
     for size_n, (size, iters) in enumerate(zip(image_sizes, num_iters)):
         cs = size / max(H, W)
-        area = cs ** 2 * H * W  # style.py:166: from the un-rounded scale, not from the resized frame
+        area = cs ** 2 * H * W  # style.py:169: from the un-rounded scale, not from the resized frame
         styles = [resize_bilinear(s, scale_factor=math.sqrt(area / (s.shape[3] * s.shape[2])) * style_scale) for s in styles_big]
         for pass_n in range(passes_per_scale):
             pastiche = None
@@ -292,7 +292,7 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
                     pastiche, last_owner = None, owner[this_f]
                 content = [resize_bilinear(big[prev_f], scale_factor=cs), resize_bilinear(big[this_f], scale_factor=cs)]
                 temporal = None
-                if size_n == 0 and pass_n == 0:  # style.py:215-226
+                if size_n == 0 and pass_n == 0:  # style.py:220-230
                     if init == "prev_warp":
                         if pastiche is None:
                             pastiche = content[0]
@@ -301,7 +301,7 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
                         pastiche = grid_sample_border(pastiche[0], grid)[None]
                     else:
                         pastiche = content[1].copy()
-                else:  # style.py:227-290
+                else:  # style.py:231-286
                     src = (prev_size, passes_per_scale) if pass_n == 0 else (size, pass_n)
                     if pastiche is None:
                         pastiche = preprocess_u8(store[src + (prev_f,)])
@@ -319,7 +319,7 @@ def vid_img(frames_u8: Sequence[np.ndarray], styles_big: List[np.ndarray], image
                     pastiche = blend(blend_image, pastiche, 1 - temporal_blend, temporal_blend)  # the UN-warped previous result
                 pastiche = np.asarray(optimize_fn(content[1], styles, pastiche, iters // passes_per_scale, temporal), dtype=np.float32)
                 store[(size, pass_n + 1, this_f)] = deprocess_u8(pastiche)
-            order = list(reversed(order))  # style.py:299-300
+            order = list(reversed(order))  # style.py:300
         prev_size = size
     return store
 
@@ -346,7 +346,7 @@ def img_vid(content_big: np.ndarray, style_clips_big: List[np.ndarray], init_vid
             style_scale: float = 1.0, roll: int = 7):
     """Drives `optimize_fn(content, style_clips, pastiche_video, num_iters, gram_frame_window) -> pastiche_video` over the
     scales like style.img_vid: resize content / style clips / pastiche (:114-130), optimise (:132), roll pastiche and style
-    clips by 7 frames (:134-135), blur over time (:137-138).  `init_video` is the initial pastiche of :92-103 (its noise is
+    clips by 7 frames (:134-135), blur over time (:137-138).  `init_video` is the initial pastiche of :93-103 (its noise is
     drawn from the global RNG and blurred on the host; the golden stores it).  Returns the per-scale videos [T,3,h,w]."""
     H, W = content_big.shape[-2:]
     pastiche = np.asarray(init_video, dtype=np.float32)
