@@ -3,10 +3,10 @@ wrappers over the C ABI (include/maua_b200.h, csrc/image_ops.cu).  Same call sha
 reference uses, so `style.py`-like drivers read the same:
 
     interpolate(x, scale_factor=s | size=(h, w))   F.interpolate(..., mode="bilinear", align_corners=False)
-                                                   reference style.py:38-41, :47-49, :57-66, :205-212, :241-255, :284-286
-    grid_sample(x, grid)                           F.grid_sample(x, grid, padding_mode="border")   style.py:223, :279
+                                                   reference style.py:38-41, :47-49, :57-66, :203-210, :242-254, :280-282
+    grid_sample(x, grid)                           F.grid_sample(x, grid, padding_mode="border")   style.py:228, :276
     preprocess(img) / deprocess_u8(t)              load.py:21-32 / :47-52
-    blend(x, y, a, b)                              style.py:290
+    blend(x, y, a, b)                              style.py:286
     match_histogram(target, sources, eps, mode)    utils.match_histogram   utils.py:88-151 (style.py:24, :67, :71)
 
 Everything runs on the tensor's CUDA device on the current stream; there is no CPU path.
@@ -132,7 +132,7 @@ def deprocess(t: torch.Tensor):
 
 
 def blend(x: torch.Tensor, y: torch.Tensor, a: float, b: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a * x + b * y (style.py:290 with a = 1 - temporal_blend, b = temporal_blend)."""
+    """a * x + b * y (style.py:286 with a = 1 - temporal_blend, b = temporal_blend)."""
     x = _dev_f32(x)
     y = _dev_f32(y, x.device)
     if x.shape != y.shape:

@@ -2,7 +2,7 @@
 
 The reference has no distributed backend at all: `style.py` optimises one content image
 (img_img, style.py:22-73) or walks the frames of a video one by one (vid_img, style.py:176-290).  Every content image
-is an independent optimisation, and within a video pass frame n only needs frame n-1's output (style.py:276-286), so
+is an independent optimisation, and within a video pass frame n only needs frame n-1's output (style.py:273-286), so
 the natural partition over an 8 x B200 box is
 
   * images  : round-robin  (job i -> rank i % world), or

@@ -104,11 +104,11 @@ def img_img_tensors(content_big: torch.Tensor, styles_big: Sequence[torch.Tensor
 def stylize_frame(net, losses, content_frame: torch.Tensor, style_images: Sequence[torch.Tensor], args, num_iters: int,
                   prev_pastiche: Optional[torch.Tensor] = None, flow_grid: Optional[torch.Tensor] = None,
                   reliable_flow: Optional[torch.Tensor] = None, blend_image: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """One frame of vid_img (style.py:276-296) on the device: warp the previous frame's pastiche along the flow
-    (`F.grid_sample(..., padding_mode="border")`, :279), resize the flow-reliability map (:283-286), capture the temporal
-    target (:288), blend the initialisation (:290) and optimise (:292-294).  `net, losses` come from `models.load_model`
+    """One frame of vid_img (style.py:273-297) on the device: warp the previous frame's pastiche along the flow
+    (`F.grid_sample(..., padding_mode="border")`, :276), resize the flow-reliability map (:278-282), capture the temporal
+    target (:284), blend the initialisation (:286) and optimise (:288-290).  `net, losses` come from `models.load_model`
     once per scale (:176-177); the style targets are captured for the first frame only (optim.set_style_targets cache).
-    Without `prev_pastiche` the frame starts from the content frame (style.py:225-226)."""
+    Without `prev_pastiche` the frame starts from the content frame (style.py:229-230)."""
     dev = net.device
     with torch.cuda.device(dev):
         content_frame = content_frame.to(dev, torch.float32).contiguous()
@@ -117,7 +117,7 @@ def stylize_frame(net, losses, content_frame: torch.Tensor, style_images: Sequen
         else:
             pastiche = prev_pastiche.to(dev, torch.float32).contiguous()
             if tuple(pastiche.shape[2:]) != tuple(content_frame.shape[2:]):
-                pastiche = image_ops.interpolate(pastiche, size=tuple(content_frame.shape[2:]))  # style.py:241-243
+                pastiche = image_ops.interpolate(pastiche, size=tuple(content_frame.shape[2:]))  # style.py:242-244
             if flow_grid is not None:
                 warp_image = image_ops.grid_sample(pastiche, flow_grid.to(dev))
                 if reliable_flow is not None:
@@ -127,7 +127,7 @@ def stylize_frame(net, losses, content_frame: torch.Tensor, style_images: Sequen
                 tb = float(getattr(args, "temporal_blend", 0.5))
                 blend_image = blend_image.to(dev, torch.float32).contiguous()
                 if tuple(blend_image.shape[2:]) != tuple(pastiche.shape[2:]):
-                    blend_image = image_ops.interpolate(blend_image, size=tuple(pastiche.shape[2:]))  # style.py:253-255
+                    blend_image = image_ops.interpolate(blend_image, size=tuple(pastiche.shape[2:]))  # style.py:252-254
                 pastiche = image_ops.blend(blend_image, pastiche, 1.0 - tb, tb)
         return optim.optimize_device(content_frame, style_images, pastiche, num_iters, args, net, losses)
 

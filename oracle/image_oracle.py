@@ -7,7 +7,7 @@ Plain numpy fp32 restatements, operation by operation, of what the reference cal
 reference repo root, JCBrouwer/maua-style @ 316c552):
 
     resize_bilinear ...... F.interpolate(x, scale_factor=s | size=hw, mode="bilinear", align_corners=False)
-                           style.py:38-41, :47-49, :57-66, :205-212, :241-255, :284-286; load.py:211-213
+                           style.py:38-41, :47-49, :57-66, :203-210, :242-254, :280-282; load.py:211-213
     grid_sample_border ... F.grid_sample(x, grid, padding_mode="border")            style.py:228, :276
     preprocess_u8 / _f32 . load.preprocess                                          load.py:21-32
     deprocess_u8 ......... load.deprocess + T.ToPILImage                             load.py:47-52
